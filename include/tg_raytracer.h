@@ -1,0 +1,184 @@
+/*
+ * tg_raytracer.h -- the drop-in boundary of libtgb200.so.
+ *
+ * Every `tg_*` entry point below keeps the name, argument order and meaning of the reference's
+ * raytracer API (/root/reference/tg/src/graphics/vulkan/tgvk_raytracer.h:240-251 and
+ * graphics/tg_sparse_voxel_octree.h:51-53); what sits behind them is hand-written sm_100a CUDA
+ * instead of Vulkan passes. `tgb200_*` / `*_ex` / `*_from_data` names are documented EXTENSIONS the
+ * reference lacks but BASELINE.json's configs need (last row).
+ *
+ * Error convention (tg_common.h:33,42, tgvk_common.h:25-37): the reference returns void / b32 and
+ * asserts in debug. We keep the signatures; a failed CUDA/NCCL call or violated precondition is
+ * recorded and readable through tgb200_last_error() (NULL == no error). There is NO CPU fallback:
+ * without a CUDA device tg_raytracer_create() fails loudly (error string set, p_device == NULL,
+ * every later call on that raytracer is a recorded error).
+ *
+ * Threading: single-threaded like the reference (memory/tg_memory.c:270,302).
+ */
+#ifndef TG_RAYTRACER_H
+#define TG_RAYTRACER_H
+
+#include "tg_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_EXPORT __attribute__((visibility("default")))
+
+struct tgb_device; /* opaque: device buffers, streams, events */
+
+/*
+ * Replaces the reference's `tg_raytracer` (tgvk_raytracer.h:110-236): the Vulkan members are
+ * gone, `p_camera` and `scene` keep their names because the application reads them directly
+ * (tg_application.c:228 reads scene.p_cluster_idx_to_object_idx).
+ */
+typedef struct tg_raytracer
+{
+    const tg_camera*   p_camera;  /* BORROWED for the raytracer's lifetime, re-read every render() (tgvk_raytracer.c:674,1153) */
+    tg_scene           scene;     /* owned; CPU mirror exactly as in the reference */
+    struct tgb_device* p_device;  /* owned; NULL if creation failed */
+    u32                width;     /* reference: swapchain extent (tgvk_raytracer.c:669-670) */
+    u32                height;
+    u32                debug_visualization;
+    u32                gi_enabled;    /* extension: 1 = one secondary ray per hit pixel through the SVO */
+    u32                frame_seed;    /* extension: seed of the secondary-ray RNG */
+    u32                svo_dirty;     /* 1 = full rebuild before next GI frame */
+    u32*               p_object_lut_idx; /* extension: per-object LUT index (README.md:12,18) */
+    u32                n_color_luts;
+} tg_raytracer;
+
+/* ---- reference entry points (tgvk_raytracer.h:240-251) ------------------------------------ */
+
+/* tgvk_raytracer.c:662-789. Resolution = tgb200_set_default_resolution() (stands in for the swapchain). */
+TG_EXPORT void tg_raytracer_create(const tg_camera* p_camera, u32 max_n_objects, u32 max_n_clusters, tg_raytracer* p_raytracer);
+/* tgvk_raytracer.c:791-796 (reference: TG_NOT_IMPLEMENTED; implemented here, Q10). */
+TG_EXPORT void tg_raytracer_destroy(tg_raytracer* p_raytracer);
+/* tgvk_raytracer.c:798-803 */
+TG_EXPORT void tg_raytracer_set_debug_visualization(tg_raytracer* p_raytracer, tg_debug_show type);
+/* tgvk_raytracer.c:805-992: object with the reference's procedural simplex-noise terrain fill. */
+TG_EXPORT void tg_raytracer_create_object(tg_raytracer* p_raytracer, v3 center, v3u extent);
+/* tgvk_raytracer.c:994-1067: returns cluster indices, compacts the pointer table downward. */
+TG_EXPORT void tg_raytracer_destroy_object(tg_raytracer* p_raytracer, u32 object_idx);
+/* tgvk_raytracer.c:1069-1077 */
+TG_EXPORT b32  tg_object_is_initialized(const tg_scene* p_scene, u32 object_idx);
+/* tgvk_raytracer.c:1122-1142: LUT 0. packed = r<<24|g<<16|b<<8|255, channel = (u32)(c*255.0f). */
+TG_EXPORT void tg_raytracer_color_lut_set(tg_raytracer* p_raytracer, u8 index, f32 r, f32 g, f32 b);
+/* tgvk_raytracer.c:1144-1553: camera -> (SVO) -> visibility -> GI + shading. */
+TG_EXPORT void tg_raytracer_render(tg_raytracer* p_raytracer);
+/* tgvk_raytracer.c:1556-1603 + clear.comp:15-21: visibility buffer <- all ones. */
+TG_EXPORT void tg_raytracer_clear(tg_raytracer* p_raytracer);
+/* tgvk_raytracer.c:1605-1655: reads one u64; p_cluster_idx receives the raw 31-bit POINTER field (Q1). */
+TG_EXPORT b32  tg_raytracer_get_hovered_voxel(tg_raytracer* p_raytracer, u32 screen_x, u32 screen_y, f32* p_depth, u32* p_cluster_idx, u32* p_voxel_idx);
+
+/* ---- reference SVO entry points (tg_sparse_voxel_octree.h:51-53) --------------------------- */
+
+/* tg_sparse_voxel_octree.c:466-542. Built on the GPU from the scene's device mirror, copied out
+ * into malloc'ed host arrays owned by *p_svo. The scene must belong to a live tg_raytracer. */
+TG_EXPORT void tg_svo_create(v3 extent_min, v3 extent_max, const tg_scene* p_scene, tg_svo* p_svo);
+/* tg_sparse_voxel_octree.c:544-556 */
+TG_EXPORT void tg_svo_destroy(tg_svo* p_svo);
+/* tg_sparse_voxel_octree.c:558-740: host-side single-ray query (picking/debug), as in the reference. */
+TG_EXPORT b32  tg_svo_traverse(const tg_svo* p_svo, v3 ray_origin, v3 ray_direction, f32* p_distance, u32* p_node_idx, u32* p_voxel_idx);
+
+/* ---- extensions ---------------------------------------------------------------------------- */
+
+/* NULL when no error has been recorded since the last tgb200_clear_error(). */
+TG_EXPORT const char* tgb200_last_error(void);
+TG_EXPORT void        tgb200_clear_error(void);
+/* Number of CUDA devices visible, or 0 (never fails). */
+TG_EXPORT i32         tgb200_device_count(void);
+/* CUDA device ordinal used by the next tg_raytracer_create (default 0; multi-GPU: LOCAL_RANK). */
+TG_EXPORT void        tgb200_set_device(i32 device);
+/* Resolution picked up by the next tg_raytracer_create (default 1920x1080). */
+TG_EXPORT void        tgb200_set_default_resolution(u32 width, u32 height);
+/* Reallocates the visibility / radiance buffers (reference: swapchain resize). */
+TG_EXPORT void        tg_raytracer_set_resolution(tg_raytracer* p_raytracer, u32 width, u32 height);
+
+/*
+ * Object whose voxels are given instead of generated (the reference can only fill procedurally,
+ * tgvk_raytracer.c:871-978). `p_solid_bits`: 16 u32 per cluster, clusters in pointer order
+ * (x fastest, then y, then z), bit 64z+8y+x. `p_lut_indices`: 512 u8 per cluster, same order, or
+ * NULL for the reference's rule (8*rel_x + vx) % 256 (tgvk_raytracer.c:947-978).
+ * Returns the object index, TG_U32_MAX on error.
+ */
+TG_EXPORT u32  tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
+                                                    const u32* p_solid_bits, const u8* p_lut_indices);
+/* Moves an object (the reference has no setter); marks the SVO for an incremental update. */
+TG_EXPORT void tg_raytracer_set_object_transform(tg_raytracer* p_raytracer, u32 object_idx, v3 translation, f32 angle_in_radians, v3 axis);
+/* color_lut_set for LUT `lut_idx` (lut[lut_idx*256 + index]); lut_idx 0 == the reference call. */
+TG_EXPORT void tg_raytracer_color_lut_set_ex(tg_raytracer* p_raytracer, u32 lut_idx, u8 index, f32 r, f32 g, f32 b);
+/* GI on/off + RNG seed of the secondary rays. */
+TG_EXPORT void tg_raytracer_set_gi(tg_raytracer* p_raytracer, b32 enabled, u32 frame_seed);
+
+/* Stages of render(), individually callable (bench / tests). All asynchronous on the raytracer's stream. */
+TG_EXPORT void tgb200_render_visibility(tg_raytracer* p_raytracer);          /* camera + cull + K1 */
+TG_EXPORT void tgb200_svo_update(tg_raytracer* p_raytracer, b32 force_full); /* K2: rebuild or incremental */
+TG_EXPORT void tgb200_render_shading(tg_raytracer* p_raytracer);             /* K3: (GI +) LUT shading */
+TG_EXPORT void tgb200_synchronize(tg_raytracer* p_raytracer);
+
+/* Copies of results into caller memory (synchronous). */
+TG_EXPORT void tg_raytracer_read_visibility(tg_raytracer* p_raytracer, u64* p_out /* w*h */);
+TG_EXPORT void tg_raytracer_read_radiance(tg_raytracer* p_raytracer, f32* p_out /* w*h*4, RGBA32F */);
+/* Replaces the device visibility buffer (tests: feed an oracle-made buffer to the shading stage). */
+TG_EXPORT void tg_raytracer_write_visibility(tg_raytracer* p_raytracer, const u64* p_in /* w*h */);
+/* Device SVO -> freshly malloc'ed host arrays in *p_svo (free with tg_svo_destroy). */
+TG_EXPORT void tgb200_svo_download(tg_raytracer* p_raytracer, tg_svo* p_svo);
+/* Host SVO -> device (tests: shade with an oracle-made SVO). */
+TG_EXPORT void tgb200_svo_upload(tg_raytracer* p_raytracer, const tg_svo* p_svo);
+
+/* Per-stage device time of the most recent call of each stage, CUDA events, milliseconds. */
+typedef struct tgb200_timings
+{
+    f32 clear_ms;
+    f32 cull_ms;
+    f32 visibility_ms;
+    f32 svo_ms;
+    f32 shading_ms;
+    f32 merge_ms;
+    u32 n_visible_objects;
+    u32 n_kernel_launches; /* kernels of this library launched since create/reset */
+} tgb200_timings;
+TG_EXPORT void tgb200_get_timings(tg_raytracer* p_raytracer, tgb200_timings* p_out);
+TG_EXPORT void tgb200_reset_launch_counter(tg_raytracer* p_raytracer);
+
+/* Raw device pointers + stream (for zero-copy interop, e.g. wrapping in a torch tensor). */
+TG_EXPORT void* tgb200_device_visibility(tg_raytracer* p_raytracer);
+TG_EXPORT void* tgb200_device_radiance(tg_raytracer* p_raytracer);
+TG_EXPORT void* tgb200_stream(tg_raytracer* p_raytracer);
+
+/*
+ * Multi-GPU: one process per GPU, clusters sharded by object. A shard's packed
+ * words carry GLOBAL cluster pointers = local pointer + global_pointer_base.
+ */
+TG_EXPORT void tgb200_set_shard(tg_raytracer* p_raytracer, u32 rank, u32 n_ranks, u32 global_pointer_base);
+/* 128-byte NCCL unique id (rank 0 creates, host code broadcasts, every rank joins). */
+TG_EXPORT void tgb200_comm_unique_id(u8* p_out_128);
+TG_EXPORT void tgb200_comm_init(tg_raytracer* p_raytracer, const u8* p_unique_id_128, u32 rank, u32 n_ranks);
+TG_EXPORT void tgb200_comm_destroy(tg_raytracer* p_raytracer);
+/* ncclAllReduce(ncclUint64, ncclMin) over the visibility buffer, in place. */
+TG_EXPORT void tgb200_merge_visibility(tg_raytracer* p_raytracer);
+
+/* ---- pure host logic, usable without a GPU (scene bookkeeping, camera) ---------------------- */
+
+/* tgvk_raytracer.c:687-712: allocates the CPU arrays, fills the LIFO free-lists descending. */
+TG_EXPORT void tgb200_scene_init(tg_scene* p_scene, u32 max_n_objects, u32 max_n_clusters);
+TG_EXPORT void tgb200_scene_free(tg_scene* p_scene);
+/* tgvk_raytracer.c:816-866: pops an object index and its clusters; returns the object index. */
+TG_EXPORT u32  tgb200_scene_alloc_object(tg_scene* p_scene, v3 center, v3u extent, f32 angle_in_radians, v3 axis);
+/* tgvk_raytracer.c:1000-1066; p_first_shifted_pointer/p_n_shifted describe the compacted range. */
+TG_EXPORT void tgb200_scene_free_object(tg_scene* p_scene, u32 object_idx, u32* p_first_shifted_pointer, u32* p_n_shifted);
+/* tgvk_core.c:382-444 + tgvk_raytracer.c:1171-1180 */
+TG_EXPORT void tgb200_camera_rays(const tg_camera* p_camera, tg_camera_rays* p_out);
+/* tgvk_raytracer.c:836-847: the 96-byte record of object `object_idx`. */
+TG_EXPORT void tgb200_object_data(const tg_scene* p_scene, u32 object_idx, u32 lut_idx, tg_object_data* p_out);
+/* tgvk_raytracer.c:1130-1134 */
+TG_EXPORT u32  tgb200_pack_color(f32 r, f32 g, f32 b);
+/* tgvk_raytracer.c:871-943: the reference's procedural terrain bits for one object (16 u32 per cluster). */
+TG_EXPORT void tgb200_procedural_solid_bits(u32 object_idx, v3u n_cluster_pointers_per_dim, u32* p_out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,178 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of oracle/libtgo.so (the scalar C restatement of the reference's voxel-rendering path)
+and of oracle/_ref/libtg_ref_aw.so (the reference's own util/tg_amanatides_woo.c, compiled unmodified).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this;
+nothing under tg_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from tg_b200 import ctypes_defs as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+VIS_BRUTE_FORCE = 0
+VIS_SCREEN_RECT = 1
+
+
+class tgo_scene_view(C.Structure):
+    _fields_ = [("n_objects_capacity", T.u32), ("p_objects", C.POINTER(T.tg_object_data)),
+                ("n_cluster_pointers", T.u32), ("p_cluster_pointers", C.POINTER(T.u32)),
+                ("p_cluster_idx_to_object_idx", C.POINTER(T.u32)), ("p_voxel_cluster_data", C.POINTER(T.u32)),
+                ("p_color_lut_idx_data", C.POINTER(T.u8)), ("p_color_lut", C.POINTER(T.u32)),
+                ("global_pointer_base", T.u32)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libtgo.so")
+    srcs = [os.path.join(_HERE, f) for f in ("tgo_visibility.c", "tgo_svo.c", "tgo_shade.c", "tgo.h", "tgo_math.h")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "libtgo.so"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/tg/src/util/tg_amanatides_woo.c") and (force or not os.path.exists(os.path.join(_HERE, "_ref", "libtg_ref_aw.so"))):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "libtgo.so"))
+        L.tgo_camera_rays.argtypes = [C.POINTER(T.tg_camera), C.POINTER(T.tg_camera_rays)]
+        L.tgo_object_data.argtypes = [C.POINTER(T.tg_voxel_object), T.u32, C.POINTER(T.tg_object_data)]
+        L.tgo_pack_color.argtypes = [T.f32, T.f32, T.f32]
+        L.tgo_pack_color.restype = T.u32
+        L.tgo_ws2ms.argtypes = [C.POINTER(T.tg_object_data), T.u32]
+        L.tgo_ws2ms.restype = T.m4
+        L.tgo_pixel_ray_direction_nn.argtypes = [C.POINTER(T.tg_camera_rays), T.u32, T.u32, T.u32, T.u32]
+        L.tgo_pixel_ray_direction_nn.restype = T.v3
+        L.tgo_visibility_fragment.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, T.u32, T.u32, T.u32]
+        L.tgo_visibility_fragment.restype = T.u64
+        L.tgo_visibility.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.u64)]
+        L.tgo_visibility.restype = T.u64
+        L.tgo_max_threads.restype = T.i32
+        L.tgo_set_threads.argtypes = [T.i32]
+        L.tgo_cluster_dda.argtypes = [C.POINTER(T.u32), T.v3, T.v3, T.f32]
+        L.tgo_cluster_dda.restype = T.i32
+        L.tgo_svo_create.argtypes = [T.v3, T.v3, C.POINTER(tgo_scene_view), C.POINTER(T.tg_voxel_object), C.POINTER(T.tg_svo)]
+        L.tgo_svo_destroy.argtypes = [C.POINTER(T.tg_svo)]
+        L.tgo_svo_traverse_glsl.argtypes = [C.POINTER(T.tg_svo), T.f32, T.v3, T.v3, C.POINTER(T.v3), C.POINTER(T.v3), C.POINTER(T.u32), C.POINTER(T.u32)]
+        L.tgo_svo_traverse_glsl.restype = T.f32
+        L.tgo_svo_traverse_c.argtypes = [C.POINTER(T.tg_svo), T.v3, T.v3, C.POINTER(T.f32), C.POINTER(T.u32), C.POINTER(T.u32)]
+        L.tgo_svo_traverse_c.restype = T.b32
+        L.tgo_amanatides_woo.argtypes = [T.v3, T.v3, T.v3, C.POINTER(T.u32), C.POINTER(T.v3i)]
+        L.tgo_amanatides_woo.restype = T.b32
+        L.tgo_intersect_aabb_obb_ignore_contact.argtypes = [T.v3, T.v3, C.POINTER(T.v3)]
+        L.tgo_intersect_aabb_obb_ignore_contact.restype = T.b32
+        L.tgo_shade.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, C.POINTER(T.u64), C.POINTER(T.tg_svo),
+                                T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.f32)]
+        _LIB = L
+    return _LIB
+
+
+def ref_aw():
+    """The reference's own tg_amanatides_woo (oracle/_ref), or None when it was never built."""
+    global _REF
+    if _REF is None:
+        build()
+        path = os.path.join(_HERE, "_ref", "libtg_ref_aw.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.tg_amanatides_woo.argtypes = [T.v3, T.v3, T.v3, C.POINTER(T.u32), C.POINTER(T.v3i)]
+        R.tg_amanatides_woo.restype = T.b32
+        _REF = R
+    return _REF
+
+
+def camera_rays(cam):
+    out = T.tg_camera_rays()
+    lib().tgo_camera_rays(C.byref(cam), C.byref(out))
+    return out
+
+
+def camera_from_spec(spec):
+    return T.make_camera(spec.position, spec.pitch, spec.yaw, spec.roll, spec.fov_y_deg, spec.aspect, spec.near, spec.far)
+
+
+class SceneView:
+    """Owns the numpy arrays behind a tgo_scene_view."""
+
+    def __init__(self, objects, cluster_pointers, c2o, masks, lut_idx=None, color_lut=None, object_lut_idx=None, global_pointer_base=0, **_):
+        L = lib()
+        self.voxel_objects = np.ascontiguousarray(objects)
+        n_obj = len(self.voxel_objects)
+        self.object_data = np.zeros(n_obj, dtype=T.OBJECT_DATA_DTYPE)
+        vo = self.voxel_objects.ctypes.data_as(C.POINTER(T.tg_voxel_object))
+        od = self.object_data.ctypes.data_as(C.POINTER(T.tg_object_data))
+        for i in range(n_obj):
+            li = int(object_lut_idx[i]) if object_lut_idx is not None else 0
+            L.tgo_object_data(C.byref(vo[i]), li, C.byref(od[i]))
+        self.cluster_pointers = np.ascontiguousarray(cluster_pointers, dtype=np.uint32)
+        self.c2o = np.ascontiguousarray(c2o, dtype=np.uint32)
+        self.masks = np.ascontiguousarray(masks, dtype=np.uint32)
+        self.lut_idx = None if lut_idx is None else np.ascontiguousarray(lut_idx, dtype=np.uint8)
+        self.color_lut = None if color_lut is None else np.ascontiguousarray(color_lut, dtype=np.uint32)
+        v = tgo_scene_view()
+        v.n_objects_capacity = n_obj
+        v.p_objects = od
+        v.n_cluster_pointers = len(self.cluster_pointers)
+        v.p_cluster_pointers = T.ptr(self.cluster_pointers, T.u32)
+        v.p_cluster_idx_to_object_idx = T.ptr(self.c2o, T.u32)
+        v.p_voxel_cluster_data = T.ptr(self.masks, T.u32)
+        v.p_color_lut_idx_data = T.ptr(self.lut_idx, T.u8) if self.lut_idx is not None else None
+        v.p_color_lut = T.ptr(self.color_lut, T.u32) if self.color_lut is not None else None
+        v.global_pointer_base = global_pointer_base
+        self.view = v
+
+    @classmethod
+    def from_scene(cls, scene, global_pointer_base=0):
+        from tg_b200.scenes import flat_arrays
+        return cls(**flat_arrays(scene, global_pointer_base))
+
+
+def visibility(view, rays, w, h, mode=VIS_SCREEN_RECT, y0=0, y1=None, ystep=1):
+    out = np.empty(w * h, dtype=np.uint64)
+    n = lib().tgo_visibility(C.byref(view.view), C.byref(rays), w, h, mode, y0, h if y1 is None else y1, ystep, T.ptr(out, T.u64))
+    return out.reshape(h, w), int(n)
+
+
+def visibility_fragment(view, rays, w, h, px, py, cluster_pointer):
+    return int(lib().tgo_visibility_fragment(C.byref(view.view), C.byref(rays), w, h, px, py, cluster_pointer))
+
+
+def svo_create(view, extent_min=(-512.0, -512.0, -512.0), extent_max=(512.0, 512.0, 512.0), capacities=None):
+    svo = T.tg_svo()
+    if capacities:
+        svo.voxel_buffer_capacity_in_u32, svo.leaf_node_data_buffer_capacity, svo.node_buffer_capacity = capacities
+    vo = view.voxel_objects.ctypes.data_as(C.POINTER(T.tg_voxel_object))
+    lib().tgo_svo_create(T.v3(*extent_min), T.v3(*extent_max), C.byref(view.view), vo, C.byref(svo))
+    return svo
+
+
+def svo_arrays(svo):
+    """(nodes u32[count], leaf_data u32[count, 65], voxels u32[count_in_u32]) copies."""
+    nodes = np.ctypeslib.as_array(svo.p_node_buffer, shape=(svo.node_buffer_count,)).copy()
+    nl = svo.leaf_node_data_buffer_count
+    leaf = np.ctypeslib.as_array(C.cast(svo.p_leaf_node_data_buffer, C.POINTER(T.u32)), shape=(max(nl, 1), 65))[:nl].copy()
+    nv = svo.voxel_buffer_count_in_u32
+    vox = np.ctypeslib.as_array(svo.p_voxels_buffer, shape=(max(nv, 1),))[:nv].copy()
+    return nodes, leaf, vox
+
+
+def svo_destroy(svo):
+    lib().tgo_svo_destroy(C.byref(svo))
+
+
+def shade(view, rays, w, h, vis, svo=None, gi=False, frame_seed=1, debug=0, y0=0, y1=None):
+    out = np.zeros((h, w, 4), dtype=np.float32)
+    vis = np.ascontiguousarray(vis, dtype=np.uint64)
+    lib().tgo_shade(C.byref(view.view), C.byref(rays), w, h, T.ptr(vis, T.u64), C.byref(svo) if svo is not None else None,
+                    1 if gi else 0, frame_seed, debug, y0, h if y1 is None else y1, T.ptr(out, T.f32))
+    return out
