@@ -174,6 +174,10 @@ TG_EXPORT void tgb200_camera_rays(const tg_camera* p_camera, tg_camera_rays* p_o
 TG_EXPORT void tgb200_object_data(const tg_scene* p_scene, u32 object_idx, u32 lut_idx, tg_object_data* p_out);
 /* tgvk_raytracer.c:1130-1134 */
 TG_EXPORT u32  tgb200_pack_color(f32 r, f32 g, f32 b);
+/* The ray of pixel (px,py) in the space of cluster `cluster_pointer`, evaluated on the HOST with the
+ * per-object factorisation the kernels use (tg_b200/csrc/tgb_hoist.h); visibility.frag:35-69. Verification hook. */
+TG_EXPORT void tgb200_debug_cluster_ray(const tg_object_data* p_object, const tg_camera_rays* p_cam, u32 width, u32 height, u32 px, u32 py,
+                                        u32 cluster_pointer, v3* p_origin_ms, v3* p_direction_ms);
 /* tgvk_raytracer.c:871-943: the reference's procedural terrain bits for one object (16 u32 per cluster). */
 TG_EXPORT void tgb200_procedural_solid_bits(u32 object_idx, v3u n_cluster_pointers_per_dim, u32* p_out);
 

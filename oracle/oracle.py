@@ -132,9 +132,9 @@ class SceneView:
         self.view = v
 
     @classmethod
-    def from_scene(cls, scene, global_pointer_base=0):
+    def from_scene(cls, scene, global_pointer_base=0, with_lut=True):
         from tg_b200.scenes import flat_arrays
-        return cls(**flat_arrays(scene, global_pointer_base))
+        return cls(**flat_arrays(scene, global_pointer_base, with_lut))
 
 
 def visibility(view, rays, w, h, mode=VIS_SCREEN_RECT, y0=0, y1=None, ystep=1):

@@ -293,6 +293,8 @@ typedef struct tgo__pinhole
 {
     f64 inv[9]; /* inverse of [u v bl] (row-major) */
     f64 cam[3];
+    f64 rx[3], uy[3], fz[3]; /* orthonormal camera frame: right (bl->br), up (bl->tl), forward */
+    f64 c0, bx, by, lu, lv;  /* plane distance, bl in the frame, |u|, |v| */
     u32 w, h;
     b32 ok;
 } tgo__pinhole;
@@ -314,6 +316,53 @@ static void tgo__pinhole_init(const tg_camera_rays* c, u32 w, u32 h, tgo__pinhol
     p->inv[6] = (d * hh - e * g) * id; p->inv[7] = (b * g - a * hh) * id;  p->inv[8] = (a * e - b * d) * id;
     p->cam[0] = c->camera.x; p->cam[1] = c->camera.y; p->cam[2] = c->camera.z;
     p->w = w; p->h = h;
+    p->lu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    p->lv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (!(p->lu > 0.0) || !(p->lv > 0.0)) { p->ok = TG_FALSE; return; }
+    for (int k = 0; k < 3; k++) { p->rx[k] = u[k] / p->lu; p->uy[k] = v[k] / p->lv; }
+    p->fz[0] = p->rx[1] * p->uy[2] - p->rx[2] * p->uy[1];
+    p->fz[1] = p->rx[2] * p->uy[0] - p->rx[0] * p->uy[2];
+    p->fz[2] = p->rx[0] * p->uy[1] - p->rx[1] * p->uy[0];
+    f64 lf = sqrt(p->fz[0] * p->fz[0] + p->fz[1] * p->fz[1] + p->fz[2] * p->fz[2]);
+    if (!(lf > 0.0)) { p->ok = TG_FALSE; return; }
+    p->c0 = (bl[0] * p->fz[0] + bl[1] * p->fz[1] + bl[2] * p->fz[2]) / lf;
+    if (p->c0 < 0.0) { lf = -lf; p->c0 = -p->c0; }
+    for (int k = 0; k < 3; k++) p->fz[k] /= lf;
+    p->bx = bl[0] * p->rx[0] + bl[1] * p->rx[1] + bl[2] * p->rx[2];
+    p->by = bl[0] * p->uy[0] + bl[1] * p->uy[1] + bl[2] * p->uy[2];
+    if (!(p->c0 > 0.0)) p->ok = TG_FALSE;
+}
+
+/* bounds of coordinate/depth over a circle of radius r around (a, z) in a plane through the eye; 0 = unbounded side */
+static void tgo__tangent_bounds(f64 a, f64 z, f64 r, f64* p_lo, f64* p_hi, b32* p_lo_ok, b32* p_hi_ok)
+{
+    const f64 d2 = a * a + z * z;
+    *p_lo_ok = TG_FALSE; *p_hi_ok = TG_FALSE; *p_lo = 0.0; *p_hi = 0.0;
+    if (d2 <= r * r * 1.0001) return;
+    const f64 theta = atan2(a, z), alpha = asin(r / sqrt(d2));
+    const f64 lo = theta - alpha, hi = theta + alpha, lim = 1.5607963267948966; /* pi/2 - 0.01 */
+    if (lo > -lim && lo < lim) { *p_lo = tan(lo); *p_lo_ok = TG_TRUE; }
+    if (hi > -lim && hi < lim) { *p_hi = tan(hi); *p_hi_ok = TG_TRUE; }
+    if (lo >= lim) { /* entirely beside/behind on the + side: nothing visible, keep conservative full range */ }
+}
+
+/* conservative pixel rectangle of a sphere; returns 0 when it is entirely behind the eye */
+static b32 tgo__sphere_rect(const tgo__pinhole* p, const f64 C[3], f64 r, i32* x0, i32* y0, i32* x1, i32* y1)
+{
+    const f64 X = C[0] * p->rx[0] + C[1] * p->rx[1] + C[2] * p->rx[2];
+    const f64 Y = C[0] * p->uy[0] + C[1] * p->uy[1] + C[2] * p->uy[2];
+    const f64 Z = C[0] * p->fz[0] + C[1] * p->fz[1] + C[2] * p->fz[2];
+    *x0 = 0; *y0 = 0; *x1 = (i32)p->w - 1; *y1 = (i32)p->h - 1;
+    if (Z + r < 0.0) return TG_FALSE;
+    f64 lo, hi; b32 lo_ok, hi_ok;
+    tgo__tangent_bounds(X, Z, r, &lo, &hi, &lo_ok, &hi_ok);
+    if (lo_ok) { const f64 px = ((p->c0 * lo - p->bx) / p->lu) * (f64)p->w - 0.5; const f64 q = floor(px) - 2.0; if (q > (f64)*x0) *x0 = q > 1e9 ? 1000000000 : (i32)q; }
+    if (hi_ok) { const f64 px = ((p->c0 * hi - p->bx) / p->lu) * (f64)p->w - 0.5; const f64 q = ceil(px) + 2.0;  if (q < (f64)*x1) *x1 = q < -1e9 ? -1000000000 : (i32)q; }
+    tgo__tangent_bounds(Y, Z, r, &lo, &hi, &lo_ok, &hi_ok);
+    /* fy grows upwards, pixel rows grow downwards */
+    if (hi_ok) { const f64 py = (1.0 - (p->c0 * hi - p->by) / p->lv) * (f64)p->h - 0.5; const f64 q = floor(py) - 2.0; if (q > (f64)*y0) *y0 = q > 1e9 ? 1000000000 : (i32)q; }
+    if (lo_ok) { const f64 py = (1.0 - (p->c0 * lo - p->by) / p->lv) * (f64)p->h - 0.5; const f64 q = ceil(py) + 2.0;  if (q < (f64)*y1) *y1 = q < -1e9 ? -1000000000 : (i32)q; }
+    return TG_TRUE;
 }
 
 /* Returns 0 if the point is not safely in front of the camera. */
@@ -373,7 +422,9 @@ static void tgo__cluster_rect(const tgo__pinhole* p, const tg_object_data* o, u3
                      R[3] * cx[0] + R[4] * cx[1] + R[5] * cx[2] + o->translation.y - p->cam[1],
                      R[6] * cx[0] + R[7] * cx[1] + R[8] * cx[2] + o->translation.z - p->cam[2] };
         const f64 dist = sqrt(C[0] * C[0] + C[1] * C[1] + C[2] * C[2]);
-        if (dist - 7.2 > (f64)far_plane * 1.001) { s->x1 = -1; }
+        if (dist - 7.2 > (f64)far_plane * 1.001) { s->x1 = -1; return; }
+        /* bounding sphere of the inflated box: radius sqrt(3) * (4 + margin) */
+        if (p->ok && !tgo__sphere_rect(p, C, 1.7320508075688772 * (4.0 + margin) + 1e-3, &s->x0, &s->y0, &s->x1, &s->y1)) { s->x1 = -1; }
         return;
     }
     {

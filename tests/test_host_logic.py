@@ -1,0 +1,180 @@
+"""CPU: the C-ABI library loads, exports every symbol include/tg_raytracer.h declares, its pure-host logic
+(scene bookkeeping of tgvk_raytracer.c:662-712,805-866,994-1077; camera maths of tgvk_core.c:382-444; the per-object
+factorisation the kernels rely on) matches hand-derived expectations and the oracle. No compute call is made."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import tg_b200
+from tg_b200 import ctypes_defs as T
+from tg_b200 import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = tg_b200.lib()
+    header = open(os.path.join(ROOT, "include", "tg_raytracer.h")).read()
+    declared = set(re.findall(r"TG_EXPORT\s+[\w\s\*]+?\b(tg\w+|tgb200_\w+)\s*\(", header))
+    assert len(declared) >= 45
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/tg_raytracer.h but not exported"
+    assert declared == set(tg_b200.SYMBOLS), declared ^ set(tg_b200.SYMBOLS)
+
+
+def test_struct_sizes_match_the_reference_layouts():
+    # 44, 96, 4, 260
+    assert C.sizeof(T.tg_voxel_object) == 44 and C.sizeof(T.tg_object_data) == 96 and C.sizeof(T.tg_svo_leaf_node_data) == 260
+    assert C.sizeof(T.m4) == 64 and C.sizeof(T.v3) == 12 and C.sizeof(T.tg_camera) == 52
+
+
+def test_free_lists_are_lifo_ascending_and_pointer_ranges_contiguous():
+    L = tg_b200.lib()
+    s = T.tg_scene()
+    L.tgb200_scene_init(C.byref(s), 4, 100)
+    assert s.n_available_object_indices == 4 and s.n_available_cluster_indices == 100
+    ids = [L.tgb200_scene_alloc_object(C.byref(s), T.v3(0, 0, 0), T.v3u(16, 8, 24), 0.0, T.v3(0, 1, 0)),
+           L.tgb200_scene_alloc_object(C.byref(s), T.v3(1, 2, 3), T.v3u(8, 8, 8), 0.5, T.v3(0, 1, 0)),
+           L.tgb200_scene_alloc_object(C.byref(s), T.v3(4, 5, 6), T.v3u(8, 16, 8), 0.7, T.v3(0, 1, 0))]
+    assert ids == [0, 1, 2]  # tgvk_raytracer.c:704-712: pops yield 0, 1, 2, ...
+    assert s.n_objects == 3 and s.n_cluster_pointers == 6 + 1 + 2
+    assert [s.p_objects[i].first_cluster_pointer for i in range(3)] == [0, 6, 7]
+    assert s.p_objects[0].n_cluster_pointers_per_dim.tuple() == (2, 1, 3)
+    assert [s.p_cluster_pointers[i] for i in range(9)] == list(range(9))  # fresh scene: idx == pointer
+    assert [s.p_cluster_idx_to_object_idx[i] for i in range(9)] == [0] * 6 + [1] + [2] * 2
+    assert L.tg_object_is_initialized(C.byref(s), 1) and not L.tg_object_is_initialized(C.byref(s), 3)
+
+    # destroy the middle object: tgvk_raytracer.c:1009-1066
+    first, n = T.u32(), T.u32()
+    L.tgb200_scene_free_object(C.byref(s), 1, C.byref(first), C.byref(n))
+    assert (first.value, n.value) == (6, 2)
+    assert s.n_objects == 2 and s.n_cluster_pointers == 8
+    assert [s.p_cluster_pointers[i] for i in range(8)] == [0, 1, 2, 3, 4, 5, 7, 8]   # compacted downward
+    assert s.p_objects[2].first_cluster_pointer == 6                                  # later object's first pointer decremented
+    assert not L.tg_object_is_initialized(C.byref(s), 1)
+    # the freed ids come back first (LIFO): object 1, cluster 6
+    idx = L.tgb200_scene_alloc_object(C.byref(s), T.v3(0, 0, 0), T.v3u(8, 8, 16), 0.0, T.v3(0, 1, 0))
+    assert idx == 1 and s.p_objects[1].first_cluster_pointer == 8
+    assert [s.p_cluster_pointers[i] for i in (8, 9)] == [6, 9]
+    assert s.p_cluster_idx_to_object_idx[6] == 1 and s.p_cluster_idx_to_object_idx[9] == 1
+    assert tg_b200.lib().tgb200_last_error() is None
+    L.tgb200_scene_free(C.byref(s))
+
+
+def test_preconditions_are_recorded_errors():
+    L = tg_b200.lib()
+    s = T.tg_scene()
+    L.tgb200_scene_init(C.byref(s), 1, 4)
+    L.tgb200_clear_error()
+    assert L.tgb200_scene_alloc_object(C.byref(s), T.v3(0, 0, 0), T.v3u(12, 8, 8), 0.0, T.v3(0, 1, 0)) == T.TG_U32_MAX  # extent % 8 (tgvk_raytracer.c:808-810)
+    assert b"multiples of 8" in L.tgb200_last_error()
+    L.tgb200_clear_error()
+    assert L.tgb200_scene_alloc_object(C.byref(s), T.v3(0, 0, 0), T.v3u(8, 8, 64), 0.0, T.v3(0, 1, 0)) == T.TG_U32_MAX  # 8 clusters > capacity 4
+    assert b"do not fit" in L.tgb200_last_error()
+    L.tgb200_clear_error()
+    L.tgb200_scene_free(C.byref(s))
+
+
+def test_camera_rays_match_oracle_bitwise(oracle):
+    L = tg_b200.lib()
+    specs = [scenes.config1().camera, scenes.config2(grid=1, width=64, height=36).camera,
+             scenes.CameraSpec((65.1368790, -30.7384720, 73.0285263), -0.173136666, 0.710419059, 0.0)]  # tg_application.c:51-59
+    rng = np.random.default_rng(3)
+    specs += [scenes.CameraSpec(tuple(rng.uniform(-900, 900, 3)), float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-3, 3)), float(rng.uniform(-0.5, 0.5)),
+                                fov_y_deg=float(rng.uniform(30, 110)), aspect=float(rng.uniform(0.5, 2.5))) for _ in range(20)]
+    for spec in specs:
+        cam = oracle.camera_from_spec(spec)
+        a = oracle.camera_rays(cam)
+        b = T.tg_camera_rays()
+        L.tgb200_camera_rays(C.byref(cam), C.byref(b))
+        assert bytes(a) == bytes(b)
+
+
+def test_pack_color_truncates(oracle):
+    L = tg_b200.lib()
+    for rgb in [(1.0, 0.0, 0.0), (0.5, 0.25, 0.999), (0.2, 0.4, 0.6)] + [c for c in scenes.reference_lut_ramp(256)[::17]]:
+        want = (int(np.float32(rgb[0]) * np.float32(255)) << 24) | (int(np.float32(rgb[1]) * np.float32(255)) << 16) | (int(np.float32(rgb[2]) * np.float32(255)) << 8) | 255
+        assert L.tgb200_pack_color(*rgb) == want == oracle.lib().tgo_pack_color(*rgb) == scenes.pack_color(*rgb)
+
+
+def test_per_object_factorisation_equals_the_full_chain(oracle):
+    """tgb_hoist.h (what K1/K3 evaluate per cluster) against the oracle's literal ws2ms3*ws2ms2*ws2ms1*ws2ms0 chain."""
+    L = tg_b200.lib()
+    OL = oracle.lib()
+    rng = np.random.default_rng(0)
+    f32 = np.float32
+    n_checked = 0
+    for trial in range(120):
+        vo = T.tg_voxel_object()
+        dims = [int(x) for x in rng.integers(1, 20, 3)]
+        vo.n_cluster_pointers_per_dim = T.v3u(*dims)
+        vo.first_cluster_pointer = int(rng.integers(0, 1000))
+        vo.translation = T.v3(*(rng.uniform(-3000, 3000, 3) if trial % 3 else np.zeros(3)))
+        vo.angle_in_radians = float(rng.uniform(-7, 7)) if trial % 5 else 0.0
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        if trial % 2 == 0:
+            ax = np.array([0.0, 1.0, 0.0])
+        vo.axis = T.v3(*ax)
+        od = T.tg_object_data()
+        OL.tgo_object_data(C.byref(vo), 0, C.byref(od))
+        spec = scenes.CameraSpec(tuple(rng.uniform(-500, 500, 3)), float(rng.uniform(-1, 1)), float(rng.uniform(-3, 3)), 0.0)
+        if trial % 11 == 0:
+            spec = scenes.CameraSpec((0.0, 0.0, 0.0), 0.0, 0.0, 0.0)
+        rays = oracle.camera_rays(oracle.camera_from_spec(spec))
+        for _ in range(10):
+            cp = vo.first_cluster_pointer + int(rng.integers(0, dims[0] * dims[1] * dims[2]))
+            px, py = int(rng.integers(0, 640)), int(rng.integers(0, 360))
+            m = OL.tgo_ws2ms(C.byref(od), cp)
+            mm = np.array([getattr(m, f[0]) for f in T.m4._fields_], dtype=f32).reshape(4, 4).T
+            d_ws = OL.tgo_pixel_ray_direction_nn(C.byref(rays), 640, 360, px, py)
+
+            def mulv(v, w):  # tgm_m4_mulv4 order, float32, no contraction
+                return [((f32(v[0]) * mm[i, 0] + f32(v[1]) * mm[i, 1]) + f32(v[2]) * mm[i, 2]) + f32(w) * mm[i, 3] for i in range(3)]
+            o_ref = mulv([rays.camera.x, rays.camera.y, rays.camera.z], 1.0)
+            r = mulv([d_ws.x, d_ws.y, d_ws.z], 0.0)
+            mag = np.sqrt(f32(r[0] * r[0] + r[1] * r[1]) + r[2] * r[2], dtype=f32)
+            ref = np.array(o_ref + [f32(r[i]) / mag for i in range(3)], dtype=f32)
+            o, d = T.v3(), T.v3()
+            L.tgb200_debug_cluster_ray(C.byref(od), C.byref(rays), 640, 360, px, py, cp, C.byref(o), C.byref(d))
+            got = np.array([o.x, o.y, o.z, d.x, d.y, d.z], dtype=f32)
+            assert np.array_equal(got, ref), (trial, got, ref)  # == treats +0/-0 alike: a signed zero never reaches a packed word
+            n_checked += 1
+    assert n_checked == 1200
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """Without a CUDA device tg_raytracer_create must fail with an error (and with one, succeed): never a CPU path."""
+    L = tg_b200.lib()
+    cam = T.make_camera((0, 0, 10), 0, 0, 0, 70, 1.0, 0.1, 100)
+    if L.tgb200_device_count() == 0:
+        with pytest.raises(tg_b200.TgError, match="no CUDA device|no CPU fallback"):
+            tg_b200.Raytracer(cam, 1, 1, 16, 16)
+        rt = T.tg_raytracer()
+        L.tg_raytracer_create(C.byref(cam), 1, 1, C.byref(rt))
+        assert not rt.p_device and L.tgb200_last_error()
+        L.tgb200_clear_error()
+        L.tg_raytracer_render(C.byref(rt))  # every later call is a recorded error, not a computation
+        assert b"no device state" in L.tgb200_last_error()
+        L.tgb200_clear_error()
+    else:
+        tg_b200.Raytracer(cam, 1, 1, 16, 16).destroy()
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product tree must not include, link or import anything under oracle/."""
+    pkg = os.path.join(ROOT, "tg_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".c", ".cu", ".cuh", ".h", ".py", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for pattern in (r"#include\s+\"[^\"]*(oracle|tgo)", r"\bimport\s+oracle", r"\bfrom\s+oracle", r"\btgo_\w+\s*\(", r"libtgo"):
+                    assert not re.search(pattern, text), (os.path.join(dirpath, f), pattern)
+    import subprocess
+    out = subprocess.run(["ldd", tg_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libtgo" not in out

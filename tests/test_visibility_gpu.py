@@ -1,0 +1,196 @@
+"""GPU: K1 (tg_b200/csrc/tgb_visibility.cu) through the C ABI against the oracle, bit for bit.
+
+The visibility buffer is integer work: the bar is bit-exact (np.array_equal on the u64 words), at sizes the oracle
+finishes in seconds, against the committed golden fixtures, and at BASELINE config 2's full size through a scanline
+subset plus size-independent properties (idempotence of re-rendering, clear value, pointer-base linearity)."""
+import os
+
+import numpy as np
+import pytest
+
+from tg_b200 import scenes
+from tests.helpers import CLEAR, describe_mismatch, gpu_visibility, oracle_visibility
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def check(O, scene, mode=None):
+    got, timings = gpu_visibility(scene)
+    want = oracle_visibility(O, scene, mode)
+    assert np.array_equal(got, want), describe_mismatch(got, want)
+    return got, timings
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_config1_full_size_bit_exact(gpu, oracle, k):
+    """BASELINE configs[0]: one object of 16^3 clusters, 1280x720."""
+    got, _ = check(oracle, scenes.config1(k=k))
+    assert (got != CLEAR).mean() > 0.05
+
+
+def test_config1_against_brute_force_oracle(gpu, oracle):
+    check(oracle, scenes.config1(k=3, width=320, height=180), oracle.VIS_BRUTE_FORCE)
+
+
+@pytest.mark.parametrize("name", ["config1_k3_320x180", "config1_k1_320x180", "small_grid3_320x180"])
+def test_against_committed_golden_fixtures(gpu, name):
+    from tests.golden.make_golden import CASES
+    want = np.load(os.path.join(GOLDEN, name + ".npz"))["vis"]
+    got, _ = gpu_visibility(CASES[name]())
+    assert np.array_equal(got, want), describe_mismatch(got, want)
+
+
+def test_rotated_objects_grid_brute_force(gpu, oracle):
+    check(oracle, scenes.small_grid(), oracle.VIS_BRUTE_FORCE)
+    check(oracle, scenes.small_grid(grid=5, width=333, height=177, dims=(3, 5, 2)), oracle.VIS_BRUTE_FORCE)  # ragged resolution
+
+
+def test_edge_cases(gpu, oracle):
+    base = dict(width=192, height=108)
+    cases = []
+    # camera inside the object, looking around
+    for pos, pitch, yaw in [((0.0, 0.0, 0.0), 0.0, 0.0), ((3.3, -2.1, 7.7), -0.9, 2.0), ((0.0, 40.0, 0.0), -1.5, 0.0), ((60.0, 0.5, 0.5), 0.0, 1.5707964)]:
+        s = scenes.config1(k=3, dims=(6, 4, 6), **base)
+        s.camera = scenes.CameraSpec(pos, pitch, yaw, 0.0, aspect=192 / 108)
+        cases.append(s)
+    # axis-aligned object (exact zeros in the rotation) and a grazing, axis-parallel view
+    s = scenes.config1(k=1, dims=(4, 4, 4), **base)
+    s.objects[0].angle = 0.0
+    s.camera = scenes.CameraSpec((0.0, 16.0, 80.0), 0.0, 0.0, 0.0, aspect=192 / 108)  # eye exactly in the top face plane
+    cases.append(s)
+    # single cluster, dense
+    s = scenes.config1(k=1, dims=(1, 1, 1), **base)
+    s.camera = scenes.CameraSpec((0.0, 0.0, 20.0), 0.0, 0.0, 0.0, aspect=192 / 108)
+    cases.append(s)
+    # far plane cuts through the object (d <= 1 test) and object entirely beyond it
+    s = scenes.config1(k=3, dims=(8, 8, 8), **base)
+    s.camera = scenes.CameraSpec((0.0, 0.0, 160.0), 0.0, 0.0, 0.0, aspect=192 / 108, far=150.0)
+    cases.append(s)
+    s = scenes.config1(k=3, dims=(4, 4, 4), **base)
+    s.camera = scenes.CameraSpec((0.0, 0.0, 160.0), 0.0, 0.0, 0.0, aspect=192 / 108, far=100.0)
+    cases.append(s)
+    # object behind the camera
+    s = scenes.config1(k=3, dims=(4, 4, 4), **base)
+    s.camera = scenes.CameraSpec((0.0, 0.0, -160.0), 0.0, 0.0, 0.0, aspect=192 / 108)
+    cases.append(s)
+    # empty masks, and one with a single voxel
+    s = scenes.config1(k=3, dims=(2, 2, 2), **base)
+    s.objects[0].bits = np.zeros_like(s.objects[0].bits)
+    cases.append(s)
+    s = scenes.config1(k=3, dims=(2, 2, 2), **base)
+    s.objects[0].bits = np.zeros_like(s.objects[0].bits)
+    s.objects[0].bits[5, 9] = 1 << 13
+    s.camera = scenes.CameraSpec((2.0, 3.0, 40.0), 0.0, 0.0, 0.0, aspect=192 / 108)
+    cases.append(s)
+    # large translations (float precision of the hoisted chain), arbitrary axis
+    s = scenes.config1(k=3, dims=(5, 3, 4), **base)
+    s.objects[0].center = (2900.0, -1300.0, 2100.0)
+    s.objects[0].axis = (0.6, 0.0, 0.8)
+    s.objects[0].angle = 1.234
+    s.camera = scenes.CameraSpec((2900.0, -1290.0, 2200.0), -0.1, 0.0, 0.0, aspect=192 / 108)
+    cases.append(s)
+    for i, s in enumerate(cases):
+        got, want = gpu_visibility(s)[0], oracle_visibility(oracle, s, oracle.VIS_BRUTE_FORCE)
+        assert np.array_equal(got, want), f"edge case {i}: " + describe_mismatch(got, want)
+
+
+def test_overlapping_objects_and_ties(gpu, oracle):
+    """Two objects occupying the same space with identical voxels: equal depths, the lower cluster pointer must win."""
+    a = scenes.config1(k=3, width=192, height=108, dims=(3, 3, 3))
+    twin = scenes.ObjectSpec(center=a.objects[0].center, extent=a.objects[0].extent, angle=a.objects[0].angle, bits=a.objects[0].bits.copy())
+    a.objects.append(twin)
+    a.camera = scenes.CameraSpec((0.0, 5.0, 60.0), -0.1, 0.0, 0.0, aspect=192 / 108)
+    got, _ = check(oracle, a, oracle.VIS_BRUTE_FORCE)
+    hit = got != CLEAR
+    assert hit.any() and (((got[hit] >> np.uint64(9)) & np.uint64(0x7FFFFFFF)) < np.uint64(27)).all()
+
+
+def test_render_is_idempotent_and_clear_resets(gpu):
+    from tg_b200.raytracer import from_scene
+    s = scenes.small_grid()
+    rt = from_scene(s)
+    try:
+        rt.clear(); rt.render_visibility(); rt.synchronize()
+        a = rt.read_visibility()
+        rt.render_visibility(); rt.synchronize()  # atomicMin onto an already resolved buffer: unchanged
+        assert np.array_equal(a, rt.read_visibility())
+        rt.clear(); rt.synchronize()
+        assert (rt.read_visibility() == CLEAR).all()
+        hit, depth, cluster, voxel = rt.get_hovered_voxel(0, 0)
+        assert not hit and cluster == 0xFFFFFFFF and voxel == 0xFFFFFFFF
+        rt.render_visibility(); rt.synchronize()
+        ys, xs = np.nonzero(a != CLEAR)
+        y, x = int(ys[len(ys) // 2]), int(xs[len(xs) // 2])
+        hit, depth, cluster, voxel = rt.get_hovered_voxel(x, y)  # tgvk_raytracer.c:1605-1655
+        w = int(a[y, x])
+        assert hit and cluster == (w >> 9) & 0x7FFFFFFF and voxel == w & 511
+        assert depth == np.float32(w >> 40) / np.float32(16777215.0)
+    finally:
+        rt.destroy()
+
+
+def test_pointer_base_linearity(gpu):
+    """Multi-GPU contract: a shard's words carry local pointer + base, nothing else changes."""
+    s = scenes.small_grid()
+    a, _ = gpu_visibility(s, base=0)
+    b, _ = gpu_visibility(s, base=1 << 20)
+    hit = a != CLEAR
+    assert np.array_equal(hit, b != CLEAR)
+    assert ((b[hit] - a[hit]) == np.uint64((1 << 20) << 9)).all()
+
+
+def test_destroy_object_then_render(gpu, oracle):
+    """Pointer-table compaction (tgvk_raytracer.c:1009-1066) mirrored on the device: cluster idx != pointer afterwards."""
+    from tg_b200.raytracer import from_scene
+    s = scenes.small_grid()
+    rt = from_scene(s)
+    try:
+        rt.destroy_object(3)
+        rt.destroy_object(0)
+        rt.clear(); rt.render_visibility(); rt.synchronize()
+        got = rt.read_visibility()
+        sc = rt.scene
+        n = sc.n_cluster_pointers
+        cap = sc.cluster_pointer_capacity
+        pointers = np.ctypeslib.as_array(sc.p_cluster_pointers, shape=(cap,))[:n].copy()
+        assert not np.array_equal(pointers, np.arange(n))
+        c2o = np.ctypeslib.as_array(sc.p_cluster_idx_to_object_idx, shape=(cap,)).copy()
+        masks = np.ctypeslib.as_array(sc.p_voxel_cluster_data, shape=(cap, 16)).copy()
+        from tg_b200 import ctypes_defs as T
+        import ctypes
+        objects = np.frombuffer(ctypes.string_at(sc.p_objects, sc.object_capacity * 44), dtype=T.VOXEL_OBJECT_DTYPE).copy()
+        view = oracle.SceneView(objects, pointers, c2o, masks)
+        rays = oracle.camera_rays(oracle.camera_from_spec(s.camera))
+        want, _ = oracle.visibility(view, rays, s.width, s.height, oracle.VIS_BRUTE_FORCE)
+        assert np.array_equal(got, want), describe_mismatch(got, want)
+    finally:
+        rt.destroy()
+
+
+def test_config2_full_size_scanline_subset_and_properties(gpu, oracle):
+    """BASELINE configs[1]: 1,024 objects, 2^21 clusters, 3840x2160. The oracle evaluates every 40th scanline."""
+    s = scenes.config2()
+    from tg_b200.raytracer import from_scene
+    rt = from_scene(s)
+    try:
+        rt.clear(); rt.render_visibility(); rt.synchronize()
+        got = rt.read_visibility()
+        t = rt.timings()
+        want = oracle_visibility(oracle, s, None, 7, None, 40)
+        rows = np.arange(7, s.height, 40)
+        assert np.array_equal(got[rows], want[rows]), describe_mismatch(got[rows], want[rows])
+        hit = got != CLEAR
+        assert 0.3 < hit.mean() < 0.9
+        # properties: pointers in range, voxel bit really set, depth < 2^24
+        ptr = ((got[hit] >> np.uint64(9)) & np.uint64(0x7FFFFFFF)).astype(np.int64)
+        vox = (got[hit] & np.uint64(511)).astype(np.int64)
+        assert ptr.max() < s.n_clusters
+        masks = np.concatenate([o.bits for o in s.objects])
+        assert ((masks[ptr, vox // 32] >> (vox % 32).astype(np.uint32)) & 1).all()
+        # idempotence at full size
+        rt.render_visibility(); rt.synchronize()
+        assert np.array_equal(got, rt.read_visibility())
+        assert t["n_visible_objects"] < 200
+    finally:
+        rt.destroy()

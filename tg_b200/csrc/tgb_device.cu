@@ -1,0 +1,262 @@
+/*
+ * tgb_device.cu -- device memory, streams and events behind the thin C-ABI seam of tgb_internal.h.
+ * Replaces the reference's Vulkan buffer / staging / queue layer for this path
+ * (/root/reference/tg/src/graphics/vulkan/tgvk_raytracer.c:156-274 buffer set-up, tgvk_core.c:3345-3482
+ * staging ring) with plain cudaMalloc'ed arrays on one stream.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "tgb_device.cuh"
+
+extern "C" i32 tgbd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static b32 tgbd__alloc(struct tgb_device* d)
+{
+    const u64 nc = d->cluster_capacity, no = d->object_capacity;
+    TGB_CUDA(cudaMalloc(&d->d_cluster_pointers, nc * sizeof(u32)));
+    TGB_CUDA(cudaMalloc(&d->d_c2o, nc * sizeof(u32)));
+    TGB_CUDA(cudaMalloc(&d->d_objects, no * sizeof(tg_object_data)));
+    TGB_CUDA(cudaMalloc(&d->d_masks, nc * 64));
+    TGB_CUDA(cudaMalloc(&d->d_lut_idx, nc * 512));
+    TGB_CUDA(cudaMalloc(&d->d_color_lut, (u64)d->n_color_luts * 256 * sizeof(u32)));
+    TGB_CUDA(cudaMalloc(&d->d_frames, no * sizeof(tgb_object_frame)));
+    TGB_CUDA(cudaMalloc(&d->d_frames_sorted, no * sizeof(tgb_object_frame)));
+    TGB_CUDA(cudaMalloc(&d->d_visible_count, 4 * sizeof(u32)));
+    TGB_CUDA(cudaMallocHost(&d->h_visible_count, 4 * sizeof(u32)));
+    TGB_CUDA(cudaMemsetAsync(d->d_cluster_pointers, 0, nc * sizeof(u32), d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_c2o, 0, nc * sizeof(u32), d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_objects, 0, no * sizeof(tg_object_data), d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_masks, 0, nc * 64, d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_color_lut, 0, (u64)d->n_color_luts * 256 * sizeof(u32), d->stream));
+    for (int i = 0; i < 12; i++) TGB_CUDA(cudaEventCreate(&d->ev[i]));
+
+    /* SVO capacities: tg_sparse_voxel_octree.c:479-484 */
+    d->svo.node_capacity = 1u << 14;
+    d->svo.leaf_capacity = 1u << 13;
+    d->svo.voxel_word_capacity = 1u << 21;
+    TGB_CUDA(cudaMalloc(&d->svo.d_nodes, (u64)d->svo.node_capacity * 4));
+    TGB_CUDA(cudaMalloc(&d->svo.d_leaf_data, (u64)d->svo.leaf_capacity * 65 * 4));
+    TGB_CUDA(cudaMalloc(&d->svo.d_voxels, (u64)d->svo.voxel_word_capacity * 4));
+    TGB_CUDA(cudaMalloc(&d->svo.d_counts, 16 * sizeof(u32)));
+    return TG_TRUE;
+}
+
+extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    if (d->d_vis) TGB_CUDA(cudaFree(d->d_vis));
+    if (d->d_radiance) TGB_CUDA(cudaFree(d->d_radiance));
+    d->d_vis = NULL;
+    d->d_radiance = NULL;
+    d->width = width;
+    d->height = height;
+    TGB_CUDA(cudaMalloc(&d->d_vis, (u64)width * height * sizeof(u64)));
+    TGB_CUDA(cudaMalloc(&d->d_radiance, (u64)width * height * sizeof(float4)));
+    TGB_CUDA(cudaMemsetAsync(d->d_vis, 0xFF, (u64)width * height * sizeof(u64), d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_radiance, 0, (u64)width * height * sizeof(float4), d->stream));
+    return TG_TRUE;
+}
+
+extern "C" struct tgb_device* tgbd_create(i32 device, u32 object_capacity, u32 cluster_capacity, u32 n_color_luts, u32 width, u32 height)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+    {
+        cudaGetLastError();
+        tgb_set_error("tg_raytracer_create: no CUDA device (%s); libtgb200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return NULL;
+    }
+    if (device < 0 || device >= n)
+    {
+        tgb_set_error("tg_raytracer_create: device %d out of range (have %d)", device, n);
+        return NULL;
+    }
+    if (cudaSetDevice(device) != cudaSuccess)
+    {
+        tgb_set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return NULL;
+    }
+    struct tgb_device* d = (struct tgb_device*)calloc(1, sizeof(*d));
+    d->device = device;
+    d->object_capacity = object_capacity;
+    d->cluster_capacity = cluster_capacity;
+    d->n_color_luts = n_color_luts ? n_color_luts : 1;
+    if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        tgb_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        free(d);
+        return NULL;
+    }
+    if (!tgbd__alloc(d) || !tgbd_resize(d, width, height))
+    {
+        tgbd_destroy(d);
+        return NULL;
+    }
+    cudaStreamSynchronize(d->stream);
+    return d;
+}
+
+extern "C" void tgbd_destroy(struct tgb_device* d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaStreamSynchronize(d->stream);
+    cudaFree(d->d_cluster_pointers); cudaFree(d->d_c2o); cudaFree(d->d_objects); cudaFree(d->d_masks);
+    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance);
+    cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_visible_count);
+    if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
+    cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts);
+    cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch);
+    for (int i = 0; i < 12; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    cudaStreamDestroy(d->stream);
+    cudaGetLastError();
+    free(d);
+}
+
+static b32 tgbd__buffer_range(struct tgb_device* d, u32 buffer, u8** pp, u64* p_size)
+{
+    const u64 nc = d->cluster_capacity, no = d->object_capacity, px = (u64)d->width * d->height;
+    switch (buffer)
+    {
+    case TGB_BUF_CLUSTER_POINTERS: *pp = (u8*)d->d_cluster_pointers; *p_size = nc * 4; break;
+    case TGB_BUF_C2O:              *pp = (u8*)d->d_c2o;              *p_size = nc * 4; break;
+    case TGB_BUF_OBJECTS:          *pp = (u8*)d->d_objects;          *p_size = no * sizeof(tg_object_data); break;
+    case TGB_BUF_MASKS:            *pp = (u8*)d->d_masks;            *p_size = nc * 64; break;
+    case TGB_BUF_LUT_IDX:          *pp = (u8*)d->d_lut_idx;          *p_size = nc * 512; break;
+    case TGB_BUF_COLOR_LUT:        *pp = (u8*)d->d_color_lut;        *p_size = (u64)d->n_color_luts * 1024; break;
+    case TGB_BUF_VISIBILITY:       *pp = (u8*)d->d_vis;              *p_size = px * 8; break;
+    case TGB_BUF_RADIANCE:         *pp = (u8*)d->d_radiance;         *p_size = px * 16; break;
+    case TGB_BUF_SVO_NODES:        *pp = (u8*)d->svo.d_nodes;        *p_size = (u64)d->svo.node_capacity * 4; break;
+    case TGB_BUF_SVO_LEAF_DATA:    *pp = (u8*)d->svo.d_leaf_data;    *p_size = (u64)d->svo.leaf_capacity * 260; break;
+    case TGB_BUF_SVO_VOXELS:       *pp = (u8*)d->svo.d_voxels;       *p_size = (u64)d->svo.voxel_word_capacity * 4; break;
+    default: tgb_set_error("unknown device buffer %u", buffer); return TG_FALSE;
+    }
+    return TG_TRUE;
+}
+
+extern "C" void* tgbd_buffer(struct tgb_device* d, u32 buffer)
+{
+    u8* p = NULL; u64 size = 0;
+    if (!tgbd__buffer_range(d, buffer, &p, &size)) return NULL;
+    return p;
+}
+
+extern "C" void* tgbd_stream(struct tgb_device* d) { return (void*)d->stream; }
+
+extern "C" b32 tgbd_upload(struct tgb_device* d, u32 buffer, u64 dst_offset_bytes, const void* p_src, u64 n_bytes)
+{
+    u8* p; u64 size;
+    if (!tgbd__buffer_range(d, buffer, &p, &size)) return TG_FALSE;
+    if (dst_offset_bytes + n_bytes > size) { tgb_set_error("upload past the end of device buffer %u (%llu + %llu > %llu)", buffer, (unsigned long long)dst_offset_bytes, (unsigned long long)n_bytes, (unsigned long long)size); return TG_FALSE; }
+    TGB_CUDA(cudaSetDevice(d->device));
+    /* pageable source: the copy is staged before the call returns, so the caller may reuse p_src */
+    TGB_CUDA(cudaMemcpyAsync(p + dst_offset_bytes, p_src, n_bytes, cudaMemcpyHostToDevice, d->stream));
+    return TG_TRUE;
+}
+
+extern "C" b32 tgbd_download(struct tgb_device* d, u32 buffer, u64 src_offset_bytes, void* p_dst, u64 n_bytes)
+{
+    u8* p; u64 size;
+    if (!tgbd__buffer_range(d, buffer, &p, &size)) return TG_FALSE;
+    if (src_offset_bytes + n_bytes > size) { tgb_set_error("download past the end of device buffer %u", buffer); return TG_FALSE; }
+    TGB_CUDA(cudaSetDevice(d->device));
+    TGB_CUDA(cudaMemcpyAsync(p_dst, p + src_offset_bytes, n_bytes, cudaMemcpyDeviceToHost, d->stream));
+    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    return TG_TRUE;
+}
+
+extern "C" b32 tgbd_move(struct tgb_device* d, u32 buffer, u64 dst_offset_bytes, u64 src_offset_bytes, u64 n_bytes)
+{
+    u8* p; u64 size;
+    if (!tgbd__buffer_range(d, buffer, &p, &size)) return TG_FALSE;
+    if (dst_offset_bytes + n_bytes > size || src_offset_bytes + n_bytes > size) { tgb_set_error("move past the end of device buffer %u", buffer); return TG_FALSE; }
+    if (n_bytes == 0) return TG_TRUE;
+    TGB_CUDA(cudaSetDevice(d->device));
+    /* ranges may overlap (shift down): bounce through a temporary */
+    void* p_tmp = NULL;
+    TGB_CUDA(cudaMalloc(&p_tmp, n_bytes));
+    TGB_CUDA(cudaMemcpyAsync(p_tmp, p + src_offset_bytes, n_bytes, cudaMemcpyDeviceToDevice, d->stream));
+    TGB_CUDA(cudaMemcpyAsync(p + dst_offset_bytes, p_tmp, n_bytes, cudaMemcpyDeviceToDevice, d->stream));
+    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    TGB_CUDA(cudaFree(p_tmp));
+    return TG_TRUE;
+}
+
+extern "C" void tgbd_synchronize(struct tgb_device* d)
+{
+    cudaSetDevice(d->device);
+    cudaError_t e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) tgb_set_error("cudaStreamSynchronize -> %s", cudaGetErrorString(e));
+}
+
+extern "C" void tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base) { d->global_pointer_base = global_pointer_base; }
+
+extern "C" void tgbd_reset_launch_counter(struct tgb_device* d) { d->n_kernel_launches = 0; }
+
+extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
+{
+    cudaSetDevice(d->device);
+    cudaStreamSynchronize(d->stream);
+    if (d->ev_clear) cudaEventElapsedTime(&d->clear_ms, d->ev[0], d->ev[1]);
+    if (d->ev_vis)   { cudaEventElapsedTime(&d->cull_ms, d->ev[2], d->ev[3]); cudaEventElapsedTime(&d->visibility_ms, d->ev[3], d->ev[4]); }
+    if (d->ev_svo)   cudaEventElapsedTime(&d->svo_ms, d->ev[5], d->ev[6]);
+    if (d->ev_shade) cudaEventElapsedTime(&d->shading_ms, d->ev[7], d->ev[8]);
+    if (d->ev_merge) cudaEventElapsedTime(&d->merge_ms, d->ev[9], d->ev[10]);
+    cudaGetLastError();
+    p_out->clear_ms = d->clear_ms;
+    p_out->cull_ms = d->cull_ms;
+    p_out->visibility_ms = d->visibility_ms;
+    p_out->svo_ms = d->svo_ms;
+    p_out->shading_ms = d->shading_ms;
+    p_out->merge_ms = d->merge_ms;
+    p_out->n_visible_objects = d->n_visible_objects;
+    p_out->n_kernel_launches = d->n_kernel_launches;
+}
+
+extern "C" void tgbd_merge_begin(struct tgb_device* d) { cudaSetDevice(d->device); cudaEventRecord(d->ev[9], d->stream); }
+extern "C" void tgbd_merge_end(struct tgb_device* d) { cudaEventRecord(d->ev[10], d->stream); d->ev_merge = TG_TRUE; }
+
+/* (8*rel_x + vx) % 256, tgvk_raytracer.c:947-978; one thread per 16 voxels (uint4 stores) */
+__global__ void k_fill_default_lut_idx(const u32* __restrict__ p_cluster_pointers, u8* __restrict__ p_lut_idx, u32 first_pointer, u32 n_cluster_pointers, u32 nx)
+{
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 n_vec = (u64)n_cluster_pointers * 32; /* 512 B / 16 B */
+    if (t >= n_vec) return;
+    const u32 rel = (u32)(t / 32);
+    const u32 part = (u32)(t % 32);      /* voxels [16*part, 16*part+16): two x-rows */
+    const u32 rel_x = rel % nx;
+    const u32 cluster_idx = p_cluster_pointers[first_pointer + rel];
+    u32 w[4];
+#pragma unroll
+    for (u32 k = 0; k < 4; k++)
+    {
+        u32 word = 0;
+#pragma unroll
+        for (u32 b = 0; b < 4; b++)
+        {
+            const u32 vx = (k * 4 + b) % 8;
+            word |= ((8u * rel_x + vx) % 256u) << (8 * b);
+        }
+        w[k] = word;
+    }
+    uint4* p_dst = (uint4*)(p_lut_idx + (u64)cluster_idx * 512) + part;
+    *p_dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+extern "C" b32 tgbd_fill_default_lut_idx(struct tgb_device* d, u32 first_pointer, u32 n_cluster_pointers, u32 nx)
+{
+    if (n_cluster_pointers == 0) return TG_TRUE;
+    TGB_CUDA(cudaSetDevice(d->device));
+    const u64 n_vec = (u64)n_cluster_pointers * 32;
+    k_fill_default_lut_idx<<<(u32)((n_vec + 255) / 256), 256, 0, d->stream>>>(d->d_cluster_pointers, d->d_lut_idx, first_pointer, n_cluster_pointers, nx);
+    TGB_LAUNCH_CHECK(d);
+    return TG_TRUE;
+}

@@ -1,0 +1,84 @@
+/*
+ * tgb_device.cuh -- device-side state of one raytracer (replaces the Vulkan buffers of
+ * tg_raytracer_data, /root/reference/tg/src/graphics/vulkan/tgvk_raytracer.h:110-137).
+ * All arrays live in HBM for the raytracer's lifetime; nothing is re-uploaded per frame except the
+ * 96-byte camera block (kernel parameter).
+ */
+#ifndef TGB_DEVICE_CUH
+#define TGB_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "tgb_internal.h"
+#include "tgb_math.h"
+#include "tgb_hoist.h"
+
+struct tgb_svo_device
+{
+    v3   bmin, bmax;
+    u32  node_capacity, leaf_capacity, voxel_word_capacity;
+    u32* d_nodes;
+    u32* d_leaf_data;   /* 65 u32 per leaf */
+    u32* d_voxels;      /* 1024 u32 per leaf */
+    u32* d_counts;      /* [0] nodes, [1] leaves, [2] overflow flag */
+    u32  n_nodes, n_leaves;
+    b32  valid;
+    /* build scratch (grown on demand) */
+    u32* d_pairs_a;     /* (node, cluster pointer) pairs, ping */
+    u32* d_pairs_b;     /* pong */
+    u64  pair_capacity;
+    u32* d_scratch;     /* scan / flags */
+    u64  scratch_capacity;
+};
+
+struct tgb_device
+{
+    i32          device;
+    cudaStream_t stream;
+    u32          object_capacity, cluster_capacity, n_color_luts, width, height;
+    u32          global_pointer_base;
+
+    u32*            d_cluster_pointers;
+    u32*            d_c2o;
+    tg_object_data* d_objects;
+    u32*            d_masks;
+    u8*             d_lut_idx;
+    u32*            d_color_lut;
+    u64*            d_vis;
+    float4*         d_radiance;
+
+    tgb_object_frame* d_frames;        /* [object_capacity] compacted visible objects */
+    tgb_object_frame* d_frames_sorted; /* [object_capacity] front-to-back */
+    u32*              d_visible_count; /* [1] */
+    u32*              h_visible_count; /* pinned */
+
+    tgb_svo_device svo;
+
+    cudaEvent_t ev[12];
+    f32         clear_ms, cull_ms, visibility_ms, svo_ms, shading_ms, merge_ms;
+    b32         ev_clear, ev_vis, ev_svo, ev_shade, ev_merge;
+    u32         n_visible_objects;
+    u32         n_kernel_launches;
+};
+
+#define TGB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            tgb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+            return TG_FALSE;                                                                        \
+        }                                                                                           \
+    } while (0)
+
+#define TGB_LAUNCH_CHECK(d)                                                                         \
+    do {                                                                                            \
+        (d)->n_kernel_launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess) {                                                                   \
+            tgb_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return TG_FALSE;                                                                        \
+        }                                                                                           \
+    } while (0)
+
+#endif

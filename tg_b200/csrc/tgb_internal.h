@@ -1,0 +1,80 @@
+/*
+ * tgb_internal.h -- the thin C-ABI seam between the C host code (tgb_host.c) and the CUDA
+ * translation units (tgb_device.cu, tgb_visibility.cu, tgb_shade.cu, tgb_svo.cu). Plain pointers
+ * and sizes only; the host side never sees a CUDA type.
+ */
+#ifndef TGB_INTERNAL_H
+#define TGB_INTERNAL_H
+
+#include "../../include/tg_raytracer.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* device buffer ids for tgbd_upload / tgbd_download */
+enum
+{
+    TGB_BUF_CLUSTER_POINTERS = 0, /* D3: u32[cluster_capacity] */
+    TGB_BUF_C2O,                  /* D4: u32[cluster_capacity] */
+    TGB_BUF_OBJECTS,              /* D5: tg_object_data[object_capacity] */
+    TGB_BUF_MASKS,                /* D1: 64 B per cluster idx */
+    TGB_BUF_LUT_IDX,              /* D2: 512 B per cluster idx */
+    TGB_BUF_COLOR_LUT,            /* D6: u32[n_luts * 256] */
+    TGB_BUF_VISIBILITY,           /* D7: u64[w*h] */
+    TGB_BUF_RADIANCE,             /* RGBA32F[w*h] */
+    TGB_BUF_SVO_NODES,
+    TGB_BUF_SVO_LEAF_DATA,
+    TGB_BUF_SVO_VOXELS,
+    TGB_BUF_COUNT
+};
+
+/* error recording (tgb_host.c) */
+void tgb_set_error(const char* p_fmt, ...);
+
+/* ---- tgb_device.cu ---- */
+i32   tgbd_device_count(void);
+struct tgb_device* tgbd_create(i32 device, u32 object_capacity, u32 cluster_capacity, u32 n_color_luts, u32 width, u32 height);
+void  tgbd_destroy(struct tgb_device* d);
+b32   tgbd_resize(struct tgb_device* d, u32 width, u32 height);
+b32   tgbd_upload(struct tgb_device* d, u32 buffer, u64 dst_offset_bytes, const void* p_src, u64 n_bytes);
+b32   tgbd_download(struct tgb_device* d, u32 buffer, u64 src_offset_bytes, void* p_dst, u64 n_bytes);
+/* device-to-device move inside one buffer (pointer-table compaction, tgvk_raytracer.c:1049-1056) */
+b32   tgbd_move(struct tgb_device* d, u32 buffer, u64 dst_offset_bytes, u64 src_offset_bytes, u64 n_bytes);
+void  tgbd_synchronize(struct tgb_device* d);
+void* tgbd_buffer(struct tgb_device* d, u32 buffer);
+void* tgbd_stream(struct tgb_device* d);
+void  tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out);
+void  tgbd_reset_launch_counter(struct tgb_device* d);
+void  tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base);
+
+/* reference material rule (8*rel_x + vx) % 256 for clusters [first_pointer, first_pointer+n) of an object (tgvk_raytracer.c:947-978) */
+b32   tgbd_fill_default_lut_idx(struct tgb_device* d, u32 first_pointer, u32 n_cluster_pointers, u32 nx);
+
+/* ---- tgb_visibility.cu ---- */
+b32   tgbd_clear(struct tgb_device* d);                                                              /* clear.comp */
+b32   tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, u32 object_capacity); /* cull + K1 */
+
+/* ---- tgb_shade.cu ---- */
+b32   tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p_cam, u32 gi_enabled, u32 frame_seed, u32 debug_visualization);
+
+/* ---- tgb_svo.cu ---- */
+b32   tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity);
+b32   tgbd_svo_update_objects(struct tgb_device* d, u32 n_moved, const u32* p_object_indices, const tg_object_data* p_old_records);
+b32   tgbd_svo_counts(struct tgb_device* d, u32* p_n_nodes, u32* p_n_leaves, u32* p_n_voxel_words, v3* p_min, v3* p_max);
+b32   tgbd_svo_set(struct tgb_device* d, v3 bmin, v3 bmax, u32 n_nodes, const void* p_nodes, u32 n_leaves, const void* p_leaf_data, u32 n_voxel_words, const void* p_voxels);
+
+/* ---- tgb_nccl.c ---- */
+b32   tgbn_unique_id(u8* p_out_128);
+void* tgbn_init(const u8* p_unique_id_128, u32 rank, u32 n_ranks);
+void  tgbn_destroy(void* p_comm);
+b32   tgbn_allreduce_min_u64(void* p_comm, void* p_device_buffer, u64 count, void* p_stream);
+/* events around the merge live in tgb_device.cu */
+void  tgbd_merge_begin(struct tgb_device* d);
+void  tgbd_merge_end(struct tgb_device* d);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

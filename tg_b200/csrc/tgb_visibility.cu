@@ -1,0 +1,508 @@
+/*
+ * tgb_visibility.cu -- K1, the compute-only visibility-buffer pass.
+ *
+ * Replaces the reference's rasterised cluster-box pass
+ *   clear            assets/shaders/raytracer/clear.comp:15-21
+ *   coverage         assets/shaders/raytracer/visibility.vert:19-26 + cluster_functions.inc:1-38
+ *                    (instanced draw of one box per cluster, tgvk_raytracer.c:1275-1317)
+ *   fragment         assets/shaders/raytracer/visibility.frag:22-208
+ * whose result is, per pixel, the 64-bit minimum over ALL clusters of the fragment function
+ * (coverage only prunes). Here rays are bound to screen tiles, objects are culled
+ * and ordered front to back once per frame (k_cull_objects / k_sort_frames), and every ray walks
+ * the cluster grid of each surviving object slice by slice along its dominant axis, visiting a
+ * CONSERVATIVE SUPERSET of the clusters whose own slab test can succeed. For each visited cluster
+ * the arithmetic that produces the written word is the reference's, operation for operation
+ * (tgb_hoist.h, tgb_math.h; this TU is compiled with -fmad=false); everything that merely selects
+ * candidates may be approximate because a superset yields the identical minimum.
+ * Early-outs compare the quantised 24-bit depth of an entry point with the best word so far and
+ * skip only on STRICTLY greater (a tie must still run: the lower pointer / voxel wins).
+ */
+#include "tgb_device.cuh"
+
+#define TGB_TILE_W        16
+#define TGB_TILE_H        16
+#define TGB_SORT_MAX      4096
+#define TGB_FULL_MASK     0xFFFFFFFFu
+
+/* ------------------------------------------------------------------------------------------- */
+/* clear.comp:19                                                                                */
+/* ------------------------------------------------------------------------------------------- */
+__global__ void k_clear_visibility(ulonglong2* __restrict__ p_vis2, u64 n_pairs, u64* __restrict__ p_vis, u64 n)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pairs) p_vis2[i] = make_ulonglong2(TG_VIS_CLEAR, TG_VIS_CLEAR);
+    if (i == 0 && (n & 1)) p_vis[n - 1] = TG_VIS_CLEAR;
+}
+
+extern "C" b32 tgbd_clear(struct tgb_device* d)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    const u64 n = (u64)d->width * d->height;
+    TGB_CUDA(cudaEventRecord(d->ev[0], d->stream));
+    k_clear_visibility<<<(u32)((n / 2 + 255) / 256) + 1, 256, 0, d->stream>>>((ulonglong2*)d->d_vis, n / 2, d->d_vis, n);
+    TGB_LAUNCH_CHECK(d);
+    TGB_CUDA(cudaEventRecord(d->ev[1], d->stream));
+    d->ev_clear = TG_TRUE;
+    return TG_TRUE;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Object culling: one thread per object slot                                                   */
+/* ------------------------------------------------------------------------------------------- */
+struct tgb_pinhole
+{
+    f64 inv[9];  /* inverse of [br-bl | tl-bl | bl], row-major */
+    f64 cam[3];
+    f64 rx[3], uy[3], fz[3]; /* orthonormal camera frame: right (bl->br), up (bl->tl), forward */
+    f64 c0, bx, by, lu, lv;  /* image-plane distance, bl in the frame, |br-bl|, |tl-bl| */
+    i32 ok;
+};
+
+static void tgb_pinhole_init(const tg_camera_rays* c, tgb_pinhole* p)
+{
+    const f64 bl[3] = { c->ray_bl.x, c->ray_bl.y, c->ray_bl.z };
+    const f64 u[3]  = { c->ray_br.x - bl[0], c->ray_br.y - bl[1], c->ray_br.z - bl[2] };
+    const f64 v[3]  = { c->ray_tl.x - bl[0], c->ray_tl.y - bl[1], c->ray_tl.z - bl[2] };
+    const f64 a = u[0], b = v[0], cc = bl[0];
+    const f64 d = u[1], e = v[1], f = bl[1];
+    const f64 g = u[2], h = v[2], i = bl[2];
+    const f64 det = a * (e * i - f * h) - b * (d * i - f * g) + cc * (d * h - e * g);
+    p->ok = det != 0.0;
+    const f64 id = p->ok ? 1.0 / det : 0.0;
+    p->inv[0] = (e * i - f * h) * id; p->inv[1] = (cc * h - b * i) * id; p->inv[2] = (b * f - cc * e) * id;
+    p->inv[3] = (f * g - d * i) * id; p->inv[4] = (a * i - cc * g) * id; p->inv[5] = (cc * d - a * f) * id;
+    p->inv[6] = (d * h - e * g) * id; p->inv[7] = (b * g - a * h) * id;  p->inv[8] = (a * e - b * d) * id;
+    p->cam[0] = c->camera.x; p->cam[1] = c->camera.y; p->cam[2] = c->camera.z;
+    p->lu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    p->lv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (!(p->lu > 0.0) || !(p->lv > 0.0)) { p->ok = 0; return; }
+    for (int k = 0; k < 3; k++) { p->rx[k] = u[k] / p->lu; p->uy[k] = v[k] / p->lv; }
+    p->fz[0] = p->rx[1] * p->uy[2] - p->rx[2] * p->uy[1];
+    p->fz[1] = p->rx[2] * p->uy[0] - p->rx[0] * p->uy[2];
+    p->fz[2] = p->rx[0] * p->uy[1] - p->rx[1] * p->uy[0];
+    f64 lf = sqrt(p->fz[0] * p->fz[0] + p->fz[1] * p->fz[1] + p->fz[2] * p->fz[2]);
+    if (!(lf > 0.0)) { p->ok = 0; return; }
+    p->c0 = (bl[0] * p->fz[0] + bl[1] * p->fz[1] + bl[2] * p->fz[2]) / lf;
+    if (p->c0 < 0.0) { lf = -lf; p->c0 = -p->c0; }
+    for (int k = 0; k < 3; k++) p->fz[k] /= lf;
+    p->bx = bl[0] * p->rx[0] + bl[1] * p->rx[1] + bl[2] * p->rx[2];
+    p->by = bl[0] * p->uy[0] + bl[1] * p->uy[1] + bl[2] * p->uy[2];
+    if (!(p->c0 > 0.0)) p->ok = 0;
+}
+
+/* Range of tan(angle) over a circle of radius r around (a, z) seen from the origin of that plane; a side is
+ * reported only when it is safely inside the forward half plane. */
+__device__ void tgb_tangent_bounds(f64 a, f64 z, f64 r, f64* p_lo, f64* p_hi, bool* p_lo_ok, bool* p_hi_ok)
+{
+    const f64 d2 = a * a + z * z;
+    *p_lo_ok = false; *p_hi_ok = false; *p_lo = 0.0; *p_hi = 0.0;
+    if (d2 <= r * r * 1.0001) return;
+    const f64 theta = atan2(a, z), alpha = asin(r / sqrt(d2));
+    const f64 lo = theta - alpha, hi = theta + alpha, lim = 1.5607963267948966; /* pi/2 - 0.01 */
+    if (lo > -lim && lo < lim) { *p_lo = tan(lo); *p_lo_ok = true; }
+    if (hi > -lim && hi < lim) { *p_hi = tan(hi); *p_hi_ok = true; }
+}
+
+__global__ void k_cull_objects(const tg_object_data* __restrict__ p_objects, u32 object_capacity, tg_camera_rays cam, tgb_pinhole pin,
+                               u32 w, u32 h, tgb_object_frame* __restrict__ p_frames, u32* __restrict__ p_count)
+{
+    const u32 object_idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (object_idx >= object_capacity) return;
+    const tg_object_data o = p_objects[object_idx];
+    /* tgvk_raytracer.c:1069-1077: initialised iff all dims != 0 */
+    if (o.n_cluster_pointers_per_dim.x == 0 || o.n_cluster_pointers_per_dim.y == 0 || o.n_cluster_pointers_per_dim.z == 0) return;
+
+    tgb_object_frame f;
+    const v3 camera = tgb_v3(cam.camera.x, cam.camera.y, cam.camera.z);
+    tgb_hoist_object(&o, camera, &f);
+    f.object_idx = object_idx;
+
+    const v3 og = tgb_hoist_cluster_origin(&f, 0, 0, 0);
+    f.og[0] = og.x; f.og[1] = og.y; f.og[2] = og.z;
+
+    const f32 ext[3] = { 8.0f * (f32)f.nx, 8.0f * (f32)f.ny, 8.0f * (f32)f.nz };
+    const f32 mag = fmaxf(fmaxf(fabsf(o.translation.x), fabsf(o.translation.y)), fabsf(o.translation.z))
+                  + fmaxf(fmaxf(fabsf(camera.x), fabsf(camera.y)), fabsf(camera.z))
+                  + fmaxf(fmaxf(ext[0], ext[1]), ext[2]);
+    f.eps = 0.03125f + 7.62939453125e-6f * mag; /* 2^-5 + 2^-17 * magnitude: >> accumulated rounding of either path */
+
+    /* distance from the camera to the (inflated) box, in the grid frame (rigid transform) */
+    f64 dist2 = 0.0;
+    for (int k = 0; k < 3; k++)
+    {
+        const f64 x = f.og[k];
+        const f64 lo = -(f64)f.eps, hi = (f64)ext[k] + (f64)f.eps;
+        const f64 dd = x < lo ? lo - x : (x > hi ? x - hi : 0.0);
+        dist2 += dd * dd;
+    }
+    const f64 dist = sqrt(dist2) * (1.0 - 1e-5) - 0.02;
+    const f64 far_plane = (f64)cam.far_plane;
+    if (dist > far_plane * (1.0 + 1e-5)) return; /* every hit would have d > 1 (visibility.frag:194) */
+    {
+        f64 q = dist <= 0.0 ? 0.0 : floor(dist / far_plane * 16777215.0) - 2.0;
+        if (q < 0.0) q = 0.0;
+        if (q > 16777215.0) q = 16777215.0;
+        f.min_depth24 = (u32)q;
+    }
+
+    /* conservative screen rectangle of the inflated box */
+    const f64 m = (f64)f.eps + 0.0625;
+    f64 minx = 1e300, miny = 1e300, maxx = -1e300, maxy = -1e300;
+    bool full = !pin.ok;
+    int n_behind = 0;
+    for (int k = 0; k < 8; k++)
+    {
+        const f64 lx = ((k & 1) ? (f64)ext[0] + m : -m) - (f64)f.half[0];
+        const f64 ly = ((k & 2) ? (f64)ext[1] + m : -m) - (f64)f.half[1];
+        const f64 lz = ((k & 4) ? (f64)ext[2] + m : -m) - (f64)f.half[2];
+        const f64 X = (f64)o.rotation.m00 * lx + (f64)o.rotation.m01 * ly + (f64)o.rotation.m02 * lz + (f64)o.translation.x - pin.cam[0];
+        const f64 Y = (f64)o.rotation.m10 * lx + (f64)o.rotation.m11 * ly + (f64)o.rotation.m12 * lz + (f64)o.translation.y - pin.cam[1];
+        const f64 Z = (f64)o.rotation.m20 * lx + (f64)o.rotation.m21 * ly + (f64)o.rotation.m22 * lz + (f64)o.translation.z - pin.cam[2];
+        const f64 a = pin.inv[0] * X + pin.inv[1] * Y + pin.inv[2] * Z;
+        const f64 b = pin.inv[3] * X + pin.inv[4] * Y + pin.inv[5] * Z;
+        const f64 c = pin.inv[6] * X + pin.inv[7] * Y + pin.inv[8] * Z;
+        const f64 len = fabs(X) + fabs(Y) + fabs(Z);
+        if (!(c > 1e-4 * len) || !(c > 1e-9))
+        {
+            full = true;
+            if (c < -1e-4 * len) n_behind++;
+            continue;
+        }
+        const f64 px = (a / c) * (f64)w - 0.5;
+        const f64 py = (1.0 - b / c) * (f64)h - 0.5;
+        minx = fmin(minx, px); maxx = fmax(maxx, px);
+        miny = fmin(miny, py); maxy = fmax(maxy, py);
+    }
+    if (n_behind == 8) return; /* entirely behind the image plane: exit <= 0 for every ray */
+    if (full)
+    {
+        /* some corner is beside / behind the eye: bound the projection of the bounding sphere instead */
+        f64 x0 = 0.0, y0 = 0.0, x1 = (f64)w - 1.0, y1 = (f64)h - 1.0;
+        if (pin.ok)
+        {
+            const f64 Cx = (f64)o.translation.x - pin.cam[0], Cy = (f64)o.translation.y - pin.cam[1], Cz = (f64)o.translation.z - pin.cam[2];
+            const f64 hx = (f64)f.half[0] + m, hy = (f64)f.half[1] + m, hz = (f64)f.half[2] + m;
+            const f64 r = sqrt(hx * hx + hy * hy + hz * hz) * (1.0 + 1e-6) + 1e-3;
+            const f64 X = Cx * pin.rx[0] + Cy * pin.rx[1] + Cz * pin.rx[2];
+            const f64 Y = Cx * pin.uy[0] + Cy * pin.uy[1] + Cz * pin.uy[2];
+            const f64 Z = Cx * pin.fz[0] + Cy * pin.fz[1] + Cz * pin.fz[2];
+            if (Z + r < 0.0) return;
+            f64 lo, hi; bool lo_ok, hi_ok;
+            tgb_tangent_bounds(X, Z, r, &lo, &hi, &lo_ok, &hi_ok);
+            if (lo_ok) x0 = fmax(x0, floor(((pin.c0 * lo - pin.bx) / pin.lu) * (f64)w - 0.5) - 2.0);
+            if (hi_ok) x1 = fmin(x1, ceil(((pin.c0 * hi - pin.bx) / pin.lu) * (f64)w - 0.5) + 2.0);
+            tgb_tangent_bounds(Y, Z, r, &lo, &hi, &lo_ok, &hi_ok);
+            if (hi_ok) y0 = fmax(y0, floor((1.0 - (pin.c0 * hi - pin.by) / pin.lv) * (f64)h - 0.5) - 2.0);
+            if (lo_ok) y1 = fmin(y1, ceil((1.0 - (pin.c0 * lo - pin.by) / pin.lv) * (f64)h - 0.5) + 2.0);
+        }
+        if (x1 < x0 || y1 < y0) return;
+        f.x0 = (i32)x0; f.y0 = (i32)y0; f.x1 = (i32)x1; f.y1 = (i32)y1;
+    }
+    else
+    {
+        minx = floor(minx) - 2.0; miny = floor(miny) - 2.0; maxx = ceil(maxx) + 2.0; maxy = ceil(maxy) + 2.0;
+        if (minx < 0.0) minx = 0.0;
+        if (miny < 0.0) miny = 0.0;
+        if (maxx > (f64)w - 1.0) maxx = (f64)w - 1.0;
+        if (maxy > (f64)h - 1.0) maxy = (f64)h - 1.0;
+        if (maxx < minx || maxy < miny) return;
+        f.x0 = (i32)minx; f.y0 = (i32)miny; f.x1 = (i32)maxx; f.y1 = (i32)maxy;
+    }
+
+    const u32 slot = atomicAdd(p_count, 1u);
+    p_frames[slot] = f;
+}
+
+/* Front-to-back order of the surviving objects: one CTA, bitonic sort of (min_depth24, object, slot) keys in shared memory. */
+__global__ void __launch_bounds__(1024) k_sort_frames(const tgb_object_frame* __restrict__ p_frames, tgb_object_frame* __restrict__ p_sorted, u32* __restrict__ p_count)
+{
+    __shared__ u64 s_keys[TGB_SORT_MAX];
+    const u32 n = p_count[0];
+    if (n > TGB_SORT_MAX)
+    {
+        /* too many survivors for the single-CTA sort: keep arrival order, K1 then must not break early */
+        const u32 n_words = n * (u32)(sizeof(tgb_object_frame) / 4);
+        const u32* p_src = (const u32*)p_frames;
+        u32* p_dst = (u32*)p_sorted;
+        for (u32 i = threadIdx.x; i < n_words; i += blockDim.x) p_dst[i] = p_src[i];
+        if (threadIdx.x == 0) p_count[1] = 0;
+        return;
+    }
+    u32 n_pow2 = 1;
+    while (n_pow2 < n) n_pow2 <<= 1;
+    for (u32 i = threadIdx.x; i < n_pow2; i += blockDim.x)
+    {
+        s_keys[i] = i < n ? (((u64)p_frames[i].min_depth24 << 40) | ((u64)p_frames[i].object_idx << 16) | (u64)i) : ~0ull;
+    }
+    __syncthreads();
+    for (u32 k = 2; k <= n_pow2; k <<= 1)
+    {
+        for (u32 j = k >> 1; j > 0; j >>= 1)
+        {
+            for (u32 i = threadIdx.x; i < n_pow2; i += blockDim.x)
+            {
+                const u32 ixj = i ^ j;
+                if (ixj > i)
+                {
+                    const u64 a = s_keys[i], b = s_keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const u32 words_per = (u32)(sizeof(tgb_object_frame) / 4);
+    const u32* p_src = (const u32*)p_frames;
+    u32* p_dst = (u32*)p_sorted;
+    for (u32 i = threadIdx.x; i < n * words_per; i += blockDim.x)
+    {
+        const u32 dst_obj = i / words_per, word = i % words_per;
+        const u32 slot = (u32)(s_keys[dst_obj] & 0xFFFFu);
+        p_dst[i] = p_src[slot * words_per + word];
+    }
+    if (threadIdx.x == 0) p_count[1] = 1;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* K1                                                                                           */
+/* ------------------------------------------------------------------------------------------- */
+
+/* visibility.frag:194-201 quantisation of a depth in [0,1] (or beyond) */
+__device__ __forceinline__ u64 tgb_depth24(f32 t, f32 far_plane)
+{
+    const f32 dq = tgb_max(0.0f, t / far_plane) * TG_VIS_DEPTH_SCALE;
+    return (u64)dq; /* cvt.rzi.u64.f32: truncation, saturating, NaN -> 0 */
+}
+
+/*
+ * One cluster, exactly visibility.frag:71-207 with the ray (o, d) in cluster space.
+ * `best` is the running per-pixel minimum.
+ */
+__device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, u32 cx, u32 cy, u32 cz, v3 d, f32 far_plane,
+                                                  const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
+                                                  u32 global_pointer_base, u64& best)
+{
+    const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
+    f32 enter, exit;
+    if (!tgb_ray_aabb(o, d, tgb_v3(0.0f, 0.0f, 0.0f), tgb_v3(8.0f, 8.0f, 8.0f), &enter, &exit)) return;
+    /* voxel_enter >= enter (same o, d, nested boxes, monotone rounding) => depth24(hit) >= depth24(enter) */
+    if (tgb_depth24(enter, far_plane) > (best >> TG_VIS_DEPTH_SHIFT)) return;
+
+    const u32 cluster_pointer = f.first_cluster_pointer + cx + f.nx * (cy + f.ny * cz);
+    const u32 cluster_idx = __ldg(&p_cluster_pointers[cluster_pointer]);
+    const uint2* __restrict__ p_slices = reinterpret_cast<const uint2*>(p_masks + (u64)cluster_idx * TG_CLUSTER_MASK_WORDS);
+
+    /* visibility.frag:83-137 */
+    v3 hit;
+    if (enter > 0.0f) { hit.x = o.x + enter * d.x; hit.y = o.y + enter * d.y; hit.z = o.z + enter * d.z; }
+    else              { hit = o; }
+    i32 x = (i32)tgb_clamp(floorf(hit.x), 0.0f, 8.0f - 1.0f);
+    i32 y = (i32)tgb_clamp(floorf(hit.y), 0.0f, 8.0f - 1.0f);
+    i32 z = (i32)tgb_clamp(floorf(hit.z), 0.0f, 8.0f - 1.0f);
+
+    i32 step_x = 0, step_y = 0, step_z = 0;
+    f32 t_max_x = TG_F32_MAX, t_max_y = TG_F32_MAX, t_max_z = TG_F32_MAX;
+    f32 t_delta_x = TG_F32_MAX, t_delta_y = TG_F32_MAX, t_delta_z = TG_F32_MAX;
+    if (d.x > 0.0f)      { step_x = 1;  t_max_x = enter + ((f32)(x + 1) - hit.x) / d.x; t_delta_x = 1.0f / d.x; }
+    else if (d.x < 0.0f) { step_x = -1; t_max_x = enter + (hit.x - (f32)x) / -d.x;      t_delta_x = 1.0f / -d.x; }
+    if (d.y > 0.0f)      { step_y = 1;  t_max_y = enter + ((f32)(y + 1) - hit.y) / d.y; t_delta_y = 1.0f / d.y; }
+    else if (d.y < 0.0f) { step_y = -1; t_max_y = enter + (hit.y - (f32)y) / -d.y;      t_delta_y = 1.0f / -d.y; }
+    if (d.z > 0.0f)      { step_z = 1;  t_max_z = enter + ((f32)(z + 1) - hit.z) / d.z; t_delta_z = 1.0f / d.z; }
+    else if (d.z < 0.0f) { step_z = -1; t_max_z = enter + (hit.z - (f32)z) / -d.z;      t_delta_z = 1.0f / -d.z; }
+
+    /* visibility.frag:141-191; the 64-bit z-slice (words 2z, 2z+1) is fetched once per z */
+    i32 z_cached = -1;
+    u32 lo = 0, hi = 0;
+    bool found = false;
+    for (;;)
+    {
+        if (z != z_cached)
+        {
+            const uint2 s = __ldg(&p_slices[z]);
+            lo = s.x; hi = s.y; z_cached = z;
+        }
+        const u32 word = (y & 4) ? hi : lo;
+        if ((word >> (((y & 3) << 3) + x)) & 1u) { found = true; break; }
+        if (t_max_x < t_max_y)
+        {
+            if (t_max_x < t_max_z) { t_max_x += t_delta_x; x += step_x; if (x < 0 || x >= 8) break; }
+            else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
+        }
+        else
+        {
+            if (t_max_y < t_max_z) { t_max_y += t_delta_y; y += step_y; if (y < 0 || y >= 8) break; }
+            else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
+        }
+    }
+    if (!found) return;
+
+    /* visibility.frag:151-157, 194-201 */
+    f32 voxel_enter, voxel_exit;
+    tgb_ray_aabb(o, d, tgb_v3((f32)x, (f32)y, (f32)z), tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)), &voxel_enter, &voxel_exit);
+    const f32 depth = tgb_max(0.0f, voxel_enter / far_plane);
+    if (depth <= 1.0f)
+    {
+        const u64 word = ((u64)(depth * TG_VIS_DEPTH_SCALE) << TG_VIS_DEPTH_SHIFT)
+                       | ((u64)(cluster_pointer + global_pointer_base) << TG_VIS_POINTER_SHIFT)
+                       | (u64)(u32)(64 * z + 8 * y + x);
+        if (word < best) best = word;
+    }
+}
+
+/*
+ * One ray against one object: enumerate, slice by slice along the dominant axis of d (front to
+ * back), every cluster whose box inflated by eps the ray can touch, and visit each.
+ */
+__device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 dir_ws, f32 far_plane,
+                                                 const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
+                                                 u32 global_pointer_base, u64& best)
+{
+    const v3 d = tgb_hoist_direction(&f, dir_ws); /* exact d_ms, shared by all clusters of the object */
+    const f32 e = f.eps;
+
+    /* permute so that axis k is the dominant one */
+    const f32 adx = fabsf(d.x), ady = fabsf(d.y), adz = fabsf(d.z);
+    const int k = (adx >= ady && adx >= adz) ? 0 : (ady >= adz ? 1 : 2);
+    const f32 dk = k == 0 ? d.x : (k == 1 ? d.y : d.z);
+    const f32 du = k == 0 ? d.y : (k == 1 ? d.z : d.x);
+    const f32 dv = k == 0 ? d.z : (k == 1 ? d.x : d.y);
+    const f32 ok = k == 0 ? f.og[0] : (k == 1 ? f.og[1] : f.og[2]);
+    const f32 ou = k == 0 ? f.og[1] : (k == 1 ? f.og[2] : f.og[0]);
+    const f32 ov = k == 0 ? f.og[2] : (k == 1 ? f.og[0] : f.og[1]);
+    const i32 nk = (i32)(k == 0 ? f.nx : (k == 1 ? f.ny : f.nz));
+    const i32 nu = (i32)(k == 0 ? f.ny : (k == 1 ? f.nz : f.nx));
+    const i32 nv = (i32)(k == 0 ? f.nz : (k == 1 ? f.nx : f.ny));
+    if (!(fabsf(dk) > 0.5f)) return; /* |d| == 1 => dominant component >= 0.577; false only for NaN directions */
+
+    /* conservative slab of the inflated object box; u / v slabs only when the ray is not parallel to them */
+    const f32 inv_dk = 1.0f / dk;
+    f32 t_in, t_out;
+    {
+        const f32 ta = (-e - ok) * inv_dk, tb = (8.0f * (f32)nk + e - ok) * inv_dk;
+        t_in = fminf(ta, tb); t_out = fmaxf(ta, tb);
+    }
+    if (fabsf(du) > 1e-20f)
+    {
+        const f32 inv = 1.0f / du;
+        const f32 ta = (-e - ou) * inv, tb = (8.0f * (f32)nu + e - ou) * inv;
+        t_in = fmaxf(t_in, fminf(ta, tb)); t_out = fminf(t_out, fmaxf(ta, tb));
+    }
+    else if (ou < -e || ou > 8.0f * (f32)nu + e) return;
+    if (fabsf(dv) > 1e-20f)
+    {
+        const f32 inv = 1.0f / dv;
+        const f32 ta = (-e - ov) * inv, tb = (8.0f * (f32)nv + e - ov) * inv;
+        t_in = fmaxf(t_in, fminf(ta, tb)); t_out = fminf(t_out, fmaxf(ta, tb));
+    }
+    else if (ov < -e || ov > 8.0f * (f32)nv + e) return;
+    /* slack: relative 2^-16 of |t| plus eps (positions move by at most |t|*2^-16 + eps) */
+    t_in  -= e + 1.52587890625e-5f * fabsf(t_in);
+    t_out += e + 1.52587890625e-5f * fabsf(t_out);
+    t_in = fmaxf(t_in, 0.0f);
+    if (!(t_in <= t_out)) return;
+
+    const f32 pk_in = ok + t_in * dk, pk_out = ok + t_out * dk;
+    const i32 sgn = dk > 0.0f ? 1 : -1;
+    i32 s     = (i32)floorf((pk_in  - (f32)sgn * (2.0f * e)) * 0.125f);
+    i32 s_end = (i32)floorf((pk_out + (f32)sgn * (2.0f * e)) * 0.125f);
+    s     = max(0, min(nk - 1, s));
+    s_end = max(0, min(nk - 1, s_end));
+
+    for (;; s += sgn)
+    {
+        const f32 ta = (8.0f * (f32)s - 2.0f * e - ok) * inv_dk, tb = (8.0f * (f32)(s + 1) + 2.0f * e - ok) * inv_dk;
+        const f32 t0 = fmaxf(fminf(ta, tb), t_in), t1 = fminf(fmaxf(ta, tb), t_out);
+        if (t0 <= t1)
+        {
+            /* slices are visited with non-decreasing t0: once even the slice entry is behind the best hit, stop */
+            if (best != TG_VIS_CLEAR)
+            {
+                const f32 t_lb = t0 - (4.0f * e + 3.0517578125e-5f * fabsf(t0));
+                if (tgb_depth24(t_lb, far_plane) > (best >> TG_VIS_DEPTH_SHIFT)) return;
+            }
+            const f32 ua = ou + t0 * du, ub = ou + t1 * du;
+            const f32 va = ov + t0 * dv, vb = ov + t1 * dv;
+            const f32 pad = 2.0f * e + 3.0517578125e-5f * (fabsf(ou) + fabsf(ov) + t1);
+            const i32 cu0 = max(0,      (i32)floorf((fminf(ua, ub) - pad) * 0.125f));
+            const i32 cu1 = min(nu - 1, (i32)floorf((fmaxf(ua, ub) + pad) * 0.125f));
+            const i32 cv0 = max(0,      (i32)floorf((fminf(va, vb) - pad) * 0.125f));
+            const i32 cv1 = min(nv - 1, (i32)floorf((fmaxf(va, vb) + pad) * 0.125f));
+            for (i32 cv = cv0; cv <= cv1; cv++)
+            {
+                for (i32 cu = cu0; cu <= cu1; cu++)
+                {
+                    const u32 cx = (u32)(k == 0 ? s : (k == 1 ? cv : cu));
+                    const u32 cy = (u32)(k == 0 ? cu : (k == 1 ? s : cv));
+                    const u32 cz = (u32)(k == 0 ? cv : (k == 1 ? cu : s));
+                    tgb_visit_cluster(f, cx, cy, cz, d, far_plane, p_cluster_pointers, p_masks, global_pointer_base, best);
+                }
+            }
+        }
+        if (s == s_end) break;
+    }
+}
+
+/*
+ * One CTA = one 16x16 pixel tile, one warp = one 8x4 pixel block (coherent rays), one lane = one
+ * ray. Objects arrive front to back; a lane retires from the object loop once the next object's
+ * lower depth bound exceeds its best word, a warp once all its lanes did. The resolve is a single
+ * 64-bit atomicMin per hit pixel (visibility.frag:206) so that other passes / shards may target
+ * the same buffer.
+ */
+__global__ void __launch_bounds__(256) k_visibility(const tgb_object_frame* __restrict__ p_frames, const u32* __restrict__ p_count,
+                                                     tg_camera_rays cam, u32 w, u32 h,
+                                                     const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
+                                                     u32 global_pointer_base, u64* __restrict__ p_vis)
+{
+    const u32 n_visible = p_count[0];
+    if (n_visible == 0) return;
+    const bool sorted = p_count[1] != 0;
+
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 wx0 = blockIdx.x * TGB_TILE_W + (warp & 1u) * 8u;
+    const u32 wy0 = blockIdx.y * TGB_TILE_H + (warp >> 1) * 4u;
+    if (wx0 >= w || wy0 >= h) return; /* warp-uniform */
+    const u32 px = wx0 + (lane & 7u), py = wy0 + (lane >> 3);
+    const bool in_screen = px < w && py < h;
+    const i32 wx1 = (i32)min(wx0 + 7u, w - 1u), wy1 = (i32)min(wy0 + 3u, h - 1u);
+
+    const v3 dir_ws = tgb_pixel_direction(&cam, w, h, in_screen ? px : wx0, in_screen ? py : wy0);
+    u64 best = TG_VIS_CLEAR;
+
+    for (u32 i = 0; i < n_visible; i++)
+    {
+        const tgb_object_frame& f = p_frames[i];
+        const bool behind_best = !in_screen || (u64)f.min_depth24 > (best >> TG_VIS_DEPTH_SHIFT);
+        if (sorted && __all_sync(TGB_FULL_MASK, behind_best)) break;
+        if (f.x1 < (i32)wx0 || f.x0 > wx1 || f.y1 < (i32)wy0 || f.y0 > wy1) continue; /* warp-uniform */
+        if (behind_best || (i32)px < f.x0 || (i32)px > f.x1 || (i32)py < f.y0 || (i32)py > f.y1) continue;
+        tgb_trace_object(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best);
+    }
+
+    if (in_screen && best != TG_VIS_CLEAR) atomicMin((unsigned long long*)&p_vis[(u64)py * w + px], (unsigned long long)best);
+}
+
+extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, u32 object_capacity)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    tgb_pinhole pin;
+    tgb_pinhole_init(p_cam, &pin);
+
+    TGB_CUDA(cudaEventRecord(d->ev[2], d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_visible_count, 0, 4 * sizeof(u32), d->stream));
+    k_cull_objects<<<(object_capacity + 127) / 128, 128, 0, d->stream>>>(d->d_objects, object_capacity, *p_cam, pin, d->width, d->height, d->d_frames, d->d_visible_count);
+    TGB_LAUNCH_CHECK(d);
+    k_sort_frames<<<1, 1024, 0, d->stream>>>(d->d_frames, d->d_frames_sorted, d->d_visible_count);
+    TGB_LAUNCH_CHECK(d);
+    TGB_CUDA(cudaEventRecord(d->ev[3], d->stream));
+
+    const dim3 grid((d->width + TGB_TILE_W - 1) / TGB_TILE_W, (d->height + TGB_TILE_H - 1) / TGB_TILE_H);
+    k_visibility<<<grid, 256, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height,
+                                              d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis);
+    TGB_LAUNCH_CHECK(d);
+    TGB_CUDA(cudaEventRecord(d->ev[4], d->stream));
+    TGB_CUDA(cudaMemcpyAsync(d->h_visible_count, d->d_visible_count, 2 * sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
+    d->ev_vis = TG_TRUE;
+    return TG_TRUE;
+}

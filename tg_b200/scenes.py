@@ -174,7 +174,7 @@ def small_grid(grid=3, width=320, height=180, k=3, dims=(4, 2, 4)):
     return s
 
 
-def flat_arrays(scene, global_pointer_base=0):
+def flat_arrays(scene, global_pointer_base=0, with_lut=True):
     """Fresh-scene flat arrays (cluster idx == cluster pointer, tgvk_raytracer.c:704-712): dict of numpy arrays
     objects[VOXEL_OBJECT_DTYPE], cluster_pointers, c2o, masks [n,16], lut_idx [n,512], color_lut [n_luts*256]."""
     from .ctypes_defs import VOXEL_OBJECT_DTYPE
@@ -189,7 +189,8 @@ def flat_arrays(scene, global_pointer_base=0):
         objects[oi]["angle_in_radians"] = o.angle
         objects[oi]["axis"] = o.axis
         masks.append(o.bits)
-        luts.append(o.lut_indices if o.lut_indices is not None else default_lut_indices(o.dims))
+        if with_lut:
+            luts.append(o.lut_indices if o.lut_indices is not None else default_lut_indices(o.dims))
         c2o.append(np.full(o.n_clusters, oi, dtype=np.uint32))
         first += o.n_clusters
     from .ctypes_defs import TG_U32_MAX  # noqa: F401
@@ -198,7 +199,7 @@ def flat_arrays(scene, global_pointer_base=0):
         color_lut[i] = pack_color(r, g, b)
     return dict(objects=objects, object_lut_idx=np.array([o.lut_idx for o in scene.objects], dtype=np.uint32),
                 cluster_pointers=np.arange(first, dtype=np.uint32), c2o=np.concatenate(c2o),
-                masks=np.ascontiguousarray(np.concatenate(masks)), lut_idx=np.ascontiguousarray(np.concatenate(luts)),
+                masks=np.ascontiguousarray(np.concatenate(masks)), lut_idx=np.ascontiguousarray(np.concatenate(luts)) if with_lut else None,
                 color_lut=color_lut, global_pointer_base=global_pointer_base)
 
 
