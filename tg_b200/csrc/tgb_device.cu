@@ -27,6 +27,7 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMalloc(&d->d_color_lut, (u64)d->n_color_luts * 256 * sizeof(u32)));
     TGB_CUDA(cudaMalloc(&d->d_frames, no * sizeof(tgb_object_frame)));
     TGB_CUDA(cudaMalloc(&d->d_frames_sorted, no * sizeof(tgb_object_frame)));
+    TGB_CUDA(cudaMalloc(&d->d_frames_all, no * sizeof(tgb_object_frame)));
     TGB_CUDA(cudaMalloc(&d->d_visible_count, 4 * sizeof(u32)));
     TGB_CUDA(cudaMallocHost(&d->h_visible_count, 4 * sizeof(u32)));
     TGB_CUDA(cudaMemsetAsync(d->d_cluster_pointers, 0, nc * sizeof(u32), d->stream));
@@ -36,10 +37,14 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMemsetAsync(d->d_color_lut, 0, (u64)d->n_color_luts * 256 * sizeof(u32), d->stream));
     for (int i = 0; i < 12; i++) TGB_CUDA(cudaEventCreate(&d->ev[i]));
 
-    /* SVO capacities: tg_sparse_voxel_octree.c:479-484 */
-    d->svo.node_capacity = 1u << 14;
-    d->svo.leaf_capacity = 1u << 13;
-    d->svo.voxel_word_capacity = 1u << 21;
+    /*
+     * SVO capacities. The reference reserves 2^14 nodes, 2^13 leaf records and 2^21 voxel words = 2048 blocks
+     * (tg_sparse_voxel_octree.c:479-484) and asserts beyond; a 1024^3 box of 32^3 blocks can hold 37,449 nodes and
+     * 32,768 leaves, which is 137 MB of a 180 GB HBM: reserve the worst case so a build can never overflow (Q12).
+     */
+    d->svo.node_capacity = 1u << 16;
+    d->svo.leaf_capacity = 1u << 15;
+    d->svo.voxel_word_capacity = 1u << 25;
     TGB_CUDA(cudaMalloc(&d->svo.d_nodes, (u64)d->svo.node_capacity * 4));
     TGB_CUDA(cudaMalloc(&d->svo.d_leaf_data, (u64)d->svo.leaf_capacity * 65 * 4));
     TGB_CUDA(cudaMalloc(&d->svo.d_voxels, (u64)d->svo.voxel_word_capacity * 4));
@@ -111,10 +116,10 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaStreamSynchronize(d->stream);
     cudaFree(d->d_cluster_pointers); cudaFree(d->d_c2o); cudaFree(d->d_objects); cudaFree(d->d_masks);
     cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance);
-    cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_visible_count);
+    cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
     cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts);
-    cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch);
+    cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch); cudaFree(d->svo.d_pair_flags); cudaFree(d->svo.d_object_flags);
     for (int i = 0; i < 12; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     cudaStreamDestroy(d->stream);
     cudaGetLastError();

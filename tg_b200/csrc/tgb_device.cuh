@@ -22,14 +22,16 @@ struct tgb_svo_device
     u32* d_leaf_data;   /* 65 u32 per leaf */
     u32* d_voxels;      /* 1024 u32 per leaf */
     u32* d_counts;      /* [0] nodes, [1] leaves, [2] overflow flag */
-    u32  n_nodes, n_leaves;
+    u32  n_nodes, n_leaves, n_pairs;
     b32  valid;
-    /* build scratch (grown on demand) */
-    u32* d_pairs_a;     /* (node, cluster pointer) pairs, ping */
-    u32* d_pairs_b;     /* pong */
+    /* build scratch */
+    u32* d_pairs_a;     /* cluster pointers grouped by leaf (segments in dense-leaf order), grown on demand */
+    u32* d_pairs_b;     /* previous build's pairs (incremental update) */
+    u8*  d_pair_flags;  /* per pair: the cluster set at least one bit of the leaf */
     u64  pair_capacity;
-    u32* d_scratch;     /* scan / flags */
+    u32* d_scratch;     /* dense-tree arrays, see tgb_svo.cu */
     u64  scratch_capacity;
+    u32* d_object_flags; /* [object_capacity] object can touch the SVO box */
 };
 
 struct tgb_device
@@ -50,6 +52,7 @@ struct tgb_device
 
     tgb_object_frame* d_frames;        /* [object_capacity] compacted visible objects */
     tgb_object_frame* d_frames_sorted; /* [object_capacity] front-to-back */
+    tgb_object_frame* d_frames_all;    /* [object_capacity] indexed by object idx (K3) */
     u32*              d_visible_count; /* [1] */
     u32*              h_visible_count; /* pinned */
 

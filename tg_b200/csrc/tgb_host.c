@@ -421,7 +421,8 @@ void tgb200_render_shading(tg_raytracer* p_raytracer)
     if (!tgb__alive(p_raytracer, "tgb200_render_shading")) return;
     tg_camera_rays cam;
     tgb200_camera_rays(p_raytracer->p_camera, &cam);
-    tgbd_render_shading(p_raytracer->p_device, &cam, p_raytracer->gi_enabled, p_raytracer->frame_seed, p_raytracer->debug_visualization);
+    tgbd_render_shading(p_raytracer->p_device, &cam, p_raytracer->scene.n_cluster_pointers, p_raytracer->gi_enabled, p_raytracer->frame_seed,
+                        p_raytracer->debug_visualization, 0, p_raytracer->height);
 }
 
 void tg_raytracer_render(tg_raytracer* p_raytracer)

@@ -56,7 +56,8 @@ b32   tgbd_clear(struct tgb_device* d);                                         
 b32   tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, u32 object_capacity); /* cull + K1 */
 
 /* ---- tgb_shade.cu ---- */
-b32   tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p_cam, u32 gi_enabled, u32 frame_seed, u32 debug_visualization);
+/* rows [y0, y1) only (multi-GPU: this rank's screen tile); pointers outside [base, base + n_local_pointers) shade to 0 */
+b32   tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p_cam, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1);
 
 /* ---- tgb_svo.cu ---- */
 b32   tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity);
