@@ -158,6 +158,13 @@ TG_EXPORT void tgb200_comm_init(tg_raytracer* p_raytracer, const u8* p_unique_id
 TG_EXPORT void tgb200_comm_destroy(tg_raytracer* p_raytracer);
 /* ncclAllReduce(ncclUint64, ncclMin) over the visibility buffer, in place. */
 TG_EXPORT void tgb200_merge_visibility(tg_raytracer* p_raytracer);
+/* Rows [first, one_past_last) of the frame this rank shades (GI rays are split by screen tile); the whole frame on one GPU. */
+TG_EXPORT void tgb200_tile_rows(tg_raytracer* p_raytracer, u32* p_first_row, u32* p_one_past_last_row);
+/* ncclAllGather of the radiance tiles: afterwards every rank holds the full frame (optional; collective). */
+TG_EXPORT void tgb200_gather_radiance(tg_raytracer* p_raytracer);
+/* Marks the replicated SVO stale on a rank that does not own the object another rank moved (scene edits are mirrored
+ * on every rank in lock-step; the next render() / tgb200_svo_update() rebuilds collectively). */
+TG_EXPORT void tgb200_mark_svo_dirty(tg_raytracer* p_raytracer);
 
 /* ---- pure host logic, usable without a GPU (scene bookkeeping, camera) ---------------------- */
 

@@ -62,6 +62,9 @@ SYMBOLS = {
     "tgb200_comm_init": (None, [_RT, _P(T.u8), T.u32, T.u32]),
     "tgb200_comm_destroy": (None, [_RT]),
     "tgb200_merge_visibility": (None, [_RT]),
+    "tgb200_tile_rows": (None, [_RT, _P(T.u32), _P(T.u32)]),
+    "tgb200_gather_radiance": (None, [_RT]),
+    "tgb200_mark_svo_dirty": (None, [_RT]),
     "tgb200_scene_init": (None, [_P(T.tg_scene), T.u32, T.u32]),
     "tgb200_scene_free": (None, [_P(T.tg_scene)]),
     "tgb200_scene_alloc_object": (T.u32, [_P(T.tg_scene), T.v3, T.v3u, T.f32, T.v3]),

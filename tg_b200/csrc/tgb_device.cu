@@ -29,6 +29,12 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMalloc(&d->d_frames_sorted, no * sizeof(tgb_object_frame)));
     TGB_CUDA(cudaMalloc(&d->d_frames_all, no * sizeof(tgb_object_frame)));
     TGB_CUDA(cudaMalloc(&d->d_visible_count, 4 * sizeof(u32)));
+    TGB_CUDA(cudaMalloc(&d->d_gi_count, 4 * sizeof(u32)));
+    {
+        int n_sms = 0;
+        TGB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, d->device));
+        d->n_sms = (u32)(n_sms > 0 ? n_sms : 148);
+    }
     TGB_CUDA(cudaMallocHost(&d->h_visible_count, 4 * sizeof(u32)));
     TGB_CUDA(cudaMemsetAsync(d->d_cluster_pointers, 0, nc * sizeof(u32), d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_c2o, 0, nc * sizeof(u32), d->stream));
@@ -56,16 +62,35 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
 {
     TGB_CUDA(cudaSetDevice(d->device));
     TGB_CUDA(cudaStreamSynchronize(d->stream));
+    if (d->n_ranks == 0) d->n_ranks = 1;
+    d->tile_rows = (height + d->n_ranks - 1) / d->n_ranks;
+    const u64 padded_px = (u64)width * d->tile_rows * d->n_ranks; /* >= width * height: equal tiles for the collectives */
+    if (d->d_mat) TGB_CUDA(cudaFree(d->d_mat));
+    if (d->d_mat_tile) TGB_CUDA(cudaFree(d->d_mat_tile));
+    d->d_mat = NULL; d->d_mat_tile = NULL;
+    if (d->n_ranks > 1)
+    {
+        TGB_CUDA(cudaMalloc(&d->d_mat, padded_px * sizeof(u64)));
+        TGB_CUDA(cudaMalloc(&d->d_mat_tile, (u64)width * d->tile_rows * sizeof(u64)));
+        TGB_CUDA(cudaMemsetAsync(d->d_mat, 0, padded_px * sizeof(u64), d->stream));
+    }
     if (d->d_vis) TGB_CUDA(cudaFree(d->d_vis));
     if (d->d_radiance) TGB_CUDA(cudaFree(d->d_radiance));
+    if (d->d_gi_q0) TGB_CUDA(cudaFree(d->d_gi_q0));
+    if (d->d_gi_q1) TGB_CUDA(cudaFree(d->d_gi_q1));
+    if (d->d_gi_q2) TGB_CUDA(cudaFree(d->d_gi_q2));
     d->d_vis = NULL;
     d->d_radiance = NULL;
+    d->d_gi_q0 = d->d_gi_q1 = d->d_gi_q2 = NULL;
     d->width = width;
     d->height = height;
     TGB_CUDA(cudaMalloc(&d->d_vis, (u64)width * height * sizeof(u64)));
-    TGB_CUDA(cudaMalloc(&d->d_radiance, (u64)width * height * sizeof(float4)));
+    TGB_CUDA(cudaMalloc(&d->d_radiance, padded_px * sizeof(float4)));
+    TGB_CUDA(cudaMalloc(&d->d_gi_q0, (u64)width * height * sizeof(float4)));
+    TGB_CUDA(cudaMalloc(&d->d_gi_q1, (u64)width * height * sizeof(float4)));
+    TGB_CUDA(cudaMalloc(&d->d_gi_q2, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMemsetAsync(d->d_vis, 0xFF, (u64)width * height * sizeof(u64), d->stream));
-    TGB_CUDA(cudaMemsetAsync(d->d_radiance, 0, (u64)width * height * sizeof(float4), d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_radiance, 0, padded_px * sizeof(float4), d->stream));
     return TG_TRUE;
 }
 
@@ -91,6 +116,7 @@ extern "C" struct tgb_device* tgbd_create(i32 device, u32 object_capacity, u32 c
     }
     struct tgb_device* d = (struct tgb_device*)calloc(1, sizeof(*d));
     d->device = device;
+    d->n_ranks = 1;
     d->object_capacity = object_capacity;
     d->cluster_capacity = cluster_capacity;
     d->n_color_luts = n_color_luts ? n_color_luts : 1;
@@ -115,11 +141,12 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaSetDevice(d->device);
     cudaStreamSynchronize(d->stream);
     cudaFree(d->d_cluster_pointers); cudaFree(d->d_c2o); cudaFree(d->d_objects); cudaFree(d->d_masks);
-    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance);
+    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_count);
     cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
     cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts);
-    cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch); cudaFree(d->svo.d_pair_flags); cudaFree(d->svo.d_object_flags);
+    cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch); cudaFree(d->svo.d_pair_flags); cudaFree(d->svo.d_object_flags); cudaFree(d->svo.d_part); cudaFree(d->svo.d_gather);
+    cudaFree(d->d_mat); cudaFree(d->d_mat_tile); cudaFree(d->d_objects_global); cudaFree(d->d_frames_global);
     for (int i = 0; i < 12; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     cudaStreamDestroy(d->stream);
     cudaGetLastError();
@@ -138,7 +165,7 @@ static b32 tgbd__buffer_range(struct tgb_device* d, u32 buffer, u8** pp, u64* p_
     case TGB_BUF_LUT_IDX:          *pp = (u8*)d->d_lut_idx;          *p_size = nc * 512; break;
     case TGB_BUF_COLOR_LUT:        *pp = (u8*)d->d_color_lut;        *p_size = (u64)d->n_color_luts * 1024; break;
     case TGB_BUF_VISIBILITY:       *pp = (u8*)d->d_vis;              *p_size = px * 8; break;
-    case TGB_BUF_RADIANCE:         *pp = (u8*)d->d_radiance;         *p_size = px * 16; break;
+    case TGB_BUF_RADIANCE:         *pp = (u8*)d->d_radiance;         *p_size = (u64)d->width * d->tile_rows * d->n_ranks * 16; break;
     case TGB_BUF_SVO_NODES:        *pp = (u8*)d->svo.d_nodes;        *p_size = (u64)d->svo.node_capacity * 4; break;
     case TGB_BUF_SVO_LEAF_DATA:    *pp = (u8*)d->svo.d_leaf_data;    *p_size = (u64)d->svo.leaf_capacity * 260; break;
     case TGB_BUF_SVO_VOXELS:       *pp = (u8*)d->svo.d_voxels;       *p_size = (u64)d->svo.voxel_word_capacity * 4; break;
@@ -203,6 +230,29 @@ extern "C" void tgbd_synchronize(struct tgb_device* d)
 }
 
 extern "C" void tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base) { d->global_pointer_base = global_pointer_base; }
+
+extern "C" b32 tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n_ranks)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    d->p_comm = p_comm;
+    d->rank = p_comm ? rank : 0;
+    d->n_ranks = p_comm ? n_ranks : 1;
+    if (d->d_objects_global) TGB_CUDA(cudaFree(d->d_objects_global));
+    if (d->d_frames_global) TGB_CUDA(cudaFree(d->d_frames_global));
+    d->d_objects_global = NULL; d->d_frames_global = NULL;
+    if (d->n_ranks > 1)
+    {
+        TGB_CUDA(cudaMalloc(&d->d_objects_global, (u64)d->n_ranks * d->object_capacity * sizeof(tg_object_data)));
+        TGB_CUDA(cudaMalloc(&d->d_frames_global, (u64)d->n_ranks * d->object_capacity * sizeof(tgb_object_frame)));
+    }
+    return tgbd_resize(d, d->width, d->height); /* tile-sized buffers depend on n_ranks */
+}
+
+extern "C" u32 tgbd_tile_rows(struct tgb_device* d) { return d->tile_rows; }
+extern "C" void* tgbd_comm(struct tgb_device* d) { return d->p_comm; }
+extern "C" u32 tgbd_rank(struct tgb_device* d) { return d->rank; }
+extern "C" u32 tgbd_n_ranks(struct tgb_device* d) { return d->n_ranks ? d->n_ranks : 1; }
 
 extern "C" void tgbd_reset_launch_counter(struct tgb_device* d) { d->n_kernel_launches = 0; }
 

@@ -32,6 +32,10 @@ struct tgb_svo_device
     u32* d_scratch;     /* dense-tree arrays, see tgb_svo.cu */
     u64  scratch_capacity;
     u32* d_object_flags; /* [object_capacity] object can touch the SVO box */
+    /* sharded build: this rank's contribution per leaf (voxels | leaf records) and the all-gathered copies of every rank */
+    u32* d_part;
+    u32* d_gather;
+    u64  part_capacity_leaves, gather_capacity_leaves;
 };
 
 struct tgb_device
@@ -49,6 +53,20 @@ struct tgb_device
     u32*            d_color_lut;
     u64*            d_vis;
     float4*         d_radiance;
+    float4*         d_gi_q0;      /* secondary-ray queue, [w*h] each: origin.xyz + pixel | direction | ambient */
+    float4*         d_gi_q1;
+    float4*         d_gi_q2;
+    u32*            d_gi_count;   /* [0] queued, [1] fetched */
+    u32             n_sms;
+
+    /* multi-GPU (one process per GPU): clusters sharded by object, SVO / objects replicated, GI split by screen tile */
+    void*             p_comm;           /* NCCL communicator or NULL */
+    u32               rank, n_ranks;
+    u32               tile_rows;        /* ceil(height / n_ranks): rank r shades rows [r * tile_rows, (r + 1) * tile_rows) */
+    u64*              d_mat;            /* [w * tile_rows * n_ranks] owner-resolved material words: global object idx << 32 | packed colour */
+    u64*              d_mat_tile;       /* [w * tile_rows] this rank's tile after the reduce-scatter */
+    tg_object_data*   d_objects_global; /* [n_ranks * object_capacity] every rank's records, pointers globalised */
+    tgb_object_frame* d_frames_global;
 
     tgb_object_frame* d_frames;        /* [object_capacity] compacted visible objects */
     tgb_object_frame* d_frames_sorted; /* [object_capacity] front-to-back */

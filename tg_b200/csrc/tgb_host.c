@@ -35,6 +35,7 @@ void tgb200_clear_error(void) { tgb__has_error = TG_FALSE; tgb__error[0] = 0; }
 #define TGB_VOID
 
 static i32 tgb__device = 0;
+
 static u32 tgb__default_w = 1920, tgb__default_h = 1080;
 
 i32  tgb200_device_count(void) { return tgbd_device_count(); }
@@ -421,6 +422,13 @@ void tgb200_render_shading(tg_raytracer* p_raytracer)
     if (!tgb__alive(p_raytracer, "tgb200_render_shading")) return;
     tg_camera_rays cam;
     tgb200_camera_rays(p_raytracer->p_camera, &cam);
+    if (tgbd_n_ranks(p_raytracer->p_device) > 1)
+    {
+        /* multi-GPU: the buffer must be the MERGED one (tgb200_merge_visibility); this rank shades its screen tile */
+        tgbd_render_shading_sharded(p_raytracer->p_device, &cam, p_raytracer->scene.n_cluster_pointers, p_raytracer->gi_enabled, p_raytracer->frame_seed,
+                                    p_raytracer->debug_visualization);
+        return;
+    }
     tgbd_render_shading(p_raytracer->p_device, &cam, p_raytracer->scene.n_cluster_pointers, p_raytracer->gi_enabled, p_raytracer->frame_seed,
                         p_raytracer->debug_visualization, 0, p_raytracer->height);
 }
@@ -432,6 +440,7 @@ void tg_raytracer_render(tg_raytracer* p_raytracer)
     /* tgvk_raytracer.c:1187-1217 builds the SVO on the first frame; here whenever it is stale and GI needs it */
     if (p_raytracer->gi_enabled) tgb200_svo_update(p_raytracer, TG_FALSE);
     tgb200_render_visibility(p_raytracer);
+    if (tgbd_n_ranks(p_raytracer->p_device) > 1) tgb200_merge_visibility(p_raytracer); /* ncclAllReduce(u64, min) over NVLink */
     tgb200_render_shading(p_raytracer);
 }
 
@@ -564,7 +573,7 @@ void tg_svo_destroy(tg_svo* p_svo)
 
 /* ---- multi-GPU ---------------------------------------------------------------------------------- */
 
-static void* tgb__comm = NULL; /* one communicator per process (one process per GPU) */
+
 
 void tgb200_set_shard(tg_raytracer* p_raytracer, u32 rank, u32 n_ranks, u32 global_pointer_base)
 {
@@ -576,24 +585,53 @@ void tgb200_set_shard(tg_raytracer* p_raytracer, u32 rank, u32 n_ranks, u32 glob
 
 void tgb200_comm_unique_id(u8* p_out_128) { tgbn_unique_id(p_out_128); }
 
+/* the communicator belongs to the raytracer that joined it (one process per GPU, one sharded raytracer per process) */
 void tgb200_comm_init(tg_raytracer* p_raytracer, const u8* p_unique_id_128, u32 rank, u32 n_ranks)
 {
     if (!tgb__alive(p_raytracer, "tgb200_comm_init")) return;
-    if (tgb__comm) { tgbn_destroy(tgb__comm); tgb__comm = NULL; }
-    tgb__comm = tgbn_init(p_unique_id_128, rank, n_ranks);
+    TGB_REQUIRE(rank < n_ranks, TGB_VOID, "tgb200_comm_init: rank %u >= n_ranks %u", rank, n_ranks);
+    tgb200_comm_destroy(p_raytracer);
+    void* p_comm = tgbn_init(p_unique_id_128, rank, n_ranks);
+    if (p_comm) tgbd_set_comm(p_raytracer->p_device, p_comm, rank, n_ranks);
 }
 
 void tgb200_comm_destroy(tg_raytracer* p_raytracer)
 {
-    (void)p_raytracer;
-    if (tgb__comm) { tgbn_destroy(tgb__comm); tgb__comm = NULL; }
+    if (!p_raytracer || !p_raytracer->p_device) return;
+    void* p_comm = tgbd_comm(p_raytracer->p_device);
+    if (!p_comm) return;
+    tgbd_set_comm(p_raytracer->p_device, NULL, 0, 1);
+    tgbn_destroy(p_comm);
+}
+
+void tgb200_mark_svo_dirty(tg_raytracer* p_raytracer)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_mark_svo_dirty")) return;
+    p_raytracer->svo_dirty = 1;
+}
+
+void tgb200_gather_radiance(tg_raytracer* p_raytracer)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_gather_radiance")) return;
+    tgbd_gather_radiance(p_raytracer->p_device);
+}
+
+void tgb200_tile_rows(tg_raytracer* p_raytracer, u32* p_first_row, u32* p_one_past_last_row)
+{
+    *p_first_row = 0; *p_one_past_last_row = 0;
+    if (!tgb__alive(p_raytracer, "tgb200_tile_rows")) return;
+    const u32 rows = tgbd_tile_rows(p_raytracer->p_device);
+    const u32 y0 = tgbd_rank(p_raytracer->p_device) * rows, y1 = y0 + rows;
+    *p_first_row = y0 < p_raytracer->height ? y0 : p_raytracer->height;
+    *p_one_past_last_row = y1 < p_raytracer->height ? y1 : p_raytracer->height;
 }
 
 void tgb200_merge_visibility(tg_raytracer* p_raytracer)
 {
     if (!tgb__alive(p_raytracer, "tgb200_merge_visibility")) return;
-    TGB_REQUIRE(tgb__comm != NULL, TGB_VOID, "tgb200_merge_visibility: no communicator (call tgb200_comm_init)");
+    void* p_comm = tgbd_comm(p_raytracer->p_device);
+    TGB_REQUIRE(p_comm != NULL, TGB_VOID, "tgb200_merge_visibility: no communicator (call tgb200_comm_init)");
     tgbd_merge_begin(p_raytracer->p_device);
-    tgbn_allreduce_min_u64(tgb__comm, tgbd_buffer(p_raytracer->p_device, TGB_BUF_VISIBILITY), (u64)p_raytracer->width * p_raytracer->height, tgbd_stream(p_raytracer->p_device));
+    tgbn_allreduce_min_u64(p_comm, tgbd_buffer(p_raytracer->p_device, TGB_BUF_VISIBILITY), (u64)p_raytracer->width * p_raytracer->height, tgbd_stream(p_raytracer->p_device));
     tgbd_merge_end(p_raytracer->p_device);
 }

@@ -47,6 +47,11 @@ void* tgbd_stream(struct tgb_device* d);
 void  tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out);
 void  tgbd_reset_launch_counter(struct tgb_device* d);
 void  tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base);
+b32   tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n_ranks);
+u32   tgbd_tile_rows(struct tgb_device* d);
+void* tgbd_comm(struct tgb_device* d);
+u32   tgbd_rank(struct tgb_device* d);
+u32   tgbd_n_ranks(struct tgb_device* d);
 
 /* reference material rule (8*rel_x + vx) % 256 for clusters [first_pointer, first_pointer+n) of an object (tgvk_raytracer.c:947-978) */
 b32   tgbd_fill_default_lut_idx(struct tgb_device* d, u32 first_pointer, u32 n_cluster_pointers, u32 nx);
@@ -59,6 +64,11 @@ b32   tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, 
 /* rows [y0, y1) only (multi-GPU: this rank's screen tile); pointers outside [base, base + n_local_pointers) shade to 0 */
 b32   tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p_cam, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1);
 
+/* multi-GPU frame tail: owner-resolved materials -> reduce-scatter by screen tile -> GI + shading of this rank's tile */
+b32   tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera_rays* p_cam, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization);
+/* all-gather of the radiance tiles so that every rank holds the full frame */
+b32   tgbd_gather_radiance(struct tgb_device* d);
+
 /* ---- tgb_svo.cu ---- */
 b32   tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity);
 b32   tgbd_svo_update_objects(struct tgb_device* d, u32 n_moved, const u32* p_object_indices, const tg_object_data* p_old_records);
@@ -70,6 +80,9 @@ b32   tgbn_unique_id(u8* p_out_128);
 void* tgbn_init(const u8* p_unique_id_128, u32 rank, u32 n_ranks);
 void  tgbn_destroy(void* p_comm);
 b32   tgbn_allreduce_min_u64(void* p_comm, void* p_device_buffer, u64 count, void* p_stream);
+b32   tgbn_allreduce_sum_u32(void* p_comm, void* p_device_buffer, u64 count, void* p_stream);
+b32   tgbn_allgather_bytes(void* p_comm, const void* p_send, void* p_recv, u64 n_bytes, void* p_stream);
+b32   tgbn_reducescatter_max_u64(void* p_comm, const void* p_send, void* p_recv, u64 count_per_rank, void* p_stream);
 /* events around the merge live in tgb_device.cu */
 void  tgbd_merge_begin(struct tgb_device* d);
 void  tgbd_merge_end(struct tgb_device* d);

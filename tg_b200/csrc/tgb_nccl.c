@@ -19,7 +19,8 @@ typedef struct { char internal[128]; } tgb_nccl_unique_id;
 typedef void* tgb_nccl_comm;
 
 /* values from nccl.h (ncclDataType_t / ncclRedOp_t), stable across NCCL 2.x */
-enum { TGB_NCCL_UINT64 = 5, TGB_NCCL_MIN = 3 };
+enum { TGB_NCCL_UINT8 = 1, TGB_NCCL_UINT32 = 3, TGB_NCCL_UINT64 = 5 };
+enum { TGB_NCCL_SUM = 0, TGB_NCCL_MAX = 2, TGB_NCCL_MIN = 3 };
 
 static struct
 {
@@ -28,6 +29,8 @@ static struct
     int (*CommInitRank)(tgb_nccl_comm*, int, tgb_nccl_unique_id, int);
     int (*CommDestroy)(tgb_nccl_comm);
     int (*AllReduce)(const void*, void*, size_t, int, int, tgb_nccl_comm, void*);
+    int (*AllGather)(const void*, void*, size_t, int, tgb_nccl_comm, void*);
+    int (*ReduceScatter)(const void*, void*, size_t, int, int, tgb_nccl_comm, void*);
     const char* (*GetErrorString)(int);
 } tgb__nccl;
 
@@ -44,8 +47,11 @@ static b32 tgb__nccl_load(void)
     *(void**)&tgb__nccl.CommInitRank   = dlsym(tgb__nccl.p_lib, "ncclCommInitRank");
     *(void**)&tgb__nccl.CommDestroy    = dlsym(tgb__nccl.p_lib, "ncclCommDestroy");
     *(void**)&tgb__nccl.AllReduce      = dlsym(tgb__nccl.p_lib, "ncclAllReduce");
+    *(void**)&tgb__nccl.AllGather      = dlsym(tgb__nccl.p_lib, "ncclAllGather");
+    *(void**)&tgb__nccl.ReduceScatter  = dlsym(tgb__nccl.p_lib, "ncclReduceScatter");
     *(void**)&tgb__nccl.GetErrorString = dlsym(tgb__nccl.p_lib, "ncclGetErrorString");
-    if (!tgb__nccl.GetUniqueId || !tgb__nccl.CommInitRank || !tgb__nccl.CommDestroy || !tgb__nccl.AllReduce || !tgb__nccl.GetErrorString)
+    if (!tgb__nccl.GetUniqueId || !tgb__nccl.CommInitRank || !tgb__nccl.CommDestroy || !tgb__nccl.AllReduce || !tgb__nccl.AllGather || !tgb__nccl.ReduceScatter ||
+        !tgb__nccl.GetErrorString)
     {
         tgb_set_error("NCCL library lacks a required symbol");
         dlclose(tgb__nccl.p_lib);
@@ -86,5 +92,29 @@ b32 tgbn_allreduce_min_u64(void* p_comm, void* p_device_buffer, u64 count, void*
 {
     if (!p_comm || !tgb__nccl.p_lib) { tgb_set_error("tgbn_allreduce_min_u64: no communicator"); return TG_FALSE; }
     TGB_NCCL(tgb__nccl.AllReduce(p_device_buffer, p_device_buffer, (size_t)count, TGB_NCCL_UINT64, TGB_NCCL_MIN, (tgb_nccl_comm)p_comm, p_stream));
+    return TG_TRUE;
+}
+
+/* per-node arrival counts of the sharded SVO build: sum over ranks, in place */
+b32 tgbn_allreduce_sum_u32(void* p_comm, void* p_device_buffer, u64 count, void* p_stream)
+{
+    if (!p_comm || !tgb__nccl.p_lib) { tgb_set_error("tgbn_allreduce_sum_u32: no communicator"); return TG_FALSE; }
+    TGB_NCCL(tgb__nccl.AllReduce(p_device_buffer, p_device_buffer, (size_t)count, TGB_NCCL_UINT32, TGB_NCCL_SUM, (tgb_nccl_comm)p_comm, p_stream));
+    return TG_TRUE;
+}
+
+/* every rank contributes n_bytes, receives n_ranks * n_bytes in rank order (object records, partial SVO leaves, radiance tiles) */
+b32 tgbn_allgather_bytes(void* p_comm, const void* p_send, void* p_recv, u64 n_bytes, void* p_stream)
+{
+    if (!p_comm || !tgb__nccl.p_lib) { tgb_set_error("tgbn_allgather_bytes: no communicator"); return TG_FALSE; }
+    TGB_NCCL(tgb__nccl.AllGather(p_send, p_recv, (size_t)n_bytes, TGB_NCCL_UINT8, (tgb_nccl_comm)p_comm, p_stream));
+    return TG_TRUE;
+}
+
+/* owner-resolved material words: element-wise max over ranks, rank r receives elements [r * count_per_rank, (r + 1) * count_per_rank) */
+b32 tgbn_reducescatter_max_u64(void* p_comm, const void* p_send, void* p_recv, u64 count_per_rank, void* p_stream)
+{
+    if (!p_comm || !tgb__nccl.p_lib) { tgb_set_error("tgbn_reducescatter_max_u64: no communicator"); return TG_FALSE; }
+    TGB_NCCL(tgb__nccl.ReduceScatter(p_send, p_recv, (size_t)count_per_rank, TGB_NCCL_UINT64, TGB_NCCL_MAX, (tgb_nccl_comm)p_comm, p_stream));
     return TG_TRUE;
 }

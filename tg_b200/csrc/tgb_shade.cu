@@ -86,171 +86,66 @@ struct tgb_svo_view
     v3 bmin, bmax;
 };
 
-/* svo_functions.inc:283-292 */
+/*
+ * svo_functions.inc:283-292, the distance to the far border of a box: per axis the shader evaluates a = (min - p) / d and
+ * b = (max - p) / d, takes max(a, b), then the minimum over the axes. Because min < max and IEEE subtraction / division
+ * are monotone and sign-symmetric, max(a, b) is the quotient towards the FAR plane of the axis, q = num / |d| with
+ * num = d > 0 ? max - p : p - min, bit for bit; d == 0 gives max(-F32_MAX, F32_MAX) = F32_MAX.
+ * Rounding is monotone, so an axis whose quotient is clearly larger than the smallest one cannot be the minimum: a
+ * 2-ulp approximate quotient ranks the axes and IEEE division is spent only on the axes within 1e-5 of the smallest
+ * (almost always one). The value returned is the shader's.
+ */
 __device__ __forceinline__ f32 tgb_exit_distance(v3 bmin, v3 bmax, v3 position, v3 d)
 {
-    const f32 ax = (d.x == 0.0f) ? TG_F32_MIN : ((bmin.x - position.x) / d.x);
-    const f32 ay = (d.y == 0.0f) ? TG_F32_MIN : ((bmin.y - position.y) / d.y);
-    const f32 az = (d.z == 0.0f) ? TG_F32_MIN : ((bmin.z - position.z) / d.z);
-    const f32 bx = (d.x == 0.0f) ? TG_F32_MAX : ((bmax.x - position.x) / d.x);
-    const f32 by = (d.y == 0.0f) ? TG_F32_MAX : ((bmax.y - position.y) / d.y);
-    const f32 bz = (d.z == 0.0f) ? TG_F32_MAX : ((bmax.z - position.z) / d.z);
-    return tgb_min(tgb_min(tgb_max(ax, bx), tgb_max(ay, by)), tgb_max(az, bz));
+    const f32 nx = d.x > 0.0f ? bmax.x - position.x : position.x - bmin.x, ax = fabsf(d.x);
+    const f32 ny = d.y > 0.0f ? bmax.y - position.y : position.y - bmin.y, ay = fabsf(d.y);
+    const f32 nz = d.z > 0.0f ? bmax.z - position.z : position.z - bmin.z, az = fabsf(d.z);
+    const f32 qx = ax != 0.0f ? __fdividef(nx, ax) : TG_F32_MAX;
+    const f32 qy = ay != 0.0f ? __fdividef(ny, ay) : TG_F32_MAX;
+    const f32 qz = az != 0.0f ? __fdividef(nz, az) : TG_F32_MAX;
+    const f32 q_min = fminf(fminf(qx, qy), qz);
+    const f32 limit = q_min + (1e-5f * fabsf(q_min) + 1e-30f);
+    /* __fdividef is only specified for 2^-126 <= |d| <= 2^126 and finite operands: anything unusual takes the exact path */
+    const bool odd = !(q_min == q_min) || fabsf(q_min) > 1e30f || (ax != 0.0f && ax < 1e-30f) || (ay != 0.0f && ay < 1e-30f) || (az != 0.0f && az < 1e-30f);
+    f32 exit = TG_F32_MAX;
+    if (ax != 0.0f && (odd || qx <= limit)) exit = tgb_min(exit, nx / ax);
+    if (ay != 0.0f && (odd || qy <= limit)) exit = tgb_min(exit, ny / ay);
+    if (az != 0.0f && (odd || qz <= limit)) exit = tgb_min(exit, nz / az);
+    return exit;
 }
 
 /*
- * Returns the hit depth in [0,1) or 1.0 on a miss, like tg_svo_traverse. The reference keeps a stack of five
- * (node, min, max) triples (svo.inc:4); here the stack holds only the node index and the octant taken at each
- * level -- a node's box is re-derived from the root box by the same chain of additions the shader performs
- * (child_min = parent_min [+ child_extent], child_max = child_min + child_extent [+ child_extent]), so the values
- * are the shader's, and the per-thread state stays in registers instead of 35 words of local memory.
+ * exit_distance(box) > F32_EPSILON (the pop test, svo_functions.inc:296-324) without dividing: q = num / |d| exceeds
+ * epsilon for sure when num > 2.5 eps |d| and is below it for sure when num < 0.5 eps |d| (this includes a ray that
+ * is on or past the border, num <= 0); only the sliver in between needs the quotient itself.
  */
-__device__ f32 tgb_svo_traverse(const tgb_svo_view& svo, f32 far_plane, v3 ray_origin_ws, v3 d)
+__device__ __forceinline__ bool tgb_axis_inside(f32 num, f32 ad)
 {
-    const v3 extent = tgb_sub(svo.bmax, svo.bmin);
-    const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin);
-    const v3 o = tgb_sub(ray_origin_ws, center);
-
-    f32 enter, exit;
-    if (!tgb_ray_aabb(o, d, svo.bmin, svo.bmax, &enter, &exit)) return 1.0f;
-    v3 position = o;
-    if (enter > 0.0f) position = tgb_add(position, tgb_scale(d, enter));
-
-    /* stack entry s (0 = root): node index idx[s]; path bits [3(s-1), 3s) = octant of entry s inside entry s-1 */
-    u32 idx0 = 0, idx1 = 0, idx2 = 0, idx3 = 0, idx4 = 0;
-    u32 path = 0;
-    u32 stack_size = 1;
-    f32 result = 1.0f;
-
-    for (u32 iterations = 0; stack_size > 0 && iterations < TGB_TRAVERSE_MAX_ITERS; iterations++)
-    {
-        /* box of the top entry, by the shader's additions from the root box */
-        v3 parent_min = svo.bmin, parent_max = svo.bmax;
-        for (u32 s = 1; s < stack_size; s++)
-        {
-            const v3 ce = tgb_scale(tgb_sub(parent_max, parent_min), 0.5f);
-            const u32 oct = (path >> (3u * (s - 1u))) & 7u;
-            v3 cmin = parent_min;
-            v3 cmax = tgb_add(cmin, ce);
-            if (oct & 1u) { cmin.x += ce.x; cmax.x += ce.x; }
-            if (oct & 2u) { cmin.y += ce.y; cmax.y += ce.y; }
-            if (oct & 4u) { cmin.z += ce.z; cmax.z += ce.z; }
-            parent_min = cmin; parent_max = cmax;
-        }
-        const u32 top = stack_size - 1u;
-        const u32 parent_idx = top == 0 ? idx0 : (top == 1 ? idx1 : (top == 2 ? idx2 : (top == 3 ? idx3 : idx4)));
-
-        const u32 node_data = __ldg(&svo.p_nodes[parent_idx]);
-        const u32 child_pointer =  node_data        & 0xFFFFu;
-        const u32 valid_mask    = (node_data >> 16) & 0xFFu;
-        const u32 leaf_mask     = (node_data >> 24) & 0xFFu;
-
-        /* svo_functions.inc:57-80 */
-        const v3 child_extent = tgb_scale(tgb_sub(parent_max, parent_min), 0.5f);
-        u32 relative_child_idx = 0;
-        v3 child_min = parent_min;
-        v3 child_max = tgb_add(child_min, child_extent);
-        if (child_max.x < position.x || (position.x == child_max.x && d.x > 0.0f)) { relative_child_idx += 1; child_min.x += child_extent.x; child_max.x += child_extent.x; }
-        if (child_max.y < position.y || (position.y == child_max.y && d.y > 0.0f)) { relative_child_idx += 2; child_min.y += child_extent.y; child_max.y += child_extent.y; }
-        if (child_max.z < position.z || (position.z == child_max.z && d.z > 0.0f)) { relative_child_idx += 4; child_min.z += child_extent.z; child_max.z += child_extent.z; }
-
-        bool advance_to_border = true;
-        if ((valid_mask & (1u << relative_child_idx)) != 0)
-        {
-            /* :86-91 */
-            const u32 child_idx = parent_idx + child_pointer + (u32)__popc(valid_mask & ((1u << relative_child_idx) - 1u));
-            if ((leaf_mask & (1u << relative_child_idx)) != 0)
-            {
-                const u32 data_pointer = __ldg(&svo.p_nodes[child_idx]);
-                if (__ldg(&svo.p_leaf_data[(u64)data_pointer * 65u]) != 0)
-                {
-                    /* :111-257: DDA through the 32^3 block */
-                    const u32* __restrict__ p_block = svo.p_voxels + (u64)data_pointer * TG_SVO_BLOCK_WORDS;
-                    v3 hit = position;
-                    v3 xyz = tgb_v3(tgb_clamp(floorf(hit.x), child_min.x, child_max.x - 1.0f),
-                                    tgb_clamp(floorf(hit.y), child_min.y, child_max.y - 1.0f),
-                                    tgb_clamp(floorf(hit.z), child_min.z, child_max.z - 1.0f));
-                    hit = tgb_sub(hit, child_min);
-                    xyz = tgb_sub(xyz, child_min);
-                    i32 x = (i32)xyz.x, y = (i32)xyz.y, z = (i32)xyz.z;
-                    i32 step_x = 0, step_y = 0, step_z = 0;
-                    f32 t_max_x = TG_F32_MAX, t_max_y = TG_F32_MAX, t_max_z = TG_F32_MAX;
-                    f32 t_delta_x = TG_F32_MAX, t_delta_y = TG_F32_MAX, t_delta_z = TG_F32_MAX;
-                    if (d.x > 0.0f)      { step_x = 1;  t_max_x = ((f32)(x + 1) - hit.x) / d.x;  t_delta_x = 1.0f / d.x; }
-                    else if (d.x < 0.0f) { step_x = -1; t_max_x = (hit.x - (f32)x) / -d.x;       t_delta_x = 1.0f / -d.x; }
-                    if (d.y > 0.0f)      { step_y = 1;  t_max_y = ((f32)(y + 1) - hit.y) / d.y;  t_delta_y = 1.0f / d.y; }
-                    else if (d.y < 0.0f) { step_y = -1; t_max_y = (hit.y - (f32)y) / -d.y;       t_delta_y = 1.0f / -d.y; }
-                    if (d.z > 0.0f)      { step_z = 1;  t_max_z = ((f32)(z + 1) - hit.z) / d.z;  t_delta_z = 1.0f / d.z; }
-                    else if (d.z < 0.0f) { step_z = -1; t_max_z = (hit.z - (f32)z) / -d.z;       t_delta_z = 1.0f / -d.z; }
-
-                    const i32 ex = (i32)child_extent.x, ey = (i32)child_extent.y, ez = (i32)child_extent.z;
-                    for (;;)
-                    {
-                        /* one x-row of the block is one word when the block is 32 wide (the only size the builder makes) */
-                        const u32 relative_voxel_idx = (u32)(ex * ey * z + ex * y + x);
-                        const u32 bits = __ldg(&p_block[relative_voxel_idx >> 5]);
-                        if ((bits >> (relative_voxel_idx & 31u)) & 1u)
-                        {
-                            const v3 voxel_min = tgb_add(child_min, tgb_v3((f32)x, (f32)y, (f32)z));
-                            const v3 voxel_max = tgb_add(child_min, tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)));
-                            tgb_ray_aabb(o, d, voxel_min, voxel_max, &enter, &exit);
-                            result = enter / far_plane;
-                            break;
-                        }
-                        if (t_max_x < t_max_y)
-                        {
-                            if (t_max_x < t_max_z) { t_max_x += t_delta_x; x += step_x; if (x < 0 || x >= ex) break; }
-                            else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= ez) break; }
-                        }
-                        else
-                        {
-                            if (t_max_y < t_max_z) { t_max_y += t_delta_y; y += step_y; if (y < 0 || y >= ey) break; }
-                            else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= ez) break; }
-                        }
-                    }
-                    if (result < 1.0f) break;
-                }
-            }
-            else
-            {
-                /* :262-270: push */
-                advance_to_border = false;
-                if (stack_size == 1) idx1 = child_idx; else if (stack_size == 2) idx2 = child_idx; else if (stack_size == 3) idx3 = child_idx; else idx4 = child_idx;
-                path = (path & ~(7u << (3u * (stack_size - 1u)))) | (relative_child_idx << (3u * (stack_size - 1u)));
-                stack_size++;
-                if (stack_size > TG_SVO_TRAVERSE_STACK_CAPACITY) return 1.0f; /* malformed tree (deeper than 5 inner levels) */
-            }
-        }
-
-        if (advance_to_border)
-        {
-            /* :279-324 */
-            exit = tgb_exit_distance(child_min, child_max, position, d);
-            position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
-            while (stack_size > 0)
-            {
-                v3 smin = svo.bmin, smax = svo.bmax;
-                for (u32 s = 1; s < stack_size; s++)
-                {
-                    const v3 ce = tgb_scale(tgb_sub(smax, smin), 0.5f);
-                    const u32 oct = (path >> (3u * (s - 1u))) & 7u;
-                    v3 cmin = smin;
-                    v3 cmax = tgb_add(cmin, ce);
-                    if (oct & 1u) { cmin.x += ce.x; cmax.x += ce.x; }
-                    if (oct & 2u) { cmin.y += ce.y; cmax.y += ce.y; }
-                    if (oct & 4u) { cmin.z += ce.z; cmax.z += ce.z; }
-                    smin = cmin; smax = cmax;
-                }
-                exit = tgb_exit_distance(smin, smax, position, d);
-                if (exit > TG_F32_EPSILON) break;
-                stack_size--;
-            }
-        }
-    }
-    return result < 1.0f ? result : 1.0f;
+    if (ad == 0.0f) return true; /* F32_MAX > eps */
+    if (num > 2.5f * TG_F32_EPSILON * ad) return true;
+    if (num < 0.5f * TG_F32_EPSILON * ad) return false;
+    return num / ad > TG_F32_EPSILON;
+}
+__device__ __forceinline__ bool tgb_still_inside(v3 bmin, v3 bmax, v3 position, v3 d)
+{
+    return tgb_axis_inside(d.x > 0.0f ? bmax.x - position.x : position.x - bmin.x, fabsf(d.x))
+        && tgb_axis_inside(d.y > 0.0f ? bmax.y - position.y : position.y - bmin.y, fabsf(d.y))
+        && tgb_axis_inside(d.z > 0.0f ? bmax.z - position.z : position.z - bmin.z, fabsf(d.z));
 }
 
-/* ---- K3 ----------------------------------------------------------------------------------------- */
+/* the child box of svo_functions.inc:57-80 for a known octant (what the shader pushed on its stack) */
+__device__ __forceinline__ void tgb_octant_box(v3 parent_min, v3 parent_max, u32 oct, v3* p_min, v3* p_max)
+{
+    const v3 ce = tgb_scale(tgb_sub(parent_max, parent_min), 0.5f);
+    v3 cmin = parent_min;
+    v3 cmax = tgb_add(cmin, ce);
+    if (oct & 1u) { cmin.x += ce.x; cmax.x += ce.x; }
+    if (oct & 2u) { cmin.y += ce.y; cmax.y += ce.y; }
+    if (oct & 4u) { cmin.z += ce.z; cmax.z += ce.z; }
+    *p_min = cmin; *p_max = cmax;
+}
+
+/* ---- K3a: per-pixel shading, secondary rays that enter the SVO box are queued ---------------------- */
 struct tgb_shade_args
 {
     const u64* __restrict__ p_vis;
@@ -267,15 +162,23 @@ struct tgb_shade_args
     u32 global_pointer_base, n_local_pointers;
     u32 gi_enabled, frame_seed, debug_visualization;
     u32 y0, y1; /* rows [y0, y1) are shaded (multi-GPU: this rank's screen tile) */
+    /* GI ray queue (SoA): origin.xyz + pixel | direction.xyz | ambient.rgb */
+    float4* __restrict__ p_q0;
+    float4* __restrict__ p_q1;
+    float4* __restrict__ p_q2;
+    u32* __restrict__ p_q_count; /* [0] rays queued, [1] rays fetched */
+    const u64* __restrict__ p_mat; /* RESOLVED mode: this tile's owner-resolved material words, row y0 first */
 };
 
-__global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
+/* returns true when a secondary ray has to be traced; *p_color is then the pixel WITHOUT its ambient term */
+/*
+ * RESOLVED (multi-GPU): the winning cluster may live on another GPU, so its material arrived as a word resolved by
+ * the owner (global object idx << 32 | packed colour) and the object tables (a.p_objects, a.p_frames) are the
+ * all-gathered global ones whose first_cluster_pointer is global. Everything downstream is the same arithmetic.
+ */
+template <bool RESOLVED>
+__device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px, u32 py, float4* p_color, v3* p_origin, v3* p_dir, v3* p_ambient)
 {
-    /* 8x4 pixel blocks per warp like K1: neighbouring pixels share clusters, objects and SVO leaves */
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const u32 px = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
-    const u32 py = a.y0 + blockIdx.y * 16u + (warp >> 1) * 4u + (lane >> 3);
-    if (px >= a.w || py >= a.y1) return;
     const u64 pixel = (u64)py * a.w + px;
 
     /* shading.frag:116-120 */
@@ -284,18 +187,31 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
     const u32 cluster_pointer_31b = (u32)(packed_data >> TG_VIS_POINTER_SHIFT) & 2147483647u;
     const u32 voxel_idx_9b        = (u32)(packed_data) & 511u;
 
-    if (!(depth_24b < 1.0f)) { a.p_out[pixel] = make_float4(1.0f, 0.0f, 1.0f, 1.0f); return; } /* :335 */
+    if (!(depth_24b < 1.0f)) { *p_color = make_float4(1.0f, 0.0f, 1.0f, 1.0f); return false; } /* :335 */
 
-    const u32 local_pointer = cluster_pointer_31b - a.global_pointer_base;
-    if (local_pointer >= a.n_local_pointers) { a.p_out[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); return; } /* another shard's cluster */
-    const u32 cluster_idx = __ldg(&a.p_cluster_pointers[local_pointer]);
-    const u32 object_idx = __ldg(&a.p_c2o[cluster_idx]);
+    u32 local_pointer, cluster_idx, object_idx, color_lut_idx, packed_color;
+    if (RESOLVED)
+    {
+        const u64 mat = a.p_mat[(u64)(py - a.y0) * a.w + px];
+        if (mat == 0) { *p_color = make_float4(0.0f, 0.0f, 0.0f, 0.0f); return false; } /* no rank owns this pointer: inconsistent shards */
+        local_pointer = cluster_pointer_31b; /* global pointer against globalised object records */
+        cluster_idx = cluster_pointer_31b;   /* debug views only */
+        object_idx = (u32)(mat >> 32);
+        color_lut_idx = 0;                   /* debug views only */
+        packed_color = (u32)mat;
+    }
+    else
+    {
+        local_pointer = cluster_pointer_31b - a.global_pointer_base;
+        if (local_pointer >= a.n_local_pointers) { *p_color = make_float4(0.0f, 0.0f, 0.0f, 0.0f); return false; } /* another shard's cluster */
+        cluster_idx = __ldg(&a.p_cluster_pointers[local_pointer]);
+        object_idx = __ldg(&a.p_c2o[cluster_idx]);
+        /* :128-135; per-object LUT (Q2) */
+        color_lut_idx = __ldg(&a.p_lut_idx[(u64)cluster_idx * 512u + voxel_idx_9b]);
+        packed_color = __ldg(&a.p_color_lut[a.p_objects[object_idx].lut_idx * 256u + color_lut_idx]);
+    }
     const tgb_object_frame& f = a.p_frames[object_idx];
     const tg_object_data& obj = a.p_objects[object_idx];
-
-    /* :128-135; per-object LUT (Q2) */
-    const u32 color_lut_idx = __ldg(&a.p_lut_idx[(u64)cluster_idx * 512u + voxel_idx_9b]);
-    const u32 packed_color = __ldg(&a.p_color_lut[obj.lut_idx * 256u + color_lut_idx]);
     const f32 color_r = (f32)( packed_color >> 24        ) / 255.0f;
     const f32 color_g = (f32)((packed_color >> 16) & 0xffu) / 255.0f;
     const f32 color_b = (f32)((packed_color >>  8) & 0xffu) / 255.0f;
@@ -339,14 +255,14 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
     /* :233-300 debug views */
     switch (a.debug_visualization)
     {
-    case TG_DEBUG_SHOW_OBJECT_INDEX:    a.p_out[pixel] = tgb_hash_color(object_idx); return;
-    case TG_DEBUG_SHOW_DEPTH:           { const f32 g = tgb_min(1.0f, 8.0f * depth_24b); a.p_out[pixel] = make_float4(g, g, g, 1.0f); return; }
+    case TG_DEBUG_SHOW_OBJECT_INDEX:    *p_color = tgb_hash_color(object_idx); return false;
+    case TG_DEBUG_SHOW_DEPTH:           { const f32 g = tgb_min(1.0f, 8.0f * depth_24b); *p_color = make_float4(g, g, g, 1.0f); return false; }
     case TG_DEBUG_SHOW_CLUSTER_INDEX:
-    case TG_DEBUG_SHOW_BLOCKS:          a.p_out[pixel] = tgb_hash_color(cluster_idx); return;
-    case TG_DEBUG_SHOW_VOXEL_INDEX:     a.p_out[pixel] = tgb_hash_color(voxel_idx_9b); return;
-    case TG_DEBUG_SHOW_COLOR_LUT_INDEX: a.p_out[pixel] = tgb_hash_color(color_lut_idx); return;
-    case TG_DEBUG_SHOW_COLOR:           a.p_out[pixel] = make_float4(color_r, color_g, color_b, 1.0f); return;
-    case TG_DEBUG_SHOW_NORMAL:          a.p_out[pixel] = make_float4(normal_ws.x * 0.5f + 0.5f, normal_ws.y * 0.5f + 0.5f, normal_ws.z * 0.5f + 0.5f, 1.0f); return;
+    case TG_DEBUG_SHOW_BLOCKS:          *p_color = tgb_hash_color(cluster_idx); return false;
+    case TG_DEBUG_SHOW_VOXEL_INDEX:     *p_color = tgb_hash_color(voxel_idx_9b); return false;
+    case TG_DEBUG_SHOW_COLOR_LUT_INDEX: *p_color = tgb_hash_color(color_lut_idx); return false;
+    case TG_DEBUG_SHOW_COLOR:           *p_color = make_float4(color_r, color_g, color_b, 1.0f); return false;
+    case TG_DEBUG_SHOW_NORMAL:          *p_color = make_float4(normal_ws.x * 0.5f + 0.5f, normal_ws.y * 0.5f + 0.5f, normal_ws.z * 0.5f + 0.5f, 1.0f); return false;
     default: break;
     }
 
@@ -358,34 +274,381 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
     const v3 specular_albedo = tgb_mix3(tgb_v3(0.04f, 0.04f, 0.04f), albedo, metallic);
     const f32 roughness = 0.8f;
     const v3 lo = tgb_shade_brdf(normal_ws, v, l, albedo, specular_albedo, metallic, roughness, tgb_v3(3.0f, 3.0f, 3.0f));
-    v3 ambient = tgb_scale(albedo, 0.1f);
+    const v3 ambient = tgb_scale(albedo, 0.1f);
 
-    /* composed GI term (DESIGN.md "GI spec"; oracle/tgo_shade.c) */
-    if (a.gi_enabled && a.debug_visualization == TG_DEBUG_SHOW_NONE)
+    /* composed GI term (DESIGN.md "GI spec"; oracle/tgo_shade.c): one secondary ray towards the sky hemisphere */
+    if (a.gi_enabled && a.debug_visualization == TG_DEBUG_SHOW_NONE && (normal_ws.x != 0.0f || normal_ws.y != 0.0f || normal_ws.z != 0.0f))
     {
-        f32 visibility = 1.0f;
-        if (normal_ws.x != 0.0f || normal_ws.y != 0.0f || normal_ws.z != 0.0f)
+        const u32 pixel_idx = a.w * py + px;
+        u32 rng = tgb_hash_u32(pixel_idx ^ tgb_hash_u32(a.frame_seed)) | 1u;
+        v3 dir = normal_ws;
+        for (u32 attempt = 0; attempt < 32; attempt++)
         {
-            const u32 pixel_idx = a.w * py + px;
-            u32 rng = tgb_hash_u32(pixel_idx ^ tgb_hash_u32(a.frame_seed)) | 1u;
-            v3 dir = normal_ws;
-            for (u32 attempt = 0; attempt < 32; attempt++)
-            {
-                v3 c;
-                c.x = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
-                c.y = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
-                c.z = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
-                c = tgb_normalize(c);
-                if (tgb_dot(c, normal_ws) > 0.0f) { dir = c; break; }
-            }
-            const v3 origin = tgb_add(hit_position_ws, tgb_scale(dir, 1.73205080757f));
-            const f32 depth2 = tgb_svo_traverse(a.svo, a.cam.far_plane, origin, dir);
-            visibility = depth2 < 1.0f ? 0.0f : 1.0f;
+            v3 c;
+            c.x = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
+            c.y = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
+            c.z = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
+            c = tgb_normalize(c);
+            if (tgb_dot(c, normal_ws) > 0.0f) { dir = c; break; }
         }
-        ambient = tgb_scale(ambient, visibility);
+        const v3 origin = tgb_add(hit_position_ws, tgb_scale(dir, 1.73205080757f));
+        /* svo_functions.inc:27-31: a ray that misses the root box is unoccluded; only the others are traced */
+        const v3 extent = tgb_sub(a.svo.bmax, a.svo.bmin);
+        const v3 center = tgb_add(tgb_scale(extent, 0.5f), a.svo.bmin);
+        f32 e0, e1;
+        if (tgb_ray_aabb(tgb_sub(origin, center), dir, a.svo.bmin, a.svo.bmax, &e0, &e1))
+        {
+            *p_color = make_float4(lo.x, lo.y, lo.z, 1.0f); /* ambient * 0 + lo, unless the ray escapes */
+            *p_origin = origin; *p_dir = dir; *p_ambient = ambient;
+            return true;
+        }
     }
+    *p_color = make_float4(ambient.x + lo.x, ambient.y + lo.y, ambient.z + lo.z, 1.0f);
+    return false;
+}
 
-    a.p_out[pixel] = make_float4(ambient.x + lo.x, ambient.y + lo.y, ambient.z + lo.z, 1.0f);
+template <bool RESOLVED>
+__global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
+{
+    /* 8x4 pixel blocks per warp like K1: neighbouring pixels share clusters, objects and material bytes */
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 px = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
+    const u32 py = a.y0 + blockIdx.y * 16u + (warp >> 1) * 4u + (lane >> 3);
+    const bool in_tile = px < a.w && py < a.y1;
+
+    float4 color = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    v3 origin = tgb_v3(0.0f, 0.0f, 0.0f), dir = origin, ambient = origin;
+    const bool trace = in_tile && tgb_shade_pixel<RESOLVED>(a, px, py, &color, &origin, &dir, &ambient);
+    if (in_tile) a.p_out[(u64)py * a.w + px] = color;
+
+    /* warp-aggregated append to the ray queue */
+    const u32 m = __ballot_sync(0xFFFFFFFFu, trace);
+    if (m == 0) return;
+    u32 base = 0;
+    if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(&a.p_q_count[0], (u32)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if (trace)
+    {
+        const u32 slot = base + (u32)__popc(m & ((1u << lane) - 1u));
+        a.p_q0[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(a.w * py + px));
+        a.p_q1[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+        a.p_q2[slot] = make_float4(ambient.x, ambient.y, ambient.z, 0.0f);
+    }
+}
+
+/* ---- K3b: the queued secondary rays through the SVO ------------------------------------------------------ */
+/*
+ * tg_svo_traverse (svo_functions.inc:1-329) as a per-lane state machine inside a persistent kernel.
+ *
+ * Secondary rays are incoherent (random hemisphere directions): inside one warp some lanes descend the tree, some
+ * walk a 32^3 leaf block voxel by voxel, some advance to the next node, and trip counts differ by two orders of
+ * magnitude. Run as one loop per thread, a warp executes the union of all those paths with a handful of lanes active
+ * (measured: 4.3 of 32, profiles/r01c). Here every ray is in one of three states and each warp iteration executes the
+ * ONE phase most of its lanes are waiting for, so the lanes that execute it do so together:
+ *   NODE  one visit of the shader's while loop up to the decision (:44-110, 262-270): read the node on top of the
+ *         stack, pick the octant; inner child -> push; leaf with data -> set up the DDA; otherwise -> ADV
+ *   ADV   advance to the far border of the child and pop every stacked node the ray has left (:279-324), then visit
+ *   DDA   up to TGB_GI_DDA_STEPS steps of the leaf DDA (:111-257); solid voxel before the far plane -> hit; leaving
+ *         the block -> ADV
+ * One REDUX per iteration counts the lanes of each kind. A lane whose ray finished fetches the next queued ray. The (node, min, max) stack of svo.inc:4 lives in shared
+ * memory ([level][component][thread], conflict-free), the top entry is cached in registers. The arithmetic that
+ * moves `position` or decides a comparison is the shader's, operation for operation.
+ */
+#define TGB_GI_THREADS   128
+#define TGB_GI_DDA_STEPS 8
+enum { TGB_ST_IDLE = 0, TGB_ST_NODE = 1, TGB_ST_DDA = 2, TGB_ST_ADV = 3 };
+
+__global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view svo, f32 far_plane, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
+                                                             const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, float4* __restrict__ p_out)
+{
+    /* stack entries 1..4 (entry 0 is the root: node 0, the SVO box) */
+    __shared__ f32 s_box[4][6][TGB_GI_THREADS];
+    __shared__ u32 s_idx[4][TGB_GI_THREADS];
+
+    const u32 tid = threadIdx.x, lane = tid & 31u;
+    const u32 n_rays = p_q_count[0];
+    const v3 extent = tgb_sub(svo.bmax, svo.bmin);
+    const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin); /* svo_functions.inc:3-8 */
+
+    u32 state = TGB_ST_IDLE, slot = 0, iterations = 0, stack_size = 0, top_idx = 0;
+    v3 o = tgb_v3(0.0f, 0.0f, 0.0f), d = o, position = o, top_min = o, top_max = o, child_min = o, child_max = o;
+    f32 t_max_x = 0.0f, t_max_y = 0.0f, t_max_z = 0.0f, t_delta_x = 0.0f, t_delta_y = 0.0f, t_delta_z = 0.0f;
+    i32 x = 0, y = 0, z = 0;
+    const u32* __restrict__ p_block = svo.p_voxels;
+    bool exhausted = false;
+
+    for (;;)
+    {
+        /* one REDUX counts the lanes per kind: idle | in a leaf DDA | in the tree (visit or advance pending) */
+        const u32 counts = __reduce_add_sync(0xFFFFFFFFu, 1u << (8u * state));
+        const u32 n_idle = counts & 0xFFu, n_node = (counts >> 8) & 0xFFu, n_dda = (counts >> 16) & 0xFFu, n_adv = counts >> 24;
+
+        /* ---- refill ---- */
+        if (!exhausted && n_idle >= 8u)
+        {
+            const u32 idle = __ballot_sync(0xFFFFFFFFu, state == TGB_ST_IDLE);
+            u32 base = 0;
+            const u32 leader = (u32)(__ffs(idle) - 1);
+            if (lane == leader) base = atomicAdd(&p_q_count[1], n_idle);
+            base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
+            if (state == TGB_ST_IDLE)
+            {
+                const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
+                if (mine < n_rays)
+                {
+                    slot = mine;
+                    const float4 q0 = p_q0[mine], q1 = p_q1[mine];
+                    o = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
+                    d = tgb_v3(q1.x, q1.y, q1.z);
+                    f32 enter, exit;
+                    if (tgb_ray_aabb(o, d, svo.bmin, svo.bmax, &enter, &exit)) /* :27-31; true: tested before queueing */
+                    {
+                        position = o;
+                        if (enter > 0.0f) position = tgb_add(position, tgb_scale(d, enter));
+                        top_min = svo.bmin; top_max = svo.bmax; top_idx = 0;
+                        stack_size = 1; iterations = 0;
+                        /* :139-176: the DDA increments depend on the ray only */
+                        t_delta_x = d.x > 0.0f ? 1.0f / d.x : (d.x < 0.0f ? 1.0f / -d.x : TG_F32_MAX);
+                        t_delta_y = d.y > 0.0f ? 1.0f / d.y : (d.y < 0.0f ? 1.0f / -d.y : TG_F32_MAX);
+                        t_delta_z = d.z > 0.0f ? 1.0f / d.z : (d.z < 0.0f ? 1.0f / -d.z : TG_F32_MAX);
+                        state = TGB_ST_NODE;
+                    }
+                }
+            }
+            exhausted = base + n_idle >= n_rays;
+            continue;
+        }
+        if (n_idle == 32u) break; /* queue drained and every ray finished */
+
+        u32 finished = 0; /* 1 = occluded, 2 = unoccluded */
+        if (n_dda >= n_node && n_dda >= n_adv)
+        {
+            if (state == TGB_ST_DDA)
+            {
+                /* :178-257 */
+                const i32 step_x = d.x > 0.0f ? 1 : (d.x < 0.0f ? -1 : 0);
+                const i32 step_y = d.y > 0.0f ? 1 : (d.y < 0.0f ? -1 : 0);
+                const i32 step_z = d.z > 0.0f ? 1 : (d.z < 0.0f ? -1 : 0);
+#pragma unroll 1
+                for (u32 k = 0; k < TGB_GI_DDA_STEPS; k++)
+                {
+                    /* a block row is one word: bit 1024 z + 32 y + x (the builder only makes 32^3 blocks) */
+                    const u32 bits = __ldg(&p_block[32 * z + y]);
+                    if ((bits >> x) & 1u)
+                    {
+                        const v3 voxel_min = tgb_add(child_min, tgb_v3((f32)x, (f32)y, (f32)z));
+                        const v3 voxel_max = tgb_add(child_min, tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)));
+                        f32 enter, exit;
+                        tgb_ray_aabb(o, d, voxel_min, voxel_max, &enter, &exit);
+                        /* :219-256 result = enter / far; only result < 1 ends the shader's loop, otherwise it advances */
+                        if (enter / far_plane < 1.0f) finished = 1u; else state = TGB_ST_ADV;
+                        break;
+                    }
+                    if (t_max_x < t_max_y)
+                    {
+                        if (t_max_x < t_max_z) { t_max_x += t_delta_x; x += step_x; if (x < 0 || x >= 32) { state = TGB_ST_ADV; break; } }
+                        else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= 32) { state = TGB_ST_ADV; break; } }
+                    }
+                    else
+                    {
+                        if (t_max_y < t_max_z) { t_max_y += t_delta_y; y += step_y; if (y < 0 || y >= 32) { state = TGB_ST_ADV; break; } }
+                        else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= 32) { state = TGB_ST_ADV; break; } }
+                    }
+                }
+            }
+        }
+        else if (n_adv > n_node)
+        {
+            if (state == TGB_ST_ADV)
+            {
+                /* :279-294 advance to the far border of the child */
+                const f32 exit = tgb_exit_distance(child_min, child_max, position, d);
+                position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
+                /* :296-324: pop while the ray has left the stacked node */
+                state = TGB_ST_NODE;
+                if (!tgb_still_inside(top_min, top_max, position, d))
+                {
+                    stack_size--;
+                    for (;;)
+                    {
+                        if (stack_size == 0) { finished = 2u; state = TGB_ST_IDLE; break; }
+                        if (stack_size == 1) { top_min = svo.bmin; top_max = svo.bmax; top_idx = 0; }
+                        else
+                        {
+                            const u32 e = stack_size - 2u;
+                            top_min = tgb_v3(s_box[e][0][tid], s_box[e][1][tid], s_box[e][2][tid]);
+                            top_max = tgb_v3(s_box[e][3][tid], s_box[e][4][tid], s_box[e][5][tid]);
+                            top_idx = s_idx[e][tid];
+                        }
+                        if (tgb_still_inside(top_min, top_max, position, d)) break;
+                        stack_size--;
+                    }
+                }
+            }
+        }
+        else
+        {
+            if (state == TGB_ST_NODE)
+            {
+                /* one visit of the shader's while loop: :44-110, 262-270 */
+                if (++iterations > TGB_TRAVERSE_MAX_ITERS) finished = 2u;
+                else
+                {
+                    const u32 node_data = __ldg(&svo.p_nodes[top_idx]);
+                    const u32 child_pointer =  node_data        & 0xFFFFu;
+                    const u32 valid_mask    = (node_data >> 16) & 0xFFu;
+                    const u32 leaf_mask     = (node_data >> 24) & 0xFFu;
+                    /* :57-80 */
+                    const v3 child_extent = tgb_scale(tgb_sub(top_max, top_min), 0.5f);
+                    u32 oct = 0;
+                    child_min = top_min;
+                    child_max = tgb_add(child_min, child_extent);
+                    if (child_max.x < position.x || (position.x == child_max.x && d.x > 0.0f)) { oct += 1; child_min.x += child_extent.x; child_max.x += child_extent.x; }
+                    if (child_max.y < position.y || (position.y == child_max.y && d.y > 0.0f)) { oct += 2; child_min.y += child_extent.y; child_max.y += child_extent.y; }
+                    if (child_max.z < position.z || (position.z == child_max.z && d.z > 0.0f)) { oct += 4; child_min.z += child_extent.z; child_max.z += child_extent.z; }
+                    state = TGB_ST_ADV;
+                    if ((valid_mask & (1u << oct)) != 0)
+                    {
+                        /* :86-91 */
+                        const u32 child_idx = top_idx + child_pointer + (u32)__popc(valid_mask & ((1u << oct) - 1u));
+                        if ((leaf_mask & (1u << oct)) == 0)
+                        {
+                            /* :262-270 push */
+                            if (stack_size >= TG_SVO_TRAVERSE_STACK_CAPACITY) finished = 2u; /* malformed tree */
+                            else
+                            {
+                                const u32 e = stack_size - 1u; /* new entry `stack_size` is stored in slot stack_size - 1 */
+                                s_box[e][0][tid] = child_min.x; s_box[e][1][tid] = child_min.y; s_box[e][2][tid] = child_min.z;
+                                s_box[e][3][tid] = child_max.x; s_box[e][4][tid] = child_max.y; s_box[e][5][tid] = child_max.z;
+                                s_idx[e][tid] = child_idx;
+                                stack_size++;
+                                top_min = child_min; top_max = child_max; top_idx = child_idx;
+                                state = TGB_ST_NODE;
+                            }
+                        }
+                        else
+                        {
+                            const u32 data_pointer = __ldg(&svo.p_nodes[child_idx]);
+                            if (__ldg(&svo.p_leaf_data[(u64)data_pointer * 65u]) != 0)
+                            {
+                                /* :111-176 (blocks are 32^3: tgbd_svo_build / tgbd_svo_set only accept a 1024^3 box) */
+                                p_block = svo.p_voxels + (u64)data_pointer * TG_SVO_BLOCK_WORDS;
+                                v3 hit = position;
+                                v3 xyz = tgb_v3(tgb_clamp(floorf(hit.x), child_min.x, child_max.x - 1.0f),
+                                                tgb_clamp(floorf(hit.y), child_min.y, child_max.y - 1.0f),
+                                                tgb_clamp(floorf(hit.z), child_min.z, child_max.z - 1.0f));
+                                hit = tgb_sub(hit, child_min);
+                                xyz = tgb_sub(xyz, child_min);
+                                x = (i32)xyz.x; y = (i32)xyz.y; z = (i32)xyz.z;
+                                t_max_x = TG_F32_MAX; t_max_y = TG_F32_MAX; t_max_z = TG_F32_MAX;
+                                if (d.x > 0.0f)      t_max_x = ((f32)(x + 1) - hit.x) / d.x;
+                                else if (d.x < 0.0f) t_max_x = (hit.x - (f32)x) / -d.x;
+                                if (d.y > 0.0f)      t_max_y = ((f32)(y + 1) - hit.y) / d.y;
+                                else if (d.y < 0.0f) t_max_y = (hit.y - (f32)y) / -d.y;
+                                if (d.z > 0.0f)      t_max_z = ((f32)(z + 1) - hit.z) / d.z;
+                                else if (d.z < 0.0f) t_max_z = (hit.z - (f32)z) / -d.z;
+                                state = TGB_ST_DDA;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        if (finished)
+        {
+            if (finished == 2u)
+            {
+                /* unoccluded: the ambient term comes back (ambient * 1 + lo) */
+                const float4 q0 = p_q0[slot], q2 = p_q2[slot];
+                const u32 pixel = __float_as_uint(q0.w);
+                float4 c = p_out[pixel];
+                c.x = q2.x + c.x; c.y = q2.y + c.y; c.z = q2.z + c.z;
+                p_out[pixel] = c;
+            }
+            state = TGB_ST_IDLE;
+        }
+    }
+}
+
+/* ---- owner-resolved materials (multi-GPU) ------------------------------------------------------------------ */
+/* local object records with pointers / LUT-independent fields globalised, into this rank's slice of the global table */
+__global__ void k_globalize_objects(const tg_object_data* __restrict__ p_objects, u32 object_capacity, u32 global_pointer_base, tg_object_data* __restrict__ p_out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= object_capacity) return;
+    tg_object_data o = p_objects[i];
+    if (o.n_cluster_pointers_per_dim.x != 0 && o.n_cluster_pointers_per_dim.y != 0 && o.n_cluster_pointers_per_dim.z != 0) o.first_cluster_pointer += global_pointer_base;
+    p_out[i] = o;
+}
+
+/*
+ * SURVEY.md section 8e "second exchange": the LUT-index bytes (512 B per cluster) exist only on the GPU that owns the
+ * cluster. After the visibility merge every rank looks at every pixel; where the winning pointer is its own it writes
+ * (global object idx << 32 | packed colour), elsewhere 0. A max-reduce-scatter by screen tile then hands each rank the
+ * resolved words of exactly the rows it shades.
+ */
+__global__ void __launch_bounds__(256) k_resolve_material(const u64* __restrict__ p_vis, u64 n_pixels, u64 n_padded, const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_c2o,
+                                                          const tg_object_data* __restrict__ p_objects, const u8* __restrict__ p_lut_idx, const u32* __restrict__ p_color_lut,
+                                                          u32 global_pointer_base, u32 n_local_pointers, u32 global_object_base, u64* __restrict__ p_mat)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_padded) return;
+    u64 word = 0;
+    if (i < n_pixels)
+    {
+        const u64 packed_data = p_vis[i];
+        const u32 depth24 = (u32)(packed_data >> TG_VIS_DEPTH_SHIFT);
+        const u32 local_pointer = ((u32)(packed_data >> TG_VIS_POINTER_SHIFT) & 2147483647u) - global_pointer_base;
+        if ((f32)depth24 / TG_VIS_DEPTH_SCALE < 1.0f && local_pointer < n_local_pointers)
+        {
+            const u32 cluster_idx = __ldg(&p_cluster_pointers[local_pointer]);
+            const u32 object_idx = __ldg(&p_c2o[cluster_idx]);
+            const u32 color_lut_idx = __ldg(&p_lut_idx[(u64)cluster_idx * 512u + ((u32)packed_data & 511u)]);
+            const u32 packed_color = __ldg(&p_color_lut[p_objects[object_idx].lut_idx * 256u + color_lut_idx]);
+            word = ((u64)(global_object_base + object_idx) << 32) | (u64)packed_color;
+        }
+    }
+    p_mat[i] = word;
+}
+
+static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam, bool resolved, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1)
+{
+    tgb_shade_args a;
+    a.p_vis = d->d_vis;
+    a.p_out = d->d_radiance;
+    a.p_cluster_pointers = d->d_cluster_pointers;
+    a.p_c2o = d->d_c2o;
+    a.p_objects = resolved ? d->d_objects_global : d->d_objects;
+    a.p_frames = resolved ? d->d_frames_global : d->d_frames_all;
+    a.p_lut_idx = d->d_lut_idx;
+    a.p_color_lut = d->d_color_lut;
+    a.svo.p_nodes = d->svo.d_nodes;
+    a.svo.p_leaf_data = d->svo.d_leaf_data;
+    a.svo.p_voxels = d->svo.d_voxels;
+    a.svo.bmin = d->svo.bmin;
+    a.svo.bmax = d->svo.bmax;
+    a.cam = *p_cam;
+    a.w = d->width; a.h = d->height;
+    a.global_pointer_base = d->global_pointer_base;
+    a.n_local_pointers = n_local_pointers;
+    a.gi_enabled = gi_enabled; a.frame_seed = frame_seed; a.debug_visualization = debug_visualization;
+    a.y0 = y0; a.y1 = y1;
+    a.p_q0 = d->d_gi_q0; a.p_q1 = d->d_gi_q1; a.p_q2 = d->d_gi_q2; a.p_q_count = d->d_gi_count;
+    a.p_mat = d->d_mat_tile;
+    const bool gi = gi_enabled && debug_visualization == TG_DEBUG_SHOW_NONE;
+    if (gi) TGB_CUDA(cudaMemsetAsync(d->d_gi_count, 0, 4 * sizeof(u32), d->stream));
+    const dim3 grid((d->width + 15) / 16, (y1 - y0 + 15) / 16);
+    if (resolved) k_shade<true><<<grid, 256, 0, d->stream>>>(a);
+    else          k_shade<false><<<grid, 256, 0, d->stream>>>(a);
+    TGB_LAUNCH_CHECK(d);
+    if (gi)
+    {
+        /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
+        k_gi_trace<<<d->n_sms * 8, TGB_GI_THREADS, 0, d->stream>>>(a.svo, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_radiance);
+        TGB_LAUNCH_CHECK(d);
+    }
+    return TG_TRUE;
 }
 
 extern "C" b32 tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p_cam, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization,
@@ -403,31 +666,52 @@ extern "C" b32 tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p
     k_object_frames<<<(d->object_capacity + 127) / 128, 128, 0, d->stream>>>(d->d_objects, d->object_capacity,
                                                                             tgb_v3(p_cam->camera.x, p_cam->camera.y, p_cam->camera.z), d->d_frames_all);
     TGB_LAUNCH_CHECK(d);
-
-    tgb_shade_args a;
-    a.p_vis = d->d_vis;
-    a.p_out = d->d_radiance;
-    a.p_cluster_pointers = d->d_cluster_pointers;
-    a.p_c2o = d->d_c2o;
-    a.p_objects = d->d_objects;
-    a.p_frames = d->d_frames_all;
-    a.p_lut_idx = d->d_lut_idx;
-    a.p_color_lut = d->d_color_lut;
-    a.svo.p_nodes = d->svo.d_nodes;
-    a.svo.p_leaf_data = d->svo.d_leaf_data;
-    a.svo.p_voxels = d->svo.d_voxels;
-    a.svo.bmin = d->svo.bmin;
-    a.svo.bmax = d->svo.bmax;
-    a.cam = *p_cam;
-    a.w = d->width; a.h = d->height;
-    a.global_pointer_base = d->global_pointer_base;
-    a.n_local_pointers = n_local_pointers;
-    a.gi_enabled = gi_enabled; a.frame_seed = frame_seed; a.debug_visualization = debug_visualization;
-    a.y0 = y0; a.y1 = y1;
-    const dim3 grid((d->width + 15) / 16, (y1 - y0 + 15) / 16);
-    k_shade<<<grid, 256, 0, d->stream>>>(a);
-    TGB_LAUNCH_CHECK(d);
+    if (!tgbd__shade_launch(d, p_cam, false, n_local_pointers, gi_enabled, frame_seed, debug_visualization, y0, y1)) return TG_FALSE;
     TGB_CUDA(cudaEventRecord(d->ev[8], d->stream));
     d->ev_shade = TG_TRUE;
     return TG_TRUE;
+}
+
+extern "C" b32 tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera_rays* p_cam, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    if (!d->p_comm || d->n_ranks < 2) { tgb_set_error("render_shading_sharded: no communicator"); return TG_FALSE; }
+    if (gi_enabled && debug_visualization == TG_DEBUG_SHOW_NONE && !d->svo.valid)
+    {
+        tgb_set_error("render_shading: GI is enabled but no SVO has been built (call tgb200_svo_update on every rank)");
+        return TG_FALSE;
+    }
+    TGB_CUDA(cudaEventRecord(d->ev[7], d->stream));
+    const u32 cap = d->object_capacity, n_global = cap * d->n_ranks;
+    const v3 camera = tgb_v3(p_cam->camera.x, p_cam->camera.y, p_cam->camera.z);
+
+    /* replicate the object records (96 B each) of every shard; pointers globalised by the owner */
+    k_globalize_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->d_objects_global + (u64)d->rank * cap);
+    TGB_LAUNCH_CHECK(d);
+    if (!tgbn_allgather_bytes(d->p_comm, d->d_objects_global + (u64)d->rank * cap, d->d_objects_global, (u64)cap * sizeof(tg_object_data), d->stream)) return TG_FALSE;
+    k_object_frames<<<(n_global + 127) / 128, 128, 0, d->stream>>>(d->d_objects_global, n_global, camera, d->d_frames_global);
+    TGB_LAUNCH_CHECK(d);
+
+    /* owner resolves the material of every pixel it won, max-reduce-scatter by screen tile */
+    const u64 n_pixels = (u64)d->width * d->height, tile_px = (u64)d->width * d->tile_rows, n_padded = tile_px * d->n_ranks;
+    k_resolve_material<<<(u32)((n_padded + 255) / 256), 256, 0, d->stream>>>(d->d_vis, n_pixels, n_padded, d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_lut_idx,
+                                                                             d->d_color_lut, d->global_pointer_base, n_local_pointers, d->rank * cap, d->d_mat);
+    TGB_LAUNCH_CHECK(d);
+    if (!tgbn_reducescatter_max_u64(d->p_comm, d->d_mat, d->d_mat_tile, tile_px, d->stream)) return TG_FALSE;
+
+    /* GI + shading of this rank's rows */
+    const u32 y0 = d->rank * d->tile_rows;
+    const u32 y1 = y0 + d->tile_rows < d->height ? y0 + d->tile_rows : d->height;
+    if (y0 < y1 && !tgbd__shade_launch(d, p_cam, true, n_local_pointers, gi_enabled, frame_seed, debug_visualization, y0, y1)) return TG_FALSE;
+    TGB_CUDA(cudaEventRecord(d->ev[8], d->stream));
+    d->ev_shade = TG_TRUE;
+    return TG_TRUE;
+}
+
+extern "C" b32 tgbd_gather_radiance(struct tgb_device* d)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    if (!d->p_comm || d->n_ranks < 2) return TG_TRUE;
+    const u64 tile_bytes = (u64)d->width * d->tile_rows * sizeof(float4);
+    return tgbn_allgather_bytes(d->p_comm, (const u8*)d->d_radiance + (u64)d->rank * tile_bytes, d->d_radiance, tile_bytes, d->stream);
 }

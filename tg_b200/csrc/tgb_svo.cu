@@ -55,7 +55,8 @@ enum
     TGB_SCR_CUR   = TGB_SCR_POFF  + TGB_SVO_MAX_LEAVES,  /* [32768] scatter cursor             */
     TGB_SCR_DENSE_OF_LEAF = TGB_SCR_CUR + TGB_SVO_MAX_LEAVES, /* [32768] dense leaf per data_pointer */
     TGB_SCR_DIRTY = TGB_SCR_DENSE_OF_LEAF + TGB_SVO_MAX_LEAVES, /* [32768] leaf must be re-sampled (incremental) */
-    TGB_SCR_TOTAL = TGB_SCR_DIRTY + TGB_SVO_MAX_LEAVES
+    TGB_SCR_CNT_G = TGB_SCR_DIRTY + TGB_SVO_MAX_LEAVES,  /* arrivals per dense node summed over all ranks (== CNT on one GPU) */
+    TGB_SCR_TOTAL = TGB_SCR_CNT_G + TGB_SVO_DENSE_TOTAL
 };
 
 /* counts block d_counts: [0] nodes, [1] leaves, [2] pairs, [3] error flags */
@@ -257,7 +258,9 @@ __global__ void __launch_bounds__(128) k_svo_descend(const u32* __restrict__ p_c
 /* ---- pass 2: DFS layout of the dense tree ---------------------------------------------------------- */
 __global__ void __launch_bounds__(1024) k_svo_layout(u32* __restrict__ p_scratch, u32* __restrict__ p_nodes, u32* __restrict__ p_counts, u32 node_capacity, u32 leaf_capacity)
 {
-    u32* __restrict__ p_cnt = p_scratch + TGB_SCR_CNT;
+    /* existence and DFS indices come from the GLOBAL arrival counts, the pair segments from this rank's own */
+    u32* __restrict__ p_cnt = p_scratch + TGB_SCR_CNT_G;
+    const u32* __restrict__ p_cnt_local = p_scratch + TGB_SCR_CNT;
     u32* __restrict__ p_s = p_scratch + TGB_SCR_S;
     u32* __restrict__ p_ls = p_scratch + TGB_SCR_LS;
     u32* __restrict__ p_base = p_scratch + TGB_SCR_BASE;
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(1024) k_svo_layout(u32* __restrict__ p_scratch
     {
         const u32 off5 = tgb_level_offset(5);
         u32 sum = 0;
-        for (u32 k = 0; k < 32; k++) sum += p_cnt[off5 + tid * 32u + k];
+        for (u32 k = 0; k < 32; k++) sum += p_cnt_local[off5 + tid * 32u + k];
         s_part[tid] = sum;
         __syncthreads();
         for (u32 stride = 1; stride < 1024; stride <<= 1)
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(1024) k_svo_layout(u32* __restrict__ p_scratch
         for (u32 k = 0; k < 32; k++)
         {
             p_scratch[TGB_SCR_POFF + tid * 32u + k] = run;
-            run += p_cnt[off5 + tid * 32u + k];
+            run += p_cnt_local[off5 + tid * 32u + k];
         }
         if (tid == 1023)
         {
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(1024) k_svo_layout(u32* __restrict__ p_scratch
 
 __global__ void __launch_bounds__(TGB_LEAF_THREADS) k_svo_fill_leaves(const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_c2o, const tg_object_data* __restrict__ p_objects,
                                                                       const u32* __restrict__ p_masks, v3 bmin, v3 bmax, const u32* __restrict__ p_scratch, const u32* __restrict__ p_pairs,
-                                                                      u8* __restrict__ p_pair_flags, u32* __restrict__ p_leaf_data, u32* __restrict__ p_voxels, u32 only_dirty)
+                                                                      u8* __restrict__ p_pair_flags, u32* __restrict__ p_leaf_data, u32* __restrict__ p_voxels, u32 only_dirty, u32 cluster_idx_base)
 {
     __shared__ u32 s_bits[TG_SVO_BLOCK_WORDS];
     __shared__ u32 s_n;
@@ -501,11 +504,43 @@ __global__ void __launch_bounds__(TGB_LEAF_THREADS) k_svo_fill_leaves(const u32*
         {
             if (p_pair_flags[pair_off + j] && p_pairs[pair_off + j] < cp) rank++;
         }
-        if (rank < TG_SVO_LEAF_MAX_CLUSTERS) p_data[1 + rank] = __ldg(&p_cluster_pointers[cp]);
+        if (rank < TG_SVO_LEAF_MAX_CLUSTERS) p_data[1 + rank] = __ldg(&p_cluster_pointers[cp]) + cluster_idx_base;
     }
     if (local_count) atomicAdd(&s_n, local_count);
     __syncthreads();
     if (tid == 0) p_data[0] = s_n < TG_SVO_LEAF_MAX_CLUSTERS ? s_n : TG_SVO_LEAF_MAX_CLUSTERS;
+}
+
+/* ---- pass 5 (multi-GPU): merge the per-rank leaf contributions ------------------------------------------------ */
+/*
+ * Each rank sampled only its own clusters. A leaf's voxel bits are an OR over clusters (order-free, S4) and its index
+ * list is "ascending pointer order, first 64" -- pointer ranges are contiguous per rank, so that is the ranks' lists
+ * concatenated in rank order. NCCL has no bitwise-OR reduction: the partial leaves are all-gathered and combined here.
+ * Gathered layout per rank: [n_leaves * 1024 voxel words | n_leaves * 65 leaf-record words].
+ */
+__global__ void __launch_bounds__(256) k_svo_combine(const u32* __restrict__ p_gather, u32 n_ranks, u32 n_leaves, u32* __restrict__ p_leaf_data, u32* __restrict__ p_voxels)
+{
+    const u32 leaf = blockIdx.x;
+    const u64 per_rank = (u64)n_leaves * (TG_SVO_BLOCK_WORDS + 65u);
+    for (u32 i = threadIdx.x; i < TG_SVO_BLOCK_WORDS; i += blockDim.x)
+    {
+        u32 bits = 0;
+        for (u32 r = 0; r < n_ranks; r++) bits |= p_gather[r * per_rank + (u64)leaf * TG_SVO_BLOCK_WORDS + i];
+        p_voxels[(u64)leaf * TG_SVO_BLOCK_WORDS + i] = bits;
+    }
+    if (threadIdx.x < 65u) p_leaf_data[(u64)leaf * 65u + threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        u32 n = 0;
+        for (u32 r = 0; r < n_ranks && n < TG_SVO_LEAF_MAX_CLUSTERS; r++)
+        {
+            const u32* p_rec = p_gather + r * per_rank + (u64)n_leaves * TG_SVO_BLOCK_WORDS + (u64)leaf * 65u;
+            const u32 n_r = p_rec[0];
+            for (u32 j = 0; j < n_r && n < TG_SVO_LEAF_MAX_CLUSTERS; j++) p_leaf_data[(u64)leaf * 65u + 1u + n++] = p_rec[1 + j];
+        }
+        p_leaf_data[(u64)leaf * 65u] = n;
+    }
 }
 
 /* ---- host side of the seam ---------------------------------------------------------------------------- */
@@ -536,11 +571,34 @@ static b32 tgbd__svo_ensure_pairs(struct tgb_device* d, u64 n_pairs)
     return TG_TRUE;
 }
 
+static b32 tgbd__svo_ensure_gather(struct tgb_device* d, u32 n_leaves)
+{
+    tgb_svo_device* s = &d->svo;
+    if (n_leaves <= s->part_capacity_leaves) return TG_TRUE;
+    u64 cap = s->part_capacity_leaves ? s->part_capacity_leaves : 1024;
+    while (cap < n_leaves) cap *= 2;
+    if (s->d_part) TGB_CUDA(cudaFree(s->d_part));
+    if (s->d_gather) TGB_CUDA(cudaFree(s->d_gather));
+    s->d_part = NULL; s->d_gather = NULL; s->part_capacity_leaves = 0;
+    const u64 words = cap * (TG_SVO_BLOCK_WORDS + 65u);
+    TGB_CUDA(cudaMalloc(&s->d_part, words * sizeof(u32)));
+    TGB_CUDA(cudaMalloc(&s->d_gather, words * sizeof(u32) * d->n_ranks));
+    s->part_capacity_leaves = cap;
+    return TG_TRUE;
+}
+
+/*
+ * Full build. On one GPU: passes 1-4. Sharded (communicator set): every rank walks its own clusters, the arrival counts
+ * are summed over the ranks (ncclAllReduce, 150 KB) so that every rank lays out the SAME tree, each rank samples its
+ * clusters into a partial copy of every leaf, the partial leaves are all-gathered and OR-combined (pass 5). The result
+ * is bit-identical on every rank and to a single-GPU build over the union of the shards. Collective: all ranks call it.
+ */
 extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity)
 {
     TGB_CUDA(cudaSetDevice(d->device));
     if (!tgbd__svo_ensure(d)) return TG_FALSE;
     tgb_svo_device* s = &d->svo;
+    const bool sharded = d->p_comm != NULL && d->n_ranks > 1;
     s->valid = TG_FALSE;
     s->bmin = extent_min; s->bmax = extent_max;
 
@@ -558,6 +616,8 @@ extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max
                                                          extent_min, extent_max, s->d_scratch, NULL, s->d_counts);
         TGB_LAUNCH_CHECK(d);
     }
+    TGB_CUDA(cudaMemcpyAsync(s->d_scratch + TGB_SCR_CNT_G, s->d_scratch + TGB_SCR_CNT, (u64)TGB_SVO_DENSE_TOTAL * sizeof(u32), cudaMemcpyDeviceToDevice, d->stream));
+    if (sharded && !tgbn_allreduce_sum_u32(d->p_comm, s->d_scratch + TGB_SCR_CNT_G, TGB_SVO_DENSE_TOTAL, d->stream)) return TG_FALSE;
     k_svo_layout<<<1, 1024, 0, d->stream>>>(s->d_scratch, s->d_nodes, s->d_counts, s->node_capacity, s->leaf_capacity);
     TGB_LAUNCH_CHECK(d);
 
@@ -574,6 +634,7 @@ extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max
     s->n_nodes = counts[0];
     s->n_leaves = counts[1];
     if (!tgbd__svo_ensure_pairs(d, counts[2])) return TG_FALSE;
+    if (sharded && !tgbd__svo_ensure_gather(d, s->n_leaves)) return TG_FALSE;
 
     if (counts[2] && grid)
     {
@@ -583,9 +644,19 @@ extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max
     }
     if (s->n_leaves)
     {
+        u32* p_voxels = sharded ? s->d_part : s->d_voxels;
+        u32* p_leaf = sharded ? s->d_part + (u64)s->n_leaves * TG_SVO_BLOCK_WORDS : s->d_leaf_data;
         k_svo_fill_leaves<<<s->n_leaves, TGB_LEAF_THREADS, 0, d->stream>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_masks, extent_min, extent_max,
-                                                                           s->d_scratch, s->d_pairs_a, s->d_pair_flags, s->d_leaf_data, s->d_voxels, 0);
+                                                                           s->d_scratch, s->d_pairs_a, s->d_pair_flags, p_leaf, p_voxels, 0,
+                                                                           sharded ? d->global_pointer_base : 0u);
         TGB_LAUNCH_CHECK(d);
+        if (sharded)
+        {
+            const u64 part_bytes = (u64)s->n_leaves * (TG_SVO_BLOCK_WORDS + 65u) * sizeof(u32);
+            if (!tgbn_allgather_bytes(d->p_comm, s->d_part, s->d_gather, part_bytes, d->stream)) return TG_FALSE;
+            k_svo_combine<<<s->n_leaves, 256, 0, d->stream>>>(s->d_gather, d->n_ranks, s->n_leaves, s->d_leaf_data, s->d_voxels);
+            TGB_LAUNCH_CHECK(d);
+        }
     }
     TGB_CUDA(cudaEventRecord(d->ev[6], d->stream));
     d->ev_svo = TG_TRUE;
@@ -620,6 +691,11 @@ extern "C" b32 tgbd_svo_set(struct tgb_device* d, v3 bmin, v3 bmax, u32 n_nodes,
     {
         tgb_set_error("svo upload: %u nodes / %u leaves / %u voxel words exceed the device capacities %u / %u / %u", n_nodes, n_leaves, n_voxel_words,
                       s->node_capacity, s->leaf_capacity, s->voxel_word_capacity);
+        return TG_FALSE;
+    }
+    if (bmax.x - bmin.x != (f32)TG_SVO_SIDE_LENGTH || bmax.y - bmin.y != (f32)TG_SVO_SIDE_LENGTH || bmax.z - bmin.z != (f32)TG_SVO_SIDE_LENGTH)
+    {
+        tgb_set_error("svo upload: the box must be %d^3 (32^3 leaf blocks, tg_sparse_voxel_octree.c:468-472)", TG_SVO_SIDE_LENGTH);
         return TG_FALSE;
     }
     s->valid = TG_FALSE;

@@ -181,6 +181,20 @@ class Raytracer:
     def merge_visibility(self):
         self._lib.tgb200_merge_visibility(C.byref(self._rt))
 
+    def tile_rows(self):
+        y0, y1 = T.u32(), T.u32()
+        self._lib.tgb200_tile_rows(C.byref(self._rt), C.byref(y0), C.byref(y1))
+        return y0.value, y1.value
+
+    def gather_radiance(self):
+        self._lib.tgb200_gather_radiance(C.byref(self._rt))
+
+    def mark_svo_dirty(self):
+        self._lib.tgb200_mark_svo_dirty(C.byref(self._rt))
+
+    def comm_destroy(self):
+        self._lib.tgb200_comm_destroy(C.byref(self._rt))
+
     # ---- scene loading -----------------------------------------------------------------------------
     def load_scene(self, scene):
         """Creates every object of a tg_b200.scenes.SceneSpec and its LUT (tg_application.c:64-98 analogue)."""

@@ -1,0 +1,40 @@
+"""Host-side plan of the multi-GPU path: which objects a rank owns, the global cluster-pointer
+base of its shard, the screen tile it shades, and the 64-bit min merge expressed for a CPU (gloo) process group.
+
+One process per GPU. Clusters are sharded BY OBJECT (an object's clusters are one contiguous pointer range,
+tgvk_raytracer.c:826-827), ranks own contiguous object ranges, so global pointers = local pointer + base. The per-GPU
+visibility buffers are merged with an element-wise 64-bit min (ncclAllReduce(ncclUint64, ncclMin) on GPUs); GI rays are
+split by screen tile: rank r shades rows [r * ceil(H / N), (r + 1) * ceil(H / N))."""
+import numpy as np
+
+
+def object_range(n_objects, n_ranks, rank):
+    """Contiguous, balanced: the first n_objects % n_ranks ranks own one object more."""
+    q, r = divmod(n_objects, n_ranks)
+    first = rank * q + min(rank, r)
+    return first, first + q + (1 if rank < r else 0)
+
+
+def shard_scene(scene, n_ranks, rank):
+    """(SceneSpec holding this rank's objects, global pointer base, global object base)."""
+    from .scenes import SceneSpec
+    first, last = object_range(len(scene.objects), n_ranks, rank)
+    base = sum(o.n_clusters for o in scene.objects[:first])
+    sub = SceneSpec(name=f"{scene.name}_shard{rank}of{n_ranks}", width=scene.width, height=scene.height, camera=scene.camera,
+                    objects=scene.objects[first:last], lut=scene.lut, n_luts=scene.n_luts)
+    return sub, base, first
+
+
+def tile_rows(height, n_ranks, rank):
+    rows = (height + n_ranks - 1) // n_ranks
+    return min(rank * rows, height), min((rank + 1) * rows, height)
+
+
+def allreduce_min_u64(vis, group=None):
+    """Element-wise unsigned 64-bit min over a torch.distributed group that lacks uint64 reductions (gloo): flipping the
+    sign bit maps unsigned order onto signed order. `vis` is a numpy uint64 array; returns the merged array."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy((vis ^ np.uint64(1 << 63)).view(np.int64).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return t.numpy().view(np.uint64) ^ np.uint64(1 << 63)
