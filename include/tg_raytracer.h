@@ -120,6 +120,8 @@ TG_EXPORT void tgb200_synchronize(tg_raytracer* p_raytracer);
 /* Copies of results into caller memory (synchronous). */
 TG_EXPORT void tg_raytracer_read_visibility(tg_raytracer* p_raytracer, u64* p_out /* w*h */);
 TG_EXPORT void tg_raytracer_read_radiance(tg_raytracer* p_raytracer, f32* p_out /* w*h*4, RGBA32F */);
+/* Rows [first_row, one_past_last_row) only, e.g. the tile this rank shaded (tgb200_tile_rows); p_out receives those rows. */
+TG_EXPORT void tg_raytracer_read_radiance_rows(tg_raytracer* p_raytracer, u32 first_row, u32 one_past_last_row, f32* p_out);
 /* Replaces the device visibility buffer (tests: feed an oracle-made buffer to the shading stage). */
 TG_EXPORT void tg_raytracer_write_visibility(tg_raytracer* p_raytracer, const u64* p_in /* w*h */);
 /* Device SVO -> freshly malloc'ed host arrays in *p_svo (free with tg_svo_destroy). */

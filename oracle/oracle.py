@@ -71,7 +71,7 @@ def lib():
         L.tgo_intersect_aabb_obb_ignore_contact.argtypes = [T.v3, T.v3, C.POINTER(T.v3)]
         L.tgo_intersect_aabb_obb_ignore_contact.restype = T.b32
         L.tgo_shade.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, C.POINTER(T.u64), C.POINTER(T.tg_svo),
-                                T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.f32)]
+                                T.u32, T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.f32)]
         _LIB = L
     return _LIB
 
@@ -170,9 +170,10 @@ def svo_destroy(svo):
     lib().tgo_svo_destroy(C.byref(svo))
 
 
-def shade(view, rays, w, h, vis, svo=None, gi=False, frame_seed=1, debug=0, y0=0, y1=None):
-    out = np.zeros((h, w, 4), dtype=np.float32)
+def shade(view, rays, w, h, vis, svo=None, gi=False, frame_seed=1, debug=0, y0=0, y1=None, out=None, ystep=1):
+    if out is None:
+        out = np.zeros((h, w, 4), dtype=np.float32)
     vis = np.ascontiguousarray(vis, dtype=np.uint64)
     lib().tgo_shade(C.byref(view.view), C.byref(rays), w, h, T.ptr(vis, T.u64), C.byref(svo) if svo is not None else None,
-                    1 if gi else 0, frame_seed, debug, y0, h if y1 is None else y1, T.ptr(out, T.f32))
+                    1 if gi else 0, frame_seed, debug, y0, h if y1 is None else y1, ystep, T.ptr(out, T.f32))
     return out

@@ -72,9 +72,9 @@ b32  tgo_amanatides_woo(v3 ray_hit_on_grid, v3 ray_direction, v3 extent, const u
 /* physics/tg_physics.c:226-392 */
 b32  tgo_intersect_aabb_obb_ignore_contact(v3 bmin, v3 bmax, const v3* p_obb_corners);
 
-/* shading.frag:114-337 (+ the pinned GI term of DESIGN.md) for rows [y0,y1). RGBA32F out. */
+/* shading.frag:114-337 (+ the pinned GI term of DESIGN.md) for rows y0, y0+ystep, ... < y1 (other rows untouched). RGBA32F out. */
 void tgo_shade(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, const u64* p_vis, const tg_svo* p_svo_or_null,
-               u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1, f32* p_out_rgba);
+               u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1, u32 ystep, f32* p_out_rgba);
 
 #ifdef __cplusplus
 }

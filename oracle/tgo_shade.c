@@ -229,12 +229,15 @@ static void tgo__shade_pixel(const tgo_scene_view* p_scene, const tg_camera_rays
 }
 
 void tgo_shade(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, const u64* p_vis, const tg_svo* p_svo_or_null,
-               u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1, f32* p_out_rgba)
+               u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1, u32 ystep, f32* p_out_rgba)
 {
     if (y1 > h) y1 = h;
+    if (ystep == 0) ystep = 1;
+    const i64 n_rows = y1 > y0 ? ((i64)(y1 - y0) + ystep - 1) / ystep : 0;
 #pragma omp parallel for schedule(dynamic, 4)
-    for (i64 py = (i64)y0; py < (i64)y1; py++)
+    for (i64 row = 0; row < n_rows; row++)
     {
+        const i64 py = (i64)y0 + row * ystep;
         for (u32 px = 0; px < w; px++)
         {
             const size_t i = (size_t)py * w + px;

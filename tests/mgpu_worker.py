@@ -67,7 +67,9 @@ def main():
         assert np.array_equal(vis, want_vis), f"{name} rank {rank}: merged visibility differs in {int((vis != want_vis).sum())} words"
         assert np.array_equal(nodes, rnodes) and np.array_equal(vox, rvox), f"{name} rank {rank}: sharded SVO nodes / voxels differ"
         assert np.array_equal(leaf, rleaf), f"{name} rank {rank}: sharded SVO leaf records differ"
-        assert np.array_equal(rad, want_rad), f"{name} rank {rank}: radiance differs in {int((rad != want_rad).any(axis=-1).sum())} pixels"
+        bad = np.argwhere((rad != want_rad).any(axis=-1))
+        assert bad.size == 0, (f"{name} rank {rank}: radiance differs in {len(bad)} pixels; rows {np.unique(bad[:, 0])[:12].tolist()}.. first "
+                               f"{[(int(y), int(x), rad[y, x].tolist(), want_rad[y, x].tolist()) for y, x in bad[:3]]}")
         dist.barrier()
         if rank == 0:
             print(f"MGPU_OK {name} world={world} tile_rows={y1 - y0} merge_ms={t['merge_ms']:.3f}", flush=True)

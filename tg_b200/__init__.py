@@ -49,6 +49,7 @@ SYMBOLS = {
     "tgb200_synchronize": (None, [_RT]),
     "tg_raytracer_read_visibility": (None, [_RT, _P(T.u64)]),
     "tg_raytracer_read_radiance": (None, [_RT, _P(T.f32)]),
+    "tg_raytracer_read_radiance_rows": (None, [_RT, T.u32, T.u32, _P(T.f32)]),
     "tg_raytracer_write_visibility": (None, [_RT, _P(T.u64)]),
     "tgb200_svo_download": (None, [_RT, _P(T.tg_svo)]),
     "tgb200_svo_upload": (None, [_RT, _P(T.tg_svo)]),

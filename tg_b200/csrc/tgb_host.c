@@ -488,6 +488,14 @@ void tg_raytracer_read_radiance(tg_raytracer* p_raytracer, f32* p_out)
     tgbd_download(p_raytracer->p_device, TGB_BUF_RADIANCE, 0, p_out, (u64)p_raytracer->width * p_raytracer->height * 16);
 }
 
+void tg_raytracer_read_radiance_rows(tg_raytracer* p_raytracer, u32 first_row, u32 one_past_last_row, f32* p_out)
+{
+    if (!tgb__alive(p_raytracer, "tg_raytracer_read_radiance_rows")) return;
+    TGB_REQUIRE(first_row <= one_past_last_row && one_past_last_row <= p_raytracer->height, TGB_VOID, "read_radiance_rows: rows [%u, %u) outside the frame", first_row, one_past_last_row);
+    if (first_row == one_past_last_row) return;
+    tgbd_download(p_raytracer->p_device, TGB_BUF_RADIANCE, (u64)first_row * p_raytracer->width * 16, p_out, (u64)(one_past_last_row - first_row) * p_raytracer->width * 16);
+}
+
 void tgb200_get_timings(tg_raytracer* p_raytracer, tgb200_timings* p_out)
 {
     memset(p_out, 0, sizeof(*p_out));

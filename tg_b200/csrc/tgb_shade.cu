@@ -173,7 +173,7 @@ struct tgb_shade_args
 /* returns true when a secondary ray has to be traced; *p_color is then the pixel WITHOUT its ambient term */
 /*
  * RESOLVED (multi-GPU): the winning cluster may live on another GPU, so its material arrived as a word resolved by
- * the owner (global object idx << 32 | packed colour) and the object tables (a.p_objects, a.p_frames) are the
+ * the owner ((global object idx + 1) << 32 | packed colour) and the object tables (a.p_objects, a.p_frames) are the
  * all-gathered global ones whose first_cluster_pointer is global. Everything downstream is the same arithmetic.
  */
 template <bool RESOLVED>
@@ -196,7 +196,7 @@ __device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px,
         if (mat == 0) { *p_color = make_float4(0.0f, 0.0f, 0.0f, 0.0f); return false; } /* no rank owns this pointer: inconsistent shards */
         local_pointer = cluster_pointer_31b; /* global pointer against globalised object records */
         cluster_idx = cluster_pointer_31b;   /* debug views only */
-        object_idx = (u32)(mat >> 32);
+        object_idx = (u32)(mat >> 32) - 1u;
         color_lut_idx = 0;                   /* debug views only */
         packed_color = (u32)mat;
     }
@@ -585,7 +585,7 @@ __global__ void k_globalize_objects(const tg_object_data* __restrict__ p_objects
 /*
  * SURVEY.md section 8e "second exchange": the LUT-index bytes (512 B per cluster) exist only on the GPU that owns the
  * cluster. After the visibility merge every rank looks at every pixel; where the winning pointer is its own it writes
- * (global object idx << 32 | packed colour), elsewhere 0. A max-reduce-scatter by screen tile then hands each rank the
+ * ((global object idx + 1) << 32 | packed colour), elsewhere 0. A max-reduce-scatter by screen tile then hands each rank the
  * resolved words of exactly the rows it shades.
  */
 __global__ void __launch_bounds__(256) k_resolve_material(const u64* __restrict__ p_vis, u64 n_pixels, u64 n_padded, const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_c2o,
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(256) k_resolve_material(const u64* __restrict_
             const u32 object_idx = __ldg(&p_c2o[cluster_idx]);
             const u32 color_lut_idx = __ldg(&p_lut_idx[(u64)cluster_idx * 512u + ((u32)packed_data & 511u)]);
             const u32 packed_color = __ldg(&p_color_lut[p_objects[object_idx].lut_idx * 256u + color_lut_idx]);
-            word = ((u64)(global_object_base + object_idx) << 32) | (u64)packed_color;
+            word = ((u64)(global_object_base + object_idx + 1u) << 32) | (u64)packed_color; /* + 1: a resolved word is never 0 */
         }
     }
     p_mat[i] = word;

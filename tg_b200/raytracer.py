@@ -141,6 +141,13 @@ class Raytracer:
         self._check()
         return out
 
+    def read_radiance_rows(self, y0, y1, out=None):
+        if out is None:
+            out = np.empty((y1 - y0, self.width, 4), dtype=np.float32)
+        self._lib.tg_raytracer_read_radiance_rows(C.byref(self._rt), y0, y1, T.ptr(out, T.f32))
+        self._check()
+        return out
+
     def svo_download(self):
         """(svo struct, nodes u32[n], leaf_data u32[n, 65], voxels u32[n_words]); struct freed with svo_free()."""
         svo = T.tg_svo()
