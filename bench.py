@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT = 3840, 2160
 METRIC = "primary+GI Mrays/s at 3840x2160"
-CPU_YSTEP = 16         # cpu_baseline sample: every 16th scanline of the same frame
+CPU_YSTEP = 4          # CPU sample: every 4th scanline of the same frame (540 rows)
 # SURVEY.md section 8d algorithmic bytes
 ALG_BYTES_PER_CLUSTER = 72    # 64 B mask + 4 B pointer + 4 B cluster->object
 ALG_BYTES_PER_OBJECT = 96
@@ -310,10 +310,10 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             arm = CpuArm(build_scene(0, 1))
-            samples = [arm.sample() for _ in range(8)]   # ~10-30 s of CPU work on the box's host cores
+            samples = [arm.sample() for _ in range(12)]  # ~10-30 s of CPU work on the box host cores
             secs = sum(t for t, _ in samples)
             cpu = {"value": sum(n for _, n in samples) / secs / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
-                   "sample": f"8 x ({arm.text(samples[0][1])}); {secs:.1f} s wall"}
+                   "sample": f"12 x ({arm.text(samples[0][1])}); {secs:.1f} s wall"}
             arm.close()
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
