@@ -43,9 +43,11 @@ typedef struct tg_raytracer
     u32                debug_visualization;
     u32                gi_enabled;    /* extension: 1 = one secondary ray per hit pixel through the SVO */
     u32                frame_seed;    /* extension: seed of the secondary-ray RNG */
-    u32                svo_dirty;     /* 1 = full rebuild before next GI frame */
+    u32                svo_dirty;     /* 0 = current; 1 = only transforms changed (incremental update); 2 = objects created / destroyed (full rebuild) */
     u32*               p_object_lut_idx; /* extension: per-object LUT index (README.md:12,18) */
     u32                n_color_luts;
+    u32                n_moved_objects;  /* objects whose transform changed since the last SVO build */
+    u32*               p_moved_objects;  /* [object_capacity] */
 } tg_raytracer;
 
 /* ---- reference entry points (tgvk_raytracer.h:240-251) ------------------------------------ */
@@ -114,6 +116,8 @@ TG_EXPORT void tg_raytracer_set_gi(tg_raytracer* p_raytracer, b32 enabled, u32 f
 /* Stages of render(), individually callable (bench / tests). All asynchronous on the raytracer's stream. */
 TG_EXPORT void tgb200_render_visibility(tg_raytracer* p_raytracer);          /* camera + cull + K1 */
 TG_EXPORT void tgb200_svo_update(tg_raytracer* p_raytracer, b32 force_full); /* K2: rebuild or incremental */
+/* Leaves the most recent tgb200_svo_update re-sampled (== all leaves after a full build). */
+TG_EXPORT u32  tgb200_svo_leaves_resampled(tg_raytracer* p_raytracer);
 TG_EXPORT void tgb200_render_shading(tg_raytracer* p_raytracer);             /* K3: (GI +) LUT shading */
 TG_EXPORT void tgb200_synchronize(tg_raytracer* p_raytracer);
 

@@ -177,3 +177,82 @@ def test_tg_svo_create_entry_point(gpu, oracle):
         L.tgb200_clear_error()
     finally:
         rt.destroy()
+
+
+def _moved(scene, frame, which):
+    """BASELINE configs[3] motion rule: translation.x += 0.5 * frame, angle += 1 degree * frame."""
+    import copy
+    s = copy.copy(scene)
+    s.objects = list(scene.objects)
+    for i in which:
+        o = copy.copy(scene.objects[i])
+        o.center = (o.center[0] + 0.5 * frame, o.center[1], o.center[2])
+        o.angle = float(np.float32(o.angle) + scenes.deg2rad(1.0) * np.float32(frame))
+        s.objects[i] = o
+    return s
+
+
+def test_incremental_update_equals_full_rebuild_and_oracle(gpu, oracle):
+    """Config 4 in miniature: objects move every frame; the incremental update must leave exactly the arrays a full
+    rebuild (and the oracle) produce, while re-sampling only the leaves the moved objects touch."""
+    base = scenes.small_grid(grid=4, dims=(4, 2, 4))
+    movers = [0, 5, 10]
+    rt = from_scene(base)
+    try:
+        rt.svo_update(force_full=True)
+        rt.synchronize()
+        n_full = rt.svo_leaves_resampled()
+        for frame in range(1, 6):
+            cur = _moved(base, frame, movers)
+            for i in movers:
+                rt.set_object_transform(i, cur.objects[i].center, cur.objects[i].angle)
+            rt.svo_update()                      # incremental: only transforms changed
+            rt.synchronize()
+            resampled = rt.svo_leaves_resampled()
+            svo, n1, l1, v1 = rt.svo_download(); rt.svo_free(svo)
+            rt.svo_update(force_full=True)
+            rt.synchronize()
+            svo, n2, l2, v2 = rt.svo_download(); rt.svo_free(svo)
+            compare((n1, l1, v1), (n2, l2, v2), f"frame {frame}: incremental vs full rebuild")
+            assert 0 < resampled < len(l2), (resampled, len(l2))
+            if frame in (1, 5):
+                compare((n1, l1, v1), oracle_svo(oracle, cur), f"frame {frame}: incremental vs oracle")
+        assert n_full > 0
+        # an update with nothing moved re-samples nothing and changes nothing
+        rt.set_object_transform(1, base.objects[1].center, base.objects[1].angle)
+        rt.svo_update(); rt.synchronize()
+        svo, n3, l3, v3 = rt.svo_download(); rt.svo_free(svo)
+        compare((n3, l3, v3), (n2, l2, v2), "no-op move")
+        # creating an object afterwards forces a full rebuild (pointer table changed)
+        rt.create_object_from_data((0.0, 40.0, 0.0), (8, 8, 8), 0.2, (0.0, 1.0, 0.0), np.full((1, 16), 0xFFFFFFFF, dtype=np.uint32))
+        rt.svo_update(); rt.synchronize()
+        assert rt.svo_leaves_resampled() >= len(l2)
+    finally:
+        rt.destroy()
+
+
+def test_config4_dynamic_scene_full_size(gpu):
+    """BASELINE configs[3]: the 10^9-voxel scene, 64 objects moving per frame. Objects 0..63 (the rule of SURVEY 8d) lie
+    outside the +-512 box; the 64 objects nearest to the player are the ones that exercise the update."""
+    full = scenes.config2()
+    order = np.argsort([o.center[0] ** 2 + o.center[2] ** 2 for o in full.objects])
+    for movers in (list(range(64)), [int(i) for i in order[:64]]):
+        rt = from_scene(full)
+        try:
+            rt.svo_update(force_full=True); rt.synchronize()
+            for frame in (1, 2, 3):
+                cur = _moved(full, frame, movers)
+                for i in movers:
+                    rt.set_object_transform(i, cur.objects[i].center, cur.objects[i].angle)
+                rt.svo_update(); rt.synchronize()
+                t_inc = rt.timings()["svo_ms"]
+                resampled = rt.svo_leaves_resampled()
+                svo, n1, l1, v1 = rt.svo_download(); rt.svo_free(svo)
+                rt.svo_update(force_full=True); rt.synchronize()
+                t_full = rt.timings()["svo_ms"]
+                svo, n2, l2, v2 = rt.svo_download(); rt.svo_free(svo)
+                compare((n1, l1, v1), (n2, l2, v2), f"movers[0]={movers[0]} frame {frame}")
+                assert resampled <= len(l2)
+            print(f"config4 movers[0]={movers[0]}: {resampled}/{len(l2)} leaves re-sampled, incremental {t_inc:.3f} ms vs full {t_full:.3f} ms")
+        finally:
+            rt.destroy()

@@ -45,6 +45,7 @@ SYMBOLS = {
     "tg_raytracer_set_gi": (None, [_RT, T.b32, T.u32]),
     "tgb200_render_visibility": (None, [_RT]),
     "tgb200_svo_update": (None, [_RT, T.b32]),
+    "tgb200_svo_leaves_resampled": (T.u32, [_RT]),
     "tgb200_render_shading": (None, [_RT]),
     "tgb200_synchronize": (None, [_RT]),
     "tg_raytracer_read_visibility": (None, [_RT, _P(T.u64)]),

@@ -26,9 +26,17 @@ struct tgb_svo_device
     b32  valid;
     /* build scratch */
     u32* d_pairs_a;     /* cluster pointers grouped by leaf (segments in dense-leaf order), grown on demand */
-    u32* d_pairs_b;     /* previous build's pairs (incremental update) */
+    u32* d_pair_leaf_a; /* dense leaf of every pair (incremental update: which leaves did a moved object reach before) */
+    u32* d_pairs_b;     /* the other half of the ping-pong: an incremental update reads the previous build's pairs */
+    u32* d_pair_leaf_b;
     u8*  d_pair_flags;  /* per pair: the cluster set at least one bit of the leaf */
-    u64  pair_capacity;
+    u64  pair_capacity, pair_capacity_b, pair_flags_capacity;
+    u32* d_moved_indices; /* [object_capacity] staging of the moved-object list */
+    u32* d_voxels_alt;  /* spare leaf arrays: an incremental update writes here, copies clean leaves over, then swaps */
+    u32* d_leaf_data_alt;
+    u32* d_object_moved; /* [object_capacity] object moved since the last build */
+    b32  incremental_ok; /* the current arrays and pair lists come from a K2 build of the current object set */
+    u32  n_leaves_resampled; /* leaves the last update re-sampled (the rest were copied) */
     u32* d_scratch;     /* dense-tree arrays, see tgb_svo.cu */
     u64  scratch_capacity;
     u32* d_object_flags; /* [object_capacity] object can touch the SVO box */

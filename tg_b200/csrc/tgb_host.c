@@ -227,10 +227,11 @@ void tg_raytracer_create(const tg_camera* p_camera, u32 max_n_objects, u32 max_n
     p_raytracer->p_device = p_device;
     p_raytracer->width = tgb__default_w;
     p_raytracer->height = tgb__default_h;
-    p_raytracer->svo_dirty = 1;
     p_raytracer->frame_seed = 1;
     tgb200_scene_init(&p_raytracer->scene, max_n_objects, max_n_clusters);
     p_raytracer->p_object_lut_idx = (u32*)calloc(max_n_objects, sizeof(u32));
+    p_raytracer->p_moved_objects = (u32*)calloc(max_n_objects, sizeof(u32));
+    p_raytracer->svo_dirty = 2;
 }
 
 void tg_raytracer_destroy(tg_raytracer* p_raytracer)
@@ -241,6 +242,7 @@ void tg_raytracer_destroy(tg_raytracer* p_raytracer)
     if (p_raytracer->p_device) tgbd_destroy(p_raytracer->p_device);
     if (p_raytracer->scene.p_objects) tgb200_scene_free(&p_raytracer->scene);
     free(p_raytracer->p_object_lut_idx);
+    free(p_raytracer->p_moved_objects);
     memset(p_raytracer, 0, sizeof(*p_raytracer));
 }
 
@@ -317,7 +319,7 @@ u32 tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v
         }
     }
     if (!p_lut_indices) tgbd_fill_default_lut_idx(d, first, n, p_object->n_cluster_pointers_per_dim.x);
-    p_raytracer->svo_dirty = 1;
+    p_raytracer->svo_dirty = 2;
     return tgb200_last_error() ? TG_U32_MAX : object_idx;
 }
 
@@ -359,7 +361,7 @@ void tg_raytracer_destroy_object(tg_raytracer* p_raytracer, u32 object_idx)
             tgb__upload_object_record(p_raytracer, i);
         }
     }
-    p_raytracer->svo_dirty = 1;
+    p_raytracer->svo_dirty = 2;
 }
 
 void tg_raytracer_set_object_transform(tg_raytracer* p_raytracer, u32 object_idx, v3 translation, f32 angle_in_radians, v3 axis)
@@ -372,7 +374,9 @@ void tg_raytracer_set_object_transform(tg_raytracer* p_raytracer, u32 object_idx
     p_object->angle_in_radians = angle_in_radians;
     p_object->axis = axis;
     tgb__upload_object_record(p_raytracer, object_idx);
-    p_raytracer->svo_dirty = 1;
+    if (p_raytracer->n_moved_objects < p_scene->object_capacity) p_raytracer->p_moved_objects[p_raytracer->n_moved_objects++] = object_idx;
+    else p_raytracer->svo_dirty = 2; /* more edits than objects: rebuild */
+    if (p_raytracer->svo_dirty < 1) p_raytracer->svo_dirty = 1;
 }
 
 void tg_raytracer_color_lut_set_ex(tg_raytracer* p_raytracer, u32 lut_idx, u8 index, f32 r, f32 g, f32 b)
@@ -411,10 +415,28 @@ void tgb200_svo_update(tg_raytracer* p_raytracer, b32 force_full)
     /* tgvk_raytracer.c:1193-1195: fixed +-512 box */
     const v3 extent_min = { -512.0f, -512.0f, -512.0f };
     const v3 extent_max = {  512.0f,  512.0f,  512.0f };
-    if (tgbd_svo_build(p_raytracer->p_device, extent_min, extent_max, p_raytracer->scene.n_cluster_pointers, p_raytracer->scene.object_capacity))
+    b32 ok;
+    if (!force_full && p_raytracer->svo_dirty == 1)
+    {
+        /* only transforms changed: re-sample the leaves the moved objects touch(ed), copy the rest */
+        ok = tgbd_svo_update_objects(p_raytracer->p_device, extent_min, extent_max, p_raytracer->scene.n_cluster_pointers, p_raytracer->scene.object_capacity,
+                                     p_raytracer->n_moved_objects, p_raytracer->p_moved_objects);
+    }
+    else
+    {
+        ok = tgbd_svo_build(p_raytracer->p_device, extent_min, extent_max, p_raytracer->scene.n_cluster_pointers, p_raytracer->scene.object_capacity);
+    }
+    if (ok)
     {
         p_raytracer->svo_dirty = 0;
+        p_raytracer->n_moved_objects = 0;
     }
+}
+
+u32 tgb200_svo_leaves_resampled(tg_raytracer* p_raytracer)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_svo_leaves_resampled")) return 0;
+    return tgbd_svo_leaves_resampled(p_raytracer->p_device);
 }
 
 void tgb200_render_shading(tg_raytracer* p_raytracer)
@@ -567,6 +589,7 @@ void tg_svo_create(v3 extent_min, v3 extent_max, const tg_scene* p_scene, tg_svo
     if (!tgb__alive(p_raytracer, "tg_svo_create")) return;
     if (!tgbd_svo_build(p_raytracer->p_device, extent_min, extent_max, p_scene->n_cluster_pointers, p_scene->object_capacity)) return;
     p_raytracer->svo_dirty = 0;
+    p_raytracer->n_moved_objects = 0;
     tgb200_svo_download(p_raytracer, p_svo);
 }
 
@@ -615,7 +638,7 @@ void tgb200_comm_destroy(tg_raytracer* p_raytracer)
 void tgb200_mark_svo_dirty(tg_raytracer* p_raytracer)
 {
     if (!tgb__alive(p_raytracer, "tgb200_mark_svo_dirty")) return;
-    p_raytracer->svo_dirty = 1;
+    p_raytracer->svo_dirty = 2;
 }
 
 void tgb200_gather_radiance(tg_raytracer* p_raytracer)

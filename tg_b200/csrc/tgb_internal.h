@@ -71,7 +71,11 @@ b32   tgbd_gather_radiance(struct tgb_device* d);
 
 /* ---- tgb_svo.cu ---- */
 b32   tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity);
-b32   tgbd_svo_update_objects(struct tgb_device* d, u32 n_moved, const u32* p_object_indices, const tg_object_data* p_old_records);
+/* incremental: only the leaves a moved object reaches now or reached in the previous build are re-sampled, the tree is
+ * laid out afresh and clean leaves are copied; the arrays equal a full rebuild. Falls back to a full build when needed. */
+b32   tgbd_svo_update_objects(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity, u32 n_moved, const u32* p_object_indices);
+void  tgbd_svo_invalidate_incremental(struct tgb_device* d);
+u32   tgbd_svo_leaves_resampled(struct tgb_device* d);
 b32   tgbd_svo_counts(struct tgb_device* d, u32* p_n_nodes, u32* p_n_leaves, u32* p_n_voxel_words, v3* p_min, v3* p_max);
 b32   tgbd_svo_set(struct tgb_device* d, v3 bmin, v3 bmax, u32 n_nodes, const void* p_nodes, u32 n_leaves, const void* p_leaf_data, u32 n_voxel_words, const void* p_voxels);
 

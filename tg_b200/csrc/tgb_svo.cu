@@ -56,7 +56,9 @@ enum
     TGB_SCR_DENSE_OF_LEAF = TGB_SCR_CUR + TGB_SVO_MAX_LEAVES, /* [32768] dense leaf per data_pointer */
     TGB_SCR_DIRTY = TGB_SCR_DENSE_OF_LEAF + TGB_SVO_MAX_LEAVES, /* [32768] leaf must be re-sampled (incremental) */
     TGB_SCR_CNT_G = TGB_SCR_DIRTY + TGB_SVO_MAX_LEAVES,  /* arrivals per dense node summed over all ranks (== CNT on one GPU) */
-    TGB_SCR_TOTAL = TGB_SCR_CNT_G + TGB_SVO_DENSE_TOTAL
+    TGB_SCR_CLEARED = TGB_SCR_CNT_G + TGB_SVO_DENSE_TOTAL, /* everything above is zeroed at the start of a build */
+    TGB_SCR_PREV_DP = TGB_SCR_CLEARED,                    /* [32768] data_pointer + 1 of the dense leaf in the PREVIOUS build, 0 = none */
+    TGB_SCR_TOTAL = TGB_SCR_PREV_DP + TGB_SVO_MAX_LEAVES
 };
 
 /* counts block d_counts: [0] nodes, [1] leaves, [2] pairs, [3] error flags */
@@ -187,7 +189,7 @@ __global__ void k_svo_object_flags(const tg_object_data* __restrict__ p_objects,
 template <bool SCATTER>
 __global__ void __launch_bounds__(128) k_svo_descend(const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_c2o, const tg_object_data* __restrict__ p_objects,
                                                      const u32* __restrict__ p_object_flags, const u32* __restrict__ p_masks, u32 n_cluster_pointers, v3 bmin, v3 bmax,
-                                                     u32* __restrict__ p_scratch, u32* __restrict__ p_pairs, const u32* __restrict__ p_counts)
+                                                     u32* __restrict__ p_scratch, u32* __restrict__ p_pairs, u32* __restrict__ p_pair_leaf, const u32* __restrict__ p_moved)
 {
     const u32 cluster_pointer = blockIdx.x * blockDim.x + threadIdx.x;
     if (cluster_pointer >= n_cluster_pointers) return;
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(128) k_svo_descend(const u32* __restrict__ p_c
 
     const tg_object_data o = p_objects[object_idx];
     const m4 ws2ms = tgb_svo_ws2ms(o, cluster_pointer - o.first_cluster_pointer);
+    const bool moved = !SCATTER && p_moved != NULL && p_moved[object_idx] != 0;
 
     u32* __restrict__ p_cnt = p_scratch + TGB_SCR_CNT;
 
@@ -242,9 +245,11 @@ __global__ void __launch_bounds__(128) k_svo_descend(const u32* __restrict__ p_c
         {
             if (SCATTER)
             {
-                const u32 slot = atomicAdd(&p_scratch[TGB_SCR_CUR + child_path], 1u);
-                p_pairs[p_scratch[TGB_SCR_POFF + child_path] + slot] = cluster_pointer;
+                const u32 slot = p_scratch[TGB_SCR_POFF + child_path] + atomicAdd(&p_scratch[TGB_SCR_CUR + child_path], 1u);
+                p_pairs[slot] = cluster_pointer;
+                p_pair_leaf[slot] = child_path;
             }
+            else if (moved) p_scratch[TGB_SCR_DIRTY + child_path] = 1u; /* a moved object reaches this leaf NOW */
         }
         else
         {
@@ -511,6 +516,50 @@ __global__ void __launch_bounds__(TGB_LEAF_THREADS) k_svo_fill_leaves(const u32*
     if (tid == 0) p_data[0] = s_n < TG_SVO_LEAF_MAX_CLUSTERS ? s_n : TG_SVO_LEAF_MAX_CLUSTERS;
 }
 
+/* ---- incremental update ---------------------------------------------------------------------------------------- */
+__global__ void k_svo_set_moved(const u32* __restrict__ p_indices, u32 n, u32 object_capacity, u32* __restrict__ p_moved)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && p_indices[i] < object_capacity) p_moved[p_indices[i]] = 1u;
+}
+
+/* a moved object reached this leaf in the PREVIOUS build: its old contribution has to go */
+__global__ void k_svo_mark_dirty_prev(const u32* __restrict__ p_pairs_prev, const u32* __restrict__ p_pair_leaf_prev, u32 n_pairs_prev, const u32* __restrict__ p_cluster_pointers,
+                                      const u32* __restrict__ p_c2o, const u32* __restrict__ p_moved, u32* __restrict__ p_scratch)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs_prev) return;
+    const u32 object_idx = __ldg(&p_c2o[__ldg(&p_cluster_pointers[p_pairs_prev[i]])]);
+    if (p_moved[object_idx]) p_scratch[TGB_SCR_DIRTY + p_pair_leaf_prev[i]] = 1u;
+}
+
+/* one CTA per leaf of the NEW layout: an untouched leaf that existed before is copied (4 KiB + 260 B), any other is flagged for re-sampling */
+__global__ void __launch_bounds__(256) k_svo_copy_clean(u32* __restrict__ p_scratch, const u32* __restrict__ p_leaf_data_old, const u32* __restrict__ p_voxels_old,
+                                                        u32* __restrict__ p_leaf_data, u32* __restrict__ p_voxels, u32* __restrict__ p_counts)
+{
+    const u32 data_pointer = blockIdx.x;
+    const u32 dense = p_scratch[TGB_SCR_DENSE_OF_LEAF + data_pointer];
+    const u32 prev = p_scratch[TGB_SCR_PREV_DP + dense];
+    const bool dirty = p_scratch[TGB_SCR_DIRTY + dense] != 0 || prev == 0;
+    __syncthreads();
+    if (dirty)
+    {
+        if (threadIdx.x == 0) { p_scratch[TGB_SCR_DIRTY + dense] = 1u; atomicAdd(&p_counts[4], 1u); }
+        return;
+    }
+    const uint4* p_src = reinterpret_cast<const uint4*>(p_voxels_old + (u64)(prev - 1u) * TG_SVO_BLOCK_WORDS);
+    uint4* p_dst = reinterpret_cast<uint4*>(p_voxels + (u64)data_pointer * TG_SVO_BLOCK_WORDS);
+    for (u32 i = threadIdx.x; i < TG_SVO_BLOCK_WORDS / 4; i += blockDim.x) p_dst[i] = p_src[i];
+    if (threadIdx.x < 65u) p_leaf_data[(u64)data_pointer * 65u + threadIdx.x] = p_leaf_data_old[(u64)(prev - 1u) * 65u + threadIdx.x];
+}
+
+/* remember where every dense leaf lives in the arrays just built */
+__global__ void k_svo_save_prev(u32* __restrict__ p_scratch, u32 n_leaves)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_leaves) p_scratch[TGB_SCR_PREV_DP + p_scratch[TGB_SCR_DENSE_OF_LEAF + i]] = i + 1u;
+}
+
 /* ---- pass 5 (multi-GPU): merge the per-rank leaf contributions ------------------------------------------------ */
 /*
  * Each rank sampled only its own clusters. A leaf's voxel bits are an OR over clusters (order-free, S4) and its index
@@ -552,10 +601,12 @@ static b32 tgbd__svo_ensure(struct tgb_device* d)
         TGB_CUDA(cudaMalloc(&s->d_scratch, (u64)TGB_SCR_TOTAL * sizeof(u32)));
         s->scratch_capacity = TGB_SCR_TOTAL;
         TGB_CUDA(cudaMalloc(&s->d_object_flags, (u64)d->object_capacity * sizeof(u32)));
+        TGB_CUDA(cudaMalloc(&s->d_moved_indices, (u64)d->object_capacity * sizeof(u32)));
     }
     return TG_TRUE;
 }
 
+/* the pair lists of the build about to run go to half "a"; an incremental update first moves the previous lists to half "b" */
 static b32 tgbd__svo_ensure_pairs(struct tgb_device* d, u64 n_pairs)
 {
     tgb_svo_device* s = &d->svo;
@@ -563,11 +614,24 @@ static b32 tgbd__svo_ensure_pairs(struct tgb_device* d, u64 n_pairs)
     u64 cap = s->pair_capacity ? s->pair_capacity : (1u << 16);
     while (cap < n_pairs) cap *= 2;
     if (s->d_pairs_a) TGB_CUDA(cudaFree(s->d_pairs_a));
-    if (s->d_pair_flags) TGB_CUDA(cudaFree(s->d_pair_flags));
-    s->d_pairs_a = NULL; s->d_pair_flags = NULL; s->pair_capacity = 0;
+    if (s->d_pair_leaf_a) TGB_CUDA(cudaFree(s->d_pair_leaf_a));
+    s->d_pairs_a = NULL; s->d_pair_leaf_a = NULL; s->pair_capacity = 0;
     TGB_CUDA(cudaMalloc(&s->d_pairs_a, cap * sizeof(u32)));
-    TGB_CUDA(cudaMalloc(&s->d_pair_flags, cap));
+    TGB_CUDA(cudaMalloc(&s->d_pair_leaf_a, cap * sizeof(u32)));
     s->pair_capacity = cap;
+    return TG_TRUE;
+}
+
+static b32 tgbd__svo_ensure_pair_flags(struct tgb_device* d, u64 n_pairs)
+{
+    tgb_svo_device* s = &d->svo;
+    if (n_pairs <= s->pair_flags_capacity) return TG_TRUE;
+    u64 cap = s->pair_flags_capacity ? s->pair_flags_capacity : (1u << 16);
+    while (cap < n_pairs) cap *= 2;
+    if (s->d_pair_flags) TGB_CUDA(cudaFree(s->d_pair_flags));
+    s->d_pair_flags = NULL; s->pair_flags_capacity = 0;
+    TGB_CUDA(cudaMalloc(&s->d_pair_flags, cap));
+    s->pair_flags_capacity = cap;
     return TG_TRUE;
 }
 
@@ -592,18 +656,49 @@ static b32 tgbd__svo_ensure_gather(struct tgb_device* d, u32 n_leaves)
  * are summed over the ranks (ncclAllReduce, 150 KB) so that every rank lays out the SAME tree, each rank samples its
  * clusters into a partial copy of every leaf, the partial leaves are all-gathered and OR-combined (pass 5). The result
  * is bit-identical on every rank and to a single-GPU build over the union of the shards. Collective: all ranks call it.
+ *
+ * Incremental update (single GPU, only transforms changed since the previous K2 build): the per-cluster walk and the
+ * layout run in full (they are cheap and keep the node array canonical), but only the leaves a moved object reaches now
+ * or reached in the previous build are re-sampled; every other leaf is copied from the previous arrays to its new
+ * data_pointer. The three arrays equal a full rebuild bit for bit (tests/test_svo_gpu.py).
  */
-extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity)
+static b32 tgbd__svo_run(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity, bool incremental, u32 n_moved, const u32* p_moved_indices)
 {
     TGB_CUDA(cudaSetDevice(d->device));
     if (!tgbd__svo_ensure(d)) return TG_FALSE;
     tgb_svo_device* s = &d->svo;
     const bool sharded = d->p_comm != NULL && d->n_ranks > 1;
+    incremental = incremental && !sharded && s->valid && s->incremental_ok
+               && s->bmin.x == extent_min.x && s->bmin.y == extent_min.y && s->bmin.z == extent_min.z
+               && s->bmax.x == extent_max.x && s->bmax.y == extent_max.y && s->bmax.z == extent_max.z;
+    const u32 n_pairs_prev = s->n_pairs;
     s->valid = TG_FALSE;
     s->bmin = extent_min; s->bmax = extent_max;
 
     TGB_CUDA(cudaEventRecord(d->ev[5], d->stream));
-    TGB_CUDA(cudaMemsetAsync(s->d_scratch, 0, (u64)TGB_SCR_TOTAL * sizeof(u32), d->stream));
+    if (incremental)
+    {
+        /* previous pair lists -> half "b" (pointer swap), spare leaf arrays on demand */
+        u32* t;
+        t = s->d_pairs_a; s->d_pairs_a = s->d_pairs_b; s->d_pairs_b = t;
+        t = s->d_pair_leaf_a; s->d_pair_leaf_a = s->d_pair_leaf_b; s->d_pair_leaf_b = t;
+        const u64 c = s->pair_capacity; s->pair_capacity = s->pair_capacity_b; s->pair_capacity_b = c;
+        if (!s->d_voxels_alt)
+        {
+            TGB_CUDA(cudaMalloc(&s->d_voxels_alt, (u64)s->voxel_word_capacity * sizeof(u32)));
+            TGB_CUDA(cudaMalloc(&s->d_leaf_data_alt, (u64)s->leaf_capacity * 65 * sizeof(u32)));
+        }
+        TGB_CUDA(cudaMemsetAsync(s->d_object_moved, 0, (u64)object_capacity * sizeof(u32), d->stream));
+        if (n_moved > object_capacity) n_moved = object_capacity;
+        if (n_moved)
+        {
+            TGB_CUDA(cudaMemcpyAsync(s->d_moved_indices, p_moved_indices, (u64)n_moved * sizeof(u32), cudaMemcpyHostToDevice, d->stream));
+            k_svo_set_moved<<<(n_moved + 127) / 128, 128, 0, d->stream>>>(s->d_moved_indices, n_moved, object_capacity, s->d_object_moved);
+            TGB_LAUNCH_CHECK(d);
+        }
+    }
+    TGB_CUDA(cudaMemsetAsync(s->d_scratch, 0, (u64)TGB_SCR_CLEARED * sizeof(u32), d->stream));
+    if (!incremental) TGB_CUDA(cudaMemsetAsync(s->d_scratch + TGB_SCR_PREV_DP, 0, (u64)TGB_SVO_MAX_LEAVES * sizeof(u32), d->stream));
     TGB_CUDA(cudaMemsetAsync(s->d_counts, 0, 16 * sizeof(u32), d->stream));
     TGB_CUDA(cudaMemsetAsync(s->d_nodes, 0, (u64)s->node_capacity * sizeof(u32), d->stream));
 
@@ -613,7 +708,13 @@ extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max
     if (grid)
     {
         k_svo_descend<false><<<grid, 128, 0, d->stream>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, s->d_object_flags, d->d_masks, n_cluster_pointers,
-                                                         extent_min, extent_max, s->d_scratch, NULL, s->d_counts);
+                                                         extent_min, extent_max, s->d_scratch, NULL, NULL, incremental ? s->d_object_moved : NULL);
+        TGB_LAUNCH_CHECK(d);
+    }
+    if (incremental && n_pairs_prev)
+    {
+        k_svo_mark_dirty_prev<<<(n_pairs_prev + 255) / 256, 256, 0, d->stream>>>(s->d_pairs_b, s->d_pair_leaf_b, n_pairs_prev, d->d_cluster_pointers, d->d_c2o,
+                                                                                s->d_object_moved, s->d_scratch);
         TGB_LAUNCH_CHECK(d);
     }
     TGB_CUDA(cudaMemcpyAsync(s->d_scratch + TGB_SCR_CNT_G, s->d_scratch + TGB_SCR_CNT, (u64)TGB_SVO_DENSE_TOTAL * sizeof(u32), cudaMemcpyDeviceToDevice, d->stream));
@@ -629,25 +730,32 @@ extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max
     {
         tgb_set_error("svo build: capacity exceeded (flags %u: 1 = child pointer >= 0xFFFF, 2 = nodes %u > %u, 4 = leaves %u > %u; tg_sparse_voxel_octree.c:116,408,413)",
                       counts[3], counts[0], s->node_capacity, counts[1], s->leaf_capacity);
+        s->incremental_ok = TG_FALSE;
         return TG_FALSE;
     }
     s->n_nodes = counts[0];
     s->n_leaves = counts[1];
-    if (!tgbd__svo_ensure_pairs(d, counts[2])) return TG_FALSE;
+    if (!tgbd__svo_ensure_pairs(d, counts[2] ? counts[2] : 1) || !tgbd__svo_ensure_pair_flags(d, counts[2] ? counts[2] : 1)) return TG_FALSE;
     if (sharded && !tgbd__svo_ensure_gather(d, s->n_leaves)) return TG_FALSE;
 
     if (counts[2] && grid)
     {
         k_svo_descend<true><<<grid, 128, 0, d->stream>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, s->d_object_flags, d->d_masks, n_cluster_pointers,
-                                                        extent_min, extent_max, s->d_scratch, s->d_pairs_a, s->d_counts);
+                                                        extent_min, extent_max, s->d_scratch, s->d_pairs_a, s->d_pair_leaf_a, NULL);
         TGB_LAUNCH_CHECK(d);
     }
+    s->n_leaves_resampled = s->n_leaves;
     if (s->n_leaves)
     {
-        u32* p_voxels = sharded ? s->d_part : s->d_voxels;
-        u32* p_leaf = sharded ? s->d_part + (u64)s->n_leaves * TG_SVO_BLOCK_WORDS : s->d_leaf_data;
+        u32* p_voxels = sharded ? s->d_part : (incremental ? s->d_voxels_alt : s->d_voxels);
+        u32* p_leaf = sharded ? s->d_part + (u64)s->n_leaves * TG_SVO_BLOCK_WORDS : (incremental ? s->d_leaf_data_alt : s->d_leaf_data);
+        if (incremental)
+        {
+            k_svo_copy_clean<<<s->n_leaves, 256, 0, d->stream>>>(s->d_scratch, s->d_leaf_data, s->d_voxels, p_leaf, p_voxels, s->d_counts);
+            TGB_LAUNCH_CHECK(d);
+        }
         k_svo_fill_leaves<<<s->n_leaves, TGB_LEAF_THREADS, 0, d->stream>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_masks, extent_min, extent_max,
-                                                                           s->d_scratch, s->d_pairs_a, s->d_pair_flags, p_leaf, p_voxels, 0,
+                                                                           s->d_scratch, s->d_pairs_a, s->d_pair_flags, p_leaf, p_voxels, incremental ? 1u : 0u,
                                                                            sharded ? d->global_pointer_base : 0u);
         TGB_LAUNCH_CHECK(d);
         if (sharded)
@@ -657,20 +765,41 @@ extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max
             k_svo_combine<<<s->n_leaves, 256, 0, d->stream>>>(s->d_gather, d->n_ranks, s->n_leaves, s->d_leaf_data, s->d_voxels);
             TGB_LAUNCH_CHECK(d);
         }
+        if (incremental)
+        {
+            u32* t;
+            t = s->d_voxels; s->d_voxels = s->d_voxels_alt; s->d_voxels_alt = t;
+            t = s->d_leaf_data; s->d_leaf_data = s->d_leaf_data_alt; s->d_leaf_data_alt = t;
+        }
     }
+    /* where every dense leaf lives now (for the next incremental update) */
+    TGB_CUDA(cudaMemsetAsync(s->d_scratch + TGB_SCR_PREV_DP, 0, (u64)TGB_SVO_MAX_LEAVES * sizeof(u32), d->stream));
+    if (s->n_leaves)
+    {
+        k_svo_save_prev<<<(s->n_leaves + 255) / 256, 256, 0, d->stream>>>(s->d_scratch, s->n_leaves);
+        TGB_LAUNCH_CHECK(d);
+    }
+    if (incremental) TGB_CUDA(cudaMemcpyAsync(&s->n_leaves_resampled, s->d_counts + 4, sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
     TGB_CUDA(cudaEventRecord(d->ev[6], d->stream));
     d->ev_svo = TG_TRUE;
     s->n_pairs = counts[2];
     s->valid = TG_TRUE;
+    s->incremental_ok = !sharded;
     return TG_TRUE;
 }
 
-extern "C" b32 tgbd_svo_update_objects(struct tgb_device* d, u32 n_moved, const u32* p_object_indices, const tg_object_data* p_old_records)
+extern "C" b32 tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity)
 {
-    (void)n_moved; (void)p_object_indices; (void)p_old_records;
-    tgb_set_error("tgbd_svo_update_objects: not built yet");
-    return TG_FALSE;
+    return tgbd__svo_run(d, extent_min, extent_max, n_cluster_pointers, object_capacity, false, 0, NULL);
 }
+
+extern "C" b32 tgbd_svo_update_objects(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity, u32 n_moved, const u32* p_object_indices)
+{
+    return tgbd__svo_run(d, extent_min, extent_max, n_cluster_pointers, object_capacity, true, n_moved, p_object_indices);
+}
+
+extern "C" void tgbd_svo_invalidate_incremental(struct tgb_device* d) { d->svo.incremental_ok = TG_FALSE; }
+extern "C" u32 tgbd_svo_leaves_resampled(struct tgb_device* d) { cudaStreamSynchronize(d->stream); return d->svo.n_leaves_resampled; }
 
 extern "C" b32 tgbd_svo_counts(struct tgb_device* d, u32* p_n_nodes, u32* p_n_leaves, u32* p_n_voxel_words, v3* p_min, v3* p_max)
 {
@@ -706,5 +835,6 @@ extern "C" b32 tgbd_svo_set(struct tgb_device* d, v3 bmin, v3 bmax, u32 n_nodes,
     s->bmin = bmin; s->bmax = bmax;
     s->n_nodes = n_nodes; s->n_leaves = n_leaves;
     s->valid = TG_TRUE;
+    s->incremental_ok = TG_FALSE; /* uploaded arrays: there are no pair lists to update from */
     return TG_TRUE;
 }

@@ -111,7 +111,8 @@ class tg_scene(C.Structure):
 class tg_raytracer(C.Structure):
     _fields_ = [("p_camera", C.POINTER(tg_camera)), ("scene", tg_scene), ("p_device", C.c_void_p),
                 ("width", u32), ("height", u32), ("debug_visualization", u32), ("gi_enabled", u32),
-                ("frame_seed", u32), ("svo_dirty", u32), ("p_object_lut_idx", C.POINTER(u32)), ("n_color_luts", u32)]
+                ("frame_seed", u32), ("svo_dirty", u32), ("p_object_lut_idx", C.POINTER(u32)), ("n_color_luts", u32),
+                ("n_moved_objects", u32), ("p_moved_objects", C.POINTER(u32))]
 
 
 class tgb200_timings(C.Structure):

@@ -114,6 +114,9 @@ class Raytracer:
     def svo_update(self, force_full=False):
         self._lib.tgb200_svo_update(C.byref(self._rt), 1 if force_full else 0)
 
+    def svo_leaves_resampled(self):
+        return self._lib.tgb200_svo_leaves_resampled(C.byref(self._rt))
+
     def render_shading(self):
         self._lib.tgb200_render_shading(C.byref(self._rt))
 
