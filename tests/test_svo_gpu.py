@@ -197,7 +197,7 @@ def test_incremental_update_equals_full_rebuild_and_oracle(gpu, oracle):
     rebuild (and the oracle) produce, while re-sampling only the leaves the moved objects touch."""
     base = scenes.small_grid(grid=4, dims=(4, 2, 4))
     movers = [0, 5, 10]
-    rt = from_scene(base)
+    rt = from_scene(base, max_n_objects=len(base.objects) + 1, max_n_clusters=base.n_clusters + 1)
     try:
         rt.svo_update(force_full=True)
         rt.synchronize()
