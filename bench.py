@@ -266,7 +266,8 @@ def main():
         for k in stage:
             stage[k] += t[k]
     barrier()
-    launches = rt.timings()["n_kernel_launches"]
+    last = rt.timings()
+    launches = last["n_kernel_launches"]
     clocks = sampler.stop()
     dev_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, stops)))
     ms_per_step = dev_ms / args.steps
@@ -320,6 +321,8 @@ def main():
                 "config": {"workload": "BASELINE configs[1]+[2] per GPU: 1,024 objects (2^21 clusters, 1.07e9 voxels), 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)"
                                        + (f"; world = {world} such shards: ncclAllReduce(u64,min) merge, material reduce-scatter, GI split by screen tile" if world > 1 else ""),
                            "rays_per_frame": rays_per_frame, "primary_rays": world * WIDTH * HEIGHT, "gi_rays": n_hit, "svo_build_ms": svo_build_ms, "svo_bytes": svo_bytes,
+                           "visible_objects": last["n_visible_objects"],
+                           "gi_work_rank0": {"rays_traced_through_svo": last["n_gi_rays"], "node_visits": last["n_gi_node_visits"], "dda_steps": last["n_gi_dda_steps"], "advances": last["n_gi_advances"]},
                            "l2": "flushed between steps (256 MiB write, outside the timed events)", "stage_ms": {k: v / args.steps for k, v in stage.items()}},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96 * world, "d2h_bytes_per_step": WIDTH * HEIGHT * 16,

@@ -144,6 +144,11 @@ typedef struct tgb200_timings
     f32 merge_ms;
     u32 n_visible_objects;
     u32 n_kernel_launches; /* kernels of this library launched since create/reset */
+    u32 n_gi_rays;         /* secondary rays the last frame traced through the SVO (those that enter its box) */
+    u32 pad;
+    u64 n_gi_node_visits;  /* work of those rays: node visits, leaf DDA steps, advances (svo_functions.inc loop iterations) */
+    u64 n_gi_dda_steps;
+    u64 n_gi_advances;
 } tgb200_timings;
 TG_EXPORT void tgb200_get_timings(tg_raytracer* p_raytracer, tgb200_timings* p_out);
 TG_EXPORT void tgb200_reset_launch_counter(tg_raytracer* p_raytracer);

@@ -178,3 +178,32 @@ def test_product_does_not_reference_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", tg_b200.LIB_PATH], capture_output=True, text=True).stdout
     assert "libtgo" not in out
+
+
+def test_tg_svo_traverse_host_query_matches_the_oracle_c_variant():
+    """tg_svo_traverse (tg_sparse_voxel_octree.h:53) is a HOST function in the reference and here: random rays over an
+    oracle-built SVO, library vs the oracle's restatement of tg_sparse_voxel_octree.c:558-740, exact equality."""
+    from oracle import oracle as O
+    L = tg_b200.lib()
+    s = scenes.small_grid()
+    svo = O.svo_create(O.SceneView.from_scene(s, with_lut=False))
+    rng = np.random.default_rng(5)
+    n_hit = 0
+    for k in range(2000):
+        o = rng.uniform(-90, 90, 3).astype(np.float32)
+        if k % 3 == 0:
+            o[1] = np.float32(rng.uniform(20, 200))
+        d = rng.normal(size=3).astype(np.float32)
+        if k % 7 == 0:
+            d[int(rng.integers(3))] = 0.0  # axis-parallel components: the -/+F32_MAX branches
+        d = d / np.float32(np.sqrt((d * d).sum(dtype=np.float32)))
+        got = (T.f32(), T.u32(), T.u32())
+        want = (T.f32(), T.u32(), T.u32())
+        a = L.tg_svo_traverse(C.byref(svo), T.v3(*o), T.v3(*d), C.byref(got[0]), C.byref(got[1]), C.byref(got[2]))
+        b = O.lib().tgo_svo_traverse_c(C.byref(svo), T.v3(*o), T.v3(*d), C.byref(want[0]), C.byref(want[1]), C.byref(want[2]))
+        assert bool(a) == bool(b), k
+        assert [g.value for g in got] == [w.value for w in want], (k, [g.value for g in got], [w.value for w in want])
+        n_hit += bool(a)
+    assert 100 < n_hit < 1900
+    O.svo_destroy(svo)
+    assert L.tgb200_last_error() is None

@@ -191,6 +191,6 @@ def test_config2_full_size_scanline_subset_and_properties(gpu, oracle):
         # idempotence at full size
         rt.render_visibility(); rt.synchronize()
         assert np.array_equal(got, rt.read_visibility())
-        assert t["n_visible_objects"] < 200
+        assert 0 < t["n_visible_objects"] < 400
     finally:
         rt.destroy()

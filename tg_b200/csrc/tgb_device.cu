@@ -29,7 +29,9 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMalloc(&d->d_frames_sorted, no * sizeof(tgb_object_frame)));
     TGB_CUDA(cudaMalloc(&d->d_frames_all, no * sizeof(tgb_object_frame)));
     TGB_CUDA(cudaMalloc(&d->d_visible_count, 4 * sizeof(u32)));
-    TGB_CUDA(cudaMalloc(&d->d_gi_count, 4 * sizeof(u32)));
+    TGB_CUDA(cudaMalloc(&d->d_gi_count, 32 * sizeof(u32)));
+    TGB_CUDA(cudaMallocHost(&d->h_gi_stats, 32 * sizeof(u32)));
+    memset(d->h_gi_stats, 0, 32 * sizeof(u32));
     {
         int n_sms = 0;
         TGB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, d->device));
@@ -145,6 +147,7 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_count);
     cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
+    if (d->h_gi_stats) cudaFreeHost(d->h_gi_stats);
     cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts);
     cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch); cudaFree(d->svo.d_pair_flags); cudaFree(d->svo.d_object_flags); cudaFree(d->svo.d_pair_leaf_a); cudaFree(d->svo.d_pair_leaf_b);
     cudaFree(d->svo.d_voxels_alt); cudaFree(d->svo.d_leaf_data_alt); cudaFree(d->svo.d_object_moved); cudaFree(d->svo.d_moved_indices); cudaFree(d->svo.d_part); cudaFree(d->svo.d_gather);
@@ -274,7 +277,18 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
     p_out->svo_ms = d->svo_ms;
     p_out->shading_ms = d->shading_ms;
     p_out->merge_ms = d->merge_ms;
+    if (d->ev_vis) d->n_visible_objects = d->h_visible_count[0];
     p_out->n_visible_objects = d->n_visible_objects;
+    p_out->n_gi_rays = d->h_gi_stats[0];
+    p_out->n_gi_node_visits = ((const u64*)d->h_gi_stats)[1];
+    p_out->n_gi_dda_steps = ((const u64*)d->h_gi_stats)[2];
+    p_out->n_gi_advances = ((const u64*)d->h_gi_stats)[3];
+    if (getenv("TGB200_GI_HISTOGRAM"))
+    {
+        fprintf(stderr, "[tgb200] GI rays: max node visits %u; log2 histogram:", d->h_gi_stats[8]);
+        for (int i = 0; i < 13; i++) fprintf(stderr, " %u", d->h_gi_stats[16 + i]);
+        fprintf(stderr, "\n");
+    }
     p_out->n_kernel_launches = d->n_kernel_launches;
 }
 

@@ -64,7 +64,8 @@ struct tgb_device
     float4*         d_gi_q0;      /* secondary-ray queue, [w*h] each: origin.xyz + pixel | direction | ambient */
     float4*         d_gi_q1;
     float4*         d_gi_q2;
-    u32*            d_gi_count;   /* [0] queued, [1] fetched */
+    u32*            d_gi_count;   /* u32 [0] queued, [1] fetched; u64 [1] node visits, [2] DDA steps, [3] advances */
+    u32*            h_gi_stats;   /* pinned copy of d_gi_count after the last frame */
     u32             n_sms;
 
     /* multi-GPU (one process per GPU): clusters sharded by object, SVO / objects replicated, GI split by screen tile */

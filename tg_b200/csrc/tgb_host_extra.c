@@ -1,4 +1,4 @@
-/* tgb_host_extra.c -- placeholders (filled in a later milestone). */
+/* tgb_host_extra.c -- host-only entry points of the boundary: the single-ray SVO query, verification hooks, the procedural fill. */
 #include "tgb_internal.h"
 #include "tgb_math.h"
 #include "tgb_hoist.h"
@@ -21,9 +21,148 @@ void tgb200_procedural_solid_bits(u32 object_idx, v3u n_cluster_pointers_per_dim
     tgb_set_error("tgb200_procedural_solid_bits: not built yet");
 }
 
+/* physics/tg_physics.c:394-406 (C twin of collide.inc: TG_MIN / TG_MAX are C ternaries, math/tg_math.h:17-22) */
+static b32 tgb__ray_aabb_c(v3 o, v3 d, v3 bmin, v3 bmax, f32* p_enter, f32* p_exit)
+{
+    const f32 ax = (d.x == 0.0f) ? TG_F32_MIN : ((bmin.x - o.x) / d.x), bx = (d.x == 0.0f) ? TG_F32_MAX : ((bmax.x - o.x) / d.x);
+    const f32 ay = (d.y == 0.0f) ? TG_F32_MIN : ((bmin.y - o.y) / d.y), by = (d.y == 0.0f) ? TG_F32_MAX : ((bmax.y - o.y) / d.y);
+    const f32 az = (d.z == 0.0f) ? TG_F32_MIN : ((bmin.z - o.z) / d.z), bz = (d.z == 0.0f) ? TG_F32_MAX : ((bmax.z - o.z) / d.z);
+    const f32 nx = ax < bx ? ax : bx, ny = ay < by ? ay : by, nz = az < bz ? az : bz;
+    const f32 fx = ax > bx ? ax : bx, fy = ay > by ? ay : by, fz = az > bz ? az : bz;
+    const f32 nxy = nx > ny ? nx : ny, fxy = fx < fy ? fx : fy;
+    *p_enter = nxy > nz ? nxy : nz;
+    *p_exit  = fxy < fz ? fxy : fz;
+    return *p_exit > 0.0f && *p_enter <= *p_exit;
+}
+
+/* tg_sparse_voxel_octree.c:704-707: distance to the far border of a box */
+static f32 tgb__exit_c(v3 bmin, v3 bmax, v3 p, v3 d)
+{
+    const f32 ax = (d.x == 0.0f) ? TG_F32_MIN : ((bmin.x - p.x) / d.x), bx = (d.x == 0.0f) ? TG_F32_MAX : ((bmax.x - p.x) / d.x);
+    const f32 ay = (d.y == 0.0f) ? TG_F32_MIN : ((bmin.y - p.y) / d.y), by = (d.y == 0.0f) ? TG_F32_MAX : ((bmax.y - p.y) / d.y);
+    const f32 az = (d.z == 0.0f) ? TG_F32_MIN : ((bmin.z - p.z) / d.z), bz = (d.z == 0.0f) ? TG_F32_MAX : ((bmax.z - p.z) / d.z);
+    const f32 fx = ax > bx ? ax : bx, fy = ay > by ? ay : by, fz = az > bz ? az : bz;
+    const f32 m = fx < fy ? fx : fy;
+    return m < fz ? m : fz;
+}
+
+/* util/tg_amanatides_woo.c:3-114 on one leaf block: no lower clamp of the start cell, t_max without an `enter` term */
+static b32 tgb__block_dda(v3 hit, v3 d, v3 extent, const u32* p_grid, i32* p_x, i32* p_y, i32* p_z)
+{
+    const f32 cx = floorf(hit.x) < extent.x - 1.0f ? floorf(hit.x) : extent.x - 1.0f;
+    const f32 cy = floorf(hit.y) < extent.y - 1.0f ? floorf(hit.y) : extent.y - 1.0f;
+    const f32 cz = floorf(hit.z) < extent.z - 1.0f ? floorf(hit.z) : extent.z - 1.0f;
+    i32 x = (i32)cx, y = (i32)cy, z = (i32)cz;
+    i32 sx = 0, sy = 0, sz = 0;
+    f32 tmx = TG_F32_MAX, tmy = TG_F32_MAX, tmz = TG_F32_MAX, tdx = TG_F32_MAX, tdy = TG_F32_MAX, tdz = TG_F32_MAX;
+    if (d.x > 0.0f)      { sx = 1;  tmx = ((f32)(x + 1) - hit.x) / d.x; tdx = 1.0f / d.x; }
+    else if (d.x < 0.0f) { sx = -1; tmx = (hit.x - (f32)x) / -d.x;      tdx = 1.0f / -d.x; }
+    if (d.y > 0.0f)      { sy = 1;  tmy = ((f32)(y + 1) - hit.y) / d.y; tdy = 1.0f / d.y; }
+    else if (d.y < 0.0f) { sy = -1; tmy = (hit.y - (f32)y) / -d.y;      tdy = 1.0f / -d.y; }
+    if (d.z > 0.0f)      { sz = 1;  tmz = ((f32)(z + 1) - hit.z) / d.z; tdz = 1.0f / d.z; }
+    else if (d.z < 0.0f) { sz = -1; tmz = (hit.z - (f32)z) / -d.z;      tdz = 1.0f / -d.z; }
+    const u32 ex = (u32)extent.x, ey = (u32)extent.y;
+    if (x < 0 || y < 0 || z < 0) return TG_FALSE; /* the reference would index out of bounds here (AW.c:12-13 has no lower clamp) */
+    for (;;)
+    {
+        const u32 v = ex * ey * (u32)z + ex * (u32)y + (u32)x;
+        if (p_grid[v / 32] & (1u << (v % 32))) { *p_x = x; *p_y = y; *p_z = z; return TG_TRUE; }
+        if (tmx < tmy)
+        {
+            if (tmx < tmz) { tmx += tdx; x += sx; if (x < 0 || (f32)x >= extent.x) break; }
+            else           { tmz += tdz; z += sz; if (z < 0 || (f32)z >= extent.z) break; }
+        }
+        else
+        {
+            if (tmy < tmz) { tmy += tdy; y += sy; if (y < 0 || (f32)y >= extent.y) break; }
+            else           { tmz += tdz; z += sz; if (z < 0 || (f32)z >= extent.z) break; }
+        }
+    }
+    return TG_FALSE;
+}
+
+/*
+ * tg_sparse_voxel_octree.c:558-740: the reference's HOST-side single-ray query over a tg_svo (picking / debugging). It is
+ * part of the boundary (tg_sparse_voxel_octree.h:53) and runs on the host in the reference too, so it does here: one ray
+ * over host arrays is not device work. This is the C variant (distance accumulates t_advance, :709-712; Amanatides-Woo
+ * of util/tg_amanatides_woo.c); the GI kernel follows the GLSL variant.
+ */
 b32 tg_svo_traverse(const tg_svo* p_svo, v3 ray_origin, v3 ray_direction, f32* p_distance, u32* p_node_idx, u32* p_voxel_idx)
 {
-    (void)p_svo; (void)ray_origin; (void)ray_direction; (void)p_distance; (void)p_node_idx; (void)p_voxel_idx;
-    tgb_set_error("tg_svo_traverse: not built yet");
+    *p_distance = TG_F32_MAX;
+    *p_node_idx = TG_U32_MAX;
+    *p_voxel_idx = TG_U32_MAX;
+    if (!p_svo || !p_svo->p_node_buffer) { tgb_set_error("tg_svo_traverse: no SVO"); return TG_FALSE; }
+
+    const v3 extent = tgb_sub(p_svo->max, p_svo->min);
+    const v3 center = tgb_add(p_svo->min, tgb_scale(extent, 0.5f));
+    const v3 o = tgb_sub(ray_origin, center);
+    const v3 d = ray_direction;
+
+    u32 stack_size, idx_stack[TG_SVO_TRAVERSE_STACK_CAPACITY] = { 0 };
+    v3 min_stack[TG_SVO_TRAVERSE_STACK_CAPACITY], max_stack[TG_SVO_TRAVERSE_STACK_CAPACITY];
+    f32 enter, exit;
+    if (!tgb__ray_aabb_c(o, d, p_svo->min, p_svo->max, &enter, &exit)) return TG_FALSE;
+    v3 position = enter > 0.0f ? tgb_add(o, tgb_scale(d, enter)) : o;
+    f32 travelled = enter > 0.0f ? enter : 0.0f;
+
+    stack_size = 1;
+    min_stack[0] = p_svo->min;
+    max_stack[0] = p_svo->max;
+    for (u32 iterations = 0; stack_size > 0 && iterations < 4096u; iterations++) /* Q9: cap valid input never reaches */
+    {
+        const u32 parent_idx = idx_stack[stack_size - 1];
+        const v3 parent_min = min_stack[stack_size - 1], parent_max = max_stack[stack_size - 1];
+        const tg_svo_inner_node node = p_svo->p_node_buffer[parent_idx].inner;
+        const v3 child_extent = tgb_scale(tgb_sub(parent_max, parent_min), 0.5f);
+        u32 oct = 0;
+        v3 child_min = parent_min;
+        v3 child_max = tgb_add(child_min, child_extent);
+        if (child_max.x < position.x || (position.x == child_max.x && d.x > 0.0f)) { oct += 1; child_min.x += child_extent.x; child_max.x += child_extent.x; }
+        if (child_max.y < position.y || (position.y == child_max.y && d.y > 0.0f)) { oct += 2; child_min.y += child_extent.y; child_max.y += child_extent.y; }
+        if (child_max.z < position.z || (position.z == child_max.z && d.z > 0.0f)) { oct += 4; child_min.z += child_extent.z; child_max.z += child_extent.z; }
+
+        b32 advance_to_border = TG_TRUE;
+        if (node.valid_mask & (1u << oct))
+        {
+            u32 rank = 0;
+            for (u32 i = 0; i < oct; i++) rank += (node.valid_mask >> i) & 1u;
+            const u32 child_idx = parent_idx + node.child_pointer + rank;
+            if (node.leaf_mask & (1u << oct))
+            {
+                const u32 data_pointer = p_svo->p_node_buffer[child_idx].leaf.data_pointer;
+                if (p_svo->p_leaf_node_data_buffer[data_pointer].n != 0)
+                {
+                    const u32 first_voxel_id = data_pointer * TG_SVO_BLOCK_VOXEL_COUNT;
+                    i32 vx, vy, vz;
+                    if (tgb__block_dda(tgb_sub(position, child_min), d, child_extent, p_svo->p_voxels_buffer + first_voxel_id / 32, &vx, &vy, &vz))
+                    {
+                        const v3 voxel_min = tgb_add(child_min, tgb_v3((f32)vx, (f32)vy, (f32)vz));
+                        const v3 voxel_max = tgb_add(voxel_min, tgb_v3(1.0f, 1.0f, 1.0f));
+                        tgb__ray_aabb_c(position, d, voxel_min, voxel_max, &enter, &exit);
+                        *p_distance = travelled + enter;
+                        *p_node_idx = child_idx;
+                        *p_voxel_idx = first_voxel_id + (u32)child_extent.x * (u32)child_extent.y * (u32)vz + (u32)child_extent.x * (u32)vy + (u32)vx;
+                        return TG_TRUE;
+                    }
+                }
+            }
+            else if (stack_size < TG_SVO_TRAVERSE_STACK_CAPACITY)
+            {
+                advance_to_border = TG_FALSE;
+                idx_stack[stack_size] = child_idx;
+                min_stack[stack_size] = child_min;
+                max_stack[stack_size] = child_max;
+                stack_size++;
+            }
+        }
+        if (advance_to_border)
+        {
+            const f32 t_advance = tgb__exit_c(child_min, child_max, position, d) + TG_F32_EPSILON;
+            position = tgb_add(position, tgb_scale(d, t_advance));
+            travelled += t_advance;
+            while (stack_size > 0 && !(tgb__exit_c(min_stack[stack_size - 1], max_stack[stack_size - 1], position, d) > TG_F32_EPSILON)) stack_size--;
+        }
+    }
     return TG_FALSE;
 }

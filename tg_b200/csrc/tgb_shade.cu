@@ -105,44 +105,39 @@ __device__ __forceinline__ f32 tgb_exit_distance(v3 bmin, v3 bmax, v3 position, 
     const f32 qz = az != 0.0f ? __fdividef(nz, az) : TG_F32_MAX;
     const f32 q_min = fminf(fminf(qx, qy), qz);
     const f32 limit = q_min + (1e-5f * fabsf(q_min) + 1e-30f);
+    /* common case, branch-free: exactly one axis is within the margin of the smallest quotient -> one IEEE division */
+    const bool cx = qx <= limit, cy = qy <= limit, cz = qz <= limit;
+    const f32 num = cx ? nx : (cy ? ny : nz), den = cx ? ax : (cy ? ay : az);
+    f32 exit = num / den;
     /* __fdividef is only specified for 2^-126 <= |d| <= 2^126 and finite operands: anything unusual takes the exact path */
     const bool odd = !(q_min == q_min) || fabsf(q_min) > 1e30f || (ax != 0.0f && ax < 1e-30f) || (ay != 0.0f && ay < 1e-30f) || (az != 0.0f && az < 1e-30f);
-    f32 exit = TG_F32_MAX;
-    if (ax != 0.0f && (odd || qx <= limit)) exit = tgb_min(exit, nx / ax);
-    if (ay != 0.0f && (odd || qy <= limit)) exit = tgb_min(exit, ny / ay);
-    if (az != 0.0f && (odd || qz <= limit)) exit = tgb_min(exit, nz / az);
+    if (((u32)cx + (u32)cy + (u32)cz != 1u) || odd)
+    {
+        exit = TG_F32_MAX;
+        if (ax != 0.0f && (odd || cx)) exit = tgb_min(exit, nx / ax);
+        if (ay != 0.0f && (odd || cy)) exit = tgb_min(exit, ny / ay);
+        if (az != 0.0f && (odd || cz)) exit = tgb_min(exit, nz / az);
+    }
     return exit;
 }
 
 /*
  * exit_distance(box) > F32_EPSILON (the pop test, svo_functions.inc:296-324) without dividing: q = num / |d| exceeds
  * epsilon for sure when num > 2.5 eps |d| and is below it for sure when num < 0.5 eps |d| (this includes a ray that
- * is on or past the border, num <= 0); only the sliver in between needs the quotient itself.
+ * is on or past the border, num <= 0); only the sliver in between needs the quotient itself. Branch-free unless a
+ * component sits in the sliver.
  */
-__device__ __forceinline__ bool tgb_axis_inside(f32 num, f32 ad)
-{
-    if (ad == 0.0f) return true; /* F32_MAX > eps */
-    if (num > 2.5f * TG_F32_EPSILON * ad) return true;
-    if (num < 0.5f * TG_F32_EPSILON * ad) return false;
-    return num / ad > TG_F32_EPSILON;
-}
 __device__ __forceinline__ bool tgb_still_inside(v3 bmin, v3 bmax, v3 position, v3 d)
 {
-    return tgb_axis_inside(d.x > 0.0f ? bmax.x - position.x : position.x - bmin.x, fabsf(d.x))
-        && tgb_axis_inside(d.y > 0.0f ? bmax.y - position.y : position.y - bmin.y, fabsf(d.y))
-        && tgb_axis_inside(d.z > 0.0f ? bmax.z - position.z : position.z - bmin.z, fabsf(d.z));
-}
-
-/* the child box of svo_functions.inc:57-80 for a known octant (what the shader pushed on its stack) */
-__device__ __forceinline__ void tgb_octant_box(v3 parent_min, v3 parent_max, u32 oct, v3* p_min, v3* p_max)
-{
-    const v3 ce = tgb_scale(tgb_sub(parent_max, parent_min), 0.5f);
-    v3 cmin = parent_min;
-    v3 cmax = tgb_add(cmin, ce);
-    if (oct & 1u) { cmin.x += ce.x; cmax.x += ce.x; }
-    if (oct & 2u) { cmin.y += ce.y; cmax.y += ce.y; }
-    if (oct & 4u) { cmin.z += ce.z; cmax.z += ce.z; }
-    *p_min = cmin; *p_max = cmax;
+    const f32 nx = d.x > 0.0f ? bmax.x - position.x : position.x - bmin.x, ax = fabsf(d.x);
+    const f32 ny = d.y > 0.0f ? bmax.y - position.y : position.y - bmin.y, ay = fabsf(d.y);
+    const f32 nz = d.z > 0.0f ? bmax.z - position.z : position.z - bmin.z, az = fabsf(d.z);
+    const bool in_x = (ax == 0.0f) | (nx > 2.5f * TG_F32_EPSILON * ax), out_x = (ax != 0.0f) & (nx < 0.5f * TG_F32_EPSILON * ax);
+    const bool in_y = (ay == 0.0f) | (ny > 2.5f * TG_F32_EPSILON * ay), out_y = (ay != 0.0f) & (ny < 0.5f * TG_F32_EPSILON * ay);
+    const bool in_z = (az == 0.0f) | (nz > 2.5f * TG_F32_EPSILON * az), out_z = (az != 0.0f) & (nz < 0.5f * TG_F32_EPSILON * az);
+    if (in_x & in_y & in_z) return true;
+    if (out_x | out_y | out_z) return false;
+    return (in_x || nx / ax > TG_F32_EPSILON) && (in_y || ny / ay > TG_F32_EPSILON) && (in_z || nz / az > TG_F32_EPSILON);
 }
 
 /* ---- K3a: per-pixel shading, secondary rays that enter the SVO box are queued ---------------------- */
@@ -376,6 +371,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
     i32 x = 0, y = 0, z = 0;
     const u32* __restrict__ p_block = svo.p_voxels;
     bool exhausted = false;
+    u32 n_visits = 0, n_steps = 0, n_advances = 0; /* work counters (reported through tgb200_timings) */
 
     for (;;)
     {
@@ -425,7 +421,8 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
         {
             if (state == TGB_ST_DDA)
             {
-                /* :178-257 */
+                /* :178-257; the step is written with selects (no branch on which axis advances): adding +0 to the
+                 * other two t_max leaves them bit-identical */
                 const i32 step_x = d.x > 0.0f ? 1 : (d.x < 0.0f ? -1 : 0);
                 const i32 step_y = d.y > 0.0f ? 1 : (d.y < 0.0f ? -1 : 0);
                 const i32 step_z = d.z > 0.0f ? 1 : (d.z < 0.0f ? -1 : 0);
@@ -434,6 +431,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
                 {
                     /* a block row is one word: bit 1024 z + 32 y + x (the builder only makes 32^3 blocks) */
                     const u32 bits = __ldg(&p_block[32 * z + y]);
+                    n_steps++;
                     if ((bits >> x) & 1u)
                     {
                         const v3 voxel_min = tgb_add(child_min, tgb_v3((f32)x, (f32)y, (f32)z));
@@ -444,44 +442,48 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
                         if (enter / far_plane < 1.0f) finished = 1u; else state = TGB_ST_ADV;
                         break;
                     }
-                    if (t_max_x < t_max_y)
-                    {
-                        if (t_max_x < t_max_z) { t_max_x += t_delta_x; x += step_x; if (x < 0 || x >= 32) { state = TGB_ST_ADV; break; } }
-                        else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= 32) { state = TGB_ST_ADV; break; } }
-                    }
-                    else
-                    {
-                        if (t_max_y < t_max_z) { t_max_y += t_delta_y; y += step_y; if (y < 0 || y >= 32) { state = TGB_ST_ADV; break; } }
-                        else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= 32) { state = TGB_ST_ADV; break; } }
-                    }
+                    const bool xy = t_max_x < t_max_y;
+                    const bool go_x = xy & (t_max_x < t_max_z);
+                    const bool go_y = !xy & (t_max_y < t_max_z);
+                    const bool go_z = !(go_x | go_y);
+                    t_max_x = go_x ? t_max_x + t_delta_x : t_max_x;
+                    t_max_y = go_y ? t_max_y + t_delta_y : t_max_y;
+                    t_max_z = go_z ? t_max_z + t_delta_z : t_max_z;
+                    x += go_x ? step_x : 0;
+                    y += go_y ? step_y : 0;
+                    z += go_z ? step_z : 0;
+                    if ((u32)(x | y | z) > 31u) { state = TGB_ST_ADV; break; } /* left the block: a coordinate is -1 or 32 */
                 }
             }
         }
         else if (n_adv > n_node)
         {
+            bool popping = false;
             if (state == TGB_ST_ADV)
             {
                 /* :279-294 advance to the far border of the child */
+                n_advances++;
                 const f32 exit = tgb_exit_distance(child_min, child_max, position, d);
                 position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
-                /* :296-324: pop while the ray has left the stacked node */
                 state = TGB_ST_NODE;
-                if (!tgb_still_inside(top_min, top_max, position, d))
+                popping = !tgb_still_inside(top_min, top_max, position, d);
+                stack_size -= popping ? 1u : 0u;
+            }
+            /* :296-324: pop while the ray has left the stacked node; the lanes of this phase pop in lock-step */
+            while (__any_sync(0xFFFFFFFFu, popping))
+            {
+                if (popping)
                 {
-                    stack_size--;
-                    for (;;)
+                    if (stack_size == 0) { finished = 2u; state = TGB_ST_IDLE; popping = false; }
+                    else
                     {
-                        if (stack_size == 0) { finished = 2u; state = TGB_ST_IDLE; break; }
-                        if (stack_size == 1) { top_min = svo.bmin; top_max = svo.bmax; top_idx = 0; }
-                        else
-                        {
-                            const u32 e = stack_size - 2u;
-                            top_min = tgb_v3(s_box[e][0][tid], s_box[e][1][tid], s_box[e][2][tid]);
-                            top_max = tgb_v3(s_box[e][3][tid], s_box[e][4][tid], s_box[e][5][tid]);
-                            top_idx = s_idx[e][tid];
-                        }
-                        if (tgb_still_inside(top_min, top_max, position, d)) break;
-                        stack_size--;
+                        const u32 e = stack_size >= 2u ? stack_size - 2u : 0u;
+                        const bool root = stack_size == 1u;
+                        top_min = root ? svo.bmin : tgb_v3(s_box[e][0][tid], s_box[e][1][tid], s_box[e][2][tid]);
+                        top_max = root ? svo.bmax : tgb_v3(s_box[e][3][tid], s_box[e][4][tid], s_box[e][5][tid]);
+                        top_idx = root ? 0u : s_idx[e][tid];
+                        popping = !tgb_still_inside(top_min, top_max, position, d);
+                        stack_size -= popping ? 1u : 0u;
                     }
                 }
             }
@@ -491,6 +493,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
             if (state == TGB_ST_NODE)
             {
                 /* one visit of the shader's while loop: :44-110, 262-270 */
+                n_visits++;
                 if (++iterations > TGB_TRAVERSE_MAX_ITERS) finished = 2u;
                 else
                 {
@@ -499,13 +502,15 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
                     const u32 valid_mask    = (node_data >> 16) & 0xFFu;
                     const u32 leaf_mask     = (node_data >> 24) & 0xFFu;
                     /* :57-80 */
+                    /* with selects: child_min = parent_min [+ extent], child_max = (parent_min + extent) [+ extent], the shader's sums */
                     const v3 child_extent = tgb_scale(tgb_sub(top_max, top_min), 0.5f);
-                    u32 oct = 0;
-                    child_min = top_min;
-                    child_max = tgb_add(child_min, child_extent);
-                    if (child_max.x < position.x || (position.x == child_max.x && d.x > 0.0f)) { oct += 1; child_min.x += child_extent.x; child_max.x += child_extent.x; }
-                    if (child_max.y < position.y || (position.y == child_max.y && d.y > 0.0f)) { oct += 2; child_min.y += child_extent.y; child_max.y += child_extent.y; }
-                    if (child_max.z < position.z || (position.z == child_max.z && d.z > 0.0f)) { oct += 4; child_min.z += child_extent.z; child_max.z += child_extent.z; }
+                    const v3 mid = tgb_add(top_min, child_extent);
+                    const bool ux = (mid.x < position.x) | ((position.x == mid.x) & (d.x > 0.0f));
+                    const bool uy = (mid.y < position.y) | ((position.y == mid.y) & (d.y > 0.0f));
+                    const bool uz = (mid.z < position.z) | ((position.z == mid.z) & (d.z > 0.0f));
+                    const u32 oct = (ux ? 1u : 0u) | (uy ? 2u : 0u) | (uz ? 4u : 0u);
+                    child_min = tgb_v3(ux ? mid.x : top_min.x, uy ? mid.y : top_min.y, uz ? mid.z : top_min.z);
+                    child_max = tgb_v3(ux ? mid.x + child_extent.x : mid.x, uy ? mid.y + child_extent.y : mid.y, uz ? mid.z + child_extent.z : mid.z);
                     state = TGB_ST_ADV;
                     if ((valid_mask & (1u << oct)) != 0)
                     {
@@ -557,6 +562,10 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
 
         if (finished)
         {
+#ifdef TGB_GI_HISTOGRAM
+            atomicMax(&p_q_count[8], iterations);
+            atomicAdd(&p_q_count[16 + (31 - __clz(iterations | 1u))], 1u);
+#endif
             if (finished == 2u)
             {
                 /* unoccluded: the ambient term comes back (ambient * 1 + lo) */
@@ -568,6 +577,16 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
             }
             state = TGB_ST_IDLE;
         }
+    }
+    /* [2] node visits, [3] DDA steps, [4] advances of this frame */
+    n_visits = __reduce_add_sync(0xFFFFFFFFu, n_visits);
+    n_steps = __reduce_add_sync(0xFFFFFFFFu, n_steps);
+    n_advances = __reduce_add_sync(0xFFFFFFFFu, n_advances);
+    if (lane == 0)
+    {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_visits);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 2, (unsigned long long)n_steps);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 3, (unsigned long long)n_advances);
     }
 }
 
@@ -637,7 +656,7 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     a.p_q0 = d->d_gi_q0; a.p_q1 = d->d_gi_q1; a.p_q2 = d->d_gi_q2; a.p_q_count = d->d_gi_count;
     a.p_mat = d->d_mat_tile;
     const bool gi = gi_enabled && debug_visualization == TG_DEBUG_SHOW_NONE;
-    if (gi) TGB_CUDA(cudaMemsetAsync(d->d_gi_count, 0, 4 * sizeof(u32), d->stream));
+    if (gi) TGB_CUDA(cudaMemsetAsync(d->d_gi_count, 0, 32 * sizeof(u32), d->stream));
     const dim3 grid((d->width + 15) / 16, (y1 - y0 + 15) / 16);
     if (resolved) k_shade<true><<<grid, 256, 0, d->stream>>>(a);
     else          k_shade<false><<<grid, 256, 0, d->stream>>>(a);
@@ -647,6 +666,7 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
         k_gi_trace<<<d->n_sms * 8, TGB_GI_THREADS, 0, d->stream>>>(a.svo, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_radiance);
         TGB_LAUNCH_CHECK(d);
+        TGB_CUDA(cudaMemcpyAsync(d->h_gi_stats, d->d_gi_count, 32 * sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
     }
     return TG_TRUE;
 }
