@@ -152,3 +152,36 @@ def test_gi_without_svo_is_a_recorded_error(gpu):
             rt.synchronize()
     finally:
         rt.destroy()
+
+
+def test_config3_full_size_stackless_equals_stack_machine_and_oracle_rows(gpu, oracle):
+    """BASELINE configs[2]: 1 secondary ray per hit pixel at 3840x2160 on the 1,024-object scene (~5 M rays through the SVO).
+    Two independent traversals must agree on every pixel -- the stackless kernel over the flattened tree and the stack
+    machine transcribed from svo_functions.inc -- and both equal the oracle on every 40th scanline."""
+    s = scenes.config2()
+    rt = from_scene(s)
+    try:
+        rt.set_gi(True, 1)
+        rt.clear(); rt.render(); rt.synchronize()
+        flat = rt.read_radiance()
+        t_flat = rt.timings()
+        vis = rt.read_visibility()
+        rt.set_gi_traversal(1)
+        rt.render_shading(); rt.synchronize()
+        stack = rt.read_radiance()
+        t_stack = rt.timings()
+        assert np.array_equal(flat, stack), f"{int((flat != stack).any(axis=-1).sum())} pixels differ between the two traversals"
+        assert t_flat["n_gi_rays"] == t_stack["n_gi_rays"] > 1_000_000
+        assert t_flat["n_gi_dda_steps"] == t_stack["n_gi_dda_steps"] and t_flat["n_gi_advances"] == t_stack["n_gi_advances"]
+    finally:
+        rt.destroy()
+    rays = oracle.camera_rays(oracle.camera_from_spec(s.camera))
+    view = oracle.SceneView.from_scene(s, with_lut=True)
+    near = [o for o in s.objects if max(abs(o.center[0]), abs(o.center[2])) < 512 + 160]
+    svo = oracle.svo_create(oracle.SceneView.from_scene(scenes.SceneSpec(name="near", width=s.width, height=s.height, camera=s.camera, objects=near), with_lut=False),
+                            capacities=(1 << 25, 1 << 15, 1 << 16))
+    want = np.zeros((s.height, s.width, 4), dtype=np.float32)
+    oracle.shade(view, rays, s.width, s.height, vis, svo, gi=True, frame_seed=1, y0=7, y1=s.height, ystep=40, out=want)
+    oracle.svo_destroy(svo)
+    rows = np.arange(7, s.height, 40)
+    close(flat[rows], want[rows], "config 3 rows")

@@ -43,6 +43,7 @@ SYMBOLS = {
     "tg_raytracer_set_object_transform": (None, [_RT, T.u32, T.v3, T.f32, T.v3]),
     "tg_raytracer_color_lut_set_ex": (None, [_RT, T.u32, T.u8, T.f32, T.f32, T.f32]),
     "tg_raytracer_set_gi": (None, [_RT, T.b32, T.u32]),
+    "tgb200_set_gi_traversal": (None, [_RT, T.u32]),
     "tgb200_render_visibility": (None, [_RT]),
     "tgb200_svo_update": (None, [_RT, T.b32]),
     "tgb200_svo_leaves_resampled": (T.u32, [_RT]),

@@ -57,6 +57,8 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMalloc(&d->svo.d_leaf_data, (u64)d->svo.leaf_capacity * 65 * 4));
     TGB_CUDA(cudaMalloc(&d->svo.d_voxels, (u64)d->svo.voxel_word_capacity * 4));
     TGB_CUDA(cudaMalloc(&d->svo.d_counts, 16 * sizeof(u32)));
+    TGB_CUDA(cudaMalloc(&d->svo.d_top_grid, (TGB_TOP_GRID_CELLS + 1) * sizeof(u32)));
+    TGB_CUDA(cudaMemsetAsync(d->svo.d_top_grid, 0, (TGB_TOP_GRID_CELLS + 1) * sizeof(u32), d->stream));
     TGB_CUDA(cudaMalloc(&d->svo.d_object_moved, no * sizeof(u32)));
     return TG_TRUE;
 }
@@ -148,7 +150,7 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
     if (d->h_gi_stats) cudaFreeHost(d->h_gi_stats);
-    cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts);
+    cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts); cudaFree(d->svo.d_top_grid);
     cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch); cudaFree(d->svo.d_pair_flags); cudaFree(d->svo.d_object_flags); cudaFree(d->svo.d_pair_leaf_a); cudaFree(d->svo.d_pair_leaf_b);
     cudaFree(d->svo.d_voxels_alt); cudaFree(d->svo.d_leaf_data_alt); cudaFree(d->svo.d_object_moved); cudaFree(d->svo.d_moved_indices); cudaFree(d->svo.d_part); cudaFree(d->svo.d_gather);
     cudaFree(d->d_mat); cudaFree(d->d_mat_tile); cudaFree(d->d_objects_global); cudaFree(d->d_frames_global);
@@ -235,6 +237,7 @@ extern "C" void tgbd_synchronize(struct tgb_device* d)
 }
 
 extern "C" void tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base) { d->global_pointer_base = global_pointer_base; }
+extern "C" void tgbd_set_gi_traversal(struct tgb_device* d, u32 kind) { d->gi_traversal = kind; }
 
 extern "C" b32 tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n_ranks)
 {

@@ -14,6 +14,13 @@
 #include "tgb_math.h"
 #include "tgb_hoist.h"
 
+/* the flattened tree (k_svo_flatten, tgb_svo.cu): one word per 32^3 cell of the 1024^3 box */
+#define TGB_TOP_GRID_DIM      32u
+#define TGB_TOP_GRID_CELLS    (TGB_TOP_GRID_DIM * TGB_TOP_GRID_DIM * TGB_TOP_GRID_DIM)
+#define TGB_TOP_HAS_DATA      0x80000000u /* the terminal node is a leaf with n != 0: bits 0..27 = data_pointer */
+#define TGB_TOP_LEVEL_SHIFT   28u         /* bits 28..30: depth of the inner node whose child is terminal (child side = 512 >> level) */
+#define TGB_TOP_POINTER_MASK  0x0FFFFFFFu
+
 struct tgb_svo_device
 {
     v3   bmin, bmax;
@@ -22,6 +29,8 @@ struct tgb_svo_device
     u32* d_leaf_data;   /* 65 u32 per leaf */
     u32* d_voxels;      /* 1024 u32 per leaf */
     u32* d_counts;      /* [0] nodes, [1] leaves, [2] overflow flag */
+    u32* d_top_grid;    /* [32^3 + 1] the tree flattened per 32^3 cell (k_svo_flatten): terminal level | has data | leaf data pointer;
+                           last word: non-zero = the grid describes the tree completely (leaves exactly at depth 5) */
     u32  n_nodes, n_leaves, n_pairs;
     b32  valid;
     /* build scratch */
@@ -67,6 +76,7 @@ struct tgb_device
     u32*            d_gi_count;   /* u32 [0] queued, [1] fetched; u64 [1] node visits, [2] DDA steps, [3] advances */
     u32*            h_gi_stats;   /* pinned copy of d_gi_count after the last frame */
     u32             n_sms;
+    u32             gi_traversal; /* 0 = stackless when possible, 1 = stack machine */
 
     /* multi-GPU (one process per GPU): clusters sharded by object, SVO / objects replicated, GI split by screen tile */
     void*             p_comm;           /* NCCL communicator or NULL */

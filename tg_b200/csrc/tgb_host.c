@@ -635,6 +635,12 @@ void tgb200_comm_destroy(tg_raytracer* p_raytracer)
     tgbn_destroy(p_comm);
 }
 
+void tgb200_set_gi_traversal(tg_raytracer* p_raytracer, u32 kind)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_set_gi_traversal")) return;
+    tgbd_set_gi_traversal(p_raytracer->p_device, kind);
+}
+
 void tgb200_mark_svo_dirty(tg_raytracer* p_raytracer)
 {
     if (!tgb__alive(p_raytracer, "tgb200_mark_svo_dirty")) return;

@@ -47,6 +47,7 @@ void* tgbd_stream(struct tgb_device* d);
 void  tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out);
 void  tgbd_reset_launch_counter(struct tgb_device* d);
 void  tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base);
+void  tgbd_set_gi_traversal(struct tgb_device* d, u32 kind);
 b32   tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n_ranks);
 u32   tgbd_tile_rows(struct tgb_device* d);
 void* tgbd_comm(struct tgb_device* d);

@@ -351,11 +351,14 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
  */
 #define TGB_GI_THREADS   128
 #define TGB_GI_DDA_STEPS 8
+#define TGB_GI_FLAT_CTAS_PER_SM 8
 enum { TGB_ST_IDLE = 0, TGB_ST_NODE = 1, TGB_ST_DDA = 2, TGB_ST_ADV = 3 };
 
-__global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view svo, f32 far_plane, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
+__global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view svo, const u32* __restrict__ p_flat_ok, f32 far_plane, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                              const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, float4* __restrict__ p_out)
 {
+    if (p_flat_ok != NULL && p_flat_ok[0] != 0) return; /* the stackless kernel k_gi_trace_flat traces this frame */
+
     /* stack entries 1..4 (entry 0 is the root: node 0, the SVO box) */
     __shared__ f32 s_box[4][6][TGB_GI_THREADS];
     __shared__ u32 s_idx[4][TGB_GI_THREADS];
@@ -590,6 +593,219 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
     }
 }
 
+/* ---- K3b, stackless: the same traversal over the flattened tree ------------------------------------------------ */
+/*
+ * tg_svo_traverse keeps a stack only to find, after every advance, the deepest stacked node that still contains
+ * `position`, and then descends again to the terminal node (an invalid octant or a leaf) around it. Both steps are a
+ * function of `position` and the shader's comparison rules alone:
+ *   - the pop loop (:296-324) ends the ray when the ROOT fails `exit > epsilon`: every stacked box lies inside the root
+ *     and IEEE subtraction / division are monotone, so a nested box that passes the test implies the root passes it;
+ *   - the descent (:57-91) picks per axis the upper half iff mid < p || (p == mid && d > 0); five levels of that rule
+ *     select one 32^3 cell of the box, and the terminal node around it is tabulated per cell by k_svo_flatten
+ *     (tgb_svo.cu). Whether the descent starts at the root or at a stacked ancestor is immaterial: the ancestor
+ *     contains `position` under the same rule (it passed the pop test on every axis the ray moves along).
+ * What moves `position` -- the far-border distance of the terminal box and `position += (exit + epsilon) * d`
+ * (:279-294) -- and the leaf DDA (:111-257) are the shader's operations, so hit / miss decisions are the oracle's.
+ * The box corners must be integers (the chain mid = min + extent / 2 is then exact and equals min + 32 * cell);
+ * other boxes, and trees k_svo_flatten could not tabulate, take the stack kernel above.
+ * Two kinds of lanes remain: TREE (advance + look-up) and DDA (up to TGB_GI_DDA_STEPS voxel steps); each warp iteration
+ * runs the phase the majority waits for.
+ */
+enum { TGB_FL_IDLE = 0, TGB_FL_TREE = 1, TGB_FL_DDA = 2 };
+
+/* index along one axis of the 32^3 cell the shader's octant rule (:63-80) selects for p */
+__device__ __forceinline__ u32 tgb_cell_axis(f32 p, f32 d, f32 box_min)
+{
+    i32 c = (i32)floorf((p - box_min) * 0.03125f); /* off by at most one (rounding of p - box_min); fixed by the exact rule below */
+    c = max(0, min(31, c));
+    const f32 lower = box_min + 32.0f * (f32)c, upper = lower + 32.0f; /* exact: integers */
+    const bool forward = d > 0.0f;
+    const bool above_lower = (lower < p) | ((p == lower) & forward);
+    const bool above_upper = (upper < p) | ((p == upper) & forward);
+    c += above_upper ? 1 : (above_lower ? 0 : -1);
+    return (u32)max(0, min(31, c));
+}
+
+__global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_view svo, const u32* __restrict__ p_grid, f32 far_plane,
+                                                                  const float4* __restrict__ p_q0, const float4* __restrict__ p_q1, const float4* __restrict__ p_q2,
+                                                                  u32* __restrict__ p_q_count, float4* __restrict__ p_out)
+{
+    if (p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
+
+    const u32 lane = threadIdx.x & 31u;
+    const u32 n_rays = p_q_count[0];
+    const v3 extent = tgb_sub(svo.bmax, svo.bmin);
+    const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin); /* svo_functions.inc:3-8 */
+
+    u32 state = TGB_FL_IDLE, slot = 0, iterations = 0;
+    bool advance_pending = false;
+    v3 d = tgb_v3(0.0f, 0.0f, 0.0f), position = d, child_min = d;
+    f32 child_size = 0.0f;
+    f32 t_max_x = 0.0f, t_max_y = 0.0f, t_max_z = 0.0f, t_delta_x = 0.0f, t_delta_y = 0.0f, t_delta_z = 0.0f;
+    i32 x = 0, y = 0, z = 0;
+    const u32* __restrict__ p_block = svo.p_voxels;
+    bool exhausted = false;
+    u32 n_visits = 0, n_steps = 0, n_advances = 0;
+
+    for (;;)
+    {
+        const u32 counts = __reduce_add_sync(0xFFFFFFFFu, 1u << (8u * state));
+        const u32 n_idle = counts & 0xFFu, n_tree = (counts >> 8) & 0xFFu, n_dda = (counts >> 16) & 0xFFu;
+
+        /* ---- refill ---- */
+        if (!exhausted && n_idle >= 8u)
+        {
+            const u32 idle = __ballot_sync(0xFFFFFFFFu, state == TGB_FL_IDLE);
+            u32 base = 0;
+            const u32 leader = (u32)(__ffs(idle) - 1);
+            if (lane == leader) base = atomicAdd(&p_q_count[1], n_idle);
+            base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
+            if (state == TGB_FL_IDLE)
+            {
+                const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
+                if (mine < n_rays)
+                {
+                    slot = mine;
+                    const float4 q0 = p_q0[mine], q1 = p_q1[mine];
+                    const v3 o = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
+                    d = tgb_v3(q1.x, q1.y, q1.z);
+                    f32 enter, exit;
+                    if (tgb_ray_aabb(o, d, svo.bmin, svo.bmax, &enter, &exit)) /* :27-31; true: tested before queueing */
+                    {
+                        position = o;
+                        if (enter > 0.0f) position = tgb_add(position, tgb_scale(d, enter));
+                        iterations = 0;
+                        advance_pending = false;
+                        /* :139-176: the DDA increments depend on the ray only */
+                        t_delta_x = d.x > 0.0f ? 1.0f / d.x : (d.x < 0.0f ? 1.0f / -d.x : TG_F32_MAX);
+                        t_delta_y = d.y > 0.0f ? 1.0f / d.y : (d.y < 0.0f ? 1.0f / -d.y : TG_F32_MAX);
+                        t_delta_z = d.z > 0.0f ? 1.0f / d.z : (d.z < 0.0f ? 1.0f / -d.z : TG_F32_MAX);
+                        state = TGB_FL_TREE;
+                    }
+                }
+            }
+            exhausted = base + n_idle >= n_rays;
+            continue;
+        }
+        if (n_idle == 32u) break; /* queue drained and every ray finished */
+
+        u32 finished = 0; /* 1 = occluded, 2 = unoccluded */
+        if (n_dda > n_tree)
+        {
+            if (state == TGB_FL_DDA)
+            {
+                /* :178-257, steps written with selects (adding +0 to the other two t_max leaves them bit-identical) */
+                const i32 step_x = d.x > 0.0f ? 1 : (d.x < 0.0f ? -1 : 0);
+                const i32 step_y = d.y > 0.0f ? 1 : (d.y < 0.0f ? -1 : 0);
+                const i32 step_z = d.z > 0.0f ? 1 : (d.z < 0.0f ? -1 : 0);
+#pragma unroll 1
+                for (u32 k = 0; k < TGB_GI_DDA_STEPS; k++)
+                {
+                    const u32 bits = __ldg(&p_block[32 * z + y]); /* a block row is one word: bit 1024 z + 32 y + x */
+                    n_steps++;
+                    if ((bits >> x) & 1u)
+                    {
+                        const float4 q0 = p_q0[slot];
+                        const v3 o = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
+                        const v3 voxel_min = tgb_add(child_min, tgb_v3((f32)x, (f32)y, (f32)z));
+                        const v3 voxel_max = tgb_add(child_min, tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)));
+                        f32 enter, exit;
+                        tgb_ray_aabb(o, d, voxel_min, voxel_max, &enter, &exit);
+                        /* :219-256 result = enter / far; only result < 1 ends the shader's loop, otherwise it advances */
+                        if (enter / far_plane < 1.0f) finished = 1u; else state = TGB_FL_TREE;
+                        break;
+                    }
+                    const bool xy = t_max_x < t_max_y;
+                    const bool go_x = xy & (t_max_x < t_max_z);
+                    const bool go_y = !xy & (t_max_y < t_max_z);
+                    const bool go_z = !(go_x | go_y);
+                    t_max_x = go_x ? t_max_x + t_delta_x : t_max_x;
+                    t_max_y = go_y ? t_max_y + t_delta_y : t_max_y;
+                    t_max_z = go_z ? t_max_z + t_delta_z : t_max_z;
+                    x += go_x ? step_x : 0;
+                    y += go_y ? step_y : 0;
+                    z += go_z ? step_z : 0;
+                    if ((u32)(x | y | z) > 31u) { state = TGB_FL_TREE; break; } /* left the block: a coordinate is -1 or 32 */
+                }
+            }
+        }
+        else if (state == TGB_FL_TREE)
+        {
+            bool inside = true;
+            if (advance_pending)
+            {
+                /* :279-294 advance to the far border of the terminal box, :296-324 the ray ends when it has left the root */
+                n_advances++;
+                const v3 child_max = tgb_add(child_min, tgb_v3(child_size, child_size, child_size));
+                const f32 exit = tgb_exit_distance(child_min, child_max, position, d);
+                position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
+                inside = tgb_still_inside(svo.bmin, svo.bmax, position, d);
+            }
+            advance_pending = true;
+            if (!inside || ++iterations > TGB_TRAVERSE_MAX_ITERS) finished = 2u;
+            else
+            {
+                /* :44-110: the terminal node around `position` */
+                n_visits++;
+                const u32 cx = tgb_cell_axis(position.x, d.x, svo.bmin.x);
+                const u32 cy = tgb_cell_axis(position.y, d.y, svo.bmin.y);
+                const u32 cz = tgb_cell_axis(position.z, d.z, svo.bmin.z);
+                const u32 entry = __ldg(&p_grid[(cz << 10) | (cy << 5) | cx]);
+                const u32 level = (entry >> TGB_TOP_LEVEL_SHIFT) & 7u;
+                const u32 cells = 16u >> level;              /* side of the terminal box in cells */
+                const u32 keep = ~(cells - 1u);
+                child_size = (f32)(cells << 5);
+                child_min = tgb_v3(svo.bmin.x + 32.0f * (f32)(cx & keep), svo.bmin.y + 32.0f * (f32)(cy & keep), svo.bmin.z + 32.0f * (f32)(cz & keep));
+                if (entry & TGB_TOP_HAS_DATA)
+                {
+                    /* :111-176 */
+                    p_block = svo.p_voxels + (u64)(entry & TGB_TOP_POINTER_MASK) * TG_SVO_BLOCK_WORDS;
+                    const v3 child_max = tgb_add(child_min, tgb_v3(child_size, child_size, child_size));
+                    v3 hit = position;
+                    v3 xyz = tgb_v3(tgb_clamp(floorf(hit.x), child_min.x, child_max.x - 1.0f),
+                                    tgb_clamp(floorf(hit.y), child_min.y, child_max.y - 1.0f),
+                                    tgb_clamp(floorf(hit.z), child_min.z, child_max.z - 1.0f));
+                    hit = tgb_sub(hit, child_min);
+                    xyz = tgb_sub(xyz, child_min);
+                    x = (i32)xyz.x; y = (i32)xyz.y; z = (i32)xyz.z;
+                    t_max_x = TG_F32_MAX; t_max_y = TG_F32_MAX; t_max_z = TG_F32_MAX;
+                    if (d.x > 0.0f)      t_max_x = ((f32)(x + 1) - hit.x) / d.x;
+                    else if (d.x < 0.0f) t_max_x = (hit.x - (f32)x) / -d.x;
+                    if (d.y > 0.0f)      t_max_y = ((f32)(y + 1) - hit.y) / d.y;
+                    else if (d.y < 0.0f) t_max_y = (hit.y - (f32)y) / -d.y;
+                    if (d.z > 0.0f)      t_max_z = ((f32)(z + 1) - hit.z) / d.z;
+                    else if (d.z < 0.0f) t_max_z = (hit.z - (f32)z) / -d.z;
+                    state = TGB_FL_DDA;
+                }
+            }
+        }
+
+        if (finished)
+        {
+            if (finished == 2u)
+            {
+                /* unoccluded: the ambient term comes back (ambient * 1 + lo); float addition commutes, the reductions do not stall */
+                const float4 q0 = p_q0[slot], q2 = p_q2[slot];
+                f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
+                atomicAdd(p_pixel + 0, q2.x);
+                atomicAdd(p_pixel + 1, q2.y);
+                atomicAdd(p_pixel + 2, q2.z);
+            }
+            state = TGB_FL_IDLE;
+        }
+    }
+    /* [2] look-ups, [3] DDA steps, [4] advances of this frame */
+    n_visits = __reduce_add_sync(0xFFFFFFFFu, n_visits);
+    n_steps = __reduce_add_sync(0xFFFFFFFFu, n_steps);
+    n_advances = __reduce_add_sync(0xFFFFFFFFu, n_advances);
+    if (lane == 0)
+    {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_visits);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 2, (unsigned long long)n_steps);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 3, (unsigned long long)n_advances);
+    }
+}
+
 /* ---- owner-resolved materials (multi-GPU) ------------------------------------------------------------------ */
 /* local object records with pointers / LUT-independent fields globalised, into this rank's slice of the global table */
 __global__ void k_globalize_objects(const tg_object_data* __restrict__ p_objects, u32 object_capacity, u32 global_pointer_base, tg_object_data* __restrict__ p_out)
@@ -664,7 +880,18 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     if (gi)
     {
         /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
-        k_gi_trace<<<d->n_sms * 8, TGB_GI_THREADS, 0, d->stream>>>(a.svo, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_radiance);
+        /* integer box corners: the flattened tree is exact (k_gi_trace_flat); the stack kernel runs only when the tree could not be tabulated */
+        const f32 c[6] = { a.svo.bmin.x, a.svo.bmin.y, a.svo.bmin.z, a.svo.bmax.x, a.svo.bmax.y, a.svo.bmax.z };
+        bool flat = d->gi_traversal == 0;
+        for (int i = 0; i < 6; i++) flat = flat && c[i] == floorf(c[i]) && fabsf(c[i]) <= 4194304.0f;
+        if (flat)
+        {
+            k_gi_trace_flat<<<d->n_sms * TGB_GI_FLAT_CTAS_PER_SM, TGB_GI_THREADS, 0, d->stream>>>(a.svo, d->svo.d_top_grid, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2,
+                                                                                                 d->d_gi_count, d->d_radiance);
+            TGB_LAUNCH_CHECK(d);
+        }
+        k_gi_trace<<<d->n_sms * 8, TGB_GI_THREADS, 0, d->stream>>>(a.svo, flat ? d->svo.d_top_grid + TGB_TOP_GRID_CELLS : NULL, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2,
+                                                                   d->d_gi_count, d->d_radiance);
         TGB_LAUNCH_CHECK(d);
         TGB_CUDA(cudaMemcpyAsync(d->h_gi_stats, d->d_gi_count, 32 * sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
     }

@@ -592,6 +592,57 @@ __global__ void __launch_bounds__(256) k_svo_combine(const u32* __restrict__ p_g
     }
 }
 
+/*
+ * The tree flattened for the stackless secondary-ray kernel (k_gi_trace_flat, tgb_shade.cu). tg_svo_traverse
+ * (svo_functions.inc:44-110) finds, from the top of its stack, the TERMINAL node that contains `position`: an octant
+ * whose valid bit is clear, or a leaf. Which node that is depends on the position and the comparison rule only, so it
+ * can be tabulated: one word per 32^3 cell of the 1024^3 box = depth of the inner node whose child is terminal
+ * (child side 512 >> depth), and for a leaf with n != 0 its data pointer. One thread per cell walks the five levels.
+ * The last word says whether the table is complete (all leaves at depth 5, no inner node deeper: what
+ * tg__construct_inner_node builds, tg_sparse_voxel_octree.c:319-464); otherwise the stack kernel runs instead.
+ */
+__global__ void k_svo_flatten(const u32* __restrict__ p_nodes, const u32* __restrict__ p_leaf_data, u32 n_nodes, u32 n_leaves, u32* __restrict__ p_grid)
+{
+    const u32 cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= TGB_TOP_GRID_CELLS) return;
+    const u32 cx = cell & 31u, cy = (cell >> 5) & 31u, cz = cell >> 10;
+    u32 node = 0, entry = 0;
+    bool ok = true, done = false;
+    for (u32 level = 0; level < 5u && !done; level++)
+    {
+        const u32 shift = 4u - level;
+        const u32 oct = ((cx >> shift) & 1u) | (((cy >> shift) & 1u) << 1) | (((cz >> shift) & 1u) << 2); /* svo_functions.inc:57-80 */
+        const u32 node_data = p_nodes[node];
+        const u32 child_pointer = node_data & 0xFFFFu, valid_mask = (node_data >> 16) & 0xFFu, leaf_mask = node_data >> 24;
+        entry = level << TGB_TOP_LEVEL_SHIFT;
+        if (((valid_mask >> oct) & 1u) == 0) { done = true; break; }
+        const u32 child = node + child_pointer + (u32)__popc(valid_mask & ((1u << oct) - 1u)); /* :86-91 */
+        if (child >= n_nodes) { ok = false; done = true; break; }
+        if ((leaf_mask >> oct) & 1u)
+        {
+            if (level != 4u) ok = false; /* a leaf larger than 32^3: not a tree the builders make */
+            const u32 data_pointer = p_nodes[child];
+            if (data_pointer >= n_leaves || data_pointer > TGB_TOP_POINTER_MASK) ok = false;
+            else if (p_leaf_data[(u64)data_pointer * 65u] != 0) entry |= TGB_TOP_HAS_DATA | data_pointer;
+            done = true;
+            break;
+        }
+        node = child;
+    }
+    if (!done) ok = false; /* an inner node at depth 5 */
+    p_grid[cell] = entry;
+    if (!ok) p_grid[TGB_TOP_GRID_CELLS] = 0;
+}
+
+static b32 tgbd__svo_flatten(struct tgb_device* d)
+{
+    tgb_svo_device* s = &d->svo;
+    TGB_CUDA(cudaMemsetAsync(s->d_top_grid + TGB_TOP_GRID_CELLS, 1, sizeof(u32), d->stream)); /* non-zero = complete, cleared by the kernel */
+    k_svo_flatten<<<TGB_TOP_GRID_CELLS / 256, 256, 0, d->stream>>>(s->d_nodes, s->d_leaf_data, s->n_nodes, s->n_leaves, s->d_top_grid);
+    TGB_LAUNCH_CHECK(d);
+    return TG_TRUE;
+}
+
 /* ---- host side of the seam ---------------------------------------------------------------------------- */
 static b32 tgbd__svo_ensure(struct tgb_device* d)
 {
@@ -780,6 +831,7 @@ static b32 tgbd__svo_run(struct tgb_device* d, v3 extent_min, v3 extent_max, u32
         TGB_LAUNCH_CHECK(d);
     }
     if (incremental) TGB_CUDA(cudaMemcpyAsync(&s->n_leaves_resampled, s->d_counts + 4, sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
+    if (!tgbd__svo_flatten(d)) return TG_FALSE;
     TGB_CUDA(cudaEventRecord(d->ev[6], d->stream));
     d->ev_svo = TG_TRUE;
     s->n_pairs = counts[2];
@@ -834,6 +886,8 @@ extern "C" b32 tgbd_svo_set(struct tgb_device* d, v3 bmin, v3 bmax, u32 n_nodes,
     TGB_CUDA(cudaStreamSynchronize(d->stream));
     s->bmin = bmin; s->bmax = bmax;
     s->n_nodes = n_nodes; s->n_leaves = n_leaves;
+    if (!n_nodes) TGB_CUDA(cudaMemsetAsync(s->d_nodes, 0, 4, d->stream)); /* an empty upload is an empty root */
+    if (!tgbd__svo_flatten(d)) return TG_FALSE;
     s->valid = TG_TRUE;
     s->incremental_ok = TG_FALSE; /* uploaded arrays: there are no pair lists to update from */
     return TG_TRUE;

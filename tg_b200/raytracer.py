@@ -199,6 +199,10 @@ class Raytracer:
     def gather_radiance(self):
         self._lib.tgb200_gather_radiance(C.byref(self._rt))
 
+    def set_gi_traversal(self, kind):
+        """0 = automatic (stackless over the flattened tree), 1 = the stack machine of svo_functions.inc."""
+        self._lib.tgb200_set_gi_traversal(C.byref(self._rt), kind)
+
     def mark_svo_dirty(self):
         self._lib.tgb200_mark_svo_dirty(C.byref(self._rt))
 
