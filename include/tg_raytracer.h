@@ -113,7 +113,7 @@ TG_EXPORT void tg_raytracer_color_lut_set_ex(tg_raytracer* p_raytracer, u32 lut_
 /* GI on/off + RNG seed of the secondary rays. */
 TG_EXPORT void tg_raytracer_set_gi(tg_raytracer* p_raytracer, b32 enabled, u32 frame_seed);
 
-/* Secondary-ray kernel: 0 = automatic (stackless over the flattened tree whenever the SVO box has integer corners, the
+/* Secondary-ray kernel: 0 = automatic (stackless over the flattened tree whenever the SVO box corners are multiples of 32, the
  * stack machine of svo_functions.inc otherwise), 1 = always the stack machine. Both give the same radiance (tests). */
 TG_EXPORT void tgb200_set_gi_traversal(tg_raytracer* p_raytracer, u32 kind);
 

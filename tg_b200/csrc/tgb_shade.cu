@@ -157,7 +157,7 @@ struct tgb_shade_args
     u32 global_pointer_base, n_local_pointers;
     u32 gi_enabled, frame_seed, debug_visualization;
     u32 y0, y1; /* rows [y0, y1) are shaded (multi-GPU: this rank's screen tile) */
-    /* GI ray queue (SoA): origin.xyz + pixel | direction.xyz | ambient.rgb */
+    /* GI ray queue (SoA): origin.xyz + pixel | direction.xyz + enter of the root slab test | ambient.rgb */
     float4* __restrict__ p_q0;
     float4* __restrict__ p_q1;
     float4* __restrict__ p_q2;
@@ -172,7 +172,7 @@ struct tgb_shade_args
  * all-gathered global ones whose first_cluster_pointer is global. Everything downstream is the same arithmetic.
  */
 template <bool RESOLVED>
-__device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px, u32 py, float4* p_color, v3* p_origin, v3* p_dir, v3* p_ambient)
+__device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px, u32 py, float4* p_color, v3* p_origin, v3* p_dir, v3* p_ambient, f32* p_root_enter)
 {
     const u64 pixel = (u64)py * a.w + px;
 
@@ -294,7 +294,7 @@ __device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px,
         if (tgb_ray_aabb(tgb_sub(origin, center), dir, a.svo.bmin, a.svo.bmax, &e0, &e1))
         {
             *p_color = make_float4(lo.x, lo.y, lo.z, 1.0f); /* ambient * 0 + lo, unless the ray escapes */
-            *p_origin = origin; *p_dir = dir; *p_ambient = ambient;
+            *p_origin = origin; *p_dir = dir; *p_ambient = ambient; *p_root_enter = e0;
             return true;
         }
     }
@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
 
     float4 color = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     v3 origin = tgb_v3(0.0f, 0.0f, 0.0f), dir = origin, ambient = origin;
-    const bool trace = in_tile && tgb_shade_pixel<RESOLVED>(a, px, py, &color, &origin, &dir, &ambient);
+    f32 root_enter = 0.0f; /* `enter` of the slab test against the SVO root (svo_functions.inc:27-31), queued for k_gi_trace_flat */
+    const bool trace = in_tile && tgb_shade_pixel<RESOLVED>(a, px, py, &color, &origin, &dir, &ambient, &root_enter);
     if (in_tile) a.p_out[(u64)py * a.w + px] = color;
 
     /* warp-aggregated append to the ray queue */
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
     {
         const u32 slot = base + (u32)__popc(m & ((1u << lane) - 1u));
         a.p_q0[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(a.w * py + px));
-        a.p_q1[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+        a.p_q1[slot] = make_float4(dir.x, dir.y, dir.z, root_enter);
         a.p_q2[slot] = make_float4(ambient.x, ambient.y, ambient.z, 0.0f);
     }
 }
@@ -606,24 +607,60 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
  *     contains `position` under the same rule (it passed the pop test on every axis the ray moves along).
  * What moves `position` -- the far-border distance of the terminal box and `position += (exit + epsilon) * d`
  * (:279-294) -- and the leaf DDA (:111-257) are the shader's operations, so hit / miss decisions are the oracle's.
- * The box corners must be integers (the chain mid = min + extent / 2 is then exact and equals min + 32 * cell);
+ * The box corners must be multiples of 32 (the chain mid = min + extent / 2 is then exact and equals min + 32 * cell);
  * other boxes, and trees k_svo_flatten could not tabulate, take the stack kernel above.
  * Two kinds of lanes remain: TREE (advance + look-up) and DDA (up to TGB_GI_DDA_STEPS voxel steps); each warp iteration
  * runs the phase the majority waits for.
  */
-enum { TGB_FL_IDLE = 0, TGB_FL_TREE = 1, TGB_FL_DDA = 2 };
+/*
+ * Lane kinds. TREE and DDA are the two working phases; HIT (a solid voxel was found: the shader's slab test against it
+ * decides, :219-256), MISS (the ray left the root: the ambient term comes back) and IDLE (needs a ray) are rare events
+ * per iteration, so they wait until a quarter of the warp needs service and are then handled together.
+ */
+enum { TGB_FL_IDLE = 0, TGB_FL_TREE = 1, TGB_FL_DDA = 2, TGB_FL_HIT = 3, TGB_FL_MISS = 4 };
+#define TGB_FL_SERVICE_LANES 8u
 
-/* index along one axis of the 32^3 cell the shader's octant rule (:63-80) selects for p */
-__device__ __forceinline__ u32 tgb_cell_axis(f32 p, f32 d, f32 box_min)
+/*
+ * Index along one axis of the 32^3 cell the shader's octant rule (:63-80: upper half iff mid < p || (p == mid && d > 0))
+ * selects for p. The box corners are multiples of 32 here, p / 32 is exact (a power of two) and so is its floor: the
+ * cell is floor(p / 32) - min / 32, one lower when p sits exactly on a cell border and the ray does not move up; a
+ * position outside the box takes the outermost cell like the shader's comparisons do.
+ */
+__device__ __forceinline__ u32 tgb_cell_axis(f32 p, f32 d, i32 box_min_cell)
 {
-    i32 c = (i32)floorf((p - box_min) * 0.03125f); /* off by at most one (rounding of p - box_min); fixed by the exact rule below */
-    c = max(0, min(31, c));
-    const f32 lower = box_min + 32.0f * (f32)c, upper = lower + 32.0f; /* exact: integers */
-    const bool forward = d > 0.0f;
-    const bool above_lower = (lower < p) | ((p == lower) & forward);
-    const bool above_upper = (upper < p) | ((p == upper) & forward);
-    c += above_upper ? 1 : (above_lower ? 0 : -1);
+    const f32 q = p * 0.03125f, fl = floorf(q);
+    const i32 c = (i32)fl - box_min_cell - (((q == fl) & !(d > 0.0f)) ? 1 : 0);
     return (u32)max(0, min(31, c));
+}
+
+/*
+ * tgb_exit_distance with the ray's exact reciprocals 1 / |d| (the DDA increments, :139-176) as the approximate
+ * quotients that rank the axes: num * RN(1 / |d|) is within 2^-22 of num / |d|, far inside the 1e-5 margin, and the
+ * value returned is still the IEEE quotient of the winning axis (see tgb_exit_distance for why that is the shader's
+ * value). `exotic` rays (a non-zero component below 1e-30, whose reciprocal overflows) always take the exact path.
+ */
+__device__ __forceinline__ f32 tgb_exit_distance_rcp(v3 bmin, f32 size, v3 position, v3 d, f32 rx, f32 ry, f32 rz, bool exotic)
+{
+    const f32 nx = d.x > 0.0f ? (bmin.x + size) - position.x : position.x - bmin.x, ax = fabsf(d.x);
+    const f32 ny = d.y > 0.0f ? (bmin.y + size) - position.y : position.y - bmin.y, ay = fabsf(d.y);
+    const f32 nz = d.z > 0.0f ? (bmin.z + size) - position.z : position.z - bmin.z, az = fabsf(d.z);
+    const f32 qx = ax != 0.0f ? nx * rx : TG_F32_MAX;
+    const f32 qy = ay != 0.0f ? ny * ry : TG_F32_MAX;
+    const f32 qz = az != 0.0f ? nz * rz : TG_F32_MAX;
+    const f32 q_min = fminf(fminf(qx, qy), qz);
+    const f32 limit = q_min + (1e-5f * fabsf(q_min) + 1e-30f);
+    const bool cx = qx <= limit, cy = qy <= limit, cz = qz <= limit;
+    const f32 num = cx ? nx : (cy ? ny : nz), den = cx ? ax : (cy ? ay : az);
+    f32 exit = num / den;
+    const bool odd = exotic | !(fabsf(q_min) < 1e30f);
+    if (((u32)cx + (u32)cy + (u32)cz != 1u) | odd)
+    {
+        exit = TG_F32_MAX;
+        if (ax != 0.0f && (odd || cx)) exit = tgb_min(exit, nx / ax);
+        if (ay != 0.0f && (odd || cy)) exit = tgb_min(exit, ny / ay);
+        if (az != 0.0f && (odd || cz)) exit = tgb_min(exit, nz / az);
+    }
+    return exit;
 }
 
 __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_view svo, const u32* __restrict__ p_grid, f32 far_plane,
@@ -636,9 +673,11 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
     const u32 n_rays = p_q_count[0];
     const v3 extent = tgb_sub(svo.bmax, svo.bmin);
     const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin); /* svo_functions.inc:3-8 */
+    const v3 box_mid = tgb_scale(tgb_add(svo.bmin, svo.bmax), 0.5f);
+    const i32 min_cell_x = (i32)(svo.bmin.x * 0.03125f), min_cell_y = (i32)(svo.bmin.y * 0.03125f), min_cell_z = (i32)(svo.bmin.z * 0.03125f);
 
-    u32 state = TGB_FL_IDLE, slot = 0, iterations = 0;
-    bool advance_pending = false;
+    u32 kind = TGB_FL_IDLE, slot = 0, iterations = 0;
+    bool advance_pending = false, setup_pending = false, exotic = false;
     v3 d = tgb_v3(0.0f, 0.0f, 0.0f), position = d, child_min = d;
     f32 child_size = 0.0f;
     f32 t_max_x = 0.0f, t_max_y = 0.0f, t_max_z = 0.0f, t_delta_x = 0.0f, t_delta_y = 0.0f, t_delta_z = 0.0f;
@@ -649,122 +688,88 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
 
     for (;;)
     {
-        const u32 counts = __reduce_add_sync(0xFFFFFFFFu, 1u << (8u * state));
-        const u32 n_idle = counts & 0xFFu, n_tree = (counts >> 8) & 0xFFu, n_dda = (counts >> 16) & 0xFFu;
+        const u32 counts = __reduce_add_sync(0xFFFFFFFFu, 1u << (6u * kind));
+        const u32 n_idle = counts & 63u, n_tree = (counts >> 6) & 63u, n_dda = (counts >> 12) & 63u, n_hit = (counts >> 18) & 63u, n_miss = (counts >> 24) & 63u;
+        const u32 n_service = n_hit + n_miss + (exhausted ? 0u : n_idle);
+        const u32 n_working = n_tree + n_dda;
+        if (n_working == 0 && n_service == 0) break; /* queue drained and every ray finished */
 
-        /* ---- refill ---- */
-        if (!exhausted && n_idle >= 8u)
+        if (n_service >= TGB_FL_SERVICE_LANES || n_working == 0)
         {
-            const u32 idle = __ballot_sync(0xFFFFFFFFu, state == TGB_FL_IDLE);
-            u32 base = 0;
-            const u32 leader = (u32)(__ffs(idle) - 1);
-            if (lane == leader) base = atomicAdd(&p_q_count[1], n_idle);
-            base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
-            if (state == TGB_FL_IDLE)
+            /* ---- service: unoccluded rays return their ambient term, voxel hits are decided, idle lanes fetch rays ---- */
+            if (kind == TGB_FL_MISS)
             {
-                const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
-                if (mine < n_rays)
+                /* ambient * 1 + lo; float addition commutes and the reductions do not stall the lane */
+                const float4 q0 = p_q0[slot], q2 = p_q2[slot];
+                f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
+                atomicAdd(p_pixel + 0, q2.x);
+                atomicAdd(p_pixel + 1, q2.y);
+                atomicAdd(p_pixel + 2, q2.z);
+                kind = TGB_FL_IDLE;
+            }
+            else if (kind == TGB_FL_HIT)
+            {
+                /* :219-256: result = enter / far of the slab test against the voxel. Only `enter` matters: the largest of the
+                 * three near-plane quotients, and min((lo - o) / d, (hi - o) / d) is the quotient of the plane the ray meets
+                 * first (division by d is monotone), so three divisions give the shader's value. */
+                const float4 q0 = p_q0[slot];
+                const v3 o = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
+                const v3 lo = tgb_add(child_min, tgb_v3((f32)x, (f32)y, (f32)z));
+                const v3 hi = tgb_add(child_min, tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)));
+                const f32 ex = d.x == 0.0f ? TG_F32_MIN : ((d.x > 0.0f ? lo.x : hi.x) - o.x) / d.x;
+                const f32 ey = d.y == 0.0f ? TG_F32_MIN : ((d.y > 0.0f ? lo.y : hi.y) - o.y) / d.y;
+                const f32 ez = d.z == 0.0f ? TG_F32_MIN : ((d.z > 0.0f ? lo.z : hi.z) - o.z) / d.z;
+                const f32 enter = tgb_max(tgb_max(ex, ey), ez);
+                /* only result < 1 ends the shader's loop (occluded), otherwise it advances past the leaf */
+                kind = (enter / far_plane < 1.0f) ? TGB_FL_IDLE : TGB_FL_TREE;
+            }
+            if (!exhausted)
+            {
+                const u32 idle = __ballot_sync(0xFFFFFFFFu, kind == TGB_FL_IDLE);
+                if (idle)
                 {
-                    slot = mine;
-                    const float4 q0 = p_q0[mine], q1 = p_q1[mine];
-                    const v3 o = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
-                    d = tgb_v3(q1.x, q1.y, q1.z);
-                    f32 enter, exit;
-                    if (tgb_ray_aabb(o, d, svo.bmin, svo.bmax, &enter, &exit)) /* :27-31; true: tested before queueing */
+                    const u32 n = (u32)__popc(idle);
+                    u32 base = 0;
+                    const u32 leader = (u32)(__ffs(idle) - 1);
+                    if (lane == leader) base = atomicAdd(&p_q_count[1], n);
+                    base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
+                    const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
+                    if (kind == TGB_FL_IDLE && mine < n_rays)
                     {
-                        position = o;
-                        if (enter > 0.0f) position = tgb_add(position, tgb_scale(d, enter));
+                        slot = mine;
+                        const float4 q0 = p_q0[mine], q1 = p_q1[mine];
+                        d = tgb_v3(q1.x, q1.y, q1.z);
+                        /* :27-31: k_shade made the slab test against the root and queued its `enter` */
+                        position = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
+                        if (q1.w > 0.0f) position = tgb_add(position, tgb_scale(d, q1.w));
                         iterations = 0;
                         advance_pending = false;
-                        /* :139-176: the DDA increments depend on the ray only */
-                        t_delta_x = d.x > 0.0f ? 1.0f / d.x : (d.x < 0.0f ? 1.0f / -d.x : TG_F32_MAX);
-                        t_delta_y = d.y > 0.0f ? 1.0f / d.y : (d.y < 0.0f ? 1.0f / -d.y : TG_F32_MAX);
-                        t_delta_z = d.z > 0.0f ? 1.0f / d.z : (d.z < 0.0f ? 1.0f / -d.z : TG_F32_MAX);
-                        state = TGB_FL_TREE;
+                        /* :139-176: the DDA increments 1 / |d| depend on the ray only (rcp.rn == IEEE 1 / x) */
+                        const f32 ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+                        t_delta_x = ax != 0.0f ? __frcp_rn(ax) : TG_F32_MAX;
+                        t_delta_y = ay != 0.0f ? __frcp_rn(ay) : TG_F32_MAX;
+                        t_delta_z = az != 0.0f ? __frcp_rn(az) : TG_F32_MAX;
+                        exotic = (ax != 0.0f && ax < 1e-30f) || (ay != 0.0f && ay < 1e-30f) || (az != 0.0f && az < 1e-30f);
+                        kind = TGB_FL_TREE;
                     }
+                    exhausted = base + n >= n_rays;
                 }
             }
-            exhausted = base + n_idle >= n_rays;
             continue;
         }
-        if (n_idle == 32u) break; /* queue drained and every ray finished */
 
-        u32 finished = 0; /* 1 = occluded, 2 = unoccluded */
         if (n_dda > n_tree)
         {
-            if (state == TGB_FL_DDA)
+            if (kind == TGB_FL_DDA)
             {
-                /* :178-257, steps written with selects (adding +0 to the other two t_max leaves them bit-identical) */
-                const i32 step_x = d.x > 0.0f ? 1 : (d.x < 0.0f ? -1 : 0);
-                const i32 step_y = d.y > 0.0f ? 1 : (d.y < 0.0f ? -1 : 0);
-                const i32 step_z = d.z > 0.0f ? 1 : (d.z < 0.0f ? -1 : 0);
-#pragma unroll 1
-                for (u32 k = 0; k < TGB_GI_DDA_STEPS; k++)
+                if (setup_pending)
                 {
-                    const u32 bits = __ldg(&p_block[32 * z + y]); /* a block row is one word: bit 1024 z + 32 y + x */
-                    n_steps++;
-                    if ((bits >> x) & 1u)
-                    {
-                        const float4 q0 = p_q0[slot];
-                        const v3 o = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
-                        const v3 voxel_min = tgb_add(child_min, tgb_v3((f32)x, (f32)y, (f32)z));
-                        const v3 voxel_max = tgb_add(child_min, tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)));
-                        f32 enter, exit;
-                        tgb_ray_aabb(o, d, voxel_min, voxel_max, &enter, &exit);
-                        /* :219-256 result = enter / far; only result < 1 ends the shader's loop, otherwise it advances */
-                        if (enter / far_plane < 1.0f) finished = 1u; else state = TGB_FL_TREE;
-                        break;
-                    }
-                    const bool xy = t_max_x < t_max_y;
-                    const bool go_x = xy & (t_max_x < t_max_z);
-                    const bool go_y = !xy & (t_max_y < t_max_z);
-                    const bool go_z = !(go_x | go_y);
-                    t_max_x = go_x ? t_max_x + t_delta_x : t_max_x;
-                    t_max_y = go_y ? t_max_y + t_delta_y : t_max_y;
-                    t_max_z = go_z ? t_max_z + t_delta_z : t_max_z;
-                    x += go_x ? step_x : 0;
-                    y += go_y ? step_y : 0;
-                    z += go_z ? step_z : 0;
-                    if ((u32)(x | y | z) > 31u) { state = TGB_FL_TREE; break; } /* left the block: a coordinate is -1 or 32 */
-                }
-            }
-        }
-        else if (state == TGB_FL_TREE)
-        {
-            bool inside = true;
-            if (advance_pending)
-            {
-                /* :279-294 advance to the far border of the terminal box, :296-324 the ray ends when it has left the root */
-                n_advances++;
-                const v3 child_max = tgb_add(child_min, tgb_v3(child_size, child_size, child_size));
-                const f32 exit = tgb_exit_distance(child_min, child_max, position, d);
-                position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
-                inside = tgb_still_inside(svo.bmin, svo.bmax, position, d);
-            }
-            advance_pending = true;
-            if (!inside || ++iterations > TGB_TRAVERSE_MAX_ITERS) finished = 2u;
-            else
-            {
-                /* :44-110: the terminal node around `position` */
-                n_visits++;
-                const u32 cx = tgb_cell_axis(position.x, d.x, svo.bmin.x);
-                const u32 cy = tgb_cell_axis(position.y, d.y, svo.bmin.y);
-                const u32 cz = tgb_cell_axis(position.z, d.z, svo.bmin.z);
-                const u32 entry = __ldg(&p_grid[(cz << 10) | (cy << 5) | cx]);
-                const u32 level = (entry >> TGB_TOP_LEVEL_SHIFT) & 7u;
-                const u32 cells = 16u >> level;              /* side of the terminal box in cells */
-                const u32 keep = ~(cells - 1u);
-                child_size = (f32)(cells << 5);
-                child_min = tgb_v3(svo.bmin.x + 32.0f * (f32)(cx & keep), svo.bmin.y + 32.0f * (f32)(cy & keep), svo.bmin.z + 32.0f * (f32)(cz & keep));
-                if (entry & TGB_TOP_HAS_DATA)
-                {
-                    /* :111-176 */
-                    p_block = svo.p_voxels + (u64)(entry & TGB_TOP_POINTER_MASK) * TG_SVO_BLOCK_WORDS;
-                    const v3 child_max = tgb_add(child_min, tgb_v3(child_size, child_size, child_size));
+                    /* :111-176: the lanes that entered a leaf since the last DDA phase set up together */
+                    setup_pending = false;
                     v3 hit = position;
-                    v3 xyz = tgb_v3(tgb_clamp(floorf(hit.x), child_min.x, child_max.x - 1.0f),
-                                    tgb_clamp(floorf(hit.y), child_min.y, child_max.y - 1.0f),
-                                    tgb_clamp(floorf(hit.z), child_min.z, child_max.z - 1.0f));
+                    v3 xyz = tgb_v3(tgb_clamp(floorf(hit.x), child_min.x, (child_min.x + child_size) - 1.0f),
+                                    tgb_clamp(floorf(hit.y), child_min.y, (child_min.y + child_size) - 1.0f),
+                                    tgb_clamp(floorf(hit.z), child_min.z, (child_min.z + child_size) - 1.0f));
                     hit = tgb_sub(hit, child_min);
                     xyz = tgb_sub(xyz, child_min);
                     x = (i32)xyz.x; y = (i32)xyz.y; z = (i32)xyz.z;
@@ -775,23 +780,68 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
                     else if (d.y < 0.0f) t_max_y = (hit.y - (f32)y) / -d.y;
                     if (d.z > 0.0f)      t_max_z = ((f32)(z + 1) - hit.z) / d.z;
                     else if (d.z < 0.0f) t_max_z = (hit.z - (f32)z) / -d.z;
-                    state = TGB_FL_DDA;
+                }
+                /* :178-257, steps written with selects (adding +0 to the other two t_max leaves them bit-identical) */
+                const i32 step_x = d.x > 0.0f ? 1 : (d.x < 0.0f ? -1 : 0);
+                const i32 step_y = d.y > 0.0f ? 1 : (d.y < 0.0f ? -1 : 0);
+                const i32 step_z = d.z > 0.0f ? 1 : (d.z < 0.0f ? -1 : 0);
+#pragma unroll 1
+                for (u32 k = 0; k < TGB_GI_DDA_STEPS; k++)
+                {
+                    const u32 bits = __ldg(&p_block[32 * z + y]); /* a block row is one word: bit 1024 z + 32 y + x */
+                    n_steps++;
+                    if ((bits >> x) & 1u) { kind = TGB_FL_HIT; break; }
+                    const bool xy = t_max_x < t_max_y;
+                    const bool go_x = xy & (t_max_x < t_max_z);
+                    const bool go_y = !xy & (t_max_y < t_max_z);
+                    const bool go_z = !(go_x | go_y);
+                    t_max_x = go_x ? t_max_x + t_delta_x : t_max_x;
+                    t_max_y = go_y ? t_max_y + t_delta_y : t_max_y;
+                    t_max_z = go_z ? t_max_z + t_delta_z : t_max_z;
+                    x += go_x ? step_x : 0;
+                    y += go_y ? step_y : 0;
+                    z += go_z ? step_z : 0;
+                    if ((u32)(x | y | z) > 31u) { kind = TGB_FL_TREE; break; } /* left the block: a coordinate is -1 or 32 */
                 }
             }
         }
-
-        if (finished)
+        else if (kind == TGB_FL_TREE)
         {
-            if (finished == 2u)
+            if (advance_pending)
             {
-                /* unoccluded: the ambient term comes back (ambient * 1 + lo); float addition commutes, the reductions do not stall */
-                const float4 q0 = p_q0[slot], q2 = p_q2[slot];
-                f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
-                atomicAdd(p_pixel + 0, q2.x);
-                atomicAdd(p_pixel + 1, q2.y);
-                atomicAdd(p_pixel + 2, q2.z);
+                /* :279-294 advance to the far border of the terminal box, :296-324 the ray ends when it has left the root */
+                n_advances++;
+                const f32 exit = tgb_exit_distance_rcp(child_min, child_size, position, d, t_delta_x, t_delta_y, t_delta_z, exotic);
+                position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
+                /* a position at least one unit inside every face passes the pop test (exit >= 1 / |d| >= ~1 > epsilon) without evaluating it */
+                const f32 off = fmaxf(fmaxf(fabsf(position.x - box_mid.x), fabsf(position.y - box_mid.y)), fabsf(position.z - box_mid.z));
+                if (!(off < 0.5f * (f32)TG_SVO_SIDE_LENGTH - 1.0f) && !tgb_still_inside(svo.bmin, svo.bmax, position, d)) kind = TGB_FL_MISS;
             }
-            state = TGB_FL_IDLE;
+            advance_pending = true;
+            if (kind == TGB_FL_TREE)
+            {
+                if (++iterations > TGB_TRAVERSE_MAX_ITERS) kind = TGB_FL_MISS;
+                else
+                {
+                    /* :44-110: the terminal node around `position` */
+                    n_visits++;
+                    const u32 cx = tgb_cell_axis(position.x, d.x, min_cell_x);
+                    const u32 cy = tgb_cell_axis(position.y, d.y, min_cell_y);
+                    const u32 cz = tgb_cell_axis(position.z, d.z, min_cell_z);
+                    const u32 entry = __ldg(&p_grid[(cz << 10) | (cy << 5) | cx]);
+                    const u32 level = (entry >> TGB_TOP_LEVEL_SHIFT) & 7u;
+                    const u32 cells = 16u >> level;              /* side of the terminal box in cells */
+                    const u32 keep = ~(cells - 1u);
+                    child_size = (f32)(cells << 5);
+                    child_min = tgb_v3(svo.bmin.x + (f32)((cx & keep) << 5), svo.bmin.y + (f32)((cy & keep) << 5), svo.bmin.z + (f32)((cz & keep) << 5));
+                    if (entry & TGB_TOP_HAS_DATA)
+                    {
+                        p_block = svo.p_voxels + (u64)(entry & TGB_TOP_POINTER_MASK) * TG_SVO_BLOCK_WORDS;
+                        setup_pending = true;
+                        kind = TGB_FL_DDA;
+                    }
+                }
+            }
         }
     }
     /* [2] look-ups, [3] DDA steps, [4] advances of this frame */
@@ -880,10 +930,10 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     if (gi)
     {
         /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
-        /* integer box corners: the flattened tree is exact (k_gi_trace_flat); the stack kernel runs only when the tree could not be tabulated */
+        /* box corners on the 32-unit lattice: the flattened tree is exact (k_gi_trace_flat); the stack kernel runs only when the tree could not be tabulated */
         const f32 c[6] = { a.svo.bmin.x, a.svo.bmin.y, a.svo.bmin.z, a.svo.bmax.x, a.svo.bmax.y, a.svo.bmax.z };
         bool flat = d->gi_traversal == 0;
-        for (int i = 0; i < 6; i++) flat = flat && c[i] == floorf(c[i]) && fabsf(c[i]) <= 4194304.0f;
+        for (int i = 0; i < 6; i++) flat = flat && fmodf(c[i], 32.0f) == 0.0f && fabsf(c[i]) <= 4194304.0f; /* corners on the 32-unit cell lattice */
         if (flat)
         {
             k_gi_trace_flat<<<d->n_sms * TGB_GI_FLAT_CTAS_PER_SM, TGB_GI_THREADS, 0, d->stream>>>(a.svo, d->svo.d_top_grid, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2,
