@@ -276,18 +276,78 @@ __device__ __forceinline__ u64 tgb_depth24(f32 t, f32 far_plane)
 }
 
 /*
- * One cluster, exactly visibility.frag:71-207 with the ray (o, d) in cluster space.
- * `best` is the running per-pixel minimum.
+ * What one ray keeps per object: the exact cluster-space direction d (shared by all clusters of the object,
+ * tgb_hoist.h), the DDA increments 1 / |d| (visibility.frag:105-136; rcp.rn is the IEEE quotient 1 / x) and their signed
+ * twins r = 1 / d, which double as APPROXIMATE reciprocals: n * r is within 2^-22 of the IEEE quotient n / d, so it can
+ * rank slab quotients and decide clear-cut comparisons, and an IEEE division is spent only on the value that is kept.
+ * `exotic` (a non-zero component below 1e-30, whose reciprocal overflows) switches every short cut off.
  */
-__device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, u32 cx, u32 cy, u32 cz, v3 d, f32 far_plane,
+struct tgb_ray_in_object
+{
+    v3  d;
+    f32 t_delta_x, t_delta_y, t_delta_z;
+    f32 rx, ry, rz;
+    bool exotic;
+};
+
+/*
+ * `enter` of collide.inc:3-24 for the box [lo, lo + size]^3 when the ray is already known to meet the box: the largest
+ * of the three near-plane quotients. min((lo - o) / d, (hi - o) / d) is the quotient of the plane the ray meets first
+ * (IEEE division by d is monotone), a zero component contributes -F32_MAX, and an axis whose approximate quotient is
+ * clearly below the largest one cannot be the maximum (rounding is monotone), so only the axes within 1e-5 of it are
+ * divided -- almost always one.
+ */
+__device__ __forceinline__ f32 tgb_slab_enter(const tgb_ray_in_object& r, f32 nx, f32 ny, f32 nz, f32 ex, f32 ey, f32 ez, f32 e_max)
+{
+    const f32 floor_e = e_max - (1e-5f * fabsf(e_max) + 1e-30f);
+    const bool cx = ex >= floor_e, cy = ey >= floor_e, cz = ez >= floor_e;
+    const f32 num = cx ? nx : (cy ? ny : nz), den = cx ? r.d.x : (cy ? r.d.y : r.d.z);
+    f32 enter = num / den;
+    if ((u32)cx + (u32)cy + (u32)cz != 1u)
+    {
+        enter = TG_F32_MIN;
+        if (cx && r.d.x != 0.0f) enter = tgb_max(enter, nx / r.d.x);
+        if (cy && r.d.y != 0.0f) enter = tgb_max(enter, ny / r.d.y);
+        if (cz && r.d.z != 0.0f) enter = tgb_max(enter, nz / r.d.z);
+    }
+    return enter;
+}
+
+/*
+ * One cluster, exactly visibility.frag:71-207 with the ray (o, d) in cluster space. `best` is the running per-pixel
+ * minimum, `t_skip` a ray parameter beyond which no hit can beat it (depth24(t) > depth24(best) for every t >= t_skip).
+ */
+__device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 far_plane,
                                                   const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
-                                                  u32 global_pointer_base, u64& best)
+                                                  u32 global_pointer_base, u64& best, f32& t_skip)
 {
     const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
-    f32 enter, exit;
-    if (!tgb_ray_aabb(o, d, tgb_v3(0.0f, 0.0f, 0.0f), tgb_v3(8.0f, 8.0f, 8.0f), &enter, &exit)) return;
-    /* voxel_enter >= enter (same o, d, nested boxes, monotone rounding) => depth24(hit) >= depth24(enter) */
-    if (tgb_depth24(enter, far_plane) > (best >> TG_VIS_DEPTH_SHIFT)) return;
+    const v3 d = r.d;
+
+    /* visibility.frag:71-81 = collide.inc:3-24 against [0,8]^3: hit iff exit > 0 && enter <= exit */
+    const f32 nx = (d.x > 0.0f ? 0.0f : 8.0f) - o.x, fx = (d.x > 0.0f ? 8.0f : 0.0f) - o.x;
+    const f32 ny = (d.y > 0.0f ? 0.0f : 8.0f) - o.y, fy = (d.y > 0.0f ? 8.0f : 0.0f) - o.y;
+    const f32 nz = (d.z > 0.0f ? 0.0f : 8.0f) - o.z, fz = (d.z > 0.0f ? 8.0f : 0.0f) - o.z;
+    const f32 ex = d.x != 0.0f ? nx * r.rx : TG_F32_MIN, xx = d.x != 0.0f ? fx * r.rx : TG_F32_MAX;
+    const f32 ey = d.y != 0.0f ? ny * r.ry : TG_F32_MIN, xy = d.y != 0.0f ? fy * r.ry : TG_F32_MAX;
+    const f32 ez = d.z != 0.0f ? nz * r.rz : TG_F32_MIN, xz = d.z != 0.0f ? fz * r.rz : TG_F32_MAX;
+    const f32 e_max = fmaxf(fmaxf(ex, ey), ez), x_min = fminf(fminf(xx, xy), xz);
+    const f32 tol = 1e-5f * (fabsf(e_max) + fabsf(x_min)) + 1e-30f;
+    f32 enter;
+    if (!r.exotic && ((x_min > tol) & (e_max + tol < x_min)))
+    {
+        /* clear hit; a cluster entered beyond t_skip cannot win (voxel_enter >= enter, depth24 is monotone) */
+        if (e_max - tol > t_skip) return;
+        enter = tgb_slab_enter(r, nx, ny, nz, ex, ey, ez, e_max);
+    }
+    else
+    {
+        if (!r.exotic && ((x_min < -tol) | (e_max - tol > x_min))) return; /* clear miss */
+        f32 exit;
+        if (!tgb_ray_aabb(o, d, tgb_v3(0.0f, 0.0f, 0.0f), tgb_v3(8.0f, 8.0f, 8.0f), &enter, &exit)) return;
+    }
+    /* voxel_enter >= enter (same o, d, nested boxes, monotone rounding) => depth24(hit) >= depth24(enter) > depth24(best) */
+    if (enter > t_skip) return;
 
     const u32 cluster_pointer = f.first_cluster_pointer + cx + f.nx * (cy + f.ny * cz);
     const u32 cluster_idx = __ldg(&p_cluster_pointers[cluster_pointer]);
@@ -303,13 +363,12 @@ __device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, u32
 
     i32 step_x = 0, step_y = 0, step_z = 0;
     f32 t_max_x = TG_F32_MAX, t_max_y = TG_F32_MAX, t_max_z = TG_F32_MAX;
-    f32 t_delta_x = TG_F32_MAX, t_delta_y = TG_F32_MAX, t_delta_z = TG_F32_MAX;
-    if (d.x > 0.0f)      { step_x = 1;  t_max_x = enter + ((f32)(x + 1) - hit.x) / d.x; t_delta_x = 1.0f / d.x; }
-    else if (d.x < 0.0f) { step_x = -1; t_max_x = enter + (hit.x - (f32)x) / -d.x;      t_delta_x = 1.0f / -d.x; }
-    if (d.y > 0.0f)      { step_y = 1;  t_max_y = enter + ((f32)(y + 1) - hit.y) / d.y; t_delta_y = 1.0f / d.y; }
-    else if (d.y < 0.0f) { step_y = -1; t_max_y = enter + (hit.y - (f32)y) / -d.y;      t_delta_y = 1.0f / -d.y; }
-    if (d.z > 0.0f)      { step_z = 1;  t_max_z = enter + ((f32)(z + 1) - hit.z) / d.z; t_delta_z = 1.0f / d.z; }
-    else if (d.z < 0.0f) { step_z = -1; t_max_z = enter + (hit.z - (f32)z) / -d.z;      t_delta_z = 1.0f / -d.z; }
+    if (d.x > 0.0f)      { step_x = 1;  t_max_x = enter + ((f32)(x + 1) - hit.x) / d.x; }
+    else if (d.x < 0.0f) { step_x = -1; t_max_x = enter + (hit.x - (f32)x) / -d.x; }
+    if (d.y > 0.0f)      { step_y = 1;  t_max_y = enter + ((f32)(y + 1) - hit.y) / d.y; }
+    else if (d.y < 0.0f) { step_y = -1; t_max_y = enter + (hit.y - (f32)y) / -d.y; }
+    if (d.z > 0.0f)      { step_z = 1;  t_max_z = enter + ((f32)(z + 1) - hit.z) / d.z; }
+    else if (d.z < 0.0f) { step_z = -1; t_max_z = enter + (hit.z - (f32)z) / -d.z; }
 
     /* visibility.frag:141-191; the 64-bit z-slice (words 2z, 2z+1) is fetched once per z */
     i32 z_cached = -1;
@@ -326,27 +385,45 @@ __device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, u32
         if ((word >> (((y & 3) << 3) + x)) & 1u) { found = true; break; }
         if (t_max_x < t_max_y)
         {
-            if (t_max_x < t_max_z) { t_max_x += t_delta_x; x += step_x; if (x < 0 || x >= 8) break; }
-            else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
+            if (t_max_x < t_max_z) { t_max_x += r.t_delta_x; x += step_x; if (x < 0 || x >= 8) break; }
+            else                   { t_max_z += r.t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
         }
         else
         {
-            if (t_max_y < t_max_z) { t_max_y += t_delta_y; y += step_y; if (y < 0 || y >= 8) break; }
-            else                   { t_max_z += t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
+            if (t_max_y < t_max_z) { t_max_y += r.t_delta_y; y += step_y; if (y < 0 || y >= 8) break; }
+            else                   { t_max_z += r.t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
         }
     }
     if (!found) return;
 
-    /* visibility.frag:151-157, 194-201 */
-    f32 voxel_enter, voxel_exit;
-    tgb_ray_aabb(o, d, tgb_v3((f32)x, (f32)y, (f32)z), tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)), &voxel_enter, &voxel_exit);
+    /* visibility.frag:151-157, 194-201: depth from the slab test against the voxel; only its `enter` is used */
+    f32 voxel_enter;
+    {
+        const f32 vx = (f32)(d.x > 0.0f ? x : x + 1) - o.x, vy = (f32)(d.y > 0.0f ? y : y + 1) - o.y, vz = (f32)(d.z > 0.0f ? z : z + 1) - o.z;
+        if (!r.exotic)
+        {
+            const f32 qx = d.x != 0.0f ? vx * r.rx : TG_F32_MIN, qy = d.y != 0.0f ? vy * r.ry : TG_F32_MIN, qz = d.z != 0.0f ? vz * r.rz : TG_F32_MIN;
+            voxel_enter = tgb_slab_enter(r, vx, vy, vz, qx, qy, qz, fmaxf(fmaxf(qx, qy), qz));
+        }
+        else
+        {
+            f32 voxel_exit;
+            tgb_ray_aabb(o, d, tgb_v3((f32)x, (f32)y, (f32)z), tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)), &voxel_enter, &voxel_exit);
+        }
+    }
     const f32 depth = tgb_max(0.0f, voxel_enter / far_plane);
     if (depth <= 1.0f)
     {
-        const u64 word = ((u64)(depth * TG_VIS_DEPTH_SCALE) << TG_VIS_DEPTH_SHIFT)
+        const f32 dq = depth * TG_VIS_DEPTH_SCALE;
+        const u64 word = ((u64)dq << TG_VIS_DEPTH_SHIFT)
                        | ((u64)(cluster_pointer + global_pointer_base) << TG_VIS_POINTER_SHIFT)
                        | (u64)(u32)(64 * z + 8 * y + x);
-        if (word < best) best = word;
+        if (word < best)
+        {
+            best = word;
+            /* t / far * 16777215 >= trunc(dq) + 1 puts depth24(t) above the best depth: t_skip with a 1e-5 relative cushion */
+            t_skip = (truncf(dq) + 1.0f) * (far_plane * (1.00001f / TG_VIS_DEPTH_SCALE));
+        }
     }
 }
 
@@ -356,13 +433,23 @@ __device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, u32
  */
 __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 dir_ws, f32 far_plane,
                                                  const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
-                                                 u32 global_pointer_base, u64& best)
+                                                 u32 global_pointer_base, u64& best, f32& t_skip)
 {
-    const v3 d = tgb_hoist_direction(&f, dir_ws); /* exact d_ms, shared by all clusters of the object */
+    tgb_ray_in_object r;
+    r.d = tgb_hoist_direction(&f, dir_ws); /* exact d_ms, shared by all clusters of the object */
+    const v3 d = r.d;
     const f32 e = f.eps;
+    const f32 adx = fabsf(d.x), ady = fabsf(d.y), adz = fabsf(d.z);
+    /* visibility.frag:105-136: t_delta = 1 / d or 1 / -d, absent axis F32_MAX */
+    r.t_delta_x = adx != 0.0f ? __frcp_rn(adx) : TG_F32_MAX;
+    r.t_delta_y = ady != 0.0f ? __frcp_rn(ady) : TG_F32_MAX;
+    r.t_delta_z = adz != 0.0f ? __frcp_rn(adz) : TG_F32_MAX;
+    r.rx = d.x < 0.0f ? -r.t_delta_x : r.t_delta_x;
+    r.ry = d.y < 0.0f ? -r.t_delta_y : r.t_delta_y;
+    r.rz = d.z < 0.0f ? -r.t_delta_z : r.t_delta_z;
+    r.exotic = (adx != 0.0f && adx < 1e-30f) || (ady != 0.0f && ady < 1e-30f) || (adz != 0.0f && adz < 1e-30f);
 
     /* permute so that axis k is the dominant one */
-    const f32 adx = fabsf(d.x), ady = fabsf(d.y), adz = fabsf(d.z);
     const int k = (adx >= ady && adx >= adz) ? 0 : (ady >= adz ? 1 : 2);
     const f32 dk = k == 0 ? d.x : (k == 1 ? d.y : d.z);
     const f32 du = k == 0 ? d.y : (k == 1 ? d.z : d.x);
@@ -376,7 +463,7 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
     if (!(fabsf(dk) > 0.5f)) return; /* |d| == 1 => dominant component >= 0.577; false only for NaN directions */
 
     /* conservative slab of the inflated object box; u / v slabs only when the ray is not parallel to them */
-    const f32 inv_dk = 1.0f / dk;
+    const f32 inv_dk = k == 0 ? r.rx : (k == 1 ? r.ry : r.rz);
     f32 t_in, t_out;
     {
         const f32 ta = (-e - ok) * inv_dk, tb = (8.0f * (f32)nk + e - ok) * inv_dk;
@@ -384,14 +471,14 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
     }
     if (fabsf(du) > 1e-20f)
     {
-        const f32 inv = 1.0f / du;
+        const f32 inv = k == 0 ? r.ry : (k == 1 ? r.rz : r.rx);
         const f32 ta = (-e - ou) * inv, tb = (8.0f * (f32)nu + e - ou) * inv;
         t_in = fmaxf(t_in, fminf(ta, tb)); t_out = fminf(t_out, fmaxf(ta, tb));
     }
     else if (ou < -e || ou > 8.0f * (f32)nu + e) return;
     if (fabsf(dv) > 1e-20f)
     {
-        const f32 inv = 1.0f / dv;
+        const f32 inv = k == 0 ? r.rz : (k == 1 ? r.rx : r.ry);
         const f32 ta = (-e - ov) * inv, tb = (8.0f * (f32)nv + e - ov) * inv;
         t_in = fmaxf(t_in, fminf(ta, tb)); t_out = fminf(t_out, fmaxf(ta, tb));
     }
@@ -416,11 +503,7 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
         if (t0 <= t1)
         {
             /* slices are visited with non-decreasing t0: once even the slice entry is behind the best hit, stop */
-            if (best != TG_VIS_CLEAR)
-            {
-                const f32 t_lb = t0 - (4.0f * e + 3.0517578125e-5f * fabsf(t0));
-                if (tgb_depth24(t_lb, far_plane) > (best >> TG_VIS_DEPTH_SHIFT)) return;
-            }
+            if (t0 - (4.0f * e + 3.0517578125e-5f * fabsf(t0)) > t_skip) return;
             const f32 ua = ou + t0 * du, ub = ou + t1 * du;
             const f32 va = ov + t0 * dv, vb = ov + t1 * dv;
             const f32 pad = 2.0f * e + 3.0517578125e-5f * (fabsf(ou) + fabsf(ov) + t1);
@@ -435,7 +518,7 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
                     const u32 cx = (u32)(k == 0 ? s : (k == 1 ? cv : cu));
                     const u32 cy = (u32)(k == 0 ? cu : (k == 1 ? s : cv));
                     const u32 cz = (u32)(k == 0 ? cv : (k == 1 ? cu : s));
-                    tgb_visit_cluster(f, cx, cy, cz, d, far_plane, p_cluster_pointers, p_masks, global_pointer_base, best);
+                    tgb_visit_cluster(f, r, cx, cy, cz, far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
                 }
             }
         }
@@ -444,40 +527,77 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
 }
 
 /*
- * One CTA = one 16x16 pixel tile, one warp = one 8x4 pixel block (coherent rays), one lane = one
- * ray. Objects arrive front to back; a lane retires from the object loop once the next object's
- * lower depth bound exceeds its best word, a warp once all its lanes did. The resolve is a single
- * 64-bit atomicMin per hit pixel (visibility.frag:206) so that other passes / shards may target
- * the same buffer.
+ * One CTA = one 16x16 pixel tile, one warp = one 8x4 pixel block (coherent rays), one lane = one ray. The CTA first
+ * compacts, window by window, the (front-to-back sorted) objects whose screen rectangle overlaps its tile into shared
+ * memory, so a warp only walks the few objects near it. A lane retires from the object loop once the next object's
+ * lower depth bound exceeds its best word, a warp once all its lanes did. The resolve is a single 64-bit atomicMin per
+ * hit pixel (visibility.frag:206) so that other passes / shards may target the same buffer.
  */
-__global__ void __launch_bounds__(256) k_visibility(const tgb_object_frame* __restrict__ p_frames, const u32* __restrict__ p_count,
-                                                     tg_camera_rays cam, u32 w, u32 h,
-                                                     const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
-                                                     u32 global_pointer_base, u64* __restrict__ p_vis)
+#define TGB_K1_THREADS 256
+__global__ void __launch_bounds__(TGB_K1_THREADS) k_visibility(const tgb_object_frame* __restrict__ p_frames, const u32* __restrict__ p_count,
+                                                               tg_camera_rays cam, u32 w, u32 h,
+                                                               const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
+                                                               u32 global_pointer_base, u64* __restrict__ p_vis)
 {
+    __shared__ u32 s_list[TGB_K1_THREADS];
+    __shared__ u32 s_warp_count[TGB_K1_THREADS / 32];
+
     const u32 n_visible = p_count[0];
     if (n_visible == 0) return;
     const bool sorted = p_count[1] != 0;
 
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const i32 tx0 = (i32)(blockIdx.x * TGB_TILE_W), ty0 = (i32)(blockIdx.y * TGB_TILE_H);
+    const i32 tx1 = (i32)min(blockIdx.x * TGB_TILE_W + TGB_TILE_W - 1u, w - 1u), ty1 = (i32)min(blockIdx.y * TGB_TILE_H + TGB_TILE_H - 1u, h - 1u);
     const u32 wx0 = blockIdx.x * TGB_TILE_W + (warp & 1u) * 8u;
     const u32 wy0 = blockIdx.y * TGB_TILE_H + (warp >> 1) * 4u;
-    if (wx0 >= w || wy0 >= h) return; /* warp-uniform */
+    const bool warp_on_screen = wx0 < w && wy0 < h; /* warp-uniform */
     const u32 px = wx0 + (lane & 7u), py = wy0 + (lane >> 3);
     const bool in_screen = px < w && py < h;
     const i32 wx1 = (i32)min(wx0 + 7u, w - 1u), wy1 = (i32)min(wy0 + 3u, h - 1u);
 
-    const v3 dir_ws = tgb_pixel_direction(&cam, w, h, in_screen ? px : wx0, in_screen ? py : wy0);
+    const v3 dir_ws = tgb_pixel_direction(&cam, w, h, in_screen ? px : min(wx0, w - 1u), in_screen ? py : min(wy0, h - 1u));
     u64 best = TG_VIS_CLEAR;
+    f32 t_skip = TG_F32_MAX;
+    bool warp_done = !warp_on_screen;
 
-    for (u32 i = 0; i < n_visible; i++)
+    for (u32 base = 0; base < n_visible; base += TGB_K1_THREADS)
     {
-        const tgb_object_frame& f = p_frames[i];
-        const bool behind_best = !in_screen || (u64)f.min_depth24 > (best >> TG_VIS_DEPTH_SHIFT);
-        if (sorted && __all_sync(TGB_FULL_MASK, behind_best)) break;
-        if (f.x1 < (i32)wx0 || f.x0 > wx1 || f.y1 < (i32)wy0 || f.y0 > wy1) continue; /* warp-uniform */
-        if (behind_best || (i32)px < f.x0 || (i32)px > f.x1 || (i32)py < f.y0 || (i32)py > f.y1) continue;
-        tgb_trace_object(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best);
+        /* order-preserving compaction of this window's objects that overlap the tile */
+        const u32 i = base + threadIdx.x;
+        bool overlaps = false;
+        if (i < n_visible)
+        {
+            const tgb_object_frame& f = p_frames[i];
+            overlaps = !(f.x1 < tx0 || f.x0 > tx1 || f.y1 < ty0 || f.y0 > ty1);
+        }
+        const u32 ballot = __ballot_sync(TGB_FULL_MASK, overlaps);
+        if (lane == 0) s_warp_count[warp] = (u32)__popc(ballot);
+        __syncthreads();
+        u32 offset = 0, n_listed = 0;
+#pragma unroll
+        for (u32 k = 0; k < TGB_K1_THREADS / 32; k++)
+        {
+            const u32 c = s_warp_count[k];
+            offset += k < warp ? c : 0u;
+            n_listed += c;
+        }
+        if (overlaps) s_list[offset + (u32)__popc(ballot & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+
+        if (!warp_done)
+        {
+            for (u32 j = 0; j < n_listed; j++)
+            {
+                const tgb_object_frame& f = p_frames[s_list[j]];
+                const bool behind_best = !in_screen || (u64)f.min_depth24 > (best >> TG_VIS_DEPTH_SHIFT);
+                if (sorted && __all_sync(TGB_FULL_MASK, behind_best)) { warp_done = true; break; }
+                if (f.x1 < (i32)wx0 || f.x0 > wx1 || f.y1 < (i32)wy0 || f.y0 > wy1) continue; /* warp-uniform */
+                if (behind_best || (i32)px < f.x0 || (i32)px > f.x1 || (i32)py < f.y0 || (i32)py > f.y1) continue;
+                tgb_trace_object(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+            }
+        }
+        if (base + TGB_K1_THREADS < n_visible) __syncthreads(); /* s_list is rewritten by the next window */
     }
 
     if (in_screen && best != TG_VIS_CLEAR) atomicMin((unsigned long long*)&p_vis[(u64)py * w + px], (unsigned long long)best);
