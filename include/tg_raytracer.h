@@ -113,6 +113,20 @@ TG_EXPORT void tg_raytracer_color_lut_set_ex(tg_raytracer* p_raytracer, u32 lut_
 /* GI on/off + RNG seed of the secondary rays. */
 TG_EXPORT void tg_raytracer_set_gi(tg_raytracer* p_raytracer, b32 enabled, u32 frame_seed);
 
+/*
+ * Frame sink: the reference hands its HDR target to the swapchain (tgvk_raytracer.c:1524-1553); a host application of this
+ * library reads the frame back instead. With a sink set, every tg_raytracer_render() / tgb200_render_shading() shades in
+ * `n_bands` row bands (1..16) and copies each finished band into `p_host` on a second stream while the next band is
+ * shaded, so the PCIe transfer of the 16 B/pixel frame overlaps the rendering. `p_host` receives the rows this rank
+ * shades (tgb200_tile_rows; the whole frame on one GPU), first shaded row first, 4 floats per pixel; pinned memory makes
+ * the copy asynchronous. The sink may be changed between frames (double buffering): a frame's ticket is
+ * tgb200_frame_ticket() right after its render call, tgb200_wait_frame(ticket) blocks until that frame is complete in
+ * host memory, tgb200_synchronize() waits for everything. NULL switches the sink off.
+ */
+TG_EXPORT void tgb200_set_frame_sink(tg_raytracer* p_raytracer, f32* p_host, u32 n_bands);
+TG_EXPORT u64  tgb200_frame_ticket(tg_raytracer* p_raytracer);
+TG_EXPORT void tgb200_wait_frame(tg_raytracer* p_raytracer, u64 ticket);
+
 /* Secondary-ray kernel: 0 = automatic (stackless over the flattened tree whenever the SVO box corners are multiples of 32, the
  * stack machine of svo_functions.inc otherwise), 1 = always the stack machine. Both give the same radiance (tests). */
 TG_EXPORT void tgb200_set_gi_traversal(tg_raytracer* p_raytracer, u32 kind);

@@ -44,6 +44,9 @@ SYMBOLS = {
     "tg_raytracer_color_lut_set_ex": (None, [_RT, T.u32, T.u8, T.f32, T.f32, T.f32]),
     "tg_raytracer_set_gi": (None, [_RT, T.b32, T.u32]),
     "tgb200_set_gi_traversal": (None, [_RT, T.u32]),
+    "tgb200_set_frame_sink": (None, [_RT, C.c_void_p, T.u32]),
+    "tgb200_frame_ticket": (T.u64, [_RT]),
+    "tgb200_wait_frame": (None, [_RT, T.u64]),
     "tgb200_render_visibility": (None, [_RT]),
     "tgb200_svo_update": (None, [_RT, T.b32]),
     "tgb200_svo_leaves_resampled": (T.u32, [_RT]),

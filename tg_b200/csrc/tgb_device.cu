@@ -9,6 +9,16 @@
 
 #include "tgb_device.cuh"
 
+/* tuning knobs read from the environment (integers; unset or malformed = the default) */
+extern "C" i32 tgbd_env_int(const char* p_name, i32 fallback)
+{
+    const char* p = getenv(p_name);
+    if (!p || !*p) return fallback;
+    char* p_end = NULL;
+    const long v = strtol(p, &p_end, 10);
+    return (p_end && *p_end == 0) ? (i32)v : fallback;
+}
+
 extern "C" i32 tgbd_device_count(void)
 {
     int n = 0;
@@ -30,20 +40,29 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMalloc(&d->d_frames_all, no * sizeof(tgb_object_frame)));
     TGB_CUDA(cudaMalloc(&d->d_visible_count, 4 * sizeof(u32)));
     TGB_CUDA(cudaMalloc(&d->d_gi_count, 32 * sizeof(u32)));
-    TGB_CUDA(cudaMallocHost(&d->h_gi_stats, 32 * sizeof(u32)));
+    TGB_CUDA(cudaHostAlloc((void**)&d->h_gi_stats, 32 * sizeof(u32), cudaHostAllocMapped));
     memset(d->h_gi_stats, 0, 32 * sizeof(u32));
     {
         int n_sms = 0;
         TGB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, d->device));
         d->n_sms = (u32)(n_sms > 0 ? n_sms : 148);
     }
-    TGB_CUDA(cudaMallocHost(&d->h_visible_count, 4 * sizeof(u32)));
+    TGB_CUDA(cudaHostAlloc((void**)&d->h_visible_count, 4 * sizeof(u32), cudaHostAllocMapped));
     TGB_CUDA(cudaMemsetAsync(d->d_cluster_pointers, 0, nc * sizeof(u32), d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_c2o, 0, nc * sizeof(u32), d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_objects, 0, no * sizeof(tg_object_data), d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_masks, 0, nc * 64, d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_color_lut, 0, (u64)d->n_color_luts * 256 * sizeof(u32), d->stream));
     for (int i = 0; i < 12; i++) TGB_CUDA(cudaEventCreate(&d->ev[i]));
+    TGB_CUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < TGB_MAX_BANDS; i++)
+    {
+        TGB_CUDA(cudaEventCreateWithFlags(&d->ev_band[i], cudaEventDisableTiming));
+        TGB_CUDA(cudaEventCreateWithFlags(&d->ev_band_copied[0][i], cudaEventDisableTiming));
+        TGB_CUDA(cudaEventCreateWithFlags(&d->ev_band_copied[1][i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < TGB_FRAME_RING; i++) TGB_CUDA(cudaEventCreateWithFlags(&d->ev_frame_copied[i], cudaEventDisableTiming));
+    d->sink_bands = 1;
 
     /*
      * SVO capacities. The reference reserves 2^14 nodes, 2^13 leaf records and 2^21 voxel words = 2048 blocks
@@ -67,6 +86,8 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
 {
     TGB_CUDA(cudaSetDevice(d->device));
     TGB_CUDA(cudaStreamSynchronize(d->stream));
+    if (d->copy_stream) TGB_CUDA(cudaStreamSynchronize(d->copy_stream)); /* pending band copies read the buffers freed below */
+    for (int i = 0; i < TGB_MAX_BANDS; i++) d->band_copy_pending[0][i] = d->band_copy_pending[1][i] = TG_FALSE;
     if (d->n_ranks == 0) d->n_ranks = 1;
     d->tile_rows = (height + d->n_ranks - 1) / d->n_ranks;
     const u64 padded_px = (u64)width * d->tile_rows * d->n_ranks; /* >= width * height: equal tiles for the collectives */
@@ -80,7 +101,10 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
         TGB_CUDA(cudaMemsetAsync(d->d_mat, 0, padded_px * sizeof(u64), d->stream));
     }
     if (d->d_vis) TGB_CUDA(cudaFree(d->d_vis));
-    if (d->d_radiance) TGB_CUDA(cudaFree(d->d_radiance));
+    if (d->d_radiance_pair[0]) TGB_CUDA(cudaFree(d->d_radiance_pair[0]));
+    if (d->d_radiance_pair[1]) TGB_CUDA(cudaFree(d->d_radiance_pair[1]));
+    d->d_radiance_pair[0] = d->d_radiance_pair[1] = NULL;
+    d->radiance_flip = 0;
     if (d->d_gi_q0) TGB_CUDA(cudaFree(d->d_gi_q0));
     if (d->d_gi_q1) TGB_CUDA(cudaFree(d->d_gi_q1));
     if (d->d_gi_q2) TGB_CUDA(cudaFree(d->d_gi_q2));
@@ -90,7 +114,8 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     d->width = width;
     d->height = height;
     TGB_CUDA(cudaMalloc(&d->d_vis, (u64)width * height * sizeof(u64)));
-    TGB_CUDA(cudaMalloc(&d->d_radiance, padded_px * sizeof(float4)));
+    TGB_CUDA(cudaMalloc(&d->d_radiance_pair[0], padded_px * sizeof(float4)));
+    d->d_radiance = d->d_radiance_pair[0];
     TGB_CUDA(cudaMalloc(&d->d_gi_q0, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMalloc(&d->d_gi_q1, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMalloc(&d->d_gi_q2, (u64)width * height * sizeof(float4)));
@@ -145,8 +170,9 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     if (!d) return;
     cudaSetDevice(d->device);
     cudaStreamSynchronize(d->stream);
+    if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
     cudaFree(d->d_cluster_pointers); cudaFree(d->d_c2o); cudaFree(d->d_objects); cudaFree(d->d_masks);
-    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_count);
+    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance_pair[0]); cudaFree(d->d_radiance_pair[1]); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_count);
     cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
     if (d->h_gi_stats) cudaFreeHost(d->h_gi_stats);
@@ -155,6 +181,9 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaFree(d->svo.d_voxels_alt); cudaFree(d->svo.d_leaf_data_alt); cudaFree(d->svo.d_object_moved); cudaFree(d->svo.d_moved_indices); cudaFree(d->svo.d_part); cudaFree(d->svo.d_gather);
     cudaFree(d->d_mat); cudaFree(d->d_mat_tile); cudaFree(d->d_objects_global); cudaFree(d->d_frames_global);
     for (int i = 0; i < 12; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    for (int i = 0; i < TGB_MAX_BANDS; i++) { if (d->ev_band[i]) cudaEventDestroy(d->ev_band[i]); if (d->ev_band_copied[0][i]) cudaEventDestroy(d->ev_band_copied[0][i]); if (d->ev_band_copied[1][i]) cudaEventDestroy(d->ev_band_copied[1][i]); }
+    for (int i = 0; i < TGB_FRAME_RING; i++) if (d->ev_frame_copied[i]) cudaEventDestroy(d->ev_frame_copied[i]);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     cudaStreamDestroy(d->stream);
     cudaGetLastError();
     free(d);
@@ -233,7 +262,27 @@ extern "C" void tgbd_synchronize(struct tgb_device* d)
 {
     cudaSetDevice(d->device);
     cudaError_t e = cudaStreamSynchronize(d->stream);
+    if (e == cudaSuccess && d->copy_stream) e = cudaStreamSynchronize(d->copy_stream);
     if (e != cudaSuccess) tgb_set_error("cudaStreamSynchronize -> %s", cudaGetErrorString(e));
+}
+
+/* ---- frame sink ---- */
+extern "C" b32 tgbd_set_frame_sink(struct tgb_device* d, f32* p_host, u32 n_bands)
+{
+    d->p_sink = p_host;
+    d->sink_bands = n_bands < 1 ? 1 : (n_bands > TGB_MAX_BANDS ? TGB_MAX_BANDS : n_bands);
+    return TG_TRUE;
+}
+
+extern "C" u64 tgbd_frames_sunk(struct tgb_device* d) { return d->n_frames_sunk; }
+
+extern "C" b32 tgbd_wait_frame(struct tgb_device* d, u64 ticket)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    if (ticket == 0 || ticket > d->n_frames_sunk) { tgb_set_error("wait_frame: ticket %llu was never issued (%llu frames so far)", (unsigned long long)ticket, (unsigned long long)d->n_frames_sunk); return TG_FALSE; }
+    if (d->n_frames_sunk - ticket >= TGB_FRAME_RING) { TGB_CUDA(cudaStreamSynchronize(d->copy_stream)); return TG_TRUE; } /* older than the ring: everything up to now */
+    TGB_CUDA(cudaEventSynchronize(d->ev_frame_copied[ticket % TGB_FRAME_RING]));
+    return TG_TRUE;
 }
 
 extern "C" void tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base) { d->global_pointer_base = global_pointer_base; }
@@ -280,9 +329,11 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
     p_out->svo_ms = d->svo_ms;
     p_out->shading_ms = d->shading_ms;
     p_out->merge_ms = d->merge_ms;
-    if (d->ev_vis) d->n_visible_objects = d->h_visible_count[0];
+    /* the counters live on the device during the frames (no per-frame read-back); fetch them now */
+    if (d->ev_vis) { cudaMemcpy(d->h_visible_count, d->d_visible_count, 2 * sizeof(u32), cudaMemcpyDeviceToHost); d->n_visible_objects = d->h_visible_count[0]; }
+    if (d->gi_stats_valid) cudaMemcpy(d->h_gi_stats, d->d_gi_count, 32 * sizeof(u32), cudaMemcpyDeviceToHost);
     p_out->n_visible_objects = d->n_visible_objects;
-    p_out->n_gi_rays = d->h_gi_stats[0];
+    p_out->n_gi_rays = d->h_gi_stats[10];
     p_out->n_gi_node_visits = ((const u64*)d->h_gi_stats)[1];
     p_out->n_gi_dda_steps = ((const u64*)d->h_gi_stats)[2];
     p_out->n_gi_advances = ((const u64*)d->h_gi_stats)[3];

@@ -21,6 +21,9 @@
 #define TGB_TOP_LEVEL_SHIFT   28u         /* bits 28..30: depth of the inner node whose child is terminal (child side = 512 >> level) */
 #define TGB_TOP_POINTER_MASK  0x0FFFFFFFu
 
+#define TGB_MAX_BANDS  16
+#define TGB_FRAME_RING 4
+
 struct tgb_svo_device
 {
     v3   bmin, bmax;
@@ -77,6 +80,7 @@ struct tgb_device
     u32*            h_gi_stats;   /* pinned copy of d_gi_count after the last frame */
     u32             n_sms;
     u32             gi_traversal; /* 0 = stackless when possible, 1 = stack machine */
+    b32             gi_stats_valid; /* d_gi_count holds the counters of the last shaded frame */
 
     /* multi-GPU (one process per GPU): clusters sharded by object, SVO / objects replicated, GI split by screen tile */
     void*             p_comm;           /* NCCL communicator or NULL */
@@ -95,12 +99,39 @@ struct tgb_device
 
     tgb_svo_device svo;
 
+    /* frame sink (tgb200_set_frame_sink): the shading stage runs in row bands and every finished band is copied to host
+     * memory on a second stream while the next band is shaded */
+    cudaStream_t copy_stream;
+    f32*         p_sink;            /* caller memory (pinned for a truly asynchronous copy) or NULL */
+    u32          sink_bands;        /* bands per frame, 1..TGB_MAX_BANDS */
+    cudaEvent_t  ev_band[TGB_MAX_BANDS];      /* band k shaded (main stream) */
+    cudaEvent_t  ev_band_copied[2][TGB_MAX_BANDS]; /* band k of buffer p copied (copy stream): the next frame shaded into p waits for it */
+    /* the radiance buffer is double-buffered while a sink is set (frame i+1 is shaded while frame i is still being copied) */
+    float4*      d_radiance_pair[2]; /* [0] allocated by tgbd_resize, [1] on first use of a sink; d_radiance points at the current one */
+    u32          radiance_flip;
+    b32          band_copy_pending[2][TGB_MAX_BANDS];
+    u32          band_row0[2][TGB_MAX_BANDS], band_row1[2][TGB_MAX_BANDS]; /* rows of the pending copies, per radiance buffer */
+    cudaEvent_t  ev_frame_copied[TGB_FRAME_RING];
+    u64          n_frames_sunk;     /* frames whose copies have been issued */
+
     cudaEvent_t ev[12];
     f32         clear_ms, cull_ms, visibility_ms, svo_ms, shading_ms, merge_ms;
     b32         ev_clear, ev_vis, ev_svo, ev_shade, ev_merge;
     u32         n_visible_objects;
     u32         n_kernel_launches;
 };
+
+/*
+ * Small per-frame bookkeeping goes through kernels, not cudaMemsetAsync / cudaMemcpyAsync: a memset or copy on the render
+ * stream queues behind the frame sink's large device-to-host copies in the copy engine and stalls the stream until they
+ * drain (measured: the shading bands of one frame and the visibility pass of the next waited for the whole 133 MB).
+ * Counters stay on the device and are fetched by tgbd_get_timings only (a per-frame store to mapped host memory also
+ * waits for the PCIe queue: +0.2 ms on the visibility pass).
+ */
+static __global__ void k_set_words(u32* __restrict__ p, u32 n, u32 value)
+{
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) p[i] = value;
+}
 
 #define TGB_CUDA(call)                                                                              \
     do {                                                                                            \

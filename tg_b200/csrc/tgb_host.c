@@ -635,6 +635,24 @@ void tgb200_comm_destroy(tg_raytracer* p_raytracer)
     tgbn_destroy(p_comm);
 }
 
+void tgb200_set_frame_sink(tg_raytracer* p_raytracer, f32* p_host, u32 n_bands)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_set_frame_sink")) return;
+    tgbd_set_frame_sink(p_raytracer->p_device, p_host, n_bands);
+}
+
+u64 tgb200_frame_ticket(tg_raytracer* p_raytracer)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_frame_ticket")) return 0;
+    return tgbd_frames_sunk(p_raytracer->p_device);
+}
+
+void tgb200_wait_frame(tg_raytracer* p_raytracer, u64 ticket)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_wait_frame")) return;
+    tgbd_wait_frame(p_raytracer->p_device, ticket);
+}
+
 void tgb200_set_gi_traversal(tg_raytracer* p_raytracer, u32 kind)
 {
     if (!tgb__alive(p_raytracer, "tgb200_set_gi_traversal")) return;

@@ -33,6 +33,7 @@ enum
 void tgb_set_error(const char* p_fmt, ...);
 
 /* ---- tgb_device.cu ---- */
+i32   tgbd_env_int(const char* p_name, i32 fallback);
 i32   tgbd_device_count(void);
 struct tgb_device* tgbd_create(i32 device, u32 object_capacity, u32 cluster_capacity, u32 n_color_luts, u32 width, u32 height);
 void  tgbd_destroy(struct tgb_device* d);
@@ -48,6 +49,10 @@ void  tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out);
 void  tgbd_reset_launch_counter(struct tgb_device* d);
 void  tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base);
 void  tgbd_set_gi_traversal(struct tgb_device* d, u32 kind);
+/* frame sink: shading in row bands, each band copied to p_host (rows this rank shades, first shaded row first) on a second stream */
+b32   tgbd_set_frame_sink(struct tgb_device* d, f32* p_host, u32 n_bands);
+u64   tgbd_frames_sunk(struct tgb_device* d);
+b32   tgbd_wait_frame(struct tgb_device* d, u64 ticket);
 b32   tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n_ranks);
 u32   tgbd_tile_rows(struct tgb_device* d);
 void* tgbd_comm(struct tgb_device* d);

@@ -156,7 +156,8 @@ struct tgb_shade_args
     u32 w, h;
     u32 global_pointer_base, n_local_pointers;
     u32 gi_enabled, frame_seed, debug_visualization;
-    u32 y0, y1; /* rows [y0, y1) are shaded (multi-GPU: this rank's screen tile) */
+    u32 y0, y1; /* rows [y0, y1) are shaded by this launch (a band of this rank's screen tile) */
+    u32 mat_y0; /* first row of the tile p_mat describes */
     /* GI ray queue (SoA): origin.xyz + pixel | direction.xyz + enter of the root slab test | ambient.rgb */
     float4* __restrict__ p_q0;
     float4* __restrict__ p_q1;
@@ -187,7 +188,7 @@ __device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px,
     u32 local_pointer, cluster_idx, object_idx, color_lut_idx, packed_color;
     if (RESOLVED)
     {
-        const u64 mat = a.p_mat[(u64)(py - a.y0) * a.w + px];
+        const u64 mat = a.p_mat[(u64)(py - a.mat_y0) * a.w + px];
         if (mat == 0) { *p_color = make_float4(0.0f, 0.0f, 0.0f, 0.0f); return false; } /* no rank owns this pointer: inconsistent shards */
         local_pointer = cluster_pointer_31b; /* global pointer against globalised object records */
         cluster_idx = cluster_pointer_31b;   /* debug views only */
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
 
     const u32 tid = threadIdx.x, lane = tid & 31u;
     const u32 n_rays = p_q_count[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
     const v3 extent = tgb_sub(svo.bmax, svo.bmin);
     const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin); /* svo_functions.inc:3-8 */
 
@@ -671,13 +673,14 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
 
     const u32 lane = threadIdx.x & 31u;
     const u32 n_rays = p_q_count[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
     const v3 extent = tgb_sub(svo.bmax, svo.bmin);
     const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin); /* svo_functions.inc:3-8 */
     const v3 box_mid = tgb_scale(tgb_add(svo.bmin, svo.bmax), 0.5f);
     const i32 min_cell_x = (i32)(svo.bmin.x * 0.03125f), min_cell_y = (i32)(svo.bmin.y * 0.03125f), min_cell_z = (i32)(svo.bmin.z * 0.03125f);
 
     u32 kind = TGB_FL_IDLE, slot = 0, iterations = 0;
-    bool advance_pending = false, setup_pending = false, exotic = false;
+    bool advance_pending = false, setup_pending = false, border_pending = false, exotic = false;
     v3 d = tgb_v3(0.0f, 0.0f, 0.0f), position = d, child_min = d;
     f32 child_size = 0.0f;
     f32 t_max_x = 0.0f, t_max_y = 0.0f, t_max_z = 0.0f, t_delta_x = 0.0f, t_delta_y = 0.0f, t_delta_z = 0.0f;
@@ -697,6 +700,12 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
         if (n_service >= TGB_FL_SERVICE_LANES || n_working == 0)
         {
             /* ---- service: unoccluded rays return their ambient term, voxel hits are decided, idle lanes fetch rays ---- */
+            if (kind == TGB_FL_MISS && border_pending)
+            {
+                /* :296-324 for a ray within one unit of a root face: still inside -> back to the tree, position already advanced */
+                border_pending = false;
+                if (tgb_still_inside(svo.bmin, svo.bmax, position, d)) { kind = TGB_FL_TREE; advance_pending = false; }
+            }
             if (kind == TGB_FL_MISS)
             {
                 /* ambient * 1 + lo; float addition commutes and the reductions do not stall the lane */
@@ -785,10 +794,10 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
                 const i32 step_x = d.x > 0.0f ? 1 : (d.x < 0.0f ? -1 : 0);
                 const i32 step_y = d.y > 0.0f ? 1 : (d.y < 0.0f ? -1 : 0);
                 const i32 step_z = d.z > 0.0f ? 1 : (d.z < 0.0f ? -1 : 0);
+                u32 bits = __ldg(&p_block[32 * z + y]); /* a block row is one word: bit 1024 z + 32 y + x; re-read only when the row changes */
 #pragma unroll 1
                 for (u32 k = 0; k < TGB_GI_DDA_STEPS; k++)
                 {
-                    const u32 bits = __ldg(&p_block[32 * z + y]); /* a block row is one word: bit 1024 z + 32 y + x */
                     n_steps++;
                     if ((bits >> x) & 1u) { kind = TGB_FL_HIT; break; }
                     const bool xy = t_max_x < t_max_y;
@@ -802,6 +811,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
                     y += go_y ? step_y : 0;
                     z += go_z ? step_z : 0;
                     if ((u32)(x | y | z) > 31u) { kind = TGB_FL_TREE; break; } /* left the block: a coordinate is -1 or 32 */
+                    if (!go_x) bits = __ldg(&p_block[32 * z + y]);
                 }
             }
         }
@@ -815,7 +825,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
                 position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
                 /* a position at least one unit inside every face passes the pop test (exit >= 1 / |d| >= ~1 > epsilon) without evaluating it */
                 const f32 off = fmaxf(fmaxf(fabsf(position.x - box_mid.x), fabsf(position.y - box_mid.y)), fabsf(position.z - box_mid.z));
-                if (!(off < 0.5f * (f32)TG_SVO_SIDE_LENGTH - 1.0f) && !tgb_still_inside(svo.bmin, svo.bmax, position, d)) kind = TGB_FL_MISS;
+                if (!(off < 0.5f * (f32)TG_SVO_SIDE_LENGTH - 1.0f)) { kind = TGB_FL_MISS; border_pending = true; } /* the few rays near a face: the test itself runs in the service phase */
             }
             advance_pending = true;
             if (kind == TGB_FL_TREE)
@@ -899,6 +909,19 @@ __global__ void __launch_bounds__(256) k_resolve_material(const u64* __restrict_
 
 static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam, bool resolved, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1)
 {
+    if (d->p_sink)
+    {
+        /* double-buffered radiance: this frame goes to the buffer the frame before last used, whose copies are (long) done */
+        if (!d->d_radiance_pair[1])
+        {
+            const u64 n_bytes = (u64)d->width * d->tile_rows * (d->n_ranks ? d->n_ranks : 1) * sizeof(float4);
+            TGB_CUDA(cudaMalloc(&d->d_radiance_pair[1], n_bytes));
+            TGB_CUDA(cudaMemsetAsync(d->d_radiance_pair[1], 0, n_bytes, d->stream));
+        }
+        d->radiance_flip ^= 1u;
+        d->d_radiance = d->d_radiance_pair[d->radiance_flip];
+    }
+    const u32 buf = d->radiance_flip;
     tgb_shade_args a;
     a.p_vis = d->d_vis;
     a.p_out = d->d_radiance;
@@ -918,33 +941,81 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     a.global_pointer_base = d->global_pointer_base;
     a.n_local_pointers = n_local_pointers;
     a.gi_enabled = gi_enabled; a.frame_seed = frame_seed; a.debug_visualization = debug_visualization;
-    a.y0 = y0; a.y1 = y1;
+    a.mat_y0 = y0;
     a.p_q0 = d->d_gi_q0; a.p_q1 = d->d_gi_q1; a.p_q2 = d->d_gi_q2; a.p_q_count = d->d_gi_count;
     a.p_mat = d->d_mat_tile;
     const bool gi = gi_enabled && debug_visualization == TG_DEBUG_SHOW_NONE;
-    if (gi) TGB_CUDA(cudaMemsetAsync(d->d_gi_count, 0, 32 * sizeof(u32), d->stream));
-    const dim3 grid((d->width + 15) / 16, (y1 - y0 + 15) / 16);
-    if (resolved) k_shade<true><<<grid, 256, 0, d->stream>>>(a);
-    else          k_shade<false><<<grid, 256, 0, d->stream>>>(a);
-    TGB_LAUNCH_CHECK(d);
-    if (gi)
+    if (gi) { k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count, 32, 0u); TGB_LAUNCH_CHECK(d); }
+
+    /* box corners on the 32-unit lattice: the flattened tree is exact (k_gi_trace_flat); the stack kernel runs only when the tree could not be tabulated */
+    bool flat = d->gi_traversal == 0;
     {
-        /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
-        /* box corners on the 32-unit lattice: the flattened tree is exact (k_gi_trace_flat); the stack kernel runs only when the tree could not be tabulated */
         const f32 c[6] = { a.svo.bmin.x, a.svo.bmin.y, a.svo.bmin.z, a.svo.bmax.x, a.svo.bmax.y, a.svo.bmax.z };
-        bool flat = d->gi_traversal == 0;
         for (int i = 0; i < 6; i++) flat = flat && fmodf(c[i], 32.0f) == 0.0f && fabsf(c[i]) <= 4194304.0f; /* corners on the 32-unit cell lattice */
-        if (flat)
+    }
+    static const int gi_ctas = max(1, min(16, tgbd_env_int("TGB_GI_CTAS_PER_SM", TGB_GI_FLAT_CTAS_PER_SM))); /* persistent CTAs per SM (tuning only) */
+
+    /*
+     * With a frame sink the rows are shaded in bands and every finished band is copied to the caller's memory on the copy
+     * stream while the next band is shaded (the 133 MB RGBA32F frame takes as long over PCIe as the whole frame takes to
+     * render). A band that would overwrite rows whose copy from the previous frame is still in flight waits for that copy.
+     */
+    const u32 n_bands = d->p_sink ? d->sink_bands : 1u;
+    const u32 band_rows = (((y1 - y0) + n_bands - 1u) / n_bands + 15u) & ~15u; /* whole 16-row tiles of k_shade */
+    b32 new_pending[TGB_MAX_BANDS];
+    for (u32 k = 0; k < TGB_MAX_BANDS; k++) new_pending[k] = TG_FALSE;
+    for (u32 b = 0; b < n_bands; b++)
+    {
+        const u32 by0 = y0 + b * band_rows;
+        if (by0 >= y1) break;
+        const u32 by1 = by0 + band_rows < y1 ? by0 + band_rows : y1;
+        for (u32 k = 0; k < TGB_MAX_BANDS; k++)
         {
-            k_gi_trace_flat<<<d->n_sms * TGB_GI_FLAT_CTAS_PER_SM, TGB_GI_THREADS, 0, d->stream>>>(a.svo, d->svo.d_top_grid, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2,
-                                                                                                 d->d_gi_count, d->d_radiance);
+            if (d->band_copy_pending[buf][k] && d->band_row0[buf][k] < by1 && by0 < d->band_row1[buf][k])
+            {
+                TGB_CUDA(cudaStreamWaitEvent(d->stream, d->ev_band_copied[buf][k], 0));
+                d->band_copy_pending[buf][k] = TG_FALSE;
+            }
+        }
+        a.y0 = by0; a.y1 = by1;
+        if (gi && b > 0) { k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count, 2, 0u); TGB_LAUNCH_CHECK(d); } /* queued / fetched; the work counters accumulate over the bands */
+        const dim3 grid((d->width + 15) / 16, (by1 - by0 + 15) / 16);
+        if (resolved) k_shade<true><<<grid, 256, 0, d->stream>>>(a);
+        else          k_shade<false><<<grid, 256, 0, d->stream>>>(a);
+        TGB_LAUNCH_CHECK(d);
+        if (gi)
+        {
+            /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
+            if (flat)
+            {
+                k_gi_trace_flat<<<d->n_sms * (u32)gi_ctas, TGB_GI_THREADS, 0, d->stream>>>(a.svo, d->svo.d_top_grid, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2,
+                                                                                        d->d_gi_count, d->d_radiance);
+                TGB_LAUNCH_CHECK(d);
+            }
+            k_gi_trace<<<d->n_sms * 8, TGB_GI_THREADS, 0, d->stream>>>(a.svo, flat ? d->svo.d_top_grid + TGB_TOP_GRID_CELLS : NULL, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2,
+                                                                       d->d_gi_count, d->d_radiance);
             TGB_LAUNCH_CHECK(d);
         }
-        k_gi_trace<<<d->n_sms * 8, TGB_GI_THREADS, 0, d->stream>>>(a.svo, flat ? d->svo.d_top_grid + TGB_TOP_GRID_CELLS : NULL, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2,
-                                                                   d->d_gi_count, d->d_radiance);
-        TGB_LAUNCH_CHECK(d);
-        TGB_CUDA(cudaMemcpyAsync(d->h_gi_stats, d->d_gi_count, 32 * sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
+        if (d->p_sink)
+        {
+            const u64 offset = (u64)(by0 - y0) * d->width * 4u, n_bytes = (u64)(by1 - by0) * d->width * sizeof(float4);
+            TGB_CUDA(cudaEventRecord(d->ev_band[b], d->stream));
+            TGB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_band[b], 0));
+            TGB_CUDA(cudaMemcpyAsync(d->p_sink + offset, d->d_radiance + (u64)by0 * d->width, n_bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+            TGB_CUDA(cudaEventRecord(d->ev_band_copied[buf][b], d->copy_stream));
+            new_pending[b] = TG_TRUE;
+            /* an older copy still tracked under this index (the band layout changed): keep the union of the row ranges, the re-recorded event covers both */
+            d->band_row0[buf][b] = d->band_copy_pending[buf][b] && d->band_row0[buf][b] < by0 ? d->band_row0[buf][b] : by0;
+            d->band_row1[buf][b] = d->band_copy_pending[buf][b] && d->band_row1[buf][b] > by1 ? d->band_row1[buf][b] : by1;
+        }
     }
+    if (d->p_sink)
+    {
+        for (u32 k = 0; k < TGB_MAX_BANDS; k++) d->band_copy_pending[buf][k] = d->band_copy_pending[buf][k] || new_pending[k];
+        d->n_frames_sunk++;
+        TGB_CUDA(cudaEventRecord(d->ev_frame_copied[d->n_frames_sunk % TGB_FRAME_RING], d->copy_stream));
+    }
+    d->gi_stats_valid = gi ? TG_TRUE : TG_FALSE;
     return TG_TRUE;
 }
 

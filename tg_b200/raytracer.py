@@ -199,6 +199,24 @@ class Raytracer:
     def gather_radiance(self):
         self._lib.tgb200_gather_radiance(C.byref(self._rt))
 
+    def set_frame_sink(self, host_array, n_bands=8):
+        """Every later render() copies its shaded rows into `host_array` (float32, rows x w x 4; pinned for overlap) band by
+        band while the frame is still being shaded; None switches it off."""
+        if host_array is None:
+            self._sink = None
+            self._lib.tgb200_set_frame_sink(C.byref(self._rt), None, 1)
+            return
+        assert host_array.dtype == np.float32 and host_array.flags["C_CONTIGUOUS"]
+        self._sink = host_array  # keep it alive while copies may be in flight
+        self._lib.tgb200_set_frame_sink(C.byref(self._rt), host_array.ctypes.data, n_bands)
+
+    def frame_ticket(self):
+        return int(self._lib.tgb200_frame_ticket(C.byref(self._rt)))
+
+    def wait_frame(self, ticket):
+        self._lib.tgb200_wait_frame(C.byref(self._rt), ticket)
+        self._check()
+
     def set_gi_traversal(self, kind):
         """0 = automatic (stackless over the flattened tree), 1 = the stack machine of svo_functions.inc."""
         self._lib.tgb200_set_gi_traversal(C.byref(self._rt), kind)
