@@ -1,7 +1,8 @@
 """ORACLE -- TEST INFRASTRUCTURE ONLY.
 
 ctypes front-end of oracle/libtgo.so (the scalar C restatement of the reference's voxel-rendering path)
-and of oracle/_ref/libtg_ref_aw.so (the reference's own util/tg_amanatides_woo.c, compiled unmodified).
+and of oracle/_ref/libtg_ref.so (the reference's own portable C files -- math, physics, Amanatides-Woo, the CPU SVO builder and
+traversal -- compiled from /root/reference by oracle/Makefile; used to pin the restatement).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this;
 nothing under tg_b200/ does.
 """
@@ -31,11 +32,11 @@ class tgo_scene_view(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libtgo.so")
-    srcs = [os.path.join(_HERE, f) for f in ("tgo_visibility.c", "tgo_svo.c", "tgo_shade.c", "tgo.h", "tgo_math.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("tgo_visibility.c", "tgo_svo.c", "tgo_shade.c", "tgo_procedural.c", "tgo.h", "tgo_math.h")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "libtgo.so"], stdout=subprocess.DEVNULL)
-    if os.path.exists("/root/reference/tg/src/util/tg_amanatides_woo.c") and (force or not os.path.exists(os.path.join(_HERE, "_ref", "libtg_ref_aw.so"))):
+    if os.path.exists("/root/reference/tg/src/graphics/tg_sparse_voxel_octree.c") and (force or not os.path.exists(os.path.join(_HERE, "_ref", "libtg_ref.so"))):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -72,23 +73,86 @@ def lib():
         L.tgo_intersect_aabb_obb_ignore_contact.restype = T.b32
         L.tgo_shade.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, C.POINTER(T.u64), C.POINTER(T.tg_svo),
                                 T.u32, T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.f32)]
+        L.tgo_simplex_noise.argtypes = [T.f32, T.f32, T.f32]
+        L.tgo_simplex_noise.restype = T.f32
+        L.tgo_procedural_voxel_is_solid.argtypes = [T.u32, T.u32, T.u32, T.u32]
+        L.tgo_procedural_voxel_is_solid.restype = T.b32
+        L.tgo_procedural_solid_bits.argtypes = [T.u32, T.v3u, C.POINTER(T.u32)]
+        for name, res, args in _MATH_SIGNATURES:
+            fn = getattr(L, "tgo_pin_" + name)
+            fn.restype, fn.argtypes = res, args
+        L.tgo_pin_xorshift32_next.argtypes = [C.POINTER(T.u32)]
+        L.tgo_pin_xorshift32_next.restype = T.u32
+        L.tgo_pin_xorshift32_next_f32.argtypes = [C.POINTER(T.u32)]
+        L.tgo_pin_xorshift32_next_f32.restype = T.f32
+        L.tgo_pin_xorshift32_next_f32_range.argtypes = [C.POINTER(T.u32), T.f32, T.f32]
+        L.tgo_pin_xorshift32_next_f32_range.restype = T.f32
+        L.tgo_pin_intersect_ray_aabb_c.argtypes = [T.v3, T.v3, T.v3, T.v3, C.POINTER(T.f32), C.POINTER(T.f32)]
+        L.tgo_pin_intersect_ray_aabb_c.restype = T.b32
         _LIB = L
     return _LIB
 
 
-def ref_aw():
-    """The reference's own tg_amanatides_woo (oracle/_ref), or None when it was never built."""
+# the tgo_math.h routines exported for the pins and their twins in the reference's math/tg_math.c (tgm_<name>)
+_MATH_SIGNATURES = [
+    ("m4_mul", T.m4, [T.m4, T.m4]), ("m4_inverse", T.m4, [T.m4]), ("m4_angle_axis", T.m4, [T.f32, T.v3]), ("m4_euler", T.m4, [T.f32, T.f32, T.f32]),
+    ("m4_perspective", T.m4, [T.f32, T.f32, T.f32, T.f32]), ("m4_translate", T.m4, [T.v3]), ("m4_mulv4", T.v4, [T.m4, T.v4]),
+    ("v3_normalized", T.v3, [T.v3]), ("v3_lerp", T.v3, [T.v3, T.v3, T.f32]),
+]
+
+
+def ref():
+    """The reference's own portable C (oracle/_ref/libtg_ref.so: math/tg_math.c, physics/tg_physics.c, util/tg_amanatides_woo.c,
+    graphics/tg_sparse_voxel_octree.c), or None when it was never built (no reference tree at build time)."""
     global _REF
     if _REF is None:
         build()
-        path = os.path.join(_HERE, "_ref", "libtg_ref_aw.so")
+        path = os.path.join(_HERE, "_ref", "libtg_ref.so")
         if not os.path.exists(path):
             return None
         R = C.CDLL(path)
         R.tg_amanatides_woo.argtypes = [T.v3, T.v3, T.v3, C.POINTER(T.u32), C.POINTER(T.v3i)]
         R.tg_amanatides_woo.restype = T.b32
+        for name, res, args in _MATH_SIGNATURES:
+            fn = getattr(R, "tgm_" + name)
+            fn.restype, fn.argtypes = res, args
+        R.tgm_simplex_noise.argtypes = [T.f32, T.f32, T.f32]
+        R.tgm_simplex_noise.restype = T.f32
+        R.tgm_rand_xorshift32_next_u32.argtypes = [C.POINTER(T.u32)]
+        R.tgm_rand_xorshift32_next_u32.restype = T.u32
+        R.tgm_rand_xorshift32_next_f32.argtypes = [C.POINTER(T.u32)]
+        R.tgm_rand_xorshift32_next_f32.restype = T.f32
+        R.tgm_rand_xorshift32_next_f32_inclusive_range.argtypes = [C.POINTER(T.u32), T.f32, T.f32]
+        R.tgm_rand_xorshift32_next_f32_inclusive_range.restype = T.f32
+        R.tg_intersect_ray_aabb.argtypes = [T.v3, T.v3, T.v3, T.v3, C.POINTER(T.f32), C.POINTER(T.f32)]
+        R.tg_intersect_ray_aabb.restype = T.b32
+        R.tg_intersect_aabb_obb_ignore_contact.argtypes = [T.v3, T.v3, C.POINTER(T.v3)]
+        R.tg_intersect_aabb_obb_ignore_contact.restype = T.b32
+        R.tg_svo_create.argtypes = [T.v3, T.v3, C.POINTER(T.tg_scene), C.POINTER(T.tg_svo)]
+        R.tg_svo_destroy.argtypes = [C.POINTER(T.tg_svo)]
+        R.tg_svo_traverse.argtypes = [C.POINTER(T.tg_svo), T.v3, T.v3, C.POINTER(T.f32), C.POINTER(T.u32), C.POINTER(T.u32)]
+        R.tg_svo_traverse.restype = T.b32
         _REF = R
     return _REF
+
+
+def ref_aw():
+    """Kept name: the library that holds the reference's tg_amanatides_woo."""
+    return ref()
+
+
+def ref_scene(view):
+    """A tg_scene (tgvk_raytracer.h:90-108) over the arrays of a SceneView, as the reference's tg_svo_create reads it."""
+    s = T.tg_scene()
+    s.object_capacity = len(view.voxel_objects)
+    s.n_objects = len(view.voxel_objects)
+    s.p_objects = view.voxel_objects.ctypes.data_as(C.POINTER(T.tg_voxel_object))
+    s.cluster_pointer_capacity = len(view.cluster_pointers)
+    s.n_cluster_pointers = len(view.cluster_pointers)
+    s.p_cluster_pointers = T.ptr(view.cluster_pointers, T.u32)
+    s.p_voxel_cluster_data = T.ptr(view.masks, T.u32)
+    s.p_cluster_idx_to_object_idx = T.ptr(view.c2o, T.u32)
+    return s
 
 
 def camera_rays(cam):

@@ -4,11 +4,17 @@
  *
  * Scalar C restatement of the reference's voxel-rendering path (its shader logic + its CPU SVO
  * builder). PARITY PINNING: the reference has no tests, golden vectors or known-answer fixtures of
- * any kind for this path (SURVEY.md sections 4 and 8c) and its Win32/Vulkan/MSVC sources do not
- * build here, so parity is pinned by (a) literal transcription with file:line provenance,
- * (b) the one reference file that compiles unmodified under gcc -- util/tg_amanatides_woo.c,
- * built into oracle/_ref/ and cross-checked against the transcribed DDA, and (c) hand-derived
- * known-answer cases in tests/. Beyond that: "parity unpinned" by reference-run outputs.
+ * any kind for this path (SURVEY.md sections 4 and 8c), and its application (Win32 + Vulkan + GLSL) cannot
+ * run here. What CAN be built is the reference's portable C: math/tg_math.c, physics/tg_physics.c,
+ * util/tg_amanatides_woo.c and graphics/tg_sparse_voxel_octree.c compile under gcc from where they lie
+ * (oracle/Makefile -> oracle/_ref/libtg_ref.so). tests/test_reference_pins.py runs THE REFERENCE'S OWN
+ * tg_svo_create, tg_svo_traverse, matrix / noise / RNG routines, slab and SAT tests on the same inputs as
+ * this restatement and demands identical bits: the SVO builder, the CPU traversal and the whole math layer
+ * are pinned by reference-run outputs. The shader logic (visibility.frag, shading.frag, svo_functions.inc)
+ * has no runnable reference (no Vulkan ICD, no GLSL compiler in the image): it is pinned by literal
+ * transcription with file:line provenance on top of that pinned math layer, by its C twins where the
+ * reference has one (tg_svo_traverse, tg_intersect_ray_aabb, tg_amanatides_woo), and by hand-derived
+ * known answers in tests/ -- for those three shaders: "parity unpinned" by reference-run outputs.
  */
 #ifndef TGO_H
 #define TGO_H
@@ -71,6 +77,12 @@ b32  tgo_svo_traverse_c(const tg_svo* p_svo, v3 ray_origin, v3 ray_direction, f3
 b32  tgo_amanatides_woo(v3 ray_hit_on_grid, v3 ray_direction, v3 extent, const u32* p_voxel_grid, v3i* p_voxel_id);
 /* physics/tg_physics.c:226-392 */
 b32  tgo_intersect_aabb_obb_ignore_contact(v3 bmin, v3 bmax, const v3* p_obb_corners);
+
+/* math/tg_math.c:182-302 */
+f32  tgo_simplex_noise(f32 x, f32 y, f32 z);
+/* tgvk_raytracer.c:871-943: the reference's procedural terrain bits of one object (16 u32 per cluster, pointer order) */
+b32  tgo_procedural_voxel_is_solid(u32 object_idx, u32 voxel_x, u32 voxel_y, u32 voxel_z);
+void tgo_procedural_solid_bits(u32 object_idx, v3u dims, u32* p_out);
 
 /* shading.frag:114-337 (+ the pinned GI term of DESIGN.md) for rows y0, y0+ystep, ... < y1 (other rows untouched). RGBA32F out. */
 void tgo_shade(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, const u64* p_vis, const tg_svo* p_svo_or_null,

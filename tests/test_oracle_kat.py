@@ -104,10 +104,10 @@ def test_camera_inside_and_beside_objects(oracle):
 
 def test_dda_against_reference_amanatides_woo(oracle):
     """The restated Amanatides-Woo (tgo_amanatides_woo, tgo_cluster_dda) against the REFERENCE's own
-    util/tg_amanatides_woo.c built unmodified into oracle/_ref/libtg_ref_aw.so."""
+    util/tg_amanatides_woo.c built unmodified into oracle/_ref/libtg_ref.so."""
     R = oracle.ref_aw()
     if R is None:
-        pytest.skip("oracle/_ref/libtg_ref_aw.so was not built (reference tree absent at build time)")
+        pytest.skip("oracle/_ref/libtg_ref.so was not built (reference tree absent at build time)")
     L = oracle.lib()
     rng = np.random.default_rng(7)
     for n in (8, 32):

@@ -69,6 +69,19 @@ def test_against_committed_golden_fixtures(gpu, name):
     assert np.array_equal(nz, g["svo_voxels_nonzero_idx"]) and np.array_equal(vox[nz], g["svo_voxels_nonzero"])
 
 
+@pytest.mark.parametrize("name", ["small_grid", "grid4_tall", "config1_small", "dense_k1", "sparse_k5"])
+def test_against_reference_made_fixtures(gpu, name):
+    """K2 against arrays THE REFERENCE'S OWN tg_svo_create produced (tests/golden/make_reference_golden.py ran the reference's
+    graphics/tg_sparse_voxel_octree.c, compiled from /root/reference, on these scenes)."""
+    from tests.golden.make_reference_golden import SVO_CASES
+    g = np.load(os.path.join(GOLDEN, f"ref_svo_{name}.npz"))
+    nodes, leaf, vox, _ = gpu_svo(SVO_CASES[name]())
+    assert np.array_equal(nodes, g["nodes"]), "node array differs from the reference's"
+    assert np.array_equal(leaf, g["leaf"]), "leaf records differ from the reference's"
+    nz = np.nonzero(vox)[0].astype(np.uint32)
+    assert vox.size == int(g["n_voxel_words"]) and np.array_equal(nz, g["voxels_nonzero_idx"]) and np.array_equal(vox[nz], g["voxels_nonzero"])
+
+
 def test_known_answer_single_axis_aligned_cluster(gpu):
     """SURVEY 8c KAT: one solid 8^3 cluster, axis aligned, centred at (20,20,20): blocks [0,32)^3 only, exactly 512 bits."""
     s = scenes.config1(k=1, dims=(1, 1, 1), width=64, height=36)
