@@ -141,6 +141,14 @@ def ref_aw():
     return ref()
 
 
+def procedural_solid_bits(object_idx, dims):
+    """tgvk_raytracer.c:871-943 restated (oracle/tgo_procedural.c): [n_clusters, 16] uint32 in pointer order."""
+    n = dims[0] * dims[1] * dims[2]
+    out = np.zeros((n, 16), dtype=np.uint32)
+    lib().tgo_procedural_solid_bits(object_idx, T.v3u(*dims), T.ptr(out, T.u32))
+    return out
+
+
 def ref_scene(view):
     """A tg_scene (tgvk_raytracer.h:90-108) over the arrays of a SceneView, as the reference's tg_svo_create reads it."""
     s = T.tg_scene()

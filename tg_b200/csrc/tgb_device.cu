@@ -19,6 +19,13 @@ extern "C" i32 tgbd_env_int(const char* p_name, i32 fallback)
     return (p_end && *p_end == 0) ? (i32)v : fallback;
 }
 
+extern "C" i32 tgbd_current_device(void)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return dev;
+}
+
 extern "C" i32 tgbd_device_count(void)
 {
     int n = 0;

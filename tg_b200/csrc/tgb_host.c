@@ -280,31 +280,42 @@ static b32 tgb__contiguous_run(const tg_scene* p_scene, const tg_voxel_object* p
     return n == 0 || (p[n - 1] - p[0] == n - 1 && p[n - 1] >= p[0]);
 }
 
-u32 tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
-                                         const u32* p_solid_bits, const u8* p_lut_indices)
+/*
+ * Shared tail of the two object constructors: scene bookkeeping (tgvk_raytracer.c:816-866), device mirrors of the object
+ * record / pointer range / cluster->object map, then the voxel bits -- given by the caller, or (p_solid_bits == NULL) the
+ * reference's procedural terrain generated ON THE DEVICE straight into the resident mask array (tgb_procedural.cu; the
+ * reference's own note at tgvk_raytracer.c:868 is "TODO: gen on GPU") and read back into the scene's CPU mirror
+ * p_voxel_cluster_data, which the reference keeps too (:934).
+ */
+static u32 tgb__create_object(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
+                              const u32* p_solid_bits, const u8* p_lut_indices)
 {
-    if (!tgb__alive(p_raytracer, "tg_raytracer_create_object_from_data")) return TG_U32_MAX;
-    TGB_REQUIRE(p_solid_bits != NULL, TG_U32_MAX, "create_object_from_data: NULL solid bits");
-    TGB_REQUIRE(lut_idx < p_raytracer->n_color_luts, TG_U32_MAX, "create_object_from_data: LUT index %u out of range (%u LUTs)", lut_idx, p_raytracer->n_color_luts);
     tg_scene* p_scene = &p_raytracer->scene;
     const u32 object_idx = tgb200_scene_alloc_object(p_scene, center, extent, angle_in_radians, axis);
     if (object_idx == TG_U32_MAX) return TG_U32_MAX;
     p_raytracer->p_object_lut_idx[object_idx] = lut_idx;
 
     const tg_voxel_object* p_object = &p_scene->p_objects[object_idx];
-    const u32 n = p_object->n_cluster_pointers_per_dim.x * p_object->n_cluster_pointers_per_dim.y * p_object->n_cluster_pointers_per_dim.z;
+    const v3u dims = p_object->n_cluster_pointers_per_dim;
+    const u32 n = dims.x * dims.y * dims.z;
     const u32 first = p_object->first_cluster_pointer;
     struct tgb_device* d = p_raytracer->p_device;
 
     tgb__upload_object_record(p_raytracer, object_idx);
     tgbd_upload(d, TGB_BUF_CLUSTER_POINTERS, (u64)first * 4, &p_scene->p_cluster_pointers[first], (u64)n * 4);
+    if (!p_solid_bits) tgbd_procedural_fill(d, object_idx, dims.x, dims.y, dims.z, first); /* after the pointer upload: same stream */
 
     if (tgb__contiguous_run(p_scene, p_object, n))
     {
         const u32 idx0 = p_scene->p_cluster_pointers[first];
-        memcpy(&p_scene->p_voxel_cluster_data[(size_t)idx0 * TG_CLUSTER_MASK_WORDS], p_solid_bits, (size_t)n * 64);
+        u32* p_mirror = &p_scene->p_voxel_cluster_data[(size_t)idx0 * TG_CLUSTER_MASK_WORDS];
         tgbd_upload(d, TGB_BUF_C2O, (u64)idx0 * 4, &p_scene->p_cluster_idx_to_object_idx[idx0], (u64)n * 4);
-        tgbd_upload(d, TGB_BUF_MASKS, (u64)idx0 * 64, p_solid_bits, (u64)n * 64);
+        if (p_solid_bits)
+        {
+            memcpy(p_mirror, p_solid_bits, (size_t)n * 64);
+            tgbd_upload(d, TGB_BUF_MASKS, (u64)idx0 * 64, p_solid_bits, (u64)n * 64);
+        }
+        else tgbd_download(d, TGB_BUF_MASKS, (u64)idx0 * 64, p_mirror, (u64)n * 64);
         if (p_lut_indices) tgbd_upload(d, TGB_BUF_LUT_IDX, (u64)idx0 * 512, p_lut_indices, (u64)n * 512);
     }
     else
@@ -312,17 +323,32 @@ u32 tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v
         for (u32 rel = 0; rel < n; rel++)
         {
             const u32 idx = p_scene->p_cluster_pointers[first + rel];
-            memcpy(&p_scene->p_voxel_cluster_data[(size_t)idx * TG_CLUSTER_MASK_WORDS], &p_solid_bits[(size_t)rel * TG_CLUSTER_MASK_WORDS], 64);
+            u32* p_mirror = &p_scene->p_voxel_cluster_data[(size_t)idx * TG_CLUSTER_MASK_WORDS];
             tgbd_upload(d, TGB_BUF_C2O, (u64)idx * 4, &object_idx, 4);
-            tgbd_upload(d, TGB_BUF_MASKS, (u64)idx * 64, &p_solid_bits[(size_t)rel * TG_CLUSTER_MASK_WORDS], 64);
+            if (p_solid_bits)
+            {
+                memcpy(p_mirror, &p_solid_bits[(size_t)rel * TG_CLUSTER_MASK_WORDS], 64);
+                tgbd_upload(d, TGB_BUF_MASKS, (u64)idx * 64, &p_solid_bits[(size_t)rel * TG_CLUSTER_MASK_WORDS], 64);
+            }
+            else tgbd_download(d, TGB_BUF_MASKS, (u64)idx * 64, p_mirror, 64);
             if (p_lut_indices) tgbd_upload(d, TGB_BUF_LUT_IDX, (u64)idx * 512, &p_lut_indices[(size_t)rel * 512], 512);
         }
     }
-    if (!p_lut_indices) tgbd_fill_default_lut_idx(d, first, n, p_object->n_cluster_pointers_per_dim.x);
+    if (!p_lut_indices) tgbd_fill_default_lut_idx(d, first, n, dims.x);
     p_raytracer->svo_dirty = 2;
     return tgb200_last_error() ? TG_U32_MAX : object_idx;
 }
 
+u32 tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
+                                         const u32* p_solid_bits, const u8* p_lut_indices)
+{
+    if (!tgb__alive(p_raytracer, "tg_raytracer_create_object_from_data")) return TG_U32_MAX;
+    TGB_REQUIRE(p_solid_bits != NULL, TG_U32_MAX, "create_object_from_data: NULL solid bits");
+    TGB_REQUIRE(lut_idx < p_raytracer->n_color_luts, TG_U32_MAX, "create_object_from_data: LUT index %u out of range (%u LUTs)", lut_idx, p_raytracer->n_color_luts);
+    return tgb__create_object(p_raytracer, center, extent, angle_in_radians, axis, lut_idx, p_solid_bits, p_lut_indices);
+}
+
+/* tgvk_raytracer.c:805-992: the unmodified reference entry point -- procedural terrain, material (8 x + vx) % 256, angle from the index */
 void tg_raytracer_create_object(tg_raytracer* p_raytracer, v3 center, v3u extent)
 {
     if (!tgb__alive(p_raytracer, "tg_raytracer_create_object")) return;
@@ -334,12 +360,7 @@ void tg_raytracer_create_object(tg_raytracer* p_raytracer, v3 center, v3u extent
     f32 angle = tgb_deg2rad((f32)(next_object_idx * 7));
     if (next_object_idx == 0) angle = tgb_deg2rad(15.0f);
     const v3 axis = { 0.0f, 1.0f, 0.0f };
-    const v3u dims = { extent.x / 8, extent.y / 8, extent.z / 8 };
-    const size_t n = (size_t)dims.x * dims.y * dims.z;
-    u32* p_bits = (u32*)malloc(n * 64);
-    tgb200_procedural_solid_bits(next_object_idx, dims, p_bits);
-    tg_raytracer_create_object_from_data(p_raytracer, center, extent, angle, axis, 0, p_bits, NULL);
-    free(p_bits);
+    tgb__create_object(p_raytracer, center, extent, angle, axis, 0, NULL, NULL);
 }
 
 void tg_raytracer_destroy_object(tg_raytracer* p_raytracer, u32 object_idx)

@@ -17,8 +17,8 @@ void tgb200_debug_cluster_ray(const tg_object_data* p_object, const tg_camera_ra
 
 void tgb200_procedural_solid_bits(u32 object_idx, v3u n_cluster_pointers_per_dim, u32* p_out)
 {
-    (void)object_idx; (void)n_cluster_pointers_per_dim; (void)p_out;
-    tgb_set_error("tgb200_procedural_solid_bits: not built yet");
+    if (tgbd_device_count() <= 0) { tgb_set_error("tgb200_procedural_solid_bits: no CUDA device (the fill runs on the GPU; there is no CPU path)"); return; }
+    tgbd_procedural_bits_to_host(tgbd_current_device(), object_idx, n_cluster_pointers_per_dim.x, n_cluster_pointers_per_dim.y, n_cluster_pointers_per_dim.z, p_out);
 }
 
 /* physics/tg_physics.c:394-406 (C twin of collide.inc: TG_MIN / TG_MAX are C ternaries, math/tg_math.h:17-22) */

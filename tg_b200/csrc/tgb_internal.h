@@ -62,6 +62,11 @@ u32   tgbd_n_ranks(struct tgb_device* d);
 /* reference material rule (8*rel_x + vx) % 256 for clusters [first_pointer, first_pointer+n) of an object (tgvk_raytracer.c:947-978) */
 b32   tgbd_fill_default_lut_idx(struct tgb_device* d, u32 first_pointer, u32 n_cluster_pointers, u32 nx);
 
+/* ---- tgb_procedural.cu: the reference's simplex-noise terrain fill (tgvk_raytracer.c:868-943) on the device ---- */
+b32   tgbd_procedural_fill(struct tgb_device* d, u32 object_idx, u32 nx, u32 ny, u32 nz, u32 first_pointer);
+b32   tgbd_procedural_bits_to_host(i32 device, u32 object_idx, u32 nx, u32 ny, u32 nz, u32* p_out);
+i32   tgbd_current_device(void);
+
 /* ---- tgb_visibility.cu ---- */
 b32   tgbd_clear(struct tgb_device* d);                                                              /* clear.comp */
 b32   tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, u32 object_capacity); /* cull + K1 */

@@ -207,3 +207,27 @@ def pack_color(r, g, b):
     """tgvk_raytracer.c:1130-1134."""
     f = np.float32
     return (int(f(r) * f(255.0)) << 24) | (int(f(g) * f(255.0)) << 16) | (int(f(b) * f(255.0)) << 8) | 255
+
+
+def reference_app_objects():
+    """The ten tg_raytracer_create_object(center, extent) calls of the reference's sample scene (tg_application.c:65-87)."""
+    calls = [((0.0, -64.0, 0.0), (128, 32, 128))]
+    for depth_idx in range(3):
+        offset_z = -float(depth_idx) * 128.0
+        x = -256.0
+        calls.append(((x, -16.0, -64.0 + offset_z), (32, 32, 32)))
+        calls.append(((x, 9.0, -96.0 + offset_z), (32, 32, 32)))
+        calls.append(((x - 6.0, 100.0, -70.0 + offset_z), (32, 32, 32)))
+    return calls
+
+
+def reference_app_scene(width, height, solid_bits_of, camera=None):
+    """The reference application's scene (tg_application.c:49-98) as a SceneSpec: camera, ten procedural objects, the 256-entry
+    LUT ramp. `solid_bits_of(object_idx, dims) -> [n_clusters, 16] uint32` supplies the terrain bits (tests pass the oracle's
+    restatement of tgvk_raytracer.c:871-943); materials follow the reference rule (8 x + vx) % 256."""
+    objs = []
+    for idx, (center, extent) in enumerate(reference_app_objects()):
+        dims = (extent[0] // 8, extent[1] // 8, extent[2] // 8)
+        objs.append(ObjectSpec(center=center, extent=extent, angle=reference_object_angle(idx), bits=solid_bits_of(idx, dims), lut_indices=None))
+    cam = camera or CameraSpec(position=(65.1368790, -30.7384720, 73.0285263), pitch=-0.173136666, yaw=0.710419059, roll=0.0, aspect=width / height)
+    return SceneSpec(name="reference_app", width=width, height=height, camera=cam, objects=objs, lut=reference_lut_ramp(256))
