@@ -127,8 +127,9 @@ TG_EXPORT void tgb200_set_frame_sink(tg_raytracer* p_raytracer, f32* p_host, u32
 TG_EXPORT u64  tgb200_frame_ticket(tg_raytracer* p_raytracer);
 TG_EXPORT void tgb200_wait_frame(tg_raytracer* p_raytracer, u64 ticket);
 
-/* Secondary-ray kernel: 0 = automatic (stackless over the flattened tree whenever the SVO box corners are multiples of 32, the
- * stack machine of svo_functions.inc otherwise), 1 = always the stack machine. Both give the same radiance (tests). */
+/* Secondary-ray kernel: 0 = automatic (stackless over the flattened tree with the rays of a CTA regrouped by phase, whenever
+ * the SVO box corners are multiples of 32; the stack machine of svo_functions.inc otherwise), 1 = always the stack machine,
+ * 2 = the stackless kernel without regrouping (one ray per lane). All give the same radiance (tests). */
 TG_EXPORT void tgb200_set_gi_traversal(tg_raytracer* p_raytracer, u32 kind);
 
 /* Stages of render(), individually callable (bench / tests). All asynchronous on the raytracer's stream. */

@@ -263,3 +263,36 @@ def test_oracle_simplex_noise_equals_reference_made_fixture(oracle):
     L = oracle.lib()
     got = np.array([L.tgo_simplex_noise(*map(np.float32, p)) for p in g["points"]], dtype=np.float32)
     assert np.array_equal(got.view(np.uint32), g["values"].view(np.uint32))
+
+
+def test_boundary_tg_svo_traverse_equals_the_reference(oracle, ref):
+    """The product's own host entry point tg_svo_traverse (include/tg_raytracer.h, tg_sparse_voxel_octree.h:53) on a
+    reference-built SVO against the reference's tg_svo_traverse: same hit flag, distance bits, node and voxel index."""
+    import tg_b200
+    P = tg_b200.lib()
+    s = scenes.small_grid(grid=4, dims=(3, 5, 2))
+    view = oracle.SceneView.from_scene(s, with_lut=False)
+    svo = T.tg_svo()
+    scene = oracle.ref_scene(view)
+    ref.tg_svo_create(T.v3(-512, -512, -512), T.v3(512, 512, 512), C.byref(scene), C.byref(svo))
+    rng = np.random.default_rng(21)
+    n_hits = 0
+    try:
+        for trial in range(3000):
+            o = rng.uniform(-100, 100, 3).astype(np.float32)
+            d = (rng.uniform(-40, 40, 3).astype(np.float32) - o)
+            if trial % 11 == 0:
+                d[int(rng.integers(0, 3))] = 0.0
+            if not d.any():
+                d[2] = 1.0
+            d = (d / np.linalg.norm(d)).astype(np.float32)
+            d0, n0, v0, d1, n1, v1 = T.f32(), T.u32(), T.u32(), T.f32(), T.u32(), T.u32()
+            r0 = P.tg_svo_traverse(C.byref(svo), T.v3(*o), T.v3(*d), C.byref(d0), C.byref(n0), C.byref(v0))
+            r1 = ref.tg_svo_traverse(C.byref(svo), T.v3(*o), T.v3(*d), C.byref(d1), C.byref(n1), C.byref(v1))
+            assert bool(r0) == bool(r1), (trial, o, d)
+            if r1:
+                n_hits += 1
+                assert np.float32(d0.value).tobytes() == np.float32(d1.value).tobytes() and n0.value == n1.value and v0.value == v1.value, (trial, o, d)
+        assert n_hits > 200
+    finally:
+        ref.tg_svo_destroy(C.byref(svo))
