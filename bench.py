@@ -99,10 +99,34 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_scene(rank, n_ranks):
-    """Rank's shard: 1,024 objects (grid 32 x 32) out of a 32 x 32N lattice; the global object index decides seed and angle."""
+WORKLOADS = {
+    "c2": "BASELINE configs[1]+[2] per GPU: 1,024 objects (2^21 clusters, 1.07e9 voxels), 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
+    "c5": "BASELINE configs[4] per GPU: 12,288 objects (25,165,824 clusters, 1.29e10 voxels; 8 GPUs = 1.03e11 voxels) generated on the device, "
+          "3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
+}
+
+
+def build_scene(rank, n_ranks, workload="c2", host_bits=True):
+    """Rank's shard. c2: 1,024 objects (grid 32 x 32) out of a 32 x 32N lattice. c5: 12,288 objects out of a 384 x 32N lattice, masks
+    generated on the device. The global object index decides seed and angle."""
     from tg_b200 import scenes
-    return scenes.grid_scene(f"config2_x{n_ranks}", 32, 32 * n_ranks, WIDTH, HEIGHT, k=3, first_object=rank * 1024, n_objects=1024)
+    if workload == "c5":
+        return scenes.config5_shard(rank, n_ranks, WIDTH, HEIGHT)
+    return scenes.grid_scene(f"config2_x{n_ranks}", 32, 32 * n_ranks, WIDTH, HEIGHT, k=3, first_object=rank * 1024, n_objects=1024, with_bits=host_bits)
+
+
+def cpu_scene(workload):
+    """The N=1 scene for the CPU arm. c5: only the objects that can write a pixel (within the far plane of the camera; the rest
+    fail depth <= 1, visibility.frag:194) get host-side masks -- 1.6 GB of masks for the others would only be skipped."""
+    from tg_b200 import scenes
+    s = build_scene(0, 1, workload)
+    if workload == "c5":
+        cam, far = s.camera.position, s.camera.far
+        near = [o for o in s.objects if ((o.center[0] - cam[0]) ** 2 + (o.center[2] - cam[2]) ** 2) ** 0.5 < far + 160.0]
+        for o in near:
+            o.bits = scenes.random_solid_bits(o.seed, o.n_clusters, o.k)
+        s.objects = near
+    return s
 
 
 class CpuArm:
@@ -145,7 +169,7 @@ def run_reference(args, rank):
     """The CPU arm (rank 0 only; the other ranks exit without work)."""
     if rank != 0:
         return
-    arm = CpuArm(build_scene(0, 1))
+    arm = CpuArm(cpu_scene(args.workload))
     times, n_rays = [], 0
     for i in range(args.warmup + args.steps):
         secs, n_rays = arm.sample()
@@ -157,7 +181,7 @@ def run_reference(args, rank):
     value = n_rays * len(times) / total / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]+[2]: 1,024 objects (2^21 clusters, 1.07e9 voxels), 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)", "sample": text},
+            "config": {"workload": WORKLOADS[args.workload], "sample": text},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": arm.cores, "kind": "port", "sample": text},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -170,6 +194,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tg_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the headline configuration (default); c5 = one 12,288-object shard of the 1e11-voxel world per GPU")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -192,7 +217,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    scene = build_scene(rank, world)
+    scene = build_scene(rank, world, args.workload, host_bits=False)  # masks generated on the device (same seeds as the host definition)
     rt = from_scene(scene, device=local_rank)
     n_clusters, n_objects = scene.n_clusters, len(scene.objects)
     if world > 1:
@@ -333,7 +358,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            arm = CpuArm(build_scene(0, 1))
+            arm = CpuArm(cpu_scene(args.workload))
             samples = [arm.sample() for _ in range(12)]  # ~10-30 s of CPU work on the box host cores
             secs = sum(t for t, _ in samples)
             cpu = {"value": sum(n for _, n in samples) / secs / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
@@ -341,7 +366,7 @@ def main():
             arm.close()
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]+[2] per GPU: 1,024 objects (2^21 clusters, 1.07e9 voxels), 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)"
+                "config": {"workload": WORKLOADS[args.workload]
                                        + (f"; world = {world} such shards: ncclAllReduce(u64,min) merge, material reduce-scatter, GI split by screen tile" if world > 1 else ""),
                            "rays_per_frame": rays_per_frame, "primary_rays": world * WIDTH * HEIGHT, "gi_rays": n_hit, "svo_build_ms": svo_build_ms, "svo_bytes": svo_bytes,
                            "visible_objects": last["n_visible_objects"],

@@ -106,6 +106,17 @@ TG_EXPORT void        tg_raytracer_set_resolution(tg_raytracer* p_raytracer, u32
  */
 TG_EXPORT u32  tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
                                                     const u32* p_solid_bits, const u8* p_lut_indices);
+/*
+ * Object filled ON THE DEVICE with seeded random solid bits (BASELINE.json's "random solid bits" configs; a 10^11-voxel world
+ * cannot be generated on the host and uploaded): cluster `rel` of the object owns the stream
+ * state0 = hash_u32(object_seed ^ hash_u32(rel)) | 1 (math/tg_math.c:809-820), every mask word is the AND of `k` successive
+ * xorshift32 draws (math/tg_math.c:328-338), i.e. density 2^-k; materials follow the reference's rule (8*rel_x + vx) % 256.
+ * The CPU mirror scene.p_voxel_cluster_data is filled like for every other object. tgb200_synthetic_solid_bits is the host
+ * twin of the generator (usable without a GPU). Returns the object index, TG_U32_MAX on error.
+ */
+TG_EXPORT u32  tg_raytracer_create_object_synthetic(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
+                                                    u32 object_seed, u32 k);
+TG_EXPORT void tgb200_synthetic_solid_bits(u32 object_seed, u32 k, u32 n_clusters, u32* p_out /* 16 u32 per cluster */);
 /* Moves an object (the reference has no setter); marks the SVO for an incremental update. */
 TG_EXPORT void tg_raytracer_set_object_transform(tg_raytracer* p_raytracer, u32 object_idx, v3 translation, f32 angle_in_radians, v3 axis);
 /* color_lut_set for LUT `lut_idx` (lut[lut_idx*256 + index]); lut_idx 0 == the reference call. */
@@ -127,9 +138,8 @@ TG_EXPORT void tgb200_set_frame_sink(tg_raytracer* p_raytracer, f32* p_host, u32
 TG_EXPORT u64  tgb200_frame_ticket(tg_raytracer* p_raytracer);
 TG_EXPORT void tgb200_wait_frame(tg_raytracer* p_raytracer, u64 ticket);
 
-/* Secondary-ray kernel: 0 = automatic (stackless over the flattened tree with the rays of a CTA regrouped by phase, whenever
- * the SVO box corners are multiples of 32; the stack machine of svo_functions.inc otherwise), 1 = always the stack machine,
- * 2 = the stackless kernel without regrouping (one ray per lane). All give the same radiance (tests). */
+/* Secondary-ray kernel: 0 = automatic (stackless over the flattened tree whenever the SVO box corners are multiples of 32;
+ * the stack machine of svo_functions.inc otherwise), 1 = always the stack machine. Both give the same radiance (tests). */
 TG_EXPORT void tgb200_set_gi_traversal(tg_raytracer* p_raytracer, u32 kind);
 
 /* Stages of render(), individually callable (bench / tests). All asynchronous on the raytracer's stream. */

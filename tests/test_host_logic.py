@@ -207,3 +207,16 @@ def test_tg_svo_traverse_host_query_matches_the_oracle_c_variant():
     assert 100 < n_hit < 1900
     O.svo_destroy(svo)
     assert L.tgb200_last_error() is None
+
+
+def test_synthetic_generator_host_twin_equals_scene_definition():
+    """tgb200_synthetic_solid_bits (C, the host twin of k_synthetic_fill) == scenes.random_solid_bits (numpy): the seeded random
+    fill of BASELINE's configs is one definition wherever it is evaluated."""
+    import ctypes as C
+    import tg_b200
+    from tg_b200 import ctypes_defs as T, scenes
+    L = tg_b200.lib()
+    for seed, n, k in ((1, 64, 3), (7, 257, 1), (12288, 2048, 3), (0xFFFFFFFF, 5, 5)):
+        out = np.empty((n, 16), dtype=np.uint32)
+        L.tgb200_synthetic_solid_bits(seed, k, n, T.ptr(out, T.u32))
+        assert np.array_equal(out, scenes.random_solid_bits(seed, n, k)), (seed, n, k)

@@ -10,7 +10,7 @@ import pytest
 
 from tg_b200 import ctypes_defs as T
 from tg_b200 import scenes
-from tg_b200.raytracer import Raytracer
+from tg_b200.raytracer import Raytracer, from_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -73,3 +73,30 @@ def test_reference_application_scene_through_the_reference_calls(gpu, oracle):
     assert hit == ((word >> 40) / 16777215.0 < 1.0)
     if hit:
         assert cluster == (word >> 9) & 0x7FFFFFFF and voxel == word & 511 and depth == np.float32(np.float32(word >> 40) / np.float32(16777215.0))
+
+
+def test_synthetic_objects_generated_on_device_equal_uploaded_ones(gpu, oracle):
+    """tg_raytracer_create_object_synthetic (k_synthetic_fill, BASELINE configs[4]'s device-side generation): the CPU mirror the
+    library reads back holds exactly scenes.random_solid_bits, and the frame of a device-generated scene equals both the frame of
+    the same scene uploaded from host arrays and the oracle's."""
+    import ctypes as C
+    s_host = scenes.small_grid(grid=4, dims=(5, 3, 4))
+    s_dev = scenes.grid_scene("small_dev", 4, 4, s_host.width, s_host.height, k=3, pitch_units=8.0 * 5 * 1.5, dims=(5, 3, 4), with_bits=False)
+    s_dev.camera = s_host.camera
+    frames = []
+    for s in (s_host, s_dev):
+        rt = from_scene(s)
+        try:
+            n = s.n_clusters
+            mirror = np.ctypeslib.as_array(rt.scene.p_voxel_cluster_data, shape=(n * 16,)).reshape(n, 16).copy()
+            want = np.concatenate([scenes.random_solid_bits(o.seed, o.n_clusters, o.k) for o in s.objects])
+            assert np.array_equal(mirror, want)
+            rt.set_gi(True, 1)
+            rt.clear(); rt.render(); rt.synchronize()
+            frames.append((rt.read_visibility(), rt.read_radiance()))
+        finally:
+            rt.destroy()
+    assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1])
+    rays = oracle.camera_rays(oracle.camera_from_spec(s_host.camera))
+    want_vis, _ = oracle.visibility(oracle.SceneView.from_scene(s_host, with_lut=True), rays, s_host.width, s_host.height, oracle.VIS_SCREEN_RECT)
+    assert np.array_equal(frames[1][0], want_vis)

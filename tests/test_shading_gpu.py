@@ -156,9 +156,8 @@ def test_gi_without_svo_is_a_recorded_error(gpu):
 
 def test_config3_full_size_stackless_equals_stack_machine_and_oracle_rows(gpu, oracle):
     """BASELINE configs[2]: 1 secondary ray per hit pixel at 3840x2160 on the 1,024-object scene (~5 M rays through the SVO).
-    Three independent kernels must agree on every pixel -- the pooled stackless kernel (rays regrouped by phase in shared
-    memory), the per-warp stackless kernel, and the stack machine transcribed from svo_functions.inc -- and equal the oracle
-    on every 40th scanline."""
+    Two independent kernels must agree on every pixel -- the stackless kernel over the flattened tree and the stack machine
+    transcribed from svo_functions.inc -- and equal the oracle on every 40th scanline."""
     s = scenes.config2()
     rt = from_scene(s)
     try:
@@ -167,12 +166,12 @@ def test_config3_full_size_stackless_equals_stack_machine_and_oracle_rows(gpu, o
         flat = rt.read_radiance()
         t_flat = rt.timings()
         vis = rt.read_visibility()
-        for kind, what in ((1, "stack machine"), (2, "per-warp stackless kernel")):
+        for kind, what in ((1, "stack machine"),):
             rt.set_gi_traversal(kind)
             rt.render_shading(); rt.synchronize()
             other = rt.read_radiance()
             t_other = rt.timings()
-            assert np.array_equal(flat, other), f"{int((flat != other).any(axis=-1).sum())} pixels differ between the pooled stackless kernel and the {what}"
+            assert np.array_equal(flat, other), f"{int((flat != other).any(axis=-1).sum())} pixels differ between the stackless kernel and the {what}"
             assert t_flat["n_gi_rays"] == t_other["n_gi_rays"] > 1_000_000
             assert t_flat["n_gi_dda_steps"] == t_other["n_gi_dda_steps"] and t_flat["n_gi_advances"] == t_other["n_gi_advances"]
     finally:

@@ -194,3 +194,56 @@ def test_config2_full_size_scanline_subset_and_properties(gpu, oracle):
         assert 0 < t["n_visible_objects"] < 400
     finally:
         rt.destroy()
+
+
+def test_config5_one_shard_full_size_scanline_subset(gpu, oracle):
+    """BASELINE configs[4], one GPU's share: 12,288 objects = 25,165,824 clusters = 1.29e10 voxels generated on the device
+    (tg_raytracer_create_object_synthetic), 3840x2160, visibility + SVO + GI. The oracle evaluates every 60th scanline over the
+    objects that can write a pixel (those within the far plane; the others fail depth <= 1, visibility.frag:194) with host-made
+    masks of the same seeds; its cluster pointers are mapped into the full scene's (every object has 2,048 clusters and the
+    subset keeps the object order, so ties resolve identically)."""
+    from tg_b200.raytracer import from_scene
+    s = scenes.config5_shard(0, 1)
+    assert len(s.objects) == 12288 and s.n_clusters == 25165824
+    rt = from_scene(s)
+    try:
+        rt.set_gi(True, 1)
+        rt.clear(); rt.render(); rt.synchronize()
+        got = rt.read_visibility()
+        rad = rt.read_radiance()
+        t = rt.timings()
+        hit = got != CLEAR
+        assert 0.3 < hit.mean() < 0.9 and 0 < t["n_visible_objects"] < 400
+        ptr = ((got[hit] >> np.uint64(9)) & np.uint64(0x7FFFFFFF)).astype(np.int64)
+        assert ptr.max() < s.n_clusters
+        # the voxel every word names is solid in the CPU mirror the library keeps (scene.p_voxel_cluster_data)
+        vox = (got[hit] & np.uint64(511)).astype(np.int64)
+        mirror = np.ctypeslib.as_array(rt.scene.p_voxel_cluster_data, shape=(s.n_clusters * 16,))
+        assert ((mirror[ptr * 16 + vox // 32] >> (vox % 32).astype(np.uint32)) & 1).all()
+    finally:
+        rt.destroy()
+    cam, far = s.camera.position, s.camera.far
+    keep = [i for i, o in enumerate(s.objects) if ((o.center[0] - cam[0]) ** 2 + (o.center[2] - cam[2]) ** 2) ** 0.5 < far + 160.0]
+    assert 20 < len(keep) < 400
+    sub = scenes.SceneSpec(name="c5_near", width=s.width, height=s.height, camera=s.camera, objects=[s.objects[i] for i in keep])
+    for o in sub.objects:
+        o.bits = scenes.random_solid_bits(o.seed, o.n_clusters, o.k)
+    rows = np.arange(11, s.height, 60)
+    want = oracle_visibility(oracle, sub, None, 11, None, 60)[rows]
+    w_hit = want != CLEAR
+    sub_ptr = (want >> np.uint64(9)) & np.uint64(0x7FFFFFFF)
+    full_ptr = np.asarray(keep, dtype=np.uint64)[(sub_ptr // np.uint64(2048)).astype(np.int64) % len(keep)] * np.uint64(2048) + sub_ptr % np.uint64(2048)
+    remapped = np.where(w_hit, (want & ~(np.uint64(0x7FFFFFFF) << np.uint64(9))) | (full_ptr << np.uint64(9)), want)
+    assert np.array_equal(got[rows], remapped), describe_mismatch(got[rows], remapped)
+    # GI + shading of those rows: the oracle shades its own (subset-pointer) buffer with its own SVO of the +-512 box
+    rays = oracle.camera_rays(oracle.camera_from_spec(s.camera))
+    view = oracle.SceneView.from_scene(sub, with_lut=True)
+    in_box = [o for o in sub.objects if max(abs(o.center[0]), abs(o.center[2])) < 512 + 160]
+    svo = oracle.svo_create(oracle.SceneView.from_scene(scenes.SceneSpec(name="c5_box", width=s.width, height=s.height, camera=s.camera, objects=in_box), with_lut=False),
+                            capacities=(1 << 25, 1 << 15, 1 << 16))
+    want_vis = np.full((s.height, s.width), CLEAR, dtype=np.uint64)
+    want_vis[rows] = want
+    want_rad = np.zeros((s.height, s.width, 4), dtype=np.float32)
+    oracle.shade(view, rays, s.width, s.height, want_vis, svo, gi=True, frame_seed=1, y0=11, y1=s.height, ystep=60, out=want_rad)
+    oracle.svo_destroy(svo)
+    assert np.allclose(rad[rows], want_rad[rows], rtol=1e-3, atol=1e-6), f"{int((~np.isclose(rad[rows], want_rad[rows], rtol=1e-3, atol=1e-6)).any(axis=-1).sum())} pixels beyond 1e-3"

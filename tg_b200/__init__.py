@@ -40,6 +40,8 @@ SYMBOLS = {
     "tgb200_set_default_resolution": (None, [T.u32, T.u32]),
     "tg_raytracer_set_resolution": (None, [_RT, T.u32, T.u32]),
     "tg_raytracer_create_object_from_data": (T.u32, [_RT, T.v3, T.v3u, T.f32, T.v3, T.u32, _P(T.u32), _P(T.u8)]),
+    "tg_raytracer_create_object_synthetic": (T.u32, [_RT, T.v3, T.v3u, T.f32, T.v3, T.u32, T.u32, T.u32]),
+    "tgb200_synthetic_solid_bits": (None, [T.u32, T.u32, T.u32, _P(T.u32)]),
     "tg_raytracer_set_object_transform": (None, [_RT, T.u32, T.v3, T.f32, T.v3]),
     "tg_raytracer_color_lut_set_ex": (None, [_RT, T.u32, T.u8, T.f32, T.f32, T.f32]),
     "tg_raytracer_set_gi": (None, [_RT, T.b32, T.u32]),

@@ -288,7 +288,7 @@ static b32 tgb__contiguous_run(const tg_scene* p_scene, const tg_voxel_object* p
  * p_voxel_cluster_data, which the reference keeps too (:934).
  */
 static u32 tgb__create_object(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
-                              const u32* p_solid_bits, const u8* p_lut_indices)
+                              const u32* p_solid_bits, const u8* p_lut_indices, u32 synthetic_k, u32 synthetic_seed)
 {
     tg_scene* p_scene = &p_raytracer->scene;
     const u32 object_idx = tgb200_scene_alloc_object(p_scene, center, extent, angle_in_radians, axis);
@@ -303,7 +303,12 @@ static u32 tgb__create_object(tg_raytracer* p_raytracer, v3 center, v3u extent, 
 
     tgb__upload_object_record(p_raytracer, object_idx);
     tgbd_upload(d, TGB_BUF_CLUSTER_POINTERS, (u64)first * 4, &p_scene->p_cluster_pointers[first], (u64)n * 4);
-    if (!p_solid_bits) tgbd_procedural_fill(d, object_idx, dims.x, dims.y, dims.z, first); /* after the pointer upload: same stream */
+    /* generated on the device, after the pointer upload (same stream): seeded random bits, or the reference's terrain */
+    if (!p_solid_bits)
+    {
+        if (synthetic_k) tgbd_synthetic_fill(d, synthetic_seed, synthetic_k, n, first);
+        else             tgbd_procedural_fill(d, object_idx, dims.x, dims.y, dims.z, first);
+    }
 
     if (tgb__contiguous_run(p_scene, p_object, n))
     {
@@ -345,7 +350,30 @@ u32 tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v
     if (!tgb__alive(p_raytracer, "tg_raytracer_create_object_from_data")) return TG_U32_MAX;
     TGB_REQUIRE(p_solid_bits != NULL, TG_U32_MAX, "create_object_from_data: NULL solid bits");
     TGB_REQUIRE(lut_idx < p_raytracer->n_color_luts, TG_U32_MAX, "create_object_from_data: LUT index %u out of range (%u LUTs)", lut_idx, p_raytracer->n_color_luts);
-    return tgb__create_object(p_raytracer, center, extent, angle_in_radians, axis, lut_idx, p_solid_bits, p_lut_indices);
+    return tgb__create_object(p_raytracer, center, extent, angle_in_radians, axis, lut_idx, p_solid_bits, p_lut_indices, 0, 0);
+}
+
+/* math/tg_math.c:328-338,809-820: the per-cluster streams of the seeded random fill, on the host (the device twin is k_synthetic_fill) */
+void tgb200_synthetic_solid_bits(u32 object_seed, u32 k, u32 n_clusters, u32* p_out)
+{
+    for (u32 rel = 0; rel < n_clusters; rel++)
+    {
+        u32 state = tgb_hash_u32(object_seed ^ tgb_hash_u32(rel)) | 1u;
+        for (u32 w = 0; w < TG_CLUSTER_MASK_WORDS; w++)
+        {
+            u32 word = 0xFFFFFFFFu;
+            for (u32 j = 0; j < k; j++) word &= tgb_xorshift32(&state);
+            p_out[(size_t)rel * TG_CLUSTER_MASK_WORDS + w] = word;
+        }
+    }
+}
+
+u32 tg_raytracer_create_object_synthetic(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx, u32 object_seed, u32 k)
+{
+    if (!tgb__alive(p_raytracer, "tg_raytracer_create_object_synthetic")) return TG_U32_MAX;
+    TGB_REQUIRE(k >= 1 && k <= 32, TG_U32_MAX, "create_object_synthetic: k = %u draws per word out of range [1, 32]", k);
+    TGB_REQUIRE(lut_idx < p_raytracer->n_color_luts, TG_U32_MAX, "create_object_synthetic: LUT index %u out of range (%u LUTs)", lut_idx, p_raytracer->n_color_luts);
+    return tgb__create_object(p_raytracer, center, extent, angle_in_radians, axis, lut_idx, NULL, NULL, k, object_seed);
 }
 
 /* tgvk_raytracer.c:805-992: the unmodified reference entry point -- procedural terrain, material (8 x + vx) % 256, angle from the index */
@@ -360,7 +388,7 @@ void tg_raytracer_create_object(tg_raytracer* p_raytracer, v3 center, v3u extent
     f32 angle = tgb_deg2rad((f32)(next_object_idx * 7));
     if (next_object_idx == 0) angle = tgb_deg2rad(15.0f);
     const v3 axis = { 0.0f, 1.0f, 0.0f };
-    tgb__create_object(p_raytracer, center, extent, angle, axis, 0, NULL, NULL);
+    tgb__create_object(p_raytracer, center, extent, angle, axis, 0, NULL, NULL, 0, 0);
 }
 
 void tg_raytracer_destroy_object(tg_raytracer* p_raytracer, u32 object_idx)

@@ -64,6 +64,8 @@ b32   tgbd_fill_default_lut_idx(struct tgb_device* d, u32 first_pointer, u32 n_c
 
 /* ---- tgb_procedural.cu: the reference's simplex-noise terrain fill (tgvk_raytracer.c:868-943) on the device ---- */
 b32   tgbd_procedural_fill(struct tgb_device* d, u32 object_idx, u32 nx, u32 ny, u32 nz, u32 first_pointer);
+/* seeded random bits (density 2^-k) of an object's clusters [first_pointer, first_pointer + n) into the resident mask array */
+b32   tgbd_synthetic_fill(struct tgb_device* d, u32 object_seed, u32 k, u32 n_clusters, u32 first_pointer);
 b32   tgbd_procedural_bits_to_host(i32 device, u32 object_idx, u32 nx, u32 ny, u32 nz, u32* p_out);
 i32   tgbd_current_device(void);
 

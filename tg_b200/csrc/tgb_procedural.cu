@@ -175,3 +175,40 @@ extern "C" b32 tgbd_procedural_bits_to_host(i32 device, u32 object_idx, u32 nx, 
     if (e != cudaSuccess) { tgb_set_error("procedural fill: %s", cudaGetErrorString(e)); return TG_FALSE; }
     return TG_TRUE;
 }
+
+/* ---- seeded random fill (BASELINE.json's "random solid bits" configs; SURVEY.md section 8d synthetic inputs) ---------------- */
+/*
+ * One thread = one cluster: state0 = hash_u32(object_seed ^ hash_u32(rel_cluster)) | 1 (math/tg_math.c:809-820 = util.inc:47-56),
+ * each of the 16 mask words is the AND of `k` successive xorshift32 draws (math/tg_math.c:328-338): density 2^-k. The same
+ * definition as tg_b200/scenes.py random_solid_bits and tgb200_synthetic_solid_bits (host), which tests compare bit for bit.
+ * Four 16-byte stores per thread; a warp writes 2 KiB contiguously when the object's cluster indices are one run.
+ */
+__global__ void __launch_bounds__(128) k_synthetic_fill(u32 object_seed, u32 k, u32 n_clusters, const u32* __restrict__ p_cluster_pointers, u32 first_pointer, u32* __restrict__ p_masks)
+{
+    const u32 rel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rel >= n_clusters) return;
+    u32 state = tgb_hash_u32(object_seed ^ tgb_hash_u32(rel)) | 1u;
+    uint4* p_dst = reinterpret_cast<uint4*>(p_masks + (u64)p_cluster_pointers[first_pointer + rel] * TG_CLUSTER_MASK_WORDS);
+#pragma unroll
+    for (u32 q = 0; q < 4; q++)
+    {
+        u32 w[4];
+#pragma unroll
+        for (u32 i = 0; i < 4; i++)
+        {
+            u32 word = 0xFFFFFFFFu;
+            for (u32 j = 0; j < k; j++) word &= tgb_xorshift32(&state);
+            w[i] = word;
+        }
+        p_dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+extern "C" b32 tgbd_synthetic_fill(struct tgb_device* d, u32 object_seed, u32 k, u32 n_clusters, u32 first_pointer)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    if (n_clusters == 0) return TG_TRUE;
+    k_synthetic_fill<<<(n_clusters + 127) / 128, 128, 0, d->stream>>>(object_seed, k, n_clusters, d->d_cluster_pointers, first_pointer, d->d_masks);
+    TGB_LAUNCH_CHECK(d);
+    return TG_TRUE;
+}

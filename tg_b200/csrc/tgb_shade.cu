@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
  * (:279-294) -- and the leaf DDA (:111-257) are the shader's operations, so hit / miss decisions are the oracle's.
  * The box corners must be multiples of 32 (the chain mid = min + extent / 2 is then exact and equals min + 32 * cell);
  * other boxes, and trees k_svo_flatten could not tabulate, take the stack kernel above.
- * Two kinds of lanes remain: TREE (advance + look-up) and DDA (up to TGB_GI_DDA_STEPS voxel steps); each warp iteration
+ * Two kinds of lanes remain: TREE (advance + look-up) and DDA (up to TGB_FL_DDA_STEPS voxel steps); each warp iteration
  * runs the phase the majority waits for.
  */
 /*
@@ -620,7 +620,8 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
  * per iteration, so they wait until a quarter of the warp needs service and are then handled together.
  */
 enum { TGB_FL_IDLE = 0, TGB_FL_TREE = 1, TGB_FL_DDA = 2, TGB_FL_HIT = 3, TGB_FL_MISS = 4 };
-#define TGB_FL_SERVICE_LANES 8u
+#define TGB_FL_SERVICE_LANES 12u /* measured best with 16 DDA steps per phase (scratch sweeps: 1.66 -> 1.55 ms GI + shading at 4K) */
+#define TGB_FL_DDA_STEPS 16
 
 /*
  * Index along one axis of the 32^3 cell the shader's octant rule (:63-80: upper half iff mid < p || (p == mid && d > 0))
@@ -867,315 +868,6 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
     }
 }
 
-/* ---- K3b, pooled: the stackless traversal with the rays of a CTA regrouped by phase every round ------------------- */
-/*
- * k_gi_trace_flat keeps a ray in the lane that fetched it, so a warp executes a phase with the lanes that happen to be
- * in it (measured: 14 of 32, profiles/r01g). Here the rays live in SHARED MEMORY -- a pool of TGB_POOL_SLOTS rays per
- * CTA, 16 words each -- filed by phase in three lists (DDA, TREE, service): whoever finishes a phase files the ray under the
- * phase it needs next, the lists swap at the one barrier that ends a round, and the
- * warps take 32 consecutive entries of one list at a time: every lane of a warp runs the same phase on a different
- * ray, the state is loaded from / stored to the pool around it. A round moves every unfinished ray of the CTA one
- * phase forward (one advance + look-up, or up to DDA_STEPS voxel steps, or its service). The arithmetic of the phases
- * is k_gi_trace_flat's (and so the shader's); only where a ray's state lives and which lane runs it differ.
- *
- * Pool word layout [field][slot]:  direction (3) | position (3) | 1 / |d| (3) | t_max (3) | CHILD: cell of the terminal
- * box (3 x 5 bits) + level (3 bits) | META: kind (3 bits), advance / set-up / border pending, exotic, iterations (13 bits) |
- * BLOCK: leaf data pointer (15 bits) + voxel x, y, z (3 x 5 bits) | SLOT: index in the global ray queue.
- */
-#define TGB_POOL_SLOTS_PER_THREAD 2
-enum { TGB_PF_DX = 0, TGB_PF_DY, TGB_PF_DZ, TGB_PF_PX, TGB_PF_PY, TGB_PF_PZ, TGB_PF_RX, TGB_PF_RY, TGB_PF_RZ, TGB_PF_TX, TGB_PF_TY, TGB_PF_TZ,
-       TGB_PF_CHILD, TGB_PF_META, TGB_PF_BLOCK, TGB_PF_SLOT, TGB_PF_COUNT };
-enum { TGB_PL_DDA = 0, TGB_PL_TREE = 1, TGB_PL_SERVICE = 2, TGB_PL_COUNT = 3 };
-#define TGB_PM_KIND_MASK   7u
-#define TGB_PM_ADVANCE     8u
-#define TGB_PM_SETUP       16u
-#define TGB_PM_BORDER      32u
-#define TGB_PM_EXOTIC      64u
-#define TGB_PM_ITER_SHIFT  7u
-
-/* files slot `s` under the phase its ray needs next round (warp-aggregated: three ballots, one atomic per list issued by lanes 0..2 together) */
-template <int SLOTS>
-__device__ __forceinline__ void tgb_pool_file(bool valid, u32 kind, u32 s, u16 (*p_lists)[SLOTS], u32* p_n, u32 lane)
-{
-    const u32 list = !valid ? (u32)TGB_PL_COUNT : (kind == TGB_FL_DDA ? (u32)TGB_PL_DDA : (kind == TGB_FL_TREE ? (u32)TGB_PL_TREE : (kind == TGB_FL_IDLE ? (u32)TGB_PL_COUNT : (u32)TGB_PL_SERVICE)));
-    const u32 m0 = __ballot_sync(0xFFFFFFFFu, list == 0u), m1 = __ballot_sync(0xFFFFFFFFu, list == 1u), m2 = __ballot_sync(0xFFFFFFFFu, list == 2u);
-    const u32 mine = lane == 0u ? m0 : (lane == 1u ? m1 : m2);
-    u32 base = 0;
-    if (lane < 3u && mine) base = atomicAdd(&p_n[lane], (u32)__popc(mine));
-    const u32 b0 = __shfl_sync(0xFFFFFFFFu, base, 0), b1 = __shfl_sync(0xFFFFFFFFu, base, 1), b2 = __shfl_sync(0xFFFFFFFFu, base, 2);
-    const u32 below = (1u << lane) - 1u;
-    if (list == 0u)      p_lists[0][b0 + (u32)__popc(m0 & below)] = (u16)s;
-    else if (list == 1u) p_lists[1][b1 + (u32)__popc(m1 & below)] = (u16)s;
-    else if (list == 2u) p_lists[2][b2 + (u32)__popc(m2 & below)] = (u16)s;
-}
-
-template <int DDA_STEPS, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_gi_trace_pool(const tgb_svo_view svo, const u32* __restrict__ p_grid, f32 far_plane,
-                                                                    const float4* __restrict__ p_q0, const float4* __restrict__ p_q1, const float4* __restrict__ p_q2,
-                                                                    u32* __restrict__ p_q_count, float4* __restrict__ p_out)
-{
-    constexpr int SLOTS = THREADS * TGB_POOL_SLOTS_PER_THREAD;
-    constexpr u32 WARPS = THREADS / 32;
-    __shared__ u32 s_state[TGB_PF_COUNT][SLOTS];
-    __shared__ u16 s_list[2][TGB_PL_COUNT][SLOTS]; /* this round's lists and the ones being filled for the next round */
-    __shared__ u32 s_n[3][4];                      /* list lengths, rotating: read | filled | cleared */
-
-    if (p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
-
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 n_rays = p_q_count[0];
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
-    const v3 extent = tgb_sub(svo.bmax, svo.bmin);
-    const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin); /* svo_functions.inc:3-8 */
-    const v3 box_mid = tgb_scale(tgb_add(svo.bmin, svo.bmax), 0.5f);
-    const i32 min_cell_x = (i32)(svo.bmin.x * 0.03125f), min_cell_y = (i32)(svo.bmin.y * 0.03125f), min_cell_z = (i32)(svo.bmin.z * 0.03125f);
-
-    /* round 0: every slot is idle and waits for a ray in the service list */
-    for (u32 i = tid; i < (u32)SLOTS; i += THREADS) { s_state[TGB_PF_META][i] = TGB_FL_IDLE; s_list[0][TGB_PL_SERVICE][i] = (u16)i; }
-    if (tid < 12u) (&s_n[0][0])[tid] = 0;
-    __syncthreads();
-    if (tid == 0) s_n[0][TGB_PL_SERVICE] = (u32)SLOTS;
-    __syncthreads();
-
-    u32 n_visits = 0, n_steps = 0, n_advances = 0;
-    for (u32 round = 0;; round++)
-    {
-        const u32 cur = round & 1u, nxt = cur ^ 1u;
-        const u32* p_n = s_n[round % 3u];
-        u32* p_n_next = s_n[(round + 1u) % 3u];
-        const u32 n_dda = p_n[TGB_PL_DDA], n_tree = p_n[TGB_PL_TREE], n_service = p_n[TGB_PL_SERVICE];
-        if (n_dda + n_tree + n_service == 0) break; /* queue drained and every ray of this CTA finished */
-        if (tid < 4u) s_n[(round + 2u) % 3u][tid] = 0; /* last read in the previous round, filled in the next one */
-        const u32 c_dda = (n_dda + 31u) >> 5, c_tree = (n_tree + 31u) >> 5, c_service = (n_service + 31u) >> 5;
-
-        /* ---- the warps take chunks of 32 entries: the long DDA chunks first, then the tree steps, then the service ---- */
-        for (u32 chunk = warp; chunk < c_dda + c_tree + c_service; chunk += WARPS)
-        {
-            if (chunk < c_dda)
-            {
-                const u32 e = chunk * 32u + lane;
-                const bool valid = e < n_dda;
-                const u32 s = valid ? s_list[cur][TGB_PL_DDA][e] : 0u;
-                u32 kind = TGB_FL_DDA;
-                if (valid)
-                {
-                    u32 meta = s_state[TGB_PF_META][s];
-                    const u32 block = s_state[TGB_PF_BLOCK][s];
-                    const v3 d = tgb_v3(__uint_as_float(s_state[TGB_PF_DX][s]), __uint_as_float(s_state[TGB_PF_DY][s]), __uint_as_float(s_state[TGB_PF_DZ][s]));
-                    const f32 t_delta_x = __uint_as_float(s_state[TGB_PF_RX][s]), t_delta_y = __uint_as_float(s_state[TGB_PF_RY][s]), t_delta_z = __uint_as_float(s_state[TGB_PF_RZ][s]);
-                    f32 t_max_x, t_max_y, t_max_z;
-                    i32 x, y, z;
-                    if (meta & TGB_PM_SETUP)
-                    {
-                        /* :111-176 */
-                        meta &= ~TGB_PM_SETUP;
-                        const u32 child = s_state[TGB_PF_CHILD][s];
-                        const v3 child_min = tgb_v3(svo.bmin.x + (f32)((child & 31u) << 5), svo.bmin.y + (f32)(((child >> 5) & 31u) << 5), svo.bmin.z + (f32)(((child >> 10) & 31u) << 5));
-                        const f32 child_size = (f32)((16u >> ((child >> 15) & 7u)) << 5);
-                        v3 hit = tgb_v3(__uint_as_float(s_state[TGB_PF_PX][s]), __uint_as_float(s_state[TGB_PF_PY][s]), __uint_as_float(s_state[TGB_PF_PZ][s]));
-                        v3 xyz = tgb_v3(tgb_clamp(floorf(hit.x), child_min.x, (child_min.x + child_size) - 1.0f),
-                                        tgb_clamp(floorf(hit.y), child_min.y, (child_min.y + child_size) - 1.0f),
-                                        tgb_clamp(floorf(hit.z), child_min.z, (child_min.z + child_size) - 1.0f));
-                        hit = tgb_sub(hit, child_min);
-                        xyz = tgb_sub(xyz, child_min);
-                        x = (i32)xyz.x; y = (i32)xyz.y; z = (i32)xyz.z;
-                        t_max_x = TG_F32_MAX; t_max_y = TG_F32_MAX; t_max_z = TG_F32_MAX;
-                        if (d.x > 0.0f)      t_max_x = ((f32)(x + 1) - hit.x) / d.x;
-                        else if (d.x < 0.0f) t_max_x = (hit.x - (f32)x) / -d.x;
-                        if (d.y > 0.0f)      t_max_y = ((f32)(y + 1) - hit.y) / d.y;
-                        else if (d.y < 0.0f) t_max_y = (hit.y - (f32)y) / -d.y;
-                        if (d.z > 0.0f)      t_max_z = ((f32)(z + 1) - hit.z) / d.z;
-                        else if (d.z < 0.0f) t_max_z = (hit.z - (f32)z) / -d.z;
-                    }
-                    else
-                    {
-                        t_max_x = __uint_as_float(s_state[TGB_PF_TX][s]); t_max_y = __uint_as_float(s_state[TGB_PF_TY][s]); t_max_z = __uint_as_float(s_state[TGB_PF_TZ][s]);
-                        x = (i32)((block >> 15) & 31u); y = (i32)((block >> 20) & 31u); z = (i32)((block >> 25) & 31u);
-                    }
-                    /* :178-257, steps written with selects (adding +0 to the other two t_max leaves them bit-identical) */
-                    const u32* __restrict__ p_block = svo.p_voxels + (u64)(block & 32767u) * TG_SVO_BLOCK_WORDS;
-                    const i32 step_x = d.x > 0.0f ? 1 : (d.x < 0.0f ? -1 : 0);
-                    const i32 step_y = d.y > 0.0f ? 1 : (d.y < 0.0f ? -1 : 0);
-                    const i32 step_z = d.z > 0.0f ? 1 : (d.z < 0.0f ? -1 : 0);
-                    u32 bits = __ldg(&p_block[32 * z + y]); /* a block row is one word: bit 1024 z + 32 y + x; re-read only when the row changes */
-#pragma unroll 1
-                    for (u32 k = 0; k < (u32)DDA_STEPS; k++)
-                    {
-                        n_steps++;
-                        if ((bits >> x) & 1u) { kind = TGB_FL_HIT; break; }
-                        const bool xy = t_max_x < t_max_y;
-                        const bool go_x = xy & (t_max_x < t_max_z);
-                        const bool go_y = !xy & (t_max_y < t_max_z);
-                        const bool go_z = !(go_x | go_y);
-                        t_max_x = go_x ? t_max_x + t_delta_x : t_max_x;
-                        t_max_y = go_y ? t_max_y + t_delta_y : t_max_y;
-                        t_max_z = go_z ? t_max_z + t_delta_z : t_max_z;
-                        x += go_x ? step_x : 0;
-                        y += go_y ? step_y : 0;
-                        z += go_z ? step_z : 0;
-                        if ((u32)(x | y | z) > 31u) { kind = TGB_FL_TREE; break; } /* left the block: a coordinate is -1 or 32 */
-                        if (!go_x) bits = __ldg(&p_block[32 * z + y]);
-                    }
-                    s_state[TGB_PF_META][s] = (meta & ~TGB_PM_KIND_MASK) | kind;
-                    if (kind != TGB_FL_TREE)
-                    {
-                        s_state[TGB_PF_BLOCK][s] = (block & 32767u) | ((u32)x << 15) | ((u32)y << 20) | ((u32)z << 25);
-                        if (kind == TGB_FL_DDA)
-                        {
-                            s_state[TGB_PF_TX][s] = __float_as_uint(t_max_x); s_state[TGB_PF_TY][s] = __float_as_uint(t_max_y); s_state[TGB_PF_TZ][s] = __float_as_uint(t_max_z);
-                        }
-                    }
-                }
-                tgb_pool_file<SLOTS>(valid, kind, s, s_list[nxt], p_n_next, lane);
-            }
-            else if (chunk < c_dda + c_tree)
-            {
-                const u32 e = (chunk - c_dda) * 32u + lane;
-                const bool valid = e < n_tree;
-                const u32 s = valid ? s_list[cur][TGB_PL_TREE][e] : 0u;
-                u32 kind = TGB_FL_TREE;
-                if (valid)
-                {
-                    u32 meta = s_state[TGB_PF_META][s];
-                    const v3 d = tgb_v3(__uint_as_float(s_state[TGB_PF_DX][s]), __uint_as_float(s_state[TGB_PF_DY][s]), __uint_as_float(s_state[TGB_PF_DZ][s]));
-                    v3 position = tgb_v3(__uint_as_float(s_state[TGB_PF_PX][s]), __uint_as_float(s_state[TGB_PF_PY][s]), __uint_as_float(s_state[TGB_PF_PZ][s]));
-                    if (meta & TGB_PM_ADVANCE)
-                    {
-                        /* :279-294 advance to the far border of the terminal box, :296-324 the ray ends when it has left the root */
-                        n_advances++;
-                        const u32 child = s_state[TGB_PF_CHILD][s];
-                        const v3 child_min = tgb_v3(svo.bmin.x + (f32)((child & 31u) << 5), svo.bmin.y + (f32)(((child >> 5) & 31u) << 5), svo.bmin.z + (f32)(((child >> 10) & 31u) << 5));
-                        const f32 child_size = (f32)((16u >> ((child >> 15) & 7u)) << 5);
-                        const f32 exit = tgb_exit_distance_rcp(child_min, child_size, position, d, __uint_as_float(s_state[TGB_PF_RX][s]), __uint_as_float(s_state[TGB_PF_RY][s]),
-                                                               __uint_as_float(s_state[TGB_PF_RZ][s]), (meta & TGB_PM_EXOTIC) != 0);
-                        position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
-                        s_state[TGB_PF_PX][s] = __float_as_uint(position.x); s_state[TGB_PF_PY][s] = __float_as_uint(position.y); s_state[TGB_PF_PZ][s] = __float_as_uint(position.z);
-                        /* a position at least one unit inside every face passes the pop test (exit >= 1 / |d| >= ~1 > epsilon) without evaluating it */
-                        const f32 off = fmaxf(fmaxf(fabsf(position.x - box_mid.x), fabsf(position.y - box_mid.y)), fabsf(position.z - box_mid.z));
-                        if (!(off < 0.5f * (f32)TG_SVO_SIDE_LENGTH - 1.0f)) { kind = TGB_FL_MISS; meta |= TGB_PM_BORDER; } /* the few rays near a face: tested in the service phase */
-                    }
-                    meta |= TGB_PM_ADVANCE;
-                    if (kind == TGB_FL_TREE)
-                    {
-                        const u32 iterations = (meta >> TGB_PM_ITER_SHIFT) + 1u;
-                        if (iterations > TGB_TRAVERSE_MAX_ITERS) kind = TGB_FL_MISS;
-                        else
-                        {
-                            /* :44-110: the terminal node around `position` */
-                            meta = (meta & ((1u << TGB_PM_ITER_SHIFT) - 1u)) | (iterations << TGB_PM_ITER_SHIFT);
-                            n_visits++;
-                            const u32 cx = tgb_cell_axis(position.x, d.x, min_cell_x);
-                            const u32 cy = tgb_cell_axis(position.y, d.y, min_cell_y);
-                            const u32 cz = tgb_cell_axis(position.z, d.z, min_cell_z);
-                            const u32 entry = __ldg(&p_grid[(cz << 10) | (cy << 5) | cx]);
-                            const u32 level = (entry >> TGB_TOP_LEVEL_SHIFT) & 7u;
-                            const u32 keep = ~((16u >> level) - 1u);
-                            s_state[TGB_PF_CHILD][s] = (cx & keep) | ((cy & keep) << 5) | ((cz & keep) << 10) | (level << 15);
-                            if (entry & TGB_TOP_HAS_DATA)
-                            {
-                                s_state[TGB_PF_BLOCK][s] = entry & 32767u;
-                                meta |= TGB_PM_SETUP;
-                                kind = TGB_FL_DDA;
-                            }
-                        }
-                    }
-                    s_state[TGB_PF_META][s] = (meta & ~TGB_PM_KIND_MASK) | kind;
-                }
-                tgb_pool_file<SLOTS>(valid, kind, s, s_list[nxt], p_n_next, lane);
-            }
-            else
-            {
-                /* ---- service: border tests, ambient returns, voxel-hit decisions, refill ---- */
-                const u32 e = (chunk - c_dda - c_tree) * 32u + lane;
-                const bool valid = e < n_service;
-                const u32 s = valid ? s_list[cur][TGB_PL_SERVICE][e] : 0u;
-                u32 meta = valid ? s_state[TGB_PF_META][s] : TGB_FL_TREE; /* an invalid lane must not look idle */
-                u32 kind = meta & TGB_PM_KIND_MASK;
-                if (valid && kind == TGB_FL_MISS && (meta & TGB_PM_BORDER))
-                {
-                    /* :296-324 for a ray within one unit of a root face: still inside -> back to the tree, position already advanced */
-                    meta &= ~TGB_PM_BORDER;
-                    const v3 d = tgb_v3(__uint_as_float(s_state[TGB_PF_DX][s]), __uint_as_float(s_state[TGB_PF_DY][s]), __uint_as_float(s_state[TGB_PF_DZ][s]));
-                    const v3 position = tgb_v3(__uint_as_float(s_state[TGB_PF_PX][s]), __uint_as_float(s_state[TGB_PF_PY][s]), __uint_as_float(s_state[TGB_PF_PZ][s]));
-                    if (tgb_still_inside(svo.bmin, svo.bmax, position, d)) { kind = TGB_FL_TREE; meta &= ~TGB_PM_ADVANCE; }
-                }
-                if (valid && kind == TGB_FL_MISS)
-                {
-                    /* unoccluded: ambient * 1 + lo; float addition commutes and the reductions do not stall the lane */
-                    const u32 q = s_state[TGB_PF_SLOT][s];
-                    const float4 q0 = p_q0[q], q2 = p_q2[q];
-                    f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
-                    atomicAdd(p_pixel + 0, q2.x);
-                    atomicAdd(p_pixel + 1, q2.y);
-                    atomicAdd(p_pixel + 2, q2.z);
-                    kind = TGB_FL_IDLE;
-                }
-                else if (valid && kind == TGB_FL_HIT)
-                {
-                    /* :219-256: result = enter / far of the slab test against the voxel; `enter` = the largest near-plane quotient */
-                    const u32 q = s_state[TGB_PF_SLOT][s], child = s_state[TGB_PF_CHILD][s], block = s_state[TGB_PF_BLOCK][s];
-                    const v3 d = tgb_v3(__uint_as_float(s_state[TGB_PF_DX][s]), __uint_as_float(s_state[TGB_PF_DY][s]), __uint_as_float(s_state[TGB_PF_DZ][s]));
-                    const float4 q0 = p_q0[q];
-                    const v3 o = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
-                    const v3 child_min = tgb_v3(svo.bmin.x + (f32)((child & 31u) << 5), svo.bmin.y + (f32)(((child >> 5) & 31u) << 5), svo.bmin.z + (f32)(((child >> 10) & 31u) << 5));
-                    const i32 x = (i32)((block >> 15) & 31u), y = (i32)((block >> 20) & 31u), z = (i32)((block >> 25) & 31u);
-                    const v3 lo = tgb_add(child_min, tgb_v3((f32)x, (f32)y, (f32)z));
-                    const v3 hi = tgb_add(child_min, tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)));
-                    const f32 ex = d.x == 0.0f ? TG_F32_MIN : ((d.x > 0.0f ? lo.x : hi.x) - o.x) / d.x;
-                    const f32 ey = d.y == 0.0f ? TG_F32_MIN : ((d.y > 0.0f ? lo.y : hi.y) - o.y) / d.y;
-                    const f32 ez = d.z == 0.0f ? TG_F32_MIN : ((d.z > 0.0f ? lo.z : hi.z) - o.z) / d.z;
-                    const f32 enter = tgb_max(tgb_max(ex, ey), ez);
-                    /* only result < 1 ends the shader's loop (occluded), otherwise it advances past the leaf */
-                    kind = (enter / far_plane < 1.0f) ? TGB_FL_IDLE : TGB_FL_TREE;
-                }
-                /* refill: the idle slots of this chunk take the next rays of the global queue */
-                const u32 idle = __ballot_sync(0xFFFFFFFFu, valid && kind == TGB_FL_IDLE);
-                if (idle)
-                {
-                    const u32 n = (u32)__popc(idle);
-                    u32 base = 0;
-                    const u32 leader = (u32)(__ffs(idle) - 1);
-                    if (lane == leader) base = atomicAdd(&p_q_count[1], n);
-                    base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
-                    const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
-                    if (valid && kind == TGB_FL_IDLE && mine < n_rays)
-                    {
-                        const float4 q0 = p_q0[mine], q1 = p_q1[mine];
-                        const v3 d = tgb_v3(q1.x, q1.y, q1.z);
-                        /* :27-31: k_shade made the slab test against the root and queued its `enter` */
-                        v3 position = tgb_sub(tgb_v3(q0.x, q0.y, q0.z), center);
-                        if (q1.w > 0.0f) position = tgb_add(position, tgb_scale(d, q1.w));
-                        /* :139-176: the DDA increments 1 / |d| depend on the ray only (rcp.rn == IEEE 1 / x) */
-                        const f32 ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-                        const bool exotic = (ax != 0.0f && ax < 1e-30f) || (ay != 0.0f && ay < 1e-30f) || (az != 0.0f && az < 1e-30f);
-                        s_state[TGB_PF_DX][s] = __float_as_uint(d.x); s_state[TGB_PF_DY][s] = __float_as_uint(d.y); s_state[TGB_PF_DZ][s] = __float_as_uint(d.z);
-                        s_state[TGB_PF_PX][s] = __float_as_uint(position.x); s_state[TGB_PF_PY][s] = __float_as_uint(position.y); s_state[TGB_PF_PZ][s] = __float_as_uint(position.z);
-                        s_state[TGB_PF_RX][s] = __float_as_uint(ax != 0.0f ? __frcp_rn(ax) : TG_F32_MAX);
-                        s_state[TGB_PF_RY][s] = __float_as_uint(ay != 0.0f ? __frcp_rn(ay) : TG_F32_MAX);
-                        s_state[TGB_PF_RZ][s] = __float_as_uint(az != 0.0f ? __frcp_rn(az) : TG_F32_MAX);
-                        s_state[TGB_PF_SLOT][s] = mine;
-                        meta = exotic ? TGB_PM_EXOTIC : 0u; /* iterations 0, nothing pending: the first tree step only looks up */
-                        kind = TGB_FL_TREE;
-                    }
-                }
-                if (valid) s_state[TGB_PF_META][s] = (meta & ~TGB_PM_KIND_MASK) | kind;
-                tgb_pool_file<SLOTS>(valid, kind, s, s_list[nxt], p_n_next, lane); /* a slot that is still idle found the queue drained: it is not filed again */
-            }
-        }
-        __syncthreads();
-    }
-    /* [2] look-ups, [3] DDA steps, [4] advances of this frame */
-    n_visits = __reduce_add_sync(0xFFFFFFFFu, n_visits);
-    n_steps = __reduce_add_sync(0xFFFFFFFFu, n_steps);
-    n_advances = __reduce_add_sync(0xFFFFFFFFu, n_advances);
-    if (lane == 0)
-    {
-        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_visits);
-        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 2, (unsigned long long)n_steps);
-        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 3, (unsigned long long)n_advances);
-    }
-}
-
 /* ---- owner-resolved materials (multi-GPU) ------------------------------------------------------------------ */
 /* local object records with pointers / LUT-independent fields globalised, into this rank's slice of the global table */
 __global__ void k_globalize_objects(const tg_object_data* __restrict__ p_objects, u32 object_capacity, u32 global_pointer_base, tg_object_data* __restrict__ p_out)
@@ -1299,24 +991,13 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
             if (flat)
             {
                 /* scheduling knobs (tuning only): DDA steps per phase, lanes that trigger a service phase, bias of the majority vote towards the DDA */
-                static const int dda_steps = tgbd_env_int("TGB_GI_DDA_STEPS", TGB_GI_DDA_STEPS);
+                static const int dda_steps = tgbd_env_int("TGB_GI_DDA_STEPS", TGB_FL_DDA_STEPS);
                 static const u32 service_lanes = (u32)tgbd_env_int("TGB_GI_SERVICE_LANES", (i32)TGB_FL_SERVICE_LANES), dda_bias = (u32)tgbd_env_int("TGB_GI_DDA_BIAS", 0);
                 const dim3 gi_grid(d->n_sms * (u32)gi_ctas);
 #define TGB_GI_LAUNCH(K) k_gi_trace_flat<K><<<gi_grid, TGB_GI_THREADS, 0, d->stream>>>(a.svo, d->svo.d_top_grid, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, \
                                                                                       d->d_gi_count, d->d_radiance, service_lanes, dda_bias)
-                static const int pooled = tgbd_env_int("TGB_GI_POOL", 1), pool_ctas = max(1, min(16, tgbd_env_int("TGB_GI_POOL_CTAS_PER_SM", 5)));
-                const dim3 pool_grid(d->n_sms * (u32)pool_ctas);
-                static const int pool_threads = tgbd_env_int("TGB_GI_POOL_THREADS", 256);
-#define TGB_GI_LAUNCH_POOL(K, T) k_gi_trace_pool<K, T><<<pool_grid, T, 0, d->stream>>>(a.svo, d->svo.d_top_grid, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, \
-                                                                                      d->d_gi_count, d->d_radiance)
-                if (pooled && d->gi_traversal == 0)
-                {
-                    if (pool_threads <= 128) { if (dda_steps <= 4) TGB_GI_LAUNCH_POOL(4, 128); else if (dda_steps <= 8) TGB_GI_LAUNCH_POOL(8, 128); else TGB_GI_LAUNCH_POOL(16, 128); }
-                    else                     { if (dda_steps <= 4) TGB_GI_LAUNCH_POOL(4, 256); else if (dda_steps <= 8) TGB_GI_LAUNCH_POOL(8, 256); else TGB_GI_LAUNCH_POOL(16, 256); }
-                }
-                else if (dda_steps <= 4) TGB_GI_LAUNCH(4); else if (dda_steps <= 8) TGB_GI_LAUNCH(8); else if (dda_steps <= 16) TGB_GI_LAUNCH(16); else TGB_GI_LAUNCH(64);
+                if (dda_steps <= 4) TGB_GI_LAUNCH(4); else if (dda_steps <= 8) TGB_GI_LAUNCH(8); else if (dda_steps <= 16) TGB_GI_LAUNCH(16); else TGB_GI_LAUNCH(64);
 #undef TGB_GI_LAUNCH
-#undef TGB_GI_LAUNCH_POOL
                 TGB_LAUNCH_CHECK(d);
             }
             k_gi_trace<<<d->n_sms * 8, TGB_GI_THREADS, 0, d->stream>>>(a.svo, flat ? d->svo.d_top_grid + TGB_TOP_GRID_CELLS : NULL, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2,

@@ -70,6 +70,12 @@ class Raytracer:
         self._check()
         return idx
 
+    def create_object_synthetic(self, center, extent, angle, axis, object_seed, k, lut_idx=0):
+        """Seeded random bits generated on the device (scenes.random_solid_bits(object_seed, n, k) without the host array)."""
+        idx = self._lib.tg_raytracer_create_object_synthetic(C.byref(self._rt), T.v3(*center), T.v3u(*extent), angle, T.v3(*axis), lut_idx, object_seed, k)
+        self._check()
+        return idx
+
     def destroy_object(self, object_idx):
         self._lib.tg_raytracer_destroy_object(C.byref(self._rt), object_idx)
         self._check()
@@ -231,7 +237,10 @@ class Raytracer:
     def load_scene(self, scene):
         """Creates every object of a tg_b200.scenes.SceneSpec and its LUT (tg_application.c:64-98 analogue)."""
         for o in scene.objects:
-            self.create_object_from_data(o.center, o.extent, o.angle, o.axis, o.bits, o.lut_indices, o.lut_idx)
+            if o.bits is None and o.seed is not None:
+                self.create_object_synthetic(o.center, o.extent, o.angle, o.axis, o.seed, o.k, o.lut_idx)
+            else:
+                self.create_object_from_data(o.center, o.extent, o.angle, o.axis, o.bits, o.lut_indices, o.lut_idx)
         for i, (r, g, b) in enumerate(scene.lut):
             self.color_lut_set(i, r, g, b)
         self.synchronize()

@@ -89,6 +89,8 @@ class ObjectSpec:
     lut_idx: int = 0
     bits: np.ndarray = None       # [n_clusters, 16] uint32, pointer order (x fastest, then y, then z)
     lut_indices: np.ndarray = None  # [n_clusters, 512] uint8 or None (reference rule)
+    seed: int = None              # bits is None and seed given: random_solid_bits(seed, n, k), generated on the device
+    k: int = 3
 
     @property
     def dims(self):
@@ -146,7 +148,8 @@ def config1(k=3, width=1280, height=720, dims=(16, 16, 16), with_materials=True)
 
 def grid_scene(name, grid_x, grid_z, width, height, k=3, pitch_units=192.0, dims=(16, 8, 16), first_object=0, n_objects=None,
                with_bits=True):
-    """Objects on a grid_x x grid_z XZ lattice centred on the origin, y = 0 (configs 2-5)."""
+    """Objects on a grid_x x grid_z XZ lattice centred on the origin, y = 0 (configs 2-5). with_bits=False leaves the masks to
+    the device generator (tg_raytracer_create_object_synthetic with the same seed idx + 1 and k): same bits, no host array."""
     total = grid_x * grid_z
     if n_objects is None:
         n_objects = total - first_object
@@ -157,7 +160,7 @@ def grid_scene(name, grid_x, grid_z, width, height, k=3, pitch_units=192.0, dims
         cx = (i - (grid_x - 1) / 2.0) * pitch_units
         cz = (j - (grid_z - 1) / 2.0) * pitch_units
         objs.append(ObjectSpec(center=(cx, 0.0, cz), extent=(dims[0] * 8, dims[1] * 8, dims[2] * 8), angle=reference_object_angle(idx),
-                               bits=random_solid_bits(idx + 1, n, k) if with_bits else None, lut_indices=None))
+                               bits=random_solid_bits(idx + 1, n, k) if with_bits else None, lut_indices=None, seed=idx + 1, k=k))
     cam = CameraSpec(position=(0.0, 200.0, 0.0), pitch=float(deg2rad(-30.0)), yaw=0.0, roll=0.0, aspect=width / height)
     return SceneSpec(name=name, width=width, height=height, camera=cam, objects=objs)
 
@@ -165,6 +168,13 @@ def grid_scene(name, grid_x, grid_z, width, height, k=3, pitch_units=192.0, dims
 def config2(width=3840, height=2160, grid=32, k=3):
     """BASELINE configs[1]: 1,024 rotated/translated objects (2^21 clusters, ~10^9 voxels), 4K."""
     return grid_scene(f"config2_{grid}x{grid}", grid, grid, width, height, k=k)
+
+
+def config5_shard(rank, n_ranks, width=3840, height=2160, k=3):
+    """BASELINE configs[4]: rank's contiguous slice of a 384 x (32 n_ranks) lattice of 16x8x16-cluster objects -- 12,288 objects
+    = 25,165,824 clusters = 1.29e10 voxels per rank; 8 ranks = 98,304 objects, 201,326,592 clusters, 1.03e11 voxels (SURVEY.md
+    section 8d). The masks are generated on the device (seed = global object index + 1), nothing of that size exists on the host."""
+    return grid_scene(f"config5_x{n_ranks}", 384, 32 * n_ranks, width, height, k=k, first_object=rank * 12288, n_objects=12288, with_bits=False)
 
 
 def small_grid(grid=3, width=320, height=180, k=3, dims=(4, 2, 4)):
