@@ -101,6 +101,8 @@ class ClockSampler:
 
 WORKLOADS = {
     "c2": "BASELINE configs[1]+[2] per GPU: 1,024 objects (2^21 clusters, 1.07e9 voxels), 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
+    "c4": "BASELINE configs[3]: the configs[1] scene with 64 objects (the nearest to the player) moving every frame (translation.x += 0.5, angle += 1 degree "
+          "per frame, 120-frame cycle): 64 transform uploads + incremental SVO update + primary visibility + 1-bounce SVO GI (1 spp), 3840x2160, 1 GPU",
     "c5": "BASELINE configs[4] per GPU: 12,288 objects (25,165,824 clusters, 1.29e10 voxels; 8 GPUs = 1.03e11 voxels) generated on the device, "
           "3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
 }
@@ -113,6 +115,19 @@ def build_scene(rank, n_ranks, workload="c2", host_bits=True):
     if workload == "c5":
         return scenes.config5_shard(rank, n_ranks, WIDTH, HEIGHT)
     return scenes.grid_scene(f"config2_x{n_ranks}", 32, 32 * n_ranks, WIDTH, HEIGHT, k=3, first_object=rank * 1024, n_objects=1024, with_bits=host_bits)
+
+
+def c4_movers(scene):
+    """configs[3]: the 64 objects nearest to the player (objects 0..63 of SURVEY 8d lie outside the +-512 SVO box and would not
+    exercise the update) and their pose at frame f: translation.x += 0.5 f, angle += 1 degree * f (float32, like the tests)."""
+    from tg_b200 import scenes
+    order = np.argsort([o.center[0] ** 2 + o.center[2] ** 2 for o in scene.objects], kind="stable")[:64]
+    movers = [int(i) for i in order]
+
+    def pose(i, f):
+        o = scene.objects[i]
+        return (o.center[0] + 0.5 * f, o.center[1], o.center[2]), float(np.float32(o.angle) + scenes.deg2rad(1.0) * np.float32(f))
+    return movers, pose
 
 
 def cpu_scene(workload):
@@ -134,31 +149,54 @@ class CpuArm:
     (screen-rect pruned, OpenMP), then GI + shading of the same rows from that buffer with the oracle's SVO (built once,
     outside the timed region, like the GPU arm)."""
 
-    def __init__(self, scene):
+    def __init__(self, scene, dynamic=False):
         from oracle import oracle as O
         from tg_b200 import scenes
         self.O = O
+        self.dynamic, self.scene, self.frame_idx = dynamic, scene, 0
+        # all the host threads this process may use (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)
+        O.lib().tgo_set_threads(len(os.sched_getaffinity(0)))
         self.cores = O.lib().tgo_max_threads()
         self.rays = O.camera_rays(O.camera_from_spec(scene.camera))
         self.view = O.SceneView.from_scene(scene, with_lut=True)
         # the SVO only sees objects that can touch the +-512 box (the others fail the SAT against every root child)
-        near = [o for o in scene.objects if max(abs(o.center[0]), abs(o.center[2])) < 512 + 160]
-        self.svo = O.svo_create(O.SceneView.from_scene(scenes.SceneSpec(name="near", width=WIDTH, height=HEIGHT, camera=scene.camera, objects=near), with_lut=False),
-                                capacities=(1 << 25, 1 << 15, 1 << 16))
+        self.svo = self._build_svo(scene)
         self.rows = np.arange(0, HEIGHT, CPU_YSTEP)
         self.frame = np.zeros((HEIGHT, WIDTH, 4), dtype=np.float32)
 
+    def _build_svo(self, scene):
+        from tg_b200 import scenes
+        O = self.O
+        near = [o for o in scene.objects if max(abs(o.center[0]), abs(o.center[2])) < 512 + 160]
+        return O.svo_create(O.SceneView.from_scene(scenes.SceneSpec(name="near", width=WIDTH, height=HEIGHT, camera=scene.camera, objects=near), with_lut=False),
+                            capacities=(1 << 25, 1 << 15, 1 << 16))
+
     def sample(self):
-        """(seconds, rays) of one sample."""
+        """(seconds, rays) of one sample. dynamic (configs[3]): the movers take their next pose and the SVO is rebuilt inside the
+        sample -- the reference has no incremental path (tg_svo_create from scratch, tgvk_raytracer.c:1187-1217)."""
         O = self.O
         t0 = time.perf_counter()
+        if self.dynamic:
+            import copy
+            self.frame_idx = self.frame_idx % 120 + 1
+            movers, pose = c4_movers(self.scene)
+            moved = copy.copy(self.scene)
+            moved.objects = list(self.scene.objects)
+            for i in movers:
+                o = copy.copy(self.scene.objects[i])
+                o.center, o.angle = pose(i, self.frame_idx)
+                moved.objects[i] = o
+            self.view = O.SceneView.from_scene(moved, with_lut=True)
+            O.svo_destroy(self.svo)
+            self.svo = self._build_svo(moved)
         vis, _ = O.visibility(self.view, self.rays, WIDTH, HEIGHT, O.VIS_SCREEN_RECT, 0, HEIGHT, CPU_YSTEP)
         O.shade(self.view, self.rays, WIDTH, HEIGHT, vis, self.svo, gi=True, frame_seed=1, y0=0, y1=HEIGHT, ystep=CPU_YSTEP, out=self.frame)
         dt = time.perf_counter() - t0
         return dt, len(self.rows) * WIDTH + int((vis[self.rows] != CLEAR).sum())
 
     def text(self, n_rays):
-        return (f"every {CPU_YSTEP}th scanline of the 3840x2160 frame ({len(self.rows)} rows): oracle visibility (screen-rect pruned) + oracle GI/shading of "
+        return (("64 objects moved + oracle tg_svo_create from scratch (whole tree, not sampled) + " if self.dynamic else "")
+                + f"every {CPU_YSTEP}th scanline of the 3840x2160 frame ({len(self.rows)} rows): oracle visibility (screen-rect pruned) + oracle GI/shading of "
                 f"those rows, {n_rays} rays per sample, OpenMP")
 
     def close(self):
@@ -169,7 +207,7 @@ def run_reference(args, rank):
     """The CPU arm (rank 0 only; the other ranks exit without work)."""
     if rank != 0:
         return
-    arm = CpuArm(cpu_scene(args.workload))
+    arm = CpuArm(cpu_scene(args.workload), dynamic=args.workload == "c4")
     times, n_rays = [], 0
     for i in range(args.warmup + args.steps):
         secs, n_rays = arm.sample()
@@ -241,11 +279,27 @@ def main():
     rt.synchronize()
     svo_build_ms = rt.timings()["svo_ms"]
 
+    dynamic = args.workload == "c4"
+    assert not (dynamic and world > 1), "configs[3] is a 1-GPU configuration"
+    movers, pose = c4_movers(scene) if dynamic else ([], None)
+    frame_idx = [0]
+
+    def move_objects():
+        """configs[3]: 64 x tg_raytracer_set_object_transform (96-byte record upload each); marks the SVO for an incremental update."""
+        frame_idx[0] = frame_idx[0] % 120 + 1
+        for i in movers:
+            center, angle = pose(i, frame_idx[0])
+            rt.set_object_transform(i, center, angle)
+
     def frame():
+        if dynamic:
+            move_objects()
         rt.clear()
         rt.render_visibility()
         if world > 1:
             rt.merge_visibility()
+        if dynamic:
+            rt.svo_update()   # incremental: only the leaves the moved objects touch are re-sampled
         rt.render_shading()
 
     def flush_l2():
@@ -278,6 +332,9 @@ def main():
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stage = {"clear_ms": 0.0, "cull_ms": 0.0, "visibility_ms": 0.0, "merge_ms": 0.0, "shading_ms": 0.0}
+    if dynamic:
+        stage["svo_ms"] = 0.0
+    leaves_resampled = 0
     rt.reset_launch_counter()
     barrier()
     for i in range(args.steps):
@@ -290,7 +347,12 @@ def main():
         t = rt.timings()  # synchronises the stream; per-stage CUDA events of this frame
         for k in stage:
             stage[k] += t[k]
+        if dynamic:
+            leaves_resampled += rt.svo_leaves_resampled()
     barrier()
+    if dynamic:  # hit pixels drift as the objects move: mean of the count before and after the timed frames
+        n_hit = (n_hit + int((rt.read_visibility() != CLEAR).sum())) // 2
+        rays_per_frame = WIDTH * HEIGHT + n_hit
     last = rt.timings()
     launches = last["n_kernel_launches"]
     clocks = sampler.stop()
@@ -306,11 +368,16 @@ def main():
     bands = 1          # throughput: whole-frame copies behind the next frame's rendering (double-buffered radiance on the device)
     latency_bands = 4  # latency: four row bands, each copied while the next is shaded
 
-    def e2e_loop(n):
+    present_tiles = [torch.empty(max(y1 - y0, 1) * WIDTH, dtype=torch.int32).pin_memory().numpy().view(np.uint32).reshape(max(y1 - y0, 1), WIDTH)[:y1 - y0] for _ in range(2)]
+
+    def e2e_loop(n, tiles=None):
+        tiles = tiles or host_tiles
         tickets = []
         for i in range(n):
             flush_l2()
-            rt.set_frame_sink(host_tiles[i % 2], bands)
+            rt.set_frame_sink(tiles[i % 2], bands)
+            if dynamic:
+                move_objects()                        # render() then updates the SVO incrementally before shading
             rt.clear()
             rt.render()                               # tg_raytracer_render: K1 [+ merge + resolve] + K3 in bands, each band copied D2H as it completes
             tickets.append(rt.frame_ticket())
@@ -328,11 +395,23 @@ def main():
     t_e2e = max_over_ranks(t_e2e)
     e2e_value = rays_per_frame * args.steps / t_e2e / 1e6
     assert np.isfinite(host_tiles[0]).all() and np.isfinite(host_tiles[1]).all()
+    # the same loop with the reference's own end of frame: the present pass (present.frag -> B8G8R8A8_UNORM swapchain image), 4 B / pixel
+    e2e_loop(2, present_tiles)
+    rt.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps, present_tiles)
+    t_present = time.perf_counter() - t0
+    barrier()
+    t_present = max_over_ranks(t_present)
+    assert present_tiles[0].any() and present_tiles[1].any()
     # latency of ONE frame from the first call to the last byte in host memory (band overlap only, nothing in flight before it)
     lat = []
     for i in range(5):
         flush_l2(); rt.synchronize()
         t0 = time.perf_counter()
+        if dynamic:
+            move_objects()
         rt.set_frame_sink(host_tiles[0], latency_bands); rt.clear(); rt.render(); rt.wait_frame(rt.frame_ticket())
         lat.append(time.perf_counter() - t0)
     frame_latency_ms = 1e3 * float(np.median(lat))
@@ -357,8 +436,8 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
-            arm = CpuArm(cpu_scene(args.workload))
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N=1 figure
+            arm = CpuArm(cpu_scene(args.workload), dynamic=args.workload == "c4")
             samples = [arm.sample() for _ in range(12)]  # ~10-30 s of CPU work on the box host cores
             secs = sum(t for t, _ in samples)
             cpu = {"value": sum(n for _, n in samples) / secs / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
@@ -370,11 +449,16 @@ def main():
                                        + (f"; world = {world} such shards: ncclAllReduce(u64,min) merge, material reduce-scatter, GI split by screen tile" if world > 1 else ""),
                            "rays_per_frame": rays_per_frame, "primary_rays": world * WIDTH * HEIGHT, "gi_rays": n_hit, "svo_build_ms": svo_build_ms, "svo_bytes": svo_bytes,
                            "visible_objects": last["n_visible_objects"],
+                           **({"svo_leaves_resampled_per_frame": leaves_resampled / args.steps, "moved_objects_per_frame": len(movers)} if dynamic else {}),
                            "gi_work_rank0": {"rays_traced_through_svo": last["n_gi_rays"], "node_visits": last["n_gi_node_visits"], "dda_steps": last["n_gi_dda_steps"], "advances": last["n_gi_advances"]},
                            "l2": "flushed between steps (256 MiB write, outside the timed events)", "stage_ms": {k: v / args.steps for k, v in stage.items()}},
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96 * world, "d2h_bytes_per_step": WIDTH * HEIGHT * 16,
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96 * world + 96 * len(movers), "d2h_bytes_per_step": WIDTH * HEIGHT * 16,
                         "ms_per_step": 1e3 * t_e2e / args.steps, "frame_latency_ms": frame_latency_ms,
+                        "presented_bgra8": {"value": rays_per_frame * args.steps / t_present / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * t_present / args.steps,
+                                            "d2h_bytes_per_step": WIDTH * HEIGHT * 4,
+                                            "note": "same loop, the frame delivered as the reference delivers it (present.frag into the B8G8R8A8_UNORM swapchain image): "
+                                                    "k_present per band + 4 B / pixel over PCIe instead of the 16 B / pixel HDR rows"},
                         "note": "per frame: tg_raytracer_clear + tg_raytracer_render through the C ABI with a frame sink: the shaded RGBA32F rows go to pinned host memory "
                                 "on a copy stream while the next frame renders (radiance double-buffered on the device, two host buffers alternate, frame i is awaited "
                                 "after frame i+1 was submitted; every rank receives its own tile). All copies and the per-frame L2 flush are inside the timed region; "

@@ -135,6 +135,23 @@ TG_EXPORT void tg_raytracer_set_gi(tg_raytracer* p_raytracer, b32 enabled, u32 f
  * host memory, tgb200_synchronize() waits for everything. NULL switches the sink off.
  */
 TG_EXPORT void tgb200_set_frame_sink(tg_raytracer* p_raytracer, f32* p_host, u32 n_bands);
+/*
+ * Present pass (present.frag:9-12; tgvk_raytracer.c:560-630,1524-1553): the reference ends a frame by copying the HDR target 1:1
+ * into the swapchain image, VK_FORMAT_B8G8R8A8_UNORM (tgvk_core.c:4239-4246). TGB200_SINK_BGRA8 makes the frame sink deliver
+ * that image instead of the HDR rows: one u32 per pixel, a << 24 | r << 16 | g << 8 | b (bytes B, G, R, A), each channel
+ * NaN -> 0, clamped to [0, 1], round-to-nearest-even of c * 255 -- a quarter of the HDR frame's bytes over PCIe.
+ */
+typedef enum tgb200_sink_format { TGB200_SINK_RGBA32F = 0, TGB200_SINK_BGRA8 = 1 } tgb200_sink_format;
+TG_EXPORT void tgb200_set_frame_sink_ex(tg_raytracer* p_raytracer, void* p_host, u32 n_bands, tgb200_sink_format format);
+/* The presented frame (whole frame, synchronous): w*h u32, B8G8R8A8_UNORM as above. */
+TG_EXPORT void tg_raytracer_read_present(tg_raytracer* p_raytracer, u32* p_out);
+/*
+ * The presented frame as a .bmp file in the container the reference's tg_image_store_to_disc writes (tg_image_io.c:438-520):
+ * BITMAPV5HEADER, BI_BITFIELDS, 32 bits per pixel, top-down rows, pixel data at offset 150. Returns TG_FALSE on an I/O error.
+ */
+TG_EXPORT b32  tgb200_save_frame_bmp(tg_raytracer* p_raytracer, const char* p_filename);
+/* The writer alone (pure host): `p_pixels` = w*h B8G8R8A8 words, first row on top. */
+TG_EXPORT b32  tgb200_write_bmp_bgra8(const char* p_filename, u32 width, u32 height, const u32* p_pixels);
 TG_EXPORT u64  tgb200_frame_ticket(tg_raytracer* p_raytracer);
 TG_EXPORT void tgb200_wait_frame(tg_raytracer* p_raytracer, u64 ticket);
 

@@ -73,6 +73,7 @@ def lib():
         L.tgo_intersect_aabb_obb_ignore_contact.restype = T.b32
         L.tgo_shade.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, C.POINTER(T.u64), C.POINTER(T.tg_svo),
                                 T.u32, T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.f32)]
+        L.tgo_present_bgra8.argtypes = [C.POINTER(T.f32), T.u64, C.POINTER(T.u32)]
         L.tgo_simplex_noise.argtypes = [T.f32, T.f32, T.f32]
         L.tgo_simplex_noise.restype = T.f32
         L.tgo_procedural_voxel_is_solid.argtypes = [T.u32, T.u32, T.u32, T.u32]
@@ -248,4 +249,12 @@ def shade(view, rays, w, h, vis, svo=None, gi=False, frame_seed=1, debug=0, y0=0
     vis = np.ascontiguousarray(vis, dtype=np.uint64)
     lib().tgo_shade(C.byref(view.view), C.byref(rays), w, h, T.ptr(vis, T.u64), C.byref(svo) if svo is not None else None,
                     1 if gi else 0, frame_seed, debug, y0, h if y1 is None else y1, ystep, T.ptr(out, T.f32))
+    return out
+
+
+def present(radiance):
+    """present.frag + B8G8R8A8_UNORM conversion: float32 [..., 4] -> uint32 [...] (a << 24 | r << 16 | g << 8 | b)."""
+    rad = np.ascontiguousarray(radiance, dtype=np.float32)
+    out = np.empty(rad.shape[:-1], dtype=np.uint32)
+    lib().tgo_present_bgra8(T.ptr(rad, T.f32), out.size, T.ptr(out, T.u32))
     return out

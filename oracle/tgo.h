@@ -88,6 +88,9 @@ void tgo_procedural_solid_bits(u32 object_idx, v3u dims, u32* p_out);
 void tgo_shade(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, const u64* p_vis, const tg_svo* p_svo_or_null,
                u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1, u32 ystep, f32* p_out_rgba);
 
+/* present.frag + B8G8R8A8_UNORM conversion of n_pixels RGBA32F pixels (see tgo_shade.c) */
+void tgo_present_bgra8(const f32* p_rgba, u64 n_pixels, u32* p_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,3 +245,24 @@ void tgo_shade(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w
         }
     }
 }
+
+/*
+ * present pass: present.frag:9-12 (out_color = texture(present_texture, v_uv), a 1:1 copy of the HDR target) followed by the
+ * swapchain format's fixed-function conversion, VK_FORMAT_B8G8R8A8_UNORM (tgvk_core.c:4239-4246): NaN -> 0, clamp to [0, 1],
+ * c * 255 rounded to nearest, ties to even (rintf under the default rounding mode). One u32 per pixel, bytes B, G, R, A.
+ */
+static u32 tgo__unorm8(f32 c)
+{
+    f32 v = c > 0.0f ? c : 0.0f;
+    v = v > 1.0f ? 1.0f : v;
+    return (u32)rintf(v * 255.0f);
+}
+
+void tgo_present_bgra8(const f32* p_rgba, u64 n_pixels, u32* p_out)
+{
+    for (u64 i = 0; i < n_pixels; i++)
+    {
+        const f32* c = &p_rgba[i * 4];
+        p_out[i] = (tgo__unorm8(c[3]) << 24) | (tgo__unorm8(c[0]) << 16) | (tgo__unorm8(c[1]) << 8) | tgo__unorm8(c[2]);
+    }
+}

@@ -220,3 +220,26 @@ def test_synthetic_generator_host_twin_equals_scene_definition():
         out = np.empty((n, 16), dtype=np.uint32)
         L.tgb200_synthetic_solid_bits(seed, k, n, T.ptr(out, T.u32))
         assert np.array_equal(out, scenes.random_solid_bits(seed, n, k)), (seed, n, k)
+
+
+def test_bmp_writer_container(tmp_path):
+    """tgb200_write_bmp_bgra8: the container of the reference's tg_image_store_to_disc (tg_image_io.c:438-520) -- 'BM', V5 header
+    (124 bytes), BI_BITFIELDS masks of B8G8R8A8, 32 bpp, negative height (top-down), pixels at byte 150 -- read back byte for byte."""
+    import struct
+    import tg_b200
+    from tg_b200 import ctypes_defs as T
+    L = tg_b200.lib()
+    w, h = 5, 3
+    px = (np.arange(w * h, dtype=np.uint32) * np.uint32(0x01030507)) | np.uint32(0xFF000000)
+    path = str(tmp_path / "frame.bmp")
+    assert L.tgb200_write_bmp_bgra8(path.encode(), w, h, T.ptr(px, T.u32))
+    raw = open(path, "rb").read()
+    assert raw[:2] == b"BM" and len(raw) == 150 + w * h * 4
+    size, _, _, offset = struct.unpack_from("<IHHI", raw, 2)
+    assert size == len(raw) and offset == 150
+    hdr, bw, bh, planes, bpp, compression, image_size = struct.unpack_from("<IiiHHII", raw, 14)
+    assert (hdr, bw, bh, planes, bpp, compression, image_size) == (124, w, -h, 1, 32, 3, w * h * 4)
+    assert struct.unpack_from("<IIII", raw, 14 + 40) == (0x00FF0000, 0x0000FF00, 0x000000FF, 0xFF000000)
+    assert np.array_equal(np.frombuffer(raw, dtype="<u4", offset=150), px)
+    assert not L.tgb200_write_bmp_bgra8(str(tmp_path / "no_dir" / "x.bmp").encode(), w, h, T.ptr(px, T.u32))
+    L.tgb200_clear_error()

@@ -191,3 +191,13 @@ def test_golden_fixtures(oracle):
         got = compute(oracle, name)
         for key in want.files:
             assert np.array_equal(want[key], got[key]), (name, key)
+
+
+def test_present_known_answers(oracle):
+    """present.frag + VK_FORMAT_B8G8R8A8_UNORM: NaN -> 0, clamp, round-to-nearest-even of c * 255; bytes B, G, R, A."""
+    rgba = np.array([[0.0, 1.0, 0.5, 1.0], [0.2, 2.0, -1.0, 0.0], [np.nan, 0.5 / 255.0, 1.5 / 255.0, 0.999], [1.0, 0.0, 1.0, 1.0]], dtype=np.float32)
+    got = oracle.present(rgba)
+    # 0.5 * 255 = 127.5 -> 128 (even); 0.5 -> 0 (even), 1.5 -> 2 (even); 0.999 * 255 = 254.745 -> 255
+    want = [(255 << 24) | (0 << 16) | (255 << 8) | 128, (0 << 24) | (51 << 16) | (255 << 8) | 0, (255 << 24) | (0 << 16) | (0 << 8) | 2, 0xFFFF00FF]
+    assert [int(x) for x in got] == want
+    assert got.view(np.uint8).reshape(-1, 4)[3].tolist() == [255, 0, 255, 255]  # memory order B, G, R, A of the miss colour (1, 0, 1, 1)

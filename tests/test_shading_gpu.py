@@ -224,3 +224,31 @@ def test_frame_sink_bands_equal_the_plain_frame(gpu):
         assert np.array_equal(rt.read_radiance(), plain[0])
     finally:
         rt.destroy()
+
+
+def test_present_pass_and_bgra8_sink(gpu, oracle, tmp_path):
+    """Present pass (present.frag + B8G8R8A8_UNORM, k_present): the presented frame equals the oracle's conversion of the same
+    radiance bit for bit; the BGRA8 frame sink (row bands copied behind the shading) delivers the same words; the .bmp holds them."""
+    import torch
+    s = scenes.small_grid(grid=4, width=333, height=177)
+    rt = from_scene(s)
+    try:
+        rt.set_gi(True, 1)
+        rt.clear(); rt.render(); rt.synchronize()
+        rad = rt.read_radiance()
+        got = rt.read_present()
+        assert np.array_equal(got, oracle.present(rad))
+        assert len(np.unique(got)) > 50
+        for bands in (1, 3, 16):
+            host = torch.zeros(s.height * s.width, dtype=torch.int32).pin_memory().numpy().view(np.uint32).reshape(s.height, s.width)
+            rt.set_frame_sink(host, bands)
+            rt.clear(); rt.render()
+            rt.wait_frame(rt.frame_ticket())
+            assert np.array_equal(host, got), f"{bands} bands"
+        rt.set_frame_sink(None)
+        path = tmp_path / "frame.bmp"
+        assert rt.save_frame_bmp(path)
+        raw = open(path, "rb").read()
+        assert np.array_equal(np.frombuffer(raw, dtype="<u4", offset=150).reshape(s.height, s.width), got)
+    finally:
+        rt.destroy()

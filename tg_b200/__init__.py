@@ -47,6 +47,10 @@ SYMBOLS = {
     "tg_raytracer_set_gi": (None, [_RT, T.b32, T.u32]),
     "tgb200_set_gi_traversal": (None, [_RT, T.u32]),
     "tgb200_set_frame_sink": (None, [_RT, C.c_void_p, T.u32]),
+    "tgb200_set_frame_sink_ex": (None, [_RT, C.c_void_p, T.u32, C.c_int]),
+    "tg_raytracer_read_present": (None, [_RT, _P(T.u32)]),
+    "tgb200_save_frame_bmp": (T.b32, [_RT, C.c_char_p]),
+    "tgb200_write_bmp_bgra8": (T.b32, [C.c_char_p, T.u32, T.u32, _P(T.u32)]),
     "tgb200_frame_ticket": (T.u64, [_RT]),
     "tgb200_wait_frame": (None, [_RT, T.u64]),
     "tgb200_render_visibility": (None, [_RT]),

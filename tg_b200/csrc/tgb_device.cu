@@ -111,6 +111,7 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     if (d->d_radiance_pair[0]) TGB_CUDA(cudaFree(d->d_radiance_pair[0]));
     if (d->d_radiance_pair[1]) TGB_CUDA(cudaFree(d->d_radiance_pair[1]));
     d->d_radiance_pair[0] = d->d_radiance_pair[1] = NULL;
+    for (int k = 0; k < 2; k++) { if (d->d_present_pair[k]) TGB_CUDA(cudaFree(d->d_present_pair[k])); d->d_present_pair[k] = NULL; }
     d->radiance_flip = 0;
     if (d->d_gi_q0) TGB_CUDA(cudaFree(d->d_gi_q0));
     if (d->d_gi_q1) TGB_CUDA(cudaFree(d->d_gi_q1));
@@ -179,7 +180,7 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaStreamSynchronize(d->stream);
     if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
     cudaFree(d->d_cluster_pointers); cudaFree(d->d_c2o); cudaFree(d->d_objects); cudaFree(d->d_masks);
-    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance_pair[0]); cudaFree(d->d_radiance_pair[1]); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_count);
+    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance_pair[0]); cudaFree(d->d_radiance_pair[1]); cudaFree(d->d_present_pair[0]); cudaFree(d->d_present_pair[1]); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_count);
     cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
     if (d->h_gi_stats) cudaFreeHost(d->h_gi_stats);
@@ -274,9 +275,10 @@ extern "C" void tgbd_synchronize(struct tgb_device* d)
 }
 
 /* ---- frame sink ---- */
-extern "C" b32 tgbd_set_frame_sink(struct tgb_device* d, f32* p_host, u32 n_bands)
+extern "C" b32 tgbd_set_frame_sink(struct tgb_device* d, void* p_host, u32 n_bands, u32 format)
 {
-    d->p_sink = p_host;
+    d->p_sink = (f32*)p_host;
+    d->sink_format = format;
     d->sink_bands = n_bands < 1 ? 1 : (n_bands > TGB_MAX_BANDS ? TGB_MAX_BANDS : n_bands);
     return TG_TRUE;
 }

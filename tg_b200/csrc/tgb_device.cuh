@@ -104,6 +104,8 @@ struct tgb_device
     cudaStream_t copy_stream;
     f32*         p_sink;            /* caller memory (pinned for a truly asynchronous copy) or NULL */
     u32          sink_bands;        /* bands per frame, 1..TGB_MAX_BANDS */
+    u32          sink_format;       /* TGB200_SINK_RGBA32F: the HDR rows; TGB200_SINK_BGRA8: the presented rows (k_present), 4 B / pixel */
+    u32*         d_present_pair[2]; /* B8G8R8A8_UNORM frames, allocated on first use; [flip] like the radiance pair */
     cudaEvent_t  ev_band[TGB_MAX_BANDS];      /* band k shaded (main stream) */
     cudaEvent_t  ev_band_copied[2][TGB_MAX_BANDS]; /* band k of buffer p copied (copy stream): the next frame shaded into p waits for it */
     /* the radiance buffer is double-buffered while a sink is set (frame i+1 is shaded while frame i is still being copied) */

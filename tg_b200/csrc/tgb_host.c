@@ -687,7 +687,20 @@ void tgb200_comm_destroy(tg_raytracer* p_raytracer)
 void tgb200_set_frame_sink(tg_raytracer* p_raytracer, f32* p_host, u32 n_bands)
 {
     if (!tgb__alive(p_raytracer, "tgb200_set_frame_sink")) return;
-    tgbd_set_frame_sink(p_raytracer->p_device, p_host, n_bands);
+    tgbd_set_frame_sink(p_raytracer->p_device, p_host, n_bands, TGB200_SINK_RGBA32F);
+}
+
+void tgb200_set_frame_sink_ex(tg_raytracer* p_raytracer, void* p_host, u32 n_bands, tgb200_sink_format format)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_set_frame_sink_ex")) return;
+    TGB_REQUIRE(format == TGB200_SINK_RGBA32F || format == TGB200_SINK_BGRA8, TGB_VOID, "set_frame_sink_ex: unknown format %u", (u32)format);
+    tgbd_set_frame_sink(p_raytracer->p_device, p_host, n_bands, (u32)format);
+}
+
+void tg_raytracer_read_present(tg_raytracer* p_raytracer, u32* p_out)
+{
+    if (!tgb__alive(p_raytracer, "tg_raytracer_read_present")) return;
+    tgbd_read_present(p_raytracer->p_device, p_out);
 }
 
 u64 tgb200_frame_ticket(tg_raytracer* p_raytracer)

@@ -2,6 +2,64 @@
 #include "tgb_internal.h"
 #include "tgb_math.h"
 #include "tgb_hoist.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/*
+ * The presented frame on disc. Same container as the reference's writer (graphics/tg_image_io.c:438-520): 14-byte file header,
+ * 124-byte BITMAPV5HEADER with BI_BITFIELDS channel masks, 12 unused bytes, pixels from byte 150, negative height = rows top
+ * down, 32 bits per pixel. The pixels are the present pass's B8G8R8A8 words, i.e. masks r 0x00FF0000, g 0x0000FF00,
+ * b 0x000000FF, a 0xFF000000.
+ */
+static void tgb__put_u16(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); }
+static void tgb__put_u32(u8* p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); }
+
+b32 tgb200_write_bmp_bgra8(const char* p_filename, u32 width, u32 height, const u32* p_pixels)
+{
+    enum { FILE_HEADER = 14, V5_HEADER = 124, PIXEL_OFFSET = 150 };
+    const u64 n_pixel_bytes = (u64)width * height * 4u;
+    if (!p_filename || !p_pixels || width == 0 || height == 0 || PIXEL_OFFSET + n_pixel_bytes > 0xFFFFFFFFull)
+    {
+        tgb_set_error("write_bmp: bad arguments (%ux%u)", width, height);
+        return TG_FALSE;
+    }
+    u8 header[PIXEL_OFFSET];
+    memset(header, 0, sizeof(header));
+    header[0] = 'B'; header[1] = 'M';
+    tgb__put_u32(header + 2, (u32)(PIXEL_OFFSET + n_pixel_bytes));
+    tgb__put_u32(header + 10, PIXEL_OFFSET);
+    u8* p_info = header + FILE_HEADER;
+    tgb__put_u32(p_info + 0, V5_HEADER);
+    tgb__put_u32(p_info + 4, width);
+    tgb__put_u32(p_info + 8, (u32)(-(i32)height));  /* top-down */
+    tgb__put_u16(p_info + 12, 1);                   /* planes */
+    tgb__put_u16(p_info + 14, 32);                  /* bits per pixel */
+    tgb__put_u32(p_info + 16, 3);                   /* BI_BITFIELDS */
+    tgb__put_u32(p_info + 20, (u32)n_pixel_bytes);
+    tgb__put_u32(p_info + 40, 0x00FF0000u);         /* red mask */
+    tgb__put_u32(p_info + 44, 0x0000FF00u);         /* green */
+    tgb__put_u32(p_info + 48, 0x000000FFu);         /* blue */
+    tgb__put_u32(p_info + 52, 0xFF000000u);         /* alpha */
+    tgb__put_u32(p_info + 56, 0x57696E20u);         /* 'Win ': LCS_WINDOWS_COLOR_SPACE */
+    FILE* p_file = fopen(p_filename, "wb");
+    if (!p_file) { tgb_set_error("write_bmp: cannot open %s", p_filename); return TG_FALSE; }
+    const b32 ok = fwrite(header, 1, sizeof(header), p_file) == sizeof(header) && fwrite(p_pixels, 1, (size_t)n_pixel_bytes, p_file) == (size_t)n_pixel_bytes;
+    if (fclose(p_file) != 0 || !ok) { tgb_set_error("write_bmp: short write to %s", p_filename); return TG_FALSE; }
+    return TG_TRUE;
+}
+
+b32 tgb200_save_frame_bmp(tg_raytracer* p_raytracer, const char* p_filename)
+{
+    if (!p_raytracer || !p_raytracer->p_device) { tgb_set_error("tgb200_save_frame_bmp: raytracer is not alive"); return TG_FALSE; }
+    const u64 n = (u64)p_raytracer->width * p_raytracer->height;
+    u32* p_pixels = (u32*)malloc((size_t)n * 4u);
+    if (!p_pixels) { tgb_set_error("tgb200_save_frame_bmp: out of memory"); return TG_FALSE; }
+    b32 ok = tgbd_read_present(p_raytracer->p_device, p_pixels);
+    if (ok) ok = tgb200_write_bmp_bgra8(p_filename, p_raytracer->width, p_raytracer->height, p_pixels);
+    free(p_pixels);
+    return ok;
+}
 
 void tgb200_debug_cluster_ray(const tg_object_data* p_object, const tg_camera_rays* p_cam, u32 width, u32 height, u32 px, u32 py,
                               u32 cluster_pointer, v3* p_origin_ms, v3* p_direction_ms)

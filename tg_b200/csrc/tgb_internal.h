@@ -50,7 +50,9 @@ void  tgbd_reset_launch_counter(struct tgb_device* d);
 void  tgbd_set_shard(struct tgb_device* d, u32 global_pointer_base);
 void  tgbd_set_gi_traversal(struct tgb_device* d, u32 kind);
 /* frame sink: shading in row bands, each band copied to p_host (rows this rank shades, first shaded row first) on a second stream */
-b32   tgbd_set_frame_sink(struct tgb_device* d, f32* p_host, u32 n_bands);
+b32   tgbd_set_frame_sink(struct tgb_device* d, void* p_host, u32 n_bands, u32 format);
+/* present pass over the whole frame into caller memory (synchronous): B8G8R8A8_UNORM, one u32 per pixel */
+b32   tgbd_read_present(struct tgb_device* d, u32* p_out);
 u64   tgbd_frames_sunk(struct tgb_device* d);
 b32   tgbd_wait_frame(struct tgb_device* d, u64 ticket);
 b32   tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n_ranks);

@@ -909,6 +909,51 @@ __global__ void __launch_bounds__(256) k_resolve_material(const u64* __restrict_
     p_mat[i] = word;
 }
 
+/* ---- present pass: present.frag:9-12 + the swapchain's format conversion --------------------------------------- */
+/*
+ * The reference ends a frame by sampling the HDR target 1:1 into the swapchain image (present.frag: out_color = texture(..);
+ * tgvk_raytracer.c:560-630,1524-1553), whose format is VK_FORMAT_B8G8R8A8_UNORM (tgvk_core.c:4239-4246). The conversion
+ * is the fixed-function float -> UNORM8 one: NaN -> 0, clamp to [0, 1], round(c * 255) to nearest (ties to even); memory
+ * order B, G, R, A = one little-endian u32  a << 24 | r << 16 | g << 8 | b. One thread = one pixel, 16 B in, 4 B out.
+ */
+__device__ __forceinline__ u32 tgb_unorm8(f32 c)
+{
+    f32 v = c > 0.0f ? c : 0.0f; /* NaN and negatives -> 0 */
+    v = v > 1.0f ? 1.0f : v;
+    return __float2uint_rn(v * 255.0f);
+}
+
+__global__ void __launch_bounds__(256) k_present(const float4* __restrict__ p_radiance, u32* __restrict__ p_out, u64 first, u64 n)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = p_radiance[first + i];
+    p_out[first + i] = (tgb_unorm8(c.w) << 24) | (tgb_unorm8(c.x) << 16) | (tgb_unorm8(c.y) << 8) | tgb_unorm8(c.z);
+}
+
+static b32 tgbd__present_buffer(struct tgb_device* d, u32 buf)
+{
+    if (!d->d_present_pair[buf])
+    {
+        const u64 n_bytes = (u64)d->width * d->tile_rows * (d->n_ranks ? d->n_ranks : 1) * sizeof(u32);
+        TGB_CUDA(cudaMalloc(&d->d_present_pair[buf], n_bytes));
+    }
+    return TG_TRUE;
+}
+
+/* the whole frame (the current radiance buffer) presented into caller memory; synchronous */
+extern "C" b32 tgbd_read_present(struct tgb_device* d, u32* p_out)
+{
+    TGB_CUDA(cudaSetDevice(d->device));
+    if (!tgbd__present_buffer(d, d->radiance_flip)) return TG_FALSE;
+    const u64 n = (u64)d->width * d->height;
+    k_present<<<(u32)((n + 255) / 256), 256, 0, d->stream>>>(d->d_radiance, d->d_present_pair[d->radiance_flip], 0, n);
+    TGB_LAUNCH_CHECK(d);
+    TGB_CUDA(cudaMemcpyAsync(p_out, d->d_present_pair[d->radiance_flip], n * sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
+    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    return TG_TRUE;
+}
+
 static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam, bool resolved, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1)
 {
     if (d->p_sink)
@@ -924,6 +969,8 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         d->d_radiance = d->d_radiance_pair[d->radiance_flip];
     }
     const u32 buf = d->radiance_flip;
+    const bool present = d->p_sink && d->sink_format == TGB200_SINK_BGRA8;
+    if (present && !tgbd__present_buffer(d, buf)) return TG_FALSE;
     tgb_shade_args a;
     a.p_vis = d->d_vis;
     a.p_out = d->d_radiance;
@@ -1006,10 +1053,16 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         }
         if (d->p_sink)
         {
-            const u64 offset = (u64)(by0 - y0) * d->width * 4u, n_bytes = (u64)(by1 - by0) * d->width * sizeof(float4);
+            const u64 first_px = (u64)by0 * d->width, n_px = (u64)(by1 - by0) * d->width;
+            if (present)
+            {
+                k_present<<<(u32)((n_px + 255) / 256), 256, 0, d->stream>>>(d->d_radiance, d->d_present_pair[buf], first_px, n_px);
+                TGB_LAUNCH_CHECK(d);
+            }
             TGB_CUDA(cudaEventRecord(d->ev_band[b], d->stream));
             TGB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_band[b], 0));
-            TGB_CUDA(cudaMemcpyAsync(d->p_sink + offset, d->d_radiance + (u64)by0 * d->width, n_bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+            if (present) TGB_CUDA(cudaMemcpyAsync((u32*)d->p_sink + (u64)(by0 - y0) * d->width, d->d_present_pair[buf] + first_px, n_px * sizeof(u32), cudaMemcpyDeviceToHost, d->copy_stream));
+            else         TGB_CUDA(cudaMemcpyAsync(d->p_sink + (u64)(by0 - y0) * d->width * 4u, d->d_radiance + first_px, n_px * sizeof(float4), cudaMemcpyDeviceToHost, d->copy_stream));
             TGB_CUDA(cudaEventRecord(d->ev_band_copied[buf][b], d->copy_stream));
             new_pending[b] = TG_TRUE;
             /* an older copy still tracked under this index (the band layout changed): keep the union of the row ranges, the re-recorded event covers both */

@@ -314,17 +314,17 @@ __device__ __forceinline__ f32 tgb_slab_enter(const tgb_ray_in_object& r, f32 nx
 }
 
 /*
- * One cluster, exactly visibility.frag:71-207 with the ray (o, d) in cluster space. `best` is the running per-pixel
- * minimum, `t_skip` a ray parameter beyond which no hit can beat it (depth24(t) > depth24(best) for every t >= t_skip).
+ * One cluster, exactly visibility.frag:71-207 with the ray (o, d) in cluster space, in two halves so that a warp can run
+ * the second one with all the lanes that have a cluster to march through (k_visibility<.., true>).
+ *
+ * First half, visibility.frag:71-81 = collide.inc:3-24 against [0,8]^3: does the ray meet the cluster (exit > 0 &&
+ * enter <= exit), and can a hit inside still beat `best`? `t_skip` is a ray parameter beyond which no hit can
+ * (depth24(t) > depth24(best) for every t >= t_skip). Returns the shader's `enter`.
  */
-__device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 far_plane,
-                                                  const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
-                                                  u32 global_pointer_base, u64& best, f32& t_skip)
+__device__ __forceinline__ bool tgb_cluster_candidate(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 t_skip, f32* p_enter)
 {
     const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
     const v3 d = r.d;
-
-    /* visibility.frag:71-81 = collide.inc:3-24 against [0,8]^3: hit iff exit > 0 && enter <= exit */
     const f32 nx = (d.x > 0.0f ? 0.0f : 8.0f) - o.x, fx = (d.x > 0.0f ? 8.0f : 0.0f) - o.x;
     const f32 ny = (d.y > 0.0f ? 0.0f : 8.0f) - o.y, fy = (d.y > 0.0f ? 8.0f : 0.0f) - o.y;
     const f32 nz = (d.z > 0.0f ? 0.0f : 8.0f) - o.z, fz = (d.z > 0.0f ? 8.0f : 0.0f) - o.z;
@@ -337,18 +337,28 @@ __device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, con
     if (!r.exotic && ((x_min > tol) & (e_max + tol < x_min)))
     {
         /* clear hit; a cluster entered beyond t_skip cannot win (voxel_enter >= enter, depth24 is monotone) */
-        if (e_max - tol > t_skip) return;
+        if (e_max - tol > t_skip) return false;
         enter = tgb_slab_enter(r, nx, ny, nz, ex, ey, ez, e_max);
     }
     else
     {
-        if (!r.exotic && ((x_min < -tol) | (e_max - tol > x_min))) return; /* clear miss */
+        if (!r.exotic && ((x_min < -tol) | (e_max - tol > x_min))) return false; /* clear miss */
         f32 exit;
-        if (!tgb_ray_aabb(o, d, tgb_v3(0.0f, 0.0f, 0.0f), tgb_v3(8.0f, 8.0f, 8.0f), &enter, &exit)) return;
+        if (!tgb_ray_aabb(o, d, tgb_v3(0.0f, 0.0f, 0.0f), tgb_v3(8.0f, 8.0f, 8.0f), &enter, &exit)) return false;
     }
     /* voxel_enter >= enter (same o, d, nested boxes, monotone rounding) => depth24(hit) >= depth24(enter) > depth24(best) */
-    if (enter > t_skip) return;
+    if (enter > t_skip) return false;
+    *p_enter = enter;
+    return true;
+}
 
+/* Second half, visibility.frag:83-207: the 8^3 Amanatides-Woo march from `enter`, the depth of the voxel found, the packed word. */
+__device__ __forceinline__ void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 enter, f32 far_plane,
+                                                  const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
+                                                  u32 global_pointer_base, u64& best, f32& t_skip)
+{
+    const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
+    const v3 d = r.d;
     const u32 cluster_pointer = f.first_cluster_pointer + cx + f.nx * (cy + f.ny * cz);
     const u32 cluster_idx = __ldg(&p_cluster_pointers[cluster_pointer]);
     const uint2* __restrict__ p_slices = reinterpret_cast<const uint2*>(p_masks + (u64)cluster_idx * TG_CLUSTER_MASK_WORDS);
@@ -431,6 +441,7 @@ __device__ __forceinline__ void tgb_visit_cluster(const tgb_object_frame& f, con
  * One ray against one object: enumerate, slice by slice along the dominant axis of d (front to
  * back), every cluster whose box inflated by eps the ray can touch, and visit each.
  */
+template <bool REGROUP>
 __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 dir_ws, f32 far_plane,
                                                  const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
                                                  u32 global_pointer_base, u64& best, f32& t_skip)
@@ -517,6 +528,57 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
     s     = max(0, min(nk - 1, s));
     s_end = max(0, min(nk - 1, s_end));
 
+    if (REGROUP)
+    {
+        /*
+         * The same enumeration as a per-lane iterator: every lane first advances to its NEXT cluster that passes the first
+         * half (the inner loop; cheap), the lanes reconverge where it ends, and the march -- two thirds of K1's instructions --
+         * runs with all the lanes that hold a cluster instead of those whose k-th enumerated cluster happens to be one
+         * (measured: 7 of 32). Same clusters, same order per lane, same arithmetic.
+         */
+        i32 n_slices = (s_end - s) * sgn + 1;
+        s -= sgn;
+        i32 cu = 0, cu0 = 0, cu1 = -1, cv = 0, cv1 = -1;
+        for (;;)
+        {
+            f32 enter = 0.0f;
+            u32 cx = 0, cy = 0, cz = 0;
+            bool have = false;
+            for (;;)
+            {
+                if (cu < cu1) cu++;
+                else if (cv < cv1) { cv++; cu = cu0; }
+                else
+                {
+                    if (n_slices <= 0) break;
+                    n_slices--;
+                    s += sgn;
+                    cu1 = -1; cv1 = -1; cu = 0; cv = 0; /* empty until the ranges are known */
+                    const f32 ta = (8.0f * (f32)s - 2.0f * e - ok) * inv_dk, tb = (8.0f * (f32)(s + 1) + 2.0f * e - ok) * inv_dk;
+                    const f32 t0 = fmaxf(fminf(ta, tb), t_in), t1 = fminf(fmaxf(ta, tb), t_out);
+                    if (!(t0 <= t1)) continue;
+                    /* slices are visited with non-decreasing t0: once even the slice entry is behind the best hit, stop */
+                    if (t0 - (4.0f * e + 3.0517578125e-5f * fabsf(t0)) > t_skip) { n_slices = 0; break; }
+                    const f32 ua = ou + t0 * du, ub = ou + t1 * du;
+                    const f32 va = ov + t0 * dv, vb = ov + t1 * dv;
+                    const f32 pad = 2.0f * e + 3.0517578125e-5f * (fabsf(ou) + fabsf(ov) + t1);
+                    cu0 = max(0, (i32)floorf((fminf(ua, ub) - pad) * 0.125f));
+                    const i32 u1 = min(nu - 1, (i32)floorf((fmaxf(ua, ub) + pad) * 0.125f));
+                    const i32 v0 = max(0, (i32)floorf((fminf(va, vb) - pad) * 0.125f));
+                    const i32 v1 = min(nv - 1, (i32)floorf((fmaxf(va, vb) + pad) * 0.125f));
+                    if (cu0 > u1 || v0 > v1) continue;
+                    cu = cu0; cu1 = u1; cv = v0; cv1 = v1;
+                }
+                cx = (u32)(k == 0 ? s : (k == 1 ? cv : cu));
+                cy = (u32)(k == 0 ? cu : (k == 1 ? s : cv));
+                cz = (u32)(k == 0 ? cv : (k == 1 ? cu : s));
+                if (tgb_cluster_candidate(f, r, cx, cy, cz, t_skip, &enter)) { have = true; break; }
+            }
+            if (!have) break;
+            tgb_cluster_march(f, r, cx, cy, cz, enter, far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+        }
+    }
+    else
     for (;; s += sgn)
     {
         const f32 ta = (8.0f * (f32)s - 2.0f * e - ok) * inv_dk, tb = (8.0f * (f32)(s + 1) + 2.0f * e - ok) * inv_dk;
@@ -539,7 +601,9 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
                     const u32 cx = (u32)(k == 0 ? s : (k == 1 ? cv : cu));
                     const u32 cy = (u32)(k == 0 ? cu : (k == 1 ? s : cv));
                     const u32 cz = (u32)(k == 0 ? cv : (k == 1 ? cu : s));
-                    tgb_visit_cluster(f, r, cx, cy, cz, far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+                    f32 enter;
+                    if (tgb_cluster_candidate(f, r, cx, cy, cz, t_skip, &enter))
+                        tgb_cluster_march(f, r, cx, cy, cz, enter, far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
                 }
             }
         }
@@ -555,7 +619,7 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
  * hit pixel (visibility.frag:206) so that other passes / shards may target the same buffer.
  */
 #define TGB_K1_THREADS 256
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool REGROUP>
 __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const tgb_object_frame* __restrict__ p_frames, const u32* __restrict__ p_count,
                                                                tg_camera_rays cam, u32 w, u32 h,
                                                                const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
@@ -616,7 +680,7 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
                 if (sorted && __all_sync(TGB_FULL_MASK, behind_best)) { warp_done = true; break; }
                 if (f.x1 < (i32)wx0 || f.x0 > wx1 || f.y1 < (i32)wy0 || f.y0 > wy1) continue; /* warp-uniform */
                 if (behind_best || (i32)px < f.x0 || (i32)px > f.x1 || (i32)py < f.y0 || (i32)py > f.y1) continue;
-                tgb_trace_object(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+                tgb_trace_object<REGROUP>(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
             }
         }
         if (base + TGB_K1_THREADS < n_visible) __syncthreads(); /* s_list is rewritten by the next window */
@@ -642,13 +706,12 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
 
     const dim3 grid((d->width + TGB_TILE_W - 1) / TGB_TILE_W, (d->height + TGB_TILE_H - 1) / TGB_TILE_H);
     /* register budget: 4 CTAs per SM = 64 registers with ~30 spilled words, measured 11 % faster than 3 CTAs = 80 registers (TGB_K1_MIN_CTAS=3 selects that build; tuning only) */
-    static const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 4);
-    if (min_ctas >= 4)
-        k_visibility<4><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height,
-                                                               d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis);
-    else
-        k_visibility<3><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height,
-                                                               d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis);
+    static const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 4), regroup = tgbd_env_int("TGB_K1_REGROUP", 1);
+#define TGB_K1_LAUNCH(C, R) k_visibility<C, R><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height, \
+                                                                                       d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis)
+    if (regroup) { if (min_ctas >= 4) TGB_K1_LAUNCH(4, true); else TGB_K1_LAUNCH(3, true); }
+    else         { if (min_ctas >= 4) TGB_K1_LAUNCH(4, false); else TGB_K1_LAUNCH(3, false); }
+#undef TGB_K1_LAUNCH
     TGB_LAUNCH_CHECK(d);
     TGB_CUDA(cudaEventRecord(d->ev[4], d->stream));
     d->ev_vis = TG_TRUE;

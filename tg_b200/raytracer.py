@@ -206,15 +206,29 @@ class Raytracer:
         self._lib.tgb200_gather_radiance(C.byref(self._rt))
 
     def set_frame_sink(self, host_array, n_bands=8):
-        """Every later render() copies its shaded rows into `host_array` (float32, rows x w x 4; pinned for overlap) band by
-        band while the frame is still being shaded; None switches it off."""
+        """Every later render() copies its shaded rows into `host_array` band by band while the frame is still being shaded
+        (pinned memory for overlap); None switches it off. float32 rows x w x 4 = the HDR rows; uint32 rows x w = the
+        presented rows (B8G8R8A8_UNORM, present.frag + the swapchain's conversion)."""
         if host_array is None:
             self._sink = None
             self._lib.tgb200_set_frame_sink(C.byref(self._rt), None, 1)
             return
-        assert host_array.dtype == np.float32 and host_array.flags["C_CONTIGUOUS"]
+        assert host_array.dtype in (np.float32, np.uint32) and host_array.flags["C_CONTIGUOUS"]
         self._sink = host_array  # keep it alive while copies may be in flight
-        self._lib.tgb200_set_frame_sink(C.byref(self._rt), host_array.ctypes.data, n_bands)
+        self._lib.tgb200_set_frame_sink_ex(C.byref(self._rt), host_array.ctypes.data, n_bands, 0 if host_array.dtype == np.float32 else 1)
+
+    def read_present(self, out=None):
+        """The presented frame: uint32 [h, w], a << 24 | r << 16 | g << 8 | b."""
+        if out is None:
+            out = np.empty((self.height, self.width), dtype=np.uint32)
+        self._lib.tg_raytracer_read_present(C.byref(self._rt), T.ptr(out, T.u32))
+        self._check()
+        return out
+
+    def save_frame_bmp(self, path):
+        ok = self._lib.tgb200_save_frame_bmp(C.byref(self._rt), str(path).encode())
+        self._check()
+        return bool(ok)
 
     def frame_ticket(self):
         return int(self._lib.tgb200_frame_ticket(C.byref(self._rt)))
