@@ -22,8 +22,8 @@
  *                            node are consecutive, allocated when the parent is visited; leaves numbered in DFS order),
  *                            write the node array, scan the per-leaf pair counts.
  *   3. k_svo_descend<true>   same walk, now scattering (leaf, cluster pointer) pairs into per-leaf segments.
- *   4. k_svo_fill_leaves     one CTA per leaf, one warp per (leaf, cluster) pair, one lane per x of a block row: the
- *                            reference's trilinear sampling, bits OR-ed into a 4 KiB shared-memory block (order
+ *   4. k_svo_fill_leaves     one CTA per leaf, one warp per (leaf, cluster) pair, per z slice the (y, x) samples of the
+ *                            clipped range dealt out to the lanes: the reference's trilinear sampling, bits OR-ed into a 4 KiB shared-memory block (order
  *                            independent), then the first 64 contributing cluster indices in ascending pointer order.
  * Everything that decides a bit or an index is the reference's arithmetic, operation for operation (-fmad=false).
  */
@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(TGB_LEAF_THREADS) k_svo_fill_leaves(const u32*
                                                                       u8* __restrict__ p_pair_flags, u32* __restrict__ p_leaf_data, u32* __restrict__ p_voxels, u32 only_dirty, u32 cluster_idx_base)
 {
     __shared__ u32 s_bits[TG_SVO_BLOCK_WORDS];
+    __shared__ f32 s_t[3][32]; /* (b + 0.5) / parent_extent per axis, :244-246 */
     __shared__ u32 s_n;
 
     const u32 data_pointer = blockIdx.x;
@@ -395,6 +396,12 @@ __global__ void __launch_bounds__(TGB_LEAF_THREADS) k_svo_fill_leaves(const u32*
     v3 parent_min, parent_max;
     tgb_dense_box(bmin, bmax, 5, dense, &parent_min, &parent_max);
     const v3 parent_extent = tgb_sub(parent_max, parent_min);
+    if (tid < 96u)
+    {
+        const u32 axis = tid >> 5, b = tid & 31u;
+        s_t[axis][b] = ((f32)b + 0.5f) / (axis == 0 ? parent_extent.x : (axis == 1 ? parent_extent.y : parent_extent.z));
+    }
+    __syncthreads();
 
     for (u32 k = warp; k < n_pairs; k += TGB_LEAF_WARPS)
     {
@@ -442,50 +449,49 @@ __global__ void __launch_bounds__(TGB_LEAF_THREADS) k_svo_fill_leaves(const u32*
             /* the cluster's 64-byte mask: lanes 0..15 hold one word each */
             const u32 my_word = lane < 16u ? __ldg(&p_masks[(u64)cluster_idx * TG_CLUSTER_MASK_WORDS + lane]) : 0u;
 
-            /* :242-315, one lane per bx of a row; a 32-wide block row is one voxel word */
-            const u32 bx = min_x + lane;
-            const f32 tx = ((f32)bx + 0.5f) / parent_extent.x;
-            const f32 omtx = 1.0f - tx;
-            for (u32 bz = min_z; bz < max_z; bz++)
+            /*
+             * :242-315. Per z slice the (by, bx) samples of the clipped range are dealt out to the lanes 32 at a time (the range
+             * is about 14 x 14 for a rotated cluster: one lane per bx of a row kept 14 of 32 lanes busy). The interpolation
+             * weights t = (b + 0.5) / extent of the three axes come from the CTA's table (the same division, done once).
+             * Every lerp keeps the reference's operands and order: z, then y, then x, omt * a + t * b.
+             */
+            const u32 nxr = max_x > min_x ? max_x - min_x : 0u, nyr = max_y > min_y ? max_y - min_y : 0u, n_xy = nxr * nyr; /* a range may be empty */
+            const u32 inv_nxr = nxr ? (65536u + nxr - 1u) / nxr : 0u; /* idx / nxr == (idx * inv_nxr) >> 16 for idx < 1024, nxr <= 32 */
+            for (u32 bz = min_z; bz < max_z && n_xy; bz++)
             {
-                const f32 tz = ((f32)bz + 0.5f) / parent_extent.z;
+                const f32 tz = s_t[2][bz];
                 const f32 omtz = 1.0f - tz;
                 const v3 pz0 = tgb_v3(omtz * bc[0].x + tz * bc[4].x, omtz * bc[0].y + tz * bc[4].y, omtz * bc[0].z + tz * bc[4].z);
                 const v3 pz1 = tgb_v3(omtz * bc[1].x + tz * bc[5].x, omtz * bc[1].y + tz * bc[5].y, omtz * bc[1].z + tz * bc[5].z);
                 const v3 pz2 = tgb_v3(omtz * bc[2].x + tz * bc[6].x, omtz * bc[2].y + tz * bc[6].y, omtz * bc[2].z + tz * bc[6].z);
                 const v3 pz3 = tgb_v3(omtz * bc[3].x + tz * bc[7].x, omtz * bc[3].y + tz * bc[7].y, omtz * bc[3].z + tz * bc[7].z);
-                for (u32 by = min_y; by < max_y; by++)
+                for (u32 base = 0; base < n_xy; base += 32u)
                 {
-                    const f32 ty = ((f32)by + 0.5f) / parent_extent.y;
-                    const f32 omty = 1.0f - ty;
+                    const u32 idx = base + lane;
+                    const bool in_range = idx < n_xy;
+                    const u32 iy = in_range ? (idx * inv_nxr) >> 16 : 0u;
+                    const u32 by = min_y + iy, bx = min_x + (in_range ? idx - iy * nxr : 0u);
+                    const f32 ty = s_t[1][by], tx = s_t[0][bx];
+                    const f32 omty = 1.0f - ty, omtx = 1.0f - tx;
                     const v3 py0 = tgb_v3(omty * pz0.x + ty * pz2.x, omty * pz0.y + ty * pz2.y, omty * pz0.z + ty * pz2.z);
                     const v3 py1 = tgb_v3(omty * pz1.x + ty * pz3.x, omty * pz1.y + ty * pz3.y, omty * pz1.z + ty * pz3.z);
-                    bool solid = false;
-                    u32 rel_voxel = 0;
-                    if (bx < max_x)
-                    {
-                        const f32 cx = omtx * py0.x + tx * py1.x;
-                        const f32 cy = omtx * py0.y + tx * py1.y;
-                        const f32 cz = omtx * py0.z + tx * py1.z;
-                        if (!(cx < 0.0f || cx >= 8.0f) && !(cy < 0.0f || cy >= 8.0f) && !(cz < 0.0f || cz >= 8.0f))
-                        {
-                            rel_voxel = 64u * (u32)cz + 8u * (u32)cy + (u32)cx;
-                            solid = true;
-                        }
-                    }
-                    /* every lane takes part in the shuffle; `solid` so far means "inside the cluster" */
+                    const f32 cx = omtx * py0.x + tx * py1.x;
+                    const f32 cy = omtx * py0.y + tx * py1.y;
+                    const f32 cz = omtx * py0.z + tx * py1.z;
+                    const bool inside = in_range && !(cx < 0.0f || cx >= 8.0f) && !(cy < 0.0f || cy >= 8.0f) && !(cz < 0.0f || cz >= 8.0f);
+                    const u32 rel_voxel = inside ? 64u * (u32)cz + 8u * (u32)cy + (u32)cx : 0u;
+                    /* every lane takes part in the shuffle */
                     const u32 word = __shfl_sync(0xFFFFFFFFu, my_word, (int)(rel_voxel >> 5));
-                    solid = solid && ((word >> (rel_voxel & 31u)) & 1u);
-                    const u32 hits = __ballot_sync(0xFFFFFFFFu, solid);
-                    if (hits)
+                    if (inside && ((word >> (rel_voxel & 31u)) & 1u))
                     {
                         contributed = true;
                         /* block voxel 1024*bz + 32*by + bx: word 32*bz + by, bit bx (parent_extent == 32) */
-                        if (lane == 0) atomicOr(&s_bits[32u * bz + by], hits << min_x);
+                        atomicOr(&s_bits[32u * bz + by], 1u << bx);
                     }
                 }
             }
         }
+        contributed = __any_sync(0xFFFFFFFFu, contributed);
         if (lane == 0) p_pair_flags[pair_off + k] = contributed ? 1 : 0;
     }
     __syncthreads();
