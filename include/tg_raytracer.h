@@ -223,6 +223,15 @@ TG_EXPORT void tgb200_gather_radiance(tg_raytracer* p_raytracer);
  * on every rank in lock-step; the next render() / tgb200_svo_update() rebuilds collectively). */
 TG_EXPORT void tgb200_mark_svo_dirty(tg_raytracer* p_raytracer);
 
+/*
+ * Scene dump / load: every initialised object (dims, transform, LUT index, solid masks, material indices) and the colour LUTs in one
+ * little-endian file (layout in tgb_host_extra.c). tgb200_scene_load creates the objects in a live raytracer through
+ * tg_raytracer_create_object_from_data, in the file's order: a fresh raytracer gets object indices 0..n-1 (holes left by destroyed
+ * objects are not reproduced). TG_FALSE + tgb200_last_error() on I/O errors, truncated files or exhausted capacity.
+ */
+TG_EXPORT b32  tgb200_scene_save(tg_raytracer* p_raytracer, const char* p_filename);
+TG_EXPORT b32  tgb200_scene_load(tg_raytracer* p_raytracer, const char* p_filename);
+
 /* ---- pure host logic, usable without a GPU (scene bookkeeping, camera) ---------------------- */
 
 /* tgvk_raytracer.c:687-712: allocates the CPU arrays, fills the LIFO free-lists descending. */

@@ -51,6 +51,8 @@ SYMBOLS = {
     "tg_raytracer_read_present": (None, [_RT, _P(T.u32)]),
     "tgb200_save_frame_bmp": (T.b32, [_RT, C.c_char_p]),
     "tgb200_write_bmp_bgra8": (T.b32, [C.c_char_p, T.u32, T.u32, _P(T.u32)]),
+    "tgb200_scene_save": (T.b32, [_RT, C.c_char_p]),
+    "tgb200_scene_load": (T.b32, [_RT, C.c_char_p]),
     "tgb200_frame_ticket": (T.u64, [_RT]),
     "tgb200_wait_frame": (None, [_RT, T.u64]),
     "tgb200_render_visibility": (None, [_RT]),

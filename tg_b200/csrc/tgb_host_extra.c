@@ -224,3 +224,103 @@ b32 tg_svo_traverse(const tg_svo* p_svo, v3 ray_origin, v3 ray_direction, f32* p
     }
     return TG_FALSE;
 }
+
+/* ---- scene dump / load: reproducible scenes for benches and bug reports ------------------------------- */
+/*
+ * File = "TGB200SC" | u32 version (1) | u32 n_objects | u32 n_color_luts | n_color_luts * 256 packed colours | per initialised object
+ * in ascending object index: { v3u dims; v3 translation; f32 angle; v3 axis; u32 lut_idx; dims.x*dims.y*dims.z * 16 u32 solid
+ * masks; the same number * 512 u8 material indices }, clusters in pointer order. Little-endian, no padding. The masks come from
+ * the CPU mirror (scene.p_voxel_cluster_data, tgvk_raytracer.h:100), materials and colour LUTs from the device (the reference
+ * keeps them in SSBOs only, tgvk_raytracer.c:20,44-47).
+ */
+#define TGB_SCENE_MAGIC "TGB200SC"
+
+b32 tgb200_scene_save(tg_raytracer* p_raytracer, const char* p_filename)
+{
+    if (!p_raytracer || !p_raytracer->p_device) { tgb_set_error("tgb200_scene_save: raytracer is not alive"); return TG_FALSE; }
+    const tg_scene* p_scene = &p_raytracer->scene;
+    FILE* p_file = fopen(p_filename, "wb");
+    if (!p_file) { tgb_set_error("tgb200_scene_save: cannot open %s", p_filename); return TG_FALSE; }
+    b32 ok = TG_TRUE;
+    u32 n_objects = 0;
+    for (u32 i = 0; i < p_scene->object_capacity; i++) n_objects += tg_object_is_initialized(p_scene, i) ? 1u : 0u;
+    const u32 version = 1, n_luts = p_raytracer->n_color_luts;
+    ok = ok && fwrite(TGB_SCENE_MAGIC, 1, 8, p_file) == 8 && fwrite(&version, 4, 1, p_file) == 1 && fwrite(&n_objects, 4, 1, p_file) == 1 && fwrite(&n_luts, 4, 1, p_file) == 1;
+    u32* p_lut = (u32*)malloc((size_t)n_luts * 256u * 4u);
+    ok = ok && p_lut && tgbd_download(p_raytracer->p_device, TGB_BUF_COLOR_LUT, 0, p_lut, (u64)n_luts * 256u * 4u) && fwrite(p_lut, 4, (size_t)n_luts * 256u, p_file) == (size_t)n_luts * 256u;
+    free(p_lut);
+    u8* p_materials = NULL;
+    size_t materials_capacity = 0;
+    for (u32 i = 0; ok && i < p_scene->object_capacity; i++)
+    {
+        if (!tg_object_is_initialized(p_scene, i)) continue;
+        const tg_voxel_object* o = &p_scene->p_objects[i];
+        const u32 n = o->n_cluster_pointers_per_dim.x * o->n_cluster_pointers_per_dim.y * o->n_cluster_pointers_per_dim.z;
+        const u32 lut_idx = p_raytracer->p_object_lut_idx[i];
+        ok = fwrite(&o->n_cluster_pointers_per_dim, sizeof(v3u), 1, p_file) == 1 && fwrite(&o->translation, sizeof(v3), 1, p_file) == 1
+          && fwrite(&o->angle_in_radians, 4, 1, p_file) == 1 && fwrite(&o->axis, sizeof(v3), 1, p_file) == 1 && fwrite(&lut_idx, 4, 1, p_file) == 1;
+        if ((size_t)n * 512u > materials_capacity)
+        {
+            free(p_materials);
+            materials_capacity = (size_t)n * 512u;
+            p_materials = (u8*)malloc(materials_capacity);
+            ok = ok && p_materials != NULL;
+        }
+        for (u32 rel = 0; ok && rel < n; rel++)
+        {
+            const u32 idx = p_scene->p_cluster_pointers[o->first_cluster_pointer + rel];
+            ok = fwrite(&p_scene->p_voxel_cluster_data[(size_t)idx * TG_CLUSTER_MASK_WORDS], 4, TG_CLUSTER_MASK_WORDS, p_file) == TG_CLUSTER_MASK_WORDS;
+        }
+        /* materials: one download when the object's cluster indices are one ascending run (always, unless objects were destroyed) */
+        const u32 idx0 = n ? p_scene->p_cluster_pointers[o->first_cluster_pointer] : 0u;
+        b32 run = TG_TRUE;
+        for (u32 rel = 1; rel < n; rel++) run = run && p_scene->p_cluster_pointers[o->first_cluster_pointer + rel] == idx0 + rel;
+        if (ok && run && n) ok = tgbd_download(p_raytracer->p_device, TGB_BUF_LUT_IDX, (u64)idx0 * 512u, p_materials, (u64)n * 512u);
+        for (u32 rel = 0; ok && !run && rel < n; rel++)
+            ok = tgbd_download(p_raytracer->p_device, TGB_BUF_LUT_IDX, (u64)p_scene->p_cluster_pointers[o->first_cluster_pointer + rel] * 512u, p_materials + (size_t)rel * 512u, 512u);
+        ok = ok && fwrite(p_materials, 512, n, p_file) == n;
+    }
+    free(p_materials);
+    if (fclose(p_file) != 0) ok = TG_FALSE;
+    if (!ok && !tgb200_last_error()) tgb_set_error("tgb200_scene_save: short write to %s", p_filename);
+    return ok;
+}
+
+b32 tgb200_scene_load(tg_raytracer* p_raytracer, const char* p_filename)
+{
+    if (!p_raytracer || !p_raytracer->p_device) { tgb_set_error("tgb200_scene_load: raytracer is not alive"); return TG_FALSE; }
+    FILE* p_file = fopen(p_filename, "rb");
+    if (!p_file) { tgb_set_error("tgb200_scene_load: cannot open %s", p_filename); return TG_FALSE; }
+    char magic[8];
+    u32 version = 0, n_objects = 0, n_luts = 0;
+    b32 ok = fread(magic, 1, 8, p_file) == 8 && memcmp(magic, TGB_SCENE_MAGIC, 8) == 0 && fread(&version, 4, 1, p_file) == 1 && version == 1
+          && fread(&n_objects, 4, 1, p_file) == 1 && fread(&n_luts, 4, 1, p_file) == 1;
+    if (!ok) tgb_set_error("tgb200_scene_load: %s is not a version-1 scene file", p_filename);
+    if (ok && n_luts > p_raytracer->n_color_luts) { tgb_set_error("tgb200_scene_load: the file holds %u colour LUTs, the raytracer %u", n_luts, p_raytracer->n_color_luts); ok = TG_FALSE; }
+    for (u32 l = 0; ok && l < n_luts; l++)
+    {
+        u32 lut[256];
+        ok = fread(lut, 4, 256, p_file) == 256 && tgbd_upload(p_raytracer->p_device, TGB_BUF_COLOR_LUT, (u64)l * 256u * 4u, lut, sizeof(lut));
+    }
+    for (u32 i = 0; ok && i < n_objects; i++)
+    {
+        v3u dims; v3 translation, axis; f32 angle = 0.0f; u32 lut_idx = 0;
+        ok = fread(&dims, sizeof(v3u), 1, p_file) == 1 && fread(&translation, sizeof(v3), 1, p_file) == 1 && fread(&angle, 4, 1, p_file) == 1
+          && fread(&axis, sizeof(v3), 1, p_file) == 1 && fread(&lut_idx, 4, 1, p_file) == 1;
+        if (!ok) break;
+        const u64 n = (u64)dims.x * dims.y * dims.z;
+        if (n == 0 || n > p_raytracer->scene.n_available_cluster_indices) { tgb_set_error("tgb200_scene_load: object %u needs %llu clusters, %u are free", i, (unsigned long long)n, p_raytracer->scene.n_available_cluster_indices); ok = TG_FALSE; break; }
+        u32* p_bits = (u32*)malloc((size_t)n * 64u);
+        u8* p_materials = (u8*)malloc((size_t)n * 512u);
+        ok = p_bits && p_materials && fread(p_bits, 64, (size_t)n, p_file) == (size_t)n && fread(p_materials, 512, (size_t)n, p_file) == (size_t)n;
+        if (ok)
+        {
+            const v3u extent = { dims.x * 8u, dims.y * 8u, dims.z * 8u };
+            ok = tg_raytracer_create_object_from_data(p_raytracer, translation, extent, angle, axis, lut_idx, p_bits, p_materials) != TG_U32_MAX;
+        }
+        free(p_bits); free(p_materials);
+    }
+    fclose(p_file);
+    if (!ok && !tgb200_last_error()) tgb_set_error("tgb200_scene_load: %s is truncated", p_filename);
+    return ok;
+}

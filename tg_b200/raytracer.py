@@ -225,6 +225,16 @@ class Raytracer:
         self._check()
         return out
 
+    def scene_save(self, path):
+        ok = self._lib.tgb200_scene_save(C.byref(self._rt), str(path).encode())
+        self._check()
+        return bool(ok)
+
+    def scene_load(self, path):
+        ok = self._lib.tgb200_scene_load(C.byref(self._rt), str(path).encode())
+        self._check()
+        return bool(ok)
+
     def save_frame_bmp(self, path):
         ok = self._lib.tgb200_save_frame_bmp(C.byref(self._rt), str(path).encode())
         self._check()
