@@ -109,12 +109,13 @@ WORKLOADS = {
 
 
 def build_scene(rank, n_ranks, workload="c2", host_bits=True):
-    """Rank's shard. c2: 1,024 objects (grid 32 x 32) out of a 32 x 32N lattice. c5: 12,288 objects out of a 384 x 32N lattice, masks
-    generated on the device. The global object index decides seed and angle."""
+    """Rank's shard. c2: 1,024 objects out of a 32 x 32N lattice. c5: 12,288 objects out of a 384 x 32N lattice, masks generated on
+    the device. Ownership is interleaved over the lattice (cell (i, j) belongs to rank (i + j) % N): every rank holds 1/N of what the
+    camera sees instead of one rank holding all of it. The global lattice index decides seed, angle and position."""
     from tg_b200 import scenes
     if workload == "c5":
         return scenes.config5_shard(rank, n_ranks, WIDTH, HEIGHT)
-    return scenes.grid_scene(f"config2_x{n_ranks}", 32, 32 * n_ranks, WIDTH, HEIGHT, k=3, first_object=rank * 1024, n_objects=1024, with_bits=host_bits)
+    return scenes.grid_scene(f"config2_x{n_ranks}", 32, 32 * n_ranks, WIDTH, HEIGHT, k=3, with_bits=host_bits, owner=(rank, n_ranks))
 
 
 def c4_movers(scene):
@@ -232,6 +233,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tg_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge", default="peer", choices=["peer", "nccl"], help="N > 1: peer = one kernel over peer memory (NVLink, falls back to nccl if unmappable); "
+                    "nccl = ncclAllReduce(u64, min) + materials + ncclReduceScatter")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the headline configuration (default); c5 = one 12,288-object shard of the 1e11-voxel world per GPU")
     args = ap.parse_args()
 
@@ -263,6 +266,7 @@ def main():
         ids = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         rt.comm_init(ids[0], rank, world)
+        rt.set_merge_kind(0 if args.merge == "peer" else 1)
     y0, y1 = rt.tile_rows()
 
     lib = tg_b200.lib()
@@ -296,8 +300,8 @@ def main():
             move_objects()
         rt.clear()
         rt.render_visibility()
-        if world > 1:
-            rt.merge_visibility()
+        if world > 1 and args.merge == "nccl":
+            rt.merge_visibility()   # else the shading stage merges this rank's tile straight from the peers' buffers
         if dynamic:
             rt.svo_update()   # incremental: only the leaves the moved objects touch are re-sampled
         rt.render_shading()
@@ -332,6 +336,8 @@ def main():
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stage = {"clear_ms": 0.0, "cull_ms": 0.0, "visibility_ms": 0.0, "merge_ms": 0.0, "shading_ms": 0.0}
+    if world > 1 and args.merge == "peer":
+        stage.update({"merge_resolve_ms": 0.0, "merge_gather_ms": 0.0, "merge_kernel_ms": 0.0})  # parts of merge_ms (rank 0)
     if dynamic:
         stage["svo_ms"] = 0.0
     leaves_resampled = 0
@@ -446,7 +452,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
                 "config": {"workload": WORKLOADS[args.workload]
-                                       + (f"; world = {world} such shards: ncclAllReduce(u64,min) merge, material reduce-scatter, GI split by screen tile" if world > 1 else ""),
+                                       + (f"; world = {world} such shards (interleaved ownership), GI split by screen tile, merge = "
+                                          + ("one kernel over peer memory (min + winner's material per tile, NVLink)" if args.merge == "peer" else "ncclAllReduce(u64,min) + material reduce-scatter")
+                                          if world > 1 else ""),
                            "rays_per_frame": rays_per_frame, "primary_rays": world * WIDTH * HEIGHT, "gi_rays": n_hit, "svo_build_ms": svo_build_ms, "svo_bytes": svo_bytes,
                            "visible_objects": last["n_visible_objects"],
                            **({"svo_leaves_resampled_per_frame": leaves_resampled / args.steps, "moved_objects_per_frame": len(movers)} if dynamic else {}),

@@ -195,6 +195,12 @@ typedef struct tgb200_timings
     u64 n_gi_node_visits;  /* work of those rays: node visits, leaf DDA steps, advances (svo_functions.inc loop iterations) */
     u64 n_gi_dda_steps;
     u64 n_gi_advances;
+    /* parts of merge_ms on the peer-memory path (0 otherwise): local material resolve | all-gather of the object records, which is
+     * where a rank waits for the slowest rank's K1 | k_merge_tile (min + winner's material over NVLink) */
+    f32 merge_resolve_ms;
+    f32 merge_gather_ms;
+    f32 merge_kernel_ms;
+    u32 pad2;
 } tgb200_timings;
 TG_EXPORT void tgb200_get_timings(tg_raytracer* p_raytracer, tgb200_timings* p_out);
 TG_EXPORT void tgb200_reset_launch_counter(tg_raytracer* p_raytracer);
@@ -213,8 +219,18 @@ TG_EXPORT void tgb200_set_shard(tg_raytracer* p_raytracer, u32 rank, u32 n_ranks
 TG_EXPORT void tgb200_comm_unique_id(u8* p_out_128);
 TG_EXPORT void tgb200_comm_init(tg_raytracer* p_raytracer, const u8* p_unique_id_128, u32 rank, u32 n_ranks);
 TG_EXPORT void tgb200_comm_destroy(tg_raytracer* p_raytracer);
-/* ncclAllReduce(ncclUint64, ncclMin) over the visibility buffer, in place. */
+/* ncclAllReduce(ncclUint64, ncclMin) over the visibility buffer, in place: afterwards every rank holds the whole merged frame. */
 TG_EXPORT void tgb200_merge_visibility(tg_raytracer* p_raytracer);
+/*
+ * How tg_raytracer_render / tgb200_render_shading exchange a sharded frame. 0 (default) = one kernel over peer memory: every rank
+ * maps the other ranks' visibility / material buffers (CUDA IPC over NVLink, collective set-up on first use) and resolves its own
+ * screen tile -- min over the ranks' words + the winner's material -- without the two whole-frame collectives; falls back to 1 on
+ * every rank when the buffers cannot be mapped. 1 = NCCL only: all-reduce(min) + owner-resolved materials + reduce-scatter(max).
+ * Both give the same frame, bit for bit. On the peer-memory path the device visibility buffer keeps this rank's LOCAL words;
+ * tg_raytracer_read_visibility / get_hovered_voxel pull the merged frame from the peers (call them between frames, ranks in
+ * lock-step), tgb200_merge_visibility still produces it in place.
+ */
+TG_EXPORT void tgb200_set_merge_kind(tg_raytracer* p_raytracer, u32 kind);
 /* Rows [first, one_past_last) of the frame this rank shades (GI rays are split by screen tile); the whole frame on one GPU. */
 TG_EXPORT void tgb200_tile_rows(tg_raytracer* p_raytracer, u32* p_first_row, u32* p_one_past_last_row);
 /* ncclAllGather of the radiance tiles: afterwards every rank holds the full frame (optional; collective). */

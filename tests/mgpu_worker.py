@@ -30,29 +30,39 @@ def main():
         s.n_luts = 2
         sub, base, first = sharding.shard_scene(s, world, rank)
         cap = max(sharding.object_range(len(s.objects), world, r)[1] - sharding.object_range(len(s.objects), world, r)[0] for r in range(world))
-        rt = from_scene(sub, device=local, max_n_objects=cap, max_n_clusters=max(sub.n_clusters, 1))
-        for i in range(8):
-            rt.color_lut_set(i, 0.1 * i, 1.0 - 0.1 * i, 0.5, lut_idx=1)
-        rt.set_shard(rank, world, base)
-        ids = [comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        rt.comm_init(ids[0], rank, world)
-        rt.set_gi(True, 5)
-        rt.clear()
-        rt.render()          # K1 -> min merge -> collective K2 -> resolve + reduce-scatter -> K3 on this rank's rows
-        rt.synchronize()
-        y0, y1 = rt.tile_rows()
-        assert (y0, y1) == sharding.tile_rows(s.height, world, rank)
-        vis = rt.read_visibility()
-        svo, nodes, leaf, vox = rt.svo_download()
-        rt.svo_free(svo)
-        rt.gather_radiance()
-        rt.synchronize()
-        rad = rt.read_radiance()
-        t = rt.timings()
-        assert t["merge_ms"] > 0
-        rt.comm_destroy()
-        rt.destroy()
+        results = {}
+        # both exchanges: 0 = one kernel over peer memory (CUDA IPC / NVLink), 1 = NCCL all-reduce + reduce-scatter
+        for kind in (0, 1):
+            rt = from_scene(sub, device=local, max_n_objects=cap, max_n_clusters=max(sub.n_clusters, 1))
+            for i in range(8):
+                rt.color_lut_set(i, 0.1 * i, 1.0 - 0.1 * i, 0.5, lut_idx=1)
+            rt.set_shard(rank, world, base)
+            ids = [comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            rt.comm_init(ids[0], rank, world)
+            rt.set_merge_kind(kind)
+            rt.set_gi(True, 5)
+            for _ in range(3):       # three frames: the peer-memory path alternates between its two buffer pairs
+                rt.clear()
+                rt.render()          # K1 -> merge -> collective K2 -> materials -> K3 on this rank's rows
+            rt.synchronize()
+            dist.barrier()
+            y0, y1 = rt.tile_rows()
+            assert (y0, y1) == sharding.tile_rows(s.height, world, rank)
+            vis = rt.read_visibility()
+            svo, nodes, leaf, vox = rt.svo_download()
+            rt.svo_free(svo)
+            rt.gather_radiance()
+            rt.synchronize()
+            rad = rt.read_radiance()
+            t = rt.timings()
+            assert t["merge_ms"] > 0
+            dist.barrier()
+            rt.comm_destroy()
+            rt.destroy()
+            results[kind] = (vis, nodes, leaf, vox, rad, t)
+        assert all(np.array_equal(a, b) for a, b in zip(results[0][:5], results[1][:5])), f"{name} rank {rank}: the peer-memory merge and the NCCL merge disagree"
+        vis, nodes, leaf, vox, rad, t = results[0]
 
         # reference: the whole scene on this GPU alone
         ref = from_scene(s, device=local)
@@ -72,7 +82,7 @@ def main():
                                f"{[(int(y), int(x), rad[y, x].tolist(), want_rad[y, x].tolist()) for y, x in bad[:3]]}")
         dist.barrier()
         if rank == 0:
-            print(f"MGPU_OK {name} world={world} tile_rows={y1 - y0} merge_ms={t['merge_ms']:.3f}", flush=True)
+            print(f"MGPU_OK {name} world={world} tile_rows={y1 - y0} merge_ms peer={results[0][5]['merge_ms']:.3f} nccl={results[1][5]['merge_ms']:.3f}", flush=True)
     dist.destroy_process_group()
 
 

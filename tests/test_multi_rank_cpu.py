@@ -31,7 +31,18 @@ assert np.array_equal(merged, whole), f"rank {rank}: {int((merged != whole).sum(
 hit = vis != np.uint64(0xFFFFFFFFFFFFFFFF)
 ptr = (vis[hit] >> np.uint64(9)) & np.uint64(0x7FFFFFFF)
 assert ptr.size and ptr.min() >= base and ptr.max() < base + sub.n_clusters, "a shard must only write its own global pointers"
+# the peer-memory merge (tgb_peer.cu): every rank takes min + winner over all ranks' LOCAL buffers for ITS tile only
+import torch
+gathered = [torch.zeros(vis.size, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(gathered, torch.from_numpy(vis.ravel().view(np.int64).copy()))
+all_vis = np.stack([g.numpy().view(np.uint64).reshape(vis.shape) for g in gathered])
+tile, who = sharding.merge_tile_from_peers(all_vis, rank, s.height, s.width)
 y0, y1 = sharding.tile_rows(s.height, world, rank)
+assert np.array_equal(tile, whole[y0:y1]), "the tile merged from the peers' buffers must equal the all-reduced rows"
+bases = [sharding.shard_scene(s, world, r)[1] for r in range(world)] + [s.n_clusters]
+tile_ptr = ((tile >> np.uint64(9)) & np.uint64(0x7FFFFFFF)).astype(np.int64)
+owner = np.searchsorted(np.asarray(bases[1:]), tile_ptr, side="right")
+assert np.array_equal(who[who >= 0], owner[who >= 0]), "the rank holding the minimum is the owner of the winning pointer (it supplies the material)"
 rows = np.zeros(s.height, dtype=np.int64); rows[y0:y1] = 1
 import torch
 t = torch.from_numpy(rows); dist.all_reduce(t)

@@ -60,7 +60,7 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMemsetAsync(d->d_objects, 0, no * sizeof(tg_object_data), d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_masks, 0, nc * 64, d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_color_lut, 0, (u64)d->n_color_luts * 256 * sizeof(u32), d->stream));
-    for (int i = 0; i < 12; i++) TGB_CUDA(cudaEventCreate(&d->ev[i]));
+    for (int i = 0; i < 16; i++) TGB_CUDA(cudaEventCreate(&d->ev[i]));
     TGB_CUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < TGB_MAX_BANDS; i++)
     {
@@ -95,6 +95,9 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     TGB_CUDA(cudaStreamSynchronize(d->stream));
     if (d->copy_stream) TGB_CUDA(cudaStreamSynchronize(d->copy_stream)); /* pending band copies read the buffers freed below */
     for (int i = 0; i < TGB_MAX_BANDS; i++) d->band_copy_pending[0][i] = d->band_copy_pending[1][i] = TG_FALSE;
+    tgbd_p2p_teardown(d); /* collective when peer memory is mapped (a resize is mirrored on every rank); d_vis / d_mat are [0] of their pairs again */
+    d->d_vis_pair[0] = NULL; d->d_mat_pair[0] = NULL;
+    d->vis_merged = TG_FALSE; d->tile_merged = TG_FALSE;
     if (d->n_ranks == 0) d->n_ranks = 1;
     d->tile_rows = (height + d->n_ranks - 1) / d->n_ranks;
     const u64 padded_px = (u64)width * d->tile_rows * d->n_ranks; /* >= width * height: equal tiles for the collectives */
@@ -179,6 +182,8 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaSetDevice(d->device);
     cudaStreamSynchronize(d->stream);
     if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
+    d->p_comm = NULL;       /* not collective here: the communicator's owner (tgb200_comm_destroy) ran the collective teardown */
+    tgbd_p2p_teardown(d);
     cudaFree(d->d_cluster_pointers); cudaFree(d->d_c2o); cudaFree(d->d_objects); cudaFree(d->d_masks);
     cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance_pair[0]); cudaFree(d->d_radiance_pair[1]); cudaFree(d->d_present_pair[0]); cudaFree(d->d_present_pair[1]); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_count);
     cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
@@ -188,7 +193,7 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch); cudaFree(d->svo.d_pair_flags); cudaFree(d->svo.d_object_flags); cudaFree(d->svo.d_pair_leaf_a); cudaFree(d->svo.d_pair_leaf_b);
     cudaFree(d->svo.d_voxels_alt); cudaFree(d->svo.d_leaf_data_alt); cudaFree(d->svo.d_object_moved); cudaFree(d->svo.d_moved_indices); cudaFree(d->svo.d_part); cudaFree(d->svo.d_gather);
     cudaFree(d->d_mat); cudaFree(d->d_mat_tile); cudaFree(d->d_objects_global); cudaFree(d->d_frames_global);
-    for (int i = 0; i < 12; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    for (int i = 0; i < 16; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     for (int i = 0; i < TGB_MAX_BANDS; i++) { if (d->ev_band[i]) cudaEventDestroy(d->ev_band[i]); if (d->ev_band_copied[0][i]) cudaEventDestroy(d->ev_band_copied[0][i]); if (d->ev_band_copied[1][i]) cudaEventDestroy(d->ev_band_copied[1][i]); }
     for (int i = 0; i < TGB_FRAME_RING; i++) if (d->ev_frame_copied[i]) cudaEventDestroy(d->ev_frame_copied[i]);
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
@@ -209,6 +214,7 @@ static b32 tgbd__buffer_range(struct tgb_device* d, u32 buffer, u8** pp, u64* p_
     case TGB_BUF_LUT_IDX:          *pp = (u8*)d->d_lut_idx;          *p_size = nc * 512; break;
     case TGB_BUF_COLOR_LUT:        *pp = (u8*)d->d_color_lut;        *p_size = (u64)d->n_color_luts * 1024; break;
     case TGB_BUF_VISIBILITY:       *pp = (u8*)d->d_vis;              *p_size = px * 8; break;
+    case TGB_BUF_VISIBILITY_MERGED: *pp = (u8*)tgbd_visibility_for_read(d); *p_size = px * 8; break;
     case TGB_BUF_RADIANCE:         *pp = (u8*)d->d_radiance;         *p_size = (u64)d->width * d->tile_rows * d->n_ranks * 16; break;
     case TGB_BUF_SVO_NODES:        *pp = (u8*)d->svo.d_nodes;        *p_size = (u64)d->svo.node_capacity * 4; break;
     case TGB_BUF_SVO_LEAF_DATA:    *pp = (u8*)d->svo.d_leaf_data;    *p_size = (u64)d->svo.leaf_capacity * 260; break;
@@ -301,6 +307,7 @@ extern "C" b32 tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n
 {
     TGB_CUDA(cudaSetDevice(d->device));
     TGB_CUDA(cudaStreamSynchronize(d->stream));
+    tgbd_p2p_teardown(d); /* with the OLD communicator still in place */
     d->p_comm = p_comm;
     d->rank = p_comm ? rank : 0;
     d->n_ranks = p_comm ? n_ranks : 1;
@@ -331,6 +338,14 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
     if (d->ev_svo)   cudaEventElapsedTime(&d->svo_ms, d->ev[5], d->ev[6]);
     if (d->ev_shade) cudaEventElapsedTime(&d->shading_ms, d->ev[7], d->ev[8]);
     if (d->ev_merge) cudaEventElapsedTime(&d->merge_ms, d->ev[9], d->ev[10]);
+    if (d->ev_merge && d->ev_merge_parts)
+    {
+        /* peer-memory merge: local material resolve | all-gather of the object records (= waiting for the slowest rank's K1) | k_merge_tile */
+        cudaEventElapsedTime(&d->merge_resolve_ms, d->ev[9], d->ev[11]);
+        cudaEventElapsedTime(&d->merge_gather_ms, d->ev[11], d->ev[12]);
+        cudaEventElapsedTime(&d->merge_kernel_ms, d->ev[12], d->ev[10]);
+    }
+    else d->merge_resolve_ms = d->merge_gather_ms = d->merge_kernel_ms = 0.0f;
     cudaGetLastError();
     p_out->clear_ms = d->clear_ms;
     p_out->cull_ms = d->cull_ms;
@@ -338,6 +353,10 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
     p_out->svo_ms = d->svo_ms;
     p_out->shading_ms = d->shading_ms;
     p_out->merge_ms = d->merge_ms;
+    p_out->merge_resolve_ms = d->merge_resolve_ms;
+    p_out->merge_gather_ms = d->merge_gather_ms;
+    p_out->merge_kernel_ms = d->merge_kernel_ms;
+    p_out->pad2 = 0;
     /* the counters live on the device during the frames (no per-frame read-back); fetch them now */
     if (d->ev_vis) { cudaMemcpy(d->h_visible_count, d->d_visible_count, 2 * sizeof(u32), cudaMemcpyDeviceToHost); d->n_visible_objects = d->h_visible_count[0]; }
     if (d->gi_stats_valid) cudaMemcpy(d->h_gi_stats, d->d_gi_count, 32 * sizeof(u32), cudaMemcpyDeviceToHost);
@@ -355,7 +374,7 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
     p_out->n_kernel_launches = d->n_kernel_launches;
 }
 
-extern "C" void tgbd_merge_begin(struct tgb_device* d) { cudaSetDevice(d->device); cudaEventRecord(d->ev[9], d->stream); }
+extern "C" void tgbd_merge_begin(struct tgb_device* d) { cudaSetDevice(d->device); cudaEventRecord(d->ev[9], d->stream); d->ev_merge_parts = TG_FALSE; }
 extern "C" void tgbd_merge_end(struct tgb_device* d) { cudaEventRecord(d->ev[10], d->stream); d->ev_merge = TG_TRUE; }
 
 /* (8*rel_x + vx) % 256, tgvk_raytracer.c:947-978; one thread per 16 voxels (uint4 stores) */

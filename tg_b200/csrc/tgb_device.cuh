@@ -22,6 +22,7 @@
 #define TGB_TOP_POINTER_MASK  0x0FFFFFFFu
 
 #define TGB_MAX_BANDS  16
+#define TGB_MAX_RANKS  16
 #define TGB_FRAME_RING 4
 
 struct tgb_svo_device
@@ -88,6 +89,21 @@ struct tgb_device
     u32               tile_rows;        /* ceil(height / n_ranks): rank r shades rows [r * tile_rows, (r + 1) * tile_rows) */
     u64*              d_mat;            /* [w * tile_rows * n_ranks] owner-resolved material words: global object idx << 32 | packed colour */
     u64*              d_mat_tile;       /* [w * tile_rows] this rank's tile after the reduce-scatter */
+    /* merge over peer memory (tgb_peer.cu): every rank maps the other ranks' visibility / material buffers (CUDA IPC over NVLink) and
+     * resolves ITS screen tile with one kernel: min over the ranks' words + the winner's material word. Both buffers are double
+     * buffered so that one collective per frame (the all-gather of the object records) is the only synchronisation. */
+    u32               merge_kind;       /* 0 = automatic: peer memory when it can be mapped, else NCCL; 1 = NCCL collectives */
+    b32               p2p_ready, p2p_failed;
+    b32               vis_merged;       /* d_vis holds the all-reduced words of the whole frame (tgb200_merge_visibility) */
+    b32               tile_merged;      /* d_vis_tile holds the merged words of this rank's tile (fused path); d_vis the local ones */
+    u64*              d_vis_tile;       /* [w * tile_rows] */
+    u32               vis_flip;
+    u64*              d_vis_pair[2];    /* [0] = the buffer tgbd_resize allocated, [1] on first use */
+    u64*              d_mat_pair[2];
+    u64*              peer_vis[2][TGB_MAX_RANKS]; /* [flip][rank]; own rank = local pointer */
+    u64*              peer_mat[2][TGB_MAX_RANKS];
+    u64*              d_vis_full;       /* whole merged frame pulled from the peers on demand (read-back, picking) */
+    u8*               d_ipc_stage;
     tg_object_data*   d_objects_global; /* [n_ranks * object_capacity] every rank's records, pointers globalised */
     tgb_object_frame* d_frames_global;
 
@@ -116,8 +132,9 @@ struct tgb_device
     cudaEvent_t  ev_frame_copied[TGB_FRAME_RING];
     u64          n_frames_sunk;     /* frames whose copies have been issued */
 
-    cudaEvent_t ev[12];
-    f32         clear_ms, cull_ms, visibility_ms, svo_ms, shading_ms, merge_ms;
+    cudaEvent_t ev[16];
+    f32         clear_ms, cull_ms, visibility_ms, svo_ms, shading_ms, merge_ms, merge_resolve_ms, merge_gather_ms, merge_kernel_ms;
+    b32         ev_merge_parts;
     b32         ev_clear, ev_vis, ev_svo, ev_shade, ev_merge;
     u32         n_visible_objects;
     u32         n_kernel_launches;

@@ -495,7 +495,9 @@ void tgb200_render_shading(tg_raytracer* p_raytracer)
     tgb200_camera_rays(p_raytracer->p_camera, &cam);
     if (tgbd_n_ranks(p_raytracer->p_device) > 1)
     {
-        /* multi-GPU: the buffer must be the MERGED one (tgb200_merge_visibility); this rank shades its screen tile */
+        /* multi-GPU: this rank shades its screen tile, from the all-reduced buffer (tgb200_merge_visibility was called) or, if not,
+         * from a tile merged over peer memory (collective set-up on first use) */
+        tgbd_p2p_prepare(p_raytracer->p_device);
         tgbd_render_shading_sharded(p_raytracer->p_device, &cam, p_raytracer->scene.n_cluster_pointers, p_raytracer->gi_enabled, p_raytracer->frame_seed,
                                     p_raytracer->debug_visualization);
         return;
@@ -511,7 +513,9 @@ void tg_raytracer_render(tg_raytracer* p_raytracer)
     /* tgvk_raytracer.c:1187-1217 builds the SVO on the first frame; here whenever it is stale and GI needs it */
     if (p_raytracer->gi_enabled) tgb200_svo_update(p_raytracer, TG_FALSE);
     tgb200_render_visibility(p_raytracer);
-    if (tgbd_n_ranks(p_raytracer->p_device) > 1) tgb200_merge_visibility(p_raytracer); /* ncclAllReduce(u64, min) over NVLink */
+    /* multi-GPU: the shading stage merges this rank's tile straight from the peers' buffers (tgb_peer.cu) when peer memory can be
+     * mapped; otherwise ncclAllReduce(u64, min) over the whole frame first */
+    if (tgbd_n_ranks(p_raytracer->p_device) > 1 && !tgbd_p2p_prepare(p_raytracer->p_device)) tgb200_merge_visibility(p_raytracer);
     tgb200_render_shading(p_raytracer);
 }
 
@@ -527,7 +531,7 @@ b32 tg_raytracer_get_hovered_voxel(tg_raytracer* p_raytracer, u32 screen_x, u32 
     TGB_REQUIRE(screen_x < p_raytracer->width && screen_y < p_raytracer->height, TG_FALSE, "get_hovered_voxel: pixel (%u,%u) outside %ux%u", screen_x, screen_y, p_raytracer->width, p_raytracer->height);
     u64 packed_data = TG_VIS_CLEAR;
     const u64 pixel_idx = (u64)p_raytracer->width * screen_y + screen_x;
-    if (!tgbd_download(p_raytracer->p_device, TGB_BUF_VISIBILITY, pixel_idx * 8, &packed_data, 8)) return TG_FALSE;
+    if (!tgbd_download(p_raytracer->p_device, TGB_BUF_VISIBILITY_MERGED, pixel_idx * 8, &packed_data, 8)) return TG_FALSE;
     /* tgvk_raytracer.c:1639-1654 */
     *p_depth = (f32)(packed_data >> 40) / 16777215.0f;
     if (*p_depth < 1.0f)
@@ -544,7 +548,7 @@ b32 tg_raytracer_get_hovered_voxel(tg_raytracer* p_raytracer, u32 screen_x, u32 
 void tg_raytracer_read_visibility(tg_raytracer* p_raytracer, u64* p_out)
 {
     if (!tgb__alive(p_raytracer, "tg_raytracer_read_visibility")) return;
-    tgbd_download(p_raytracer->p_device, TGB_BUF_VISIBILITY, 0, p_out, (u64)p_raytracer->width * p_raytracer->height * 8);
+    tgbd_download(p_raytracer->p_device, TGB_BUF_VISIBILITY_MERGED, 0, p_out, (u64)p_raytracer->width * p_raytracer->height * 8);
 }
 
 void tg_raytracer_write_visibility(tg_raytracer* p_raytracer, const u64* p_in)
@@ -743,12 +747,19 @@ void tgb200_tile_rows(tg_raytracer* p_raytracer, u32* p_first_row, u32* p_one_pa
     *p_one_past_last_row = y1 < p_raytracer->height ? y1 : p_raytracer->height;
 }
 
+void tgb200_set_merge_kind(tg_raytracer* p_raytracer, u32 kind)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_set_merge_kind")) return;
+    tgbd_set_merge_kind(p_raytracer->p_device, kind);
+}
+
 void tgb200_merge_visibility(tg_raytracer* p_raytracer)
 {
     if (!tgb__alive(p_raytracer, "tgb200_merge_visibility")) return;
     void* p_comm = tgbd_comm(p_raytracer->p_device);
     TGB_REQUIRE(p_comm != NULL, TGB_VOID, "tgb200_merge_visibility: no communicator (call tgb200_comm_init)");
     tgbd_merge_begin(p_raytracer->p_device);
-    tgbn_allreduce_min_u64(p_comm, tgbd_buffer(p_raytracer->p_device, TGB_BUF_VISIBILITY), (u64)p_raytracer->width * p_raytracer->height, tgbd_stream(p_raytracer->p_device));
+    if (tgbn_allreduce_min_u64(p_comm, tgbd_buffer(p_raytracer->p_device, TGB_BUF_VISIBILITY), (u64)p_raytracer->width * p_raytracer->height, tgbd_stream(p_raytracer->p_device)))
+        tgbd_note_merged(p_raytracer->p_device);
     tgbd_merge_end(p_raytracer->p_device);
 }

@@ -23,6 +23,7 @@ enum
     TGB_BUF_COLOR_LUT,            /* D6: u32[n_luts * 256] */
     TGB_BUF_VISIBILITY,           /* D7: u64[w*h] */
     TGB_BUF_RADIANCE,             /* RGBA32F[w*h] */
+    TGB_BUF_VISIBILITY_MERGED,    /* read-only view: the whole merged frame (== TGB_BUF_VISIBILITY on one GPU or after the all-reduce) */
     TGB_BUF_SVO_NODES,
     TGB_BUF_SVO_LEAF_DATA,
     TGB_BUF_SVO_VOXELS,
@@ -102,6 +103,13 @@ b32   tgbn_allreduce_min_u64(void* p_comm, void* p_device_buffer, u64 count, voi
 b32   tgbn_allreduce_sum_u32(void* p_comm, void* p_device_buffer, u64 count, void* p_stream);
 b32   tgbn_allgather_bytes(void* p_comm, const void* p_send, void* p_recv, u64 n_bytes, void* p_stream);
 b32   tgbn_reducescatter_max_u64(void* p_comm, const void* p_send, void* p_recv, u64 count_per_rank, void* p_stream);
+/* ---- tgb_peer.cu: merge over peer memory ---- */
+void  tgbd_set_merge_kind(struct tgb_device* d, u32 kind);
+b32   tgbd_p2p_prepare(struct tgb_device* d);   /* collective on first use; TG_TRUE when the fused path can run */
+void  tgbd_p2p_teardown(struct tgb_device* d);  /* collective: unmaps the peers' buffers (before they are freed) */
+void  tgbd_note_merged(struct tgb_device* d);   /* the all-reduce has run on the current buffer */
+void* tgbd_visibility_for_read(struct tgb_device* d); /* whole merged frame: pulls the other tiles from the peers if necessary */
+b32   tgbd_p2p_merge_tile(struct tgb_device* d);
 /* events around the merge live in tgb_device.cu */
 void  tgbd_merge_begin(struct tgb_device* d);
 void  tgbd_merge_end(struct tgb_device* d);

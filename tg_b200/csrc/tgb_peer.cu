@@ -1,0 +1,198 @@
+/*
+ * tgb_peer.cu -- the multi-GPU exchange of the frame as ONE kernel over peer memory (NVLink / NVSwitch).
+ *
+ * With NCCL alone a sharded frame needs two 66 MB collectives at 4K: ncclAllReduce(u64, min) over the visibility buffers, so
+ * that every rank learns which pixels it won, and ncclReduceScatter(u64, max) over the material words the winners then
+ * resolve (tgb_nccl.c; the 512 B / cluster material data exists on the owner only). But a rank only SHADES its own screen
+ * tile, so all it needs is, per pixel of that tile, the minimum of the ranks' words and the material word of the rank that
+ * holds the minimum. Here every rank resolves the material of its LOCAL winners right after K1 (k_resolve_material on the
+ * unmerged buffer: every hit is its own), maps the other ranks' visibility and material buffers into its address space
+ * (CUDA IPC handles, exchanged once through the communicator) and runs k_merge_tile: N coalesced 8-byte loads per pixel --
+ * N - 1 of them over NVLink -- a running min, one more load from the winner. 58 MB cross the switch per rank at N = 8
+ * instead of two all-to-all collectives, and nothing is written that another rank reads.
+ *
+ * Synchronisation: both buffers are double buffered (flipped by tgbd_clear), and the one collective that remains per frame
+ * -- the all-gather of the 96-byte object records, needed anyway because objects may have moved -- sits between K1 and the
+ * merge: a rank leaves it only after every rank has entered it, i.e. finished K1 + resolve of this frame and, in stream
+ * order, the merge of the previous frame (which read the OTHER buffer pair). The min is associative and commutative, so
+ * the merged tile is bit-identical to the all-reduce and to a single-GPU frame (tests/test_multi_gpu.py runs both paths).
+ * Peer loads use ld.volatile semantics (__ldcv): a word another GPU wrote this frame must not come from a stale line.
+ */
+#include "tgb_device.cuh"
+
+struct tgb_peer_table
+{
+    const u64* p_vis[TGB_MAX_RANKS];
+    const u64* p_mat[TGB_MAX_RANKS];
+};
+
+/* pixels [first, first + n) of the frame: merged word -> p_vis_out[first + i], winner's material word -> p_mat_out[i] (if any) */
+__global__ void __launch_bounds__(256) k_merge_tile(const tgb_peer_table t, u32 n_ranks, u64 first, u64 n, u64* __restrict__ p_vis_out, u64* __restrict__ p_mat_out, u64 n_mat_out)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mat_out && i >= n) return;
+    u64 best = TG_VIS_CLEAR, mat = 0;
+    if (i < n)
+    {
+        u32 who = 0;
+        for (u32 r = 0; r < n_ranks; r++)
+        {
+            const u64 w = __ldcv(&t.p_vis[r][first + i]);
+            if (w < best) { best = w; who = r; } /* shards own disjoint pointer ranges: two ranks never hold the same word */
+        }
+        if (best != TG_VIS_CLEAR && p_mat_out) mat = __ldcv(&t.p_mat[who][first + i]);
+        p_vis_out[first + i] = best;
+    }
+    if (p_mat_out && i < n_mat_out) p_mat_out[i] = mat; /* the padded tail of the last tile: no material */
+}
+
+extern "C" void tgbd_set_merge_kind(struct tgb_device* d, u32 kind) { d->merge_kind = kind; }
+extern "C" void tgbd_note_merged(struct tgb_device* d) { d->vis_merged = TG_TRUE; }
+
+static void tgbd__p2p_close(struct tgb_device* d)
+{
+    for (u32 f = 0; f < 2; f++)
+    {
+        for (u32 r = 0; r < TGB_MAX_RANKS; r++)
+        {
+            if (r != d->rank && d->peer_vis[f][r]) cudaIpcCloseMemHandle(d->peer_vis[f][r]);
+            if (r != d->rank && d->peer_mat[f][r]) cudaIpcCloseMemHandle(d->peer_mat[f][r]);
+            d->peer_vis[f][r] = NULL; d->peer_mat[f][r] = NULL;
+        }
+    }
+    cudaGetLastError();
+}
+
+/*
+ * Collective. Before a rank frees buffers its peers have mapped (resize, communicator teardown): every rank first finishes its
+ * own reads (stream sync), then a tiny all-reduce makes sure all of them did, then the mappings go.
+ */
+extern "C" void tgbd_p2p_teardown(struct tgb_device* d)
+{
+    if (!d->p2p_ready && !d->d_vis_pair[1] && !d->d_vis_full && !d->d_vis_tile) { d->p2p_failed = TG_FALSE; return; }
+    cudaSetDevice(d->device);
+    if (d->p2p_ready && d->p_comm && d->d_ipc_stage)
+    {
+        tgbn_allreduce_sum_u32(d->p_comm, d->d_ipc_stage, 1, d->stream);
+        cudaStreamSynchronize(d->stream);
+    }
+    tgbd__p2p_close(d);
+    /* back to the single buffers tgbd_resize owns */
+    if (d->d_vis_pair[1]) cudaFree(d->d_vis_pair[1]);
+    if (d->d_mat_pair[1]) cudaFree(d->d_mat_pair[1]);
+    if (d->d_vis_full) cudaFree(d->d_vis_full);
+    if (d->d_vis_tile) cudaFree(d->d_vis_tile);
+    if (d->d_ipc_stage) cudaFree(d->d_ipc_stage);
+    d->d_vis_pair[1] = NULL; d->d_mat_pair[1] = NULL; d->d_vis_full = NULL; d->d_vis_tile = NULL; d->d_ipc_stage = NULL;
+    if (d->d_vis_pair[0]) d->d_vis = d->d_vis_pair[0];
+    if (d->d_mat_pair[0]) d->d_mat = d->d_mat_pair[0];
+    d->vis_flip = 0;
+    d->p2p_ready = TG_FALSE; d->p2p_failed = TG_FALSE;
+    cudaGetLastError();
+}
+
+/*
+ * Collective on first use (every rank calls it at the same point of its frame): allocates the second buffer pair, exchanges the
+ * four IPC handles through the communicator, maps the peers' buffers. All ranks agree on the outcome (a sum of failure flags):
+ * if any mapping failed everywhere falls back to the NCCL collectives, which are the same function of the same inputs.
+ */
+extern "C" b32 tgbd_p2p_prepare(struct tgb_device* d)
+{
+    if (d->n_ranks < 2 || !d->p_comm || d->merge_kind == 1) return TG_FALSE;
+    if (d->p2p_ready) return TG_TRUE;
+    if (d->p2p_failed) return TG_FALSE;
+    if (d->n_ranks > TGB_MAX_RANKS) { d->p2p_failed = TG_TRUE; return TG_FALSE; }
+    TGB_CUDA(cudaSetDevice(d->device));
+    const u64 px = (u64)d->width * d->height, padded_px = (u64)d->width * d->tile_rows * d->n_ranks;
+    d->d_vis_pair[0] = d->d_vis; d->d_mat_pair[0] = d->d_mat; d->vis_flip = 0;
+    TGB_CUDA(cudaMalloc(&d->d_vis_pair[1], px * sizeof(u64)));
+    TGB_CUDA(cudaMalloc(&d->d_mat_pair[1], padded_px * sizeof(u64)));
+    TGB_CUDA(cudaMalloc(&d->d_vis_tile, (u64)d->width * d->tile_rows * sizeof(u64)));
+    TGB_CUDA(cudaMalloc(&d->d_ipc_stage, (u64)d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t)));
+    TGB_CUDA(cudaMemsetAsync(d->d_vis_pair[1], 0xFF, px * sizeof(u64), d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_mat_pair[1], 0, padded_px * sizeof(u64), d->stream));
+
+    cudaIpcMemHandle_t mine[4];
+    u32 n_failed = 0;
+    void* p_mine[4] = { d->d_vis_pair[0], d->d_vis_pair[1], d->d_mat_pair[0], d->d_mat_pair[1] };
+    for (int k = 0; k < 4; k++)
+    {
+        if (cudaIpcGetMemHandle(&mine[k], p_mine[k]) != cudaSuccess) { n_failed++; memset(&mine[k], 0, sizeof(mine[k])); cudaGetLastError(); }
+    }
+    cudaIpcMemHandle_t* p_all = (cudaIpcMemHandle_t*)malloc((size_t)d->n_ranks * sizeof(mine));
+    if (!p_all) { tgb_set_error("p2p_prepare: out of memory"); return TG_FALSE; }
+    TGB_CUDA(cudaMemcpyAsync(d->d_ipc_stage + (u64)d->rank * sizeof(mine), mine, sizeof(mine), cudaMemcpyHostToDevice, d->stream));
+    if (!tgbn_allgather_bytes(d->p_comm, d->d_ipc_stage + (u64)d->rank * sizeof(mine), d->d_ipc_stage, sizeof(mine), d->stream)) { free(p_all); return TG_FALSE; }
+    TGB_CUDA(cudaMemcpyAsync(p_all, d->d_ipc_stage, (u64)d->n_ranks * sizeof(mine), cudaMemcpyDeviceToHost, d->stream));
+    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    for (u32 r = 0; r < d->n_ranks; r++)
+    {
+        for (u32 k = 0; k < 4; k++)
+        {
+            void* p = NULL;
+            if (r == d->rank) p = p_mine[k];
+            else if (n_failed == 0 && cudaIpcOpenMemHandle(&p, p_all[r * 4u + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { p = NULL; n_failed++; cudaGetLastError(); }
+            if (k < 2) d->peer_vis[k][r] = (u64*)p; else d->peer_mat[k - 2][r] = (u64*)p;
+        }
+    }
+    free(p_all);
+    /* agree: the stage buffer's first word becomes the number of failed mappings over all ranks */
+    TGB_CUDA(cudaMemcpyAsync(d->d_ipc_stage, &n_failed, sizeof(u32), cudaMemcpyHostToDevice, d->stream));
+    if (!tgbn_allreduce_sum_u32(d->p_comm, d->d_ipc_stage, 1, d->stream)) return TG_FALSE;
+    u32 total_failed = 0;
+    TGB_CUDA(cudaMemcpyAsync(&total_failed, d->d_ipc_stage, sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
+    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    if (total_failed)
+    {
+        tgbd__p2p_close(d);
+        cudaFree(d->d_vis_pair[1]); cudaFree(d->d_mat_pair[1]); cudaFree(d->d_vis_tile);
+        d->d_vis_pair[1] = NULL; d->d_mat_pair[1] = NULL; d->d_vis_tile = NULL;
+        d->p2p_failed = TG_TRUE;
+        if (getenv("TGB200_VERBOSE")) fprintf(stderr, "[tgb200] rank %u: peer memory unavailable (%u failed mappings), using the NCCL collectives\n", d->rank, total_failed);
+        return TG_FALSE;
+    }
+    d->p2p_ready = TG_TRUE;
+    return TG_TRUE;
+}
+
+static tgb_peer_table tgbd__peer_table(struct tgb_device* d)
+{
+    tgb_peer_table t;
+    for (u32 r = 0; r < TGB_MAX_RANKS; r++)
+    {
+        t.p_vis[r] = r < d->n_ranks ? d->peer_vis[d->vis_flip][r] : NULL;
+        t.p_mat[r] = r < d->n_ranks ? d->peer_mat[d->vis_flip][r] : NULL;
+    }
+    return t;
+}
+
+/* this rank's tile: merged words into d_vis_tile, the winners' material words into d_mat_tile (asynchronous on the stream) */
+extern "C" b32 tgbd_p2p_merge_tile(struct tgb_device* d)
+{
+    if (!d->p2p_ready) { tgb_set_error("p2p_merge_tile: peer memory is not mapped"); return TG_FALSE; }
+    const u64 px = (u64)d->width * d->height, tile_px = (u64)d->width * d->tile_rows;
+    const u64 first = (u64)d->rank * tile_px;
+    const u64 n = first < px ? (first + tile_px <= px ? tile_px : px - first) : 0;
+    /* d_vis keeps this rank's LOCAL words (the peers read them, and a re-render without a clear must find them): the merged tile
+     * goes to its own buffer, addressed with whole-frame pixel indices like d_vis */
+    k_merge_tile<<<(u32)((tile_px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), d->n_ranks, first, n, d->d_vis_tile - first, d->d_mat_tile, tile_px);
+    TGB_LAUNCH_CHECK(d);
+    d->tile_merged = TG_TRUE;
+    return TG_TRUE;
+}
+
+/*
+ * The whole merged frame for a read-back or a pick. After the all-reduce that is d_vis itself; on the fused path d_vis holds this
+ * rank's local words and only the tile was merged, so the frame is pulled from the peers into a separate buffer. Valid while the
+ * peers have finished K1 of this frame and not cleared this buffer again (they render in lock-step; call it between frames).
+ */
+extern "C" void* tgbd_visibility_for_read(struct tgb_device* d)
+{
+    if (d->n_ranks < 2 || d->vis_merged || !d->p2p_ready) return d->d_vis;
+    if (cudaSetDevice(d->device) != cudaSuccess) return d->d_vis;
+    const u64 px = (u64)d->width * d->height;
+    if (!d->d_vis_full && cudaMalloc(&d->d_vis_full, px * sizeof(u64)) != cudaSuccess) { tgb_set_error("visibility_for_read: out of device memory"); return d->d_vis; }
+    k_merge_tile<<<(u32)((px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), d->n_ranks, 0, px, d->d_vis_full, NULL, 0);
+    d->n_kernel_launches++;
+    return d->d_vis_full;
+}

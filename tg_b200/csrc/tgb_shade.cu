@@ -284,8 +284,15 @@ __device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px,
             c.x = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
             c.y = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
             c.z = tgb_xorshift32_range(&rng, -1.0f, 1.0f);
+            /* The shader normalises every candidate and tests dot(c, normal) > 0. The sign of that dot product is the sign of
+             * dot(raw, normal) whenever the latter is clear of rounding: |raw| <= sqrt(3), |normal| = 1, so the un-normalised
+             * sum carries an error below 5e-7 and, divided by the length, the normalised one is off by less than 4e-7 -- a
+             * candidate with s < -1e-5 is rejected by the shader too, one with s > 1e-5 accepted, and only the sliver in
+             * between (and NaN) needs the shader's own comparison. Half of the candidates skip the square root and divisions. */
+            const f32 s = (c.x * normal_ws.x + c.y * normal_ws.y) + c.z * normal_ws.z;
+            if (s < -1e-5f) continue;
             c = tgb_normalize(c);
-            if (tgb_dot(c, normal_ws) > 0.0f) { dir = c; break; }
+            if (s > 1e-5f || tgb_dot(c, normal_ws) > 0.0f) { dir = c; break; }
         }
         const v3 origin = tgb_add(hit_position_ws, tgb_scale(dir, 1.73205080757f));
         /* svo_functions.inc:27-31: a ray that misses the root box is unoccluded; only the others are traced */
@@ -972,7 +979,8 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     const bool present = d->p_sink && d->sink_format == TGB200_SINK_BGRA8;
     if (present && !tgbd__present_buffer(d, buf)) return TG_FALSE;
     tgb_shade_args a;
-    a.p_vis = d->d_vis;
+    /* after the peer-memory merge the merged words of this rank's tile live in d_vis_tile, addressed with whole-frame pixel indices */
+    a.p_vis = (resolved && d->tile_merged && !d->vis_merged) ? d->d_vis_tile - (u64)d->rank * d->tile_rows * d->width : d->d_vis;
     a.p_out = d->d_radiance;
     a.p_cluster_pointers = d->d_cluster_pointers;
     a.p_c2o = d->d_c2o;
@@ -1110,23 +1118,52 @@ extern "C" b32 tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera
         tgb_set_error("render_shading: GI is enabled but no SVO has been built (call tgb200_svo_update on every rank)");
         return TG_FALSE;
     }
-    TGB_CUDA(cudaEventRecord(d->ev[7], d->stream));
     const u32 cap = d->object_capacity, n_global = cap * d->n_ranks;
     const v3 camera = tgb_v3(p_cam->camera.x, p_cam->camera.y, p_cam->camera.z);
-
-    /* replicate the object records (96 B each) of every shard; pointers globalised by the owner */
-    k_globalize_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->d_objects_global + (u64)d->rank * cap);
-    TGB_LAUNCH_CHECK(d);
-    if (!tgbn_allgather_bytes(d->p_comm, d->d_objects_global + (u64)d->rank * cap, d->d_objects_global, (u64)cap * sizeof(tg_object_data), d->stream)) return TG_FALSE;
-    k_object_frames<<<(n_global + 127) / 128, 128, 0, d->stream>>>(d->d_objects_global, n_global, camera, d->d_frames_global);
-    TGB_LAUNCH_CHECK(d);
-
-    /* owner resolves the material of every pixel it won, max-reduce-scatter by screen tile */
     const u64 n_pixels = (u64)d->width * d->height, tile_px = (u64)d->width * d->tile_rows, n_padded = tile_px * d->n_ranks;
-    k_resolve_material<<<(u32)((n_padded + 255) / 256), 256, 0, d->stream>>>(d->d_vis, n_pixels, n_padded, d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_lut_idx,
-                                                                             d->d_color_lut, d->global_pointer_base, n_local_pointers, d->rank * cap, d->d_mat);
-    TGB_LAUNCH_CHECK(d);
-    if (!tgbn_reducescatter_max_u64(d->p_comm, d->d_mat, d->d_mat_tile, tile_px, d->stream)) return TG_FALSE;
+    const bool fused = !d->vis_merged;
+    if (fused && !d->p2p_ready)
+    {
+        tgb_set_error("render_shading: the visibility buffer is not merged (call tgb200_merge_visibility on every rank, or let tg_raytracer_render pick the peer-memory merge)");
+        return TG_FALSE;
+    }
+    if (fused)
+    {
+        /* merge over peer memory (tgb_peer.cu): material of the LOCAL winners, then the one collective of the frame -- the all-gather
+         * of the object records, which doubles as the barrier "every rank has finished K1 + resolve" -- then min + winner's material
+         * for this rank's tile straight from the peers' buffers. Timed as the merge stage. */
+        tgbd_merge_begin(d);
+        k_resolve_material<<<(u32)((n_padded + 255) / 256), 256, 0, d->stream>>>(d->d_vis, n_pixels, n_padded, d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_lut_idx,
+                                                                                 d->d_color_lut, d->global_pointer_base, n_local_pointers, d->rank * cap, d->d_mat);
+        TGB_LAUNCH_CHECK(d);
+        k_globalize_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->d_objects_global + (u64)d->rank * cap);
+        TGB_LAUNCH_CHECK(d);
+        TGB_CUDA(cudaEventRecord(d->ev[11], d->stream));
+        if (!tgbn_allgather_bytes(d->p_comm, d->d_objects_global + (u64)d->rank * cap, d->d_objects_global, (u64)cap * sizeof(tg_object_data), d->stream)) return TG_FALSE;
+        TGB_CUDA(cudaEventRecord(d->ev[12], d->stream));
+        if (!tgbd_p2p_merge_tile(d)) return TG_FALSE;
+        tgbd_merge_end(d);
+        d->ev_merge_parts = TG_TRUE;
+        TGB_CUDA(cudaEventRecord(d->ev[7], d->stream));
+        k_object_frames<<<(n_global + 127) / 128, 128, 0, d->stream>>>(d->d_objects_global, n_global, camera, d->d_frames_global);
+        TGB_LAUNCH_CHECK(d);
+    }
+    else
+    {
+        TGB_CUDA(cudaEventRecord(d->ev[7], d->stream));
+        /* replicate the object records (96 B each) of every shard; pointers globalised by the owner */
+        k_globalize_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->d_objects_global + (u64)d->rank * cap);
+        TGB_LAUNCH_CHECK(d);
+        if (!tgbn_allgather_bytes(d->p_comm, d->d_objects_global + (u64)d->rank * cap, d->d_objects_global, (u64)cap * sizeof(tg_object_data), d->stream)) return TG_FALSE;
+        k_object_frames<<<(n_global + 127) / 128, 128, 0, d->stream>>>(d->d_objects_global, n_global, camera, d->d_frames_global);
+        TGB_LAUNCH_CHECK(d);
+
+        /* owner resolves the material of every pixel it won, max-reduce-scatter by screen tile */
+        k_resolve_material<<<(u32)((n_padded + 255) / 256), 256, 0, d->stream>>>(d->d_vis, n_pixels, n_padded, d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_lut_idx,
+                                                                                 d->d_color_lut, d->global_pointer_base, n_local_pointers, d->rank * cap, d->d_mat);
+        TGB_LAUNCH_CHECK(d);
+        if (!tgbn_reducescatter_max_u64(d->p_comm, d->d_mat, d->d_mat_tile, tile_px, d->stream)) return TG_FALSE;
+    }
 
     /* GI + shading of this rank's rows */
     const u32 y0 = d->rank * d->tile_rows;

@@ -37,6 +37,14 @@ __global__ void k_clear_visibility(ulonglong2* __restrict__ p_vis2, u64 n_pairs,
 extern "C" b32 tgbd_clear(struct tgb_device* d)
 {
     TGB_CUDA(cudaSetDevice(d->device));
+    if (d->p2p_ready)
+    {
+        /* merge over peer memory (tgb_peer.cu): the peers may still read last frame's words, this frame goes to the other pair */
+        d->vis_flip ^= 1u;
+        d->d_vis = d->d_vis_pair[d->vis_flip];
+        d->d_mat = d->d_mat_pair[d->vis_flip];
+    }
+    d->vis_merged = TG_FALSE; d->tile_merged = TG_FALSE;
     const u64 n = (u64)d->width * d->height;
     TGB_CUDA(cudaEventRecord(d->ev[0], d->stream));
     k_clear_visibility<<<(u32)((n / 2 + 255) / 256) + 1, 256, 0, d->stream>>>((ulonglong2*)d->d_vis, n / 2, d->d_vis, n);

@@ -194,6 +194,10 @@ class Raytracer:
         self._lib.tgb200_comm_init(C.byref(self._rt), buf, rank, n_ranks)
         self._check()
 
+    def set_merge_kind(self, kind):
+        """0 = merge over peer memory when it can be mapped (default), 1 = NCCL collectives only."""
+        self._lib.tgb200_set_merge_kind(C.byref(self._rt), kind)
+
     def merge_visibility(self):
         self._lib.tgb200_merge_visibility(C.byref(self._rt))
 

@@ -147,9 +147,11 @@ def config1(k=3, width=1280, height=720, dims=(16, 16, 16), with_materials=True)
 
 
 def grid_scene(name, grid_x, grid_z, width, height, k=3, pitch_units=192.0, dims=(16, 8, 16), first_object=0, n_objects=None,
-               with_bits=True):
+               with_bits=True, owner=None):
     """Objects on a grid_x x grid_z XZ lattice centred on the origin, y = 0 (configs 2-5). with_bits=False leaves the masks to
-    the device generator (tg_raytracer_create_object_synthetic with the same seed idx + 1 and k): same bits, no host array."""
+    the device generator (tg_raytracer_create_object_synthetic with the same seed idx + 1 and k): same bits, no host array.
+    owner=(rank, n_ranks) keeps the objects of one rank of an interleaved multi-GPU partition (seed, angle and position still
+    follow the global lattice index)."""
     total = grid_x * grid_z
     if n_objects is None:
         n_objects = total - first_object
@@ -157,6 +159,8 @@ def grid_scene(name, grid_x, grid_z, width, height, k=3, pitch_units=192.0, dims
     objs = []
     for idx in range(first_object, first_object + n_objects):
         i, j = idx % grid_x, idx // grid_x
+        if owner is not None and (i + j) % owner[1] != owner[0]:
+            continue  # interleaved ownership: rank r of n holds the lattice cells with (i + j) % n == r, 1/n of every neighbourhood
         cx = (i - (grid_x - 1) / 2.0) * pitch_units
         cz = (j - (grid_z - 1) / 2.0) * pitch_units
         objs.append(ObjectSpec(center=(cx, 0.0, cz), extent=(dims[0] * 8, dims[1] * 8, dims[2] * 8), angle=reference_object_angle(idx),
@@ -171,10 +175,12 @@ def config2(width=3840, height=2160, grid=32, k=3):
 
 
 def config5_shard(rank, n_ranks, width=3840, height=2160, k=3):
-    """BASELINE configs[4]: rank's contiguous slice of a 384 x (32 n_ranks) lattice of 16x8x16-cluster objects -- 12,288 objects
+    """BASELINE configs[4]: rank's share of a 384 x (32 n_ranks) lattice of 16x8x16-cluster objects -- 12,288 objects
     = 25,165,824 clusters = 1.29e10 voxels per rank; 8 ranks = 98,304 objects, 201,326,592 clusters, 1.03e11 voxels (SURVEY.md
-    section 8d). The masks are generated on the device (seed = global object index + 1), nothing of that size exists on the host."""
-    return grid_scene(f"config5_x{n_ranks}", 384, 32 * n_ranks, width, height, k=k, first_object=rank * 12288, n_objects=12288, with_bits=False)
+    section 8d). Ownership is interleaved over the lattice ((i + j) % n_ranks), so every rank holds an equal part of whatever the
+    camera sees; a rank's objects are a contiguous range of GLOBAL cluster pointers (rank-major pointer space). The masks are
+    generated on the device (seed = global lattice index + 1), nothing of that size exists on the host."""
+    return grid_scene(f"config5_x{n_ranks}", 384, 32 * n_ranks, width, height, k=k, with_bits=False, owner=(rank, n_ranks))
 
 
 def small_grid(grid=3, width=320, height=180, k=3, dims=(4, 2, 4)):

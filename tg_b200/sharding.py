@@ -38,3 +38,16 @@ def allreduce_min_u64(vis, group=None):
     t = torch.from_numpy((vis ^ np.uint64(1 << 63)).view(np.int64).copy())
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return t.numpy().view(np.uint64) ^ np.uint64(1 << 63)
+
+
+def merge_tile_from_peers(all_vis, rank, height, width):
+    """The peer-memory merge of tg_b200/csrc/tgb_peer.cu stated on the host: `all_vis` = every rank's LOCAL buffer
+    [n_ranks, h, w] (what k_merge_tile reads over NVLink); returns (merged words of this rank's tile rows, winner rank per pixel
+    or -1). min is associative, so the tile equals the same rows of the all-reduced frame."""
+    n_ranks = all_vis.shape[0]
+    y0, y1 = tile_rows(height, n_ranks, rank)
+    tile = all_vis[:, y0:y1]
+    who = np.argmin(tile, axis=0)          # first rank holding the minimum, like the kernel's strict `<`
+    best = np.take_along_axis(tile, who[None], axis=0)[0]
+    who = np.where(best == np.uint64(0xFFFFFFFFFFFFFFFF), -1, who)
+    return best, who
