@@ -11,7 +11,7 @@ secondary ray per hit pixel through the replicated 1-bit SVO). The SVO (K2) is b
 the reference builds it on its first frame (tgvk_raytracer.c:1187-1217); its build time is reported beside the frame.
 N=1 workload = BASELINE configs[1]/[2]: 1,024 objects, 2^21 clusters (1.07e9 voxels), 4K. At N>1 every rank owns one
 such 1,024-object shard of an N-times larger world (weak scaling), traces the full 4K frame against its shard, and
-shades 1/N of the rows. `value` = rays all ranks traced per second: N * W*H primary + one GI ray per hit pixel.
+shades 1/N of the rows (16-row bands dealt out to the ranks). `value` = rays all ranks traced per second: N * W*H primary + one GI ray per hit pixel.
 `--impl reference` times the CPU path (the oracle port of the reference's shader logic; the reference itself is
 Win32/Vulkan-only and cannot run here) on a bounded scanline sample of the same workload, rank 0 only.
 """
@@ -433,7 +433,7 @@ def main():
         rt.svo_free(svo)
     except Exception:
         pass
-    tile_px = WIDTH * (y1 - y0)
+    tile_px = WIDTH * int((rt.tile_physical_rows() >= 0).sum())  # the rows this rank shades (16-row bands dealt out to the ranks)
     gi_bytes = tile_px * ALG_BYTES_PER_PIXEL_GI + n_objects * world * ALG_BYTES_PER_OBJECT + svo_bytes
     gi_ms = stage["shading_ms"] / args.steps
     vis_bytes = n_clusters * ALG_BYTES_PER_CLUSTER + n_objects * ALG_BYTES_PER_OBJECT + WIDTH * HEIGHT * ALG_BYTES_PER_PIXEL_VIS

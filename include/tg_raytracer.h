@@ -170,7 +170,7 @@ TG_EXPORT void tgb200_synchronize(tg_raytracer* p_raytracer);
 /* Copies of results into caller memory (synchronous). */
 TG_EXPORT void tg_raytracer_read_visibility(tg_raytracer* p_raytracer, u64* p_out /* w*h */);
 TG_EXPORT void tg_raytracer_read_radiance(tg_raytracer* p_raytracer, f32* p_out /* w*h*4, RGBA32F */);
-/* Rows [first_row, one_past_last_row) only, e.g. the tile this rank shaded (tgb200_tile_rows); p_out receives those rows. */
+/* Frame rows [first_row, one_past_last_row) only; p_out receives those rows. */
 TG_EXPORT void tg_raytracer_read_radiance_rows(tg_raytracer* p_raytracer, u32 first_row, u32 one_past_last_row, f32* p_out);
 /* Replaces the device visibility buffer (tests: feed an oracle-made buffer to the shading stage). */
 TG_EXPORT void tg_raytracer_write_visibility(tg_raytracer* p_raytracer, const u64* p_in /* w*h */);
@@ -205,7 +205,8 @@ typedef struct tgb200_timings
 TG_EXPORT void tgb200_get_timings(tg_raytracer* p_raytracer, tgb200_timings* p_out);
 TG_EXPORT void tgb200_reset_launch_counter(tg_raytracer* p_raytracer);
 
-/* Raw device pointers + stream (for zero-copy interop, e.g. wrapping in a torch tensor). */
+/* Raw device pointers + stream (for zero-copy interop, e.g. wrapping in a torch tensor). Multi-GPU: the buffers are padded to whole
+ * 16-row bands and keep rows in tile order, rank-major (tgb200_tile_rows); on one GPU that is frame order. */
 TG_EXPORT void* tgb200_device_visibility(tg_raytracer* p_raytracer);
 TG_EXPORT void* tgb200_device_radiance(tg_raytracer* p_raytracer);
 TG_EXPORT void* tgb200_stream(tg_raytracer* p_raytracer);
@@ -231,8 +232,17 @@ TG_EXPORT void tgb200_merge_visibility(tg_raytracer* p_raytracer);
  * lock-step), tgb200_merge_visibility still produces it in place.
  */
 TG_EXPORT void tgb200_set_merge_kind(tg_raytracer* p_raytracer, u32 kind);
-/* Rows [first, one_past_last) of the frame this rank shades (GI rays are split by screen tile); the whole frame on one GPU. */
+/*
+ * The rows this rank shades. GI rays are split by screen tile; to give every rank an equal share of the hit pixels the frame is
+ * cut into bands of 16 rows and band b belongs to rank b mod n_ranks (tg_b200/csrc/tgb_rows.h). A rank's rows are numbered
+ * [first, one_past_last) in "tile order" -- its bands one after the other; tile order is what the frame sink delivers and what
+ * tgb200_gather_radiance exchanges. tgb200_tile_physical_row maps the i-th row of this rank's tile (0 <= i < one_past_last - first)
+ * to the frame row it shows, or TG_U32_MAX for a padding row (the last band of the frame may be partial, the last ranks may own
+ * one band less). On one GPU the tile is the whole frame, [0, height), in frame order. The read_* / write_* / get_hovered_voxel
+ * entry points always speak frame rows.
+ */
 TG_EXPORT void tgb200_tile_rows(tg_raytracer* p_raytracer, u32* p_first_row, u32* p_one_past_last_row);
+TG_EXPORT u32  tgb200_tile_physical_row(tg_raytracer* p_raytracer, u32 tile_row);
 /* ncclAllGather of the radiance tiles: afterwards every rank holds the full frame (optional; collective). */
 TG_EXPORT void tgb200_gather_radiance(tg_raytracer* p_raytracer);
 /* Marks the replicated SVO stale on a rank that does not own the object another rank moved (scene edits are mirrored

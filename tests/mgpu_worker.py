@@ -49,6 +49,7 @@ def main():
             dist.barrier()
             y0, y1 = rt.tile_rows()
             assert (y0, y1) == sharding.tile_rows(s.height, world, rank)
+            assert np.array_equal(rt.tile_physical_rows(), sharding.tile_physical_rows(s.height, world, rank))
             vis = rt.read_visibility()
             svo, nodes, leaf, vox = rt.svo_download()
             rt.svo_free(svo)

@@ -37,13 +37,14 @@ gathered = [torch.zeros(vis.size, dtype=torch.int64) for _ in range(world)]
 dist.all_gather(gathered, torch.from_numpy(vis.ravel().view(np.int64).copy()))
 all_vis = np.stack([g.numpy().view(np.uint64).reshape(vis.shape) for g in gathered])
 tile, who = sharding.merge_tile_from_peers(all_vis, rank, s.height, s.width)
-y0, y1 = sharding.tile_rows(s.height, world, rank)
-assert np.array_equal(tile, whole[y0:y1]), "the tile merged from the peers' buffers must equal the all-reduced rows"
+my_rows = sharding.tile_physical_rows(s.height, world, rank)
+my_rows = my_rows[my_rows >= 0]
+assert np.array_equal(tile, whole[my_rows]), "the tile merged from the peers' buffers must equal the all-reduced rows"
 bases = [sharding.shard_scene(s, world, r)[1] for r in range(world)] + [s.n_clusters]
 tile_ptr = ((tile >> np.uint64(9)) & np.uint64(0x7FFFFFFF)).astype(np.int64)
 owner = np.searchsorted(np.asarray(bases[1:]), tile_ptr, side="right")
 assert np.array_equal(who[who >= 0], owner[who >= 0]), "the rank holding the minimum is the owner of the winning pointer (it supplies the material)"
-rows = np.zeros(s.height, dtype=np.int64); rows[y0:y1] = 1
+rows = np.zeros(s.height, dtype=np.int64); rows[my_rows] = 1
 import torch
 t = torch.from_numpy(rows); dist.all_reduce(t)
 assert (t.numpy() == 1).all(), "screen tiles must partition the rows"
@@ -66,8 +67,13 @@ def test_object_ranges_partition_the_scene():
     bases = [sharding.shard_scene(s, 4, r)[1] for r in range(4)]
     assert bases == sorted(bases) and bases[0] == 0
     assert sum(sharding.shard_scene(s, 4, r)[0].n_clusters for r in range(4)) == s.n_clusters
-    assert [sharding.tile_rows(2160, 8, r) for r in (0, 7)] == [(0, 270), (1890, 2160)]
-    assert sharding.tile_rows(10, 4, 3) == (9, 10) and sharding.tile_rows(10, 8, 7) == (10, 10)
+    # screen tiles: 16-row bands dealt out to the ranks; tiles are whole bands, equal for every rank, and partition the rows
+    assert sharding.tile_row_count(2160, 8) == 272 and [sharding.tile_rows(2160, 8, r) for r in (0, 7)] == [(0, 272), (1904, 2176)]
+    assert sharding.tile_rows(2160, 1, 0) == (0, 2160) and np.array_equal(sharding.tile_physical_rows(7, 1, 0), np.arange(7))
+    assert sharding.tile_physical_rows(2160, 8, 3)[:18].tolist() == list(range(48, 64)) + [176, 177]
+    for h, n in ((2160, 8), (2160, 4), (177, 2), (10, 4), (33, 8)):
+        owned = np.concatenate([sharding.tile_physical_rows(h, n, r) for r in range(n)])
+        assert len(owned) == n * sharding.tile_row_count(h, n) and sorted(owned[owned >= 0].tolist()) == list(range(h))
 
 
 def test_min_merge_of_sharded_oracle_frames_world_size_2(tmp_path):

@@ -78,6 +78,7 @@ SYMBOLS = {
     "tgb200_merge_visibility": (None, [_RT]),
     "tgb200_set_merge_kind": (None, [_RT, T.u32]),
     "tgb200_tile_rows": (None, [_RT, _P(T.u32), _P(T.u32)]),
+    "tgb200_tile_physical_row": (T.u32, [_RT, T.u32]),
     "tgb200_gather_radiance": (None, [_RT]),
     "tgb200_mark_svo_dirty": (None, [_RT]),
     "tgb200_scene_init": (None, [_P(T.tg_scene), T.u32, T.u32]),

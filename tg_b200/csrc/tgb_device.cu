@@ -99,8 +99,8 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     d->d_vis_pair[0] = NULL; d->d_mat_pair[0] = NULL;
     d->vis_merged = TG_FALSE; d->tile_merged = TG_FALSE;
     if (d->n_ranks == 0) d->n_ranks = 1;
-    d->tile_rows = (height + d->n_ranks - 1) / d->n_ranks;
-    const u64 padded_px = (u64)width * d->tile_rows * d->n_ranks; /* >= width * height: equal tiles for the collectives */
+    d->tile_rows = tgb_tile_rows_for(height, d->n_ranks);
+    const u64 padded_px = (u64)width * d->tile_rows * d->n_ranks; /* >= width * height: whole bands, equal tiles; every frame buffer has this many pixels (tgb_rows.h) */
     if (d->d_mat) TGB_CUDA(cudaFree(d->d_mat));
     if (d->d_mat_tile) TGB_CUDA(cudaFree(d->d_mat_tile));
     d->d_mat = NULL; d->d_mat_tile = NULL;
@@ -124,13 +124,13 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     d->d_gi_q0 = d->d_gi_q1 = d->d_gi_q2 = NULL;
     d->width = width;
     d->height = height;
-    TGB_CUDA(cudaMalloc(&d->d_vis, (u64)width * height * sizeof(u64)));
+    TGB_CUDA(cudaMalloc(&d->d_vis, padded_px * sizeof(u64)));
     TGB_CUDA(cudaMalloc(&d->d_radiance_pair[0], padded_px * sizeof(float4)));
     d->d_radiance = d->d_radiance_pair[0];
     TGB_CUDA(cudaMalloc(&d->d_gi_q0, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMalloc(&d->d_gi_q1, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMalloc(&d->d_gi_q2, (u64)width * height * sizeof(float4)));
-    TGB_CUDA(cudaMemsetAsync(d->d_vis, 0xFF, (u64)width * height * sizeof(u64), d->stream));
+    TGB_CUDA(cudaMemsetAsync(d->d_vis, 0xFF, padded_px * sizeof(u64), d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_radiance, 0, padded_px * sizeof(float4), d->stream));
     return TG_TRUE;
 }
@@ -204,7 +204,7 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
 
 static b32 tgbd__buffer_range(struct tgb_device* d, u32 buffer, u8** pp, u64* p_size)
 {
-    const u64 nc = d->cluster_capacity, no = d->object_capacity, px = (u64)d->width * d->height;
+    const u64 nc = d->cluster_capacity, no = d->object_capacity, px = (u64)d->width * d->tile_rows * (d->n_ranks ? d->n_ranks : 1); /* padded frame, virtual row order */
     switch (buffer)
     {
     case TGB_BUF_CLUSTER_POINTERS: *pp = (u8*)d->d_cluster_pointers; *p_size = nc * 4; break;
@@ -323,6 +323,7 @@ extern "C" b32 tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n
 }
 
 extern "C" u32 tgbd_tile_rows(struct tgb_device* d) { return d->tile_rows; }
+extern "C" u64 tgbd_padded_pixels(struct tgb_device* d) { return (u64)d->width * d->tile_rows * (d->n_ranks ? d->n_ranks : 1); }
 extern "C" void* tgbd_comm(struct tgb_device* d) { return d->p_comm; }
 extern "C" u32 tgbd_rank(struct tgb_device* d) { return d->rank; }
 extern "C" u32 tgbd_n_ranks(struct tgb_device* d) { return d->n_ranks ? d->n_ranks : 1; }

@@ -13,6 +13,7 @@
 #include "tgb_internal.h"
 #include "tgb_math.h"
 #include "tgb_hoist.h"
+#include "tgb_rows.h"
 
 /* the flattened tree (k_svo_flatten, tgb_svo.cu): one word per 32^3 cell of the 1024^3 box */
 #define TGB_TOP_GRID_DIM      32u
@@ -86,7 +87,7 @@ struct tgb_device
     /* multi-GPU (one process per GPU): clusters sharded by object, SVO / objects replicated, GI split by screen tile */
     void*             p_comm;           /* NCCL communicator or NULL */
     u32               rank, n_ranks;
-    u32               tile_rows;        /* ceil(height / n_ranks): rank r shades rows [r * tile_rows, (r + 1) * tile_rows) */
+    u32               tile_rows;        /* tgb_rows.h: rank r shades VIRTUAL rows [r * tile_rows, (r + 1) * tile_rows) = the 16-row bands b with b mod n_ranks == r */
     u64*              d_mat;            /* [w * tile_rows * n_ranks] owner-resolved material words: global object idx << 32 | packed colour */
     u64*              d_mat_tile;       /* [w * tile_rows] this rank's tile after the reduce-scatter */
     /* merge over peer memory (tgb_peer.cu): every rank maps the other ranks' visibility / material buffers (CUDA IPC over NVLink) and

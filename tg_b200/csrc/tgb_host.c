@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "tgb_internal.h"
+#include "tgb_rows.h"
 #include "tgb_math.h"
 
 /* ---- error recording ---------------------------------------------------------------------- */
@@ -525,12 +526,44 @@ void tgb200_synchronize(tg_raytracer* p_raytracer)
     tgbd_synchronize(p_raytracer->p_device);
 }
 
+/*
+ * The frame buffers keep rows in VIRTUAL order (tgb_rows.h: 16-row bands dealt out to the ranks; the identity on one GPU).
+ * Callers see physical rows: these two move rows [first_row, one_past_last_row) between a device frame buffer and caller memory.
+ */
+static b32 tgb__download_rows(tg_raytracer* p_raytracer, u32 buffer, u32 bytes_per_pixel, u32 first_row, u32 one_past_last_row, void* p_out)
+{
+    struct tgb_device* d = p_raytracer->p_device;
+    const u32 n_ranks = tgbd_n_ranks(d), tile_rows = tgbd_tile_rows(d);
+    const u64 row_bytes = (u64)p_raytracer->width * bytes_per_pixel;
+    if (first_row >= one_past_last_row) return TG_TRUE;
+    if (n_ranks == 1) return tgbd_download(d, buffer, (u64)first_row * row_bytes, p_out, (u64)(one_past_last_row - first_row) * row_bytes);
+    u8* p_tmp = (u8*)malloc((size_t)(tgbd_padded_pixels(d) * bytes_per_pixel));
+    if (!p_tmp) { tgb_set_error("read-back: out of host memory"); return TG_FALSE; }
+    const b32 ok = tgbd_download(d, buffer, 0, p_tmp, tgbd_padded_pixels(d) * bytes_per_pixel);
+    for (u32 row = first_row; ok && row < one_past_last_row; row++)
+        memcpy((u8*)p_out + (u64)(row - first_row) * row_bytes, p_tmp + (u64)tgb_row_to_virtual(row, n_ranks, tile_rows) * row_bytes, (size_t)row_bytes);
+    free(p_tmp);
+    return ok;
+}
+
+static b32 tgb__upload_rows(tg_raytracer* p_raytracer, u32 buffer, u32 bytes_per_pixel, const void* p_in)
+{
+    struct tgb_device* d = p_raytracer->p_device;
+    const u32 n_ranks = tgbd_n_ranks(d), tile_rows = tgbd_tile_rows(d);
+    const u64 row_bytes = (u64)p_raytracer->width * bytes_per_pixel;
+    if (n_ranks == 1) return tgbd_upload(d, buffer, 0, p_in, (u64)p_raytracer->height * row_bytes);
+    b32 ok = TG_TRUE;
+    for (u32 row = 0; ok && row < p_raytracer->height; row++)
+        ok = tgbd_upload(d, buffer, (u64)tgb_row_to_virtual(row, n_ranks, tile_rows) * row_bytes, (const u8*)p_in + (u64)row * row_bytes, row_bytes);
+    return ok;
+}
+
 b32 tg_raytracer_get_hovered_voxel(tg_raytracer* p_raytracer, u32 screen_x, u32 screen_y, f32* p_depth, u32* p_cluster_idx, u32* p_voxel_idx)
 {
     if (!tgb__alive(p_raytracer, "tg_raytracer_get_hovered_voxel")) return TG_FALSE;
     TGB_REQUIRE(screen_x < p_raytracer->width && screen_y < p_raytracer->height, TG_FALSE, "get_hovered_voxel: pixel (%u,%u) outside %ux%u", screen_x, screen_y, p_raytracer->width, p_raytracer->height);
     u64 packed_data = TG_VIS_CLEAR;
-    const u64 pixel_idx = (u64)p_raytracer->width * screen_y + screen_x;
+    const u64 pixel_idx = (u64)p_raytracer->width * tgb_row_to_virtual(screen_y, tgbd_n_ranks(p_raytracer->p_device), tgbd_tile_rows(p_raytracer->p_device)) + screen_x;
     if (!tgbd_download(p_raytracer->p_device, TGB_BUF_VISIBILITY_MERGED, pixel_idx * 8, &packed_data, 8)) return TG_FALSE;
     /* tgvk_raytracer.c:1639-1654 */
     *p_depth = (f32)(packed_data >> 40) / 16777215.0f;
@@ -548,19 +581,19 @@ b32 tg_raytracer_get_hovered_voxel(tg_raytracer* p_raytracer, u32 screen_x, u32 
 void tg_raytracer_read_visibility(tg_raytracer* p_raytracer, u64* p_out)
 {
     if (!tgb__alive(p_raytracer, "tg_raytracer_read_visibility")) return;
-    tgbd_download(p_raytracer->p_device, TGB_BUF_VISIBILITY_MERGED, 0, p_out, (u64)p_raytracer->width * p_raytracer->height * 8);
+    tgb__download_rows(p_raytracer, TGB_BUF_VISIBILITY_MERGED, 8, 0, p_raytracer->height, p_out);
 }
 
 void tg_raytracer_write_visibility(tg_raytracer* p_raytracer, const u64* p_in)
 {
     if (!tgb__alive(p_raytracer, "tg_raytracer_write_visibility")) return;
-    tgbd_upload(p_raytracer->p_device, TGB_BUF_VISIBILITY, 0, p_in, (u64)p_raytracer->width * p_raytracer->height * 8);
+    tgb__upload_rows(p_raytracer, TGB_BUF_VISIBILITY, 8, p_in);
 }
 
 void tg_raytracer_read_radiance(tg_raytracer* p_raytracer, f32* p_out)
 {
     if (!tgb__alive(p_raytracer, "tg_raytracer_read_radiance")) return;
-    tgbd_download(p_raytracer->p_device, TGB_BUF_RADIANCE, 0, p_out, (u64)p_raytracer->width * p_raytracer->height * 16);
+    tgb__download_rows(p_raytracer, TGB_BUF_RADIANCE, 16, 0, p_raytracer->height, p_out);
 }
 
 void tg_raytracer_read_radiance_rows(tg_raytracer* p_raytracer, u32 first_row, u32 one_past_last_row, f32* p_out)
@@ -568,7 +601,7 @@ void tg_raytracer_read_radiance_rows(tg_raytracer* p_raytracer, u32 first_row, u
     if (!tgb__alive(p_raytracer, "tg_raytracer_read_radiance_rows")) return;
     TGB_REQUIRE(first_row <= one_past_last_row && one_past_last_row <= p_raytracer->height, TGB_VOID, "read_radiance_rows: rows [%u, %u) outside the frame", first_row, one_past_last_row);
     if (first_row == one_past_last_row) return;
-    tgbd_download(p_raytracer->p_device, TGB_BUF_RADIANCE, (u64)first_row * p_raytracer->width * 16, p_out, (u64)(one_past_last_row - first_row) * p_raytracer->width * 16);
+    tgb__download_rows(p_raytracer, TGB_BUF_RADIANCE, 16, first_row, one_past_last_row, p_out);
 }
 
 void tgb200_get_timings(tg_raytracer* p_raytracer, tgb200_timings* p_out)
@@ -704,7 +737,18 @@ void tgb200_set_frame_sink_ex(tg_raytracer* p_raytracer, void* p_host, u32 n_ban
 void tg_raytracer_read_present(tg_raytracer* p_raytracer, u32* p_out)
 {
     if (!tgb__alive(p_raytracer, "tg_raytracer_read_present")) return;
-    tgbd_read_present(p_raytracer->p_device, p_out);
+    struct tgb_device* d = p_raytracer->p_device;
+    const u32 n_ranks = tgbd_n_ranks(d), tile_rows = tgbd_tile_rows(d);
+    const u64 n_px = (u64)p_raytracer->width * p_raytracer->height;
+    u32* p_tmp = (u32*)malloc((size_t)(tgbd_padded_pixels(d) * 4u)); /* the device frame is padded to whole 16-row bands, rows in virtual order */
+    if (!p_tmp) { tgb_set_error("read_present: out of host memory"); return; }
+    if (tgbd_read_present(d, p_tmp))
+    {
+        if (n_ranks == 1) memcpy(p_out, p_tmp, (size_t)n_px * 4u);
+        else for (u32 row = 0; row < p_raytracer->height; row++)
+            memcpy(p_out + (u64)row * p_raytracer->width, p_tmp + (u64)tgb_row_to_virtual(row, n_ranks, tile_rows) * p_raytracer->width, (size_t)p_raytracer->width * 4u);
+    }
+    free(p_tmp);
 }
 
 u64 tgb200_frame_ticket(tg_raytracer* p_raytracer)
@@ -741,10 +785,19 @@ void tgb200_tile_rows(tg_raytracer* p_raytracer, u32* p_first_row, u32* p_one_pa
 {
     *p_first_row = 0; *p_one_past_last_row = 0;
     if (!tgb__alive(p_raytracer, "tgb200_tile_rows")) return;
+    if (tgbd_n_ranks(p_raytracer->p_device) == 1) { *p_one_past_last_row = p_raytracer->height; return; }
     const u32 rows = tgbd_tile_rows(p_raytracer->p_device);
-    const u32 y0 = tgbd_rank(p_raytracer->p_device) * rows, y1 = y0 + rows;
-    *p_first_row = y0 < p_raytracer->height ? y0 : p_raytracer->height;
-    *p_one_past_last_row = y1 < p_raytracer->height ? y1 : p_raytracer->height;
+    *p_first_row = tgbd_rank(p_raytracer->p_device) * rows;
+    *p_one_past_last_row = *p_first_row + rows;
+}
+
+u32 tgb200_tile_physical_row(tg_raytracer* p_raytracer, u32 tile_row)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_tile_physical_row")) return TG_U32_MAX;
+    const u32 n_ranks = tgbd_n_ranks(p_raytracer->p_device), rows = tgbd_tile_rows(p_raytracer->p_device);
+    if (tile_row >= rows) return TG_U32_MAX;
+    const u32 physical = tgb_row_to_physical(tgbd_rank(p_raytracer->p_device) * rows + tile_row, n_ranks, rows);
+    return physical < p_raytracer->height ? physical : TG_U32_MAX;
 }
 
 void tgb200_set_merge_kind(tg_raytracer* p_raytracer, u32 kind)
@@ -759,7 +812,7 @@ void tgb200_merge_visibility(tg_raytracer* p_raytracer)
     void* p_comm = tgbd_comm(p_raytracer->p_device);
     TGB_REQUIRE(p_comm != NULL, TGB_VOID, "tgb200_merge_visibility: no communicator (call tgb200_comm_init)");
     tgbd_merge_begin(p_raytracer->p_device);
-    if (tgbn_allreduce_min_u64(p_comm, tgbd_buffer(p_raytracer->p_device, TGB_BUF_VISIBILITY), (u64)p_raytracer->width * p_raytracer->height, tgbd_stream(p_raytracer->p_device)))
+    if (tgbn_allreduce_min_u64(p_comm, tgbd_buffer(p_raytracer->p_device, TGB_BUF_VISIBILITY), tgbd_padded_pixels(p_raytracer->p_device), tgbd_stream(p_raytracer->p_device)))
         tgbd_note_merged(p_raytracer->p_device);
     tgbd_merge_end(p_raytracer->p_device);
 }

@@ -55,7 +55,9 @@ b32 tgb200_save_frame_bmp(tg_raytracer* p_raytracer, const char* p_filename)
     const u64 n = (u64)p_raytracer->width * p_raytracer->height;
     u32* p_pixels = (u32*)malloc((size_t)n * 4u);
     if (!p_pixels) { tgb_set_error("tgb200_save_frame_bmp: out of memory"); return TG_FALSE; }
-    b32 ok = tgbd_read_present(p_raytracer->p_device, p_pixels);
+    tgb200_clear_error();
+    tg_raytracer_read_present(p_raytracer, p_pixels); /* un-permutes the rows of a sharded frame */
+    b32 ok = tgb200_last_error() == NULL;
     if (ok) ok = tgb200_write_bmp_bgra8(p_filename, p_raytracer->width, p_raytracer->height, p_pixels);
     free(p_pixels);
     return ok;

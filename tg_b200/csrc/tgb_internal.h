@@ -58,6 +58,7 @@ u64   tgbd_frames_sunk(struct tgb_device* d);
 b32   tgbd_wait_frame(struct tgb_device* d, u64 ticket);
 b32   tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n_ranks);
 u32   tgbd_tile_rows(struct tgb_device* d);
+u64   tgbd_padded_pixels(struct tgb_device* d); /* pixels of every frame buffer: width * tile_rows * n_ranks, rows in virtual order (tgb_rows.h) */
 void* tgbd_comm(struct tgb_device* d);
 u32   tgbd_rank(struct tgb_device* d);
 u32   tgbd_n_ranks(struct tgb_device* d);

@@ -103,7 +103,7 @@ extern "C" b32 tgbd_p2p_prepare(struct tgb_device* d)
     if (d->p2p_failed) return TG_FALSE;
     if (d->n_ranks > TGB_MAX_RANKS) { d->p2p_failed = TG_TRUE; return TG_FALSE; }
     TGB_CUDA(cudaSetDevice(d->device));
-    const u64 px = (u64)d->width * d->height, padded_px = (u64)d->width * d->tile_rows * d->n_ranks;
+    const u64 padded_px = (u64)d->width * d->tile_rows * d->n_ranks, px = padded_px; /* every frame buffer is padded to whole tiles */
     d->d_vis_pair[0] = d->d_vis; d->d_mat_pair[0] = d->d_mat; d->vis_flip = 0;
     TGB_CUDA(cudaMalloc(&d->d_vis_pair[1], px * sizeof(u64)));
     TGB_CUDA(cudaMalloc(&d->d_mat_pair[1], padded_px * sizeof(u64)));
@@ -170,9 +170,8 @@ static tgb_peer_table tgbd__peer_table(struct tgb_device* d)
 extern "C" b32 tgbd_p2p_merge_tile(struct tgb_device* d)
 {
     if (!d->p2p_ready) { tgb_set_error("p2p_merge_tile: peer memory is not mapped"); return TG_FALSE; }
-    const u64 px = (u64)d->width * d->height, tile_px = (u64)d->width * d->tile_rows;
-    const u64 first = (u64)d->rank * tile_px;
-    const u64 n = first < px ? (first + tile_px <= px ? tile_px : px - first) : 0;
+    const u64 tile_px = (u64)d->width * d->tile_rows;
+    const u64 first = (u64)d->rank * tile_px, n = tile_px; /* this rank's virtual rows: one contiguous block of every buffer */
     /* d_vis keeps this rank's LOCAL words (the peers read them, and a re-render without a clear must find them): the merged tile
      * goes to its own buffer, addressed with whole-frame pixel indices like d_vis */
     k_merge_tile<<<(u32)((tile_px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), d->n_ranks, first, n, d->d_vis_tile - first, d->d_mat_tile, tile_px);
@@ -190,7 +189,7 @@ extern "C" void* tgbd_visibility_for_read(struct tgb_device* d)
 {
     if (d->n_ranks < 2 || d->vis_merged || !d->p2p_ready) return d->d_vis;
     if (cudaSetDevice(d->device) != cudaSuccess) return d->d_vis;
-    const u64 px = (u64)d->width * d->height;
+    const u64 px = (u64)d->width * d->tile_rows * d->n_ranks;
     if (!d->d_vis_full && cudaMalloc(&d->d_vis_full, px * sizeof(u64)) != cudaSuccess) { tgb_set_error("visibility_for_read: out of device memory"); return d->d_vis; }
     k_merge_tile<<<(u32)((px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), d->n_ranks, 0, px, d->d_vis_full, NULL, 0);
     d->n_kernel_launches++;

@@ -156,8 +156,9 @@ struct tgb_shade_args
     u32 w, h;
     u32 global_pointer_base, n_local_pointers;
     u32 gi_enabled, frame_seed, debug_visualization;
-    u32 y0, y1; /* rows [y0, y1) are shaded by this launch (a band of this rank's screen tile) */
-    u32 mat_y0; /* first row of the tile p_mat describes */
+    u32 y0, y1; /* VIRTUAL rows [y0, y1) are shaded by this launch (a band of this rank's screen tile; tgb_rows.h) */
+    u32 mat_y0; /* first virtual row of the tile p_mat describes */
+    u32 n_ranks, tile_rows; /* virtual <-> physical row mapping */
     /* GI ray queue (SoA): origin.xyz + pixel | direction.xyz + enter of the root slab test | ambient.rgb */
     float4* __restrict__ p_q0;
     float4* __restrict__ p_q1;
@@ -173,9 +174,9 @@ struct tgb_shade_args
  * all-gathered global ones whose first_cluster_pointer is global. Everything downstream is the same arithmetic.
  */
 template <bool RESOLVED>
-__device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px, u32 py, float4* p_color, v3* p_origin, v3* p_dir, v3* p_ambient, f32* p_root_enter)
+__device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px, u32 py, u32 vy, float4* p_color, v3* p_origin, v3* p_dir, v3* p_ambient, f32* p_root_enter)
 {
-    const u64 pixel = (u64)py * a.w + px;
+    const u64 pixel = (u64)vy * a.w + px; /* buffers keep rows in virtual order; the ray and the RNG seed use the physical row py */
 
     /* shading.frag:116-120 */
     const u64 packed_data = a.p_vis[pixel];
@@ -188,7 +189,7 @@ __device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px,
     u32 local_pointer, cluster_idx, object_idx, color_lut_idx, packed_color;
     if (RESOLVED)
     {
-        const u64 mat = a.p_mat[(u64)(py - a.mat_y0) * a.w + px];
+        const u64 mat = a.p_mat[(u64)(vy - a.mat_y0) * a.w + px];
         if (mat == 0) { *p_color = make_float4(0.0f, 0.0f, 0.0f, 0.0f); return false; } /* no rank owns this pointer: inconsistent shards */
         local_pointer = cluster_pointer_31b; /* global pointer against globalised object records */
         cluster_idx = cluster_pointer_31b;   /* debug views only */
@@ -316,14 +317,15 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
     /* 8x4 pixel blocks per warp like K1: neighbouring pixels share clusters, objects and material bytes */
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const u32 px = blockIdx.x * 16u + (warp & 1u) * 8u + (lane & 7u);
-    const u32 py = a.y0 + blockIdx.y * 16u + (warp >> 1) * 4u + (lane >> 3);
-    const bool in_tile = px < a.w && py < a.y1;
+    const u32 vy = a.y0 + blockIdx.y * 16u + (warp >> 1) * 4u + (lane >> 3);  /* bands are 16 rows: a CTA stays inside one */
+    const u32 py = tgb_row_to_physical(vy, a.n_ranks, a.tile_rows);
+    const bool in_tile = px < a.w && vy < a.y1 && py < a.h;
 
     float4 color = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     v3 origin = tgb_v3(0.0f, 0.0f, 0.0f), dir = origin, ambient = origin;
     f32 root_enter = 0.0f; /* `enter` of the slab test against the SVO root (svo_functions.inc:27-31), queued for k_gi_trace_flat */
-    const bool trace = in_tile && tgb_shade_pixel<RESOLVED>(a, px, py, &color, &origin, &dir, &ambient, &root_enter);
-    if (in_tile) a.p_out[(u64)py * a.w + px] = color;
+    const bool trace = in_tile && tgb_shade_pixel<RESOLVED>(a, px, py, vy, &color, &origin, &dir, &ambient, &root_enter);
+    if (in_tile) a.p_out[(u64)vy * a.w + px] = color;
 
     /* warp-aggregated append to the ray queue */
     const u32 m = __ballot_sync(0xFFFFFFFFu, trace);
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
     if (trace)
     {
         const u32 slot = base + (u32)__popc(m & ((1u << lane) - 1u));
-        a.p_q0[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(a.w * py + px));
+        a.p_q0[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(a.w * vy + px)); /* where the ambient term goes */
         a.p_q1[slot] = make_float4(dir.x, dir.y, dir.z, root_enter);
         a.p_q2[slot] = make_float4(ambient.x, ambient.y, ambient.z, 0.0f);
     }
@@ -953,7 +955,7 @@ extern "C" b32 tgbd_read_present(struct tgb_device* d, u32* p_out)
 {
     TGB_CUDA(cudaSetDevice(d->device));
     if (!tgbd__present_buffer(d, d->radiance_flip)) return TG_FALSE;
-    const u64 n = (u64)d->width * d->height;
+    const u64 n = (u64)d->width * d->tile_rows * (d->n_ranks ? d->n_ranks : 1); /* the padded frame, virtual row order; p_out must hold it */
     k_present<<<(u32)((n + 255) / 256), 256, 0, d->stream>>>(d->d_radiance, d->d_present_pair[d->radiance_flip], 0, n);
     TGB_LAUNCH_CHECK(d);
     TGB_CUDA(cudaMemcpyAsync(p_out, d->d_present_pair[d->radiance_flip], n * sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
@@ -995,6 +997,7 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     a.svo.bmax = d->svo.bmax;
     a.cam = *p_cam;
     a.w = d->width; a.h = d->height;
+    a.n_ranks = d->n_ranks ? d->n_ranks : 1; a.tile_rows = d->tile_rows;
     a.global_pointer_base = d->global_pointer_base;
     a.n_local_pointers = n_local_pointers;
     a.gi_enabled = gi_enabled; a.frame_seed = frame_seed; a.debug_visualization = debug_visualization;
@@ -1120,7 +1123,7 @@ extern "C" b32 tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera
     }
     const u32 cap = d->object_capacity, n_global = cap * d->n_ranks;
     const v3 camera = tgb_v3(p_cam->camera.x, p_cam->camera.y, p_cam->camera.z);
-    const u64 n_pixels = (u64)d->width * d->height, tile_px = (u64)d->width * d->tile_rows, n_padded = tile_px * d->n_ranks;
+    const u64 tile_px = (u64)d->width * d->tile_rows, n_padded = tile_px * d->n_ranks, n_pixels = n_padded; /* padding rows hold the clear word */
     const bool fused = !d->vis_merged;
     if (fused && !d->p2p_ready)
     {
@@ -1166,8 +1169,7 @@ extern "C" b32 tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera
     }
 
     /* GI + shading of this rank's rows */
-    const u32 y0 = d->rank * d->tile_rows;
-    const u32 y1 = y0 + d->tile_rows < d->height ? y0 + d->tile_rows : d->height;
+    const u32 y0 = d->rank * d->tile_rows, y1 = y0 + d->tile_rows; /* virtual rows; k_shade skips the padding rows */
     if (y0 < y1 && !tgbd__shade_launch(d, p_cam, true, n_local_pointers, gi_enabled, frame_seed, debug_visualization, y0, y1)) return TG_FALSE;
     TGB_CUDA(cudaEventRecord(d->ev[8], d->stream));
     d->ev_shade = TG_TRUE;

@@ -45,7 +45,7 @@ extern "C" b32 tgbd_clear(struct tgb_device* d)
         d->d_mat = d->d_mat_pair[d->vis_flip];
     }
     d->vis_merged = TG_FALSE; d->tile_merged = TG_FALSE;
-    const u64 n = (u64)d->width * d->height;
+    const u64 n = (u64)d->width * d->tile_rows * d->n_ranks; /* the padded frame */
     TGB_CUDA(cudaEventRecord(d->ev[0], d->stream));
     k_clear_visibility<<<(u32)((n / 2 + 255) / 256) + 1, 256, 0, d->stream>>>((ulonglong2*)d->d_vis, n / 2, d->d_vis, n);
     TGB_LAUNCH_CHECK(d);
@@ -631,7 +631,7 @@ template <int MIN_CTAS, bool REGROUP>
 __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const tgb_object_frame* __restrict__ p_frames, const u32* __restrict__ p_count,
                                                                tg_camera_rays cam, u32 w, u32 h,
                                                                const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
-                                                               u32 global_pointer_base, u64* __restrict__ p_vis)
+                                                               u32 global_pointer_base, u64* __restrict__ p_vis, u32 n_ranks, u32 tile_rows)
 {
     __shared__ u32 s_list[TGB_K1_THREADS];
     __shared__ u32 s_warp_count[TGB_K1_THREADS / 32];
@@ -694,7 +694,8 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
         if (base + TGB_K1_THREADS < n_visible) __syncthreads(); /* s_list is rewritten by the next window */
     }
 
-    if (in_screen && best != TG_VIS_CLEAR) atomicMin((unsigned long long*)&p_vis[(u64)py * w + px], (unsigned long long)best);
+    /* the buffer keeps rows in virtual order (tgb_rows.h; the identity on one GPU) */
+    if (in_screen && best != TG_VIS_CLEAR) atomicMin((unsigned long long*)&p_vis[(u64)tgb_row_to_virtual(py, n_ranks, tile_rows) * w + px], (unsigned long long)best);
 }
 
 extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, u32 object_capacity)
@@ -716,7 +717,7 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
     /* register budget: 4 CTAs per SM = 64 registers with ~30 spilled words, measured 11 % faster than 3 CTAs = 80 registers (TGB_K1_MIN_CTAS=3 selects that build; tuning only) */
     static const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 4), regroup = tgbd_env_int("TGB_K1_REGROUP", 1);
 #define TGB_K1_LAUNCH(C, R) k_visibility<C, R><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height, \
-                                                                                       d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis)
+                                                                                       d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis, d->n_ranks, d->tile_rows)
     if (regroup) { if (min_ctas >= 4) TGB_K1_LAUNCH(4, true); else TGB_K1_LAUNCH(3, true); }
     else         { if (min_ctas >= 4) TGB_K1_LAUNCH(4, false); else TGB_K1_LAUNCH(3, false); }
 #undef TGB_K1_LAUNCH

@@ -206,6 +206,13 @@ class Raytracer:
         self._lib.tgb200_tile_rows(C.byref(self._rt), C.byref(y0), C.byref(y1))
         return y0.value, y1.value
 
+    def tile_physical_rows(self):
+        """Frame row of every row of this rank's tile, in tile order (what the frame sink delivers); -1 = padding row."""
+        y0, y1 = self.tile_rows()
+        rows = np.array([self._lib.tgb200_tile_physical_row(C.byref(self._rt), i) for i in range(y1 - y0)], dtype=np.int64)
+        rows[rows == 0xFFFFFFFF] = -1
+        return rows
+
     def gather_radiance(self):
         self._lib.tgb200_gather_radiance(C.byref(self._rt))
 

@@ -4,7 +4,8 @@ base of its shard, the screen tile it shades, and the 64-bit min merge expressed
 One process per GPU. Clusters are sharded BY OBJECT (an object's clusters are one contiguous pointer range,
 tgvk_raytracer.c:826-827), ranks own contiguous object ranges, so global pointers = local pointer + base. The per-GPU
 visibility buffers are merged with an element-wise 64-bit min (ncclAllReduce(ncclUint64, ncclMin) on GPUs); GI rays are
-split by screen tile: rank r shades rows [r * ceil(H / N), (r + 1) * ceil(H / N))."""
+split by screen tile: the frame is cut into 16-row bands and rank r shades the bands b with b mod N == r (an equal share of
+the hit pixels for every rank, whatever the view)."""
 import numpy as np
 
 
@@ -25,9 +26,31 @@ def shard_scene(scene, n_ranks, rank):
     return sub, base, first
 
 
+BAND_ROWS = 16  # tg_b200/csrc/tgb_rows.h: the frame is cut into 16-row bands, band b belongs to rank b mod n_ranks
+
+
+def tile_row_count(height, n_ranks):
+    """Rows of a rank's tile, padding included: whole bands, the same for every rank."""
+    n_bands = (height + BAND_ROWS - 1) // BAND_ROWS
+    return ((n_bands + n_ranks - 1) // n_ranks) * BAND_ROWS
+
+
 def tile_rows(height, n_ranks, rank):
-    rows = (height + n_ranks - 1) // n_ranks
-    return min(rank * rows, height), min((rank + 1) * rows, height)
+    """A rank's rows in tile ("virtual") order, [first, one_past_last): the whole frame in frame order on one GPU."""
+    if n_ranks == 1:
+        return 0, height
+    t = tile_row_count(height, n_ranks)
+    return rank * t, (rank + 1) * t
+
+
+def tile_physical_rows(height, n_ranks, rank):
+    """Frame row of every row of the rank's tile, in tile order; -1 = padding (a partial last band, a band the rank does not have)."""
+    if n_ranks == 1:
+        return np.arange(height, dtype=np.int64)
+    t = tile_row_count(height, n_ranks)
+    i = np.arange(t, dtype=np.int64)
+    rows = ((i // BAND_ROWS) * n_ranks + rank) * BAND_ROWS + i % BAND_ROWS
+    return np.where(rows < height, rows, -1)
 
 
 def allreduce_min_u64(vis, group=None):
@@ -45,8 +68,8 @@ def merge_tile_from_peers(all_vis, rank, height, width):
     [n_ranks, h, w] (what k_merge_tile reads over NVLink); returns (merged words of this rank's tile rows, winner rank per pixel
     or -1). min is associative, so the tile equals the same rows of the all-reduced frame."""
     n_ranks = all_vis.shape[0]
-    y0, y1 = tile_rows(height, n_ranks, rank)
-    tile = all_vis[:, y0:y1]
+    rows = tile_physical_rows(height, n_ranks, rank)
+    tile = all_vis[:, rows[rows >= 0]]
     who = np.argmin(tile, axis=0)          # first rank holding the minimum, like the kernel's strict `<`
     best = np.take_along_axis(tile, who[None], axis=0)[0]
     who = np.where(best == np.uint64(0xFFFFFFFFFFFFFFFF), -1, who)
