@@ -31,8 +31,11 @@ def main():
         sub, base, first = sharding.shard_scene(s, world, rank)
         cap = max(sharding.object_range(len(s.objects), world, r)[1] - sharding.object_range(len(s.objects), world, r)[0] for r in range(world))
         results = {}
-        # both exchanges: 0 = one kernel over peer memory (CUDA IPC / NVLink), 1 = NCCL all-reduce + reduce-scatter
-        for kind in (0, 1):
+        # the exchanges: 0 = one kernel over peer memory (CUDA IPC / NVLink), 1 = NCCL all-reduce + reduce-scatter,
+        # 2 = peer memory requested but one rank cannot map it: every rank must agree on the NCCL path
+        for kind in (0, 1, 2):
+            if kind == 2:
+                os.environ["TGB200_FAIL_P2P_ON_RANK"] = str(world - 1)
             rt = from_scene(sub, device=local, max_n_objects=cap, max_n_clusters=max(sub.n_clusters, 1))
             for i in range(8):
                 rt.color_lut_set(i, 0.1 * i, 1.0 - 0.1 * i, 0.5, lut_idx=1)
@@ -40,7 +43,7 @@ def main():
             ids = [comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
             rt.comm_init(ids[0], rank, world)
-            rt.set_merge_kind(kind)
+            rt.set_merge_kind(0 if kind == 2 else kind)
             rt.set_gi(True, 5)
             for _ in range(3):       # three frames: the peer-memory path alternates between its two buffer pairs
                 rt.clear()
@@ -58,11 +61,27 @@ def main():
             rad = rt.read_radiance()
             t = rt.timings()
             assert t["merge_ms"] > 0
+            assert (t["merge_kernel_ms"] > 0) == (kind == 0), "kind 0 must run k_merge_tile, the others the NCCL collectives"
+            # frame sink on a sharded frame: this rank's tile rows (16-row bands, tile order) land in host memory, HDR and presented
+            rows = rt.tile_physical_rows()
+            import torch
+            hdr = torch.zeros(len(rows) * s.width * 4, dtype=torch.float32).pin_memory().numpy().reshape(len(rows), s.width, 4)
+            rt.set_frame_sink(hdr, 3)
+            rt.clear(); rt.render(); rt.wait_frame(rt.frame_ticket())
+            assert np.array_equal(hdr[rows >= 0], rad[rows[rows >= 0]]), f"{name} rank {rank} kind {kind}: frame sink rows differ from the gathered frame"
+            bgra = torch.zeros(len(rows) * s.width, dtype=torch.int32).pin_memory().numpy().view(np.uint32).reshape(len(rows), s.width)
+            rt.set_frame_sink(bgra, 2)
+            rt.clear(); rt.render(); rt.wait_frame(rt.frame_ticket())
+            rt.set_frame_sink(None)
+            rt.gather_radiance(); rt.synchronize()
+            assert np.array_equal(bgra[rows >= 0], rt.read_present()[rows[rows >= 0]]), f"{name} rank {rank} kind {kind}: presented sink rows differ"
             dist.barrier()
             rt.comm_destroy()
             rt.destroy()
             results[kind] = (vis, nodes, leaf, vox, rad, t)
-        assert all(np.array_equal(a, b) for a, b in zip(results[0][:5], results[1][:5])), f"{name} rank {rank}: the peer-memory merge and the NCCL merge disagree"
+            os.environ.pop("TGB200_FAIL_P2P_ON_RANK", None)
+        for other in (1, 2):
+            assert all(np.array_equal(a, b) for a, b in zip(results[0][:5], results[other][:5])), f"{name} rank {rank}: the peer-memory merge and exchange {other} disagree"
         vis, nodes, leaf, vox, rad, t = results[0]
 
         # reference: the whole scene on this GPU alone

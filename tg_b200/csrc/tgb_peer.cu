@@ -114,6 +114,8 @@ extern "C" b32 tgbd_p2p_prepare(struct tgb_device* d)
 
     cudaIpcMemHandle_t mine[4];
     u32 n_failed = 0;
+    /* test hook: TGB200_FAIL_P2P_ON_RANK=r makes rank r report a failed mapping, which must send EVERY rank to the NCCL path */
+    if (getenv("TGB200_FAIL_P2P_ON_RANK") && (u32)atoi(getenv("TGB200_FAIL_P2P_ON_RANK")) == d->rank) n_failed++;
     void* p_mine[4] = { d->d_vis_pair[0], d->d_vis_pair[1], d->d_mat_pair[0], d->d_mat_pair[1] };
     for (int k = 0; k < 4; k++)
     {
