@@ -629,8 +629,9 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
  * per iteration, so they wait until a quarter of the warp needs service and are then handled together.
  */
 enum { TGB_FL_IDLE = 0, TGB_FL_TREE = 1, TGB_FL_DDA = 2, TGB_FL_HIT = 3, TGB_FL_MISS = 4 };
-#define TGB_FL_SERVICE_LANES 12u /* measured best with 16 DDA steps per phase (scratch sweeps: 1.66 -> 1.55 ms GI + shading at 4K) */
+#define TGB_FL_SERVICE_LANES 16u /* measured best with 16 DDA steps and 4 tree cells per phase */
 #define TGB_FL_DDA_STEPS 16
+#define TGB_FL_TREE_REPS 4 /* cells a ray may cross per tree phase: 1.548 -> 1.506 ms for the stage with 16 service lanes (sweeps of this round) */
 
 /*
  * Index along one axis of the 32^3 cell the shader's octant rule (:63-80: upper half iff mid < p || (p == mid && d > 0))
@@ -678,7 +679,7 @@ __device__ __forceinline__ f32 tgb_exit_distance_rcp(v3 bmin, f32 size, v3 posit
 template <int DDA_STEPS>
 __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_view svo, const u32* __restrict__ p_grid, f32 far_plane,
                                                                   const float4* __restrict__ p_q0, const float4* __restrict__ p_q1, const float4* __restrict__ p_q2,
-                                                                  u32* __restrict__ p_q_count, float4* __restrict__ p_out, u32 service_lanes, u32 dda_bias)
+                                                                  u32* __restrict__ p_q_count, float4* __restrict__ p_out, u32 service_lanes, u32 dda_bias, u32 tree_reps)
 {
     if (p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
 
@@ -826,7 +827,9 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
                 }
             }
         }
-        else if (kind == TGB_FL_TREE)
+        else
+#pragma unroll 1
+        for (u32 rep = 0; rep < tree_reps && kind == TGB_FL_TREE; rep++) /* a ray crossing empty cells stays in the tree phase: up to tree_reps cells per phase */
         {
             if (advance_pending)
             {
@@ -1050,10 +1053,11 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
             {
                 /* scheduling knobs (tuning only): DDA steps per phase, lanes that trigger a service phase, bias of the majority vote towards the DDA */
                 static const int dda_steps = tgbd_env_int("TGB_GI_DDA_STEPS", TGB_FL_DDA_STEPS);
-                static const u32 service_lanes = (u32)tgbd_env_int("TGB_GI_SERVICE_LANES", (i32)TGB_FL_SERVICE_LANES), dda_bias = (u32)tgbd_env_int("TGB_GI_DDA_BIAS", 0);
+                static const u32 service_lanes = (u32)tgbd_env_int("TGB_GI_SERVICE_LANES", (i32)TGB_FL_SERVICE_LANES), dda_bias = (u32)tgbd_env_int("TGB_GI_DDA_BIAS", 0),
+                                 tree_reps = (u32)max(1, tgbd_env_int("TGB_GI_TREE_REPS", TGB_FL_TREE_REPS));
                 const dim3 gi_grid(d->n_sms * (u32)gi_ctas);
 #define TGB_GI_LAUNCH(K) k_gi_trace_flat<K><<<gi_grid, TGB_GI_THREADS, 0, d->stream>>>(a.svo, d->svo.d_top_grid, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, \
-                                                                                      d->d_gi_count, d->d_radiance, service_lanes, dda_bias)
+                                                                                      d->d_gi_count, d->d_radiance, service_lanes, dda_bias, tree_reps)
                 if (dda_steps <= 4) TGB_GI_LAUNCH(4); else if (dda_steps <= 8) TGB_GI_LAUNCH(8); else if (dda_steps <= 16) TGB_GI_LAUNCH(16); else TGB_GI_LAUNCH(64);
 #undef TGB_GI_LAUNCH
                 TGB_LAUNCH_CHECK(d);
