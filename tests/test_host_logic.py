@@ -243,3 +243,50 @@ def test_bmp_writer_container(tmp_path):
     assert np.array_equal(np.frombuffer(raw, dtype="<u4", offset=150), px)
     assert not L.tgb200_write_bmp_bgra8(str(tmp_path / "no_dir" / "x.bmp").encode(), w, h, T.ptr(px, T.u32))
     L.tgb200_clear_error()
+
+
+def test_row_mapping_header_equals_the_sharding_plan(tmp_path):
+    """tg_b200/csrc/tgb_rows.h (16-row bands dealt out to the ranks; what K1, k_shade and the host read-back paths use) compiled
+    with gcc and compared with tg_b200/sharding.py for ragged and full-size frames: tile size, frame row of every tile row,
+    virtual row of every frame row, identity on one rank."""
+    import subprocess
+    from tg_b200 import sharding
+    src = tmp_path / "rows.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "tgb_rows.h"
+int main(void)
+{
+    const unsigned cases[][2] = { {2160, 8}, {2160, 4}, {2160, 1}, {177, 2}, {10, 4}, {33, 8}, {16, 3} };
+    for (unsigned c = 0; c < sizeof(cases) / sizeof(cases[0]); c++)
+    {
+        const unsigned h = cases[c][0], n = cases[c][1], t = tgb_tile_rows_for(h, n);
+        printf("case %u %u %u\n", h, n, t);
+        for (unsigned v = 0; v < n * t; v++) printf("%u ", tgb_row_to_physical(v, n, t));
+        printf("\n");
+        for (unsigned p = 0; p < h; p++) printf("%u ", tgb_row_to_virtual(p, n, t));
+        printf("\n");
+    }
+    return 0;
+}
+''')
+    exe = tmp_path / "rows"
+    csrc = os.path.join(ROOT, "tg_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=gnu11", "-O1", "-I", csrc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-lm"])
+    lines = subprocess.check_output([str(exe)], text=True).strip().split("\n")
+    for i in range(0, len(lines), 3):
+        _, h, n, t = lines[i].split()
+        h, n, t = int(h), int(n), int(t)
+        phys = np.array(lines[i + 1].split(), dtype=np.int64)
+        virt = np.array(lines[i + 2].split(), dtype=np.int64)
+        assert t == sharding.tile_row_count(h, n)
+        for r in range(n):
+            want = sharding.tile_physical_rows(h, n, r)
+            got = phys[r * t:(r + 1) * t]
+            if n == 1:
+                assert np.array_equal(got[:h], want)      # one rank: frame order, padding rows at the end
+            else:
+                assert np.array_equal(np.where(got < h, got, -1), want), (h, n, r)
+        assert np.array_equal(phys[virt], np.arange(h)), (h, n)   # the two maps are inverse to each other on the frame's rows
+        if n == 1:
+            assert np.array_equal(virt, np.arange(h))
