@@ -147,8 +147,8 @@ extern "C" b32 tgbd_p2p_prepare(struct tgb_device* d)
     if (total_failed)
     {
         tgbd__p2p_close(d);
-        cudaFree(d->d_vis_pair[1]); cudaFree(d->d_mat_pair[1]); cudaFree(d->d_vis_tile);
-        d->d_vis_pair[1] = NULL; d->d_mat_pair[1] = NULL; d->d_vis_tile = NULL;
+        cudaFree(d->d_vis_pair[1]); cudaFree(d->d_mat_pair[1]); cudaFree(d->d_vis_tile); cudaFree(d->d_ipc_stage);
+        d->d_vis_pair[1] = NULL; d->d_mat_pair[1] = NULL; d->d_vis_tile = NULL; d->d_ipc_stage = NULL;
         d->p2p_failed = TG_TRUE;
         if (getenv("TGB200_VERBOSE")) fprintf(stderr, "[tgb200] rank %u: peer memory unavailable (%u failed mappings), using the NCCL collectives\n", d->rank, total_failed);
         return TG_FALSE;
