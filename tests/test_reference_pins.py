@@ -296,3 +296,43 @@ def test_boundary_tg_svo_traverse_equals_the_reference(oracle, ref):
         assert n_hits > 200
     finally:
         ref.tg_svo_destroy(C.byref(svo))
+
+
+@pytest.mark.parametrize("name", ["small_grid", "grid4_tall"])
+def test_glsl_traversal_transcription_agrees_with_the_reference_c_traversal(oracle, ref, name):
+    """G3: the oracle's transcription of the GLSL tg_svo_traverse (svo_functions.inc:1-329) -- the variant the GI kernels follow,
+    which cannot be executed here -- against THE REFERENCE'S OWN C traversal (tg_sparse_voxel_octree.c:558-740) run on a
+    reference-built SVO. The two variants differ in bookkeeping (Q7: how the distance is accumulated, the DDA start clamp), so the
+    distance is compared to 1e-4 relative, but on 20,000 random rays per scene they must make the same hit / miss decision and
+    name the same leaf node and the same voxel (the C variant reports leaf data_pointer * 32768 + voxel)."""
+    s = SVO_CASES[name]()
+    view = oracle.SceneView.from_scene(s, with_lut=False)
+    want = T.tg_svo()
+    scene = oracle.ref_scene(view)
+    ref.tg_svo_create(T.v3(-512, -512, -512), T.v3(512, 512, 512), C.byref(scene), C.byref(want))
+    nodes = np.ctypeslib.as_array(want.p_node_buffer, shape=(want.node_buffer_count,))
+    L = oracle.lib()
+    rng = np.random.default_rng(21)
+    n_hits = 0
+    try:
+        for trial in range(20000):
+            o = rng.uniform(-90, 90, 3).astype(np.float32)
+            o[1] = np.float32(rng.uniform(-30, 120))
+            d = rng.uniform(-40, 40, 3).astype(np.float32) - o
+            if trial % 9 == 0:
+                d[int(rng.integers(0, 3))] = 0.0
+            if not d.any():
+                d[1] = -1.0
+            d = (d / np.linalg.norm(d)).astype(np.float32)
+            hp, hn, node, voxel = T.v3(), T.v3(), T.u32(), T.u32()
+            depth = L.tgo_svo_traverse_glsl(C.byref(want), 1000.0, T.v3(*o), T.v3(*d), C.byref(hp), C.byref(hn), C.byref(node), C.byref(voxel))
+            d1, n1, v1 = T.f32(), T.u32(), T.u32()
+            r1 = ref.tg_svo_traverse(C.byref(want), T.v3(*o), T.v3(*d), C.byref(d1), C.byref(n1), C.byref(v1))
+            assert (depth < 1.0) == bool(r1), (trial, o, d, depth, d1.value)
+            if r1:
+                n_hits += 1
+                assert node.value == n1.value and voxel.value == v1.value - int(nodes[n1.value]) * 32768, (trial, o, d)
+                assert abs(depth * 1000.0 - d1.value) <= 1e-4 * max(1.0, abs(d1.value)), (trial, depth * 1000.0, d1.value)
+        assert n_hits > 5000
+    finally:
+        ref.tg_svo_destroy(C.byref(want))
