@@ -336,3 +336,57 @@ def test_glsl_traversal_transcription_agrees_with_the_reference_c_traversal(orac
         assert n_hits > 5000
     finally:
         ref.tg_svo_destroy(C.byref(want))
+
+
+def test_visibility_transcription_sees_the_voxels_the_reference_traversal_sees(oracle, ref):
+    """V3-V7: visibility.frag cannot run here and has no CPU twin, but for axis-aligned objects on the integer lattice a cluster
+    voxel IS a world unit cell IS a voxel of the reference's SVO, so the reference's own code answers the same question by another
+    route: tg_svo_create + tg_svo_traverse (tg_sparse_voxel_octree.c) along the primary ray of every pixel. The oracle's
+    visibility buffer must make the same hit / miss decision, name the same world voxel (pointer -> object, cluster, voxel) and a
+    depth24 within 2 LSB of the traversal's distance (different arithmetic, same geometry) on every pixel."""
+    specs = [((0.0, 0.0, 0.0), (32, 16, 32)), ((48.0, 8.0, -16.0), (16, 32, 16)), ((-40.0, -8.0, 24.0), (24, 16, 40)), ((8.0, 40.0, 8.0), (16, 8, 16))]
+    objs = []
+    for i, (c, e) in enumerate(specs):
+        n = (e[0] // 8) * (e[1] // 8) * (e[2] // 8)
+        objs.append(scenes.ObjectSpec(center=c, extent=e, angle=0.0, bits=scenes.random_solid_bits(100 + i, n, 3)))
+    w, h = 160, 90
+    cam = scenes.CameraSpec(position=(6.0, 34.0, 66.0), pitch=float(scenes.deg2rad(-28.0)), yaw=float(scenes.deg2rad(6.0)), roll=0.0, aspect=w / h)
+    s = scenes.SceneSpec("aligned", w, h, cam, objs)
+    view = oracle.SceneView.from_scene(s, with_lut=False)
+    rays = oracle.camera_rays(oracle.camera_from_spec(cam))
+    vis, _ = oracle.visibility(view, rays, w, h, oracle.VIS_BRUTE_FORCE)
+    svo = T.tg_svo()
+    scene = oracle.ref_scene(view)
+    ref.tg_svo_create(T.v3(-512, -512, -512), T.v3(512, 512, 512), C.byref(scene), C.byref(svo))
+    nodes = np.ctypeslib.as_array(svo.p_node_buffer, shape=(svo.node_buffer_count,))
+    firsts = np.cumsum([0] + [o.n_clusters for o in objs])
+    L = oracle.lib()
+    o = np.array(cam.position, dtype=np.float32)
+    n_hits = 0
+    try:
+        for py in range(h):
+            for px in range(w):
+                dv = L.tgo_pixel_ray_direction_nn(C.byref(rays), w, h, px, py)
+                d = np.array([dv.x, dv.y, dv.z], dtype=np.float32)
+                d = (d / np.float32(np.sqrt(np.float32(d @ d)))).astype(np.float32)
+                dist, node, voxel = T.f32(), T.u32(), T.u32()
+                r = ref.tg_svo_traverse(C.byref(svo), T.v3(*o), T.v3(*d), C.byref(dist), C.byref(node), C.byref(voxel))
+                word = int(vis[py, px])
+                assert (word != 0xFFFFFFFFFFFFFFFF) == bool(r), (px, py)
+                if not r:
+                    continue
+                n_hits += 1
+                pointer, vox, depth24 = (word >> 9) & 0x7FFFFFFF, word & 511, word >> 40
+                oi = int(np.searchsorted(firsts, pointer, side="right") - 1)
+                nx, ny, _ = objs[oi].dims
+                rel = pointer - firsts[oi]
+                seen = (np.array(objs[oi].center) - np.array(objs[oi].extent) / 2 + 8 * np.array([rel % nx, (rel // nx) % ny, rel // (nx * ny)])
+                        + np.array([vox % 8, (vox // 8) % 8, vox // 64]))
+                rel_voxel = voxel.value - int(nodes[node.value]) * 32768   # the C traversal reports data_pointer * 32768 + voxel
+                p = o.astype(np.float64) + d.astype(np.float64) * (dist.value + 1e-3)
+                traversed = np.floor((p + 512) / 32) * 32 - 512 + np.array([rel_voxel % 32, (rel_voxel // 32) % 32, rel_voxel // 1024])
+                assert np.array_equal(seen, traversed), (px, py, seen, traversed)
+                assert abs(depth24 - int(np.float32(dist.value) / np.float32(1000.0) * np.float32(16777215.0))) <= 2, (px, py)
+        assert n_hits > 2500, n_hits
+    finally:
+        ref.tg_svo_destroy(C.byref(svo))
