@@ -9,9 +9,14 @@ A step = one frame of the hot path over the synthetic scene through libtgb200.so
 ncclAllReduce(u64, min) merge + owner-resolved materials, reduce-scattered by screen tile] + GI / shading (K3: one
 secondary ray per hit pixel through the replicated 1-bit SVO). The SVO (K2) is built once before the timed region, like
 the reference builds it on its first frame (tgvk_raytracer.c:1187-1217); its build time is reported beside the frame.
-N=1 workload = BASELINE configs[1]/[2]: 1,024 objects, 2^21 clusters (1.07e9 voxels), 4K. At N>1 every rank owns one
-such 1,024-object shard of an N-times larger world (weak scaling), traces the full 4K frame against its shard, and
-shades 1/N of the rows (16-row bands dealt out to the ranks). `value` = rays all ranks traced per second: N * W*H primary + one GI ray per hit pixel.
+Headline workload (c2) = BASELINE configs[1]/[2]: 1,024 objects, 2^21 clusters (1.07e9 voxels), 4K. At N>1 the SAME scene is dealt
+out over the ranks by object (strong scaling: the frame's work is fixed), every rank traces the full 4K frame against its
+objects and shades 1/N of the rows (16-row bands dealt out to the ranks). `value` = SURVEY 8(d) rays per second at every N:
+W*H primary + one GI ray per hit pixel (that every rank casts its own W*H primaries against its shard is an implementation
+detail reported as `rank_primary_rays`, not counted). The same invocation also times configs[3] (c4, N=1), configs[4] (c5: one
+12,288-object shard per GPU, the 1e11-voxel world at N=8) and the dense-view stress c2far briefly and attaches them under
+`also`; at N>1 every workload first proves, inside its warm-up, that the sharded frame equals the single-GPU frame
+(`parity_check`).
 `--impl reference` times the CPU path (the oracle port of the reference's shader logic; the reference itself is
 Win32/Vulkan-only and cannot run here) on a bounded scanline sample of the same workload, rank 0 only.
 """
@@ -100,22 +105,48 @@ class ClockSampler:
 
 
 WORKLOADS = {
-    "c2": "BASELINE configs[1]+[2] per GPU: 1,024 objects (2^21 clusters, 1.07e9 voxels), 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
+    "c2": "BASELINE configs[1]+[2]: 1,024 objects (2^21 clusters, 1.07e9 voxels), 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
     "c4": "BASELINE configs[3]: the configs[1] scene with 64 objects (the nearest to the player) moving every frame (translation.x += 0.5, angle += 1 degree "
           "per frame, 120-frame cycle): 64 transform uploads + incremental SVO update + primary visibility + 1-bounce SVO GI (1 spp), 3840x2160, 1 GPU",
     "c5": "BASELINE configs[4] per GPU: 12,288 objects (25,165,824 clusters, 1.29e10 voxels; 8 GPUs = 1.03e11 voxels) generated on the device, "
           "3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
+    "c2far": "dense-view stress, beside the headline: the configs[1] scene (1,024 objects, 2^21 clusters) with the far plane at 4000 so that several hundred "
+             "objects survive the cull instead of ~33, 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
 }
+SCALING = {"c2": "strong", "c4": "strong", "c2far": "strong", "c5": "weak"}
+C2FAR_FAR = 4000.0
 
 
 def build_scene(rank, n_ranks, workload="c2", host_bits=True):
-    """Rank's shard. c2: 1,024 objects out of a 32 x 32N lattice. c5: 12,288 objects out of a 384 x 32N lattice, masks generated on
-    the device. Ownership is interleaved over the lattice (cell (i, j) belongs to rank (i + j) % N): every rank holds 1/N of what the
-    camera sees instead of one rank holding all of it. The global lattice index decides seed, angle and position."""
+    """Rank's shard. c2 / c4 / c2far: the 32 x 32 lattice of configs[1] (1,024 objects), dealt out over the ranks -- the world is the
+    same at every N (strong scaling). c5: 12,288 objects out of a 384 x 32N lattice per rank, masks generated on the device (weak
+    scaling: the resident world grows with N). Ownership is interleaved over the lattice (cell (i, j) belongs to rank (i + j) % N):
+    every rank holds 1/N of what the camera sees instead of one rank holding all of it. The global lattice index decides seed,
+    angle and position."""
     from tg_b200 import scenes
     if workload == "c5":
         return scenes.config5_shard(rank, n_ranks, WIDTH, HEIGHT)
-    return scenes.grid_scene(f"config2_x{n_ranks}", 32, 32 * n_ranks, WIDTH, HEIGHT, k=3, with_bits=host_bits, owner=(rank, n_ranks))
+    s = scenes.grid_scene(f"config2_{rank}of{n_ranks}", 32, 32, WIDTH, HEIGHT, k=3, with_bits=host_bits, owner=(rank, n_ranks) if n_ranks > 1 else None)
+    if workload == "c2far":
+        s.camera.far = C2FAR_FAR
+    return s
+
+
+def union_scene(n_ranks, workload):
+    """The single-GPU scene whose frame the sharded frame must equal bit for bit: every rank's objects in rank-major order, so that
+    a cluster's pointer is its global pointer (base of rank r = r * clusters per rank). c5: the whole world does not fit one GPU;
+    only the objects that can write a pixel (within the far plane) are kept, so pointers differ and only depth / voxel / radiance
+    are comparable (union_pointers_match = False)."""
+    from tg_b200 import scenes
+    shards = [build_scene(r, n_ranks, workload, host_bits=False) for r in range(n_ranks)]
+    u = shards[0]
+    objects = [o for sh in shards for o in sh.objects]
+    pointers_match = True
+    if workload == "c5":
+        cam, far = u.camera.position, u.camera.far
+        objects = [o for o in objects if ((o.center[0] - cam[0]) ** 2 + (o.center[2] - cam[2]) ** 2) ** 0.5 < far + 160.0]
+        pointers_match = False
+    return scenes.SceneSpec(name=f"union_{workload}", width=WIDTH, height=HEIGHT, camera=u.camera, objects=objects, lut=u.lut, n_luts=u.n_luts), pointers_match
 
 
 def c4_movers(scene):
@@ -150,11 +181,10 @@ class CpuArm:
     (screen-rect pruned, OpenMP), then GI + shading of the same rows from that buffer with the oracle's SVO (built once,
     outside the timed region, like the GPU arm)."""
 
-    def __init__(self, scene, dynamic=False):
+    def __init__(self, scene, dynamic=False, ystep=CPU_YSTEP):
         from oracle import oracle as O
-        from tg_b200 import scenes
         self.O = O
-        self.dynamic, self.scene, self.frame_idx = dynamic, scene, 0
+        self.dynamic, self.scene, self.frame_idx, self.ystep = dynamic, scene, 0, ystep
         # all the host threads this process may use (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)
         O.lib().tgo_set_threads(len(os.sched_getaffinity(0)))
         self.cores = O.lib().tgo_max_threads()
@@ -162,7 +192,7 @@ class CpuArm:
         self.view = O.SceneView.from_scene(scene, with_lut=True)
         # the SVO only sees objects that can touch the +-512 box (the others fail the SAT against every root child)
         self.svo = self._build_svo(scene)
-        self.rows = np.arange(0, HEIGHT, CPU_YSTEP)
+        self.rows = np.arange(0, HEIGHT, ystep)
         self.frame = np.zeros((HEIGHT, WIDTH, 4), dtype=np.float32)
 
     def _build_svo(self, scene):
@@ -190,14 +220,14 @@ class CpuArm:
             self.view = O.SceneView.from_scene(moved, with_lut=True)
             O.svo_destroy(self.svo)
             self.svo = self._build_svo(moved)
-        vis, _ = O.visibility(self.view, self.rays, WIDTH, HEIGHT, O.VIS_SCREEN_RECT, 0, HEIGHT, CPU_YSTEP)
-        O.shade(self.view, self.rays, WIDTH, HEIGHT, vis, self.svo, gi=True, frame_seed=1, y0=0, y1=HEIGHT, ystep=CPU_YSTEP, out=self.frame)
+        vis, _ = O.visibility(self.view, self.rays, WIDTH, HEIGHT, O.VIS_SCREEN_RECT, 0, HEIGHT, self.ystep)
+        O.shade(self.view, self.rays, WIDTH, HEIGHT, vis, self.svo, gi=True, frame_seed=1, y0=0, y1=HEIGHT, ystep=self.ystep, out=self.frame)
         dt = time.perf_counter() - t0
         return dt, len(self.rows) * WIDTH + int((vis[self.rows] != CLEAR).sum())
 
     def text(self, n_rays):
         return (("64 objects moved + oracle tg_svo_create from scratch (whole tree, not sampled) + " if self.dynamic else "")
-                + f"every {CPU_YSTEP}th scanline of the 3840x2160 frame ({len(self.rows)} rows): oracle visibility (screen-rect pruned) + oracle GI/shading of "
+                + f"every {self.ystep}th scanline of the 3840x2160 frame ({len(self.rows)} rows): oracle visibility (screen-rect pruned) + oracle GI/shading of "
                 f"those rows, {n_rays} rays per sample, OpenMP")
 
     def close(self):
@@ -208,7 +238,7 @@ def run_reference(args, rank):
     """The CPU arm (rank 0 only; the other ranks exit without work)."""
     if rank != 0:
         return
-    arm = CpuArm(cpu_scene(args.workload), dynamic=args.workload == "c4")
+    arm = CpuArm(cpu_scene(args.workload), dynamic=args.workload == "c4", ystep=CPU_YSTEP * (4 if args.workload == "c2far" else 1))
     times, n_rays = [], 0
     for i in range(args.warmup + args.steps):
         secs, n_rays = arm.sample()
@@ -219,61 +249,118 @@ def run_reference(args, rank):
     total = sum(times)
     value = n_rays * len(times) / total / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
+            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": SCALING[args.workload], "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "sample": text},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": arm.cores, "kind": "port", "sample": text},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="tg_b200")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--merge", default="peer", choices=["peer", "nccl"], help="N > 1: peer = one kernel over peer memory (NVLink, falls back to nccl if unmappable); "
-                    "nccl = ncclAllReduce(u64, min) + materials + ncclReduceScatter")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the headline configuration (default); c5 = one 12,288-object shard of the 1e11-voxel world per GPU")
-    args = ap.parse_args()
+class Ctx:
+    """One process of the job: rank / world / device, and the few collectives bench.py itself needs."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
 
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    args.warmup = max(args.warmup, 3)
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
+    def reduce(self, x, op="max"):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN, "sum": self.dist.ReduceOp.SUM}[op])
+        return float(t.item())
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def parity_check(ctx, rt, frame, workload):
+    """N > 1, inside the warm-up: (1) the frame merged by the one-kernel peer-memory exchange equals, word for word and radiance bit
+    for radiance bit, the frame merged by the NCCL collectives; (2) the sharded frame equals the frame ONE GPU renders from the
+    union of the shards (every rank renders that union on its own GPU and compares the whole visibility buffer and the whole
+    gathered radiance frame). Returns the dict attached to the bench line; every entry is the AND over all ranks."""
+    from tg_b200.raytracer import from_scene
+
+    def sharded(kind):
+        frame(kind)
+        rt.synchronize()
+        ctx.barrier()
+        vis = rt.read_visibility()
+        rt.gather_radiance()
+        rt.synchronize()
+        rad = rt.read_radiance().view(np.uint32).copy()
+        ctx.barrier()
+        return vis, rad
+
+    vis_p, rad_p = sharded("peer")
+    vis_n, rad_n = sharded("nccl")
+    out = {"merged_eq_nccl": bool(np.array_equal(vis_p, vis_n) and np.array_equal(rad_p, rad_n)), "peer_memory_path_ran": bool(rt.timings()["merge_ms"] > 0)}
+    union, pointers_match = union_scene(ctx.world, workload)
+    ref = from_scene(union, device=ctx.local_rank)
+    try:
+        ref.set_gi(True, 1)
+        ref.clear()
+        ref.render()
+        ref.synchronize()
+        want_vis, want_rad = ref.read_visibility(), ref.read_radiance().view(np.uint32)
+    finally:
+        ref.destroy()
+    if pointers_match:
+        out["sharded_eq_single"] = bool(np.array_equal(vis_p, want_vis) and np.array_equal(rad_p, want_rad))
+        out["compared"] = "every u64 visibility word and every radiance bit of the 3840x2160 frame, on every rank, against one GPU rendering the union of the shards"
+    else:
+        # same depth24 and voxel for every pixel; the pointer field numbers clusters differently in the reduced union
+        field = np.uint64(0xFFFFFF00000001FF)
+        same_words = np.array_equal(vis_p & field, want_vis & field)
+        n_rad = int((rad_p != want_rad).any(axis=-1).sum())
+        out["sharded_eq_single"] = bool(same_words and n_rad == 0)
+        out["radiance_pixels_differing"] = n_rad
+        out["compared"] = ("depth24 + voxel9 of every visibility word and every radiance bit of the 3840x2160 frame, on every rank, against one GPU rendering "
+                           f"the {len(union.objects)} objects of the world that lie within the far plane (the whole world does not fit one GPU; pointers number "
+                           "clusters differently there)")
+    for k in ("merged_eq_nccl", "peer_memory_path_ran", "sharded_eq_single"):
+        out[k] = bool(ctx.reduce(1.0 if out[k] else 0.0, "min") > 0.5)
+    return out
+
+
+def gpu_arm(ctx, args, workload, steps, warmup, headline):
+    """One workload through libtgb200.so on this process's GPU; rank 0 returns the result dict, the others None."""
     import ctypes as C
-    import torch
-    import torch.distributed as dist
     import tg_b200
     from tg_b200.raytracer import comm_unique_id, from_scene
+    torch, rank, world, local_rank, dev = ctx.torch, ctx.rank, ctx.world, ctx.local_rank, ctx.dev
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    scene = build_scene(rank, world, args.workload, host_bits=False)  # masks generated on the device (same seeds as the host definition)
+    scene = build_scene(rank, world, workload, host_bits=False)  # masks generated on the device (same seeds as the host definition)
     rt = from_scene(scene, device=local_rank)
     n_clusters, n_objects = scene.n_clusters, len(scene.objects)
     if world > 1:
         rt.set_shard(rank, world, rank * n_clusters)
         ids = [comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
+        ctx.dist.broadcast_object_list(ids, src=0)
         rt.comm_init(ids[0], rank, world)
         rt.set_merge_kind(0 if args.merge == "peer" else 1)
     y0, y1 = rt.tile_rows()
 
     lib = tg_b200.lib()
     stream = torch.cuda.ExternalStream(lib.tgb200_stream(C.byref(rt._rt)), device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    host_tile = torch.empty(max(y1 - y0, 1) * WIDTH * 4, dtype=torch.float32).pin_memory()
-    host_tile_np = host_tile.numpy().reshape(max(y1 - y0, 1), WIDTH, 4)[:y1 - y0]
+    flush = ctx.flush
 
     # static scene: the SVO is built before the timed frames (collective when sharded); second build = warm number
     rt.set_gi(True, 1)
@@ -283,7 +370,7 @@ def main():
     rt.synchronize()
     svo_build_ms = rt.timings()["svo_ms"]
 
-    dynamic = args.workload == "c4"
+    dynamic = workload == "c4"
     assert not (dynamic and world > 1), "configs[3] is a 1-GPU configuration"
     movers, pose = c4_movers(scene) if dynamic else ([], None)
     frame_idx = [0]
@@ -295,12 +382,13 @@ def main():
             center, angle = pose(i, frame_idx[0])
             rt.set_object_transform(i, center, angle)
 
-    def frame():
+    def frame(merge=None):
+        merge = merge or args.merge
         if dynamic:
             move_objects()
         rt.clear()
         rt.render_visibility()
-        if world > 1 and args.merge == "nccl":
+        if world > 1 and merge == "nccl":
             rt.merge_visibility()   # else the shading stage merges this rank's tile straight from the peers' buffers
         if dynamic:
             rt.svo_update()   # incremental: only the leaves the moved objects touch are re-sampled
@@ -310,31 +398,24 @@ def main():
         with torch.cuda.stream(stream):
             flush.fill_(1)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---- warm-up ----
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         flush_l2()
         frame()
     rt.synchronize()
+    parity = parity_check(ctx, rt, frame, workload) if world > 1 else None
+    if parity is not None:   # the check changed the exchange kind twice: one more warm frame on the timed path
+        flush_l2()
+        frame()
+        rt.synchronize()
     n_hit = int((rt.read_visibility() != CLEAR).sum())   # merged buffer: identical on every rank
-    rays_per_frame = world * WIDTH * HEIGHT + n_hit       # every rank traces the full frame against its shard; one GI ray per hit pixel
+    rays_per_frame = WIDTH * HEIGHT + n_hit               # W*H primary + one GI ray per hit pixel, at every N
 
     # ---- device-timed: inputs resident in HBM, CUDA events on the library's stream, L2 flushed between steps ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     stage = {"clear_ms": 0.0, "cull_ms": 0.0, "visibility_ms": 0.0, "merge_ms": 0.0, "shading_ms": 0.0}
     if world > 1 and args.merge == "peer":
         stage.update({"merge_resolve_ms": 0.0, "merge_gather_ms": 0.0, "merge_kernel_ms": 0.0})  # parts of merge_ms (rank 0)
@@ -342,8 +423,8 @@ def main():
         stage["svo_ms"] = 0.0
     leaves_resampled = 0
     rt.reset_launch_counter()
-    barrier()
-    for i in range(args.steps):
+    ctx.barrier()
+    for i in range(steps):
         flush_l2()
         with torch.cuda.stream(stream):
             starts[i].record()
@@ -355,29 +436,28 @@ def main():
             stage[k] += t[k]
         if dynamic:
             leaves_resampled += rt.svo_leaves_resampled()
-    barrier()
+    ctx.barrier()
     if dynamic:  # hit pixels drift as the objects move: mean of the count before and after the timed frames
         n_hit = (n_hit + int((rt.read_visibility() != CLEAR).sum())) // 2
         rays_per_frame = WIDTH * HEIGHT + n_hit
     last = rt.timings()
     launches = last["n_kernel_launches"]
     clocks = sampler.stop()
-    dev_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, stops)))
-    ms_per_step = dev_ms / args.steps
+    dev_ms = ctx.reduce(sum(s.elapsed_time(e) for s, e in zip(starts, stops)), "max")
+    ms_per_step = dev_ms / steps
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end: the user's calls with HOST buffers. Every frame: tg_raytracer_clear + tg_raytracer_render with a frame sink
     # (tgb200_set_frame_sink): the shaded RGBA32F rows are copied into pinned host memory on a copy stream while the next frame
     # renders; two host buffers alternate, frame i is awaited (tgb200_wait_frame) after frame i+1 has been submitted. All
     # copies and the L2 flush of every frame are inside the timed region.
-    host_tiles = [host_tile_np, torch.empty(max(y1 - y0, 1) * WIDTH * 4, dtype=torch.float32).pin_memory().numpy().reshape(max(y1 - y0, 1), WIDTH, 4)[:y1 - y0]]
+    rows = max(y1 - y0, 1)
+    host_tiles = [torch.empty(rows * WIDTH * 4, dtype=torch.float32).pin_memory().numpy().reshape(rows, WIDTH, 4)[:y1 - y0] for _ in range(2)]
+    present_tiles = [torch.empty(rows * WIDTH, dtype=torch.int32).pin_memory().numpy().view(np.uint32).reshape(rows, WIDTH)[:y1 - y0] for _ in range(2)]
     bands = 1          # throughput: whole-frame copies behind the next frame's rendering (double-buffered radiance on the device)
     latency_bands = 4  # latency: four row bands, each copied while the next is shaded
 
-    present_tiles = [torch.empty(max(y1 - y0, 1) * WIDTH, dtype=torch.int32).pin_memory().numpy().view(np.uint32).reshape(max(y1 - y0, 1), WIDTH)[:y1 - y0] for _ in range(2)]
-
-    def e2e_loop(n, tiles=None):
-        tiles = tiles or host_tiles
+    def e2e_loop(n, tiles):
         tickets = []
         for i in range(n):
             flush_l2()
@@ -391,36 +471,34 @@ def main():
                 rt.wait_frame(tickets[i - 1])
         rt.wait_frame(tickets[-1])
 
-    e2e_loop(2)
-    rt.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(args.steps)
-    t_e2e = time.perf_counter() - t0
-    barrier()
-    t_e2e = max_over_ranks(t_e2e)
-    e2e_value = rays_per_frame * args.steps / t_e2e / 1e6
+    def e2e_timed(tiles):
+        e2e_loop(2, tiles)
+        rt.synchronize()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        e2e_loop(steps, tiles)
+        dt = time.perf_counter() - t0
+        ctx.barrier()
+        return ctx.reduce(dt, "max")
+
+    t_e2e = e2e_timed(host_tiles)
+    e2e_value = rays_per_frame * steps / t_e2e / 1e6
     assert np.isfinite(host_tiles[0]).all() and np.isfinite(host_tiles[1]).all()
     # the same loop with the reference's own end of frame: the present pass (present.frag -> B8G8R8A8_UNORM swapchain image), 4 B / pixel
-    e2e_loop(2, present_tiles)
-    rt.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(args.steps, present_tiles)
-    t_present = time.perf_counter() - t0
-    barrier()
-    t_present = max_over_ranks(t_present)
+    t_present = e2e_timed(present_tiles)
     assert present_tiles[0].any() and present_tiles[1].any()
-    # latency of ONE frame from the first call to the last byte in host memory (band overlap only, nothing in flight before it)
-    lat = []
-    for i in range(5):
-        flush_l2(); rt.synchronize()
-        t0 = time.perf_counter()
-        if dynamic:
-            move_objects()
-        rt.set_frame_sink(host_tiles[0], latency_bands); rt.clear(); rt.render(); rt.wait_frame(rt.frame_ticket())
-        lat.append(time.perf_counter() - t0)
-    frame_latency_ms = 1e3 * float(np.median(lat))
+    frame_latency_ms = None
+    if headline:
+        # latency of ONE frame from the first call to the last byte in host memory (band overlap only, nothing in flight before it)
+        lat = []
+        for i in range(5):
+            flush_l2(); rt.synchronize()
+            t0 = time.perf_counter()
+            if dynamic:
+                move_objects()
+            rt.set_frame_sink(host_tiles[0], latency_bands); rt.clear(); rt.render(); rt.wait_frame(rt.frame_ticket())
+            lat.append(time.perf_counter() - t0)
+        frame_latency_ms = 1e3 * float(np.median(lat))
     rt.set_frame_sink(None)
     rt.synchronize()
 
@@ -434,57 +512,130 @@ def main():
     except Exception:
         pass
     tile_px = WIDTH * int((rt.tile_physical_rows() >= 0).sum())  # the rows this rank shades (16-row bands dealt out to the ranks)
-    gi_bytes = tile_px * ALG_BYTES_PER_PIXEL_GI + n_objects * world * ALG_BYTES_PER_OBJECT + svo_bytes
-    gi_ms = stage["shading_ms"] / args.steps
+    n_objects_world = int(ctx.reduce(float(n_objects), "sum"))
+    gi_bytes = tile_px * ALG_BYTES_PER_PIXEL_GI + n_objects_world * ALG_BYTES_PER_OBJECT + svo_bytes
+    gi_ms = stage["shading_ms"] / steps
     vis_bytes = n_clusters * ALG_BYTES_PER_CLUSTER + n_objects * ALG_BYTES_PER_OBJECT + WIDTH * HEIGHT * ALG_BYTES_PER_PIXEL_VIS
-    vis_ms = (stage["clear_ms"] + stage["cull_ms"] + stage["visibility_ms"]) / args.steps
+    vis_ms = (stage["clear_ms"] + stage["cull_ms"] + stage["visibility_ms"]) / steps
     gi_achieved, vis_achieved = gi_bytes / (gi_ms * 1e-3) / 1e9, vis_bytes / (vis_ms * 1e-3) / 1e9
 
+    def roofline(kernel, alg_bytes, achieved, stage_ms, traffic_file):
+        # `frac` follows SURVEY 8(d)'s accounting (every submitted cluster counts, touched or not); `frac_touched` is what the kernel really
+        # moves through DRAM (ncu dram__bytes_read + write of the committed capture, c2 at N=1) over the same time: the honest HBM figure
+        traffic = profiled_traffic(traffic_file) if workload in ("c2", "c4") and world == 1 else None
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "frac_touched": (traffic / (stage_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "kernel": kernel, "algorithmic_bytes": alg_bytes, "stage_ms": stage_ms, "peak_source": peak_src,
+                "note": "issue-bound under divergence, not bandwidth-bound: frac counts SURVEY 8(d) bytes whether or not the kernel touches them; "
+                        "frac_touched = measured DRAM traffic / stage time / peak"}
+
+    result = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N=1 figure
-            arm = CpuArm(cpu_scene(args.workload), dynamic=args.workload == "c4")
+        if headline and not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N=1 figure
+            arm = CpuArm(cpu_scene(workload), dynamic=dynamic)
             samples = [arm.sample() for _ in range(12)]  # ~10-30 s of CPU work on the box host cores
             secs = sum(t for t, _ in samples)
             cpu = {"value": sum(n for _, n in samples) / secs / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
                    "sample": f"12 x ({arm.text(samples[0][1])}); {secs:.1f} s wall"}
             arm.close()
-        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
-                "config": {"workload": WORKLOADS[args.workload]
-                                       + (f"; world = {world} such shards (interleaved ownership), GI split by screen tile, merge = "
-                                          + ("one kernel over peer memory (min + winner's material per tile, NVLink)" if args.merge == "peer" else "ncclAllReduce(u64,min) + material reduce-scatter")
-                                          if world > 1 else ""),
-                           "rays_per_frame": rays_per_frame, "primary_rays": world * WIDTH * HEIGHT, "gi_rays": n_hit, "svo_build_ms": svo_build_ms, "svo_bytes": svo_bytes,
-                           "visible_objects": last["n_visible_objects"],
-                           **({"svo_leaves_resampled_per_frame": leaves_resampled / args.steps, "moved_objects_per_frame": len(movers)} if dynamic else {}),
-                           "gi_work_rank0": {"rays_traced_through_svo": last["n_gi_rays"], "node_visits": last["n_gi_node_visits"], "dda_steps": last["n_gi_dda_steps"], "advances": last["n_gi_advances"]},
-                           "l2": "flushed between steps (256 MiB write, outside the timed events)", "stage_ms": {k: v / args.steps for k, v in stage.items()}},
-                "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96 * world + 96 * len(movers), "d2h_bytes_per_step": WIDTH * HEIGHT * 16,
-                        "ms_per_step": 1e3 * t_e2e / args.steps, "frame_latency_ms": frame_latency_ms,
-                        "presented_bgra8": {"value": rays_per_frame * args.steps / t_present / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * t_present / args.steps,
-                                            "d2h_bytes_per_step": WIDTH * HEIGHT * 4,
-                                            "note": "same loop, the frame delivered as the reference delivers it (present.frag into the B8G8R8A8_UNORM swapchain image): "
-                                                    "k_present per band + 4 B / pixel over PCIe instead of the 16 B / pixel HDR rows"},
-                        "note": "per frame: tg_raytracer_clear + tg_raytracer_render through the C ABI with a frame sink: the shaded RGBA32F rows go to pinned host memory "
-                                "on a copy stream while the next frame renders (radiance double-buffered on the device, two host buffers alternate, frame i is awaited "
-                                "after frame i+1 was submitted; every rank receives its own tile). All copies and the per-frame L2 flush are inside the timed region; "
-                                f"frame_latency_ms is one isolated frame in {latency_bands} row bands (each copied while the next is shaded), first call to last byte in host memory. "
-                                "The scene arrays stay resident in HBM like the reference's SSBOs, the camera block is the per-frame input"},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": gi_achieved, "peak": peak, "unit": "GB/s", "frac": gi_achieved / peak, "traffic": profiled_traffic("k3_traffic.json"),
-                             "kernel": "GI + shading stage (k_object_frames + k_shade + k_gi_trace" + (" + k_resolve_material + reduce-scatter" if world > 1 else "") + ")",
-                             "algorithmic_bytes": gi_bytes, "stage_ms": gi_ms, "peak_source": peak_src},
-                "roofline_visibility": {"bound": "hbm", "achieved": vis_achieved, "peak": peak, "unit": "GB/s", "frac": vis_achieved / peak, "traffic": profiled_traffic("k1_traffic.json"),
-                                        "kernel": "visibility stage (k_clear_visibility + k_cull_objects + k_sort_frames + k_visibility)",
-                                        "algorithmic_bytes": vis_bytes, "stage_ms": vis_ms, "peak_source": peak_src},
-                "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        e2e_note = ("per frame: tg_raytracer_clear + tg_raytracer_render through the C ABI with a frame sink: the shaded RGBA32F rows go to pinned host memory "
+                    "on a copy stream while the next frame renders (radiance double-buffered on the device, two host buffers alternate, frame i is awaited "
+                    "after frame i+1 was submitted; every rank receives its own tile). All copies and the per-frame L2 flush are inside the timed region. "
+                    "The scene arrays stay resident in HBM like the reference's SSBOs, the camera block is the per-frame input")
+        if world > 1:
+            e2e_note += (f". Host-ingest bound at N = {world}: the {world} ranks together deliver the 133 MB HDR frame ({133 // world} MB each) into ONE host's memory "
+                         "every frame; the gap between e2e and the device-timed frame is that PCIe / host-memory ingest (it shrinks 4x with the 4 B / pixel "
+                         "presented frame, see presented_bgra8), not GPU work")
+        result = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": SCALING[workload], "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[workload]
+                                   + (f"; the objects are dealt out over {world} ranks (interleaved ownership), GI split by screen tile, merge = "
+                                      + ("one kernel over peer memory (min + winner's material per tile, NVLink)" if args.merge == "peer" else "ncclAllReduce(u64,min) + material reduce-scatter")
+                                      if world > 1 else ""),
+                       "rays_per_frame": rays_per_frame, "primary_rays": WIDTH * HEIGHT, "gi_rays": n_hit, "rank_primary_rays": world * WIDTH * HEIGHT,
+                       "objects_world": n_objects_world, "clusters_per_rank": n_clusters,
+                       "svo_build_ms": svo_build_ms, "svo_bytes": svo_bytes, "visible_objects": last["n_visible_objects"],
+                       **({"svo_leaves_resampled_per_frame": leaves_resampled / steps, "moved_objects_per_frame": len(movers)} if dynamic else {}),
+                       "gi_work_rank0": {"rays_traced_through_svo": last["n_gi_rays"], "node_visits": last["n_gi_node_visits"], "dda_steps": last["n_gi_dda_steps"], "advances": last["n_gi_advances"]},
+                       "l2": "flushed between steps (256 MiB write, outside the timed events)", "stage_ms": {k: v / steps for k, v in stage.items()}},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96 * world + 96 * len(movers), "d2h_bytes_per_step": WIDTH * HEIGHT * 16,
+                    "ms_per_step": 1e3 * t_e2e / steps, "frame_latency_ms": frame_latency_ms,
+                    "presented_bgra8": {"value": rays_per_frame * steps / t_present / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * t_present / steps,
+                                        "d2h_bytes_per_step": WIDTH * HEIGHT * 4,
+                                        "note": "same loop, the frame delivered as the reference delivers it (present.frag into the B8G8R8A8_UNORM swapchain image): "
+                                                "k_present per band + 4 B / pixel over PCIe instead of the 16 B / pixel HDR rows"},
+                    "note": e2e_note},
+            "gpu_launches": int(launches),
+            "roofline": roofline("GI + shading stage (k_object_frames + k_shade + k_gi_trace_pool" + (" + k_resolve_material + exchange" if world > 1 else "") + ")",
+                                 gi_bytes, gi_achieved, gi_ms, "k3_traffic.json"),
+            "roofline_visibility": roofline("visibility stage (k_clear_visibility + k_cull_objects + k_sort_frames + k_visibility)", vis_bytes, vis_achieved, vis_ms, "k1_traffic.json"),
+            "cpu_baseline": cpu}
+        if parity is not None:
+            result["parity_check"] = parity
     rt.comm_destroy()
     rt.destroy()
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.barrier()
+    return result
+
+
+def compact(r):
+    """What an `also` workload contributes to the headline line."""
+    keep = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "gpu_launches")}
+    keep["workload"] = r["config"]["workload"]
+    for k in ("rays_per_frame", "gi_rays", "visible_objects", "stage_ms", "svo_build_ms", "svo_leaves_resampled_per_frame", "moved_objects_per_frame", "objects_world", "clusters_per_rank"):
+        if k in r["config"]:
+            keep[k] = r["config"][k]
+    keep["fps"] = 1e3 / r["ms_per_step"]
+    keep["e2e"] = {k: r["e2e"][k] for k in ("value", "ms_per_step")}
+    keep["e2e"]["presented_bgra8_ms_per_step"] = r["e2e"]["presented_bgra8"]["ms_per_step"]
+    keep["roofline_frac"] = r["roofline"]["frac"]
+    keep["roofline_visibility_frac"] = r["roofline_visibility"]["frac"]
+    if "parity_check" in r:
+        keep["parity_check"] = r["parity_check"]
+    return keep
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="tg_b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge", default="peer", choices=["peer", "nccl"], help="N > 1: peer = one kernel over peer memory (NVLink, falls back to nccl if unmappable); "
+                    "nccl = ncclAllReduce(u64, min) + materials + ncclReduceScatter")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the headline configuration (default); c4 = configs[3]; c5 = one 12,288-object shard of the "
+                    "1e11-voxel world per GPU; c2far = dense-view stress")
+    ap.add_argument("--also", default=None, help="comma-separated workloads timed briefly in the same invocation and attached under `also` "
+                    "(default with --workload c2: c4 at N=1, c5 at every N, c2far at N=1; 'none' disables)")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")))
+        return
+    args.warmup = max(args.warmup, 3)
+
+    ctx = Ctx()
+    line = gpu_arm(ctx, args, args.workload, args.steps, args.warmup, headline=True)
+    if args.also is None:
+        also = (["c4", "c2far", "c5"] if ctx.world == 1 else ["c5"]) if args.workload == "c2" else []
+    else:
+        also = [w for w in args.also.split(",") if w and w != "none"]
+    extra = {}
+    for w in also:
+        if w == "c4" and ctx.world > 1:
+            continue
+        r = gpu_arm(ctx, args, w, max(5, min(args.steps, 10)), 3, headline=False)
+        if r is not None:
+            extra[w] = compact(r)
+    if ctx.rank == 0:
+        if extra:
+            line["also"] = extra
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -57,6 +57,11 @@ TG_EXPORT void tg_raytracer_create(const tg_camera* p_camera, u32 max_n_objects,
 /* tgvk_raytracer.c:791-796 (reference: TG_NOT_IMPLEMENTED; implemented here, Q10). */
 TG_EXPORT void tg_raytracer_destroy(tg_raytracer* p_raytracer);
 /* tgvk_raytracer.c:798-803 */
+/* TG_DEBUG_SHOW_BLOCKS: like the reference (tgvk_raytracer.c:1226-1272), the visibility buffer is then written by a primary-ray pass
+ * through the SVO (debug_visibility_svo.frag:27-71: depth24 | leaf node index | voxel % 512; the SVO is built when stale) instead of
+ * the cluster pass, and the shading pass hashes cluster_pointers[node index] (shading.frag:122-126,247-256; an index beyond the live
+ * pointer range reads as cluster 0). On a sharded raytracer the pointer table is distributed: the BLOCKS view hashes the node index
+ * itself, CLUSTER_INDEX the global pointer and COLOR_LUT_INDEX 0 -- those three debug views differ from the single-GPU image. */
 TG_EXPORT void tg_raytracer_set_debug_visualization(tg_raytracer* p_raytracer, tg_debug_show type);
 /* tgvk_raytracer.c:805-992: object with the reference's procedural simplex-noise terrain fill. */
 TG_EXPORT void tg_raytracer_create_object(tg_raytracer* p_raytracer, v3 center, v3u extent);
@@ -102,7 +107,9 @@ TG_EXPORT void        tg_raytracer_set_resolution(tg_raytracer* p_raytracer, u32
  * tgvk_raytracer.c:871-978). `p_solid_bits`: 16 u32 per cluster, clusters in pointer order
  * (x fastest, then y, then z), bit 64z+8y+x. `p_lut_indices`: 512 u8 per cluster, same order, or
  * NULL for the reference's rule (8*rel_x + vx) % 256 (tgvk_raytracer.c:947-978).
- * Returns the object index, TG_U32_MAX on error.
+ * `axis` must be a unit vector (|axis|^2 within 2e-5 of 1): tgm_m4_angle_axis does not normalise it and the object-level culling
+ * assumes a rigid transform; anything else is a recorded error (the same holds for create_object_synthetic, set_object_transform
+ * and scene_load). Returns the object index, TG_U32_MAX on error -- a failed create leaves the scene and the device as they were.
  */
 TG_EXPORT u32  tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
                                                     const u32* p_solid_bits, const u8* p_lut_indices);
@@ -165,6 +172,9 @@ TG_EXPORT void tgb200_svo_update(tg_raytracer* p_raytracer, b32 force_full); /* 
 /* Leaves the most recent tgb200_svo_update re-sampled (== all leaves after a full build). */
 TG_EXPORT u32  tgb200_svo_leaves_resampled(tg_raytracer* p_raytracer);
 TG_EXPORT void tgb200_render_shading(tg_raytracer* p_raytracer);             /* K3: (GI +) LUT shading */
+/* K3 over physical rows [first_row, one_past_last_row) only (one GPU): what one rank of a sharded frame shades, without the
+ * exchange -- used to measure and test the shading stage at a screen tile's size. Other rows of the radiance buffer keep their content. */
+TG_EXPORT void tgb200_render_shading_rows(tg_raytracer* p_raytracer, u32 first_row, u32 one_past_last_row);
 TG_EXPORT void tgb200_synchronize(tg_raytracer* p_raytracer);
 
 /* Copies of results into caller memory (synchronous). */

@@ -65,6 +65,7 @@ def lib():
         L.tgo_svo_destroy.argtypes = [C.POINTER(T.tg_svo)]
         L.tgo_svo_traverse_glsl.argtypes = [C.POINTER(T.tg_svo), T.f32, T.v3, T.v3, C.POINTER(T.v3), C.POINTER(T.v3), C.POINTER(T.u32), C.POINTER(T.u32)]
         L.tgo_svo_traverse_glsl.restype = T.f32
+        L.tgo_visibility_svo.argtypes = [C.POINTER(T.tg_svo), C.POINTER(T.tg_camera_rays), T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.u64)]
         L.tgo_svo_traverse_c.argtypes = [C.POINTER(T.tg_svo), T.v3, T.v3, C.POINTER(T.f32), C.POINTER(T.u32), C.POINTER(T.u32)]
         L.tgo_svo_traverse_c.restype = T.b32
         L.tgo_amanatides_woo.argtypes = [T.v3, T.v3, T.v3, C.POINTER(T.u32), C.POINTER(T.v3i)]
@@ -214,6 +215,13 @@ def visibility(view, rays, w, h, mode=VIS_SCREEN_RECT, y0=0, y1=None, ystep=1):
     out = np.empty(w * h, dtype=np.uint64)
     n = lib().tgo_visibility(C.byref(view.view), C.byref(rays), w, h, mode, y0, h if y1 is None else y1, ystep, T.ptr(out, T.u64))
     return out.reshape(h, w), int(n)
+
+
+def visibility_svo(svo, rays, w, h, y0=0, y1=None, ystep=1):
+    """debug_visibility_svo.frag: the BLOCKS view's primary rays through the SVO -> u64 words [h, w]."""
+    out = np.empty(w * h, dtype=np.uint64)
+    lib().tgo_visibility_svo(C.byref(svo), C.byref(rays), w, h, y0, h if y1 is None else y1, ystep, T.ptr(out, T.u64))
+    return out.reshape(h, w)
 
 
 def visibility_fragment(view, rays, w, h, px, py, cluster_pointer):

@@ -74,6 +74,8 @@ void tgo_svo_create(v3 extent_min, v3 extent_max, const tgo_scene_view* p_scene,
 void tgo_svo_destroy(tg_svo* p_svo);
 /* svo_functions.inc:1-329 (GLSL). Returns depth in [0,1) on hit, 1.0 on miss. */
 f32  tgo_svo_traverse_glsl(const tg_svo* p_svo, f32 far_plane, v3 ray_origin_ws, v3 ray_direction_ws, v3* p_hit_position, v3* p_hit_normal, u32* p_node_idx, u32* p_voxel_idx);
+/* debug_visibility_svo.frag:27-71 (the BLOCKS view's primary-ray pass through the SVO, tgvk_raytracer.c:1226-1272); rows y0, y0+ystep, ... < y1 */
+void tgo_visibility_svo(const tg_svo* p_svo, const tg_camera_rays* p_cam, u32 w, u32 h, u32 y0, u32 y1, u32 ystep, u64* p_out);
 /* tg_sparse_voxel_octree.c:558-740 (C twin, uses the Amanatides-Woo of util/tg_amanatides_woo.c:3-114) */
 b32  tgo_svo_traverse_c(const tg_svo* p_svo, v3 ray_origin, v3 ray_direction, f32* p_distance, u32* p_node_idx, u32* p_voxel_idx);
 /* util/tg_amanatides_woo.c:3-114 restated */

@@ -113,6 +113,17 @@ static void tgo__shade_pixel(const tgo_scene_view* p_scene, const tg_camera_rays
         return;
     }
 
+    if (debug_visualization == TG_DEBUG_SHOW_BLOCKS)
+    {
+        /* The word was written by debug_visibility_svo.frag (tgo_visibility_svo): its pointer field is an SVO NODE index, which
+         * shading.frag:122-126,247-256 nevertheless runs through the cluster-pointer table and hashes. Everything the shader computes
+         * in between (material, normal) is dead for this view. Defined deviation: a node index beyond the live pointer range reads
+         * whatever the reference's SSBO holds there; here it reads as cluster 0. */
+        const u32 cluster_idx_of_node = cluster_pointer_31b < p_scene->n_cluster_pointers ? p_scene->p_cluster_pointers[cluster_pointer_31b] : 0u;
+        tgo__hash_color(cluster_idx_of_node, p_rgba);
+        return;
+    }
+
     /* multi-GPU: the word carries a GLOBAL pointer; this view holds pointers [base, base + n) */
     const u32 local_pointer = cluster_pointer_31b - p_scene->global_pointer_base;
     const u32 cluster_idx = p_scene->p_cluster_pointers[local_pointer];

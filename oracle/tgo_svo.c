@@ -727,3 +727,38 @@ f32 tgo_svo_traverse_glsl(const tg_svo* p_svo, f32 far_plane, v3 ray_origin_ws, 
     }
     return result;
 }
+
+/*
+ * debug_visibility_svo.frag:27-71, the primary-ray pass the reference dispatches INSTEAD of the cluster pass while the BLOCKS
+ * debug view is on (tgvk_raytracer.c:1226-1272): one full-screen fragment per pixel traverses the SVO from the camera with the
+ * UN-normalised pixel direction and writes  depth24(d) << 40 | (node_idx & 0x7FFFFFFF) << 9 | voxel_idx % 512  with atomicMin
+ * whenever d <= 1 (:52-71). A miss returns d = 1, node = voxel = 0xFFFFFFFF: the word is then all ones, the clear value.
+ * Defined deviation: `u64(d * 16777215.0)` of a negative d (camera inside a solid voxel) is undefined in GLSL; both sides
+ * convert like CUDA's cvt.rzi.u64.f32 (negative and NaN -> 0).
+ * Rows y0, y0 + ystep, ... < y1; the other rows keep the clear value.
+ */
+void tgo_visibility_svo(const tg_svo* p_svo, const tg_camera_rays* p_cam, u32 w, u32 h, u32 y0, u32 y1, u32 ystep, u64* p_out)
+{
+    if (y1 > h) y1 = h;
+    if (ystep == 0) ystep = 1;
+    for (size_t i = 0; i < (size_t)w * h; i++) p_out[i] = TG_VIS_CLEAR; /* clear.comp:19 */
+    const v3 camera = tgo_v3(p_cam->camera.x, p_cam->camera.y, p_cam->camera.z);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (i64 py = (i64)y0; py < (i64)y1; py += ystep)
+    {
+        for (u32 px = 0; px < w; px++)
+        {
+            const v3 dir = tgo_pixel_ray_direction_nn(p_cam, w, h, px, (u32)py);
+            v3 hp, hn; u32 node_idx, voxel_idx;
+            const f32 d = tgo_svo_traverse_glsl(p_svo, p_cam->far_plane, camera, dir, &hp, &hn, &node_idx, &voxel_idx);
+            if (d <= 1.0f)
+            {
+                const f32 dq = d * TG_VIS_DEPTH_SCALE;
+                const u64 depth_24b = dq > 0.0f ? (u64)dq : 0; /* NaN compares false -> 0 */
+                const u64 word = (depth_24b << TG_VIS_DEPTH_SHIFT) | ((u64)(node_idx & 2147483647u) << TG_VIS_POINTER_SHIFT) | (u64)(voxel_idx % 512u);
+                u64* p = &p_out[(size_t)py * w + px];
+                if (word < *p) *p = word; /* atomicMin on the cleared word */
+            }
+        }
+    }
+}

@@ -1,0 +1,129 @@
+/*
+ * TEST INFRASTRUCTURE. The per-ray traversal state machine of k_gi_trace_pool (tg_b200/csrc/tgb_gi_walk.cuh) compiled
+ * by a plain C++ compiler and driven ray by ray on the host, so that its hit / miss decisions can be held against the
+ * oracle's transcription of svo_functions.inc without a GPU (tests/test_gi_walk_cpu.py). The flattened tree is rebuilt
+ * here with the rules of k_svo_flatten (tgb_svo.cu); phase budgets are parameters so that the test can vary them the
+ * way the kernel's scheduler does (a ray may be suspended after any number of steps).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../tg_b200/csrc/tgb_gi_walk.cuh"
+
+extern "C" {
+
+/* k_svo_flatten on the host: p_grid[32^3 + 1], last word non-zero = complete */
+void tgbsim_flatten(const u32* p_nodes, const u32* p_leaf_data, u32 n_nodes, u32 n_leaves, u32* p_grid)
+{
+    p_grid[TGB_TOP_GRID_CELLS] = 1;
+    for (u32 cell = 0; cell < TGB_TOP_GRID_CELLS; cell++)
+    {
+        const u32 cx = cell & 31u, cy = (cell >> 5) & 31u, cz = cell >> 10;
+        u32 node = 0, entry = 0;
+        bool ok = true, done = false;
+        for (u32 level = 0; level < 5u && !done; level++)
+        {
+            const u32 shift = 4u - level;
+            const u32 oct = ((cx >> shift) & 1u) | (((cy >> shift) & 1u) << 1) | (((cz >> shift) & 1u) << 2);
+            const u32 node_data = p_nodes[node];
+            const u32 child_pointer = node_data & 0xFFFFu, valid_mask = (node_data >> 16) & 0xFFu, leaf_mask = node_data >> 24;
+            entry = level << TGB_TOP_LEVEL_SHIFT;
+            if (((valid_mask >> oct) & 1u) == 0) { done = true; break; }
+            const u32 child = node + child_pointer + (u32)__builtin_popcount(valid_mask & ((1u << oct) - 1u));
+            if (child >= n_nodes) { ok = false; done = true; break; }
+            if ((leaf_mask >> oct) & 1u)
+            {
+                if (level != 4u) ok = false;
+                const u32 data_pointer = p_nodes[child];
+                if (data_pointer >= n_leaves || data_pointer > TGB_TOP_POINTER_MASK) ok = false;
+                else if (p_leaf_data[(uint64_t)data_pointer * 65u] != 0) entry |= TGB_TOP_HAS_DATA | data_pointer;
+                done = true;
+                break;
+            }
+            node = child;
+        }
+        if (!done) ok = false;
+        p_grid[cell] = entry;
+        if (!ok) p_grid[TGB_TOP_GRID_CELLS] = 0;
+    }
+}
+
+/*
+ * n rays (origin_ws, dir) through the flattened tree exactly as k_shade + k_gi_trace_pool handle them: root slab test
+ * (svo_functions.inc:27-31; a miss is unoccluded), then service / tree / DDA phases until the ray is decided.
+ * p_occluded[i] = 1 when the shader's traversal would return a depth < 1. Returns the number of rays that hit the
+ * iteration cap (must be 0 on valid input).
+ */
+u32 tgbsim_gi_trace(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, u32 n, const f32* p_origins, const f32* p_dirs,
+                    u32 tree_reps, u32 dda_steps, u8* p_occluded, u64* p_work /* [3]: look-ups, DDA steps, advances */)
+{
+    tgb_gi_frame fr;
+    tgb_gi_frame_init(&fr, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane, p_grid, p_voxels);
+    u32 n_capped = 0;
+    for (u32 i = 0; i < n; i++)
+    {
+        const v3 origin = tgb_v3(p_origins[3 * i], p_origins[3 * i + 1], p_origins[3 * i + 2]);
+        const v3 d = tgb_v3(p_dirs[3 * i], p_dirs[3 * i + 1], p_dirs[3 * i + 2]);
+        f32 e0, e1;
+        if (!tgb_ray_aabb(tgb_sub(origin, fr.center), d, fr.bmin, fr.bmax, &e0, &e1)) { p_occluded[i] = 0; continue; } /* k_shade: not queued */
+        v3 position, t_delta, t_max = tgb_v3(0, 0, 0);
+        u32 flags, cell = 0, data = 0, kind = TGB_RAY_TREE;
+        i32 x = 0, y = 0, z = 0;
+        u32 n_visits = 0, n_steps = 0, n_advances = 0;
+        tgb_gi_ray_start(&fr, origin, d, e0, &position, &t_delta, &flags);
+        bool occluded = false;
+        for (;;)
+        {
+            if (kind == TGB_RAY_TREE) kind = tgb_gi_tree_phase(&fr, d, t_delta, &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
+            else if (kind == TGB_RAY_DDA)
+            {
+                if (flags & TGB_RF_SETUP)
+                {
+                    flags &= ~TGB_RF_SETUP;
+                    v3 child_min; f32 child_size;
+                    tgb_cell_box(&fr, cell, &child_min, &child_size);
+                    tgb_gi_dda_setup(d, position, child_min, child_size, &x, &y, &z, &t_max);
+                }
+                kind = tgb_gi_dda_phase(p_voxels + (uint64_t)data * TG_SVO_BLOCK_WORDS, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
+                /* what the kernel stores between phases: 5 bits per coordinate */
+                if (kind == TGB_RAY_DDA || kind == TGB_RAY_HIT) { x &= 31; y &= 31; z &= 31; }
+            }
+            else if (kind == TGB_RAY_HIT)
+            {
+                v3 child_min; f32 child_size;
+                tgb_cell_box(&fr, cell, &child_min, &child_size);
+                kind = tgb_gi_hit_test(&fr, origin, d, child_min, x, y, z);
+                if (kind == TGB_RAY_IDLE) { occluded = true; break; }
+            }
+            else /* MISS */
+            {
+                if (flags & TGB_RF_BORDER) kind = tgb_gi_border_test(&fr, d, position, &flags);
+                if (kind == TGB_RAY_MISS) { if ((cell >> 18) > TGB_TRAVERSE_MAX_ITERS) n_capped++; break; }
+            }
+        }
+        p_occluded[i] = occluded ? 1 : 0;
+        if (p_work) { p_work[0] += n_visits; p_work[1] += n_steps; p_work[2] += n_advances; }
+    }
+    return n_capped;
+}
+
+}
+
+#include "../../tg_b200/csrc/tgb_svo_traverse.cuh"
+
+extern "C" {
+
+/* tgb_svo_traverse_stack (the BLOCKS view's traversal) for n rays: result bits, node index, voxel index, packed word */
+void tgbsim_svo_traverse(const u32* p_nodes, const u32* p_leaf_data, const u32* p_voxels, const f32* p_bmin, const f32* p_bmax, f32 far_plane, u32 n,
+                         const f32* p_origins, const f32* p_dirs, f32* p_result, u32* p_node_idx, u32* p_voxel_idx, u64* p_word)
+{
+    for (u32 i = 0; i < n; i++)
+    {
+        p_result[i] = tgb_svo_traverse_stack(p_nodes, p_leaf_data, p_voxels, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane,
+                                             tgb_v3(p_origins[3 * i], p_origins[3 * i + 1], p_origins[3 * i + 2]), tgb_v3(p_dirs[3 * i], p_dirs[3 * i + 1], p_dirs[3 * i + 2]),
+                                             &p_node_idx[i], &p_voxel_idx[i]);
+        p_word[i] = tgb_svo_visibility_word(p_result[i], p_node_idx[i], p_voxel_idx[i]);
+    }
+}
+
+}

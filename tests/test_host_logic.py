@@ -290,3 +290,31 @@ int main(void)
         assert np.array_equal(phys[virt], np.arange(h)), (h, n)   # the two maps are inverse to each other on the frame's rows
         if n == 1:
             assert np.array_equal(virt, np.arange(h))
+
+
+def test_non_unit_rotation_axis_is_rejected_and_a_failed_create_leaves_the_scene_untouched():
+    """tgm_m4_angle_axis does not normalise its axis and the object-level culling assumes a rigid transform, so the axis is
+    checked where it enters; and a create that fails must not consume a slot (host-only scene bookkeeping, no GPU needed)."""
+    import ctypes as C
+    import tg_b200
+    from tg_b200 import ctypes_defs as T
+    L = tg_b200.lib()
+    L.tgb200_clear_error()
+    scene = T.tg_scene()
+    L.tgb200_scene_init(C.byref(scene), 4, 64)
+    try:
+        a = L.tgb200_scene_alloc_object(C.byref(scene), T.v3(0, 0, 0), T.v3u(8, 8, 8), 0.5, T.v3(0.0, 1.0, 0.0))
+        assert a != 0xFFFFFFFF and L.tgb200_last_error() is None
+        before = (scene.n_objects, scene.n_cluster_pointers, scene.n_available_object_indices, scene.n_available_cluster_indices)
+        for axis in ((0.0, 2.0, 0.0), (0.0, 0.0, 0.0), (0.6, 0.6, 0.6)):
+            b = L.tgb200_scene_alloc_object(C.byref(scene), T.v3(0, 0, 0), T.v3u(8, 8, 8), 0.5, T.v3(*axis))
+            assert b == 0xFFFFFFFF and b"unit vector" in L.tgb200_last_error()
+            L.tgb200_clear_error()
+            assert before == (scene.n_objects, scene.n_cluster_pointers, scene.n_available_object_indices, scene.n_available_cluster_indices)
+        # a normalised non-axis-aligned axis is fine
+        n = 3 ** -0.5
+        c = L.tgb200_scene_alloc_object(C.byref(scene), T.v3(0, 0, 0), T.v3u(8, 8, 8), 0.5, T.v3(n, n, n))
+        assert c != 0xFFFFFFFF and L.tgb200_last_error() is None
+    finally:
+        L.tgb200_scene_free(C.byref(scene))
+        L.tgb200_clear_error()

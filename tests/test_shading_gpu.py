@@ -104,6 +104,36 @@ def test_debug_visualizations(gpu, oracle):
         rt.destroy()
 
 
+@pytest.mark.parametrize("make", [lambda: scenes.small_grid(), lambda: scenes.config1(k=3, width=320, height=180)])
+def test_blocks_view_runs_the_svo_primary_ray_pass(gpu, oracle, make):
+    """TG_DEBUG_SHOW_BLOCKS (tgvk_raytracer.c:1226-1272): clear() + render() write the visibility buffer with one primary ray per pixel
+    through the SVO (debug_visibility_svo.frag:27-71: depth24 | leaf node index | voxel % 512) instead of the cluster pass -- bit-exact
+    against the oracle's twin -- and the shading pass hashes cluster_pointers[node index] (shading.frag:247-256)."""
+    s = make()
+    rays = oracle.camera_rays(oracle.camera_from_spec(s.camera))
+    view = oracle.SceneView.from_scene(s, with_lut=True)
+    svo = oracle.svo_create(view)
+    rt = from_scene(s)
+    try:
+        want_vis = oracle.visibility_svo(svo, rays, s.width, s.height)
+        want_rad = oracle.shade(view, rays, s.width, s.height, want_vis, None, gi=False, debug=5)
+        cluster_pass, _ = oracle.visibility(view, rays, s.width, s.height, oracle.VIS_SCREEN_RECT)
+        rt.set_debug_visualization(5)
+        rt.clear(); rt.render(); rt.synchronize()
+        got = rt.read_visibility()
+        assert np.array_equal(got, want_vis), f"{int((got != want_vis).sum())} of {got.size} BLOCKS-view words differ"
+        hit = want_vis != np.uint64(0xFFFFFFFFFFFFFFFF)
+        assert hit.sum() > 500 and (want_vis[hit] != cluster_pass[hit]).any(), "the SVO pass writes node indices, not cluster pointers"
+        close(rt.read_radiance(), want_rad, "BLOCKS view")
+        # leaving the view brings the cluster pass back
+        rt.set_debug_visualization(0)
+        rt.clear(); rt.render(); rt.synchronize()
+        assert np.array_equal(rt.read_visibility(), cluster_pass)
+    finally:
+        oracle.svo_destroy(svo)
+        rt.destroy()
+
+
 def test_per_object_lut_and_seed_dependence(gpu, oracle):
     s = scenes.small_grid()
     for i, o in enumerate(s.objects):

@@ -59,6 +59,7 @@ SYMBOLS = {
     "tgb200_svo_update": (None, [_RT, T.b32]),
     "tgb200_svo_leaves_resampled": (T.u32, [_RT]),
     "tgb200_render_shading": (None, [_RT]),
+    "tgb200_render_shading_rows": (None, [_RT, T.u32, T.u32]),
     "tgb200_synchronize": (None, [_RT]),
     "tg_raytracer_read_visibility": (None, [_RT, _P(T.u64)]),
     "tg_raytracer_read_radiance": (None, [_RT, _P(T.f32)]),

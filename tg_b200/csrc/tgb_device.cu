@@ -9,7 +9,7 @@
 
 #include "tgb_device.cuh"
 
-/* tuning knobs read from the environment (integers; unset or malformed = the default) */
+/* tuning knobs read from the environment at every use (integers; unset or malformed = the default): a sweep can change them between frames */
 extern "C" i32 tgbd_env_int(const char* p_name, i32 fallback)
 {
     const char* p = getenv(p_name);

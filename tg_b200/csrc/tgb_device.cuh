@@ -14,13 +14,7 @@
 #include "tgb_math.h"
 #include "tgb_hoist.h"
 #include "tgb_rows.h"
-
-/* the flattened tree (k_svo_flatten, tgb_svo.cu): one word per 32^3 cell of the 1024^3 box */
-#define TGB_TOP_GRID_DIM      32u
-#define TGB_TOP_GRID_CELLS    (TGB_TOP_GRID_DIM * TGB_TOP_GRID_DIM * TGB_TOP_GRID_DIM)
-#define TGB_TOP_HAS_DATA      0x80000000u /* the terminal node is a leaf with n != 0: bits 0..27 = data_pointer */
-#define TGB_TOP_LEVEL_SHIFT   28u         /* bits 28..30: depth of the inner node whose child is terminal (child side = 512 >> level) */
-#define TGB_TOP_POINTER_MASK  0x0FFFFFFFu
+#include "tgb_gi_walk.cuh" /* flattened-tree layout (TGB_TOP_*) + the per-ray traversal pieces */
 
 #define TGB_MAX_BANDS  16
 #define TGB_MAX_RANKS  16

@@ -1,0 +1,246 @@
+/*
+ * tgb_gi_pool.cu -- K3b, the queued secondary rays through the 1-bit SVO with SEVERAL RAYS PER LANE.
+ *
+ *   SVO traversal      assets/shaders/raytracer/svo_functions.inc:1-329 (per-ray pieces: tgb_gi_walk.cuh)
+ *   secondary rays     tgvk_raytracer.c:1405-1431, TODO.h:33-43 (queued by k_shade, tgb_shade.cu)
+ *
+ * Secondary rays are incoherent: at any moment some rays of a warp cross empty space (TREE: advance to the far border of
+ * the terminal box + look the next one up), some walk a 32^3 leaf block voxel by voxel (DDA), a few wait for a decision
+ * (HIT / MISS) or a new ray (IDLE). k_gi_trace_flat (tgb_shade.cu) gave every lane one ray and let the warp run the phase
+ * most lanes waited for: 12.8 of 32 lanes did useful work per issued instruction (profiles/r01q_k3b_summary.txt), the
+ * kernel being issue-bound that is what its duration follows.
+ *
+ * Here every lane owns K rays whose state (16 words, tgb_gi_walk.cuh) lives in shared memory -- one column per word,
+ * [word][k][thread], so a lane's accesses never conflict -- and registers only hold the working set of the phase being run.
+ * Each warp iteration counts the lanes that have AT LEAST ONE ray waiting for each phase, runs the phase with the larger
+ * count, and every such lane picks one of its waiting rays: with p the fraction of rays in a phase, 1 - (1 - p)^K of the
+ * lanes take part instead of p. Nothing is exchanged between lanes (no filing, no sorting: the shared-memory pools of
+ * round 1 lost to exactly that); a phase loads ~10 words and stores ~5 per lane around a few hundred instructions.
+ * The arithmetic per ray is untouched, so hit / miss decisions are those of k_gi_trace_flat and of the shader.
+ */
+#include "tgb_device.cuh"
+#include "tgb_gi_walk.cuh"
+
+#define TGB_POOL_THREADS 128
+#define TGB_POOL_WORDS   16
+
+/* shared-memory columns */
+enum { W_DX = 0, W_DY, W_DZ, W_PX, W_PY, W_PZ, W_TDX, W_TDY, W_TDZ, W_TMX, W_TMY, W_TMZ, W_CELL, W_VOX, W_DATA, W_SLOT };
+
+template <int K>
+__global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
+                                                                    const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, float4* __restrict__ p_out,
+                                                                    u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot, u32 n_sms)
+{
+    if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
+
+    extern __shared__ u32 s_pool[];
+    const u32 tid = threadIdx.x, lane = tid & 31u;
+#define S(w, k) s_pool[((u32)(w) * K + (u32)(k)) * TGB_POOL_THREADS + tid]
+#define SF(w, k) __uint_as_float(S(w, k))
+
+    const u32 n_rays = p_q_count[0];
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
+    /* few rays (a band, a screen tile of a sharded frame): fewer CTAs so that every ray slot still sees min_rays_per_slot rays --
+     * a lane whose K rays all came from the last refill finishes them with the warp draining around it */
+    if (blockIdx.x >= n_sms && (u64)blockIdx.x * (TGB_POOL_THREADS * K) * min_rays_per_slot >= n_rays) return;
+
+    u32 kinds = 0; /* 4 bits per ray slot, all IDLE */
+    bool exhausted = false;
+    u32 n_visits = 0, n_steps = 0, n_advances = 0;
+
+    for (;;)
+    {
+        u32 has_tree = 0, has_dda = 0, n_svc = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+        {
+            const u32 kd = (kinds >> (4 * k)) & 15u;
+            has_tree |= (kd == TGB_RAY_TREE) ? 1u : 0u;
+            has_dda |= (kd == TGB_RAY_DDA) ? 1u : 0u;
+            n_svc += ((kd >= TGB_RAY_HIT) | ((kd == TGB_RAY_IDLE) & !exhausted)) ? 1u : 0u;
+        }
+        const u32 counts = __reduce_add_sync(0xFFFFFFFFu, has_tree | (has_dda << 8) | (n_svc << 16));
+        const u32 n_tree = counts & 0xFFu, n_dda = (counts >> 8) & 0xFFu, n_service = counts >> 16;
+        if (n_tree + n_dda == 0 && n_service == 0) break; /* queue drained and every ray finished */
+
+        if (n_service >= service_slots || n_tree + n_dda == 0)
+        {
+            /* ---- service: unoccluded rays return their ambient term, voxel hits are decided, idle slots fetch rays ---- */
+#pragma unroll
+            for (int k = 0; k < K; k++)
+            {
+                u32 kd = (kinds >> (4 * k)) & 15u;
+                if (kd == TGB_RAY_MISS)
+                {
+                    const u32 vox = S(W_VOX, k);
+                    u32 flags = vox >> 16;
+                    if (flags & TGB_RF_BORDER)
+                    {
+                        kd = tgb_gi_border_test(&fr, tgb_v3(SF(W_DX, k), SF(W_DY, k), SF(W_DZ, k)), tgb_v3(SF(W_PX, k), SF(W_PY, k), SF(W_PZ, k)), &flags);
+                        S(W_VOX, k) = (vox & 0xFFFFu) | (flags << 16);
+                    }
+                }
+                if (kd == TGB_RAY_MISS)
+                {
+                    /* ambient * 1 + lo; float addition commutes and the reductions do not stall the lane */
+                    const u32 slot = S(W_SLOT, k);
+                    const float4 q0 = p_q0[slot], q2 = p_q2[slot];
+                    f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
+                    atomicAdd(p_pixel + 0, q2.x);
+                    atomicAdd(p_pixel + 1, q2.y);
+                    atomicAdd(p_pixel + 2, q2.z);
+                    kd = TGB_RAY_IDLE;
+                }
+                else if (kd == TGB_RAY_HIT)
+                {
+                    const float4 q0 = p_q0[S(W_SLOT, k)];
+                    const u32 vox = S(W_VOX, k);
+                    v3 child_min; f32 child_size;
+                    tgb_cell_box(&fr, S(W_CELL, k), &child_min, &child_size);
+                    kd = tgb_gi_hit_test(&fr, tgb_v3(q0.x, q0.y, q0.z), tgb_v3(SF(W_DX, k), SF(W_DY, k), SF(W_DZ, k)), child_min,
+                                         (i32)(vox & 31u), (i32)((vox >> 5) & 31u), (i32)((vox >> 10) & 31u));
+                }
+                if (!exhausted)
+                {
+                    const u32 idle = __ballot_sync(0xFFFFFFFFu, kd == TGB_RAY_IDLE);
+                    if (idle)
+                    {
+                        const u32 n = (u32)__popc(idle);
+                        u32 base = 0;
+                        const u32 leader = (u32)(__ffs(idle) - 1);
+                        if (lane == leader) base = atomicAdd(&p_q_count[1], n);
+                        base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
+                        const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
+                        if (kd == TGB_RAY_IDLE && mine < n_rays)
+                        {
+                            const float4 q0 = p_q0[mine], q1 = p_q1[mine];
+                            const v3 d = tgb_v3(q1.x, q1.y, q1.z);
+                            v3 position, t_delta; u32 flags;
+                            tgb_gi_ray_start(&fr, tgb_v3(q0.x, q0.y, q0.z), d, q1.w, &position, &t_delta, &flags);
+                            S(W_DX, k) = __float_as_uint(d.x); S(W_DY, k) = __float_as_uint(d.y); S(W_DZ, k) = __float_as_uint(d.z);
+                            S(W_PX, k) = __float_as_uint(position.x); S(W_PY, k) = __float_as_uint(position.y); S(W_PZ, k) = __float_as_uint(position.z);
+                            S(W_TDX, k) = __float_as_uint(t_delta.x); S(W_TDY, k) = __float_as_uint(t_delta.y); S(W_TDZ, k) = __float_as_uint(t_delta.z);
+                            S(W_CELL, k) = 0u;          /* iterations = 0 */
+                            S(W_VOX, k) = flags << 16;  /* no advance pending: the first tree phase looks the entry cell up */
+                            S(W_SLOT, k) = mine;
+                            kd = TGB_RAY_TREE;
+                        }
+                        exhausted = base + n >= n_rays;
+                    }
+                }
+                kinds = (kinds & ~(15u << (4 * k))) | (kd << (4 * k));
+            }
+            continue;
+        }
+
+        if (n_dda + dda_bias > n_tree && n_dda > 0)
+        {
+            if (has_dda)
+            {
+                u32 k = 0;
+#pragma unroll
+                for (int j = K - 1; j >= 0; j--) if (((kinds >> (4 * j)) & 15u) == TGB_RAY_DDA) k = (u32)j;
+                const u32 vox = S(W_VOX, k);
+                u32 flags = vox >> 16;
+                const v3 t_delta = tgb_v3(SF(W_TDX, k), SF(W_TDY, k), SF(W_TDZ, k));
+                const u32* __restrict__ p_block = fr.p_voxels + (u64)S(W_DATA, k) * TG_SVO_BLOCK_WORDS;
+                i32 x, y, z; v3 t_max;
+                if (flags & TGB_RF_SETUP)
+                {
+                    /* :111-176: the lanes that entered a leaf since their last DDA phase set up together */
+                    flags &= ~TGB_RF_SETUP;
+                    v3 child_min; f32 child_size;
+                    tgb_cell_box(&fr, S(W_CELL, k), &child_min, &child_size);
+                    tgb_gi_dda_setup(tgb_v3(SF(W_DX, k), SF(W_DY, k), SF(W_DZ, k)), tgb_v3(SF(W_PX, k), SF(W_PY, k), SF(W_PZ, k)), child_min, child_size, &x, &y, &z, &t_max);
+                }
+                else
+                {
+                    x = (i32)(vox & 31u); y = (i32)((vox >> 5) & 31u); z = (i32)((vox >> 10) & 31u);
+                    t_max = tgb_v3(SF(W_TMX, k), SF(W_TMY, k), SF(W_TMZ, k));
+                }
+                const u32 kd = tgb_gi_dda_phase(p_block, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
+                S(W_TMX, k) = __float_as_uint(t_max.x); S(W_TMY, k) = __float_as_uint(t_max.y); S(W_TMZ, k) = __float_as_uint(t_max.z);
+                S(W_VOX, k) = ((u32)x & 31u) | (((u32)y & 31u) << 5) | (((u32)z & 31u) << 10) | (flags << 16);
+                kinds = (kinds & ~(15u << (4 * k))) | (kd << (4 * k));
+            }
+        }
+        else if (has_tree)
+        {
+            u32 k = 0;
+#pragma unroll
+            for (int j = K - 1; j >= 0; j--) if (((kinds >> (4 * j)) & 15u) == TGB_RAY_TREE) k = (u32)j;
+            const u32 vox = S(W_VOX, k);
+            u32 flags = vox >> 16, cell = S(W_CELL, k), data = 0;
+            v3 position = tgb_v3(SF(W_PX, k), SF(W_PY, k), SF(W_PZ, k));
+            const u32 kd = tgb_gi_tree_phase(&fr, tgb_v3(SF(W_DX, k), SF(W_DY, k), SF(W_DZ, k)), tgb_v3(SF(W_TDX, k), SF(W_TDY, k), SF(W_TDZ, k)),
+                                             &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
+            S(W_PX, k) = __float_as_uint(position.x); S(W_PY, k) = __float_as_uint(position.y); S(W_PZ, k) = __float_as_uint(position.z);
+            S(W_CELL, k) = cell;
+            S(W_VOX, k) = (vox & 0xFFFFu) | (flags << 16);
+            if (kd == TGB_RAY_DDA) S(W_DATA, k) = data;
+            kinds = (kinds & ~(15u << (4 * k))) | (kd << (4 * k));
+        }
+    }
+#undef S
+#undef SF
+    /* [2] look-ups, [3] DDA steps, [4] advances of this frame */
+    n_visits = __reduce_add_sync(0xFFFFFFFFu, n_visits);
+    n_steps = __reduce_add_sync(0xFFFFFFFFu, n_steps);
+    n_advances = __reduce_add_sync(0xFFFFFFFFu, n_advances);
+    if (lane == 0)
+    {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_visits);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 2, (unsigned long long)n_steps);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 3, (unsigned long long)n_advances);
+    }
+}
+
+/*
+ * Launch for one band of rays (called by tgbd__shade_launch, tgb_shade.cu, after k_shade queued them). Tuning knobs are read
+ * from the environment once (benchmark sweeps only): rays per lane, CTAs per SM, phase budgets, service threshold.
+ */
+template <int K>
+static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, u32 ctas_per_sm, u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot)
+{
+    const size_t smem = (size_t)TGB_POOL_WORDS * K * TGB_POOL_THREADS * sizeof(u32);
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        TGB_CUDA(cudaFuncSetAttribute(k_gi_trace_pool<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    /* resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA) and the 2048-thread limit */
+    u32 fit = (u32)((227u * 1024u) / (smem + 1024u));
+    if (fit > 2048u / TGB_POOL_THREADS) fit = 2048u / TGB_POOL_THREADS;
+    if (ctas_per_sm == 0 || ctas_per_sm > fit) ctas_per_sm = fit < 8u ? fit : 8u;
+    k_gi_trace_pool<K><<<d->n_sms * ctas_per_sm, TGB_POOL_THREADS, smem, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_radiance,
+                                                                                     service_slots, dda_bias, tree_reps, dda_steps, min_rays_per_slot, d->n_sms);
+    TGB_LAUNCH_CHECK(d);
+    return TG_TRUE;
+}
+
+extern "C" b32 tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane)
+{
+    const int rays_per_lane = tgbd_env_int("TGB_GI_RAYS_PER_LANE", 4);
+    const u32 ctas_per_sm = (u32)tgbd_env_int("TGB_GI_POOL_CTAS_PER_SM", 0);
+    const u32 dda_steps = (u32)max(1, tgbd_env_int("TGB_GI_POOL_DDA_STEPS", 16));
+    const u32 tree_reps = (u32)max(1, tgbd_env_int("TGB_GI_POOL_TREE_REPS", 4));
+    const u32 dda_bias = (u32)tgbd_env_int("TGB_GI_POOL_DDA_BIAS", 0);
+    const u32 min_rays_per_slot = (u32)max(1, tgbd_env_int("TGB_GI_POOL_MIN_RAYS_PER_SLOT", 4));
+    const int service_env = tgbd_env_int("TGB_GI_POOL_SERVICE_SLOTS", 0);
+    tgb_gi_frame fr;
+    tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
+#define TGB_POOL_CASE(KK) case KK: return tgbd__gi_pool_launch<KK>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : 8u * KK, dda_bias, tree_reps, dda_steps, min_rays_per_slot)
+    switch (rays_per_lane)
+    {
+    TGB_POOL_CASE(1);
+    TGB_POOL_CASE(2);
+    TGB_POOL_CASE(3);
+    TGB_POOL_CASE(4);
+    TGB_POOL_CASE(6);
+    TGB_POOL_CASE(8);
+    default: return tgbd__gi_pool_launch<4>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : 32u, dda_bias, tree_reps, dda_steps, min_rays_per_slot);
+    }
+#undef TGB_POOL_CASE
+}

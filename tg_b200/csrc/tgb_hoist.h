@@ -17,7 +17,7 @@
  * signed zero never changes a packed word (it only feeds ==0 / <0 / >0 tests and sums).
  * So: run the reference chain ONCE per object for cluster 0 with the generic routines, keep
  * (c, p, q, oc, r33), and per cluster evaluate three mul + nine add with the reference's own
- * operation order. tests/test_hoist.py checks this against the oracle's full chain bit for bit.
+ * operation order. tests/test_host_logic.py::test_per_object_factorisation_equals_the_full_chain checks this against the oracle's full chain bit for bit.
  */
 #ifndef TGB_HOIST_H
 #define TGB_HOIST_H

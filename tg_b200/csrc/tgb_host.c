@@ -82,11 +82,24 @@ b32 tg_object_is_initialized(const tg_scene* p_scene, u32 object_idx)
     return p_object->n_cluster_pointers_per_dim.x != 0 && p_object->n_cluster_pointers_per_dim.y != 0 && p_object->n_cluster_pointers_per_dim.z != 0;
 }
 
+/*
+ * tgm_m4_angle_axis (math/tg_math.c:1870-1910) does not normalise its axis: a non-unit axis yields a scaled / sheared matrix. The
+ * reference's per-cluster rasteriser would still draw such an object; the object-level culling here (distance and screen-rectangle
+ * bounds of the rigid box, k_cull_objects / k_svo_object_flags) assumes an orthonormal rotation, so the axis is checked where it
+ * enters (the reference only ever passes (0,1,0), tgvk_raytracer.c:841).
+ */
+static b32 tgb__axis_is_unit(v3 axis)
+{
+    const f64 l2 = (f64)axis.x * axis.x + (f64)axis.y * axis.y + (f64)axis.z * axis.z;
+    return l2 > 1.0 - 2e-5 && l2 < 1.0 + 2e-5;
+}
+
 u32 tgb200_scene_alloc_object(tg_scene* p_scene, v3 center, v3u extent, f32 angle_in_radians, v3 axis)
 {
     /* tgvk_raytracer.c:807-812 */
     TGB_REQUIRE(extent.x % 8 == 0 && extent.y % 8 == 0 && extent.z % 8 == 0 && extent.x && extent.y && extent.z, TG_U32_MAX,
                 "create_object: extent (%u,%u,%u) must be non-zero multiples of 8", extent.x, extent.y, extent.z);
+    TGB_REQUIRE(tgb__axis_is_unit(axis), TG_U32_MAX, "create_object: rotation axis (%g,%g,%g) is not a unit vector", (double)axis.x, (double)axis.y, (double)axis.z);
     TGB_REQUIRE(p_scene->n_objects < p_scene->object_capacity && p_scene->n_available_object_indices > 0, TG_U32_MAX, "create_object: object capacity %u exhausted", p_scene->object_capacity);
     const v3u dims = { extent.x / 8, extent.y / 8, extent.z / 8 };
     const u64 n64 = (u64)dims.x * dims.y * dims.z;
@@ -267,11 +280,25 @@ void tg_raytracer_set_gi(tg_raytracer* p_raytracer, b32 enabled, u32 frame_seed)
     p_raytracer->frame_seed = frame_seed;
 }
 
-static void tgb__upload_object_record(tg_raytracer* p_raytracer, u32 object_idx)
+static b32 tgb__upload_object_record(tg_raytracer* p_raytracer, u32 object_idx)
 {
     tg_object_data rec;
     tgb200_object_data(&p_raytracer->scene, object_idx, p_raytracer->p_object_lut_idx[object_idx], &rec);
-    tgbd_upload(p_raytracer->p_device, TGB_BUF_OBJECTS, (u64)object_idx * sizeof(tg_object_data), &rec, sizeof(rec));
+    return tgbd_upload(p_raytracer->p_device, TGB_BUF_OBJECTS, (u64)object_idx * sizeof(tg_object_data), &rec, sizeof(rec));
+}
+
+/* Exact inverse of tgb200_scene_alloc_object for the object allocated LAST (its pointers end the table): both free-lists get their
+ * entries back in the order they were popped, so a failed create leaves the scene as it found it. */
+static void tgb__scene_undo_alloc(tg_scene* p_scene, u32 object_idx)
+{
+    tg_voxel_object* p_object = &p_scene->p_objects[object_idx];
+    const u32 n = p_object->n_cluster_pointers_per_dim.x * p_object->n_cluster_pointers_per_dim.y * p_object->n_cluster_pointers_per_dim.z;
+    for (u32 rel = n; rel-- > 0;)
+        p_scene->p_available_cluster_indices[p_scene->n_available_cluster_indices++] = p_scene->p_cluster_pointers[p_object->first_cluster_pointer + rel];
+    p_scene->n_cluster_pointers -= n;
+    p_scene->p_available_object_indices[p_scene->n_available_object_indices++] = object_idx;
+    memset(p_object, 0, sizeof(*p_object));
+    p_scene->n_objects--;
 }
 
 /* Are the object's cluster indices one ascending run? (always true for scenes without destroys) */
@@ -302,47 +329,56 @@ static u32 tgb__create_object(tg_raytracer* p_raytracer, v3 center, v3u extent, 
     const u32 first = p_object->first_cluster_pointer;
     struct tgb_device* d = p_raytracer->p_device;
 
-    tgb__upload_object_record(p_raytracer, object_idx);
-    tgbd_upload(d, TGB_BUF_CLUSTER_POINTERS, (u64)first * 4, &p_scene->p_cluster_pointers[first], (u64)n * 4);
+    /* failures are tracked locally: the library's error flag is sticky and may still hold an earlier, unrelated error */
+    b32 ok = tgb__upload_object_record(p_raytracer, object_idx);
+    ok = ok && tgbd_upload(d, TGB_BUF_CLUSTER_POINTERS, (u64)first * 4, &p_scene->p_cluster_pointers[first], (u64)n * 4);
     /* generated on the device, after the pointer upload (same stream): seeded random bits, or the reference's terrain */
-    if (!p_solid_bits)
+    if (ok && !p_solid_bits)
     {
-        if (synthetic_k) tgbd_synthetic_fill(d, synthetic_seed, synthetic_k, n, first);
-        else             tgbd_procedural_fill(d, object_idx, dims.x, dims.y, dims.z, first);
+        if (synthetic_k) ok = tgbd_synthetic_fill(d, synthetic_seed, synthetic_k, n, first);
+        else             ok = tgbd_procedural_fill(d, object_idx, dims.x, dims.y, dims.z, first);
     }
 
-    if (tgb__contiguous_run(p_scene, p_object, n))
+    if (ok && tgb__contiguous_run(p_scene, p_object, n))
     {
         const u32 idx0 = p_scene->p_cluster_pointers[first];
         u32* p_mirror = &p_scene->p_voxel_cluster_data[(size_t)idx0 * TG_CLUSTER_MASK_WORDS];
-        tgbd_upload(d, TGB_BUF_C2O, (u64)idx0 * 4, &p_scene->p_cluster_idx_to_object_idx[idx0], (u64)n * 4);
+        ok = tgbd_upload(d, TGB_BUF_C2O, (u64)idx0 * 4, &p_scene->p_cluster_idx_to_object_idx[idx0], (u64)n * 4);
         if (p_solid_bits)
         {
             memcpy(p_mirror, p_solid_bits, (size_t)n * 64);
-            tgbd_upload(d, TGB_BUF_MASKS, (u64)idx0 * 64, p_solid_bits, (u64)n * 64);
+            ok = ok && tgbd_upload(d, TGB_BUF_MASKS, (u64)idx0 * 64, p_solid_bits, (u64)n * 64);
         }
-        else tgbd_download(d, TGB_BUF_MASKS, (u64)idx0 * 64, p_mirror, (u64)n * 64);
-        if (p_lut_indices) tgbd_upload(d, TGB_BUF_LUT_IDX, (u64)idx0 * 512, p_lut_indices, (u64)n * 512);
+        else ok = ok && tgbd_download(d, TGB_BUF_MASKS, (u64)idx0 * 64, p_mirror, (u64)n * 64);
+        if (p_lut_indices) ok = ok && tgbd_upload(d, TGB_BUF_LUT_IDX, (u64)idx0 * 512, p_lut_indices, (u64)n * 512);
     }
     else
     {
-        for (u32 rel = 0; rel < n; rel++)
+        for (u32 rel = 0; ok && rel < n; rel++)
         {
             const u32 idx = p_scene->p_cluster_pointers[first + rel];
             u32* p_mirror = &p_scene->p_voxel_cluster_data[(size_t)idx * TG_CLUSTER_MASK_WORDS];
-            tgbd_upload(d, TGB_BUF_C2O, (u64)idx * 4, &object_idx, 4);
+            ok = tgbd_upload(d, TGB_BUF_C2O, (u64)idx * 4, &object_idx, 4);
             if (p_solid_bits)
             {
                 memcpy(p_mirror, &p_solid_bits[(size_t)rel * TG_CLUSTER_MASK_WORDS], 64);
-                tgbd_upload(d, TGB_BUF_MASKS, (u64)idx * 64, &p_solid_bits[(size_t)rel * TG_CLUSTER_MASK_WORDS], 64);
+                ok = ok && tgbd_upload(d, TGB_BUF_MASKS, (u64)idx * 64, &p_solid_bits[(size_t)rel * TG_CLUSTER_MASK_WORDS], 64);
             }
-            else tgbd_download(d, TGB_BUF_MASKS, (u64)idx * 64, p_mirror, 64);
-            if (p_lut_indices) tgbd_upload(d, TGB_BUF_LUT_IDX, (u64)idx * 512, &p_lut_indices[(size_t)rel * 512], 512);
+            else ok = ok && tgbd_download(d, TGB_BUF_MASKS, (u64)idx * 64, p_mirror, 64);
+            if (p_lut_indices) ok = ok && tgbd_upload(d, TGB_BUF_LUT_IDX, (u64)idx * 512, &p_lut_indices[(size_t)rel * 512], 512);
         }
     }
-    if (!p_lut_indices) tgbd_fill_default_lut_idx(d, first, n, dims.x);
+    if (ok && !p_lut_indices) ok = tgbd_fill_default_lut_idx(d, first, n, dims.x);
     p_raytracer->svo_dirty = 2;
-    return tgb200_last_error() ? TG_U32_MAX : object_idx;
+    if (!ok)
+    {
+        /* roll the bookkeeping back (the object was the last one allocated: nothing shifts) and blank its device record, so that a
+         * failed create leaves neither a leaked slot on the host nor a half-initialised object on the device */
+        tgb__scene_undo_alloc(p_scene, object_idx);
+        tgb__upload_object_record(p_raytracer, object_idx);
+        return TG_U32_MAX;
+    }
+    return object_idx;
 }
 
 u32 tg_raytracer_create_object_from_data(tg_raytracer* p_raytracer, v3 center, v3u extent, f32 angle_in_radians, v3 axis, u32 lut_idx,
@@ -419,6 +455,7 @@ void tg_raytracer_set_object_transform(tg_raytracer* p_raytracer, u32 object_idx
     if (!tgb__alive(p_raytracer, "tg_raytracer_set_object_transform")) return;
     tg_scene* p_scene = &p_raytracer->scene;
     TGB_REQUIRE(object_idx < p_scene->object_capacity && tg_object_is_initialized(p_scene, object_idx), TGB_VOID, "set_object_transform: object %u is not initialised", object_idx);
+    TGB_REQUIRE(tgb__axis_is_unit(axis), TGB_VOID, "set_object_transform: rotation axis (%g,%g,%g) is not a unit vector", (double)axis.x, (double)axis.y, (double)axis.z);
     tg_voxel_object* p_object = &p_scene->p_objects[object_idx];
     p_object->translation = translation;
     p_object->angle_in_radians = angle_in_radians;
@@ -455,6 +492,13 @@ void tgb200_render_visibility(tg_raytracer* p_raytracer)
     TGB_REQUIRE(p_raytracer->scene.n_objects > 0, TGB_VOID, "render: the scene has no objects (tgvk_raytracer.c:1147)");
     tg_camera_rays cam;
     tgb200_camera_rays(p_raytracer->p_camera, &cam); /* re-read every frame, tgvk_raytracer.c:1153 */
+    if (p_raytracer->debug_visualization == TG_DEBUG_SHOW_BLOCKS)
+    {
+        /* tgvk_raytracer.c:1226-1272: while the BLOCKS view is selected the SVO primary-ray pass runs INSTEAD of the cluster pass */
+        tgb200_svo_update(p_raytracer, TG_FALSE);
+        tgbd_render_visibility_svo(p_raytracer->p_device, &cam);
+        return;
+    }
     tgbd_render_visibility(p_raytracer->p_device, &cam, p_raytracer->scene.object_capacity);
 }
 
@@ -505,6 +549,18 @@ void tgb200_render_shading(tg_raytracer* p_raytracer)
     }
     tgbd_render_shading(p_raytracer->p_device, &cam, p_raytracer->scene.n_cluster_pointers, p_raytracer->gi_enabled, p_raytracer->frame_seed,
                         p_raytracer->debug_visualization, 0, p_raytracer->height);
+}
+
+void tgb200_render_shading_rows(tg_raytracer* p_raytracer, u32 first_row, u32 one_past_last_row)
+{
+    if (!tgb__alive(p_raytracer, "tgb200_render_shading_rows")) return;
+    TGB_REQUIRE(tgbd_n_ranks(p_raytracer->p_device) <= 1, TGB_VOID, "render_shading_rows: a sharded raytracer shades its own tile (tgb200_render_shading)");
+    TGB_REQUIRE(first_row < one_past_last_row && one_past_last_row <= p_raytracer->height, TGB_VOID, "render_shading_rows: rows [%u, %u) outside the %u-row frame",
+                first_row, one_past_last_row, p_raytracer->height);
+    tg_camera_rays cam;
+    tgb200_camera_rays(p_raytracer->p_camera, &cam);
+    tgbd_render_shading(p_raytracer->p_device, &cam, p_raytracer->scene.n_cluster_pointers, p_raytracer->gi_enabled, p_raytracer->frame_seed,
+                        p_raytracer->debug_visualization, first_row, one_past_last_row);
 }
 
 void tg_raytracer_render(tg_raytracer* p_raytracer)

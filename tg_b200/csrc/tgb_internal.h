@@ -77,6 +77,9 @@ i32   tgbd_current_device(void);
 b32   tgbd_clear(struct tgb_device* d);                                                              /* clear.comp */
 b32   tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, u32 object_capacity); /* cull + K1 */
 
+/* ---- tgb_debug_svo.cu: the BLOCKS view's primary rays through the SVO (debug_visibility_svo.frag), instead of cull + K1 ---- */
+b32   tgbd_render_visibility_svo(struct tgb_device* d, const tg_camera_rays* p_cam);
+
 /* ---- tgb_shade.cu ---- */
 /* rows [y0, y1) only (multi-GPU: this rank's screen tile); pointers outside [base, base + n_local_pointers) shade to 0 */
 b32   tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p_cam, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1);
@@ -85,6 +88,9 @@ b32   tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p_cam, u32
 b32   tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera_rays* p_cam, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization);
 /* all-gather of the radiance tiles so that every rank holds the full frame */
 b32   tgbd_gather_radiance(struct tgb_device* d);
+
+/* ---- tgb_gi_pool.cu: the queued secondary rays of one band through the flattened SVO, several rays per lane ---- */
+b32   tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane);
 
 /* ---- tgb_svo.cu ---- */
 b32   tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity);

@@ -104,52 +104,84 @@ extern "C" b32 tgbd_p2p_prepare(struct tgb_device* d)
     if (d->n_ranks > TGB_MAX_RANKS) { d->p2p_failed = TG_TRUE; return TG_FALSE; }
     TGB_CUDA(cudaSetDevice(d->device));
     const u64 padded_px = (u64)d->width * d->tile_rows * d->n_ranks, px = padded_px; /* every frame buffer is padded to whole tiles */
+    /*
+     * From here on every rank MUST reach both collectives below whatever happens locally (a rank that returned early would leave its
+     * peers blocked in ncclAllGather): local CUDA / allocation failures only count as failed mappings, and the outcome all ranks
+     * agree on is the sum of those counts.
+     */
+    u32 n_failed = 0;
+#define TGB_P2P_TRY(call) do { if ((call) != cudaSuccess) { n_failed++; cudaGetLastError(); } } while (0)
     d->d_vis_pair[0] = d->d_vis; d->d_mat_pair[0] = d->d_mat; d->vis_flip = 0;
-    TGB_CUDA(cudaMalloc(&d->d_vis_pair[1], px * sizeof(u64)));
-    TGB_CUDA(cudaMalloc(&d->d_mat_pair[1], padded_px * sizeof(u64)));
-    TGB_CUDA(cudaMalloc(&d->d_vis_tile, (u64)d->width * d->tile_rows * sizeof(u64)));
-    TGB_CUDA(cudaMalloc(&d->d_ipc_stage, (u64)d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t)));
-    TGB_CUDA(cudaMemsetAsync(d->d_vis_pair[1], 0xFF, px * sizeof(u64), d->stream));
-    TGB_CUDA(cudaMemsetAsync(d->d_mat_pair[1], 0, padded_px * sizeof(u64), d->stream));
+    TGB_P2P_TRY(cudaMalloc(&d->d_vis_pair[1], px * sizeof(u64)));
+    TGB_P2P_TRY(cudaMalloc(&d->d_mat_pair[1], padded_px * sizeof(u64)));
+    TGB_P2P_TRY(cudaMalloc(&d->d_vis_tile, (u64)d->width * d->tile_rows * sizeof(u64)));
+    if (!d->d_ipc_stage && cudaMalloc(&d->d_ipc_stage, (u64)d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t)) != cudaSuccess)
+    {
+        /* without the staging buffer the collectives themselves cannot run on any rank that got it; this one failure is fatal for the
+         * exchange and is reported (the other ranks would wait): there is nothing smaller to allocate instead */
+        cudaGetLastError();
+        d->d_ipc_stage = NULL;
+        tgb_set_error("p2p_prepare: out of device memory for the %u-byte handle staging buffer", (u32)(d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t)));
+        if (d->d_vis_pair[1]) cudaFree(d->d_vis_pair[1]);
+        if (d->d_mat_pair[1]) cudaFree(d->d_mat_pair[1]);
+        if (d->d_vis_tile) cudaFree(d->d_vis_tile);
+        d->d_vis_pair[1] = NULL; d->d_mat_pair[1] = NULL; d->d_vis_tile = NULL;
+        d->p2p_failed = TG_TRUE;
+        return TG_FALSE;
+    }
+    if (d->d_vis_pair[1]) TGB_P2P_TRY(cudaMemsetAsync(d->d_vis_pair[1], 0xFF, px * sizeof(u64), d->stream));
+    if (d->d_mat_pair[1]) TGB_P2P_TRY(cudaMemsetAsync(d->d_mat_pair[1], 0, padded_px * sizeof(u64), d->stream));
 
     cudaIpcMemHandle_t mine[4];
-    u32 n_failed = 0;
     /* test hook: TGB200_FAIL_P2P_ON_RANK=r makes rank r report a failed mapping, which must send EVERY rank to the NCCL path */
     if (getenv("TGB200_FAIL_P2P_ON_RANK") && (u32)atoi(getenv("TGB200_FAIL_P2P_ON_RANK")) == d->rank) n_failed++;
     void* p_mine[4] = { d->d_vis_pair[0], d->d_vis_pair[1], d->d_mat_pair[0], d->d_mat_pair[1] };
     for (int k = 0; k < 4; k++)
     {
-        if (cudaIpcGetMemHandle(&mine[k], p_mine[k]) != cudaSuccess) { n_failed++; memset(&mine[k], 0, sizeof(mine[k])); cudaGetLastError(); }
+        if (!p_mine[k] || cudaIpcGetMemHandle(&mine[k], p_mine[k]) != cudaSuccess) { n_failed++; memset(&mine[k], 0, sizeof(mine[k])); cudaGetLastError(); }
     }
     cudaIpcMemHandle_t* p_all = (cudaIpcMemHandle_t*)malloc((size_t)d->n_ranks * sizeof(mine));
-    if (!p_all) { tgb_set_error("p2p_prepare: out of memory"); return TG_FALSE; }
-    TGB_CUDA(cudaMemcpyAsync(d->d_ipc_stage + (u64)d->rank * sizeof(mine), mine, sizeof(mine), cudaMemcpyHostToDevice, d->stream));
-    if (!tgbn_allgather_bytes(d->p_comm, d->d_ipc_stage + (u64)d->rank * sizeof(mine), d->d_ipc_stage, sizeof(mine), d->stream)) { free(p_all); return TG_FALSE; }
-    TGB_CUDA(cudaMemcpyAsync(p_all, d->d_ipc_stage, (u64)d->n_ranks * sizeof(mine), cudaMemcpyDeviceToHost, d->stream));
-    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    if (!p_all) n_failed++;
+    b32 collectives_ok = TG_TRUE;
+    TGB_P2P_TRY(cudaMemcpyAsync(d->d_ipc_stage + (u64)d->rank * sizeof(mine), mine, sizeof(mine), cudaMemcpyHostToDevice, d->stream));
+    if (!tgbn_allgather_bytes(d->p_comm, d->d_ipc_stage + (u64)d->rank * sizeof(mine), d->d_ipc_stage, sizeof(mine), d->stream)) collectives_ok = TG_FALSE;
+    if (p_all)
+    {
+        TGB_P2P_TRY(cudaMemcpyAsync(p_all, d->d_ipc_stage, (u64)d->n_ranks * sizeof(mine), cudaMemcpyDeviceToHost, d->stream));
+        TGB_P2P_TRY(cudaStreamSynchronize(d->stream));
+    }
     for (u32 r = 0; r < d->n_ranks; r++)
     {
         for (u32 k = 0; k < 4; k++)
         {
             void* p = NULL;
             if (r == d->rank) p = p_mine[k];
-            else if (n_failed == 0 && cudaIpcOpenMemHandle(&p, p_all[r * 4u + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { p = NULL; n_failed++; cudaGetLastError(); }
+            else if (n_failed == 0 && collectives_ok && cudaIpcOpenMemHandle(&p, p_all[r * 4u + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { p = NULL; n_failed++; cudaGetLastError(); }
             if (k < 2) d->peer_vis[k][r] = (u64*)p; else d->peer_mat[k - 2][r] = (u64*)p;
         }
     }
     free(p_all);
     /* agree: the stage buffer's first word becomes the number of failed mappings over all ranks */
-    TGB_CUDA(cudaMemcpyAsync(d->d_ipc_stage, &n_failed, sizeof(u32), cudaMemcpyHostToDevice, d->stream));
-    if (!tgbn_allreduce_sum_u32(d->p_comm, d->d_ipc_stage, 1, d->stream)) return TG_FALSE;
-    u32 total_failed = 0;
-    TGB_CUDA(cudaMemcpyAsync(&total_failed, d->d_ipc_stage, sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
-    TGB_CUDA(cudaStreamSynchronize(d->stream));
-    if (total_failed)
+    u32 total_failed = 1;
+    TGB_P2P_TRY(cudaMemcpyAsync(d->d_ipc_stage, &n_failed, sizeof(u32), cudaMemcpyHostToDevice, d->stream));
+    if (!tgbn_allreduce_sum_u32(d->p_comm, d->d_ipc_stage, 1, d->stream)) collectives_ok = TG_FALSE;
+    if (cudaMemcpyAsync(&total_failed, d->d_ipc_stage, sizeof(u32), cudaMemcpyDeviceToHost, d->stream) != cudaSuccess || cudaStreamSynchronize(d->stream) != cudaSuccess)
     {
+        cudaGetLastError();
+        total_failed = 1;
+    }
+#undef TGB_P2P_TRY
+    if (total_failed || n_failed || !collectives_ok)
+    {
+        /* every early-out path ends here: mappings closed, the partial allocations freed, the failure remembered (no retry, no leak) */
         tgbd__p2p_close(d);
-        cudaFree(d->d_vis_pair[1]); cudaFree(d->d_mat_pair[1]); cudaFree(d->d_vis_tile); cudaFree(d->d_ipc_stage);
+        if (d->d_vis_pair[1]) cudaFree(d->d_vis_pair[1]);
+        if (d->d_mat_pair[1]) cudaFree(d->d_mat_pair[1]);
+        if (d->d_vis_tile) cudaFree(d->d_vis_tile);
+        if (d->d_ipc_stage) cudaFree(d->d_ipc_stage);
         d->d_vis_pair[1] = NULL; d->d_mat_pair[1] = NULL; d->d_vis_tile = NULL; d->d_ipc_stage = NULL;
         d->p2p_failed = TG_TRUE;
+        cudaGetLastError();
         if (getenv("TGB200_VERBOSE")) fprintf(stderr, "[tgb200] rank %u: peer memory unavailable (%u failed mappings), using the NCCL collectives\n", d->rank, total_failed);
         return TG_FALSE;
     }

@@ -16,7 +16,6 @@
 #include "tgb_device.cuh"
 
 #define TGB_PI_F               3.14159265358979323846f
-#define TGB_TRAVERSE_MAX_ITERS 4096u /* Q9: cap that valid input never reaches */
 
 /* ---- per-object frames for ALL objects, indexed by object idx -------------------------------- */
 __global__ void k_object_frames(const tg_object_data* __restrict__ p_objects, u32 object_capacity, v3 camera, tgb_object_frame* __restrict__ p_frames)
@@ -86,60 +85,6 @@ struct tgb_svo_view
     v3 bmin, bmax;
 };
 
-/*
- * svo_functions.inc:283-292, the distance to the far border of a box: per axis the shader evaluates a = (min - p) / d and
- * b = (max - p) / d, takes max(a, b), then the minimum over the axes. Because min < max and IEEE subtraction / division
- * are monotone and sign-symmetric, max(a, b) is the quotient towards the FAR plane of the axis, q = num / |d| with
- * num = d > 0 ? max - p : p - min, bit for bit; d == 0 gives max(-F32_MAX, F32_MAX) = F32_MAX.
- * Rounding is monotone, so an axis whose quotient is clearly larger than the smallest one cannot be the minimum: a
- * 2-ulp approximate quotient ranks the axes and IEEE division is spent only on the axes within 1e-5 of the smallest
- * (almost always one). The value returned is the shader's.
- */
-__device__ __forceinline__ f32 tgb_exit_distance(v3 bmin, v3 bmax, v3 position, v3 d)
-{
-    const f32 nx = d.x > 0.0f ? bmax.x - position.x : position.x - bmin.x, ax = fabsf(d.x);
-    const f32 ny = d.y > 0.0f ? bmax.y - position.y : position.y - bmin.y, ay = fabsf(d.y);
-    const f32 nz = d.z > 0.0f ? bmax.z - position.z : position.z - bmin.z, az = fabsf(d.z);
-    const f32 qx = ax != 0.0f ? __fdividef(nx, ax) : TG_F32_MAX;
-    const f32 qy = ay != 0.0f ? __fdividef(ny, ay) : TG_F32_MAX;
-    const f32 qz = az != 0.0f ? __fdividef(nz, az) : TG_F32_MAX;
-    const f32 q_min = fminf(fminf(qx, qy), qz);
-    const f32 limit = q_min + (1e-5f * fabsf(q_min) + 1e-30f);
-    /* common case, branch-free: exactly one axis is within the margin of the smallest quotient -> one IEEE division */
-    const bool cx = qx <= limit, cy = qy <= limit, cz = qz <= limit;
-    const f32 num = cx ? nx : (cy ? ny : nz), den = cx ? ax : (cy ? ay : az);
-    f32 exit = num / den;
-    /* __fdividef is only specified for 2^-126 <= |d| <= 2^126 and finite operands: anything unusual takes the exact path */
-    const bool odd = !(q_min == q_min) || fabsf(q_min) > 1e30f || (ax != 0.0f && ax < 1e-30f) || (ay != 0.0f && ay < 1e-30f) || (az != 0.0f && az < 1e-30f);
-    if (((u32)cx + (u32)cy + (u32)cz != 1u) || odd)
-    {
-        exit = TG_F32_MAX;
-        if (ax != 0.0f && (odd || cx)) exit = tgb_min(exit, nx / ax);
-        if (ay != 0.0f && (odd || cy)) exit = tgb_min(exit, ny / ay);
-        if (az != 0.0f && (odd || cz)) exit = tgb_min(exit, nz / az);
-    }
-    return exit;
-}
-
-/*
- * exit_distance(box) > F32_EPSILON (the pop test, svo_functions.inc:296-324) without dividing: q = num / |d| exceeds
- * epsilon for sure when num > 2.5 eps |d| and is below it for sure when num < 0.5 eps |d| (this includes a ray that
- * is on or past the border, num <= 0); only the sliver in between needs the quotient itself. Branch-free unless a
- * component sits in the sliver.
- */
-__device__ __forceinline__ bool tgb_still_inside(v3 bmin, v3 bmax, v3 position, v3 d)
-{
-    const f32 nx = d.x > 0.0f ? bmax.x - position.x : position.x - bmin.x, ax = fabsf(d.x);
-    const f32 ny = d.y > 0.0f ? bmax.y - position.y : position.y - bmin.y, ay = fabsf(d.y);
-    const f32 nz = d.z > 0.0f ? bmax.z - position.z : position.z - bmin.z, az = fabsf(d.z);
-    const bool in_x = (ax == 0.0f) | (nx > 2.5f * TG_F32_EPSILON * ax), out_x = (ax != 0.0f) & (nx < 0.5f * TG_F32_EPSILON * ax);
-    const bool in_y = (ay == 0.0f) | (ny > 2.5f * TG_F32_EPSILON * ay), out_y = (ay != 0.0f) & (ny < 0.5f * TG_F32_EPSILON * ay);
-    const bool in_z = (az == 0.0f) | (nz > 2.5f * TG_F32_EPSILON * az), out_z = (az != 0.0f) & (nz < 0.5f * TG_F32_EPSILON * az);
-    if (in_x & in_y & in_z) return true;
-    if (out_x | out_y | out_z) return false;
-    return (in_x || nx / ax > TG_F32_EPSILON) && (in_y || ny / ay > TG_F32_EPSILON) && (in_z || nz / az > TG_F32_EPSILON);
-}
-
 /* ---- K3a: per-pixel shading, secondary rays that enter the SVO box are queued ---------------------- */
 struct tgb_shade_args
 {
@@ -185,6 +130,18 @@ __device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px,
     const u32 voxel_idx_9b        = (u32)(packed_data) & 511u;
 
     if (!(depth_24b < 1.0f)) { *p_color = make_float4(1.0f, 0.0f, 1.0f, 1.0f); return false; } /* :335 */
+
+    if (a.debug_visualization == TG_DEBUG_SHOW_BLOCKS)
+    {
+        /* The word comes from the SVO primary-ray pass (tgb_debug_svo.cu; debug_visibility_svo.frag): its pointer field is a leaf NODE
+         * index, which shading.frag:122-126,247-256 runs through the cluster-pointer table and hashes; what the shader computes in
+         * between is dead for this view. A node index beyond the live pointer range reads as cluster 0 (the reference reads whatever
+         * its SSBO holds there). Sharded: the pointer table is distributed, the node index itself is hashed (documented in
+         * tg_raytracer.h). */
+        const u32 cluster_idx_of_node = RESOLVED ? cluster_pointer_31b : (cluster_pointer_31b < a.n_local_pointers ? __ldg(&a.p_cluster_pointers[cluster_pointer_31b]) : 0u);
+        *p_color = tgb_hash_color(cluster_idx_of_node);
+        return false;
+    }
 
     u32 local_pointer, cluster_idx, object_idx, color_lut_idx, packed_color;
     if (RESOLVED)
@@ -633,49 +590,6 @@ enum { TGB_FL_IDLE = 0, TGB_FL_TREE = 1, TGB_FL_DDA = 2, TGB_FL_HIT = 3, TGB_FL_
 #define TGB_FL_DDA_STEPS 16
 #define TGB_FL_TREE_REPS 4 /* cells a ray may cross per tree phase: 1.548 -> 1.506 ms for the stage with 16 service lanes (sweeps of this round) */
 
-/*
- * Index along one axis of the 32^3 cell the shader's octant rule (:63-80: upper half iff mid < p || (p == mid && d > 0))
- * selects for p. The box corners are multiples of 32 here, p / 32 is exact (a power of two) and so is its floor: the
- * cell is floor(p / 32) - min / 32, one lower when p sits exactly on a cell border and the ray does not move up; a
- * position outside the box takes the outermost cell like the shader's comparisons do.
- */
-__device__ __forceinline__ u32 tgb_cell_axis(f32 p, f32 d, i32 box_min_cell)
-{
-    const f32 q = p * 0.03125f, fl = floorf(q);
-    const i32 c = (i32)fl - box_min_cell - (((q == fl) & !(d > 0.0f)) ? 1 : 0);
-    return (u32)max(0, min(31, c));
-}
-
-/*
- * tgb_exit_distance with the ray's exact reciprocals 1 / |d| (the DDA increments, :139-176) as the approximate
- * quotients that rank the axes: num * RN(1 / |d|) is within 2^-22 of num / |d|, far inside the 1e-5 margin, and the
- * value returned is still the IEEE quotient of the winning axis (see tgb_exit_distance for why that is the shader's
- * value). `exotic` rays (a non-zero component below 1e-30, whose reciprocal overflows) always take the exact path.
- */
-__device__ __forceinline__ f32 tgb_exit_distance_rcp(v3 bmin, f32 size, v3 position, v3 d, f32 rx, f32 ry, f32 rz, bool exotic)
-{
-    const f32 nx = d.x > 0.0f ? (bmin.x + size) - position.x : position.x - bmin.x, ax = fabsf(d.x);
-    const f32 ny = d.y > 0.0f ? (bmin.y + size) - position.y : position.y - bmin.y, ay = fabsf(d.y);
-    const f32 nz = d.z > 0.0f ? (bmin.z + size) - position.z : position.z - bmin.z, az = fabsf(d.z);
-    const f32 qx = ax != 0.0f ? nx * rx : TG_F32_MAX;
-    const f32 qy = ay != 0.0f ? ny * ry : TG_F32_MAX;
-    const f32 qz = az != 0.0f ? nz * rz : TG_F32_MAX;
-    const f32 q_min = fminf(fminf(qx, qy), qz);
-    const f32 limit = q_min + (1e-5f * fabsf(q_min) + 1e-30f);
-    const bool cx = qx <= limit, cy = qy <= limit, cz = qz <= limit;
-    const f32 num = cx ? nx : (cy ? ny : nz), den = cx ? ax : (cy ? ay : az);
-    f32 exit = num / den;
-    const bool odd = exotic | !(fabsf(q_min) < 1e30f);
-    if (((u32)cx + (u32)cy + (u32)cz != 1u) | odd)
-    {
-        exit = TG_F32_MAX;
-        if (ax != 0.0f && (odd || cx)) exit = tgb_min(exit, nx / ax);
-        if (ay != 0.0f && (odd || cy)) exit = tgb_min(exit, ny / ay);
-        if (az != 0.0f && (odd || cz)) exit = tgb_min(exit, nz / az);
-    }
-    return exit;
-}
-
 template <int DDA_STEPS>
 __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_view svo, const u32* __restrict__ p_grid, f32 far_plane,
                                                                   const float4* __restrict__ p_q0, const float4* __restrict__ p_q1, const float4* __restrict__ p_q2,
@@ -1016,7 +930,7 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         const f32 c[6] = { a.svo.bmin.x, a.svo.bmin.y, a.svo.bmin.z, a.svo.bmax.x, a.svo.bmax.y, a.svo.bmax.z };
         for (int i = 0; i < 6; i++) flat = flat && fmodf(c[i], 32.0f) == 0.0f && fabsf(c[i]) <= 4194304.0f; /* corners on the 32-unit cell lattice */
     }
-    static const int gi_ctas = max(1, min(16, tgbd_env_int("TGB_GI_CTAS_PER_SM", TGB_GI_FLAT_CTAS_PER_SM))); /* persistent CTAs per SM (tuning only) */
+    const int gi_ctas = max(1, min(16, tgbd_env_int("TGB_GI_CTAS_PER_SM", TGB_GI_FLAT_CTAS_PER_SM))); /* persistent CTAs per SM (tuning only) */
 
     /*
      * With a frame sink the rows are shaded in bands and every finished band is copied to the caller's memory on the copy
@@ -1049,11 +963,17 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         if (gi)
         {
             /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
-            if (flat)
+            /* TGB_GI_KERNEL: 2 (default) = several rays per lane, state in shared memory (tgb_gi_pool.cu); 1 = one ray per lane (k_gi_trace_flat) */
+            const int gi_kernel = tgbd_env_int("TGB_GI_KERNEL", 2);
+            if (flat && gi_kernel == 2)
+            {
+                if (!tgbd_gi_pool_trace(d, p_cam->far_plane)) return TG_FALSE;
+            }
+            else if (flat)
             {
                 /* scheduling knobs (tuning only): DDA steps per phase, lanes that trigger a service phase, bias of the majority vote towards the DDA */
-                static const int dda_steps = tgbd_env_int("TGB_GI_DDA_STEPS", TGB_FL_DDA_STEPS);
-                static const u32 service_lanes = (u32)tgbd_env_int("TGB_GI_SERVICE_LANES", (i32)TGB_FL_SERVICE_LANES), dda_bias = (u32)tgbd_env_int("TGB_GI_DDA_BIAS", 0),
+                const int dda_steps = tgbd_env_int("TGB_GI_DDA_STEPS", TGB_FL_DDA_STEPS);
+                const u32 service_lanes = (u32)tgbd_env_int("TGB_GI_SERVICE_LANES", (i32)TGB_FL_SERVICE_LANES), dda_bias = (u32)tgbd_env_int("TGB_GI_DDA_BIAS", 0),
                                  tree_reps = (u32)max(1, tgbd_env_int("TGB_GI_TREE_REPS", TGB_FL_TREE_REPS));
                 const dim3 gi_grid(d->n_sms * (u32)gi_ctas);
 #define TGB_GI_LAUNCH(K) k_gi_trace_flat<K><<<gi_grid, TGB_GI_THREADS, 0, d->stream>>>(a.svo, d->svo.d_top_grid, p_cam->far_plane, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, \

@@ -715,7 +715,7 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
 
     const dim3 grid((d->width + TGB_TILE_W - 1) / TGB_TILE_W, (d->height + TGB_TILE_H - 1) / TGB_TILE_H);
     /* register budget: 4 CTAs per SM = 64 registers with ~30 spilled words, measured 11 % faster than 3 CTAs = 80 registers (TGB_K1_MIN_CTAS=3 selects that build; tuning only) */
-    static const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 4), regroup = tgbd_env_int("TGB_K1_REGROUP", 1);
+    const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 4), regroup = tgbd_env_int("TGB_K1_REGROUP", 1);
 #define TGB_K1_LAUNCH(C, R) k_visibility<C, R><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height, \
                                                                                        d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis, d->n_ranks, d->tile_rows)
     if (regroup) { if (min_ctas >= 4) TGB_K1_LAUNCH(4, true); else TGB_K1_LAUNCH(3, true); }
