@@ -108,12 +108,15 @@ WORKLOADS = {
     "c2": "BASELINE configs[1]+[2]: 1,024 objects (2^21 clusters, 1.07e9 voxels), 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
     "c4": "BASELINE configs[3]: the configs[1] scene with 64 objects (the nearest to the player) moving every frame (translation.x += 0.5, angle += 1 degree "
           "per frame, 120-frame cycle): 64 transform uploads + incremental SVO update + primary visibility + 1-bounce SVO GI (1 spp), 3840x2160, 1 GPU",
+    "c4m8": "configs[3] with 8 instead of 64 movers (the 8 objects nearest to the player; same motion): what the incremental SVO update buys when only part of the "
+            "+-512 box changes -- with 64 movers every object inside the box moves and every leaf is re-sampled",
     "c5": "BASELINE configs[4] per GPU: 12,288 objects (25,165,824 clusters, 1.29e10 voxels; 8 GPUs = 1.03e11 voxels) generated on the device, "
           "3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
     "c2far": "dense-view stress, beside the headline: the configs[1] scene (1,024 objects, 2^21 clusters) with the far plane at 4000 so that several hundred "
              "objects survive the cull instead of ~33, 3840x2160, primary visibility + 1-bounce SVO GI (1 spp)",
 }
-SCALING = {"c2": "strong", "c4": "strong", "c2far": "strong", "c5": "weak"}
+SCALING = {"c2": "strong", "c4": "strong", "c4m8": "strong", "c2far": "strong", "c5": "weak"}
+N_MOVERS = {"c4": 64, "c4m8": 8}
 C2FAR_FAR = 4000.0
 
 
@@ -149,11 +152,11 @@ def union_scene(n_ranks, workload):
     return scenes.SceneSpec(name=f"union_{workload}", width=WIDTH, height=HEIGHT, camera=u.camera, objects=objects, lut=u.lut, n_luts=u.n_luts), pointers_match
 
 
-def c4_movers(scene):
-    """configs[3]: the 64 objects nearest to the player (objects 0..63 of SURVEY 8d lie outside the +-512 SVO box and would not
+def c4_movers(scene, n=64):
+    """configs[3]: the n = 64 objects nearest to the player (objects 0..63 of SURVEY 8d lie outside the +-512 SVO box and would not
     exercise the update) and their pose at frame f: translation.x += 0.5 f, angle += 1 degree * f (float32, like the tests)."""
     from tg_b200 import scenes
-    order = np.argsort([o.center[0] ** 2 + o.center[2] ** 2 for o in scene.objects], kind="stable")[:64]
+    order = np.argsort([o.center[0] ** 2 + o.center[2] ** 2 for o in scene.objects], kind="stable")[:n]
     movers = [int(i) for i in order]
 
     def pose(i, f):
@@ -181,10 +184,10 @@ class CpuArm:
     (screen-rect pruned, OpenMP), then GI + shading of the same rows from that buffer with the oracle's SVO (built once,
     outside the timed region, like the GPU arm)."""
 
-    def __init__(self, scene, dynamic=False, ystep=CPU_YSTEP):
+    def __init__(self, scene, dynamic=False, ystep=CPU_YSTEP, n_movers=64):
         from oracle import oracle as O
         self.O = O
-        self.dynamic, self.scene, self.frame_idx, self.ystep = dynamic, scene, 0, ystep
+        self.dynamic, self.scene, self.frame_idx, self.ystep, self.n_movers = dynamic, scene, 0, ystep, n_movers
         # all the host threads this process may use (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)
         O.lib().tgo_set_threads(len(os.sched_getaffinity(0)))
         self.cores = O.lib().tgo_max_threads()
@@ -210,7 +213,7 @@ class CpuArm:
         if self.dynamic:
             import copy
             self.frame_idx = self.frame_idx % 120 + 1
-            movers, pose = c4_movers(self.scene)
+            movers, pose = c4_movers(self.scene, self.n_movers)
             moved = copy.copy(self.scene)
             moved.objects = list(self.scene.objects)
             for i in movers:
@@ -226,7 +229,7 @@ class CpuArm:
         return dt, len(self.rows) * WIDTH + int((vis[self.rows] != CLEAR).sum())
 
     def text(self, n_rays):
-        return (("64 objects moved + oracle tg_svo_create from scratch (whole tree, not sampled) + " if self.dynamic else "")
+        return ((f"{self.n_movers} objects moved + oracle tg_svo_create from scratch (whole tree, not sampled) + " if self.dynamic else "")
                 + f"every {self.ystep}th scanline of the 3840x2160 frame ({len(self.rows)} rows): oracle visibility (screen-rect pruned) + oracle GI/shading of "
                 f"those rows, {n_rays} rays per sample, OpenMP")
 
@@ -238,7 +241,7 @@ def run_reference(args, rank):
     """The CPU arm (rank 0 only; the other ranks exit without work)."""
     if rank != 0:
         return
-    arm = CpuArm(cpu_scene(args.workload), dynamic=args.workload == "c4", ystep=CPU_YSTEP * (4 if args.workload == "c2far" else 1))
+    arm = CpuArm(cpu_scene(args.workload), dynamic=args.workload in N_MOVERS, ystep=CPU_YSTEP * (4 if args.workload == "c2far" else 1), n_movers=N_MOVERS.get(args.workload, 0))
     times, n_rays = [], 0
     for i in range(args.warmup + args.steps):
         secs, n_rays = arm.sample()
@@ -370,9 +373,9 @@ def gpu_arm(ctx, args, workload, steps, warmup, headline):
     rt.synchronize()
     svo_build_ms = rt.timings()["svo_ms"]
 
-    dynamic = workload == "c4"
+    dynamic = workload in N_MOVERS
     assert not (dynamic and world > 1), "configs[3] is a 1-GPU configuration"
-    movers, pose = c4_movers(scene) if dynamic else ([], None)
+    movers, pose = c4_movers(scene, N_MOVERS[workload]) if dynamic else ([], None)
     frame_idx = [0]
 
     def move_objects():
@@ -522,7 +525,7 @@ def gpu_arm(ctx, args, workload, steps, warmup, headline):
     def roofline(kernel, alg_bytes, achieved, stage_ms, traffic_file):
         # `frac` follows SURVEY 8(d)'s accounting (every submitted cluster counts, touched or not); `frac_touched` is what the kernel really
         # moves through DRAM (ncu dram__bytes_read + write of the committed capture, c2 at N=1) over the same time: the honest HBM figure
-        traffic = profiled_traffic(traffic_file) if workload in ("c2", "c4") and world == 1 else None
+        traffic = profiled_traffic(traffic_file) if workload in ("c2", "c4", "c4m8") and world == 1 else None
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "frac_touched": (traffic / (stage_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "kernel": kernel, "algorithmic_bytes": alg_bytes, "stage_ms": stage_ms, "peak_source": peak_src,
@@ -533,7 +536,7 @@ def gpu_arm(ctx, args, workload, steps, warmup, headline):
     if rank == 0:
         cpu = None
         if headline and not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N=1 figure
-            arm = CpuArm(cpu_scene(workload), dynamic=dynamic)
+            arm = CpuArm(cpu_scene(workload), dynamic=dynamic, n_movers=N_MOVERS.get(workload, 0))
             samples = [arm.sample() for _ in range(12)]  # ~10-30 s of CPU work on the box host cores
             secs = sum(t for t, _ in samples)
             cpu = {"value": sum(n for _, n in samples) / secs / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
@@ -610,7 +613,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the headline configuration (default); c4 = configs[3]; c5 = one 12,288-object shard of the "
                     "1e11-voxel world per GPU; c2far = dense-view stress")
     ap.add_argument("--also", default=None, help="comma-separated workloads timed briefly in the same invocation and attached under `also` "
-                    "(default with --workload c2: c4 at N=1, c5 at every N, c2far at N=1; 'none' disables)")
+                    "(default with --workload c2: c4, c4m8 and c2far at N=1, c5 at every N; 'none' disables)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -621,12 +624,12 @@ def main():
     ctx = Ctx()
     line = gpu_arm(ctx, args, args.workload, args.steps, args.warmup, headline=True)
     if args.also is None:
-        also = (["c4", "c2far", "c5"] if ctx.world == 1 else ["c5"]) if args.workload == "c2" else []
+        also = (["c4", "c4m8", "c2far", "c5"] if ctx.world == 1 else ["c5"]) if args.workload == "c2" else []
     else:
         also = [w for w in args.also.split(",") if w and w != "none"]
     extra = {}
     for w in also:
-        if w == "c4" and ctx.world > 1:
+        if w in N_MOVERS and ctx.world > 1:
             continue
         r = gpu_arm(ctx, args, w, max(5, min(args.steps, 10)), 3, headline=False)
         if r is not None:

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                 {
                     /* ambient * 1 + lo; float addition commutes and the reductions do not stall the lane */
                     const u32 slot = S(W_SLOT, k);
-                    const float4 q0 = p_q0[slot], q2 = p_q2[slot];
+                    const float4 q0 = __ldcs(&p_q0[slot]), q2 = __ldcs(&p_q2[slot]); /* streaming: read once, keep L1 for the tree */
                     f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
                     atomicAdd(p_pixel + 0, q2.x);
                     atomicAdd(p_pixel + 1, q2.y);
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                 }
                 else if (kd == TGB_RAY_HIT)
                 {
-                    const float4 q0 = p_q0[S(W_SLOT, k)];
+                    const float4 q0 = __ldcs(&p_q0[S(W_SLOT, k)]);
                     const u32 vox = S(W_VOX, k);
                     v3 child_min; f32 child_size;
                     tgb_cell_box(&fr, S(W_CELL, k), &child_min, &child_size);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                         const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
                         if (kd == TGB_RAY_IDLE && mine < n_rays)
                         {
-                            const float4 q0 = p_q0[mine], q1 = p_q1[mine];
+                            const float4 q0 = __ldcs(&p_q0[mine]), q1 = __ldcs(&p_q1[mine]);
                             const v3 d = tgb_v3(q1.x, q1.y, q1.z);
                             v3 position, t_delta; u32 flags;
                             tgb_gi_ray_start(&fr, tgb_v3(q0.x, q0.y, q0.z), d, q1.w, &position, &t_delta, &flags);
@@ -222,7 +222,7 @@ static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, u3
 
 extern "C" b32 tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane)
 {
-    const int rays_per_lane = tgbd_env_int("TGB_GI_RAYS_PER_LANE", 4);
+    const int rays_per_lane = tgbd_env_int("TGB_GI_RAYS_PER_LANE", 3); /* measured: 1.40 ms for the stage with 3, 1.43 with 2, 1.52 with 4 (L1 shrinks with the pool), 1.51 for k_gi_trace_flat */
     const u32 ctas_per_sm = (u32)tgbd_env_int("TGB_GI_POOL_CTAS_PER_SM", 0);
     const u32 dda_steps = (u32)max(1, tgbd_env_int("TGB_GI_POOL_DDA_STEPS", 16));
     const u32 tree_reps = (u32)max(1, tgbd_env_int("TGB_GI_POOL_TREE_REPS", 4));
@@ -231,7 +231,7 @@ extern "C" b32 tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane)
     const int service_env = tgbd_env_int("TGB_GI_POOL_SERVICE_SLOTS", 0);
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
-#define TGB_POOL_CASE(KK) case KK: return tgbd__gi_pool_launch<KK>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : 8u * KK, dda_bias, tree_reps, dda_steps, min_rays_per_slot)
+#define TGB_POOL_CASE(KK) case KK: return tgbd__gi_pool_launch<KK>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : (KK == 3 ? 64u : 16u * KK), dda_bias, tree_reps, dda_steps, min_rays_per_slot)
     switch (rays_per_lane)
     {
     TGB_POOL_CASE(1);
@@ -240,7 +240,7 @@ extern "C" b32 tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane)
     TGB_POOL_CASE(4);
     TGB_POOL_CASE(6);
     TGB_POOL_CASE(8);
-    default: return tgbd__gi_pool_launch<4>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : 32u, dda_bias, tree_reps, dda_steps, min_rays_per_slot);
+    default: return tgbd__gi_pool_launch<3>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : 64u, dda_bias, tree_reps, dda_steps, min_rays_per_slot);
     }
 #undef TGB_POOL_CASE
 }

@@ -211,16 +211,19 @@ TGB_HD u32 tgb_gi_tree_phase(const tgb_gi_frame* f, v3 d, v3 t_delta, v3* p_posi
                              u32* p_n_visits, u32* p_n_advances)
 {
     v3 position = *p_position;
-    u32 cell = *p_cell, flags = *p_flags, kind = TGB_RAY_TREE;
-    u32 iterations = cell >> 18;
+    u32 flags = *p_flags, kind = TGB_RAY_TREE;
+    u32 iterations = *p_cell >> 18;
+    /* the terminal box is kept unpacked across the repetitions: decoded once on entry, packed once on exit */
+    u32 cx = *p_cell & 31u, cy = (*p_cell >> 5) & 31u, cz = (*p_cell >> 10) & 31u, level = (*p_cell >> 15) & 7u;
+    v3 child_min; f32 child_size;
+    tgb_cell_box(f, *p_cell, &child_min, &child_size);
+    const bool exotic = (flags & TGB_RF_EXOTIC) != 0;
     for (u32 rep = 0; rep < reps && kind == TGB_RAY_TREE; rep++)
     {
         if (flags & TGB_RF_ADVANCE)
         {
             (*p_n_advances)++;
-            v3 child_min; f32 child_size;
-            tgb_cell_box(f, cell, &child_min, &child_size);
-            const f32 exit = tgb_exit_distance_rcp(child_min, child_size, position, d, t_delta.x, t_delta.y, t_delta.z, (flags & TGB_RF_EXOTIC) != 0);
+            const f32 exit = tgb_exit_distance_rcp(child_min, child_size, position, d, t_delta.x, t_delta.y, t_delta.z, exotic);
             position = tgb_add(position, tgb_scale(d, exit + TG_F32_EPSILON));
             /* a position at least one unit inside every face passes the pop test (exit >= 1 / |d| >= ~1 > epsilon) without evaluating it */
             const f32 off = fmaxf(fmaxf(fabsf(position.x - f->box_mid.x), fabsf(position.y - f->box_mid.y)), fabsf(position.z - f->box_mid.z));
@@ -233,11 +236,14 @@ TGB_HD u32 tgb_gi_tree_phase(const tgb_gi_frame* f, v3 d, v3 t_delta, v3* p_posi
             else
             {
                 (*p_n_visits)++;
-                const u32 cx = tgb_cell_axis(position.x, d.x, f->min_cell_x);
-                const u32 cy = tgb_cell_axis(position.y, d.y, f->min_cell_y);
-                const u32 cz = tgb_cell_axis(position.z, d.z, f->min_cell_z);
+                cx = tgb_cell_axis(position.x, d.x, f->min_cell_x);
+                cy = tgb_cell_axis(position.y, d.y, f->min_cell_y);
+                cz = tgb_cell_axis(position.z, d.z, f->min_cell_z);
                 const u32 entry = TGB_LDG(&f->p_grid[(cz << 10) | (cy << 5) | cx]);
-                cell = cx | (cy << 5) | (cz << 10) | (((entry >> TGB_TOP_LEVEL_SHIFT) & 7u) << 15);
+                level = (entry >> TGB_TOP_LEVEL_SHIFT) & 7u;
+                const u32 cells = 16u >> level, keep = ~(cells - 1u);
+                child_size = (f32)(cells << 5);
+                child_min = tgb_v3(f->bmin.x + (f32)((cx & keep) << 5), f->bmin.y + (f32)((cy & keep) << 5), f->bmin.z + (f32)((cz & keep) << 5));
                 if (entry & TGB_TOP_HAS_DATA)
                 {
                     *p_data = entry & TGB_TOP_POINTER_MASK;
@@ -248,7 +254,7 @@ TGB_HD u32 tgb_gi_tree_phase(const tgb_gi_frame* f, v3 d, v3 t_delta, v3* p_posi
         }
     }
     *p_position = position;
-    *p_cell = (cell & 0x3FFFFu) | (iterations << 18);
+    *p_cell = cx | (cy << 5) | (cz << 10) | (level << 15) | (iterations << 18);
     *p_flags = flags;
     return kind;
 }

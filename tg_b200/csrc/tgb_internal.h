@@ -77,6 +77,9 @@ i32   tgbd_current_device(void);
 b32   tgbd_clear(struct tgb_device* d);                                                              /* clear.comp */
 b32   tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, u32 object_capacity); /* cull + K1 */
 
+/* ---- tgb_visibility_pool.cu: K1 with several pixels per lane (after cull + sort; declines frames with an object > 32767 clusters along an axis) ---- */
+b32   tgbd_k1_pool_render(struct tgb_device* d, const tg_camera_rays* p_cam);
+
 /* ---- tgb_debug_svo.cu: the BLOCKS view's primary rays through the SVO (debug_visibility_svo.frag), instead of cull + K1 ---- */
 b32   tgbd_render_visibility_svo(struct tgb_device* d, const tg_camera_rays* p_cam);
 

@@ -18,6 +18,7 @@
  * skip only on STRICTLY greater (a tie must still run: the lower pointer / voxel wins).
  */
 #include "tgb_device.cuh"
+#include "tgb_k1_walk.cuh"
 
 #define TGB_TILE_W        16
 #define TGB_TILE_H        16
@@ -125,14 +126,8 @@ __global__ void k_cull_objects(const tg_object_data* __restrict__ p_objects, u32
     tgb_hoist_object(&o, camera, &f);
     f.object_idx = object_idx;
 
-    const v3 og = tgb_hoist_cluster_origin(&f, 0, 0, 0);
-    f.og[0] = og.x; f.og[1] = og.y; f.og[2] = og.z;
-
+    tgb_frame_conservative(&f, &o, camera); /* og, eps */
     const f32 ext[3] = { 8.0f * (f32)f.nx, 8.0f * (f32)f.ny, 8.0f * (f32)f.nz };
-    const f32 mag = fmaxf(fmaxf(fabsf(o.translation.x), fabsf(o.translation.y)), fabsf(o.translation.z))
-                  + fmaxf(fmaxf(fabsf(camera.x), fabsf(camera.y)), fabsf(camera.z))
-                  + fmaxf(fmaxf(ext[0], ext[1]), ext[2]);
-    f.eps = 0.03125f + 7.62939453125e-6f * mag; /* 2^-5 + 2^-17 * magnitude: >> accumulated rounding of either path */
 
     /* distance from the camera to the (inflated) box, in the grid frame (rigid transform) */
     f64 dist2 = 0.0;
@@ -217,6 +212,7 @@ __global__ void k_cull_objects(const tg_object_data* __restrict__ p_objects, u32
         f.x0 = (i32)minx; f.y0 = (i32)miny; f.x1 = (i32)maxx; f.y1 = (i32)maxy;
     }
 
+    if (f.nx > 32767u || f.ny > 32767u || f.nz > 32767u) atomicOr(&p_count[2], 1u); /* k_visibility_pool packs its iterator into 16-bit fields: this frame takes k_visibility */
     const u32 slot = atomicAdd(p_count, 1u);
     p_frames[slot] = f;
 }
@@ -275,175 +271,6 @@ __global__ void __launch_bounds__(1024) k_sort_frames(const tgb_object_frame* __
 /* ------------------------------------------------------------------------------------------- */
 /* K1                                                                                           */
 /* ------------------------------------------------------------------------------------------- */
-
-/* visibility.frag:194-201 quantisation of a depth in [0,1] (or beyond) */
-__device__ __forceinline__ u64 tgb_depth24(f32 t, f32 far_plane)
-{
-    const f32 dq = tgb_max(0.0f, t / far_plane) * TG_VIS_DEPTH_SCALE;
-    return (u64)dq; /* cvt.rzi.u64.f32: truncation, saturating, NaN -> 0 */
-}
-
-/*
- * What one ray keeps per object: the exact cluster-space direction d (shared by all clusters of the object,
- * tgb_hoist.h), the DDA increments 1 / |d| (visibility.frag:105-136; rcp.rn is the IEEE quotient 1 / x) and their signed
- * twins r = 1 / d, which double as APPROXIMATE reciprocals: n * r is within 2^-22 of the IEEE quotient n / d, so it can
- * rank slab quotients and decide clear-cut comparisons, and an IEEE division is spent only on the value that is kept.
- * `exotic` (a non-zero component below 1e-30, whose reciprocal overflows) switches every short cut off.
- */
-struct tgb_ray_in_object
-{
-    v3  d;
-    f32 t_delta_x, t_delta_y, t_delta_z;
-    f32 rx, ry, rz;
-    bool exotic;
-};
-
-/*
- * `enter` of collide.inc:3-24 for the box [lo, lo + size]^3 when the ray is already known to meet the box: the largest
- * of the three near-plane quotients. min((lo - o) / d, (hi - o) / d) is the quotient of the plane the ray meets first
- * (IEEE division by d is monotone), a zero component contributes -F32_MAX, and an axis whose approximate quotient is
- * clearly below the largest one cannot be the maximum (rounding is monotone), so only the axes within 1e-5 of it are
- * divided -- almost always one.
- */
-__device__ __forceinline__ f32 tgb_slab_enter(const tgb_ray_in_object& r, f32 nx, f32 ny, f32 nz, f32 ex, f32 ey, f32 ez, f32 e_max)
-{
-    const f32 floor_e = e_max - (1e-5f * fabsf(e_max) + 1e-30f);
-    const bool cx = ex >= floor_e, cy = ey >= floor_e, cz = ez >= floor_e;
-    const f32 num = cx ? nx : (cy ? ny : nz), den = cx ? r.d.x : (cy ? r.d.y : r.d.z);
-    f32 enter = num / den;
-    if ((u32)cx + (u32)cy + (u32)cz != 1u)
-    {
-        enter = TG_F32_MIN;
-        if (cx && r.d.x != 0.0f) enter = tgb_max(enter, nx / r.d.x);
-        if (cy && r.d.y != 0.0f) enter = tgb_max(enter, ny / r.d.y);
-        if (cz && r.d.z != 0.0f) enter = tgb_max(enter, nz / r.d.z);
-    }
-    return enter;
-}
-
-/*
- * One cluster, exactly visibility.frag:71-207 with the ray (o, d) in cluster space, in two halves so that a warp can run
- * the second one with all the lanes that have a cluster to march through (k_visibility<.., true>).
- *
- * First half, visibility.frag:71-81 = collide.inc:3-24 against [0,8]^3: does the ray meet the cluster (exit > 0 &&
- * enter <= exit), and can a hit inside still beat `best`? `t_skip` is a ray parameter beyond which no hit can
- * (depth24(t) > depth24(best) for every t >= t_skip). Returns the shader's `enter`.
- */
-__device__ __forceinline__ bool tgb_cluster_candidate(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 t_skip, f32* p_enter)
-{
-    const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
-    const v3 d = r.d;
-    const f32 nx = (d.x > 0.0f ? 0.0f : 8.0f) - o.x, fx = (d.x > 0.0f ? 8.0f : 0.0f) - o.x;
-    const f32 ny = (d.y > 0.0f ? 0.0f : 8.0f) - o.y, fy = (d.y > 0.0f ? 8.0f : 0.0f) - o.y;
-    const f32 nz = (d.z > 0.0f ? 0.0f : 8.0f) - o.z, fz = (d.z > 0.0f ? 8.0f : 0.0f) - o.z;
-    const f32 ex = d.x != 0.0f ? nx * r.rx : TG_F32_MIN, xx = d.x != 0.0f ? fx * r.rx : TG_F32_MAX;
-    const f32 ey = d.y != 0.0f ? ny * r.ry : TG_F32_MIN, xy = d.y != 0.0f ? fy * r.ry : TG_F32_MAX;
-    const f32 ez = d.z != 0.0f ? nz * r.rz : TG_F32_MIN, xz = d.z != 0.0f ? fz * r.rz : TG_F32_MAX;
-    const f32 e_max = fmaxf(fmaxf(ex, ey), ez), x_min = fminf(fminf(xx, xy), xz);
-    const f32 tol = 1e-5f * (fabsf(e_max) + fabsf(x_min)) + 1e-30f;
-    f32 enter;
-    if (!r.exotic && ((x_min > tol) & (e_max + tol < x_min)))
-    {
-        /* clear hit; a cluster entered beyond t_skip cannot win (voxel_enter >= enter, depth24 is monotone) */
-        if (e_max - tol > t_skip) return false;
-        enter = tgb_slab_enter(r, nx, ny, nz, ex, ey, ez, e_max);
-    }
-    else
-    {
-        if (!r.exotic && ((x_min < -tol) | (e_max - tol > x_min))) return false; /* clear miss */
-        f32 exit;
-        if (!tgb_ray_aabb(o, d, tgb_v3(0.0f, 0.0f, 0.0f), tgb_v3(8.0f, 8.0f, 8.0f), &enter, &exit)) return false;
-    }
-    /* voxel_enter >= enter (same o, d, nested boxes, monotone rounding) => depth24(hit) >= depth24(enter) > depth24(best) */
-    if (enter > t_skip) return false;
-    *p_enter = enter;
-    return true;
-}
-
-/* Second half, visibility.frag:83-207: the 8^3 Amanatides-Woo march from `enter`, the depth of the voxel found, the packed word. */
-__device__ __forceinline__ void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 enter, f32 far_plane,
-                                                  const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
-                                                  u32 global_pointer_base, u64& best, f32& t_skip)
-{
-    const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
-    const v3 d = r.d;
-    const u32 cluster_pointer = f.first_cluster_pointer + cx + f.nx * (cy + f.ny * cz);
-    const u32 cluster_idx = __ldg(&p_cluster_pointers[cluster_pointer]);
-    const uint2* __restrict__ p_slices = reinterpret_cast<const uint2*>(p_masks + (u64)cluster_idx * TG_CLUSTER_MASK_WORDS);
-
-    /* visibility.frag:83-137 */
-    v3 hit;
-    if (enter > 0.0f) { hit.x = o.x + enter * d.x; hit.y = o.y + enter * d.y; hit.z = o.z + enter * d.z; }
-    else              { hit = o; }
-    i32 x = (i32)tgb_clamp(floorf(hit.x), 0.0f, 8.0f - 1.0f);
-    i32 y = (i32)tgb_clamp(floorf(hit.y), 0.0f, 8.0f - 1.0f);
-    i32 z = (i32)tgb_clamp(floorf(hit.z), 0.0f, 8.0f - 1.0f);
-
-    i32 step_x = 0, step_y = 0, step_z = 0;
-    f32 t_max_x = TG_F32_MAX, t_max_y = TG_F32_MAX, t_max_z = TG_F32_MAX;
-    if (d.x > 0.0f)      { step_x = 1;  t_max_x = enter + ((f32)(x + 1) - hit.x) / d.x; }
-    else if (d.x < 0.0f) { step_x = -1; t_max_x = enter + (hit.x - (f32)x) / -d.x; }
-    if (d.y > 0.0f)      { step_y = 1;  t_max_y = enter + ((f32)(y + 1) - hit.y) / d.y; }
-    else if (d.y < 0.0f) { step_y = -1; t_max_y = enter + (hit.y - (f32)y) / -d.y; }
-    if (d.z > 0.0f)      { step_z = 1;  t_max_z = enter + ((f32)(z + 1) - hit.z) / d.z; }
-    else if (d.z < 0.0f) { step_z = -1; t_max_z = enter + (hit.z - (f32)z) / -d.z; }
-
-    /* visibility.frag:141-191; the 64-bit z-slice (words 2z, 2z+1) is fetched once per z */
-    i32 z_cached = -1;
-    u32 lo = 0, hi = 0;
-    bool found = false;
-    for (;;)
-    {
-        if (z != z_cached)
-        {
-            const uint2 s = __ldg(&p_slices[z]);
-            lo = s.x; hi = s.y; z_cached = z;
-        }
-        const u32 word = (y & 4) ? hi : lo;
-        if ((word >> (((y & 3) << 3) + x)) & 1u) { found = true; break; }
-        if (t_max_x < t_max_y)
-        {
-            if (t_max_x < t_max_z) { t_max_x += r.t_delta_x; x += step_x; if (x < 0 || x >= 8) break; }
-            else                   { t_max_z += r.t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
-        }
-        else
-        {
-            if (t_max_y < t_max_z) { t_max_y += r.t_delta_y; y += step_y; if (y < 0 || y >= 8) break; }
-            else                   { t_max_z += r.t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
-        }
-    }
-    if (!found) return;
-
-    /* visibility.frag:151-157, 194-201: depth from the slab test against the voxel; only its `enter` is used */
-    f32 voxel_enter;
-    {
-        const f32 vx = (f32)(d.x > 0.0f ? x : x + 1) - o.x, vy = (f32)(d.y > 0.0f ? y : y + 1) - o.y, vz = (f32)(d.z > 0.0f ? z : z + 1) - o.z;
-        if (!r.exotic)
-        {
-            const f32 qx = d.x != 0.0f ? vx * r.rx : TG_F32_MIN, qy = d.y != 0.0f ? vy * r.ry : TG_F32_MIN, qz = d.z != 0.0f ? vz * r.rz : TG_F32_MIN;
-            voxel_enter = tgb_slab_enter(r, vx, vy, vz, qx, qy, qz, fmaxf(fmaxf(qx, qy), qz));
-        }
-        else
-        {
-            f32 voxel_exit;
-            tgb_ray_aabb(o, d, tgb_v3((f32)x, (f32)y, (f32)z), tgb_v3((f32)(x + 1), (f32)(y + 1), (f32)(z + 1)), &voxel_enter, &voxel_exit);
-        }
-    }
-    const f32 depth = tgb_max(0.0f, voxel_enter / far_plane);
-    if (depth <= 1.0f)
-    {
-        const f32 dq = depth * TG_VIS_DEPTH_SCALE;
-        const u64 word = ((u64)dq << TG_VIS_DEPTH_SHIFT)
-                       | ((u64)(cluster_pointer + global_pointer_base) << TG_VIS_POINTER_SHIFT)
-                       | (u64)(u32)(64 * z + 8 * y + x);
-        if (word < best)
-        {
-            best = word;
-            /* t / far * 16777215 >= trunc(dq) + 1 puts depth24(t) above the best depth: t_skip with a 1e-5 relative cushion */
-            t_skip = (truncf(dq) + 1.0f) * (far_plane * (1.00001f / TG_VIS_DEPTH_SCALE));
-        }
-    }
-}
 
 /*
  * One ray against one object: enumerate, slice by slice along the dominant axis of d (front to
@@ -631,13 +458,14 @@ template <int MIN_CTAS, bool REGROUP>
 __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const tgb_object_frame* __restrict__ p_frames, const u32* __restrict__ p_count,
                                                                tg_camera_rays cam, u32 w, u32 h,
                                                                const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
-                                                               u32 global_pointer_base, u64* __restrict__ p_vis, u32 n_ranks, u32 tile_rows)
+                                                               u32 global_pointer_base, u64* __restrict__ p_vis, u32 n_ranks, u32 tile_rows, u32 fallback_only)
 {
     __shared__ u32 s_list[TGB_K1_THREADS];
     __shared__ u32 s_warp_count[TGB_K1_THREADS / 32];
 
     const u32 n_visible = p_count[0];
     if (n_visible == 0) return;
+    if (fallback_only && p_count[2] == 0) return; /* k_visibility_pool (tgb_visibility_pool.cu) rendered this frame */
     const bool sorted = p_count[1] != 0;
 
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -713,11 +541,15 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
     TGB_LAUNCH_CHECK(d);
     TGB_CUDA(cudaEventRecord(d->ev[3], d->stream));
 
+    /* TGB_K1_KERNEL: 2 (default) = several pixels per lane, walk state in shared memory (tgb_visibility_pool.cu); 1 = one pixel per lane */
+    const int k1_kernel = tgbd_env_int("TGB_K1_KERNEL", 2);
+    if (k1_kernel == 2 && !tgbd_k1_pool_render(d, p_cam)) return TG_FALSE;
+    const u32 fallback_only = k1_kernel == 2 ? 1u : 0u; /* after the pool kernel: only frames it declined (an object too large for its packed iterator) */
     const dim3 grid((d->width + TGB_TILE_W - 1) / TGB_TILE_W, (d->height + TGB_TILE_H - 1) / TGB_TILE_H);
     /* register budget: 4 CTAs per SM = 64 registers with ~30 spilled words, measured 11 % faster than 3 CTAs = 80 registers (TGB_K1_MIN_CTAS=3 selects that build; tuning only) */
     const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 4), regroup = tgbd_env_int("TGB_K1_REGROUP", 1);
 #define TGB_K1_LAUNCH(C, R) k_visibility<C, R><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height, \
-                                                                                       d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis, d->n_ranks, d->tile_rows)
+                                                                                       d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis, d->n_ranks, d->tile_rows, fallback_only)
     if (regroup) { if (min_ctas >= 4) TGB_K1_LAUNCH(4, true); else TGB_K1_LAUNCH(3, true); }
     else         { if (min_ctas >= 4) TGB_K1_LAUNCH(4, false); else TGB_K1_LAUNCH(3, false); }
 #undef TGB_K1_LAUNCH

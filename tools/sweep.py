@@ -36,8 +36,15 @@ GI_SWEEP = [
     {"TGB_GI_KERNEL": 2, "TGB_GI_RAYS_PER_LANE": 2, "TGB_GI_POOL_CTAS_PER_SM": 16},
 ]
 K1_SWEEP = [
-    {"TGB_K1_KERNEL": 1},
-    {"TGB_K1_KERNEL": 2},
+    {"TGB_K1_KERNEL": 1},                                   # round-1 kernel: one pixel per lane
+    {"TGB_K1_KERNEL": 2},                                   # pool, defaults (K = 2, 4 CTAs / SM)
+    {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 1},
+    {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 1, "TGB_K1_POOL_MIN_CTAS": 3},
+    {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 2, "TGB_K1_POOL_MIN_CTAS": 3},
+    {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 3},
+    {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 3, "TGB_K1_POOL_MIN_CTAS": 4},
+    {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 4},
+    {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 4, "TGB_K1_POOL_MIN_CTAS": 2},
 ]
 
 
