@@ -57,6 +57,8 @@ def lib():
         L.tgo_visibility_fragment.restype = T.u64
         L.tgo_visibility.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.u64)]
         L.tgo_visibility.restype = T.u64
+        L.tgo_visibility_window.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.u64)]
+        L.tgo_visibility_window.restype = T.u64
         L.tgo_max_threads.restype = T.i32
         L.tgo_set_threads.argtypes = [T.i32]
         L.tgo_cluster_dda.argtypes = [C.POINTER(T.u32), T.v3, T.v3, T.f32]
@@ -214,6 +216,13 @@ class SceneView:
 def visibility(view, rays, w, h, mode=VIS_SCREEN_RECT, y0=0, y1=None, ystep=1):
     out = np.empty(w * h, dtype=np.uint64)
     n = lib().tgo_visibility(C.byref(view.view), C.byref(rays), w, h, mode, y0, h if y1 is None else y1, ystep, T.ptr(out, T.u64))
+    return out.reshape(h, w), int(n)
+
+
+def visibility_window(view, rays, w, h, x0, x1, y0, y1):
+    """Unpruned brute force (every pixel of the window x every cluster pointer) -> (words [h, w] with the clear value outside, fragments)."""
+    out = np.empty(w * h, dtype=np.uint64)
+    n = lib().tgo_visibility_window(C.byref(view.view), C.byref(rays), w, h, x0, x1, y0, y1, T.ptr(out, T.u64))
     return out.reshape(h, w), int(n)
 
 

@@ -63,6 +63,8 @@ u64  tgo_visibility_fragment(const tgo_scene_view* p_scene, const tg_camera_rays
  * Returns the number of (pixel, cluster) fragments evaluated.
  */
 u64  tgo_visibility(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, u32 mode, u32 y0, u32 y1, u32 ystep, u64* p_out);
+/* every pixel of the window [x0, x1) x [y0, y1) against EVERY cluster pointer, unpruned (full-resolution frames) */
+u64  tgo_visibility_window(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, u32 x0, u32 x1, u32 y0, u32 y1, u64* p_out);
 i32  tgo_max_threads(void);
 void tgo_set_threads(i32 n);
 

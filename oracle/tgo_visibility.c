@@ -515,3 +515,32 @@ u64 tgo_visibility(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u
     free(p_setup);
     return n_fragments;
 }
+
+/*
+ * Brute force over a pixel WINDOW [x0, x1) x [y0, y1): every pixel of the window against every cluster pointer of the scene through
+ * tgo_visibility_fragment (visibility.frag:22-208, nothing hoisted, nothing pruned). The other pixels keep the clear value. For
+ * full-resolution frames, where brute force over whole scanlines is out of reach: the screen-rectangle pruning of TGO_VIS_SCREEN_RECT
+ * (the same design as the CUDA path's object cull) is then not the only witness.
+ */
+u64 tgo_visibility_window(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, u32 x0, u32 x1, u32 y0, u32 y1, u64* p_out)
+{
+    if (x1 > w) x1 = w;
+    if (y1 > h) y1 = h;
+    for (size_t i = 0; i < (size_t)w * h; i++) p_out[i] = TG_VIS_CLEAR;
+    const u32 n = p_scene->n_cluster_pointers;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+    for (i64 py = (i64)y0; py < (i64)y1; py++)
+    {
+        for (i64 px = (i64)x0; px < (i64)x1; px++)
+        {
+            u64 best = TG_VIS_CLEAR;
+            for (u32 cp = 0; cp < n; cp++)
+            {
+                const u64 word = tgo_visibility_fragment(p_scene, p_cam, w, h, (u32)px, (u32)py, cp);
+                if (word < best) best = word;
+            }
+            p_out[(size_t)py * w + (size_t)px] = best;
+        }
+    }
+    return (u64)(x1 > x0 ? x1 - x0 : 0) * (u64)(y1 > y0 ? y1 - y0 : 0) * n;
+}

@@ -40,6 +40,11 @@ tile, who = sharding.merge_tile_from_peers(all_vis, rank, s.height, s.width)
 my_rows = sharding.tile_physical_rows(s.height, world, rank)
 my_rows = my_rows[my_rows >= 0]
 assert np.array_equal(tile, whole[my_rows]), "the tile merged from the peers' buffers must equal the all-reduced rows"
+# ... and with K1's per-tile hit flags: a peer's tile without a hit is not read at all, the merged words stay the same
+flags = [sharding.tile_hit_flags(v) for v in all_vis]
+assert all(f.shape == ((s.height + 15) // 16, (s.width + 15) // 16) for f in flags) and flags[rank].any() and not all(f.all() for f in flags)
+tile_f, skipped = sharding.merge_tile_from_flagged_peers(all_vis, flags, rank, s.height, s.width)
+assert np.array_equal(tile_f, tile) and skipped > 0.0, "skipping the peers' empty tiles must not change the merged tile"
 bases = [sharding.shard_scene(s, world, r)[1] for r in range(world)] + [s.n_clusters]
 tile_ptr = ((tile >> np.uint64(9)) & np.uint64(0x7FFFFFFF)).astype(np.int64)
 owner = np.searchsorted(np.asarray(bases[1:]), tile_ptr, side="right")

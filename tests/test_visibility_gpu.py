@@ -300,3 +300,92 @@ def test_scene_dump_and_load_round_trip(gpu, tmp_path):
         import tg_b200
         tg_b200.lib().tgb200_clear_error()
         rt3.destroy()
+
+
+def _objects_in_window_cone(scene, rays, x0, x1, y0, y1, radius):
+    """Indices of the objects whose bounding sphere meets the cone around the window's rays -- a float64 statement of "can this object
+    touch a ray of the window" that shares no code with the screen-rectangle pruning of either path."""
+    def ray(px, py):
+        fx, fy = (px + 0.5) / scene.width, 1.0 - (py + 0.5) / scene.height
+        c = lambda v: np.array([v.x, v.y, v.z], dtype=np.float64)
+        bl, br, tr, tl = c(rays.ray_bl), c(rays.ray_br), c(rays.ray_tr), c(rays.ray_tl)
+        left, right = bl * (1 - fy) + tl * fy, br * (1 - fy) + tr * fy
+        d = left * (1 - fx) + right * fx
+        return d / np.linalg.norm(d)
+    axis = ray(0.5 * (x0 + x1 - 1), 0.5 * (y0 + y1 - 1))
+    half = max(np.arccos(np.clip(np.dot(axis, ray(px, py)), -1, 1)) for px in (x0, x1 - 1) for py in (y0, y1 - 1)) + 1e-3
+    cam = np.array([rays.camera.x, rays.camera.y, rays.camera.z], dtype=np.float64)
+    keep = []
+    for i, o in enumerate(scene.objects):
+        v = np.asarray(o.center, dtype=np.float64) - cam
+        dist = np.linalg.norm(v)
+        if dist - radius > scene.camera.far * 1.001:
+            continue
+        if dist <= radius or np.arccos(np.clip(np.dot(v / dist, axis), -1, 1)) <= half + np.arcsin(min(1.0, radius / dist)):
+            keep.append(i)
+    return keep
+
+
+@pytest.mark.parametrize("window", [(1890, 1938, 640, 688), (300, 348, 1700, 1748), (600, 648, 600, 648), (2300, 2348, 500, 548), (1912, 1960, 520, 568)])
+def test_config2_full_size_windows_against_unpruned_brute_force(gpu, oracle, window):
+    """BASELINE configs[1] at 3840x2160: five 48x48-pixel windows (near objects, object silhouettes near the horizon, two objects overlapping in depth) of the frame against the oracle's UNPRUNED brute force (every pixel x
+    every cluster of every object that can touch the window's cone of rays, chosen by a float64 sphere-vs-cone test written here).
+    The scanline test above leans on the oracle's screen-rectangle pruning, which is the same design as k_cull_objects; this one does
+    not share it."""
+    from tg_b200.raytracer import from_scene
+    x0, x1, y0, y1 = window
+    s = scenes.grid_scene("config2_devicebits", 32, 32, 3840, 2160, k=3, with_bits=False)
+    rays = oracle.camera_rays(oracle.camera_from_spec(s.camera))
+    rt = from_scene(s)
+    try:
+        rt.clear(); rt.render_visibility(); rt.synchronize()
+        got = rt.read_visibility()[y0:y1, x0:x1]
+    finally:
+        rt.destroy()
+    keep = _objects_in_window_cone(s, rays, x0, x1, y0, y1, radius=0.5 * float(np.linalg.norm(s.objects[0].extent)) + 1.0)
+    assert 1 <= len(keep) <= 40, len(keep)
+    sub = scenes.SceneSpec(name="c2_window", width=s.width, height=s.height, camera=s.camera, objects=[s.objects[i] for i in keep])
+    for o in sub.objects:
+        o.bits = scenes.random_solid_bits(o.seed, o.n_clusters, o.k)
+    view = oracle.SceneView.from_scene(sub, with_lut=False)
+    want, n_fragments = oracle.visibility_window(view, rays, s.width, s.height, x0, x1, y0, y1)
+    want = want[y0:y1, x0:x1]
+    assert n_fragments == 48 * 48 * sub.n_clusters
+    # the sub-scene numbers its clusters from 0: map its pointers to the full scene's (every object has 2,048 clusters, order kept)
+    w_hit = want != CLEAR
+    sub_ptr = (want >> np.uint64(9)) & np.uint64(0x7FFFFFFF)
+    full_ptr = np.asarray(keep, dtype=np.uint64)[(sub_ptr // np.uint64(2048)).astype(np.int64) % len(keep)] * np.uint64(2048) + sub_ptr % np.uint64(2048)
+    remapped = np.where(w_hit, (want & ~(np.uint64(0x7FFFFFFF) << np.uint64(9))) | (full_ptr << np.uint64(9)), want)
+    assert np.array_equal(got, remapped), describe_mismatch(got, remapped)
+    assert w_hit.sum() > 100
+
+
+def test_dense_view_far_plane_4000_scanline_subset(gpu, oracle):
+    """The dense-view stress of bench.py (`c2far`): the configs[1] scene with the far plane at 4000, so that several hundred objects
+    survive the cull, the front-to-back sort and the per-tile object windows carry real load, and distant objects project to a few
+    pixels. Every 120th scanline against the oracle; visibility + GI radiance."""
+    from tg_b200.raytracer import from_scene
+    s = scenes.config2()
+    s.camera.far = 4000.0
+    rt = from_scene(s)
+    try:
+        rt.set_gi(True, 1)
+        rt.clear(); rt.render(); rt.synchronize()
+        got = rt.read_visibility()
+        rad = rt.read_radiance()
+        t = rt.timings()
+    finally:
+        rt.destroy()
+    assert t["n_visible_objects"] > 250, t["n_visible_objects"]
+    rows = np.arange(5, s.height, 120)
+    want = oracle_visibility(oracle, s, None, 5, None, 120)
+    assert np.array_equal(got[rows], want[rows]), describe_mismatch(got[rows], want[rows])
+    rays = oracle.camera_rays(oracle.camera_from_spec(s.camera))
+    view = oracle.SceneView.from_scene(s, with_lut=True)
+    in_box = [o for o in s.objects if max(abs(o.center[0]), abs(o.center[2])) < 512 + 160]
+    svo = oracle.svo_create(oracle.SceneView.from_scene(scenes.SceneSpec(name="far_box", width=s.width, height=s.height, camera=s.camera, objects=in_box), with_lut=False),
+                            capacities=(1 << 25, 1 << 15, 1 << 16))
+    want_rad = np.zeros((s.height, s.width, 4), dtype=np.float32)
+    oracle.shade(view, rays, s.width, s.height, want, svo, gi=True, frame_seed=1, y0=5, y1=s.height, ystep=120, out=want_rad)
+    oracle.svo_destroy(svo)
+    assert np.allclose(rad[rows], want_rad[rows], rtol=1e-3, atol=1e-6), f"{int((~np.isclose(rad[rows], want_rad[rows], rtol=1e-3, atol=1e-6)).any(axis=-1).sum())} pixels beyond 1e-3"

@@ -106,9 +106,13 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     d->d_mat = NULL; d->d_mat_tile = NULL;
     if (d->n_ranks > 1)
     {
-        TGB_CUDA(cudaMalloc(&d->d_mat, padded_px * sizeof(u64)));
+        const u32 old_w = d->width; d->width = width; /* the tail layout (tile flags, frame counter) follows the NEW size */
+        const u64 mat_bytes = tgbd_mat_bytes(d);
+        d->width = old_w;
+        TGB_CUDA(cudaMalloc(&d->d_mat, mat_bytes));
         TGB_CUDA(cudaMalloc(&d->d_mat_tile, (u64)width * d->tile_rows * sizeof(u64)));
-        TGB_CUDA(cudaMemsetAsync(d->d_mat, 0, padded_px * sizeof(u64), d->stream));
+        TGB_CUDA(cudaMemsetAsync(d->d_mat, 0, mat_bytes, d->stream));
+        d->frame_seq = 0; d->mat_from_k1 = TG_FALSE; d->objects_gathered = TG_FALSE;
     }
     if (d->d_vis) TGB_CUDA(cudaFree(d->d_vis));
     if (d->d_radiance_pair[0]) TGB_CUDA(cudaFree(d->d_radiance_pair[0]));
@@ -241,6 +245,8 @@ extern "C" b32 tgbd_upload(struct tgb_device* d, u32 buffer, u64 dst_offset_byte
     TGB_CUDA(cudaSetDevice(d->device));
     /* pageable source: the copy is staged before the call returns, so the caller may reuse p_src */
     TGB_CUDA(cudaMemcpyAsync(p + dst_offset_bytes, p_src, n_bytes, cudaMemcpyHostToDevice, d->stream));
+    if (buffer == TGB_BUF_VISIBILITY) d->mat_from_k1 = TG_FALSE; /* uploaded words: the sharded shading stage resolves their materials itself */
+    if (buffer == TGB_BUF_OBJECTS) d->objects_gathered = TG_FALSE;
     return TG_TRUE;
 }
 
@@ -278,6 +284,7 @@ extern "C" void tgbd_synchronize(struct tgb_device* d)
     cudaError_t e = cudaStreamSynchronize(d->stream);
     if (e == cudaSuccess && d->copy_stream) e = cudaStreamSynchronize(d->copy_stream);
     if (e != cudaSuccess) tgb_set_error("cudaStreamSynchronize -> %s", cudaGetErrorString(e));
+    else tgbd_p2p_check(d);
 }
 
 /* ---- frame sink ---- */
@@ -334,6 +341,7 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
 {
     cudaSetDevice(d->device);
     cudaStreamSynchronize(d->stream);
+    tgbd_p2p_check(d);
     if (d->ev_clear) cudaEventElapsedTime(&d->clear_ms, d->ev[0], d->ev[1]);
     if (d->ev_vis)   { cudaEventElapsedTime(&d->cull_ms, d->ev[2], d->ev[3]); cudaEventElapsedTime(&d->visibility_ms, d->ev[3], d->ev[4]); }
     if (d->ev_svo)   cudaEventElapsedTime(&d->svo_ms, d->ev[5], d->ev[6]);
@@ -341,7 +349,7 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
     if (d->ev_merge) cudaEventElapsedTime(&d->merge_ms, d->ev[9], d->ev[10]);
     if (d->ev_merge && d->ev_merge_parts)
     {
-        /* peer-memory merge: local material resolve | all-gather of the object records (= waiting for the slowest rank's K1) | k_merge_tile */
+        /* peer-memory merge: publish "K1 done" (+ material resolve when K1's epilogue did not run) | wait for the slowest rank's K1 | k_merge_tile */
         cudaEventElapsedTime(&d->merge_resolve_ms, d->ev[9], d->ev[11]);
         cudaEventElapsedTime(&d->merge_gather_ms, d->ev[11], d->ev[12]);
         cudaEventElapsedTime(&d->merge_kernel_ms, d->ev[12], d->ev[10]);

@@ -492,6 +492,9 @@ void tgb200_render_visibility(tg_raytracer* p_raytracer)
     TGB_REQUIRE(p_raytracer->scene.n_objects > 0, TGB_VOID, "render: the scene has no objects (tgvk_raytracer.c:1147)");
     tg_camera_rays cam;
     tgb200_camera_rays(p_raytracer->p_camera, &cam); /* re-read every frame, tgvk_raytracer.c:1153 */
+    /* sharded: peer memory is mapped on the first frame (collective; a no-op afterwards and when the NCCL exchange was chosen), so that
+     * K1 can already resolve its materials and flag its tiles for the merge */
+    if (tgbd_n_ranks(p_raytracer->p_device) > 1) tgbd_p2p_prepare(p_raytracer->p_device);
     if (p_raytracer->debug_visualization == TG_DEBUG_SHOW_BLOCKS)
     {
         /* tgvk_raytracer.c:1226-1272: while the BLOCKS view is selected the SVO primary-ray pass runs INSTEAD of the cluster pass */

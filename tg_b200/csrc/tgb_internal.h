@@ -120,6 +120,10 @@ void  tgbd_p2p_teardown(struct tgb_device* d);  /* collective: unmaps the peers'
 void  tgbd_note_merged(struct tgb_device* d);   /* the all-reduce has run on the current buffer */
 void* tgbd_visibility_for_read(struct tgb_device* d); /* whole merged frame: pulls the other tiles from the peers if necessary */
 b32   tgbd_p2p_merge_tile(struct tgb_device* d);
+b32   tgbd_gather_objects(struct tgb_device* d);     /* collective: every rank's object records, pointers globalised */
+b32   tgbd_p2p_barrier(struct tgb_device* d);        /* publish "K1 done" for this frame, wait for every peer's (device side, asynchronous) */
+b32   tgbd_p2p_flag_all_tiles(struct tgb_device* d); /* this rank's words did not come from K1's epilogue: every tile counts as hit */
+void  tgbd_p2p_check(struct tgb_device* d);          /* after a stream synchronisation: did the device-side barrier time out? */
 /* events around the merge live in tgb_device.cu */
 void  tgbd_merge_begin(struct tgb_device* d);
 void  tgbd_merge_end(struct tgb_device* d);

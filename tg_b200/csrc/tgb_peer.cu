@@ -11,11 +11,19 @@
  * N - 1 of them over NVLink -- a running min, one more load from the winner. 58 MB cross the switch per rank at N = 8
  * instead of two all-to-all collectives, and nothing is written that another rank reads.
  *
- * Synchronisation: both buffers are double buffered (flipped by tgbd_clear), and the one collective that remains per frame
- * -- the all-gather of the 96-byte object records, needed anyway because objects may have moved -- sits between K1 and the
- * merge: a rank leaves it only after every rank has entered it, i.e. finished K1 + resolve of this frame and, in stream
- * order, the merge of the previous frame (which read the OTHER buffer pair). The min is associative and commutative, so
- * the merged tile is bit-identical to the all-reduce and to a single-GPU frame (tests/test_multi_gpu.py runs both paths).
+ * What crosses the switch is cut further by K1 itself: its epilogue (k_visibility<.., SHARDED>) resolves the material of the rank's
+ * hits (no second pass over the buffer) and records per 16x16 tile whether the rank has any hit there; k_merge_tile reads a peer's
+ * words only for tiles that peer flagged -- with the objects dealt out over the ranks a tile is covered by one or two ranks, not N.
+ *
+ * Synchronisation: both buffers are double buffered (flipped by tgbd_clear) and carry, behind the material words, the tile flags
+ * and a frame counter. A rank PUBLISHES the frame number when its K1 is done (k_signal: system-scope fence, then the store) and
+ * WAITS until every peer has published it (k_wait_peers polls the peers' counters over NVLink) before k_merge_tile runs -- no
+ * collective sits between K1 and the merge any more; the all-gather of the 96-byte object records (objects may have moved) runs
+ * before K1, where nobody waits for anybody's K1. Why two buffers suffice: a rank that starts frame i + 2 (and clears the buffer
+ * of frame i) has finished its merge of frame i + 1, which waited for every peer's K1 of frame i + 1, which those peers started
+ * after their merge of frame i -- the last reader of that buffer. The min is associative and commutative, so the merged tile is
+ * bit-identical to the all-reduce and to a single-GPU frame (tests/test_multi_gpu.py runs both paths; bench.py re-checks it at
+ * full size inside its warm-up).
  * Peer loads use ld.volatile semantics (__ldcv): a word another GPU wrote this frame must not come from a stale line.
  */
 #include "tgb_device.cuh"
@@ -26,24 +34,76 @@ struct tgb_peer_table
     const u64* p_mat[TGB_MAX_RANKS];
 };
 
-/* pixels [first, first + n) of the frame: merged word -> p_vis_out[first + i], winner's material word -> p_mat_out[i] (if any) */
-__global__ void __launch_bounds__(256) k_merge_tile(const tgb_peer_table t, u32 n_ranks, u64 first, u64 n, u64* __restrict__ p_vis_out, u64* __restrict__ p_mat_out, u64 n_mat_out)
+struct tgb_peer_flags
+{
+    const u32* p_tile_flags[TGB_MAX_RANKS]; /* NULL table entry 0 = no flags: read every rank's words */
+};
+
+/* pixels [first, first + n) of the frame (virtual row order): merged word -> p_vis_out[first + i], winner's material word -> p_mat_out[i] (if any) */
+__global__ void __launch_bounds__(256) k_merge_tile(const tgb_peer_table t, const tgb_peer_flags fl, u32 n_ranks, u32 w, u32 tiles_x, u64 first, u64 n,
+                                                    u64* __restrict__ p_vis_out, u64* __restrict__ p_mat_out, u64 n_mat_out)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_mat_out && i >= n) return;
     u64 best = TG_VIS_CLEAR, mat = 0;
     if (i < n)
     {
+        const u64 pixel = first + i;
+        const u32 tile = (u32)(pixel / w / TGB_BAND_ROWS) * tiles_x + (u32)(pixel % w) / 16u;
+        const bool use_flags = fl.p_tile_flags[0] != NULL;
         u32 who = 0;
         for (u32 r = 0; r < n_ranks; r++)
         {
-            const u64 w = __ldcv(&t.p_vis[r][first + i]);
-            if (w < best) { best = w; who = r; } /* shards own disjoint pointer ranges: two ranks never hold the same word */
+            if (use_flags && __ldcv(&fl.p_tile_flags[r][tile]) == 0u) continue; /* that rank has no hit in this tile: its words are the clear value */
+            const u64 v = __ldcv(&t.p_vis[r][pixel]);
+            if (v < best) { best = v; who = r; } /* shards own disjoint pointer ranges: two ranks never hold the same word */
         }
-        if (best != TG_VIS_CLEAR && p_mat_out) mat = __ldcv(&t.p_mat[who][first + i]);
-        p_vis_out[first + i] = best;
+        if (best != TG_VIS_CLEAR && p_mat_out) mat = __ldcv(&t.p_mat[who][pixel]);
+        p_vis_out[pixel] = best;
     }
     if (p_mat_out && i < n_mat_out) p_mat_out[i] = mat; /* the padded tail of the last tile: no material */
+}
+
+__global__ void k_fill_words(u32* __restrict__ p, u32 n, u32 value)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = value;
+}
+
+/* local object records with pointers globalised, into this rank's slice of the global table (the LUT-independent fields are copied) */
+__global__ void k_globalize_objects(const tg_object_data* __restrict__ p_objects, u32 object_capacity, u32 global_pointer_base, tg_object_data* __restrict__ p_out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= object_capacity) return;
+    tg_object_data o = p_objects[i];
+    if (o.n_cluster_pointers_per_dim.x != 0 && o.n_cluster_pointers_per_dim.y != 0 && o.n_cluster_pointers_per_dim.z != 0) o.first_cluster_pointer += global_pointer_base;
+    p_out[i] = o;
+}
+
+/* "this rank's K1 (and material words) of frame `seq` are complete": everything written before is visible system-wide first */
+__global__ void k_signal(u32* __restrict__ p_signal, u32 seq)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile u32*>(p_signal) = seq;
+}
+
+/*
+ * Lane r waits until rank r has published frame `seq` (wrap-safe comparison). Bounded: a peer that never arrives (a crashed
+ * process) must not hang this GPU for ever -- after ~4 s the kernel gives up and raises the error word the host checks at the
+ * next synchronisation point.
+ */
+__global__ void k_wait_peers(const tgb_peer_flags signals, u32 n_ranks, u32 seq, u32* __restrict__ p_error)
+{
+    const u32 r = threadIdx.x;
+    if (r >= n_ranks) return;
+    const volatile u32* p = reinterpret_cast<const volatile u32*>(signals.p_tile_flags[r]);
+    const long long t0 = clock64();
+    while ((i32)(*p - seq) < 0)
+    {
+        __nanosleep(64);
+        if (clock64() - t0 > 8000000000ll) { atomicExch(p_error, 1u + r); break; }
+    }
+    __threadfence_system();
 }
 
 extern "C" void tgbd_set_merge_kind(struct tgb_device* d, u32 kind) { d->merge_kind = kind; }
@@ -113,9 +173,9 @@ extern "C" b32 tgbd_p2p_prepare(struct tgb_device* d)
 #define TGB_P2P_TRY(call) do { if ((call) != cudaSuccess) { n_failed++; cudaGetLastError(); } } while (0)
     d->d_vis_pair[0] = d->d_vis; d->d_mat_pair[0] = d->d_mat; d->vis_flip = 0;
     TGB_P2P_TRY(cudaMalloc(&d->d_vis_pair[1], px * sizeof(u64)));
-    TGB_P2P_TRY(cudaMalloc(&d->d_mat_pair[1], padded_px * sizeof(u64)));
+    TGB_P2P_TRY(cudaMalloc(&d->d_mat_pair[1], tgbd_mat_bytes(d)));
     TGB_P2P_TRY(cudaMalloc(&d->d_vis_tile, (u64)d->width * d->tile_rows * sizeof(u64)));
-    if (!d->d_ipc_stage && cudaMalloc(&d->d_ipc_stage, (u64)d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t)) != cudaSuccess)
+    if (!d->d_ipc_stage && cudaMalloc(&d->d_ipc_stage, (u64)d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t) + 64u) != cudaSuccess)
     {
         /* without the staging buffer the collectives themselves cannot run on any rank that got it; this one failure is fatal for the
          * exchange and is reported (the other ranks would wait): there is nothing smaller to allocate instead */
@@ -130,7 +190,7 @@ extern "C" b32 tgbd_p2p_prepare(struct tgb_device* d)
         return TG_FALSE;
     }
     if (d->d_vis_pair[1]) TGB_P2P_TRY(cudaMemsetAsync(d->d_vis_pair[1], 0xFF, px * sizeof(u64), d->stream));
-    if (d->d_mat_pair[1]) TGB_P2P_TRY(cudaMemsetAsync(d->d_mat_pair[1], 0, padded_px * sizeof(u64), d->stream));
+    if (d->d_mat_pair[1]) TGB_P2P_TRY(cudaMemsetAsync(d->d_mat_pair[1], 0, tgbd_mat_bytes(d), d->stream));
 
     cudaIpcMemHandle_t mine[4];
     /* test hook: TGB200_FAIL_P2P_ON_RANK=r makes rank r report a failed mapping, which must send EVERY rank to the NCCL path */
@@ -185,6 +245,8 @@ extern "C" b32 tgbd_p2p_prepare(struct tgb_device* d)
         if (getenv("TGB200_VERBOSE")) fprintf(stderr, "[tgb200] rank %u: peer memory unavailable (%u failed mappings), using the NCCL collectives\n", d->rank, total_failed);
         return TG_FALSE;
     }
+    cudaMemsetAsync(d->d_ipc_stage + (u64)d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t), 0, 64, d->stream); /* k_wait_peers' error word */
+    d->frame_seq = 1; /* the frame in flight (its clear ran before the mapping existed) publishes 1; every counter starts at 0 */
     d->p2p_ready = TG_TRUE;
     return TG_TRUE;
 }
@@ -200,6 +262,55 @@ static tgb_peer_table tgbd__peer_table(struct tgb_device* d)
     return t;
 }
 
+/* the peers' tile flags (tail of their material buffers of the current flip), or their frame counters */
+static tgb_peer_flags tgbd__peer_tails(struct tgb_device* d, bool signals)
+{
+    tgb_peer_flags f;
+    for (u32 r = 0; r < TGB_MAX_RANKS; r++)
+    {
+        const u64* p_mat = r < d->n_ranks ? d->peer_mat[d->vis_flip][r] : NULL;
+        f.p_tile_flags[r] = p_mat ? (signals ? tgbd_mat_signal(d, p_mat) : tgbd_mat_tile_flags(d, p_mat)) : NULL;
+    }
+    return f;
+}
+
+/* the error word of k_wait_peers lives behind the IPC handle staging area */
+static u32* tgbd__wait_error(struct tgb_device* d) { return (u32*)(d->d_ipc_stage + (u64)d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t)); }
+
+/* the 96-byte object records of every rank (pointers globalised by the owner): collective, every rank calls it at the same point of its frame */
+extern "C" b32 tgbd_gather_objects(struct tgb_device* d)
+{
+    if (!d->p_comm || d->n_ranks < 2) return TG_TRUE;
+    const u32 cap = d->object_capacity;
+    k_globalize_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->d_objects_global + (u64)d->rank * cap);
+    TGB_LAUNCH_CHECK(d);
+    if (!tgbn_allgather_bytes(d->p_comm, d->d_objects_global + (u64)d->rank * cap, d->d_objects_global, (u64)cap * sizeof(tg_object_data), d->stream)) return TG_FALSE;
+    d->objects_gathered = TG_TRUE;
+    return TG_TRUE;
+}
+
+/* publish "K1 done" for this frame, then wait for every peer's (asynchronous on the stream) */
+extern "C" b32 tgbd_p2p_barrier(struct tgb_device* d)
+{
+    if (!d->p2p_ready) { tgb_set_error("p2p_barrier: peer memory is not mapped"); return TG_FALSE; }
+    k_signal<<<1, 1, 0, d->stream>>>(tgbd_mat_signal(d, d->d_mat), d->frame_seq);
+    TGB_LAUNCH_CHECK(d);
+    TGB_CUDA(cudaEventRecord(d->ev[11], d->stream));
+    k_wait_peers<<<1, 32, 0, d->stream>>>(tgbd__peer_tails(d, true), d->n_ranks, d->frame_seq, tgbd__wait_error(d));
+    TGB_LAUNCH_CHECK(d);
+    TGB_CUDA(cudaEventRecord(d->ev[12], d->stream));
+    return TG_TRUE;
+}
+
+/* every tile flag of this rank's current buffer = 1: the words were not written by K1's epilogue (uploaded buffer, BLOCKS view) */
+extern "C" b32 tgbd_p2p_flag_all_tiles(struct tgb_device* d)
+{
+    const u32 n = tgbd_n_tiles(d);
+    k_fill_words<<<(n + 255) / 256, 256, 0, d->stream>>>(tgbd_mat_tile_flags(d, d->d_mat), n, 1u);
+    TGB_LAUNCH_CHECK(d);
+    return TG_TRUE;
+}
+
 /* this rank's tile: merged words into d_vis_tile, the winners' material words into d_mat_tile (asynchronous on the stream) */
 extern "C" b32 tgbd_p2p_merge_tile(struct tgb_device* d)
 {
@@ -208,7 +319,8 @@ extern "C" b32 tgbd_p2p_merge_tile(struct tgb_device* d)
     const u64 first = (u64)d->rank * tile_px, n = tile_px; /* this rank's virtual rows: one contiguous block of every buffer */
     /* d_vis keeps this rank's LOCAL words (the peers read them, and a re-render without a clear must find them): the merged tile
      * goes to its own buffer, addressed with whole-frame pixel indices like d_vis */
-    k_merge_tile<<<(u32)((tile_px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), d->n_ranks, first, n, d->d_vis_tile - first, d->d_mat_tile, tile_px);
+    k_merge_tile<<<(u32)((tile_px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), tgbd__peer_tails(d, false), d->n_ranks, d->width, tgbd_tiles_x(d), first, n,
+                                                                      d->d_vis_tile - first, d->d_mat_tile, tile_px);
     TGB_LAUNCH_CHECK(d);
     d->tile_merged = TG_TRUE;
     return TG_TRUE;
@@ -216,8 +328,9 @@ extern "C" b32 tgbd_p2p_merge_tile(struct tgb_device* d)
 
 /*
  * The whole merged frame for a read-back or a pick. After the all-reduce that is d_vis itself; on the fused path d_vis holds this
- * rank's local words and only the tile was merged, so the frame is pulled from the peers into a separate buffer. Valid while the
- * peers have finished K1 of this frame and not cleared this buffer again (they render in lock-step; call it between frames).
+ * rank's local words and only the tile was merged, so the frame is pulled from the peers into a separate buffer (every rank's words,
+ * no tile flags: the slow, always-valid form). Valid while the peers have finished K1 of this frame and not cleared this buffer
+ * again (they render in lock-step; call it between frames).
  */
 extern "C" void* tgbd_visibility_for_read(struct tgb_device* d)
 {
@@ -225,7 +338,22 @@ extern "C" void* tgbd_visibility_for_read(struct tgb_device* d)
     if (cudaSetDevice(d->device) != cudaSuccess) return d->d_vis;
     const u64 px = (u64)d->width * d->tile_rows * d->n_ranks;
     if (!d->d_vis_full && cudaMalloc(&d->d_vis_full, px * sizeof(u64)) != cudaSuccess) { tgb_set_error("visibility_for_read: out of device memory"); return d->d_vis; }
-    k_merge_tile<<<(u32)((px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), d->n_ranks, 0, px, d->d_vis_full, NULL, 0);
+    tgb_peer_flags none;
+    memset(&none, 0, sizeof(none));
+    k_merge_tile<<<(u32)((px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), none, d->n_ranks, d->width, tgbd_tiles_x(d), 0, px, d->d_vis_full, NULL, 0);
     d->n_kernel_launches++;
     return d->d_vis_full;
+}
+
+/* host side of k_wait_peers' time-out: called where the stream has just been synchronised */
+extern "C" void tgbd_p2p_check(struct tgb_device* d)
+{
+    if (!d->p2p_ready || !d->d_ipc_stage) return;
+    u32 err = 0;
+    if (cudaMemcpy(&err, tgbd__wait_error(d), sizeof(u32), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return; }
+    if (err)
+    {
+        tgb_set_error("peer-memory merge: rank %u never published its frame (waited ~4 s for its K1): that process is gone or its frames are out of step", err - 1u);
+        cudaMemset(tgbd__wait_error(d), 0, sizeof(u32));
+    }
 }

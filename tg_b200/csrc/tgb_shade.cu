@@ -795,16 +795,6 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
 }
 
 /* ---- owner-resolved materials (multi-GPU) ------------------------------------------------------------------ */
-/* local object records with pointers / LUT-independent fields globalised, into this rank's slice of the global table */
-__global__ void k_globalize_objects(const tg_object_data* __restrict__ p_objects, u32 object_capacity, u32 global_pointer_base, tg_object_data* __restrict__ p_out)
-{
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= object_capacity) return;
-    tg_object_data o = p_objects[i];
-    if (o.n_cluster_pointers_per_dim.x != 0 && o.n_cluster_pointers_per_dim.y != 0 && o.n_cluster_pointers_per_dim.z != 0) o.first_cluster_pointer += global_pointer_base;
-    p_out[i] = o;
-}
-
 /*
  * SURVEY.md section 8e "second exchange": the LUT-index bytes (512 B per cluster) exist only on the GPU that owns the
  * cluster. After the visibility merge every rank looks at every pixel; where the winning pointer is its own it writes
@@ -1056,18 +1046,20 @@ extern "C" b32 tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera
     }
     if (fused)
     {
-        /* merge over peer memory (tgb_peer.cu): material of the LOCAL winners, then the one collective of the frame -- the all-gather
-         * of the object records, which doubles as the barrier "every rank has finished K1 + resolve" -- then min + winner's material
-         * for this rank's tile straight from the peers' buffers. Timed as the merge stage. */
+        /* merge over peer memory (tgb_peer.cu). K1's epilogue already resolved the material of this rank's hits and flagged its tiles;
+         * what is left: publish "K1 done", wait for the peers' counters, min + winner's material for this rank's tile straight from the
+         * peers' buffers. Timed as the merge stage. Words that did not come from K1 (an uploaded buffer, the BLOCKS view's SVO pass) take
+         * the second pass over the buffer first, and objects that were not gathered before K1 are gathered now. */
         tgbd_merge_begin(d);
-        k_resolve_material<<<(u32)((n_padded + 255) / 256), 256, 0, d->stream>>>(d->d_vis, n_pixels, n_padded, d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_lut_idx,
-                                                                                 d->d_color_lut, d->global_pointer_base, n_local_pointers, d->rank * cap, d->d_mat);
-        TGB_LAUNCH_CHECK(d);
-        k_globalize_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->d_objects_global + (u64)d->rank * cap);
-        TGB_LAUNCH_CHECK(d);
-        TGB_CUDA(cudaEventRecord(d->ev[11], d->stream));
-        if (!tgbn_allgather_bytes(d->p_comm, d->d_objects_global + (u64)d->rank * cap, d->d_objects_global, (u64)cap * sizeof(tg_object_data), d->stream)) return TG_FALSE;
-        TGB_CUDA(cudaEventRecord(d->ev[12], d->stream));
+        if (!d->mat_from_k1)
+        {
+            k_resolve_material<<<(u32)((n_padded + 255) / 256), 256, 0, d->stream>>>(d->d_vis, n_pixels, n_padded, d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_lut_idx,
+                                                                                     d->d_color_lut, d->global_pointer_base, n_local_pointers, d->rank * cap, d->d_mat);
+            TGB_LAUNCH_CHECK(d);
+            if (!tgbd_p2p_flag_all_tiles(d)) return TG_FALSE;
+        }
+        if (!d->objects_gathered && !tgbd_gather_objects(d)) return TG_FALSE;
+        if (!tgbd_p2p_barrier(d)) return TG_FALSE; /* records ev[11] (published) and ev[12] (every peer arrived) */
         if (!tgbd_p2p_merge_tile(d)) return TG_FALSE;
         tgbd_merge_end(d);
         d->ev_merge_parts = TG_TRUE;
@@ -1079,9 +1071,7 @@ extern "C" b32 tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera
     {
         TGB_CUDA(cudaEventRecord(d->ev[7], d->stream));
         /* replicate the object records (96 B each) of every shard; pointers globalised by the owner */
-        k_globalize_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->d_objects_global + (u64)d->rank * cap);
-        TGB_LAUNCH_CHECK(d);
-        if (!tgbn_allgather_bytes(d->p_comm, d->d_objects_global + (u64)d->rank * cap, d->d_objects_global, (u64)cap * sizeof(tg_object_data), d->stream)) return TG_FALSE;
+        if (!d->objects_gathered && !tgbd_gather_objects(d)) return TG_FALSE;
         k_object_frames<<<(n_global + 127) / 128, 128, 0, d->stream>>>(d->d_objects_global, n_global, camera, d->d_frames_global);
         TGB_LAUNCH_CHECK(d);
 

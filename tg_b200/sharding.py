@@ -74,3 +74,25 @@ def merge_tile_from_peers(all_vis, rank, height, width):
     best = np.take_along_axis(tile, who[None], axis=0)[0]
     who = np.where(best == np.uint64(0xFFFFFFFFFFFFFFFF), -1, who)
     return best, who
+
+
+def tile_hit_flags(vis):
+    """K1's epilogue on the peer-memory path, stated on the host: one flag per 16x16 pixel tile of a rank's LOCAL buffer, set when
+    the rank has any hit there ([ceil(h/16), ceil(w/16)] bool). k_merge_tile does not read a peer's tile whose flag is clear."""
+    h, w = vis.shape
+    th, tw = (h + BAND_ROWS - 1) // BAND_ROWS, (w + 15) // 16
+    padded = np.full((th * BAND_ROWS, tw * 16), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    padded[:h, :w] = vis
+    return (padded.reshape(th, BAND_ROWS, tw, 16) != np.uint64(0xFFFFFFFFFFFFFFFF)).any(axis=(1, 3))
+
+
+def merge_tile_from_flagged_peers(all_vis, all_flags, rank, height, width):
+    """merge_tile_from_peers reading only the tiles a peer flagged (what crosses NVLink): (merged words of the rank's tile rows,
+    fraction of the (rank, pixel) reads that were skipped). Skipped tiles hold only the clear value, so the minimum is unchanged."""
+    n_ranks = all_vis.shape[0]
+    rows = tile_physical_rows(height, n_ranks, rank)
+    rows = rows[rows >= 0]
+    cols = np.arange(width)
+    flagged = np.stack([f[np.ix_(rows // BAND_ROWS, cols // 16)] for f in all_flags])     # [n_ranks, rows, width]
+    words = np.where(flagged, all_vis[:, rows], np.uint64(0xFFFFFFFFFFFFFFFF))
+    return words.min(axis=0), 1.0 - float(flagged.mean())
