@@ -112,7 +112,7 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
         TGB_CUDA(cudaMalloc(&d->d_mat, mat_bytes));
         TGB_CUDA(cudaMalloc(&d->d_mat_tile, (u64)width * d->tile_rows * sizeof(u64)));
         TGB_CUDA(cudaMemsetAsync(d->d_mat, 0, mat_bytes, d->stream));
-        d->frame_seq = 0; d->mat_from_k1 = TG_FALSE; d->objects_gathered = TG_FALSE;
+        d->frame_seq = 0; d->tiles_flagged = TG_FALSE; d->objects_gathered = TG_FALSE;
     }
     if (d->d_vis) TGB_CUDA(cudaFree(d->d_vis));
     if (d->d_radiance_pair[0]) TGB_CUDA(cudaFree(d->d_radiance_pair[0]));
@@ -245,7 +245,7 @@ extern "C" b32 tgbd_upload(struct tgb_device* d, u32 buffer, u64 dst_offset_byte
     TGB_CUDA(cudaSetDevice(d->device));
     /* pageable source: the copy is staged before the call returns, so the caller may reuse p_src */
     TGB_CUDA(cudaMemcpyAsync(p + dst_offset_bytes, p_src, n_bytes, cudaMemcpyHostToDevice, d->stream));
-    if (buffer == TGB_BUF_VISIBILITY) d->mat_from_k1 = TG_FALSE; /* uploaded words: the sharded shading stage resolves their materials itself */
+    if (buffer == TGB_BUF_VISIBILITY) d->tiles_flagged = TG_FALSE; /* uploaded words: the sharded shading stage resolves their materials itself */
     if (buffer == TGB_BUF_OBJECTS) d->objects_gathered = TG_FALSE;
     return TG_TRUE;
 }
@@ -325,6 +325,9 @@ extern "C" b32 tgbd_set_comm(struct tgb_device* d, void* p_comm, u32 rank, u32 n
     {
         TGB_CUDA(cudaMalloc(&d->d_objects_global, (u64)d->n_ranks * d->object_capacity * sizeof(tg_object_data)));
         TGB_CUDA(cudaMalloc(&d->d_frames_global, (u64)d->n_ranks * d->object_capacity * sizeof(tgb_object_frame)));
+        /* slots no rank has published yet must read as uninitialised objects (all dims 0), not as garbage */
+        TGB_CUDA(cudaMemsetAsync(d->d_objects_global, 0, (u64)d->n_ranks * d->object_capacity * sizeof(tg_object_data), d->stream));
+        TGB_CUDA(cudaMemsetAsync(d->d_frames_global, 0, (u64)d->n_ranks * d->object_capacity * sizeof(tgb_object_frame), d->stream));
     }
     return tgbd_resize(d, d->width, d->height); /* tile-sized buffers depend on n_ranks */
 }

@@ -99,10 +99,10 @@ struct tgb_device
     u64*              peer_mat[2][TGB_MAX_RANKS];
     u64*              d_vis_full;       /* whole merged frame pulled from the peers on demand (read-back, picking) */
     /* Behind the material words every d_mat buffer carries a small tail the peers read too (same IPC mapping): one u32 per 16x16 tile
-     * "this rank has a hit in the tile" (K1's epilogue; k_merge_tile skips the peers' empty tiles: at N = 8 a tile is covered by one or
+     * "this rank has a hit in the tile" (written by K1; the material pass and the peers' k_merge_tile skip empty tiles: at N = 8 a tile is covered by one or
      * two ranks' objects, not eight) and the frame counter this rank publishes when its K1 is done (tgb_peer.cu: the device-side barrier). */
     u32               frame_seq;        /* frames started on the peer-memory path (tgbd_clear); equal on all ranks (they render in lock-step) */
-    b32               mat_from_k1;      /* K1's epilogue wrote this frame's material words and tile flags */
+    b32               tiles_flagged;    /* K1 wrote this frame's tile flags (false: uploaded words, BLOCKS view -> every tile counts as hit) */
     b32               objects_gathered; /* the object records were all-gathered since the last clear */
     u8*               d_ipc_stage;
     tg_object_data*   d_objects_global; /* [n_ranks * object_capacity] every rank's records, pointers globalised */
@@ -153,13 +153,18 @@ static __global__ void k_set_words(u32* __restrict__ p, u32 n, u32 value)
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) p[i] = value;
 }
 
-/* layout of a material buffer: [padded_px] u64 words | [n_tiles] u32 tile flags | [1] u32 frame counter (+ padding) */
+/* layout of a material buffer: [padded_px] u64 words | [n_tiles] u32 tile flags | [16] u32: frame counter, number of published objects, padding |
+ * [object_capacity] tg_object_data published records (globalised pointers) | [object_capacity] u32 their object indices.
+ * A rank publishes the objects that survived its cull (only those can have won a pixel), or all of them when no cull ran. */
 static inline u32 tgbd_tiles_x(const struct tgb_device* d) { return (d->width + 15u) / 16u; }
 static inline u32 tgbd_n_tiles(const struct tgb_device* d) { return tgbd_tiles_x(d) * (d->tile_rows * (d->n_ranks ? d->n_ranks : 1u) / TGB_BAND_ROWS); }
 static inline u64 tgbd_padded_px(const struct tgb_device* d) { return (u64)d->width * d->tile_rows * (d->n_ranks ? d->n_ranks : 1u); }
-static inline u64 tgbd_mat_bytes(const struct tgb_device* d) { return tgbd_padded_px(d) * sizeof(u64) + (((u64)tgbd_n_tiles(d) + 16u) * sizeof(u32) + 7u) / 8u * 8u; }
+static inline u64 tgbd_mat_flag_bytes(const struct tgb_device* d) { return (((u64)tgbd_n_tiles(d) + 16u) * sizeof(u32) + 15u) / 16u * 16u; }
+static inline u64 tgbd_mat_bytes(const struct tgb_device* d) { return tgbd_padded_px(d) * sizeof(u64) + tgbd_mat_flag_bytes(d) + (u64)d->object_capacity * (sizeof(tg_object_data) + sizeof(u32)); }
 static inline u32* tgbd_mat_tile_flags(const struct tgb_device* d, const u64* p_mat) { return (u32*)(p_mat + tgbd_padded_px(d)); }
-static inline u32* tgbd_mat_signal(const struct tgb_device* d, const u64* p_mat) { return tgbd_mat_tile_flags(d, p_mat) + tgbd_n_tiles(d); }
+static inline u32* tgbd_mat_signal(const struct tgb_device* d, const u64* p_mat) { return tgbd_mat_tile_flags(d, p_mat) + tgbd_n_tiles(d); } /* [0] frame counter, [1] published objects */
+static inline tg_object_data* tgbd_mat_objects(const struct tgb_device* d, const u64* p_mat) { return (tg_object_data*)((u8*)tgbd_mat_tile_flags(d, p_mat) + tgbd_mat_flag_bytes(d)); }
+static inline u32* tgbd_mat_object_indices(const struct tgb_device* d, const u64* p_mat) { return (u32*)(tgbd_mat_objects(d, p_mat) + d->object_capacity); }
 
 #define TGB_CUDA(call)                                                                              \
     do {                                                                                            \

@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
 
     const u32 n_rays = p_q_count[0];
     if (blockIdx.x == 0 && tid == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
-    /* few rays (a band, a screen tile of a sharded frame): fewer CTAs so that every ray slot still sees min_rays_per_slot rays --
-     * a lane whose K rays all came from the last refill finishes them with the warp draining around it */
+    /* CTAs beyond what the queue can feed (a band, a screen tile of a sharded frame) leave at once. min_rays_per_slot > 1 would keep
+     * even fewer CTAs so that every ray slot sees several rays; measured on a 272-row tile (873 k rays): 0.41 ms with 1, 0.49 with 4, 0.69
+     * with 8 -- with few rays the longest dependent chains set the duration and parallelism is all that helps (profiles/r02k) */
     if (blockIdx.x >= n_sms && (u64)blockIdx.x * (TGB_POOL_THREADS * K) * min_rays_per_slot >= n_rays) return;
 
     u32 kinds = 0; /* 4 bits per ray slot, all IDLE */
@@ -227,7 +228,7 @@ extern "C" b32 tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane)
     const u32 dda_steps = (u32)max(1, tgbd_env_int("TGB_GI_POOL_DDA_STEPS", 16));
     const u32 tree_reps = (u32)max(1, tgbd_env_int("TGB_GI_POOL_TREE_REPS", 4));
     const u32 dda_bias = (u32)tgbd_env_int("TGB_GI_POOL_DDA_BIAS", 0);
-    const u32 min_rays_per_slot = (u32)max(1, tgbd_env_int("TGB_GI_POOL_MIN_RAYS_PER_SLOT", 4));
+    const u32 min_rays_per_slot = (u32)max(1, tgbd_env_int("TGB_GI_POOL_MIN_RAYS_PER_SLOT", 1));
     const int service_env = tgbd_env_int("TGB_GI_POOL_SERVICE_SLOTS", 0);
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);

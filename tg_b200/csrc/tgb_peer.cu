@@ -11,15 +11,15 @@
  * N - 1 of them over NVLink -- a running min, one more load from the winner. 58 MB cross the switch per rank at N = 8
  * instead of two all-to-all collectives, and nothing is written that another rank reads.
  *
- * What crosses the switch is cut further by K1 itself: its epilogue (k_visibility<.., SHARDED>) resolves the material of the rank's
- * hits (no second pass over the buffer) and records per 16x16 tile whether the rank has any hit there; k_merge_tile reads a peer's
- * words only for tiles that peer flagged -- with the objects dealt out over the ranks a tile is covered by one or two ranks, not N.
+ * What crosses the switch is cut further by K1 itself: k_visibility<.., SHARDED> records per 16x16 tile whether the rank has any hit
+ * there; the material pass only visits those tiles (k_resolve_material_tiles) and k_merge_tile reads a peer's words only for tiles
+ * that peer flagged -- with the objects dealt out over the ranks a tile is covered by one or two ranks, not N.
  *
  * Synchronisation: both buffers are double buffered (flipped by tgbd_clear) and carry, behind the material words, the tile flags
  * and a frame counter. A rank PUBLISHES the frame number when its K1 is done (k_signal: system-scope fence, then the store) and
  * WAITS until every peer has published it (k_wait_peers polls the peers' counters over NVLink) before k_merge_tile runs -- no
- * collective sits between K1 and the merge any more; the all-gather of the 96-byte object records (objects may have moved) runs
- * before K1, where nobody waits for anybody's K1. Why two buffers suffice: a rank that starts frame i + 2 (and clears the buffer
+ * collective sits in the frame any more: the 96-byte object records the shading stage needs from every rank (objects may have moved)
+ * are published in the same tail before the counter and collected from the peers after the wait (k_collect_objects). Why two buffers suffice: a rank that starts frame i + 2 (and clears the buffer
  * of frame i) has finished its merge of frame i + 1, which waited for every peer's K1 of frame i + 1, which those peers started
  * after their merge of frame i -- the last reader of that buffer. The min is associative and commutative, so the merged tile is
  * bit-identical to the all-reduce and to a single-GPU frame (tests/test_multi_gpu.py runs both paths; bench.py re-checks it at
@@ -39,29 +39,50 @@ struct tgb_peer_flags
     const u32* p_tile_flags[TGB_MAX_RANKS]; /* NULL table entry 0 = no flags: read every rank's words */
 };
 
-/* pixels [first, first + n) of the frame (virtual row order): merged word -> p_vis_out[first + i], winner's material word -> p_mat_out[i] (if any) */
-__global__ void __launch_bounds__(256) k_merge_tile(const tgb_peer_table t, const tgb_peer_flags fl, u32 n_ranks, u32 w, u32 tiles_x, u64 first, u64 n,
-                                                    u64* __restrict__ p_vis_out, u64* __restrict__ p_mat_out, u64 n_mat_out)
+/* pixels [first, first + n) of the frame (virtual row order), every rank's words: merged word -> p_vis_out[first + i] (read-back / picking) */
+__global__ void __launch_bounds__(256) k_merge_linear(const tgb_peer_table t, u32 n_ranks, u64 first, u64 n, u64* __restrict__ p_vis_out)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_mat_out && i >= n) return;
-    u64 best = TG_VIS_CLEAR, mat = 0;
-    if (i < n)
+    if (i >= n) return;
+    u64 best = TG_VIS_CLEAR;
+    for (u32 r = 0; r < n_ranks; r++)
     {
-        const u64 pixel = first + i;
-        const u32 tile = (u32)(pixel / w / TGB_BAND_ROWS) * tiles_x + (u32)(pixel % w) / 16u;
-        const bool use_flags = fl.p_tile_flags[0] != NULL;
-        u32 who = 0;
-        for (u32 r = 0; r < n_ranks; r++)
-        {
-            if (use_flags && __ldcv(&fl.p_tile_flags[r][tile]) == 0u) continue; /* that rank has no hit in this tile: its words are the clear value */
-            const u64 v = __ldcv(&t.p_vis[r][pixel]);
-            if (v < best) { best = v; who = r; } /* shards own disjoint pointer ranges: two ranks never hold the same word */
-        }
-        if (best != TG_VIS_CLEAR && p_mat_out) mat = __ldcv(&t.p_mat[who][pixel]);
-        p_vis_out[pixel] = best;
+        const u64 v = __ldcv(&t.p_vis[r][first + i]);
+        best = v < best ? v : best;
     }
-    if (p_mat_out && i < n_mat_out) p_mat_out[i] = mat; /* the padded tail of the last tile: no material */
+    p_vis_out[first + i] = best;
+}
+
+/*
+ * This rank's screen tile, one CTA per 16x16 pixel tile (blockIdx.y = band of the rank's tile, virtual rows first_row + 16 y ...):
+ * the CTA first fetches every rank's flag for the tile (N independent 4-byte loads), and its pixels then read words only from the
+ * ranks that have a hit there -- none at all for a tile of sky. Merged word -> p_vis_out[pixel] (whole-frame pixel index), the
+ * winner's material word -> p_mat_out[pixel - first_row * w].
+ */
+__global__ void __launch_bounds__(256) k_merge_tile(const tgb_peer_table t, const tgb_peer_flags fl, u32 n_ranks, u32 w, u32 tiles_x, u32 first_row,
+                                                    u64* __restrict__ p_vis_out, u64* __restrict__ p_mat_out)
+{
+    __shared__ u32 s_ranks;
+    const u32 vy0 = first_row + blockIdx.y * TGB_BAND_ROWS;
+    const u32 tile = (vy0 / TGB_BAND_ROWS) * tiles_x + blockIdx.x;
+    if (threadIdx.x == 0) s_ranks = 0u;
+    __syncthreads();
+    if (threadIdx.x < n_ranks && __ldcv(&fl.p_tile_flags[threadIdx.x][tile]) != 0u) atomicOr(&s_ranks, 1u << threadIdx.x);
+    __syncthreads();
+    const u32 x = blockIdx.x * 16u + (threadIdx.x & 15u), vy = vy0 + (threadIdx.x >> 4);
+    if (x >= w) return;
+    const u64 pixel = (u64)vy * w + x;
+    u64 best = TG_VIS_CLEAR, mat = 0;
+    u32 who = 0;
+    for (u32 m = s_ranks; m != 0; m &= m - 1u)
+    {
+        const u32 r = (u32)__ffs((int)m) - 1u;
+        const u64 v = __ldcv(&t.p_vis[r][pixel]);
+        if (v < best) { best = v; who = r; } /* shards own disjoint pointer ranges: two ranks never hold the same word */
+    }
+    if (best != TG_VIS_CLEAR) mat = __ldcv(&t.p_mat[who][pixel]);
+    p_vis_out[pixel] = best;
+    p_mat_out[pixel - (u64)first_row * w] = mat;
 }
 
 __global__ void k_fill_words(u32* __restrict__ p, u32 n, u32 value)
@@ -78,6 +99,40 @@ __global__ void k_globalize_objects(const tg_object_data* __restrict__ p_objects
     tg_object_data o = p_objects[i];
     if (o.n_cluster_pointers_per_dim.x != 0 && o.n_cluster_pointers_per_dim.y != 0 && o.n_cluster_pointers_per_dim.z != 0) o.first_cluster_pointer += global_pointer_base;
     p_out[i] = o;
+}
+
+/*
+ * What a rank publishes for the peers' shading stage: the 96-byte records (pointers globalised) of the objects that can have won a
+ * pixel -- the survivors of its cull (p_count[0] of them, named by the front-to-back sorted frames), or every object slot when no cull
+ * ran for the words in the buffer (p_frames == NULL). One thread per published object.
+ */
+__global__ void k_publish_objects(const tg_object_data* __restrict__ p_objects, u32 object_capacity, u32 global_pointer_base, const tgb_object_frame* __restrict__ p_frames,
+                                  const u32* __restrict__ p_count, tg_object_data* __restrict__ p_out, u32* __restrict__ p_out_idx, u32* __restrict__ p_out_count)
+{
+    const u32 n = p_frames ? min(p_count[0], object_capacity) : object_capacity;
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *p_out_count = n;
+    if (i >= n) return;
+    const u32 object_idx = p_frames ? p_frames[i].object_idx : i;
+    tg_object_data o = p_objects[object_idx];
+    if (o.n_cluster_pointers_per_dim.x != 0 && o.n_cluster_pointers_per_dim.y != 0 && o.n_cluster_pointers_per_dim.z != 0) o.first_cluster_pointer += global_pointer_base;
+    p_out[i] = o;
+    p_out_idx[i] = object_idx;
+}
+
+/* every rank's published records (tail of its material buffer of this frame) -> the dense global table [n_ranks * capacity]: blockIdx.y = rank */
+struct tgb_peer_objects { const tg_object_data* p_records[TGB_MAX_RANKS]; const u32* p_indices[TGB_MAX_RANKS]; const u32* p_counts[TGB_MAX_RANKS]; };
+__global__ void k_collect_objects(const tgb_peer_objects src, u32 object_capacity, tg_object_data* __restrict__ p_out)
+{
+    /* 96-byte records as 24 words each; volatile loads: the peers wrote them this frame */
+    const u32 r = blockIdx.y, words = (u32)(sizeof(tg_object_data) / 4u);
+    const u32 n = min(__ldcv(src.p_counts[r]), object_capacity);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n * words; i += gridDim.x * blockDim.x)
+    {
+        const u32 entry = i / words, k = i - entry * words;
+        const u32 object_idx = __ldcv(&src.p_indices[r][entry]);
+        if (object_idx < object_capacity) reinterpret_cast<u32*>(p_out + (u64)r * object_capacity + object_idx)[k] = __ldcv(reinterpret_cast<const u32*>(src.p_records[r] + entry) + k);
+    }
 }
 
 /* "this rank's K1 (and material words) of frame `seq` are complete": everything written before is visible system-wide first */
@@ -277,7 +332,8 @@ static tgb_peer_flags tgbd__peer_tails(struct tgb_device* d, bool signals)
 /* the error word of k_wait_peers lives behind the IPC handle staging area */
 static u32* tgbd__wait_error(struct tgb_device* d) { return (u32*)(d->d_ipc_stage + (u64)d->n_ranks * 4u * sizeof(cudaIpcMemHandle_t)); }
 
-/* the 96-byte object records of every rank (pointers globalised by the owner): collective, every rank calls it at the same point of its frame */
+/* the 96-byte object records of every rank (pointers globalised by the owner) through NCCL: collective, every rank calls it at the same
+ * point of its frame (the NCCL exchange path; the peer-memory path publishes them in tgbd_p2p_barrier instead) */
 extern "C" b32 tgbd_gather_objects(struct tgb_device* d)
 {
     if (!d->p_comm || d->n_ranks < 2) return TG_TRUE;
@@ -289,16 +345,36 @@ extern "C" b32 tgbd_gather_objects(struct tgb_device* d)
     return TG_TRUE;
 }
 
-/* publish "K1 done" for this frame, then wait for every peer's (asynchronous on the stream) */
+/*
+ * Publish this rank's frame -- the records (pointers globalised) of the objects that survived its cull into the tail of the current
+ * material buffer, then the frame counter behind a system-scope fence --, wait for every peer's counter, and collect the peers' object records. Everything the
+ * shading stage needs from the other ranks then sits in this GPU's memory or is read by k_merge_tile; no NCCL call in the frame.
+ * Asynchronous on the stream.
+ */
 extern "C" b32 tgbd_p2p_barrier(struct tgb_device* d)
 {
     if (!d->p2p_ready) { tgb_set_error("p2p_barrier: peer memory is not mapped"); return TG_FALSE; }
+    const u32 cap = d->object_capacity;
+    k_publish_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->tiles_flagged ? d->d_frames_sorted : NULL, d->d_visible_count,
+                                                              tgbd_mat_objects(d, d->d_mat), tgbd_mat_object_indices(d, d->d_mat), tgbd_mat_signal(d, d->d_mat) + 1);
+    TGB_LAUNCH_CHECK(d);
     k_signal<<<1, 1, 0, d->stream>>>(tgbd_mat_signal(d, d->d_mat), d->frame_seq);
     TGB_LAUNCH_CHECK(d);
     TGB_CUDA(cudaEventRecord(d->ev[11], d->stream));
     k_wait_peers<<<1, 32, 0, d->stream>>>(tgbd__peer_tails(d, true), d->n_ranks, d->frame_seq, tgbd__wait_error(d));
     TGB_LAUNCH_CHECK(d);
     TGB_CUDA(cudaEventRecord(d->ev[12], d->stream));
+    tgb_peer_objects src;
+    for (u32 r = 0; r < TGB_MAX_RANKS; r++)
+    {
+        const u64* p_mat = r < d->n_ranks ? d->peer_mat[d->vis_flip][r] : NULL;
+        src.p_records[r] = p_mat ? tgbd_mat_objects(d, p_mat) : NULL;
+        src.p_indices[r] = p_mat ? tgbd_mat_object_indices(d, p_mat) : NULL;
+        src.p_counts[r] = p_mat ? tgbd_mat_signal(d, p_mat) + 1 : NULL;
+    }
+    k_collect_objects<<<dim3(8, d->n_ranks), 256, 0, d->stream>>>(src, cap, d->d_objects_global);
+    TGB_LAUNCH_CHECK(d);
+    d->objects_gathered = TG_TRUE;
     return TG_TRUE;
 }
 
@@ -316,11 +392,12 @@ extern "C" b32 tgbd_p2p_merge_tile(struct tgb_device* d)
 {
     if (!d->p2p_ready) { tgb_set_error("p2p_merge_tile: peer memory is not mapped"); return TG_FALSE; }
     const u64 tile_px = (u64)d->width * d->tile_rows;
-    const u64 first = (u64)d->rank * tile_px, n = tile_px; /* this rank's virtual rows: one contiguous block of every buffer */
+    const u64 first = (u64)d->rank * tile_px; /* this rank's virtual rows: one contiguous block of every buffer */
     /* d_vis keeps this rank's LOCAL words (the peers read them, and a re-render without a clear must find them): the merged tile
      * goes to its own buffer, addressed with whole-frame pixel indices like d_vis */
-    k_merge_tile<<<(u32)((tile_px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), tgbd__peer_tails(d, false), d->n_ranks, d->width, tgbd_tiles_x(d), first, n,
-                                                                      d->d_vis_tile - first, d->d_mat_tile, tile_px);
+    const dim3 tiles(tgbd_tiles_x(d), d->tile_rows / TGB_BAND_ROWS);
+    k_merge_tile<<<tiles, 256, 0, d->stream>>>(tgbd__peer_table(d), tgbd__peer_tails(d, false), d->n_ranks, d->width, tgbd_tiles_x(d), d->rank * d->tile_rows,
+                                               d->d_vis_tile - first, d->d_mat_tile);
     TGB_LAUNCH_CHECK(d);
     d->tile_merged = TG_TRUE;
     return TG_TRUE;
@@ -338,9 +415,7 @@ extern "C" void* tgbd_visibility_for_read(struct tgb_device* d)
     if (cudaSetDevice(d->device) != cudaSuccess) return d->d_vis;
     const u64 px = (u64)d->width * d->tile_rows * d->n_ranks;
     if (!d->d_vis_full && cudaMalloc(&d->d_vis_full, px * sizeof(u64)) != cudaSuccess) { tgb_set_error("visibility_for_read: out of device memory"); return d->d_vis; }
-    tgb_peer_flags none;
-    memset(&none, 0, sizeof(none));
-    k_merge_tile<<<(u32)((px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), none, d->n_ranks, d->width, tgbd_tiles_x(d), 0, px, d->d_vis_full, NULL, 0);
+    k_merge_linear<<<(u32)((px + 255) / 256), 256, 0, d->stream>>>(tgbd__peer_table(d), d->n_ranks, 0, px, d->d_vis_full);
     d->n_kernel_launches++;
     return d->d_vis_full;
 }

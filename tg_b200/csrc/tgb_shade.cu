@@ -825,6 +825,37 @@ __global__ void __launch_bounds__(256) k_resolve_material(const u64* __restrict_
     p_mat[i] = word;
 }
 
+/* the same for the flagged 16x16 tiles only (sharded frame on the peer-memory path) */
+__global__ void __launch_bounds__(256) k_resolve_material_tiles(const u64* __restrict__ p_vis, u32 w, u32 tiles_x, const u32* __restrict__ p_tile_flags,
+                                                                const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_c2o,
+                                                                const tg_object_data* __restrict__ p_objects, const u8* __restrict__ p_lut_idx, const u32* __restrict__ p_color_lut,
+                                                                u32 global_pointer_base, u32 n_local_pointers, u32 global_object_base, u64* __restrict__ p_mat)
+{
+    /* a CTA walks 8 neighbouring tiles of its band: most of a rank's tiles have no hit, and a launch of one CTA per tile costs more than the flagged tiles' work */
+    for (u32 t = 0; t < 8u; t++)
+    {
+        const u32 tile_x = blockIdx.x * 8u + t;
+        if (tile_x >= tiles_x) break;
+        if (p_tile_flags[blockIdx.y * tiles_x + tile_x] == 0u) continue; /* no hit: nobody reads this tile's material words */
+        const u32 x = tile_x * 16u + (threadIdx.x & 15u), vy = blockIdx.y * 16u + (threadIdx.x >> 4);
+        if (x >= w) continue;
+        const u64 i = (u64)vy * w + x;
+        const u64 packed_data = p_vis[i];
+        const u32 depth24 = (u32)(packed_data >> TG_VIS_DEPTH_SHIFT);
+        const u32 local_pointer = ((u32)(packed_data >> TG_VIS_POINTER_SHIFT) & 2147483647u) - global_pointer_base;
+        u64 word = 0;
+        if ((f32)depth24 / TG_VIS_DEPTH_SCALE < 1.0f && local_pointer < n_local_pointers)
+        {
+            const u32 cluster_idx = __ldg(&p_cluster_pointers[local_pointer]);
+            const u32 object_idx = __ldg(&p_c2o[cluster_idx]);
+            const u32 color_lut_idx = __ldg(&p_lut_idx[(u64)cluster_idx * 512u + ((u32)packed_data & 511u)]);
+            const u32 packed_color = __ldg(&p_color_lut[p_objects[object_idx].lut_idx * 256u + color_lut_idx]);
+            word = ((u64)(global_object_base + object_idx + 1u) << 32) | (u64)packed_color;
+        }
+        p_mat[i] = word;
+    }
+}
+
 /* ---- present pass: present.frag:9-12 + the swapchain's format conversion --------------------------------------- */
 /*
  * The reference ends a frame by sampling the HDR target 1:1 into the swapchain image (present.frag: out_color = texture(..);
@@ -1046,20 +1077,27 @@ extern "C" b32 tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera
     }
     if (fused)
     {
-        /* merge over peer memory (tgb_peer.cu). K1's epilogue already resolved the material of this rank's hits and flagged its tiles;
-         * what is left: publish "K1 done", wait for the peers' counters, min + winner's material for this rank's tile straight from the
-         * peers' buffers. Timed as the merge stage. Words that did not come from K1 (an uploaded buffer, the BLOCKS view's SVO pass) take
-         * the second pass over the buffer first, and objects that were not gathered before K1 are gathered now. */
+        /* merge over peer memory (tgb_peer.cu). K1 flagged the tiles in which this rank has a hit: the material of this rank's LOCAL
+         * winners is resolved for those tiles only; then publish "K1 + materials done", wait for the peers' counters, min + winner's
+         * material for this rank's tile straight from the peers' buffers. Timed as the merge stage. Words that did not come from K1
+         * (an uploaded buffer, the BLOCKS view's SVO pass) take the pass over the whole buffer and count every tile as hit; the object records travel
+         * through the same peer-memory tail (tgbd_p2p_barrier). */
         tgbd_merge_begin(d);
-        if (!d->mat_from_k1)
+        if (d->tiles_flagged)
+        {
+            const dim3 tiles((tgbd_tiles_x(d) + 7u) / 8u, d->tile_rows * d->n_ranks / TGB_BAND_ROWS);
+            k_resolve_material_tiles<<<tiles, 256, 0, d->stream>>>(d->d_vis, d->width, tgbd_tiles_x(d), tgbd_mat_tile_flags(d, d->d_mat), d->d_cluster_pointers, d->d_c2o, d->d_objects,
+                                                                   d->d_lut_idx, d->d_color_lut, d->global_pointer_base, n_local_pointers, d->rank * cap, d->d_mat);
+            TGB_LAUNCH_CHECK(d);
+        }
+        else
         {
             k_resolve_material<<<(u32)((n_padded + 255) / 256), 256, 0, d->stream>>>(d->d_vis, n_pixels, n_padded, d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_lut_idx,
                                                                                      d->d_color_lut, d->global_pointer_base, n_local_pointers, d->rank * cap, d->d_mat);
             TGB_LAUNCH_CHECK(d);
             if (!tgbd_p2p_flag_all_tiles(d)) return TG_FALSE;
         }
-        if (!d->objects_gathered && !tgbd_gather_objects(d)) return TG_FALSE;
-        if (!tgbd_p2p_barrier(d)) return TG_FALSE; /* records ev[11] (published) and ev[12] (every peer arrived) */
+        if (!tgbd_p2p_barrier(d)) return TG_FALSE; /* publishes this rank's object records + frame counter, records ev[11] (published) and ev[12] (every peer arrived), collects the peers' records */
         if (!tgbd_p2p_merge_tile(d)) return TG_FALSE;
         tgbd_merge_end(d);
         d->ev_merge_parts = TG_TRUE;

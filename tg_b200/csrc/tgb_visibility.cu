@@ -48,7 +48,7 @@ extern "C" b32 tgbd_clear(struct tgb_device* d)
         d->d_mat = d->d_mat_pair[d->vis_flip];
         d->frame_seq++; /* what this rank publishes when its K1 is done, and what it waits for on its peers (tgb_peer.cu) */
     }
-    d->mat_from_k1 = TG_FALSE; d->objects_gathered = TG_FALSE;
+    d->tiles_flagged = TG_FALSE; d->objects_gathered = TG_FALSE;
     d->vis_merged = TG_FALSE; d->tile_merged = TG_FALSE;
     const u64 n = (u64)d->width * d->tile_rows * d->n_ranks; /* the padded frame */
     TGB_CUDA(cudaEventRecord(d->ev[0], d->stream));
@@ -459,20 +459,15 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
  */
 #define TGB_K1_THREADS 256
 /*
- * SHARDED (one process per GPU, merge over peer memory, tgb_peer.cu): a pixel is traced by exactly one lane against ALL of this
- * rank's objects, so the lane's best word is the rank's final word for the pixel and its material can be resolved right here --
- * the winner already holds the pointer and the voxel -- instead of by a second pass over the 66 MB buffer (k_resolve_material).
- * The CTA also records whether its 16x16 tile has any hit: k_merge_tile does not read a peer's tile that has none.
+ * SHARDED (one process per GPU, merge over peer memory, tgb_peer.cu): the CTA records whether its 16x16 tile has any hit. The
+ * material pass (k_resolve_material_tiles) and the peers' k_merge_tile skip the tiles that have none -- with the objects dealt out
+ * over N ranks that is most of a rank's frame. (Resolving the material right here, in K1's epilogue, was measured: the four
+ * dependent loads at the end of every CTA's life cost more, +0.07 ms at N = 2, than the separate pass over the flagged tiles.)
  */
 struct tgb_k1_shard_args
 {
-    const u32* __restrict__ p_c2o;
-    const tg_object_data* __restrict__ p_objects;
-    const u8* __restrict__ p_lut_idx;
-    const u32* __restrict__ p_color_lut;
-    u64* __restrict__ p_mat;        /* (global object idx + 1) << 32 | packed colour, virtual row order like p_vis */
     u32* __restrict__ p_tile_flags; /* [virtual band][tile column] */
-    u32 global_object_base, tiles_x;
+    u32 tiles_x;
 };
 
 template <int MIN_CTAS, bool REGROUP, bool SHARDED>
@@ -554,16 +549,6 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
     if (hit) atomicMin((unsigned long long*)&p_vis[pixel], (unsigned long long)best);
     if (SHARDED)
     {
-        if (hit)
-        {
-            /* the words of k_resolve_material (tgb_shade.cu) for the pixels this rank holds: shading.frag:122-135 on the owner */
-            const u32 local_pointer = ((u32)(best >> TG_VIS_POINTER_SHIFT) & 2147483647u) - global_pointer_base;
-            const u32 cluster_idx = __ldg(&p_cluster_pointers[local_pointer]);
-            const u32 object_idx = __ldg(&sh.p_c2o[cluster_idx]);
-            const u32 color_lut_idx = __ldg(&sh.p_lut_idx[(u64)cluster_idx * 512u + ((u32)best & 511u)]);
-            const u32 packed_color = __ldg(&sh.p_color_lut[sh.p_objects[object_idx].lut_idx * 256u + color_lut_idx]);
-            sh.p_mat[pixel] = ((u64)(sh.global_object_base + object_idx + 1u) << 32) | (u64)packed_color;
-        }
         const int any_hit = __syncthreads_or(hit ? 1 : 0);
         if (threadIdx.x == 0) sh.p_tile_flags[(tgb_row_to_virtual(blockIdx.y * TGB_TILE_H, n_ranks, tile_rows) / TGB_BAND_ROWS) * sh.tiles_x + blockIdx.x] = any_hit ? 1u : 0u;
     }
@@ -576,10 +561,6 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
     tgb_pinhole_init(p_cam, &pin);
 
     TGB_CUDA(cudaEventRecord(d->ev[2], d->stream));
-    /* Sharded, peer-memory path: the shading stage needs every rank's object records (96 B each; objects may have moved since the last
-     * frame). The all-gather runs HERE, before K1, where no rank waits in it for another rank's K1 -- the "K1 done" barrier of the
-     * merge is a counter in peer memory (tgb_peer.cu). */
-    if (d->p2p_ready && d->n_ranks > 1 && !tgbd_gather_objects(d)) return TG_FALSE;
     k_set_words<<<1, 32, 0, d->stream>>>(d->d_visible_count, 4, 0u);
     TGB_LAUNCH_CHECK(d);
     k_cull_objects<<<(object_capacity + 127) / 128, 128, 0, d->stream>>>(d->d_objects, object_capacity, *p_cam, pin, d->width, d->height, d->d_frames, d->d_visible_count);
@@ -597,15 +578,14 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
     const dim3 grid((d->width + TGB_TILE_W - 1) / TGB_TILE_W, (d->height + TGB_TILE_H - 1) / TGB_TILE_H);
     /* register budget: 4 CTAs per SM = 64 registers with ~30 spilled words, measured 11 % faster than 3 CTAs = 80 registers (TGB_K1_MIN_CTAS=3 selects that build; tuning only) */
     const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 4), regroup = tgbd_env_int("TGB_K1_REGROUP", 1);
-    /* sharded frame on the peer-memory path: K1's epilogue resolves the materials of this rank's hits and flags the tiles that have any */
+    /* sharded frame on the peer-memory path: K1 flags the tiles in which this rank has a hit */
     const bool sharded = d->p2p_ready && d->n_ranks > 1 && k1_kernel != 2;
     tgb_k1_shard_args sh;
     memset(&sh, 0, sizeof(sh));
     if (sharded)
     {
-        sh.p_c2o = d->d_c2o; sh.p_objects = d->d_objects; sh.p_lut_idx = d->d_lut_idx; sh.p_color_lut = d->d_color_lut;
-        sh.p_mat = d->d_mat; sh.p_tile_flags = tgbd_mat_tile_flags(d, d->d_mat);
-        sh.global_object_base = d->rank * d->object_capacity; sh.tiles_x = tgbd_tiles_x(d);
+        sh.p_tile_flags = tgbd_mat_tile_flags(d, d->d_mat);
+        sh.tiles_x = tgbd_tiles_x(d);
     }
 #define TGB_K1_LAUNCH(C, R, S) k_visibility<C, R, S><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height, \
                                                                                        d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis, d->n_ranks, d->tile_rows, fallback_only, sh)
@@ -614,7 +594,7 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
     else              { if (min_ctas >= 4) TGB_K1_LAUNCH(4, false, false); else TGB_K1_LAUNCH(3, false, false); }
 #undef TGB_K1_LAUNCH
     TGB_LAUNCH_CHECK(d);
-    d->mat_from_k1 = sharded ? TG_TRUE : TG_FALSE;
+    d->tiles_flagged = sharded ? TG_TRUE : TG_FALSE;
     TGB_CUDA(cudaEventRecord(d->ev[4], d->stream));
     d->ev_vis = TG_TRUE;
     return TG_TRUE;

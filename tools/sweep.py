@@ -53,7 +53,8 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--what", default="gi")
     ap.add_argument("--frames", type=int, default=12)
-    ap.add_argument("--rows", type=int, default=0, help="shade only the first ROWS rows (emulates the screen tile of a sharded frame)")
+    ap.add_argument("--rows", type=int, default=0, help="shade only ROWS rows starting at --row0 (emulates the screen tile of a sharded frame)")
+    ap.add_argument("--row0", type=int, default=0)
     ap.add_argument("--configs", default="", help="JSON list of knob dicts (overrides --what)")
     args = ap.parse_args()
 
@@ -91,7 +92,7 @@ def main():
             rt.clear()
             rt.render_visibility()
             if args.rows:
-                lib.tgb200_render_shading_rows(C.byref(rt._rt), 0, args.rows)
+                lib.tgb200_render_shading_rows(C.byref(rt._rt), args.row0, args.row0 + args.rows)
             else:
                 rt.render_shading()
             t = rt.timings()
@@ -100,7 +101,7 @@ def main():
                     stage[k].append(t[k])
         vis, rad = rt.read_visibility(), rt.read_radiance().view(np.uint32)
         if args.rows:
-            rad = rad[:args.rows]
+            rad = rad[args.row0:args.row0 + args.rows]
         if want_vis is None:
             want_vis, want_rad = vis.copy(), rad.copy()
         out = {"config": cfg, **{k: float(np.median(v)) for k, v in stage.items()}, "shading_min_ms": float(np.min(stage["shading_ms"])),
