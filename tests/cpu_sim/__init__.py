@@ -25,7 +25,7 @@ def lib():
         L.tgbsim_gi_trace.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.tgbsim_gi_trace.restype = C.c_uint32
         L.tgbsim_svo_traverse.argtypes = [u32p, u32p, u32p, f32p, f32p, C.c_float, C.c_uint32, f32p, f32p, f32p, u32p, u32p, C.POINTER(C.c_uint64)]
-        L.tgbsim_visibility.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+        L.tgbsim_visibility.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _LIB = L
     return _LIB
@@ -64,11 +64,11 @@ def svo_traverse(nodes, leaf_data, voxels, bmin, bmax, far_plane, origins, dirs)
     return res, node, vox, word
 
 
-def visibility(view, rays, w, h, y0=0, y1=None, ystep=1):
+def visibility(view, rays, w, h, y0=0, y1=None, ystep=1, defer=False):
     """K1's per-ray walk (tgb_k1_walk.cuh) over an oracle SceneView on the host -> (u64 words [h, w], [candidates marched, set-ups])."""
     out = np.empty(w * h, dtype=np.uint64)
-    work = np.zeros(2, dtype=np.uint64)
+    work = np.zeros(3, dtype=np.uint64)
     v = view.view
     lib().tgbsim_visibility(C.cast(v.p_objects, C.c_void_p), v.n_objects_capacity, v.p_cluster_pointers, v.p_voxel_cluster_data, C.cast(C.pointer(rays), C.c_void_p), w, h,
-                            v.global_pointer_base, y0, h if y1 is None else y1, ystep, _p(out, C.c_uint64), _p(work, C.c_uint64))
+                            v.global_pointer_base, y0, h if y1 is None else y1, ystep, 1 if defer else 0, _p(out, C.c_uint64), _p(work, C.c_uint64))
     return out.reshape(h, w), work

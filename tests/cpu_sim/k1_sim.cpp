@@ -11,7 +11,8 @@
 extern "C" {
 
 void tgbsim_visibility(const tg_object_data* p_objects, u32 n_objects, const u32* p_cluster_pointers, const u32* p_masks, const tg_camera_rays* p_cam,
-                       u32 w, u32 h, u32 global_pointer_base, u32 y0, u32 y1, u32 ystep, u64* p_out, u64* p_work /* [2]: candidates marched, set-ups that met the box */)
+                       u32 w, u32 h, u32 global_pointer_base, u32 y0, u32 y1, u32 ystep, u32 defer, u64* p_out,
+                       u64* p_work /* [3]: candidates marched, set-ups that met the box, second voxels found while one was pending */)
 {
     for (size_t i = 0; i < (size_t)w * h; i++) p_out[i] = TG_VIS_CLEAR;
     const v3 camera = tgb_v3(p_cam->camera.x, p_cam->camera.y, p_cam->camera.z);
@@ -37,6 +38,9 @@ void tgbsim_visibility(const tg_object_data* p_objects, u32 n_objects, const u32
                 if (!tgb_k1_setup(f, dir_ws, &walk)) continue;
                 if (p_work) p_work[1]++;
                 u32 cx, cy, cz; f32 enter;
+                /* defer: k_visibility's deferred word -- the walk goes on with an upper bound of t_skip, the exact word of the voxel found is
+                 * computed when the object is finished (or when a second voxel turns up) */
+                bool pending = false; u32 pcx = 0, pcy = 0, pcz = 0; i32 pvoxel = -1;
                 while (tgb_k1_next_candidate(f, &walk, t_skip, &cx, &cy, &cz, &enter))
                 {
                     /* the kernel re-derives the cluster from the stored walk */
@@ -45,8 +49,24 @@ void tgbsim_visibility(const tg_object_data* p_objects, u32 n_objects, const u32
                     if (rx != cx || ry != cy || rz != cz) { p_out[0] = 0xBADBADBADull; return; }
                     tgb_ray_in_object r;
                     tgb_ray_in_object_restore(&r, walk.d, walk.t_delta_x, walk.t_delta_y, walk.t_delta_z, walk.exotic != 0);
-                    tgb_cluster_march(f, r, cx, cy, cz, enter, p_cam->far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+                    if (!defer) tgb_cluster_march(f, r, cx, cy, cz, enter, p_cam->far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+                    else
+                    {
+                        const i32 voxel = tgb_cluster_find(f, r, cx, cy, cz, enter, p_cluster_pointers, p_masks);
+                        if (voxel >= 0)
+                        {
+                            if (pending) { tgb_cluster_word(f, r, pcx, pcy, pcz, pvoxel, p_cam->far_plane, global_pointer_base, best, t_skip); if (p_work) p_work[2]++; }
+                            pending = true; pcx = cx; pcy = cy; pcz = cz; pvoxel = voxel;
+                            t_skip = fminf(t_skip, tgb_cluster_t_skip_bound(f, r, cx, cy, cz, voxel, p_cam->far_plane));
+                        }
+                    }
                     if (p_work) p_work[0]++;
+                }
+                if (pending)
+                {
+                    tgb_ray_in_object r;
+                    tgb_ray_in_object_restore(&r, walk.d, walk.t_delta_x, walk.t_delta_y, walk.t_delta_z, walk.exotic != 0);
+                    tgb_cluster_word(f, r, pcx, pcy, pcz, pvoxel, p_cam->far_plane, global_pointer_base, best, t_skip);
                 }
                 p_out[(size_t)py * w + px] = best;
             }

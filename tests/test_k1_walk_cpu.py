@@ -18,6 +18,10 @@ def test_resumable_walk_equals_the_oracle(oracle, make, base):
     want, _ = oracle.visibility(view, rays, s.width, s.height, oracle.VIS_SCREEN_RECT)
     got, work = cpu_sim.visibility(view, rays, s.width, s.height)
     assert np.array_equal(got, want), describe_mismatch(got, want)
+    # k_visibility's deferred word: the walk continues on an upper bound of t_skip, the exact word is computed at the end of the object
+    deferred, work_d = cpu_sim.visibility(view, rays, s.width, s.height, defer=True)
+    assert np.array_equal(deferred, want), describe_mismatch(deferred, want)
+    assert work_d[0] >= work[0] and work_d[0] < 1.05 * work[0] + 50, (work, work_d)   # the looser bound admits few extra candidates
     assert work[0] > 0 and (want != np.uint64(0xFFFFFFFFFFFFFFFF)).sum() > 100
 
 
@@ -30,5 +34,6 @@ def test_camera_inside_an_object_and_grazing_views(oracle):
         rays = oracle.camera_rays(oracle.camera_from_spec(s.camera))
         view = oracle.SceneView.from_scene(s, with_lut=False)
         want, _ = oracle.visibility(view, rays, s.width, s.height, oracle.VIS_BRUTE_FORCE)
-        got, _ = cpu_sim.visibility(view, rays, s.width, s.height)
-        assert np.array_equal(got, want), f"camera {pos}: " + describe_mismatch(got, want)
+        for defer in (False, True):
+            got, _ = cpu_sim.visibility(view, rays, s.width, s.height, defer=defer)
+            assert np.array_equal(got, want), f"camera {pos} defer={defer}: " + describe_mismatch(got, want)

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                 {
                     /* ambient * 1 + lo; float addition commutes and the reductions do not stall the lane */
                     const u32 slot = S(W_SLOT, k);
-                    const float4 q0 = __ldcs(&p_q0[slot]), q2 = __ldcs(&p_q2[slot]); /* streaming: read once, keep L1 for the tree */
+                    const float4 q0 = __ldcg(&p_q0[slot]), q2 = __ldcs(&p_q2[slot]); /* q2 is read once (streaming); q0 was read at the refill: L2 only, keep L1 for the tree */
                     f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
                     atomicAdd(p_pixel + 0, q2.x);
                     atomicAdd(p_pixel + 1, q2.y);
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                 }
                 else if (kd == TGB_RAY_HIT)
                 {
-                    const float4 q0 = __ldcs(&p_q0[S(W_SLOT, k)]);
+                    const float4 q0 = __ldcg(&p_q0[S(W_SLOT, k)]);
                     const u32 vox = S(W_VOX, k);
                     v3 child_min; f32 child_size;
                     tgb_cell_box(&fr, S(W_CELL, k), &child_min, &child_size);
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                         const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
                         if (kd == TGB_RAY_IDLE && mine < n_rays)
                         {
-                            const float4 q0 = __ldcs(&p_q0[mine]), q1 = __ldcs(&p_q1[mine]);
+                            const float4 q0 = __ldcg(&p_q0[mine]), q1 = __ldcs(&p_q1[mine]); /* q0 is read again when the ray is decided (L2), q1 never */
                             const v3 d = tgb_v3(q1.x, q1.y, q1.z);
                             v3 position, t_delta; u32 flags;
                             tgb_gi_ray_start(&fr, tgb_v3(q0.x, q0.y, q0.z), d, q1.w, &position, &t_delta, &flags);

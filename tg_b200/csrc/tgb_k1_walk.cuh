@@ -140,9 +140,12 @@ TGB_HD bool tgb_cluster_candidate(const tgb_object_frame& f, const tgb_ray_in_ob
     return true;
 }
 
-/* Second half, visibility.frag:83-207: the 8^3 Amanatides-Woo march from `enter`, the depth of the voxel found, the packed word. */
-TGB_HD void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 enter, f32 far_plane,
-                              const u32* p_cluster_pointers, const u32* p_masks, u32 global_pointer_base, u64& best, f32& t_skip)
+/*
+ * Second half, visibility.frag:83-191: the 8^3 Amanatides-Woo march from `enter`. Returns the index 64 z + 8 y + x of the first solid
+ * voxel the shader's DDA meets, or -1 when the ray leaves the cluster without meeting one.
+ */
+TGB_HD i32 tgb_cluster_find(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 enter,
+                            const u32* p_cluster_pointers, const u32* p_masks)
 {
     const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
     const v3 d = r.d;
@@ -170,7 +173,6 @@ TGB_HD void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object
     /* visibility.frag:141-191; the 64-bit z-slice (words 2z, 2z+1) is fetched once per z */
     i32 z_cached = -1;
     u32 lo = 0, hi = 0;
-    bool found = false;
     for (;;)
     {
         if (z != z_cached)
@@ -179,7 +181,7 @@ TGB_HD void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object
             lo = s.x; hi = s.y; z_cached = z;
         }
         const u32 word = (y & 4) ? hi : lo;
-        if ((word >> (((y & 3) << 3) + x)) & 1u) { found = true; break; }
+        if ((word >> (((y & 3) << 3) + x)) & 1u) return 64 * z + 8 * y + x;
         if (t_max_x < t_max_y)
         {
             if (t_max_x < t_max_z) { t_max_x += r.t_delta_x; x += step_x; if (x < 0 || x >= 8) break; }
@@ -191,9 +193,20 @@ TGB_HD void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object
             else                   { t_max_z += r.t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
         }
     }
-    if (!found) return;
+    return -1;
+}
 
-    /* visibility.frag:151-157, 194-201: depth from the slab test against the voxel; only its `enter` is used */
+/*
+ * visibility.frag:151-157, 194-207 for the voxel tgb_cluster_find returned: depth from the slab test against the voxel (only its
+ * `enter` is used), quantisation, the packed word, best / t_skip update.
+ */
+TGB_HD void tgb_cluster_word(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, i32 voxel, f32 far_plane,
+                             u32 global_pointer_base, u64& best, f32& t_skip)
+{
+    const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
+    const v3 d = r.d;
+    const u32 cluster_pointer = f.first_cluster_pointer + cx + f.nx * (cy + f.ny * cz);
+    const i32 x = voxel & 7, y = (voxel >> 3) & 7, z = voxel >> 6;
     f32 voxel_enter;
     {
         const f32 vx = (f32)(d.x > 0.0f ? x : x + 1) - o.x, vy = (f32)(d.y > 0.0f ? y : y + 1) - o.y, vz = (f32)(d.z > 0.0f ? z : z + 1) - o.z;
@@ -214,7 +227,7 @@ TGB_HD void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object
         const f32 dq = depth * TG_VIS_DEPTH_SCALE;
         const u64 word = ((u64)dq << TG_VIS_DEPTH_SHIFT)
                        | ((u64)(cluster_pointer + global_pointer_base) << TG_VIS_POINTER_SHIFT)
-                       | (u64)(u32)(64 * z + 8 * y + x);
+                       | (u64)(u32)voxel;
         if (word < best)
         {
             best = word;
@@ -222,6 +235,37 @@ TGB_HD void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object
             t_skip = (truncf(dq) + 1.0f) * (far_plane * (1.00001f / TG_VIS_DEPTH_SCALE));
         }
     }
+}
+
+/*
+ * An UPPER bound of the t_skip tgb_cluster_word would leave for this voxel, from approximate quotients only (no division): lets
+ * the walk go on -- and stop early -- while the exact word is computed later, together with the other lanes' (k_visibility).
+ * The approximate near-plane quotients are within 2e-7 of the exact ones, so inflating the largest by 1e-6 bounds the exact
+ * `enter`; the quantised depth of that bound, plus 2 instead of 1 (one unit for the rounding of this evaluation), times the same
+ * cushioned scale is never below (trunc(dq) + 1) * far * 1.00001 / scale. A bound that is too LARGE only lets more candidates
+ * through (a superset yields the same minimum); `exotic` rays get no bound.
+ */
+TGB_HD f32 tgb_cluster_t_skip_bound(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, i32 voxel, f32 far_plane)
+{
+    if (r.exotic) return TG_F32_MAX;
+    const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
+    const v3 d = r.d;
+    const i32 x = voxel & 7, y = (voxel >> 3) & 7, z = voxel >> 6;
+    const f32 vx = (f32)(d.x > 0.0f ? x : x + 1) - o.x, vy = (f32)(d.y > 0.0f ? y : y + 1) - o.y, vz = (f32)(d.z > 0.0f ? z : z + 1) - o.z;
+    const f32 qx = d.x != 0.0f ? vx * r.rx : TG_F32_MIN, qy = d.y != 0.0f ? vy * r.ry : TG_F32_MIN, qz = d.z != 0.0f ? vz * r.rz : TG_F32_MIN;
+    const f32 q = fmaxf(fmaxf(qx, qy), qz);
+    const f32 q_up = q + (1e-6f * fabsf(q) + 1e-30f);
+    const f32 dq_up = fmaxf(0.0f, q_up / far_plane) * TG_VIS_DEPTH_SCALE;
+    if (!(dq_up < 3.0e7f)) return TG_F32_MAX; /* beyond the far plane (or NaN): no bound */
+    return (floorf(dq_up) + 2.0f) * (far_plane * (1.00001f / TG_VIS_DEPTH_SCALE));
+}
+
+/* both halves in one go */
+TGB_HD void tgb_cluster_march(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 enter, f32 far_plane,
+                              const u32* p_cluster_pointers, const u32* p_masks, u32 global_pointer_base, u64& best, f32& t_skip)
+{
+    const i32 voxel = tgb_cluster_find(f, r, cx, cy, cz, enter, p_cluster_pointers, p_masks);
+    if (voxel >= 0) tgb_cluster_word(f, r, cx, cy, cz, voxel, far_plane, global_pointer_base, best, t_skip);
 }
 
 /* ---- the walk over one object's cluster grid, resumable ------------------------------------------------------------------ */

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(1024) k_sort_frames(const tgb_object_frame* __
  * One ray against one object: enumerate, slice by slice along the dominant axis of d (front to
  * back), every cluster whose box inflated by eps the ray can touch, and visit each.
  */
-template <bool REGROUP>
+template <bool REGROUP, bool DEFER>
 __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 dir_ws, f32 far_plane,
                                                  const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
                                                  u32 global_pointer_base, u64& best, f32& t_skip)
@@ -378,6 +378,15 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
         i32 n_slices = (s_end - s) * sgn + 1;
         s -= sgn;
         i32 cu = 0, cu0 = 0, cu1 = -1, cv = 0, cv1 = -1;
+        /*
+         * DEFER (off by default, see the launcher): the word of a voxel found (a slab test with an IEEE division, the depth quantisation,
+         * the packing: a seventh of the kernel's instructions) normally runs right after each march, with the 6.6 lanes of 32 that have
+         * just found one. Deferred, the walk goes on with an UPPER bound of the t_skip that word would give (tgb_cluster_t_skip_bound; a looser bound only admits
+         * more candidates, the minimum is the same), and the exact word is computed once the object is finished -- by all the lanes
+         * that found a voxel in it, together. A second voxel found meanwhile (a tie, a rounding sliver) first settles the pending one.
+         */
+        const bool can_defer = DEFER && ((f.nx | f.ny | f.nz) < 65536u);
+        u32 pend0 = 0, pend1 = 0; /* cx | cy << 16, cz | voxel << 16 | 1 << 31 */
         for (;;)
         {
             f32 enter = 0.0f;
@@ -414,8 +423,19 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
                 if (tgb_cluster_candidate(f, r, cx, cy, cz, t_skip, &enter)) { have = true; break; }
             }
             if (!have) break;
-            tgb_cluster_march(f, r, cx, cy, cz, enter, far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+            const i32 voxel = tgb_cluster_find(f, r, cx, cy, cz, enter, p_cluster_pointers, p_masks);
+            if (voxel >= 0)
+            {
+                if (!can_defer) tgb_cluster_word(f, r, cx, cy, cz, voxel, far_plane, global_pointer_base, best, t_skip);
+                else
+                {
+                    if (pend1 >> 31) tgb_cluster_word(f, r, pend0 & 0xFFFFu, pend0 >> 16, pend1 & 0xFFFFu, (i32)((pend1 >> 16) & 511u), far_plane, global_pointer_base, best, t_skip);
+                    pend0 = cx | (cy << 16); pend1 = cz | ((u32)voxel << 16) | 0x80000000u;
+                    t_skip = fminf(t_skip, tgb_cluster_t_skip_bound(f, r, cx, cy, cz, voxel, far_plane));
+                }
+            }
         }
+        if (pend1 >> 31) tgb_cluster_word(f, r, pend0 & 0xFFFFu, pend0 >> 16, pend1 & 0xFFFFu, (i32)((pend1 >> 16) & 511u), far_plane, global_pointer_base, best, t_skip);
     }
     else
     for (;; s += sgn)
@@ -470,7 +490,7 @@ struct tgb_k1_shard_args
     u32 tiles_x;
 };
 
-template <int MIN_CTAS, bool REGROUP, bool SHARDED>
+template <int MIN_CTAS, bool REGROUP, bool SHARDED, bool DEFER>
 __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const tgb_object_frame* __restrict__ p_frames, const u32* __restrict__ p_count,
                                                                tg_camera_rays cam, u32 w, u32 h,
                                                                const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
@@ -537,7 +557,7 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
                 if (sorted && __all_sync(TGB_FULL_MASK, behind_best)) { warp_done = true; break; }
                 if (f.x1 < (i32)wx0 || f.x0 > wx1 || f.y1 < (i32)wy0 || f.y0 > wy1) continue; /* warp-uniform */
                 if (behind_best || (i32)px < f.x0 || (i32)px > f.x1 || (i32)py < f.y0 || (i32)py > f.y1) continue;
-                tgb_trace_object<REGROUP>(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+                tgb_trace_object<REGROUP, DEFER>(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
             }
         }
         if (base + TGB_K1_THREADS < n_visible) __syncthreads(); /* s_list is rewritten by the next window */
@@ -576,8 +596,9 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
     if (k1_kernel == 2 && !tgbd_k1_pool_render(d, p_cam)) return TG_FALSE;
     const u32 fallback_only = k1_kernel == 2 ? 1u : 0u; /* after the pool kernel: only frames it declined (an object too large for its packed iterator) */
     const dim3 grid((d->width + TGB_TILE_W - 1) / TGB_TILE_W, (d->height + TGB_TILE_H - 1) / TGB_TILE_H);
-    /* register budget: 4 CTAs per SM = 64 registers with ~30 spilled words, measured 11 % faster than 3 CTAs = 80 registers (TGB_K1_MIN_CTAS=3 selects that build; tuning only) */
-    const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 4), regroup = tgbd_env_int("TGB_K1_REGROUP", 1);
+    /* register budget: 5 CTAs per SM = 48 registers + ~30 spilled words; measured 0.711 ms against 0.737 with 4 CTAs (64 registers), 0.715 with 6 (40), 0.843 with 3
+     * (80): the kernel is issue-bound and more resident warps buy more than the spills cost (TGB_K1_MIN_CTAS selects the other builds; tuning only) */
+    const int min_ctas = tgbd_env_int("TGB_K1_MIN_CTAS", 5), regroup = tgbd_env_int("TGB_K1_REGROUP", 1);
     /* sharded frame on the peer-memory path: K1 flags the tiles in which this rank has a hit */
     const bool sharded = d->p2p_ready && d->n_ranks > 1 && k1_kernel != 2;
     tgb_k1_shard_args sh;
@@ -587,11 +608,19 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
         sh.p_tile_flags = tgbd_mat_tile_flags(d, d->d_mat);
         sh.tiles_x = tgbd_tiles_x(d);
     }
-#define TGB_K1_LAUNCH(C, R, S) k_visibility<C, R, S><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height, \
+#define TGB_K1_LAUNCH(C, R, S, D) k_visibility<C, R, S, D><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height, \
                                                                                        d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis, d->n_ranks, d->tile_rows, fallback_only, sh)
-    if (sharded)      { if (min_ctas >= 4) TGB_K1_LAUNCH(4, true, true); else TGB_K1_LAUNCH(3, true, true); }
-    else if (regroup) { if (min_ctas >= 4) TGB_K1_LAUNCH(4, true, false); else TGB_K1_LAUNCH(3, true, false); }
-    else              { if (min_ctas >= 4) TGB_K1_LAUNCH(4, false, false); else TGB_K1_LAUNCH(3, false, false); }
+    /* TGB_K1_DEFER_WORD=1: the word of a voxel found is computed at the end of the object by all lanes together instead of right after the march.
+     * Bit-identical, measured SLOWER (c2: 0.80 ms against 0.72; c2far 1.12 against 0.98): the bound, the second origin evaluation and the candidates the
+     * looser bound admits cost more than the idle lanes of the immediate form. Off; kept as the measured record. */
+    const int defer = tgbd_env_int("TGB_K1_DEFER_WORD", 0);
+    if (sharded)      { if (defer) TGB_K1_LAUNCH(5, true, true, true); else TGB_K1_LAUNCH(5, true, true, false); }
+    else if (regroup)
+    {
+        if (defer) { if (min_ctas >= 6) TGB_K1_LAUNCH(6, true, false, true); else if (min_ctas == 5) TGB_K1_LAUNCH(5, true, false, true); else TGB_K1_LAUNCH(4, true, false, true); }
+        else       { if (min_ctas >= 6) TGB_K1_LAUNCH(6, true, false, false); else if (min_ctas == 5) TGB_K1_LAUNCH(5, true, false, false); else if (min_ctas == 4) TGB_K1_LAUNCH(4, true, false, false); else TGB_K1_LAUNCH(3, true, false, false); }
+    }
+    else              { if (min_ctas >= 4) TGB_K1_LAUNCH(4, false, false, false); else TGB_K1_LAUNCH(3, false, false, false); }
 #undef TGB_K1_LAUNCH
     TGB_LAUNCH_CHECK(d);
     d->tiles_flagged = sharded ? TG_TRUE : TG_FALSE;
