@@ -269,3 +269,54 @@ def test_config4_dynamic_scene_full_size(gpu):
             print(f"config4 movers[0]={movers[0]}: {resampled}/{len(l2)} leaves re-sampled, incremental {t_inc:.3f} ms vs full {t_full:.3f} ms")
         finally:
             rt.destroy()
+
+
+def test_config4_full_size_incremental_update_against_the_oracle(gpu, oracle):
+    """BASELINE configs[3] at full size, against the ORACLE (the test above only compares the incremental update with the GPU's own full
+    rebuild): the 10^9-voxel scene, the 64 objects nearest to the player moved for three frames, updated incrementally; the three SVO
+    arrays must equal the oracle's from-scratch tg_svo_create of the moved scene, and the frame rendered with that tree (visibility +
+    GI radiance, every 90th scanline) the oracle's frame. The oracle only gets the objects that can touch the +-512 box."""
+    full = scenes.config2()
+    order = np.argsort([o.center[0] ** 2 + o.center[2] ** 2 for o in full.objects], kind="stable")
+    movers = [int(i) for i in order[:64]]
+    rt = from_scene(full)
+    try:
+        rt.set_gi(True, 1)
+        rt.svo_update(force_full=True); rt.synchronize()
+        for frame in (1, 2, 3):
+            cur = _moved(full, frame, movers)
+            for i in movers:
+                rt.set_object_transform(i, cur.objects[i].center, cur.objects[i].angle)
+            rt.clear(); rt.render(); rt.synchronize()   # render() updates the SVO incrementally before shading
+        assert 0 < rt.svo_leaves_resampled()
+        svo, n1, l1, v1 = rt.svo_download(); rt.svo_free(svo)
+        vis, rad = rt.read_visibility(), rt.read_radiance()
+    finally:
+        rt.destroy()
+    in_box = [o for o in cur.objects if max(abs(o.center[0]), abs(o.center[2])) < 512 + 160 + 2]
+    box_scene = scenes.SceneSpec(name="c4_box", width=cur.width, height=cur.height, camera=cur.camera, objects=in_box)
+    osvo = oracle.svo_create(oracle.SceneView.from_scene(box_scene, with_lut=False), capacities=(1 << 25, 1 << 15, 1 << 16))
+    try:
+        wn, wl, wv = oracle.svo_arrays(osvo)
+        # the oracle numbers the clusters of its sub-scene from 0: leaf records hold cluster indices -> compare nodes and voxels bit for bit, and the
+        # leaf records through the object-order-preserving pointer map (every object has 2,048 clusters)
+        assert np.array_equal(n1, wn), "node arrays differ"
+        assert np.array_equal(v1, wv), f"{int((v1 != wv).sum())} voxel words differ"
+        keep = np.asarray([i for i, o in enumerate(cur.objects) if any(o is b for b in in_box)], dtype=np.uint32)
+        gl, ol = l1.view(np.uint32).reshape(-1, 65), wl.view(np.uint32).reshape(-1, 65)
+        assert np.array_equal(gl[:, 0], ol[:, 0]), "per-leaf cluster counts differ"
+        n = np.minimum(ol[:, 0], 64)
+        mask = np.arange(64)[None, :] < n[:, None]
+        mapped = keep[(ol[:, 1:] // 2048) % len(keep)] * 2048 + ol[:, 1:] % 2048
+        assert np.array_equal(gl[:, 1:][mask], mapped[mask]), "leaf cluster lists differ"
+        rows = np.arange(13, cur.height, 90)
+        rays = oracle.camera_rays(oracle.camera_from_spec(cur.camera))
+        view = oracle.SceneView.from_scene(cur, with_lut=True)
+        want_vis, _ = oracle.visibility(view, rays, cur.width, cur.height, oracle.VIS_SCREEN_RECT, 13, cur.height, 90)
+        assert np.array_equal(vis[rows], want_vis[rows]), f"{int((vis[rows] != want_vis[rows]).sum())} visibility words differ"
+        want_rad = np.zeros((cur.height, cur.width, 4), dtype=np.float32)
+        oracle.shade(view, rays, cur.width, cur.height, want_vis, osvo, gi=True, frame_seed=1, y0=13, y1=cur.height, ystep=90, out=want_rad)
+        bad = ~np.isclose(rad[rows], want_rad[rows], rtol=1e-3, atol=1e-6)
+        assert not bad.any(), f"{int(bad.any(axis=-1).sum())} pixels beyond 1e-3"
+    finally:
+        oracle.svo_destroy(osvo)

@@ -62,6 +62,8 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMemsetAsync(d->d_color_lut, 0, (u64)d->n_color_luts * 256 * sizeof(u32), d->stream));
     for (int i = 0; i < 16; i++) TGB_CUDA(cudaEventCreate(&d->ev[i]));
     TGB_CUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    TGB_CUDA(cudaStreamCreateWithFlags(&d->svo_stream, cudaStreamNonBlocking));
+    TGB_CUDA(cudaEventCreateWithFlags(&d->ev_inputs, cudaEventDisableTiming));
     for (int i = 0; i < TGB_MAX_BANDS; i++)
     {
         TGB_CUDA(cudaEventCreateWithFlags(&d->ev_band[i], cudaEventDisableTiming));
@@ -201,6 +203,8 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     for (int i = 0; i < TGB_MAX_BANDS; i++) { if (d->ev_band[i]) cudaEventDestroy(d->ev_band[i]); if (d->ev_band_copied[0][i]) cudaEventDestroy(d->ev_band_copied[0][i]); if (d->ev_band_copied[1][i]) cudaEventDestroy(d->ev_band_copied[1][i]); }
     for (int i = 0; i < TGB_FRAME_RING; i++) if (d->ev_frame_copied[i]) cudaEventDestroy(d->ev_frame_copied[i]);
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    if (d->svo_stream) { cudaStreamSynchronize(d->svo_stream); cudaStreamDestroy(d->svo_stream); }
+    if (d->ev_inputs) cudaEventDestroy(d->ev_inputs);
     cudaStreamDestroy(d->stream);
     cudaGetLastError();
     free(d);
@@ -247,6 +251,7 @@ extern "C" b32 tgbd_upload(struct tgb_device* d, u32 buffer, u64 dst_offset_byte
     TGB_CUDA(cudaMemcpyAsync(p + dst_offset_bytes, p_src, n_bytes, cudaMemcpyHostToDevice, d->stream));
     if (buffer == TGB_BUF_VISIBILITY) d->tiles_flagged = TG_FALSE; /* uploaded words: the sharded shading stage resolves their materials itself */
     if (buffer == TGB_BUF_OBJECTS) d->objects_gathered = TG_FALSE;
+    if (buffer != TGB_BUF_VISIBILITY && buffer != TGB_BUF_RADIANCE) d->inputs_changed_since_clear = TG_TRUE; /* scene data uploaded after tgbd_clear: K2 must not start before it */
     return TG_TRUE;
 }
 

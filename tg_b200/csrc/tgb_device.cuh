@@ -118,6 +118,9 @@ struct tgb_device
 
     /* frame sink (tgb200_set_frame_sink): the shading stage runs in row bands and every finished band is copied to host
      * memory on a second stream while the next band is shaded */
+    cudaStream_t svo_stream;        /* K2 runs here on one GPU, concurrently with K1 (tgb_svo.cu) */
+    cudaEvent_t  ev_inputs;         /* recorded on the main stream by tgbd_clear: the frame's uploads are queued, the previous frame's shading too */
+    b32          ev_inputs_valid, inputs_changed_since_clear;
     cudaStream_t copy_stream;
     f32*         p_sink;            /* caller memory (pinned for a truly asynchronous copy) or NULL */
     u32          sink_bands;        /* bands per frame, 1..TGB_MAX_BANDS */

@@ -570,9 +570,10 @@ void tg_raytracer_render(tg_raytracer* p_raytracer)
 {
     if (!tgb__alive(p_raytracer, "tg_raytracer_render")) return;
     TGB_REQUIRE(p_raytracer->scene.n_objects > 0, TGB_VOID, "render: the scene has no objects (tgvk_raytracer.c:1147)");
-    /* tgvk_raytracer.c:1187-1217 builds the SVO on the first frame; here whenever it is stale and GI needs it */
-    if (p_raytracer->gi_enabled) tgb200_svo_update(p_raytracer, TG_FALSE);
+    /* tgvk_raytracer.c:1187-1217 builds the SVO on the first frame; here whenever it is stale and GI needs it -- queued AFTER K1 so that,
+     * on one GPU, the build (its own stream) runs next to K1 instead of in front of it */
     tgb200_render_visibility(p_raytracer);
+    if (p_raytracer->gi_enabled) tgb200_svo_update(p_raytracer, TG_FALSE);
     /* multi-GPU: the shading stage merges this rank's tile straight from the peers' buffers (tgb_peer.cu) when peer memory can be
      * mapped; otherwise ncclAllReduce(u64, min) over the whole frame first */
     if (tgbd_n_ranks(p_raytracer->p_device) > 1 && !tgbd_p2p_prepare(p_raytracer->p_device)) tgb200_merge_visibility(p_raytracer);

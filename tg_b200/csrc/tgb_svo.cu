@@ -640,11 +640,11 @@ __global__ void k_svo_flatten(const u32* __restrict__ p_nodes, const u32* __rest
     if (!ok) p_grid[TGB_TOP_GRID_CELLS] = 0;
 }
 
-static b32 tgbd__svo_flatten(struct tgb_device* d)
+static b32 tgbd__svo_flatten(struct tgb_device* d, cudaStream_t st)
 {
     tgb_svo_device* s = &d->svo;
-    TGB_CUDA(cudaMemsetAsync(s->d_top_grid + TGB_TOP_GRID_CELLS, 1, sizeof(u32), d->stream)); /* non-zero = complete, cleared by the kernel */
-    k_svo_flatten<<<TGB_TOP_GRID_CELLS / 256, 256, 0, d->stream>>>(s->d_nodes, s->d_leaf_data, s->n_nodes, s->n_leaves, s->d_top_grid);
+    TGB_CUDA(cudaMemsetAsync(s->d_top_grid + TGB_TOP_GRID_CELLS, 1, sizeof(u32), st)); /* non-zero = complete, cleared by the kernel */
+    k_svo_flatten<<<TGB_TOP_GRID_CELLS / 256, 256, 0, st>>>(s->d_nodes, s->d_leaf_data, s->n_nodes, s->n_leaves, s->d_top_grid);
     TGB_LAUNCH_CHECK(d);
     return TG_TRUE;
 }
@@ -732,7 +732,23 @@ static b32 tgbd__svo_run(struct tgb_device* d, v3 extent_min, v3 extent_max, u32
     s->valid = TG_FALSE;
     s->bmin = extent_min; s->bmax = extent_max;
 
-    TGB_CUDA(cudaEventRecord(d->ev[5], d->stream));
+    /*
+     * K3 is the only consumer of the tree, K1 neither reads nor writes it: on one GPU the build runs on its OWN stream, next to the K1
+     * the caller has already queued on the main stream (tg_raytracer_render and bench.py call K1 first). It starts when the frame's
+     * inputs are complete -- the event tgbd_clear records after the application's uploads; an upload after the clear falls back to "now"
+     * -- which also orders it behind the previous frame's shading (the reader of the arrays it rewrites), and the main stream waits
+     * for its end. The one-CTA layout pass, the host round trip and the short passes then hide behind K1. (Sharded builds keep the main
+     * stream: their collectives are ordered with the frame's.)
+     */
+    cudaStream_t st = d->stream;
+    if (!sharded && d->svo_stream && tgbd_env_int("TGB_SVO_STREAM", 1))
+    {
+        st = d->svo_stream;
+        if (d->inputs_changed_since_clear || !d->ev_inputs_valid) { TGB_CUDA(cudaEventRecord(d->ev_inputs, d->stream)); d->ev_inputs_valid = TG_TRUE; d->inputs_changed_since_clear = TG_FALSE; }
+        TGB_CUDA(cudaStreamWaitEvent(st, d->ev_inputs, 0));
+    }
+
+    TGB_CUDA(cudaEventRecord(d->ev[5], st));
     if (incremental)
     {
         /* previous pair lists -> half "b" (pointer swap), spare leaf arrays on demand */
@@ -745,44 +761,44 @@ static b32 tgbd__svo_run(struct tgb_device* d, v3 extent_min, v3 extent_max, u32
             TGB_CUDA(cudaMalloc(&s->d_voxels_alt, (u64)s->voxel_word_capacity * sizeof(u32)));
             TGB_CUDA(cudaMalloc(&s->d_leaf_data_alt, (u64)s->leaf_capacity * 65 * sizeof(u32)));
         }
-        TGB_CUDA(cudaMemsetAsync(s->d_object_moved, 0, (u64)object_capacity * sizeof(u32), d->stream));
+        TGB_CUDA(cudaMemsetAsync(s->d_object_moved, 0, (u64)object_capacity * sizeof(u32), st));
         if (n_moved > object_capacity) n_moved = object_capacity;
         if (n_moved)
         {
-            TGB_CUDA(cudaMemcpyAsync(s->d_moved_indices, p_moved_indices, (u64)n_moved * sizeof(u32), cudaMemcpyHostToDevice, d->stream));
-            k_svo_set_moved<<<(n_moved + 127) / 128, 128, 0, d->stream>>>(s->d_moved_indices, n_moved, object_capacity, s->d_object_moved);
+            TGB_CUDA(cudaMemcpyAsync(s->d_moved_indices, p_moved_indices, (u64)n_moved * sizeof(u32), cudaMemcpyHostToDevice, st));
+            k_svo_set_moved<<<(n_moved + 127) / 128, 128, 0, st>>>(s->d_moved_indices, n_moved, object_capacity, s->d_object_moved);
             TGB_LAUNCH_CHECK(d);
         }
     }
-    TGB_CUDA(cudaMemsetAsync(s->d_scratch, 0, (u64)TGB_SCR_CLEARED * sizeof(u32), d->stream));
-    if (!incremental) TGB_CUDA(cudaMemsetAsync(s->d_scratch + TGB_SCR_PREV_DP, 0, (u64)TGB_SVO_MAX_LEAVES * sizeof(u32), d->stream));
-    TGB_CUDA(cudaMemsetAsync(s->d_counts, 0, 16 * sizeof(u32), d->stream));
-    TGB_CUDA(cudaMemsetAsync(s->d_nodes, 0, (u64)s->node_capacity * sizeof(u32), d->stream));
+    TGB_CUDA(cudaMemsetAsync(s->d_scratch, 0, (u64)TGB_SCR_CLEARED * sizeof(u32), st));
+    if (!incremental) TGB_CUDA(cudaMemsetAsync(s->d_scratch + TGB_SCR_PREV_DP, 0, (u64)TGB_SVO_MAX_LEAVES * sizeof(u32), st));
+    TGB_CUDA(cudaMemsetAsync(s->d_counts, 0, 16 * sizeof(u32), st));
+    TGB_CUDA(cudaMemsetAsync(s->d_nodes, 0, (u64)s->node_capacity * sizeof(u32), st));
 
-    k_svo_object_flags<<<(object_capacity + 127) / 128, 128, 0, d->stream>>>(d->d_objects, object_capacity, extent_min, extent_max, s->d_object_flags);
+    k_svo_object_flags<<<(object_capacity + 127) / 128, 128, 0, st>>>(d->d_objects, object_capacity, extent_min, extent_max, s->d_object_flags);
     TGB_LAUNCH_CHECK(d);
     const u32 grid = (n_cluster_pointers + 127) / 128;
     if (grid)
     {
-        k_svo_descend<false><<<grid, 128, 0, d->stream>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, s->d_object_flags, d->d_masks, n_cluster_pointers,
+        k_svo_descend<false><<<grid, 128, 0, st>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, s->d_object_flags, d->d_masks, n_cluster_pointers,
                                                          extent_min, extent_max, s->d_scratch, NULL, NULL, incremental ? s->d_object_moved : NULL);
         TGB_LAUNCH_CHECK(d);
     }
     if (incremental && n_pairs_prev)
     {
-        k_svo_mark_dirty_prev<<<(n_pairs_prev + 255) / 256, 256, 0, d->stream>>>(s->d_pairs_b, s->d_pair_leaf_b, n_pairs_prev, d->d_cluster_pointers, d->d_c2o,
+        k_svo_mark_dirty_prev<<<(n_pairs_prev + 255) / 256, 256, 0, st>>>(s->d_pairs_b, s->d_pair_leaf_b, n_pairs_prev, d->d_cluster_pointers, d->d_c2o,
                                                                                 s->d_object_moved, s->d_scratch);
         TGB_LAUNCH_CHECK(d);
     }
-    TGB_CUDA(cudaMemcpyAsync(s->d_scratch + TGB_SCR_CNT_G, s->d_scratch + TGB_SCR_CNT, (u64)TGB_SVO_DENSE_TOTAL * sizeof(u32), cudaMemcpyDeviceToDevice, d->stream));
-    if (sharded && !tgbn_allreduce_sum_u32(d->p_comm, s->d_scratch + TGB_SCR_CNT_G, TGB_SVO_DENSE_TOTAL, d->stream)) return TG_FALSE;
-    k_svo_layout<<<1, 1024, 0, d->stream>>>(s->d_scratch, s->d_nodes, s->d_counts, s->node_capacity, s->leaf_capacity);
+    TGB_CUDA(cudaMemcpyAsync(s->d_scratch + TGB_SCR_CNT_G, s->d_scratch + TGB_SCR_CNT, (u64)TGB_SVO_DENSE_TOTAL * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    if (sharded && !tgbn_allreduce_sum_u32(d->p_comm, s->d_scratch + TGB_SCR_CNT_G, TGB_SVO_DENSE_TOTAL, st)) return TG_FALSE;
+    k_svo_layout<<<1, 1024, 0, st>>>(s->d_scratch, s->d_nodes, s->d_counts, s->node_capacity, s->leaf_capacity);
     TGB_LAUNCH_CHECK(d);
 
     /* the one host round trip of a build: node / leaf / pair counts size the remaining launches */
     u32 counts[4] = { 0, 0, 0, 0 };
-    TGB_CUDA(cudaMemcpyAsync(counts, s->d_counts, sizeof(counts), cudaMemcpyDeviceToHost, d->stream));
-    TGB_CUDA(cudaStreamSynchronize(d->stream));
+    TGB_CUDA(cudaMemcpyAsync(counts, s->d_counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
+    TGB_CUDA(cudaStreamSynchronize(st));
     if (counts[3])
     {
         tgb_set_error("svo build: capacity exceeded (flags %u: 1 = child pointer >= 0xFFFF, 2 = nodes %u > %u, 4 = leaves %u > %u; tg_sparse_voxel_octree.c:116,408,413)",
@@ -797,7 +813,7 @@ static b32 tgbd__svo_run(struct tgb_device* d, v3 extent_min, v3 extent_max, u32
 
     if (counts[2] && grid)
     {
-        k_svo_descend<true><<<grid, 128, 0, d->stream>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, s->d_object_flags, d->d_masks, n_cluster_pointers,
+        k_svo_descend<true><<<grid, 128, 0, st>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, s->d_object_flags, d->d_masks, n_cluster_pointers,
                                                         extent_min, extent_max, s->d_scratch, s->d_pairs_a, s->d_pair_leaf_a, NULL);
         TGB_LAUNCH_CHECK(d);
     }
@@ -808,18 +824,18 @@ static b32 tgbd__svo_run(struct tgb_device* d, v3 extent_min, v3 extent_max, u32
         u32* p_leaf = sharded ? s->d_part + (u64)s->n_leaves * TG_SVO_BLOCK_WORDS : (incremental ? s->d_leaf_data_alt : s->d_leaf_data);
         if (incremental)
         {
-            k_svo_copy_clean<<<s->n_leaves, 256, 0, d->stream>>>(s->d_scratch, s->d_leaf_data, s->d_voxels, p_leaf, p_voxels, s->d_counts);
+            k_svo_copy_clean<<<s->n_leaves, 256, 0, st>>>(s->d_scratch, s->d_leaf_data, s->d_voxels, p_leaf, p_voxels, s->d_counts);
             TGB_LAUNCH_CHECK(d);
         }
-        k_svo_fill_leaves<<<s->n_leaves, TGB_LEAF_THREADS, 0, d->stream>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_masks, extent_min, extent_max,
+        k_svo_fill_leaves<<<s->n_leaves, TGB_LEAF_THREADS, 0, st>>>(d->d_cluster_pointers, d->d_c2o, d->d_objects, d->d_masks, extent_min, extent_max,
                                                                            s->d_scratch, s->d_pairs_a, s->d_pair_flags, p_leaf, p_voxels, incremental ? 1u : 0u,
                                                                            sharded ? d->global_pointer_base : 0u);
         TGB_LAUNCH_CHECK(d);
         if (sharded)
         {
             const u64 part_bytes = (u64)s->n_leaves * (TG_SVO_BLOCK_WORDS + 65u) * sizeof(u32);
-            if (!tgbn_allgather_bytes(d->p_comm, s->d_part, s->d_gather, part_bytes, d->stream)) return TG_FALSE;
-            k_svo_combine<<<s->n_leaves, 256, 0, d->stream>>>(s->d_gather, d->n_ranks, s->n_leaves, s->d_leaf_data, s->d_voxels);
+            if (!tgbn_allgather_bytes(d->p_comm, s->d_part, s->d_gather, part_bytes, st)) return TG_FALSE;
+            k_svo_combine<<<s->n_leaves, 256, 0, st>>>(s->d_gather, d->n_ranks, s->n_leaves, s->d_leaf_data, s->d_voxels);
             TGB_LAUNCH_CHECK(d);
         }
         if (incremental)
@@ -830,15 +846,16 @@ static b32 tgbd__svo_run(struct tgb_device* d, v3 extent_min, v3 extent_max, u32
         }
     }
     /* where every dense leaf lives now (for the next incremental update) */
-    TGB_CUDA(cudaMemsetAsync(s->d_scratch + TGB_SCR_PREV_DP, 0, (u64)TGB_SVO_MAX_LEAVES * sizeof(u32), d->stream));
+    TGB_CUDA(cudaMemsetAsync(s->d_scratch + TGB_SCR_PREV_DP, 0, (u64)TGB_SVO_MAX_LEAVES * sizeof(u32), st));
     if (s->n_leaves)
     {
-        k_svo_save_prev<<<(s->n_leaves + 255) / 256, 256, 0, d->stream>>>(s->d_scratch, s->n_leaves);
+        k_svo_save_prev<<<(s->n_leaves + 255) / 256, 256, 0, st>>>(s->d_scratch, s->n_leaves);
         TGB_LAUNCH_CHECK(d);
     }
-    if (incremental) TGB_CUDA(cudaMemcpyAsync(&s->n_leaves_resampled, s->d_counts + 4, sizeof(u32), cudaMemcpyDeviceToHost, d->stream));
-    if (!tgbd__svo_flatten(d)) return TG_FALSE;
-    TGB_CUDA(cudaEventRecord(d->ev[6], d->stream));
+    if (incremental) TGB_CUDA(cudaMemcpyAsync(&s->n_leaves_resampled, s->d_counts + 4, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    if (!tgbd__svo_flatten(d, st)) return TG_FALSE;
+    TGB_CUDA(cudaEventRecord(d->ev[6], st));
+    if (st != d->stream) TGB_CUDA(cudaStreamWaitEvent(d->stream, d->ev[6], 0)); /* whatever follows on the main stream (K3, downloads) sees the finished tree */
     d->ev_svo = TG_TRUE;
     s->n_pairs = counts[2];
     s->valid = TG_TRUE;
@@ -893,7 +910,7 @@ extern "C" b32 tgbd_svo_set(struct tgb_device* d, v3 bmin, v3 bmax, u32 n_nodes,
     s->bmin = bmin; s->bmax = bmax;
     s->n_nodes = n_nodes; s->n_leaves = n_leaves;
     if (!n_nodes) TGB_CUDA(cudaMemsetAsync(s->d_nodes, 0, 4, d->stream)); /* an empty upload is an empty root */
-    if (!tgbd__svo_flatten(d)) return TG_FALSE;
+    if (!tgbd__svo_flatten(d, d->stream)) return TG_FALSE;
     s->valid = TG_TRUE;
     s->incremental_ok = TG_FALSE; /* uploaded arrays: there are no pair lists to update from */
     return TG_TRUE;

@@ -49,6 +49,9 @@ extern "C" b32 tgbd_clear(struct tgb_device* d)
         d->frame_seq++; /* what this rank publishes when its K1 is done, and what it waits for on its peers (tgb_peer.cu) */
     }
     d->tiles_flagged = TG_FALSE; d->objects_gathered = TG_FALSE;
+    /* the frame's inputs are queued (uploads precede the clear in every caller of this library): K2 may start behind this point on its own stream */
+    TGB_CUDA(cudaEventRecord(d->ev_inputs, d->stream));
+    d->ev_inputs_valid = TG_TRUE; d->inputs_changed_since_clear = TG_FALSE;
     d->vis_merged = TG_FALSE; d->tile_merged = TG_FALSE;
     const u64 n = (u64)d->width * d->tile_rows * d->n_ranks; /* the padded frame */
     TGB_CUDA(cudaEventRecord(d->ev[0], d->stream));
