@@ -39,6 +39,9 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMalloc(&d->d_cluster_pointers, nc * sizeof(u32)));
     TGB_CUDA(cudaMalloc(&d->d_c2o, nc * sizeof(u32)));
     TGB_CUDA(cudaMalloc(&d->d_objects, no * sizeof(tg_object_data)));
+    d->h_objects = (u8*)calloc(no ? no : 1, sizeof(tg_object_data)); /* host shadow of the records (tgbd_flush_objects) */
+    if (!d->h_objects) { tgb_set_error("out of host memory for %llu object records", (unsigned long long)no); return TG_FALSE; }
+    d->objects_dirty_lo = ~0ull; d->objects_dirty_hi = 0;
     TGB_CUDA(cudaMalloc(&d->d_masks, nc * 64));
     TGB_CUDA(cudaMalloc(&d->d_lut_idx, nc * 512));
     TGB_CUDA(cudaMalloc(&d->d_color_lut, (u64)d->n_color_luts * 256 * sizeof(u32)));
@@ -195,6 +198,7 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
     if (d->h_gi_stats) cudaFreeHost(d->h_gi_stats);
+    free(d->h_objects);
     cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts); cudaFree(d->svo.d_top_grid);
     cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch); cudaFree(d->svo.d_pair_flags); cudaFree(d->svo.d_object_flags); cudaFree(d->svo.d_pair_leaf_a); cudaFree(d->svo.d_pair_leaf_b);
     cudaFree(d->svo.d_voxels_alt); cudaFree(d->svo.d_leaf_data_alt); cudaFree(d->svo.d_object_moved); cudaFree(d->svo.d_moved_indices); cudaFree(d->svo.d_part); cudaFree(d->svo.d_gather);
@@ -235,17 +239,38 @@ static b32 tgbd__buffer_range(struct tgb_device* d, u32 buffer, u8** pp, u64* p_
 extern "C" void* tgbd_buffer(struct tgb_device* d, u32 buffer)
 {
     u8* p = NULL; u64 size = 0;
+    tgbd_flush_objects(d);
     if (!tgbd__buffer_range(d, buffer, &p, &size)) return NULL;
     return p;
 }
 
 extern "C" void* tgbd_stream(struct tgb_device* d) { return (void*)d->stream; }
 
+extern "C" b32 tgbd_flush_objects(struct tgb_device* d)
+{
+    if (d->objects_dirty_lo >= d->objects_dirty_hi) return TG_TRUE;
+    const u64 lo = d->objects_dirty_lo, n = d->objects_dirty_hi - lo;
+    d->objects_dirty_lo = ~0ull; d->objects_dirty_hi = 0;
+    TGB_CUDA(cudaSetDevice(d->device));
+    /* pageable source: staged before the call returns, so the shadow may be rewritten for the next frame while this frame is still in flight */
+    TGB_CUDA(cudaMemcpyAsync((u8*)d->d_objects + lo, d->h_objects + lo, n, cudaMemcpyHostToDevice, d->stream));
+    return TG_TRUE;
+}
+
 extern "C" b32 tgbd_upload(struct tgb_device* d, u32 buffer, u64 dst_offset_bytes, const void* p_src, u64 n_bytes)
 {
     u8* p; u64 size;
     if (!tgbd__buffer_range(d, buffer, &p, &size)) return TG_FALSE;
     if (dst_offset_bytes + n_bytes > size) { tgb_set_error("upload past the end of device buffer %u (%llu + %llu > %llu)", buffer, (unsigned long long)dst_offset_bytes, (unsigned long long)n_bytes, (unsigned long long)size); return TG_FALSE; }
+    if (buffer == TGB_BUF_OBJECTS && d->h_objects)
+    {
+        memcpy(d->h_objects + dst_offset_bytes, p_src, n_bytes);
+        if (dst_offset_bytes < d->objects_dirty_lo) d->objects_dirty_lo = dst_offset_bytes;
+        if (dst_offset_bytes + n_bytes > d->objects_dirty_hi) d->objects_dirty_hi = dst_offset_bytes + n_bytes;
+        d->objects_gathered = TG_FALSE;
+        d->inputs_changed_since_clear = TG_TRUE;
+        return TG_TRUE;
+    }
     TGB_CUDA(cudaSetDevice(d->device));
     /* pageable source: the copy is staged before the call returns, so the caller may reuse p_src */
     TGB_CUDA(cudaMemcpyAsync(p + dst_offset_bytes, p_src, n_bytes, cudaMemcpyHostToDevice, d->stream));
@@ -260,6 +285,7 @@ extern "C" b32 tgbd_download(struct tgb_device* d, u32 buffer, u64 src_offset_by
     u8* p; u64 size;
     if (!tgbd__buffer_range(d, buffer, &p, &size)) return TG_FALSE;
     if (src_offset_bytes + n_bytes > size) { tgb_set_error("download past the end of device buffer %u", buffer); return TG_FALSE; }
+    if (!tgbd_flush_objects(d)) return TG_FALSE;
     TGB_CUDA(cudaSetDevice(d->device));
     TGB_CUDA(cudaMemcpyAsync(p_dst, p + src_offset_bytes, n_bytes, cudaMemcpyDeviceToHost, d->stream));
     TGB_CUDA(cudaStreamSynchronize(d->stream));
@@ -286,6 +312,7 @@ extern "C" b32 tgbd_move(struct tgb_device* d, u32 buffer, u64 dst_offset_bytes,
 extern "C" void tgbd_synchronize(struct tgb_device* d)
 {
     cudaSetDevice(d->device);
+    tgbd_flush_objects(d);
     cudaError_t e = cudaStreamSynchronize(d->stream);
     if (e == cudaSuccess && d->copy_stream) e = cudaStreamSynchronize(d->copy_stream);
     if (e != cudaSuccess) tgb_set_error("cudaStreamSynchronize -> %s", cudaGetErrorString(e));
@@ -348,6 +375,7 @@ extern "C" void tgbd_reset_launch_counter(struct tgb_device* d) { d->n_kernel_la
 extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
 {
     cudaSetDevice(d->device);
+    tgbd_flush_objects(d);
     cudaStreamSynchronize(d->stream);
     tgbd_p2p_check(d);
     if (d->ev_clear) cudaEventElapsedTime(&d->clear_ms, d->ev[0], d->ev[1]);

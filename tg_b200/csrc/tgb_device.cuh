@@ -118,6 +118,10 @@ struct tgb_device
 
     /* frame sink (tgb200_set_frame_sink): the shading stage runs in row bands and every finished band is copied to host
      * memory on a second stream while the next band is shaded */
+    /* object records are uploaded lazily: tgbd_upload(TGB_BUF_OBJECTS) lands in this host shadow, and the dirty byte range goes to the device in ONE
+     * copy the next time anything on the device can read it (tgbd_flush_objects) -- 64 moved objects are one 6 KB copy instead of 64 96-byte ones */
+    u8*          h_objects;         /* [object_capacity * sizeof(tg_object_data)] */
+    u64          objects_dirty_lo, objects_dirty_hi; /* byte range, empty when lo >= hi */
     cudaStream_t svo_stream;        /* K2 runs here on one GPU, concurrently with K1 (tgb_svo.cu) */
     cudaEvent_t  ev_inputs;         /* recorded on the main stream by tgbd_clear: the frame's uploads are queued, the previous frame's shading too */
     b32          ev_inputs_valid, inputs_changed_since_clear;

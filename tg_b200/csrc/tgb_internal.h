@@ -44,6 +44,7 @@ b32   tgbd_download(struct tgb_device* d, u32 buffer, u64 src_offset_bytes, void
 /* device-to-device move inside one buffer (pointer-table compaction, tgvk_raytracer.c:1049-1056) */
 b32   tgbd_move(struct tgb_device* d, u32 buffer, u64 dst_offset_bytes, u64 src_offset_bytes, u64 n_bytes);
 void  tgbd_synchronize(struct tgb_device* d);
+b32   tgbd_flush_objects(struct tgb_device* d); /* pending object-record uploads -> the device (one copy); every device entry point that reads them calls it */
 void* tgbd_buffer(struct tgb_device* d, u32 buffer);
 void* tgbd_stream(struct tgb_device* d);
 void  tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out);

@@ -337,6 +337,7 @@ static u32* tgbd__wait_error(struct tgb_device* d) { return (u32*)(d->d_ipc_stag
 extern "C" b32 tgbd_gather_objects(struct tgb_device* d)
 {
     if (!d->p_comm || d->n_ranks < 2) return TG_TRUE;
+    if (!tgbd_flush_objects(d)) return TG_FALSE;
     const u32 cap = d->object_capacity;
     k_globalize_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->d_objects_global + (u64)d->rank * cap);
     TGB_LAUNCH_CHECK(d);
@@ -354,6 +355,7 @@ extern "C" b32 tgbd_gather_objects(struct tgb_device* d)
 extern "C" b32 tgbd_p2p_barrier(struct tgb_device* d)
 {
     if (!d->p2p_ready) { tgb_set_error("p2p_barrier: peer memory is not mapped"); return TG_FALSE; }
+    if (!tgbd_flush_objects(d)) return TG_FALSE;
     const u32 cap = d->object_capacity;
     k_publish_objects<<<(cap + 127) / 128, 128, 0, d->stream>>>(d->d_objects, cap, d->global_pointer_base, d->tiles_flagged ? d->d_frames_sorted : NULL, d->d_visible_count,
                                                               tgbd_mat_objects(d, d->d_mat), tgbd_mat_object_indices(d, d->d_mat), tgbd_mat_signal(d, d->d_mat) + 1);

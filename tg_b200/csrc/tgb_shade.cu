@@ -1040,6 +1040,7 @@ extern "C" b32 tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p
                                    u32 y0, u32 y1)
 {
     TGB_CUDA(cudaSetDevice(d->device));
+    if (!tgbd_flush_objects(d)) return TG_FALSE;
     if (gi_enabled && debug_visualization == TG_DEBUG_SHOW_NONE && !d->svo.valid)
     {
         tgb_set_error("render_shading: GI is enabled but no SVO has been built or uploaded");
@@ -1060,6 +1061,7 @@ extern "C" b32 tgbd_render_shading(struct tgb_device* d, const tg_camera_rays* p
 extern "C" b32 tgbd_render_shading_sharded(struct tgb_device* d, const tg_camera_rays* p_cam, u32 n_local_pointers, u32 gi_enabled, u32 frame_seed, u32 debug_visualization)
 {
     TGB_CUDA(cudaSetDevice(d->device));
+    if (!tgbd_flush_objects(d)) return TG_FALSE;
     if (!d->p_comm || d->n_ranks < 2) { tgb_set_error("render_shading_sharded: no communicator"); return TG_FALSE; }
     if (gi_enabled && debug_visualization == TG_DEBUG_SHOW_NONE && !d->svo.valid)
     {

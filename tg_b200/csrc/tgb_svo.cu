@@ -722,6 +722,7 @@ static b32 tgbd__svo_ensure_gather(struct tgb_device* d, u32 n_leaves)
 static b32 tgbd__svo_run(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity, bool incremental, u32 n_moved, const u32* p_moved_indices)
 {
     TGB_CUDA(cudaSetDevice(d->device));
+    if (!tgbd_flush_objects(d)) return TG_FALSE; /* on the main stream, in front of the event the build waits for */
     if (!tgbd__svo_ensure(d)) return TG_FALSE;
     tgb_svo_device* s = &d->svo;
     const bool sharded = d->p_comm != NULL && d->n_ranks > 1;

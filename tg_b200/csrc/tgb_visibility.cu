@@ -40,6 +40,7 @@ __global__ void k_clear_visibility(ulonglong2* __restrict__ p_vis2, u64 n_pairs,
 extern "C" b32 tgbd_clear(struct tgb_device* d)
 {
     TGB_CUDA(cudaSetDevice(d->device));
+    if (!tgbd_flush_objects(d)) return TG_FALSE; /* the frame's transform uploads: one copy, in front of the "inputs complete" event below */
     if (d->p2p_ready)
     {
         /* merge over peer memory (tgb_peer.cu): the peers may still read last frame's words, this frame goes to the other pair */
@@ -580,6 +581,7 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
 extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays* p_cam, u32 object_capacity)
 {
     TGB_CUDA(cudaSetDevice(d->device));
+    if (!tgbd_flush_objects(d)) return TG_FALSE;
     tgb_pinhole pin;
     tgb_pinhole_init(p_cam, &pin);
 
