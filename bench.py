@@ -294,7 +294,7 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
-def parity_check(ctx, rt, frame, workload):
+def parity_check(ctx, rt, frame, workload, merge):
     """N > 1, inside the warm-up: (1) the frame merged by the one-kernel peer-memory exchange equals, word for word and radiance bit
     for radiance bit, the frame merged by the NCCL collectives; (2) the sharded frame equals the frame ONE GPU renders from the
     union of the shards (every rank renders that union on its own GPU and compares the whole visibility buffer and the whole
@@ -312,8 +312,10 @@ def parity_check(ctx, rt, frame, workload):
         ctx.barrier()
         return vis, rad
 
+    rt.set_merge_kind(0)          # the peer-memory exchange may run (mapped on first use, collectively) whatever --merge says for the timed frames
     vis_p, rad_p = sharded("peer")
     vis_n, rad_n = sharded("nccl")
+    rt.set_merge_kind(0 if merge == "peer" else 1)
     out = {"merged_eq_nccl": bool(np.array_equal(vis_p, vis_n) and np.array_equal(rad_p, rad_n)), "peer_memory_path_ran": bool(rt.timings()["merge_ms"] > 0)}
     union, pointers_match = union_scene(ctx.world, workload)
     ref = from_scene(union, device=ctx.local_rank)
@@ -406,7 +408,7 @@ def gpu_arm(ctx, args, workload, steps, warmup, headline):
         flush_l2()
         frame()
     rt.synchronize()
-    parity = parity_check(ctx, rt, frame, workload) if world > 1 else None
+    parity = parity_check(ctx, rt, frame, workload, args.merge) if world > 1 else None
     if parity is not None:   # the check changed the exchange kind twice: one more warm frame on the timed path
         flush_l2()
         frame()
