@@ -55,10 +55,18 @@ void tgbsim_flatten(const u32* p_nodes, const u32* p_leaf_data, u32 n_nodes, u32
  * iteration cap (must be 0 on valid input).
  */
 u32 tgbsim_gi_trace(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, u32 n, const f32* p_origins, const f32* p_dirs,
-                    u32 tree_reps, u32 dda_steps, u8* p_occluded, u64* p_work /* [3]: look-ups, DDA steps, advances */)
+                    u32 tree_reps, u32 dda_steps, u32 grid16, u8* p_occluded, u64* p_work /* [3]: look-ups, DDA steps, advances */)
 {
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane, p_grid, p_voxels);
+    /* grid16: the kernel's 16-bit form of the table (tgb_top16_pack), read back through tgb_top16_unpack */
+    unsigned short* p_grid16 = NULL;
+    if (grid16)
+    {
+        p_grid16 = (unsigned short*)malloc(TGB_TOP_GRID_CELLS * sizeof(unsigned short));
+        for (u32 c = 0; c < TGB_TOP_GRID_CELLS; c++) p_grid16[c] = (unsigned short)tgb_top16_pack(p_grid[c]);
+        fr.p_grid16 = p_grid16;
+    }
     u32 n_capped = 0;
     for (u32 i = 0; i < n; i++)
     {
@@ -74,7 +82,8 @@ u32 tgbsim_gi_trace(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u
         bool occluded = false;
         for (;;)
         {
-            if (kind == TGB_RAY_TREE) kind = tgb_gi_tree_phase(&fr, d, t_delta, &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
+            if (kind == TGB_RAY_TREE) kind = grid16 ? tgb_gi_tree_phase_t<2>(&fr, d, t_delta, &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances)
+                                                    : tgb_gi_tree_phase(&fr, d, t_delta, &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
             else if (kind == TGB_RAY_DDA)
             {
                 if (flags & TGB_RF_SETUP)
@@ -104,6 +113,7 @@ u32 tgbsim_gi_trace(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u
         p_occluded[i] = occluded ? 1 : 0;
         if (p_work) { p_work[0] += n_visits; p_work[1] += n_steps; p_work[2] += n_advances; }
     }
+    free(p_grid16);
     return n_capped;
 }
 

@@ -88,8 +88,9 @@ static b32 tgbd__alloc(struct tgb_device* d)
     TGB_CUDA(cudaMalloc(&d->svo.d_leaf_data, (u64)d->svo.leaf_capacity * 65 * 4));
     TGB_CUDA(cudaMalloc(&d->svo.d_voxels, (u64)d->svo.voxel_word_capacity * 4));
     TGB_CUDA(cudaMalloc(&d->svo.d_counts, 16 * sizeof(u32)));
-    TGB_CUDA(cudaMalloc(&d->svo.d_top_grid, (TGB_TOP_GRID_CELLS + 1) * sizeof(u32)));
-    TGB_CUDA(cudaMemsetAsync(d->svo.d_top_grid, 0, (TGB_TOP_GRID_CELLS + 1) * sizeof(u32), d->stream));
+    /* [32^3 + 1] u32 cells + completeness word, then the same cells in 16 bits */
+    TGB_CUDA(cudaMalloc(&d->svo.d_top_grid, (TGB_TOP_GRID_CELLS + 1) * sizeof(u32) + TGB_TOP_GRID_CELLS * sizeof(unsigned short)));
+    TGB_CUDA(cudaMemsetAsync(d->svo.d_top_grid, 0, (TGB_TOP_GRID_CELLS + 1) * sizeof(u32) + TGB_TOP_GRID_CELLS * sizeof(unsigned short), d->stream));
     TGB_CUDA(cudaMalloc(&d->svo.d_object_moved, no * sizeof(u32)));
     return TG_TRUE;
 }

@@ -32,6 +32,11 @@
 #define TGB_TOP_LEVEL_SHIFT   28u         /* bits 28..30: depth of the inner node whose child is terminal (child side = 512 >> level) */
 #define TGB_TOP_POINTER_MASK  0x0FFFFFFFu
 
+/* 16-bit form of a cell: leaf with data -> 0x8000 | data pointer (< 32768 leaves, level 4), otherwise the level */
+#define TGB_TOP16_HAS_DATA    0x8000u
+TGB_HD u32 tgb_top16_pack(u32 entry) { return (entry & TGB_TOP_HAS_DATA) ? (TGB_TOP16_HAS_DATA | (entry & 0x7FFFu)) : ((entry >> TGB_TOP_LEVEL_SHIFT) & 7u); }
+TGB_HD u32 tgb_top16_unpack(u32 e16) { return (e16 & TGB_TOP16_HAS_DATA) ? (TGB_TOP_HAS_DATA | (4u << TGB_TOP_LEVEL_SHIFT) | (e16 & 0x7FFFu)) : (e16 << TGB_TOP_LEVEL_SHIFT); }
+
 #define TGB_TRAVERSE_MAX_ITERS 4096u /* Q9: cap that valid input never reaches */
 
 /*
@@ -145,11 +150,13 @@ struct tgb_gi_frame
     i32 min_cell_x, min_cell_y, min_cell_z;
     f32 far_plane;
     const u32* p_grid;   /* [32^3 + 1] flattened tree */
+    const unsigned short* p_grid16; /* [32^3] the same in 16 bits per cell (tgb_top16_*): half the cache footprint; global or shared memory */
     const u32* p_voxels; /* 1024 u32 per leaf */
 };
 
 TGB_HD void tgb_gi_frame_init(tgb_gi_frame* f, v3 bmin, v3 bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels)
 {
+    f->p_grid16 = 0;
     f->bmin = bmin; f->bmax = bmax;
     const v3 extent = tgb_sub(bmax, bmin);
     f->center = tgb_add(tgb_scale(extent, 0.5f), bmin);
@@ -207,8 +214,10 @@ TGB_HD void tgb_gi_ray_start(const tgb_gi_frame* f, v3 origin, v3 dir, f32 root_
  * TREE (budget used up), DDA (arrived in a leaf with data: *p_data set, SETUP flagged) or MISS (left the root, or within
  * one unit of a root face: BORDER flagged, the exact pop test is made by tgb_gi_border_test).
  */
-TGB_HD u32 tgb_gi_tree_phase(const tgb_gi_frame* f, v3 d, v3 t_delta, v3* p_position, u32* p_cell, u32* p_flags, u32* p_data, u32 reps,
-                             u32* p_n_visits, u32* p_n_advances)
+/* GRID: 0 = the 32-bit table, 1 = the 16-bit table through the read-only path, 2 = the 16-bit table with plain loads (staged in shared memory) */
+template <int GRID>
+TGB_HD u32 tgb_gi_tree_phase_t(const tgb_gi_frame* f, v3 d, v3 t_delta, v3* p_position, u32* p_cell, u32* p_flags, u32* p_data, u32 reps,
+                               u32* p_n_visits, u32* p_n_advances)
 {
     v3 position = *p_position;
     u32 flags = *p_flags, kind = TGB_RAY_TREE;
@@ -239,7 +248,8 @@ TGB_HD u32 tgb_gi_tree_phase(const tgb_gi_frame* f, v3 d, v3 t_delta, v3* p_posi
                 cx = tgb_cell_axis(position.x, d.x, f->min_cell_x);
                 cy = tgb_cell_axis(position.y, d.y, f->min_cell_y);
                 cz = tgb_cell_axis(position.z, d.z, f->min_cell_z);
-                const u32 entry = TGB_LDG(&f->p_grid[(cz << 10) | (cy << 5) | cx]);
+                const u32 cell_idx = (cz << 10) | (cy << 5) | cx;
+                const u32 entry = GRID == 0 ? TGB_LDG(&f->p_grid[cell_idx]) : tgb_top16_unpack(GRID == 1 ? (u32)TGB_LDG(&f->p_grid16[cell_idx]) : (u32)f->p_grid16[cell_idx]);
                 level = (entry >> TGB_TOP_LEVEL_SHIFT) & 7u;
                 const u32 cells = 16u >> level, keep = ~(cells - 1u);
                 child_size = (f32)(cells << 5);
@@ -257,6 +267,12 @@ TGB_HD u32 tgb_gi_tree_phase(const tgb_gi_frame* f, v3 d, v3 t_delta, v3* p_posi
     *p_cell = cx | (cy << 5) | (cz << 10) | (level << 15) | (iterations << 18);
     *p_flags = flags;
     return kind;
+}
+
+TGB_HD u32 tgb_gi_tree_phase(const tgb_gi_frame* f, v3 d, v3 t_delta, v3* p_position, u32* p_cell, u32* p_flags, u32* p_data, u32 reps,
+                             u32* p_n_visits, u32* p_n_advances)
+{
+    return tgb_gi_tree_phase_t<0>(f, d, t_delta, p_position, p_cell, p_flags, p_data, reps, p_n_visits, p_n_advances);
 }
 
 /* MISS with BORDER flagged: the pop test of the root itself (:296-324); still inside -> back to the tree at the advanced position */

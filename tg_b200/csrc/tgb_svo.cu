@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(256) k_svo_combine(const u32* __restrict__ p_g
  * The last word says whether the table is complete (all leaves at depth 5, no inner node deeper: what
  * tg__construct_inner_node builds, tg_sparse_voxel_octree.c:319-464); otherwise the stack kernel runs instead.
  */
-__global__ void k_svo_flatten(const u32* __restrict__ p_nodes, const u32* __restrict__ p_leaf_data, u32 n_nodes, u32 n_leaves, u32* __restrict__ p_grid)
+__global__ void k_svo_flatten(const u32* __restrict__ p_nodes, const u32* __restrict__ p_leaf_data, u32 n_nodes, u32 n_leaves, u32* __restrict__ p_grid, unsigned short* __restrict__ p_grid16)
 {
     const u32 cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= TGB_TOP_GRID_CELLS) return;
@@ -637,6 +637,7 @@ __global__ void k_svo_flatten(const u32* __restrict__ p_nodes, const u32* __rest
     }
     if (!done) ok = false; /* an inner node at depth 5 */
     p_grid[cell] = entry;
+    p_grid16[cell] = (unsigned short)tgb_top16_pack(entry); /* the same in 16 bits (a data pointer is a leaf index < 32768) */
     if (!ok) p_grid[TGB_TOP_GRID_CELLS] = 0;
 }
 
@@ -644,7 +645,7 @@ static b32 tgbd__svo_flatten(struct tgb_device* d, cudaStream_t st)
 {
     tgb_svo_device* s = &d->svo;
     TGB_CUDA(cudaMemsetAsync(s->d_top_grid + TGB_TOP_GRID_CELLS, 1, sizeof(u32), st)); /* non-zero = complete, cleared by the kernel */
-    k_svo_flatten<<<TGB_TOP_GRID_CELLS / 256, 256, 0, st>>>(s->d_nodes, s->d_leaf_data, s->n_nodes, s->n_leaves, s->d_top_grid);
+    k_svo_flatten<<<TGB_TOP_GRID_CELLS / 256, 256, 0, st>>>(s->d_nodes, s->d_leaf_data, s->n_nodes, s->n_leaves, s->d_top_grid, (unsigned short*)(s->d_top_grid + TGB_TOP_GRID_CELLS + 1));
     TGB_LAUNCH_CHECK(d);
     return TG_TRUE;
 }
