@@ -563,7 +563,7 @@ def gpu_arm(ctx, args, workload, steps, warmup, headline):
                        "objects_world": n_objects_world, "clusters_per_rank": n_clusters,
                        "svo_build_ms": svo_build_ms, "svo_bytes": svo_bytes, "visible_objects": last["n_visible_objects"],
                        **({"svo_leaves_resampled_per_frame": leaves_resampled / steps, "moved_objects_per_frame": len(movers)} if dynamic else {}),
-                       "gi_work_rank0": {"rays_traced_through_svo": last["n_gi_rays"], "node_visits": last["n_gi_node_visits"], "dda_steps": last["n_gi_dda_steps"], "advances": last["n_gi_advances"]},
+                       "gi_work_rank0": {"rays_traced_through_svo": last["n_gi_rays"], "of_those_by_the_exact_kernel": last["n_gi_rays_exact"], "node_visits": last["n_gi_node_visits"], "dda_steps": last["n_gi_dda_steps"], "advances": last["n_gi_advances"]},
                        "l2": "flushed between steps (256 MiB write, outside the timed events)", "stage_ms": {k: v / steps for k, v in stage.items()}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 96 * world + 96 * len(movers), "d2h_bytes_per_step": WIDTH * HEIGHT * 16,

@@ -201,7 +201,7 @@ typedef struct tgb200_timings
     u32 n_visible_objects;
     u32 n_kernel_launches; /* kernels of this library launched since create/reset */
     u32 n_gi_rays;         /* secondary rays the last frame traced through the SVO (those that enter its box) */
-    u32 pad;
+    u32 n_gi_rays_exact;   /* of those, the rays the certified fast walk (tgb_gi_fast.cu) handed to the exact kernel; all of them when the exact kernel runs alone */
     u64 n_gi_node_visits;  /* work of those rays: node visits, leaf DDA steps, advances (svo_functions.inc loop iterations) */
     u64 n_gi_dda_steps;
     u64 n_gi_advances;

@@ -186,16 +186,27 @@ def test_gi_without_svo_is_a_recorded_error(gpu):
 
 def test_config3_full_size_stackless_equals_stack_machine_and_oracle_rows(gpu, oracle):
     """BASELINE configs[2]: 1 secondary ray per hit pixel at 3840x2160 on the 1,024-object scene (~5 M rays through the SVO).
-    Two independent kernels must agree on every pixel -- the stackless kernel over the flattened tree and the stack machine
-    transcribed from svo_functions.inc -- and equal the oracle on every 40th scanline."""
+    Three independent kernels must agree on every pixel -- the certified fast walk (with the exact kernel on the few per cent it
+    hands over), the exact stackless kernel over the flattened tree on every ray, and the stack machine transcribed from
+    svo_functions.inc -- and equal the oracle on every 40th scanline."""
     s = scenes.config2()
     rt = from_scene(s)
     try:
         rt.set_gi(True, 1)
         rt.clear(); rt.render(); rt.synchronize()
-        flat = rt.read_radiance()
-        t_flat = rt.timings()
+        flat = rt.read_radiance()          # default: the certified fast walk + the exact kernel on the rays it hands over (tgb_gi_fast.cu)
+        t_fast = rt.timings()
         vis = rt.read_visibility()
+        assert 0 < t_fast["n_gi_rays_exact"] < 0.2 * t_fast["n_gi_rays"], (t_fast["n_gi_rays_exact"], t_fast["n_gi_rays"])
+        os.environ["TGB_GI_KERNEL"] = "2"  # the exact kernel on every ray (tgb_gi_pool.cu)
+        try:
+            rt.render_shading(); rt.synchronize()
+            exact = rt.read_radiance()
+            t_flat = rt.timings()
+        finally:
+            os.environ.pop("TGB_GI_KERNEL", None)
+        assert np.array_equal(flat, exact), f"{int((flat != exact).any(axis=-1).sum())} pixels differ between the certified fast walk and the exact kernel"
+        assert t_flat["n_gi_rays_exact"] == t_flat["n_gi_rays"] == t_fast["n_gi_rays"]
         for kind, what in ((1, "stack machine"),):
             rt.set_gi_traversal(kind)
             rt.render_shading(); rt.synchronize()

@@ -129,6 +129,8 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     if (d->d_gi_q0) TGB_CUDA(cudaFree(d->d_gi_q0));
     if (d->d_gi_q1) TGB_CUDA(cudaFree(d->d_gi_q1));
     if (d->d_gi_q2) TGB_CUDA(cudaFree(d->d_gi_q2));
+    if (d->d_gi_exact) TGB_CUDA(cudaFree(d->d_gi_exact));
+    d->d_gi_exact = NULL;
     d->d_vis = NULL;
     d->d_radiance = NULL;
     d->d_gi_q0 = d->d_gi_q1 = d->d_gi_q2 = NULL;
@@ -140,6 +142,7 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     TGB_CUDA(cudaMalloc(&d->d_gi_q0, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMalloc(&d->d_gi_q1, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMalloc(&d->d_gi_q2, (u64)width * height * sizeof(float4)));
+    TGB_CUDA(cudaMalloc(&d->d_gi_exact, (u64)width * height * sizeof(u32)));
     TGB_CUDA(cudaMemsetAsync(d->d_vis, 0xFF, padded_px * sizeof(u64), d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_radiance, 0, padded_px * sizeof(float4), d->stream));
     return TG_TRUE;
@@ -195,7 +198,7 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     d->p_comm = NULL;       /* not collective here: the communicator's owner (tgb200_comm_destroy) ran the collective teardown */
     tgbd_p2p_teardown(d);
     cudaFree(d->d_cluster_pointers); cudaFree(d->d_c2o); cudaFree(d->d_objects); cudaFree(d->d_masks);
-    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance_pair[0]); cudaFree(d->d_radiance_pair[1]); cudaFree(d->d_present_pair[0]); cudaFree(d->d_present_pair[1]); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_count);
+    cudaFree(d->d_lut_idx); cudaFree(d->d_color_lut); cudaFree(d->d_vis); cudaFree(d->d_radiance_pair[0]); cudaFree(d->d_radiance_pair[1]); cudaFree(d->d_present_pair[0]); cudaFree(d->d_present_pair[1]); cudaFree(d->d_gi_q0); cudaFree(d->d_gi_q1); cudaFree(d->d_gi_q2); cudaFree(d->d_gi_exact); cudaFree(d->d_gi_count);
     cudaFree(d->d_frames); cudaFree(d->d_frames_sorted); cudaFree(d->d_frames_all); cudaFree(d->d_visible_count);
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
     if (d->h_gi_stats) cudaFreeHost(d->h_gi_stats);
@@ -408,6 +411,7 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
     if (d->gi_stats_valid) cudaMemcpy(d->h_gi_stats, d->d_gi_count, 32 * sizeof(u32), cudaMemcpyDeviceToHost);
     p_out->n_visible_objects = d->n_visible_objects;
     p_out->n_gi_rays = d->h_gi_stats[10];
+    p_out->n_gi_rays_exact = d->h_gi_stats[14];
     p_out->n_gi_node_visits = ((const u64*)d->h_gi_stats)[1];
     p_out->n_gi_dda_steps = ((const u64*)d->h_gi_stats)[2];
     p_out->n_gi_advances = ((const u64*)d->h_gi_stats)[3];

@@ -72,7 +72,8 @@ struct tgb_device
     float4*         d_gi_q0;      /* secondary-ray queue, [w*h] each: origin.xyz + pixel | direction | ambient */
     float4*         d_gi_q1;
     float4*         d_gi_q2;
-    u32*            d_gi_count;   /* u32 [0] queued, [1] fetched; u64 [1] node visits, [2] DDA steps, [3] advances */
+    u32*            d_gi_exact;   /* [w*h] queue slots the certified fast walk handed to the exact kernel (tgb_gi_fast.cu) */
+    u32*            d_gi_count;   /* u32 [0] queued, [1] fetched; u64 [1] node visits, [2] DDA steps, [3] advances; u32 [10] rays of the frame, [12] handed over (band), [13] fetched of those, [14] handed over (frame) */
     u32*            h_gi_stats;   /* pinned copy of d_gi_count after the last frame */
     u32             n_sms;
     u32             gi_traversal; /* 0 = stackless when possible, 1 = stack machine */

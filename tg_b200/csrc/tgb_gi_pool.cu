@@ -29,8 +29,8 @@ enum { W_DX = 0, W_DY, W_DZ, W_PX, W_PY, W_PZ, W_TDX, W_TDY, W_TDZ, W_TMX, W_TMY
 
 template <int K, int GRID>
 __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
-                                                                    const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, float4* __restrict__ p_out,
-                                                                    u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot, u32 n_sms)
+                                                                    const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, const u32* __restrict__ p_list, u32 count_word,
+                                                                    float4* __restrict__ p_out, u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot, u32 n_sms)
 {
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
 
@@ -39,8 +39,10 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
 #define S(w, k) s_pool[((u32)(w) * K + (u32)(k)) * TGB_POOL_THREADS + tid]
 #define SF(w, k) __uint_as_float(S(w, k))
 
-    const u32 n_rays = p_q_count[0];
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
+    /* the whole queue (p_list == NULL: p_q_count[0] rays, fetch counter [1]) or the slots k_gi_trace_fast handed over (tgb_gi_fast.cu:
+     * p_q_count[count_word] entries of p_list, fetch counter [count_word + 1]) */
+    const u32 n_rays = p_q_count[count_word];
+    if (p_list == NULL && blockIdx.x == 0 && tid == 0) { atomicAdd(&p_q_count[10], n_rays); atomicAdd(&p_q_count[14], n_rays); } /* rays of the frame, summed over its bands; all of them traced exactly */
     /* CTAs beyond what the queue can feed (a band, a screen tile of a sharded frame) leave at once. min_rays_per_slot > 1 would keep
      * even fewer CTAs so that every ray slot sees several rays; measured on a 272-row tile (873 k rays): 0.41 ms with 1, 0.49 with 4, 0.69
      * with 8 -- with few rays the longest dependent chains set the duration and parallelism is all that helps (profiles/r02k) */
@@ -110,12 +112,13 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                         const u32 n = (u32)__popc(idle);
                         u32 base = 0;
                         const u32 leader = (u32)(__ffs(idle) - 1);
-                        if (lane == leader) base = atomicAdd(&p_q_count[1], n);
+                        if (lane == leader) base = atomicAdd(&p_q_count[count_word + 1u], n);
                         base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
                         const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
                         if (kd == TGB_RAY_IDLE && mine < n_rays)
                         {
-                            const float4 q0 = __ldcg(&p_q0[mine]), q1 = __ldcs(&p_q1[mine]); /* q0 is read again when the ray is decided (L2), q1 never */
+                            const u32 queue_slot = p_list ? __ldcs(&p_list[mine]) : mine;
+                            const float4 q0 = __ldcg(&p_q0[queue_slot]), q1 = __ldcs(&p_q1[queue_slot]); /* q0 is read again when the ray is decided (L2), q1 never */
                             const v3 d = tgb_v3(q1.x, q1.y, q1.z);
                             v3 position, t_delta; u32 flags;
                             tgb_gi_ray_start(&fr, tgb_v3(q0.x, q0.y, q0.z), d, q1.w, &position, &t_delta, &flags);
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                             S(W_TDX, k) = __float_as_uint(t_delta.x); S(W_TDY, k) = __float_as_uint(t_delta.y); S(W_TDZ, k) = __float_as_uint(t_delta.z);
                             S(W_CELL, k) = 0u;          /* iterations = 0 */
                             S(W_VOX, k) = flags << 16;  /* no advance pending: the first tree phase looks the entry cell up */
-                            S(W_SLOT, k) = mine;
+                            S(W_SLOT, k) = queue_slot;
                             kd = TGB_RAY_TREE;
                         }
                         exhausted = base + n >= n_rays;
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
  * from the environment once (benchmark sweeps only): rays per lane, CTAs per SM, phase budgets, service threshold.
  */
 template <int K, int GRID>
-static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, u32 ctas_per_sm, u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot)
+static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, const u32* p_list, u32 count_word, u32 ctas_per_sm, u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot)
 {
     const size_t smem = (size_t)TGB_POOL_WORDS * K * TGB_POOL_THREADS * sizeof(u32);
     static bool attr_set = false;
@@ -215,13 +218,13 @@ static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, u3
     u32 fit = (u32)((227u * 1024u) / (smem + 1024u));
     if (fit > 2048u / TGB_POOL_THREADS) fit = 2048u / TGB_POOL_THREADS;
     if (ctas_per_sm == 0 || ctas_per_sm > fit) ctas_per_sm = fit < 8u ? fit : 8u;
-    k_gi_trace_pool<K, GRID><<<d->n_sms * ctas_per_sm, TGB_POOL_THREADS, smem, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_radiance,
+    k_gi_trace_pool<K, GRID><<<d->n_sms * ctas_per_sm, TGB_POOL_THREADS, smem, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
                                                                                      service_slots, dda_bias, tree_reps, dda_steps, min_rays_per_slot, d->n_sms);
     TGB_LAUNCH_CHECK(d);
     return TG_TRUE;
 }
 
-extern "C" b32 tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane)
+extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, const u32* p_list, u32 count_word)
 {
     const int rays_per_lane = tgbd_env_int("TGB_GI_RAYS_PER_LANE", 3); /* measured: 1.40 ms for the stage with 3, 1.43 with 2, 1.52 with 4 (L1 shrinks with the pool), 1.51 for k_gi_trace_flat */
     const u32 ctas_per_sm = (u32)tgbd_env_int("TGB_GI_POOL_CTAS_PER_SM", 0);
@@ -236,15 +239,21 @@ extern "C" b32 tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane)
      * stage -- the look-ups are concentrated on few cells and hit L1 either way; what misses is the voxel rows. Off; kept as the measured record. */
     const int grid16 = tgbd_env_int("TGB_GI_POOL_GRID16", 0);
     fr.p_grid16 = (const unsigned short*)(d->svo.d_top_grid + TGB_TOP_GRID_CELLS + 1);
-#define TGB_POOL_CASE(KK) case KK: return grid16 ? tgbd__gi_pool_launch<KK, 1>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : (KK == 3 ? 64u : 16u * KK), dda_bias, tree_reps, dda_steps, min_rays_per_slot) \
-                                                : tgbd__gi_pool_launch<KK, 0>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : (KK == 3 ? 64u : 16u * KK), dda_bias, tree_reps, dda_steps, min_rays_per_slot)
+#define TGB_POOL_CASE(KK) case KK: return grid16 ? tgbd__gi_pool_launch<KK, 1>(d, fr, p_list, count_word, ctas_per_sm, service_env > 0 ? (u32)service_env : (KK == 3 ? 64u : 16u * KK), dda_bias, tree_reps, dda_steps, min_rays_per_slot) \
+                                                : tgbd__gi_pool_launch<KK, 0>(d, fr, p_list, count_word, ctas_per_sm, service_env > 0 ? (u32)service_env : (KK == 3 ? 64u : 16u * KK), dda_bias, tree_reps, dda_steps, min_rays_per_slot)
     switch (rays_per_lane)
     {
     TGB_POOL_CASE(1);
     TGB_POOL_CASE(2);
     TGB_POOL_CASE(3);
     TGB_POOL_CASE(4);
-    default: return tgbd__gi_pool_launch<3, 1>(d, fr, ctas_per_sm, service_env > 0 ? (u32)service_env : 64u, dda_bias, tree_reps, dda_steps, min_rays_per_slot);
+    default: return tgbd__gi_pool_launch<3, 1>(d, fr, p_list, count_word, ctas_per_sm, service_env > 0 ? (u32)service_env : 64u, dda_bias, tree_reps, dda_steps, min_rays_per_slot);
     }
 #undef TGB_POOL_CASE
+}
+
+/* the whole queue of the band */
+extern "C" b32 tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane)
+{
+    return tgbd_gi_pool_trace_list(d, far_plane, NULL, 0u);
 }

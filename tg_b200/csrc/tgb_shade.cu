@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace(const tgb_svo_view 
 
     const u32 tid = threadIdx.x, lane = tid & 31u;
     const u32 n_rays = p_q_count[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&p_q_count[10], n_rays); atomicAdd(&p_q_count[14], n_rays); } /* rays of the frame, summed over its bands; all of them traced exactly */
     const v3 extent = tgb_sub(svo.bmax, svo.bmin);
     const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin); /* svo_functions.inc:3-8 */
 
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(TGB_GI_THREADS) k_gi_trace_flat(const tgb_svo_
 
     const u32 lane = threadIdx.x & 31u;
     const u32 n_rays = p_q_count[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&p_q_count[10], n_rays); atomicAdd(&p_q_count[14], n_rays); } /* rays of the frame, summed over its bands; all of them traced exactly */
     const v3 extent = tgb_sub(svo.bmax, svo.bmin);
     const v3 center = tgb_add(tgb_scale(extent, 0.5f), svo.bmin); /* svo_functions.inc:3-8 */
     const v3 box_mid = tgb_scale(tgb_add(svo.bmin, svo.bmax), 0.5f);
@@ -984,9 +984,14 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         if (gi)
         {
             /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
-            /* TGB_GI_KERNEL: 2 (default) = several rays per lane, state in shared memory (tgb_gi_pool.cu); 1 = one ray per lane (k_gi_trace_flat) */
-            const int gi_kernel = tgbd_env_int("TGB_GI_KERNEL", 2);
-            if (flat && gi_kernel == 2)
+            /* TGB_GI_KERNEL: 3 (default) = certified fast walk, the exact kernel only on the rays it hands over (tgb_gi_fast.cu);
+             * 2 = the exact kernel on every ray, several rays per lane (tgb_gi_pool.cu); 1 = the exact kernel, one ray per lane (k_gi_trace_flat) */
+            const int gi_kernel = tgbd_env_int("TGB_GI_KERNEL", 3);
+            if (flat && gi_kernel == 3)
+            {
+                if (!tgbd_gi_fast_trace(d, p_cam->far_plane)) return TG_FALSE;
+            }
+            else if (flat && gi_kernel == 2)
             {
                 if (!tgbd_gi_pool_trace(d, p_cam->far_plane)) return TG_FALSE;
             }

@@ -117,7 +117,7 @@ class tg_raytracer(C.Structure):
 
 class tgb200_timings(C.Structure):
     _fields_ = [("clear_ms", f32), ("cull_ms", f32), ("visibility_ms", f32), ("svo_ms", f32), ("shading_ms", f32),
-                ("merge_ms", f32), ("n_visible_objects", u32), ("n_kernel_launches", u32), ("n_gi_rays", u32), ("pad", u32),
+                ("merge_ms", f32), ("n_visible_objects", u32), ("n_kernel_launches", u32), ("n_gi_rays", u32), ("n_gi_rays_exact", u32),
                 ("n_gi_node_visits", u64), ("n_gi_dda_steps", u64), ("n_gi_advances", u64),
                 ("merge_resolve_ms", f32), ("merge_gather_ms", f32), ("merge_kernel_ms", f32), ("pad2", u32)]
 

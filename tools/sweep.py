@@ -35,6 +35,26 @@ GI_SWEEP = [
     {"TGB_GI_KERNEL": 2, "TGB_GI_RAYS_PER_LANE": 2, "TGB_GI_POOL_CTAS_PER_SM": 12},
     {"TGB_GI_KERNEL": 2, "TGB_GI_RAYS_PER_LANE": 2, "TGB_GI_POOL_CTAS_PER_SM": 16},
 ]
+FAST_SWEEP = [
+    {"TGB_GI_KERNEL": 2},                                   # the exact kernel on every ray (the frame every other line must equal)
+    {"TGB_GI_KERNEL": 3},                                   # certified fast walk + exact kernel on the hand-overs, defaults
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 6},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 8},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 16},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 24},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 4},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 6},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 12},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 16},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_TREE_REPS": 1},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_TREE_REPS": 2},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_TREE_REPS": 8},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_STEPS": 4},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_STEPS": 8},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_STEPS": 32},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_BIAS": 4},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_BIAS": 8},
+]
 K1_SWEEP = [
     {"TGB_K1_KERNEL": 1},                                   # round-1 kernel: one pixel per lane
     {"TGB_K1_KERNEL": 2},                                   # pool, defaults (K = 2, 4 CTAs / SM)
@@ -76,7 +96,7 @@ def main():
     if args.configs:
         configs = json.loads(args.configs)
     else:
-        configs = {"gi": GI_SWEEP, "k1": K1_SWEEP, "all": GI_SWEEP + K1_SWEEP}[args.what]
+        configs = {"gi": GI_SWEEP, "fast": FAST_SWEEP, "k1": K1_SWEEP, "all": GI_SWEEP + K1_SWEEP}[args.what]
     touched = sorted({k for c in configs for k in c})
     want_vis = want_rad = None
     for cfg in configs:
@@ -107,7 +127,7 @@ def main():
         out = {"config": cfg, **{k: float(np.median(v)) for k, v in stage.items()}, "shading_min_ms": float(np.min(stage["shading_ms"])),
                "vis_equal": bool(np.array_equal(vis, want_vis)), "radiance_bits_equal": bool(np.array_equal(rad, want_rad)),
                "radiance_close_1e-3": bool(np.allclose(rad.view(np.float32), want_rad.view(np.float32), rtol=1e-3, atol=1e-6)),
-               "gi": {k: t[k] for k in ("n_gi_rays", "n_gi_node_visits", "n_gi_dda_steps", "n_gi_advances")}}
+               "gi": {k: t[k] for k in ("n_gi_rays", "n_gi_rays_exact", "n_gi_node_visits", "n_gi_dda_steps", "n_gi_advances")}}
         print(json.dumps(out), flush=True)
     rt.destroy()
 
