@@ -24,7 +24,7 @@ def lib():
         L.tgbsim_flatten.argtypes = [u32p, u32p, C.c_uint32, C.c_uint32, u32p]
         L.tgbsim_gi_trace.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.tgbsim_gi_trace.restype = C.c_uint32
-        L.tgbsim_gi_fast.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
+        L.tgbsim_gi_fast.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_float, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.tgbsim_svo_traverse.argtypes = [u32p, u32p, u32p, f32p, f32p, C.c_float, C.c_uint32, f32p, f32p, f32p, u32p, u32p, C.POINTER(C.c_uint64)]
         L.tgbsim_visibility.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -53,7 +53,7 @@ def gi_trace(bmin, bmax, far_plane, grid, voxels, origins, dirs, tree_reps=4, dd
     return occluded.astype(bool), int(capped), work
 
 
-def gi_fast(bmin, bmax, far_plane, grid, voxels, origins, dirs, tree_reps=4, dda_steps=16, delta=1.0e-3):
+def gi_fast(bmin, bmax, far_plane, grid, voxels, origins, dirs, steps=8, delta=1.0e-3):
     """the certified fast walk (tgb_gi_fast.cuh) per ray -> (result u8: 0 unoccluded / 1 occluded / 2 handed to the exact kernel, work[3])."""
     origins = np.ascontiguousarray(origins, dtype=np.float32)
     dirs = np.ascontiguousarray(dirs, dtype=np.float32)
@@ -61,7 +61,7 @@ def gi_fast(bmin, bmax, far_plane, grid, voxels, origins, dirs, tree_reps=4, dda
     result = np.zeros(len(origins), dtype=np.uint8)
     work = np.zeros(3, dtype=np.uint64)
     lib().tgbsim_gi_fast(_p(bmin, C.c_float), _p(bmax, C.c_float), far_plane, _p(grid, C.c_uint32), _p(voxels, C.c_uint32), len(origins),
-                         _p(origins, C.c_float), _p(dirs, C.c_float), tree_reps, dda_steps, delta, _p(result, C.c_uint8), _p(work, C.c_uint64))
+                         _p(origins, C.c_float), _p(dirs, C.c_float), steps, delta, _p(result, C.c_uint8), _p(work, C.c_uint64))
     return result, work
 
 

@@ -145,10 +145,10 @@ extern "C" {
 /*
  * The certified fast walk (tgb_gi_fast.cuh: what k_gi_trace_fast runs per ray) for n rays. p_result[i]: 0 = unoccluded, 1 = occluded,
  * 2 = handed to the exact kernel (uncertain and unoccluded, shallow direction, cap). Rays that miss the root are unoccluded
- * (k_shade does not queue them). p_work[3]: boxes entered, DDA steps, rays handed over.
+ * (k_shade does not queue them). p_work[3]: empty boxes entered, voxels entered, rays handed over.
  */
 void tgbsim_gi_fast(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, u32 n, const f32* p_origins, const f32* p_dirs,
-                    u32 tree_reps, u32 dda_steps, f32 delta, u8* p_result, u64* p_work)
+                    u32 steps, f32 delta, u8* p_result, u64* p_work)
 {
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane, p_grid, p_voxels);
@@ -160,13 +160,12 @@ void tgbsim_gi_fast(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u
         if (!tgb_ray_aabb(tgb_sub(origin, fr.center), d, fr.bmin, fr.bmax, &e0, &e1)) { p_result[i] = 0; continue; }
         tgb_fast_ray r;
         memset(&r, 0, sizeof r);
-        u32 n_visits = 0, n_steps = 0;
+        u32 n_cells = 0, n_voxels = 0;
         u32 kind = tgb_fast_start(&fr, origin, d, e0, delta, &r);
-        while (kind == TGB_FAST_TREE || kind == TGB_FAST_DDA)
-            kind = kind == TGB_FAST_TREE ? tgb_fast_tree_phase(&fr, &r, tree_reps, &n_visits) : tgb_fast_dda_phase(&fr, &r, dda_steps, &n_steps);
-        if (kind == TGB_FAST_UNOCCLUDED && r.uncertain) kind = TGB_FAST_EXACT;
+        while (kind == TGB_FAST_WALK) kind = tgb_fast_walk(&fr, &r, steps, &n_cells, &n_voxels);
+        if (kind == TGB_FAST_UNOCCLUDED && (r.flags & TGB_FAST_UNCERTAIN)) kind = TGB_FAST_EXACT;
         p_result[i] = kind == TGB_FAST_OCCLUDED ? 1 : (kind == TGB_FAST_UNOCCLUDED ? 0 : 2);
-        if (p_work) { p_work[0] += n_visits; p_work[1] += n_steps; p_work[2] += kind == TGB_FAST_EXACT ? 1 : 0; }
+        if (p_work) { p_work[0] += n_cells; p_work[1] += n_voxels; p_work[2] += kind == TGB_FAST_EXACT ? 1 : 0; }
     }
 }
 

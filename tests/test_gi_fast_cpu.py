@@ -41,7 +41,7 @@ def _surface_rays(rng, s, n):
 
 @pytest.mark.parametrize("make,spread", [(lambda: scenes.small_grid(), 300.0), (lambda: scenes.config1(k=3, width=64, height=36), 200.0),
                                          (lambda: scenes.grid_scene("g6", 6, 6, 64, 36, k=3), 600.0)])
-@pytest.mark.parametrize("budgets", [(4, 16), (1, 1), (3, 5)])
+@pytest.mark.parametrize("budgets", [(8,), (1,), (5,)])
 def test_every_decided_ray_is_decided_like_the_shader(oracle, make, spread, budgets):
     s = make()
     svo, grid, voxels = _svo(oracle, s)
@@ -59,12 +59,12 @@ def test_every_decided_ray_is_decided_like_the_shader(oracle, make, spread, budg
         bad = np.flatnonzero(decided & ((got == 1) != want))
         assert len(bad) == 0, f"{len(bad)} rays decided differently from the shader, first: o={o[bad[:2]].tolist()} d={d[bad[:2]].tolist()}"
         # axis-parallel directions (a tenth of the rays) are handed over by rule; of the others most must be decided here
-        generic = np.abs(d).min(axis=1) >= 8.0e-3
+        generic = np.abs(d).min(axis=1) >= 1.0e-3
         assert not (got[~generic] == 1).any()   # (a shallow ray that misses the root box is never queued: unoccluded)
         assert decided[generic].mean() > 0.6, decided[generic].mean()
         assert (got == 1).any() and (got == 0).any() and work[2] == (~decided).sum()
-        # the phase budgets only suspend and resume the walk
-        ref, _ = cpu_sim.gi_fast(BMIN, BMAX, far, grid, voxels, o, d, 64, 64)
+        # the step budget only suspends and resumes the walk
+        ref, _ = cpu_sim.gi_fast(BMIN, BMAX, far, grid, voxels, o, d, 64)
         assert np.array_equal(ref, got)
     finally:
         oracle.svo_destroy(svo)
@@ -72,8 +72,8 @@ def test_every_decided_ray_is_decided_like_the_shader(oracle, make, spread, budg
 
 @pytest.mark.parametrize("make", [lambda: scenes.grid_scene("g6", 6, 6, 64, 36, k=3), lambda: scenes.small_grid()])
 def test_a_million_rays_with_a_tenth_of_the_margin(oracle, make):
-    """DELTA = 1e-4 instead of the product's 1e-3: still no ray decided differently from the exact walk (tools/gi_fast_margin.py: the
-    first disagreement out of 2e7 rays appears at 3e-6), and the product's DELTA hands over only a few per cent."""
+    """DELTA0 = 2e-5 instead of the product's 2e-4: still no ray decided differently from the exact walk (tools/gi_fast_margin.py: the
+    first disagreement out of 2e7 rays appears below 3e-6), and the product's DELTA hands over only a few per cent."""
     s = make()
     svo, grid, voxels = _svo(oracle, s)
     try:
@@ -82,7 +82,7 @@ def test_a_million_rays_with_a_tenth_of_the_margin(oracle, make):
         far = np.float32(s.camera.far)
         exact, capped, _ = cpu_sim.gi_trace(BMIN, BMAX, far, grid, voxels, o, d)
         assert capped == 0
-        for delta, most in ((1.0e-3, 0.25), (1.0e-4, 0.08)):
+        for delta, most in ((2.0e-4, 0.08), (2.0e-5, 0.04)):
             got, work = cpu_sim.gi_fast(BMIN, BMAX, far, grid, voxels, o, d, delta=delta)
             decided = got != 2
             bad = np.flatnonzero(decided & ((got == 1) != exact))

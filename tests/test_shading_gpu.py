@@ -194,18 +194,18 @@ def test_config3_full_size_stackless_equals_stack_machine_and_oracle_rows(gpu, o
     try:
         rt.set_gi(True, 1)
         rt.clear(); rt.render(); rt.synchronize()
-        flat = rt.read_radiance()          # default: the certified fast walk + the exact kernel on the rays it hands over (tgb_gi_fast.cu)
-        t_fast = rt.timings()
+        flat = rt.read_radiance()          # default: the exact kernel on every ray (tgb_gi_pool.cu)
+        t_flat = rt.timings()
         vis = rt.read_visibility()
-        assert 0 < t_fast["n_gi_rays_exact"] < 0.2 * t_fast["n_gi_rays"], (t_fast["n_gi_rays_exact"], t_fast["n_gi_rays"])
-        os.environ["TGB_GI_KERNEL"] = "2"  # the exact kernel on every ray (tgb_gi_pool.cu)
+        os.environ["TGB_GI_KERNEL"] = "3"  # the certified fast walk + the exact kernel on the rays it hands over (tgb_gi_fast.cu)
         try:
             rt.render_shading(); rt.synchronize()
-            exact = rt.read_radiance()
-            t_flat = rt.timings()
+            fast = rt.read_radiance()
+            t_fast = rt.timings()
         finally:
             os.environ.pop("TGB_GI_KERNEL", None)
-        assert np.array_equal(flat, exact), f"{int((flat != exact).any(axis=-1).sum())} pixels differ between the certified fast walk and the exact kernel"
+        assert np.array_equal(flat, fast), f"{int((flat != fast).any(axis=-1).sum())} pixels differ between the certified fast walk and the exact kernel"
+        assert 0 < t_fast["n_gi_rays_exact"] < 0.1 * t_fast["n_gi_rays"], (t_fast["n_gi_rays_exact"], t_fast["n_gi_rays"])
         assert t_flat["n_gi_rays_exact"] == t_flat["n_gi_rays"] == t_fast["n_gi_rays"]
         for kind, what in ((1, "stack machine"),):
             rt.set_gi_traversal(kind)

@@ -4,88 +4,99 @@
  *   SVO traversal      assets/shaders/raytracer/svo_functions.inc:1-329
  *   secondary rays     tgvk_raytracer.c:1405-1431, TODO.h:33-43 (queued by k_shade, tgb_shade.cu)
  *
- * One ray per lane, everything in registers: the walk's state is the ray (origin, direction, reciprocals), a ray parameter and a
- * cell; no division, no tie rules, no accumulated position -- a fifth of the instructions of the exact walk per visited cell.
- * Decisions it can certify (tgb_gi_fast.cuh: every ray displaced sideways by less than DELTA decides the same) are final:
- * occluded rays keep the radiance k_shade wrote, unoccluded rays add their ambient term. The others -- a few per cent -- are
- * appended to a list of queue slots, and k_gi_trace_pool (tgb_gi_pool.cu: the shader's own arithmetic) traces exactly those right
- * after this kernel. The frame is therefore the one the exact kernel alone produces (tests: radiance bit-identical between
- * TGB_GI_KERNEL=2 and 3 on every pixel).
+ * One ray per lane, everything in registers, ONE kind of step for every cell of the SVO (empty terminal box or voxel of a leaf
+ * block): all lanes that hold a ray run the same instructions, where the exact kernels split every warp into a tree camp and a
+ * DDA camp. Decisions the walk can certify (tgb_gi_fast.cuh: every ray displaced sideways by less than DELTA decides the same)
+ * are final: occluded rays keep the radiance k_shade wrote, unoccluded rays add their ambient term. The others -- a few per
+ * cent -- are appended to a list of queue slots, and k_gi_trace_pool (tgb_gi_pool.cu: the shader's own arithmetic) traces exactly
+ * those right after this kernel. The frame is therefore the one the exact kernel alone produces (tests: radiance bit-identical
+ * between TGB_GI_KERNEL=2 and 3 on every pixel of the 4K frame).
  *
- * Scheduling as in k_gi_trace_flat: lanes are TREE (boxes of the flattened tree) or DDA (voxels of a leaf block), each warp
- * iteration runs the phase most lanes wait for; finished lanes wait for a service phase (ambient term / hand-over / next ray).
+ * Persistent: lanes whose ray is decided wait until `service_lanes` of the warp do, then the warp returns ambient terms, hands
+ * uncertain rays over and fetches new rays together.
  */
 #include "tgb_device.cuh"
 #include "tgb_gi_fast.cuh"
 
 #define TGB_FAST_THREADS 128
+#define TGB_FAST_WARPS   (TGB_FAST_THREADS / 32)
+#define TGB_FAST_CHUNK   64u    /* queue slots a warp reserves with one atomic */
 
+/* 16 bytes global -> shared without passing through registers (LDGSTS; L2 only: a queue record is read once) */
+__device__ __forceinline__ void tgb_cp_async16(void* p_shared, const void* p_global)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((u32)__cvta_generic_to_shared(p_shared)), "l"(p_global) : "memory");
+}
+__device__ __forceinline__ void tgb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tgb_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+/* words of a ready ray in the warp's pool */
+enum { P_OBX = 0, P_OBY, P_OBZ, P_DX, P_DY, P_DZ, P_IX, P_IY, P_IZ, P_W, P_T, P_VOX, P_SLOT, P_PIXEL, P_AX, P_AY, P_AZ, P_WORDS };
+#define TGB_FAST_POOL_EXACT 0x80000000u /* P_VOX: the ray is not taken by the fast walk (shallow direction) */
+#define TGB_FAST_POOL_FIRST 0x40000000u /* P_VOX: TGB_FAST_FIRST */
+
+/*
+ * How a ray reaches a lane. Queue slots are reserved per warp in chunks (one atomic per TGB_FAST_CHUNK rays). The records of the next
+ * 32 slots (origin + pixel | direction + root enter | ambient: 3 x 16 B each) are fetched by cp.async, one record per lane, while
+ * the warp walks; when the warp's pool of ready rays is empty all 32 lanes set their record up TOGETHER (reciprocals, W, start
+ * voxel: tgb_fast_start) and file the ready rays in shared memory, one column per word. A lane whose ray is decided only copies
+ * a ready ray into its registers: a service costs neither memory latency nor a set-up run by a quarter of the warp.
+ */
 __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                     const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, u32* __restrict__ p_exact_list,
-                                                                    float4* __restrict__ p_out, u32 service_lanes, u32 tree_reps, u32 dda_steps, u32 dda_bias)
+                                                                    float4* __restrict__ p_out, u32 service_lanes, u32 steps)
 {
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
 
-    const u32 lane = threadIdx.x & 31u;
+    __shared__ float4 s_rec[3][TGB_FAST_THREADS];                 /* staged records, one per lane */
+    __shared__ u32 s_pool[TGB_FAST_WARPS][P_WORDS][32];           /* ready rays of the warp */
+    __shared__ u32 s_cur[5][TGB_FAST_THREADS];                    /* of the ray a lane walks: queue slot, pixel, ambient */
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 n_rays = p_q_count[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
 
     tgb_fast_ray r;
-    r.o = r.d = r.inv = r.p = r.t_max = tgb_v3(0.0f, 0.0f, 0.0f);
-    r.w = r.t_cur = r.m_cur = r.w_leaf = 0.0f;
-    r.cell = r.vox = r.data = r.entry_axis = r.uncertain = r.n_boxes = 0;
-    u32 kind = TGB_FAST_IDLE, slot = 0, pixel = 0;
-    bool exhausted = false;
-    u32 n_visits = 0, n_steps = 0, n_exact = 0;
+    r.ob = r.d = r.inv = r.r = r.posf = tgb_v3(0.0f, 0.0f, 0.0f);
+    r.w = r.w_step = r.w_t = r.t_cur = 0.0f;
+    r.vx = r.vy = r.vz = 0;
+    r.cell = r.entry = r.flags = r.n_steps = 0;
+    u32 kind = TGB_FAST_IDLE;
+    /* warp-uniform */
+    u32 ready = 0;                       /* pool entries that hold a ready ray */
+    u32 staged_n = 0;                    /* records in flight / arrived in s_rec (lanes 0 .. staged_n - 1) */
+    u32 staged_base = 0;
+    u32 c_next = 0, c_end = 0;           /* the warp's reserved chunk of the queue */
+    bool drained = false;                /* no more chunks */
+    u32 n_cells = 0, n_exact = 0;
 
     for (;;)
     {
-        const u32 counts = __reduce_add_sync(0xFFFFFFFFu, 1u << (6u * (kind > TGB_FAST_OCCLUDED ? TGB_FAST_OCCLUDED : kind)));
-        const u32 n_idle = counts & 63u, n_tree = (counts >> 6) & 63u, n_dda = (counts >> 12) & 63u, n_done = (counts >> 18) & 63u;
-        const u32 n_service = n_done + (exhausted ? 0u : n_idle);
-        const u32 n_working = n_tree + n_dda;
-        if (n_working == 0 && n_service == 0) break; /* queue drained and every ray finished */
+        /* one REDUX counts the lanes that walk and the lanes whose ray is decided */
+        const u32 counts = __reduce_add_sync(0xFFFFFFFFu, kind == TGB_FAST_WALK ? 1u : (kind == TGB_FAST_IDLE ? 0u : 0x100u));
+        const u32 n_walking = counts & 0xFFu, n_decided = counts >> 8, n_idle = 32u - n_walking - n_decided;
+        const bool more = ready != 0u || staged_n != 0u || !drained || c_next < c_end;
+        if (n_walking == 0 && n_decided == 0 && !more) break; /* queue drained, every ray decided and served */
 
-        if (n_service >= service_lanes || n_working == 0)
+        if (n_decided + (more ? n_idle : 0u) >= service_lanes || n_walking == 0)
         {
-            /* ---- service: certain unoccluded rays return their ambient term, idle lanes fetch rays, uncertain rays are handed over ---- */
+            /* ---- service: certain unoccluded rays return their ambient term, uncertain ones are handed over ---- */
             if (kind == TGB_FAST_UNOCCLUDED)
             {
-                if (r.uncertain) kind = TGB_FAST_EXACT;
+                if (r.flags & TGB_FAST_UNCERTAIN) kind = TGB_FAST_EXACT;
                 else
                 {
-                    const float4 q2 = __ldcs(&p_q2[slot]);
-                    f32* p_pixel = reinterpret_cast<f32*>(&p_out[pixel]);
-                    atomicAdd(p_pixel + 0, q2.x);
-                    atomicAdd(p_pixel + 1, q2.y);
-                    atomicAdd(p_pixel + 2, q2.z);
+                    f32* p_pixel = reinterpret_cast<f32*>(&p_out[s_cur[1][tid]]);
+                    atomicAdd(p_pixel + 0, __uint_as_float(s_cur[2][tid]));
+                    atomicAdd(p_pixel + 1, __uint_as_float(s_cur[3][tid]));
+                    atomicAdd(p_pixel + 2, __uint_as_float(s_cur[4][tid]));
                     kind = TGB_FAST_IDLE;
                 }
             }
             else if (kind == TGB_FAST_OCCLUDED) kind = TGB_FAST_IDLE;
-            if (!exhausted)
+            if (kind != TGB_FAST_WALK) { n_cells += r.n_steps; r.n_steps = 0; } /* cells the decided ray entered */
+            for (u32 round = 0; round < 2u; round++)
             {
-                const u32 idle = __ballot_sync(0xFFFFFFFFu, kind == TGB_FAST_IDLE);
-                if (idle)
-                {
-                    const u32 n = (u32)__popc(idle);
-                    u32 base = 0;
-                    const u32 leader = (u32)(__ffs(idle) - 1);
-                    if (lane == leader) base = atomicAdd(&p_q_count[1], n);
-                    base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
-                    const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
-                    if (kind == TGB_FAST_IDLE && mine < n_rays)
-                    {
-                        slot = mine;
-                        const float4 q0 = __ldcs(&p_q0[mine]), q1 = __ldcs(&p_q1[mine]);
-                        pixel = __float_as_uint(q0.w);
-                        kind = tgb_fast_start(&fr, tgb_v3(q0.x, q0.y, q0.z), tgb_v3(q1.x, q1.y, q1.z), q1.w, TGB_FAST_DELTA, &r);
-                    }
-                    exhausted = base + n >= n_rays;
-                }
-            }
-            {
-                /* hand-over: the slot goes to the list k_gi_trace_pool reads (warp-aggregated append) */
+                /* hand-over: the slot goes to the list k_gi_trace_pool reads (warp-aggregated append); second round: shallow rays just taken */
                 const u32 handed = __ballot_sync(0xFFFFFFFFu, kind == TGB_FAST_EXACT);
                 if (handed)
                 {
@@ -95,29 +106,103 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
                     base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
                     if (kind == TGB_FAST_EXACT)
                     {
-                        p_exact_list[base + (u32)__popc(handed & ((1u << lane) - 1u))] = slot;
+                        p_exact_list[base + (u32)__popc(handed & ((1u << lane) - 1u))] = s_cur[0][tid];
                         n_exact++;
                         kind = TGB_FAST_IDLE;
                     }
+                }
+                if (round == 1u) break;
+
+                /* ---- the pool is empty: the staged records become ready rays, all lanes together ---- */
+                if (ready == 0u)
+                {
+                    for (u32 attempt = 0; attempt < 2u && ready == 0u; attempt++)
+                    {
+                        if (staged_n != 0u)
+                        {
+                            tgb_cp_async_wait_all();
+                            if (lane < staged_n)
+                            {
+                                const float4 q0 = s_rec[0][tid], q1 = s_rec[1][tid], q2 = s_rec[2][tid];
+                                tgb_fast_ray n;
+                                const u32 k0 = tgb_fast_start(&fr, tgb_v3(q0.x, q0.y, q0.z), tgb_v3(q1.x, q1.y, q1.z), q1.w, TGB_FAST_DELTA, &n);
+                                u32* p = &s_pool[warp][0][lane];
+                                p[P_OBX * 32] = __float_as_uint(n.ob.x); p[P_OBY * 32] = __float_as_uint(n.ob.y); p[P_OBZ * 32] = __float_as_uint(n.ob.z);
+                                p[P_DX * 32] = __float_as_uint(q1.x); p[P_DY * 32] = __float_as_uint(q1.y); p[P_DZ * 32] = __float_as_uint(q1.z);
+                                p[P_IX * 32] = __float_as_uint(n.inv.x); p[P_IY * 32] = __float_as_uint(n.inv.y); p[P_IZ * 32] = __float_as_uint(n.inv.z);
+                                p[P_W * 32] = __float_as_uint(n.w); p[P_T * 32] = __float_as_uint(n.t_cur);
+                                p[P_VOX * 32] = k0 == TGB_FAST_EXACT ? TGB_FAST_POOL_EXACT
+                                                                      : ((u32)n.vx | ((u32)n.vy << 10) | ((u32)n.vz << 20) | ((n.flags & TGB_FAST_FIRST) ? TGB_FAST_POOL_FIRST : 0u));
+                                p[P_SLOT * 32] = staged_base + lane; p[P_PIXEL * 32] = __float_as_uint(q0.w);
+                                p[P_AX * 32] = __float_as_uint(q2.x); p[P_AY * 32] = __float_as_uint(q2.y); p[P_AZ * 32] = __float_as_uint(q2.z);
+                            }
+                            __syncwarp();
+                            ready = staged_n >= 32u ? 0xFFFFFFFFu : ((1u << staged_n) - 1u);
+                            staged_n = 0;
+                        }
+                        /* stage the next 32 records of the warp's chunk (a new chunk when this one is used up) */
+                        if (c_next >= c_end && !drained)
+                        {
+                            u32 nb = 0;
+                            if (lane == 0) nb = atomicAdd(&p_q_count[1], TGB_FAST_CHUNK);
+                            nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
+                            c_next = nb < n_rays ? nb : n_rays;
+                            c_end = nb + TGB_FAST_CHUNK < n_rays ? nb + TGB_FAST_CHUNK : n_rays;
+                            drained = nb + TGB_FAST_CHUNK >= n_rays;
+                        }
+                        if (c_next < c_end)
+                        {
+                            staged_n = c_end - c_next < 32u ? c_end - c_next : 32u;
+                            staged_base = c_next;
+                            c_next += staged_n;
+                            if (lane < staged_n)
+                            {
+                                tgb_cp_async16(&s_rec[0][tid], &p_q0[staged_base + lane]);
+                                tgb_cp_async16(&s_rec[1][tid], &p_q1[staged_base + lane]);
+                                tgb_cp_async16(&s_rec[2][tid], &p_q2[staged_base + lane]);
+                            }
+                            tgb_cp_async_commit();
+                        }
+                    }
+                }
+                /* ---- idle lanes take a ready ray ---- */
+                {
+                    const u32 idle = __ballot_sync(0xFFFFFFFFu, kind == TGB_FAST_IDLE);
+                    const u32 rank = (u32)__popc(idle & ((1u << lane) - 1u));
+                    const u32 e = __fns(ready, 0u, (int)rank + 1);   /* the rank-th ready entry, or none */
+                    if (kind == TGB_FAST_IDLE && e != 0xFFFFFFFFu)
+                    {
+                        const u32* p = &s_pool[warp][0][e];
+                        const u32 vox = p[P_VOX * 32];
+                        r.ob = tgb_v3(__uint_as_float(p[P_OBX * 32]), __uint_as_float(p[P_OBY * 32]), __uint_as_float(p[P_OBZ * 32]));
+                        r.d = tgb_v3(__uint_as_float(p[P_DX * 32]), __uint_as_float(p[P_DY * 32]), __uint_as_float(p[P_DZ * 32]));
+                        r.inv = tgb_v3(__uint_as_float(p[P_IX * 32]), __uint_as_float(p[P_IY * 32]), __uint_as_float(p[P_IZ * 32]));
+                        tgb_fast_derive(&r, __uint_as_float(p[P_W * 32]));
+                        r.t_cur = __uint_as_float(p[P_T * 32]);
+                        r.vx = (i32)(vox & 1023u); r.vy = (i32)((vox >> 10) & 1023u); r.vz = (i32)((vox >> 20) & 1023u);
+                        r.cell = 0xFFFFFFFFu; r.entry = 0; r.n_steps = 0;
+                        r.flags = (vox & TGB_FAST_POOL_FIRST) ? TGB_FAST_FIRST : 0u;
+                        s_cur[0][tid] = p[P_SLOT * 32]; s_cur[1][tid] = p[P_PIXEL * 32];
+                        s_cur[2][tid] = p[P_AX * 32]; s_cur[3][tid] = p[P_AY * 32]; s_cur[4][tid] = p[P_AZ * 32];
+                        kind = (vox & TGB_FAST_POOL_EXACT) ? TGB_FAST_EXACT : TGB_FAST_WALK;
+                    }
+                    const u32 n_taken = (u32)__popc(idle) < (u32)__popc(ready) ? (u32)__popc(idle) : (u32)__popc(ready);
+                    const u32 last = n_taken ? __fns(ready, 0u, (int)n_taken) : 0xFFFFFFFFu; /* position of the last entry taken */
+                    if (n_taken) ready &= last >= 31u ? 0u : ~((2u << last) - 1u);
+                    __syncwarp();
                 }
             }
             continue;
         }
 
-        if (n_dda + dda_bias > n_tree && n_dda > 0)
-        {
-            if (kind == TGB_FAST_DDA) kind = tgb_fast_dda_phase(&fr, &r, dda_steps, &n_steps);
-        }
-        else if (kind == TGB_FAST_TREE) kind = tgb_fast_tree_phase(&fr, &r, tree_reps, &n_visits);
+        if (kind == TGB_FAST_WALK) kind = tgb_fast_walk(&fr, &r, steps, (u32*)0, (u32*)0);
     }
-    /* [2] boxes, [3] DDA steps of this frame (the exact kernel adds its own); [14] rays handed over */
-    n_visits = __reduce_add_sync(0xFFFFFFFFu, n_visits);
-    n_steps = __reduce_add_sync(0xFFFFFFFFu, n_steps);
+    /* [2] cells (empty boxes and voxels) entered by the fast walk in this frame; the exact kernel adds its look-ups there and counts its DDA steps in [3]; [14] rays handed over */
+    n_cells = __reduce_add_sync(0xFFFFFFFFu, n_cells);
     n_exact = __reduce_add_sync(0xFFFFFFFFu, n_exact);
     if (lane == 0)
     {
-        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_visits);
-        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 2, (unsigned long long)n_steps);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_cells);
         atomicAdd(&p_q_count[14], n_exact);
     }
 }
@@ -129,16 +214,14 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
 extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane)
 {
     const u32 ctas_per_sm = (u32)max(1, min(16, tgbd_env_int("TGB_GI_FAST_CTAS_PER_SM", 8)));
-    const u32 service_lanes = (u32)max(1, tgbd_env_int("TGB_GI_FAST_SERVICE_LANES", 12));
-    const u32 tree_reps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_TREE_REPS", 4));
-    const u32 dda_steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_DDA_STEPS", 16));
-    const u32 dda_bias = (u32)tgbd_env_int("TGB_GI_FAST_DDA_BIAS", 0);
+    const u32 service_lanes = (u32)max(1, min(32, tgbd_env_int("TGB_GI_FAST_SERVICE_LANES", 8)));
+    const u32 steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_STEPS", 4));
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
     k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count + 12, 2, 0u); /* handed over / fetched by the exact kernel */
     TGB_LAUNCH_CHECK(d);
     k_gi_trace_fast<<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
-                                                                                 service_lanes, tree_reps, dda_steps, dda_bias);
+                                                                                 service_lanes, steps);
     TGB_LAUNCH_CHECK(d);
     return tgbd_gi_pool_trace_list(d, far_plane, d->d_gi_exact, 12u);
 }

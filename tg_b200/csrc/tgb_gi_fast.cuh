@@ -5,73 +5,90 @@
  *
  * What the GI pass needs from tg_svo_traverse is one bit per ray: does the shader's traversal return a depth < 1
  * (occluded) or not. The exact kernels (k_gi_trace_pool, k_gi_trace_flat, k_gi_trace) obtain it by running the shader's own
- * arithmetic, operation for operation: an IEEE division per advanced cell, the shader's tie rules, its accumulated
- * `position` -- ~180 thread instructions per visited cell (profiles/r02b_gi_pool_regions.txt).
+ * arithmetic, operation for operation: an IEEE division per advanced cell, the shader's tie rules, its accumulated `position`,
+ * and two different inner loops (tree cells, leaf voxels) that split every warp into two camps (12 - 17 of 32 lanes busy,
+ * profiles/r02b_gi_pool_regions.txt).
  *
- * The shader's traversal is a geometric one: it visits the voxels of the 1-bit SVO that the ray o + t d passes through, in
- * order, and stops at the first solid one (before the far plane). Its floating-point path differs from the ideal line only
- * by rounding: `position` is advanced by `position += (exit + eps) * d` at most a few dozen times at coordinates below 512
- * (half an ulp(512) = 3e-5 per advance and component; along-ray errors do not move the line), and inside a leaf the DDA's
- * t_max are sums of a few dozen small floats. In other words the shader decides like an exact traversal of a ray DISPLACED
- * sideways by less than ~3e-4 units. So a cheap traversal of the ideal line (FMA, reciprocal multiplies, no tie rules)
- * reaches the same decision whenever no decision it took depended on less than DELTA = 1e-3 units of displacement:
+ * The shader's traversal is a geometric one: it visits the cells of the 1-bit SVO -- empty terminal boxes, voxels of the leaf
+ * blocks -- that the ray o + t d passes through, in order, and stops at the first solid voxel (before the far plane). Its
+ * floating-point path differs from the ideal line only by rounding: `position` is advanced by `position += (exit + eps) * d`
+ * at most a few dozen times at coordinates below 512 (half an ulp(512) = 3e-5 per advance and component; along-ray errors do not
+ * move the line; 2^-24 of the advanced distance per component for the product), and inside a leaf the DDA's t_max are sums of
+ * a few dozen small floats. In other words, after n advances the shader decides like an exact traversal of a ray DISPLACED
+ * sideways by less than n * 2.1e-5 units. So a cheap traversal of the ideal line reaches the same decision whenever no decision
+ * it took depended on less than DELTA(n) = DELTA0 + n * DELTA1 units of displacement, DELTA0 = 2e-4 covering this walk's own
+ * rounding (the origin is moved into the box's frame once: half an ulp(1024) = 6e-5; so is the position that selects the next
+ * cell), DELTA1 = 3e-5 per box the ray has entered.
  *
- *   HIT   is certain when the ray stays inside the solid voxel for longer than 2 W (W = DELTA * sum 1 / |d_k|, the time
- *         a sideways displacement of DELTA can shift any plane crossing): every ray displaced by less than DELTA passes through
- *         that voxel too, so the shader's traversal meets it -- or an earlier solid voxel; either way it returns occluded.
- *         (Unless the voxel lies at the far plane: svo_functions.inc:219-256 only ends on enter / far < 1.)
- *   MISS  is certain when, in addition, no two consecutive plane crossings of the walk were closer than W in time (a displaced
- *         ray could have swapped them and visited a voxel this walk did not test) and the ray entered no box closer than
- *         DELTA-equivalent to a lattice line of that box's granularity (voxel planes for a leaf, 32-unit planes for an empty
- *         terminal box).
+ * The walk here has ONE kind of step for every cell, whatever its size (voxel 1, empty terminal box 32 .. 512): look the cell
+ * around the ray's integer position up, take the times the ray crosses the cell's three near planes and three far planes
+ * (one FMA each from the cell's corner), leave through the nearest far plane. All lanes of a warp run the same instructions
+ * whether their rays cross empty space or walk a leaf. With W = DELTA(n) * sum 1 / |d_k| (the time by which a sideways displacement
+ * of DELTA can shift any plane crossing, plus 2.5e-7 t for the rounding of the times themselves):
  *
- * Every ray that ends unoccluded with an uncertain event on its way, every ray with a direction component below 8 DELTA
- * (a ray can then linger next to a plane over several crossings) and every ray that runs into the iteration cap is handed
- * to the exact kernel (tgb_gi_pool.cu) through a list of queue slots. The decision taken here is therefore the shader's on every
- * ray; tests/test_gi_fast_cpu.py holds the host build of these functions against the exact state machine (itself held against
- * the oracle) on millions of rays, and sweeps DELTA down to where the first disagreement appears (tools/gi_fast_margin.py).
- * Host-compilable; the same IEEE operations on both sides (fmaf, 1 / x, floorf, rintf), so the host build predicts the
- * device's decisions AND its flags.
+ *   OCCLUDED   is certain when the cell is a solid voxel and the ray stays inside it for longer than 2 W: every ray displaced by
+ *              less than DELTA passes through that voxel too, so the shader's traversal meets it -- or an earlier solid voxel;
+ *              either way it returns occluded. (Unless the voxel lies at the far plane: svo_functions.inc:219-256 only ends on
+ *              enter / far < 1; such rays are handed over.)
+ *   UNOCCLUDED is certain when the ray left the root and no step on the way was UNCERTAIN. A displaced ray visits the same cells
+ *              in the same order unless it passes an EDGE of a visited cell on the other side; a step is uncertain when the ray
+ *              passes an edge of its cell within W in time: two near planes crossed within W of each other (entered next to an
+ *              edge), two far planes within W (left next to an edge), or the far plane less than W after the near plane (cut a
+ *              corner; for a solid voxel: 2 W, the grazed voxel then counts as uncertain and not as a hit). Where cells of
+ *              different sizes meet, the finer cell's own check covers the lines that lie inside the coarser cell's face.
+ *              A ray that starts inside a cell is checked against every plane of that cell on both sides.
+ *
+ * Every ray that ends unoccluded after an uncertain step, every ray with a direction component below TGB_FAST_SHALLOW (zero
+ * included: W is then so large that nothing could be certified anyway) and every ray that runs into the step cap is handed to the exact
+ * kernel (tgb_gi_pool.cu) through a list of queue slots. The decision taken here is therefore the shader's on every ray;
+ * tests/test_gi_fast_cpu.py holds the host build of these functions against the exact state machine (itself held against the
+ * oracle) on millions of rays, and tools/gi_fast_margin.py sweeps DELTA down to where the first disagreement appears (3e-6).
+ * Host-compilable; the same IEEE operations on both sides (fmaf, 1 / x, floorf), so the host build predicts the device's
+ * decisions AND its hand-overs.
  */
 #ifndef TGB_GI_FAST_CUH
 #define TGB_GI_FAST_CUH
 
 #include "tgb_gi_walk.cuh"
 
-#define TGB_FAST_DELTA        1.0e-3f  /* sideways displacement (world units) a decision must survive */
-#define TGB_FAST_SHALLOW      8.0e-3f  /* direction components below this (zero included) go to the exact kernel */
-#define TGB_FAST_MAX_BOXES    200u     /* boxes a ray may enter (a straight line crosses < 96 cells); beyond: exact kernel */
+#define TGB_FAST_DELTA        2.0e-4f  /* DELTA0: sideways displacement (world units) a decision must survive at the start of the ray */
+#define TGB_FAST_DELTA_STEP   0.15f    /* DELTA1 / DELTA0: growth per box entered (3e-5 for DELTA0 = 2e-4) */
+#define TGB_FAST_SHALLOW      1.0e-3f  /* direction components below this (zero included) go to the exact kernel */
+#define TGB_FAST_MAX_STEPS    1024u    /* cells a ray may enter (a straight line crosses < 3 * 1024 voxels, in practice a few dozen cells); beyond: exact kernel */
 #define TGB_FAST_FAR_FRACTION 0.99f    /* a solid voxel beyond this fraction of the far plane is not decided here */
 
-/* kinds of the fast walk (TREE / DDA as in tgb_gi_walk.cuh) */
-enum { TGB_FAST_IDLE = 0, TGB_FAST_TREE = 1, TGB_FAST_DDA = 2, TGB_FAST_OCCLUDED = 3, TGB_FAST_UNOCCLUDED = 4, TGB_FAST_EXACT = 5 };
+/* kinds of the fast walk */
+enum { TGB_FAST_IDLE = 0, TGB_FAST_WALK = 1, TGB_FAST_OCCLUDED = 2, TGB_FAST_UNOCCLUDED = 3, TGB_FAST_EXACT = 4 };
 
 struct tgb_fast_ray
 {
-    v3  o, d, inv;          /* origin relative to the box centre, direction, 1 / d */
-    f32 w;                  /* W = DELTA * sum 1 / |d_k| (time units) */
-    f32 t_cur;              /* ray parameter at which the current box was entered */
-    v3  p;                  /* o + t_cur d */
-    v3  t_max;              /* leaf DDA: time of the next plane crossing per axis, relative to t_cur */
-    f32 m_cur;              /* leaf DDA: time the current voxel was entered, relative to t_cur */
-    f32 w_leaf;             /* W scaled for the magnitude of t_cur */
-    u32 cell;               /* cx | cy << 5 | cz << 10 of the 32^3 cell the ray stands in */
-    u32 vox;                /* leaf DDA: x | y << 5 | z << 10 */
-    u32 data;               /* leaf data pointer */
-    u32 entry_axis;         /* axis through whose plane the current box was entered; bits 0..2 = axes NOT to check on entry */
-    u32 uncertain;          /* an uncertain event happened on the way */
-    u32 n_boxes;
+    v3  ob;                 /* origin relative to the box's min corner (in the shader's frame: origin - center - bmin) */
+    v3  d, inv;             /* direction, 1 / d */
+    v3  r;                  /* |inv| */
+    v3  posf;               /* 1 where d_k > 0, else 0 */
+    f32 w, w_step, w_t;     /* W = DELTA(n) * sum |inv_k| (time units), its growth per box and per unit of t */
+    f32 t_cur;              /* ray parameter from which the ray is known to be in the current cell */
+    i32 vx, vy, vz;         /* integer position in the box, 0 .. 1023 */
+    u32 cell, entry;        /* the last 32^3 cell looked up and its table entry */
+    u32 flags;              /* bit 0: an uncertain step happened; bit 1: first step of a ray that starts inside the box */
+    u32 n_steps;
 };
 
-/* distance of q to the nearest lattice plane of the given spacing (1 or 32) */
-TGB_HD f32 tgb_fast_lattice_distance(f32 q, f32 spacing, f32 inv_spacing)
+#define TGB_FAST_UNCERTAIN 1u
+#define TGB_FAST_FIRST     2u
+
+/* the fields that follow from d, inv and W(0) (a ready ray is stored without them, tgb_gi_fast.cu) */
+TGB_HD void tgb_fast_derive(tgb_fast_ray* r, f32 w)
 {
-    const f32 s = q * inv_spacing;
-    return fabsf(s - rintf(s)) * spacing;
+    r->r = tgb_v3(fabsf(r->inv.x), fabsf(r->inv.y), fabsf(r->inv.z));
+    r->posf = tgb_v3(r->d.x > 0.0f ? 1.0f : 0.0f, r->d.y > 0.0f ? 1.0f : 0.0f, r->d.z > 0.0f ? 1.0f : 0.0f);
+    r->w = w;
+    r->w_step = TGB_FAST_DELTA_STEP * w;
+    r->w_t = (2.5e-7f / TGB_FAST_DELTA) * w;
 }
 
 /*
- * A fresh ray from its queue record (origin, direction, `enter` of the slab test against the root). Returns TREE, or EXACT for the
+ * A fresh ray from its queue record (origin, direction, `enter` of the slab test against the root). Returns WALK, or EXACT for the
  * rays the fast walk does not take (a direction component below TGB_FAST_SHALLOW). `delta` is TGB_FAST_DELTA in the product; the
  * margin sweep (tools/gi_fast_margin.py) lowers it until the first disagreement with the exact walk appears.
  */
@@ -79,157 +96,85 @@ TGB_HD u32 tgb_fast_start(const tgb_gi_frame* f, v3 origin, v3 dir, f32 root_ent
 {
     const f32 ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
     if (!(ax >= TGB_FAST_SHALLOW && ay >= TGB_FAST_SHALLOW && az >= TGB_FAST_SHALLOW)) return TGB_FAST_EXACT; /* NaN included */
-    r->o = tgb_sub(origin, f->center);
+    r->ob = tgb_sub(tgb_sub(origin, f->center), f->bmin);
     r->d = dir;
     r->inv = tgb_v3(TGB_RCP_RN(dir.x), TGB_RCP_RN(dir.y), TGB_RCP_RN(dir.z));
-    r->w = delta * ((fabsf(r->inv.x) + fabsf(r->inv.y)) + fabsf(r->inv.z));
+    tgb_fast_derive(r, delta * ((fabsf(r->inv.x) + fabsf(r->inv.y)) + fabsf(r->inv.z)));
     r->t_cur = root_enter > 0.0f ? root_enter : 0.0f;
-    r->p = tgb_v3(fmaf(r->t_cur, dir.x, r->o.x), fmaf(r->t_cur, dir.y, r->o.y), fmaf(r->t_cur, dir.z, r->o.z));
-    /* the cell around p; a ray that starts on (or outside) a root face is clamped into the outermost cell, and that axis has
-     * nothing on its other side to be confused with */
-    const f32 half = 0.5f * (f32)TG_SVO_SIDE_LENGTH;
-    u32 skip = 0;
-    skip |= fabsf(r->p.x - f->box_mid.x) > half - 0.01f ? 1u : 0u;
-    skip |= fabsf(r->p.y - f->box_mid.y) > half - 0.01f ? 2u : 0u;
-    skip |= fabsf(r->p.z - f->box_mid.z) > half - 0.01f ? 4u : 0u;
-    const i32 cx = (i32)floorf((r->p.x - f->bmin.x) * 0.03125f), cy = (i32)floorf((r->p.y - f->bmin.y) * 0.03125f), cz = (i32)floorf((r->p.z - f->bmin.z) * 0.03125f);
-    r->cell = (u32)(cx < 0 ? 0 : (cx > 31 ? 31 : cx)) | ((u32)(cy < 0 ? 0 : (cy > 31 ? 31 : cy)) << 5) | ((u32)(cz < 0 ? 0 : (cz > 31 ? 31 : cz)) << 10);
-    r->entry_axis = skip;
-    r->uncertain = 0;
-    r->n_boxes = 0;
-    return TGB_FAST_TREE;
-}
-
-/* is p, entering a box through the planes in `skip`, closer than W-equivalent to a lattice plane of the other axes? */
-TGB_HD bool tgb_fast_entry_uncertain(const tgb_gi_frame* f, const tgb_fast_ray* r, f32 w, f32 spacing, f32 inv_spacing)
-{
-    const u32 skip = r->entry_axis;
-    bool near = false;
-    near = near || (!(skip & 1u) && tgb_fast_lattice_distance(r->p.x - f->bmin.x, spacing, inv_spacing) < w * fabsf(r->d.x));
-    near = near || (!(skip & 2u) && tgb_fast_lattice_distance(r->p.y - f->bmin.y, spacing, inv_spacing) < w * fabsf(r->d.y));
-    near = near || (!(skip & 4u) && tgb_fast_lattice_distance(r->p.z - f->bmin.z, spacing, inv_spacing) < w * fabsf(r->d.z));
-    return near;
+    /* the voxel around the starting point; a ray that starts on (or outside) a root face is clamped into the outermost layer */
+    const f32 px = fmaf(r->t_cur, dir.x, r->ob.x), py = fmaf(r->t_cur, dir.y, r->ob.y), pz = fmaf(r->t_cur, dir.z, r->ob.z);
+    const f32 top = (f32)TG_SVO_SIDE_LENGTH - 1.0f;
+    r->vx = (i32)tgb_clamp(floorf(px), 0.0f, top);
+    r->vy = (i32)tgb_clamp(floorf(py), 0.0f, top);
+    r->vz = (i32)tgb_clamp(floorf(pz), 0.0f, top);
+    r->cell = 0xFFFFFFFFu;
+    r->entry = 0;
+    r->flags = root_enter > 0.0f ? 0u : TGB_FAST_FIRST;
+    r->n_steps = 0;
+    return TGB_FAST_WALK;
 }
 
 /*
- * Tree phase: up to `reps` boxes. Looks the terminal box around the ray's cell up; a leaf with data sets the DDA up (kind DDA),
- * an empty box is crossed to its far border. Returns TREE (budget used up), DDA, UNOCCLUDED (left the root) or EXACT (cap).
+ * Up to `steps` cells. Returns WALK (budget used up), OCCLUDED, UNOCCLUDED (left the root; certain only if no step was uncertain)
+ * or EXACT (step cap).
  */
-TGB_HD u32 tgb_fast_tree_phase(const tgb_gi_frame* f, tgb_fast_ray* r, u32 reps, u32* p_n_visits)
+TGB_HD u32 tgb_fast_walk(const tgb_gi_frame* f, tgb_fast_ray* r, u32 steps, u32* p_n_cells, u32* p_n_voxels)
 {
-    for (u32 rep = 0; rep < reps; rep++)
+    i32 vx = r->vx, vy = r->vy, vz = r->vz;
+    f32 t_cur = r->t_cur, w_n = r->w;
+    u32 cell = r->cell, entry = r->entry, flags = r->flags;
+    u32 kind = TGB_FAST_WALK;
+    u32 k = 0;
+    for (;;)
     {
-        if (++r->n_boxes > TGB_FAST_MAX_BOXES) return TGB_FAST_EXACT;
-        (*p_n_visits)++;
-        const u32 cx = r->cell & 31u, cy = (r->cell >> 5) & 31u, cz = r->cell >> 10;
-        const u32 entry = TGB_LDG(&f->p_grid[r->cell]);
-        const f32 w = r->w * (1.0f + r->t_cur * 0.00390625f); /* the rounding of t grows with t */
-        if (entry & TGB_TOP_HAS_DATA)
+        /* ---- the cell around (vx, vy, vz): a voxel of a leaf block, or the empty terminal box of the flattened tree ---- */
+        const u32 c = (((u32)vz & 0x3E0u) << 5) | ((u32)vy & 0x3E0u) | ((u32)vx >> 5);
+        const bool new_cell = c != cell;
+        if (new_cell) { cell = c; entry = TGB_LDG(&f->p_grid[c]); }
+        const bool leaf = (entry & TGB_TOP_HAS_DATA) != 0;
+        u32 row = 0;
+        if (leaf) row = TGB_LDG(&f->p_voxels[((entry & 0x3FFFFFu) << 10) | (((u32)vz & 31u) << 5) | ((u32)vy & 31u)]); /* < 2^22 leaves: the word index fits 32 bits */
+        const bool solid = ((row >> ((u32)vx & 31u)) & 1u) != 0;
+        if (p_n_cells) { if (leaf) (*p_n_voxels)++; else (*p_n_cells)++; }
+        if (new_cell | !leaf) w_n += r->w_step; /* one more advance of the shader's `position` */
+        const u32 size = leaf ? 1u : (512u >> ((entry >> TGB_TOP_LEVEL_SHIFT) & 7u));
+        const u32 mask = 0u - size;
+        const f32 size_f = (f32)size;
+        /* crossing times of the far planes (difference form: exact when the ray is close to the plane) and of the near planes */
+        const f32 fx = (fmaf(size_f, r->posf.x, (f32)((u32)vx & mask)) - r->ob.x) * r->inv.x;
+        const f32 fy = (fmaf(size_f, r->posf.y, (f32)((u32)vy & mask)) - r->ob.y) * r->inv.y;
+        const f32 fz = (fmaf(size_f, r->posf.z, (f32)((u32)vz & mask)) - r->ob.z) * r->inv.z;
+        const f32 nx = fmaf(-size_f, r->r.x, fx), ny = fmaf(-size_f, r->r.y, fy), nz = fmaf(-size_f, r->r.z, fz);
+        const f32 t_exit = fminf(fminf(fx, fy), fz);
+        const f32 t_in = fmaxf(fmaxf(fmaxf(nx, ny), nz), t_cur);
+        const f32 w = fmaf(t_cur, r->w_t, w_n);
+        /* edges of the cell within W in time: near-near, far-far, near-far */
+        const f32 t_lo = t_in - w, t_hi = t_exit + w;
+        const bool bx = nx > t_lo, by = ny > t_lo, bz = nz > t_lo;
+        const bool ex = fx < t_hi, ey = fy < t_hi, ez = fz < t_hi;
+        bool uncertain = ((bx & by) | (bx & bz) | (by & bz)) | ((ex & ey) | (ex & ez) | (ey & ez));
+        if (flags & TGB_FAST_FIRST) uncertain = uncertain | bx | by | bz; /* started inside the cell: any plane close behind */
+        uncertain = uncertain | ((t_exit - t_in) < (solid ? w + w : w));
+        if (solid && !uncertain)
         {
-            /* a leaf with data: voxel around p, next plane crossings relative to t_cur */
-            if (tgb_fast_entry_uncertain(f, r, w, 1.0f, 1.0f)) r->uncertain = 1;
-            const v3 lmin = tgb_v3(f->bmin.x + (f32)(cx << 5), f->bmin.y + (f32)(cy << 5), f->bmin.z + (f32)(cz << 5));
-            const f32 hx = r->p.x - lmin.x, hy = r->p.y - lmin.y, hz = r->p.z - lmin.z;
-            const f32 vx = tgb_clamp(floorf(hx), 0.0f, 31.0f), vy = tgb_clamp(floorf(hy), 0.0f, 31.0f), vz = tgb_clamp(floorf(hz), 0.0f, 31.0f);
-            r->t_max.x = ((r->d.x > 0.0f ? vx + 1.0f : vx) - hx) * r->inv.x;
-            r->t_max.y = ((r->d.y > 0.0f ? vy + 1.0f : vy) - hy) * r->inv.y;
-            r->t_max.z = ((r->d.z > 0.0f ? vz + 1.0f : vz) - hz) * r->inv.z;
-            r->vox = (u32)(i32)vx | ((u32)(i32)vy << 5) | ((u32)(i32)vz << 10);
-            r->data = entry & TGB_TOP_POINTER_MASK;
-            r->m_cur = 0.0f;
-            r->w_leaf = w;
-            return TGB_FAST_DDA;
+            if (t_in < TGB_FAST_FAR_FRACTION * f->far_plane) { kind = TGB_FAST_OCCLUDED; break; }
+            flags |= TGB_FAST_UNCERTAIN; kind = TGB_FAST_UNOCCLUDED; break; /* at the far plane: the exact kernel decides */
         }
-        /* an empty terminal box of 16 >> level cells: to its far border */
-        if (tgb_fast_entry_uncertain(f, r, w, 32.0f, 0.03125f)) r->uncertain = 1;
-        const u32 level = (entry >> TGB_TOP_LEVEL_SHIFT) & 7u;
-        const u32 cells = 16u >> level, keep = ~(cells - 1u);
-        const u32 bx = cx & keep, by = cy & keep, bz = cz & keep;
-        const u32 fx = r->d.x > 0.0f ? bx + cells : bx, fy = r->d.y > 0.0f ? by + cells : by, fz = r->d.z > 0.0f ? bz + cells : bz;
-        const f32 tx = ((f->bmin.x + (f32)(fx << 5)) - r->o.x) * r->inv.x;
-        const f32 ty = ((f->bmin.y + (f32)(fy << 5)) - r->o.y) * r->inv.y;
-        const f32 tz = ((f->bmin.z + (f32)(fz << 5)) - r->o.z) * r->inv.z;
-        const bool xy = tx < ty;
-        const bool go_x = xy & (tx < tz), go_y = !xy & (ty < tz), go_z = !(go_x | go_y);
-        const f32 t_exit = go_x ? tx : (go_y ? ty : tz);
-        r->t_cur = t_exit;
-        r->p = tgb_v3(fmaf(t_exit, r->d.x, r->o.x), fmaf(t_exit, r->d.y, r->o.y), fmaf(t_exit, r->d.z, r->o.z));
-        /* the next cell: exact along the exit axis, from p along the other two (clamped into the box: p is inside by construction) */
-        i32 nx = (i32)floorf((r->p.x - f->bmin.x) * 0.03125f), ny = (i32)floorf((r->p.y - f->bmin.y) * 0.03125f), nz = (i32)floorf((r->p.z - f->bmin.z) * 0.03125f);
-        nx = nx < (i32)bx ? (i32)bx : (nx > (i32)(bx + cells - 1u) ? (i32)(bx + cells - 1u) : nx);
-        ny = ny < (i32)by ? (i32)by : (ny > (i32)(by + cells - 1u) ? (i32)(by + cells - 1u) : ny);
-        nz = nz < (i32)bz ? (i32)bz : (nz > (i32)(bz + cells - 1u) ? (i32)(bz + cells - 1u) : nz);
-        if (go_x) nx = r->d.x > 0.0f ? (i32)(bx + cells) : (i32)bx - 1;
-        if (go_y) ny = r->d.y > 0.0f ? (i32)(by + cells) : (i32)by - 1;
-        if (go_z) nz = r->d.z > 0.0f ? (i32)(bz + cells) : (i32)bz - 1;
-        if ((u32)(nx | ny | nz) > 31u) return TGB_FAST_UNOCCLUDED; /* left the root */
-        r->cell = (u32)nx | ((u32)ny << 5) | ((u32)nz << 10);
-        r->entry_axis = go_x ? 1u : (go_y ? 2u : 4u);
+        flags = (flags & ~TGB_FAST_FIRST) | (uncertain ? TGB_FAST_UNCERTAIN : 0u);
+        /* ---- leave through the nearest far plane(s): exact along the exit axis, from the position along the others ---- */
+        const f32 px = fmaf(t_exit, r->d.x, r->ob.x) + (fx == t_exit ? r->posf.x - 0.5f : 0.0f);
+        const f32 py = fmaf(t_exit, r->d.y, r->ob.y) + (fy == t_exit ? r->posf.y - 0.5f : 0.0f);
+        const f32 pz = fmaf(t_exit, r->d.z, r->ob.z) + (fz == t_exit ? r->posf.z - 0.5f : 0.0f);
+        vx = (i32)floorf(px); vy = (i32)floorf(py); vz = (i32)floorf(pz);
+        t_cur = t_exit;
+        if ((u32)(vx | vy | vz) >= (u32)TG_SVO_SIDE_LENGTH) { kind = TGB_FAST_UNOCCLUDED; break; } /* left the root */
+        if (++k >= steps) break;
     }
-    return TGB_FAST_TREE;
-}
-
-/*
- * DDA phase: up to `steps` voxels of the leaf block. Returns DDA (budget used up), OCCLUDED (a solid voxel the ray certainly passes
- * through), TREE (left the block; the ray stands in the neighbouring cell), UNOCCLUDED (left the root).
- */
-TGB_HD u32 tgb_fast_dda_phase(const tgb_gi_frame* f, tgb_fast_ray* r, u32 steps, u32* p_n_steps)
-{
-    const u32* p_block = f->p_voxels + (u64)r->data * TG_SVO_BLOCK_WORDS;
-    const f32 rx = fabsf(r->inv.x), ry = fabsf(r->inv.y), rz = fabsf(r->inv.z);
-    const i32 step_x = r->d.x > 0.0f ? 1 : -1, step_y = r->d.y > 0.0f ? 1 : -1, step_z = r->d.z > 0.0f ? 1 : -1;
-    f32 tx = r->t_max.x, ty = r->t_max.y, tz = r->t_max.z, m_cur = r->m_cur;
-    i32 x = (i32)(r->vox & 31u), y = (i32)((r->vox >> 5) & 31u), z = (i32)(r->vox >> 10);
-    const f32 w = r->w_leaf, w2 = 2.0f * w;
-    u32 uncertain = r->uncertain;
-    u32 kind = TGB_FAST_DDA;
-    u32 bits = TGB_LDG(&p_block[32 * z + y]);
-#ifdef __CUDA_ARCH__
-#pragma unroll 1
-#endif
-    for (u32 k = 0; k < steps; k++)
-    {
-        (*p_n_steps)++;
-        const bool solid = ((bits >> x) & 1u) != 0;
-        const f32 m_next = fminf(fminf(tx, ty), tz);
-        const f32 gap = m_next - m_cur;
-        if (gap < (solid ? w2 : w)) uncertain = 1;   /* a grazed solid voxel, or two crossings a displaced ray could swap */
-        else if (solid)
-        {
-            /* certain unless it lies at the far plane (the shader skips the rest of the leaf there: left to the exact kernel) */
-            if (r->t_cur + m_cur < TGB_FAST_FAR_FRACTION * f->far_plane) { kind = TGB_FAST_OCCLUDED; break; }
-            uncertain = 1; kind = TGB_FAST_UNOCCLUDED; break;
-        }
-        const bool xy = tx < ty;
-        const bool go_x = xy & (tx < tz), go_y = !xy & (ty < tz), go_z = !(go_x | go_y);
-        tx = go_x ? tx + rx : tx;
-        ty = go_y ? ty + ry : ty;
-        tz = go_z ? tz + rz : tz;
-        x += go_x ? step_x : 0;
-        y += go_y ? step_y : 0;
-        z += go_z ? step_z : 0;
-        m_cur = m_next;
-        if ((u32)(x | y | z) > 31u)
-        {
-            /* left the block through the plane of the axis that stepped: the neighbouring cell, entered at t_cur + m. A displaced ray
-             * could cross the NEXT voxel plane before leaving and visit one more voxel of this block */
-            if (fminf(fminf(tx, ty), tz) - m_cur < w) uncertain = 1;
-            i32 cx = (i32)(r->cell & 31u), cy = (i32)((r->cell >> 5) & 31u), cz = (i32)(r->cell >> 10);
-            cx += go_x ? step_x : 0; cy += go_y ? step_y : 0; cz += go_z ? step_z : 0;
-            if ((u32)(cx | cy | cz) > 31u) { kind = TGB_FAST_UNOCCLUDED; break; }
-            r->cell = (u32)cx | ((u32)cy << 5) | ((u32)cz << 10);
-            r->entry_axis = go_x ? 1u : (go_y ? 2u : 4u);
-            r->t_cur = r->t_cur + m_cur;
-            r->p = tgb_v3(fmaf(r->t_cur, r->d.x, r->o.x), fmaf(r->t_cur, r->d.y, r->o.y), fmaf(r->t_cur, r->d.z, r->o.z));
-            kind = TGB_FAST_TREE;
-            break;
-        }
-        if (!go_x) bits = TGB_LDG(&p_block[32 * z + y]);
-    }
-    r->t_max = tgb_v3(tx, ty, tz);
-    r->m_cur = m_cur;
-    r->vox = ((u32)x & 31u) | (((u32)y & 31u) << 5) | (((u32)z & 31u) << 10);
-    r->uncertain = uncertain;
+    r->n_steps += k;
+    if (kind == TGB_FAST_WALK && r->n_steps > TGB_FAST_MAX_STEPS) kind = TGB_FAST_EXACT;
+    r->vx = vx; r->vy = vy; r->vz = vz;
+    r->t_cur = t_cur; r->w = w_n;
+    r->cell = cell; r->entry = entry; r->flags = flags;
     return kind;
 }
 

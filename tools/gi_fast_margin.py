@@ -2,8 +2,8 @@
 
 Runs the host builds of the fast walk and of the exact state machine (tests/cpu_sim; the latter is held against the oracle's
 transcription of svo_functions.inc by tests/test_gi_walk_cpu.py) on the same rays and reports, per DELTA: the share of rays handed to
-the exact kernel and the number of rays the fast walk DECIDED differently from the exact one. The product uses DELTA = 1e-3; the sweep
-goes down until disagreements appear, which shows how far below 1e-3 the real sideways displacement of the shader's walk stays.
+the exact kernel and the number of rays the fast walk DECIDED differently from the exact one. The product uses DELTA0 = 2e-4 (growing by 3e-5 per box entered); the sweep
+goes down until disagreements appear, which shows how far below that the real sideways displacement of the shader's walk stays.
 
     python tools/gi_fast_margin.py [n_rays] [scene]      scene: g6 (6x6 objects, default) | small | c1
 """
@@ -57,11 +57,11 @@ def main():
     exact, capped, work = cpu_sim.gi_trace(bmin, bmax, far, grid, voxels, o, d)
     t1 = time.time()
     print(f"{which}: {n} rays, exact walk {t1 - t0:.1f} s: occluded {exact.mean():.3f}, per ray {work[0] / n:.1f} look-ups {work[1] / n:.1f} DDA steps; capped {capped}")
-    for delta in (1e-3, 3e-4, 1e-4, 3e-5, 1e-5, 3e-6, 1e-6, 0.0):
+    for delta in (1e-3, 2e-4, 1e-4, 3e-5, 1e-5, 3e-6, 1e-6, 0.0):
         res, w = cpu_sim.gi_fast(bmin, bmax, far, grid, voxels, o, d, delta=delta)
         decided = res != 2
         bad = np.flatnonzero(decided & ((res == 1) != exact))
-        print(f"  delta {delta:8.1e}: handed over {1.0 - decided.mean():7.4f}  decided differently {len(bad):6d}  per ray {w[0] / n:.1f} boxes {w[1] / n:.1f} DDA steps"
+        print(f"  delta {delta:8.1e}: handed over {1.0 - decided.mean():7.4f}  decided differently {len(bad):6d}  per ray {w[0] / n:.1f} boxes {w[1] / n:.1f} voxels"
               + (f"   first: o={o[bad[0]].tolist()} d={d[bad[0]].tolist()}" if len(bad) else ""))
 
 

@@ -38,22 +38,20 @@ GI_SWEEP = [
 FAST_SWEEP = [
     {"TGB_GI_KERNEL": 2},                                   # the exact kernel on every ray (the frame every other line must equal)
     {"TGB_GI_KERNEL": 3},                                   # certified fast walk + exact kernel on the hand-overs, defaults
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 4},
     {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 6},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 8},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 12},
     {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 16},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 24},
     {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 4},
     {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 6},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 12},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 16},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_TREE_REPS": 1},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_TREE_REPS": 2},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_TREE_REPS": 8},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_STEPS": 4},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_STEPS": 8},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_STEPS": 32},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_BIAS": 4},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_DDA_BIAS": 8},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 10},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_STEPS": 1},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_STEPS": 2},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_STEPS": 8},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_STEPS": 16},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_RAYS_PER_LANE": 1, "TGB_GI_POOL_CTAS_PER_SM": 16},   # the exact kernel's shape for the few handed-over rays
+    {"TGB_GI_KERNEL": 3, "TGB_GI_RAYS_PER_LANE": 1, "TGB_GI_POOL_CTAS_PER_SM": 8},
+    {"TGB_GI_KERNEL": 3, "TGB_GI_RAYS_PER_LANE": 2, "TGB_GI_POOL_CTAS_PER_SM": 12},
 ]
 K1_SWEEP = [
     {"TGB_K1_KERNEL": 1},                                   # round-1 kernel: one pixel per lane
