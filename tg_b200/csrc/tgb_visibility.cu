@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
         if (SHARDED && threadIdx.x == 0) sh.p_tile_flags[(tgb_row_to_virtual(blockIdx.y * TGB_TILE_H, n_ranks, tile_rows) / TGB_BAND_ROWS) * sh.tiles_x + blockIdx.x] = 0u;
         return;
     }
-    if (fallback_only && p_count[2] == 0) return; /* k_visibility_pool (tgb_visibility_pool.cu) rendered this frame */
+    if ((fallback_only & 1u) && p_count[2] == 0) return; /* k_visibility_pool (tgb_visibility_pool.cu) rendered this frame */
     const bool sorted = p_count[1] != 0;
 
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -522,6 +522,23 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
     const u32 px = wx0 + (lane & 7u), py = wy0 + (lane >> 3);
     const bool in_screen = px < w && py < h;
     const i32 wx1 = (i32)min(wx0 + 7u, w - 1u), wy1 = (i32)min(wy0 + 3u, h - 1u);
+
+    /* A tile no visible object's rectangle touches (most tiles of a rank that holds 1 / N of the objects) leaves after one barrier,
+     * before anything per-ray is computed. One window covers up to TGB_K1_THREADS visible objects. */
+    if (n_visible <= TGB_K1_THREADS && !(fallback_only & 2u)) /* bit 1: TGB_K1_EARLY_EXIT=0, the measured alternative */
+    {
+        bool touched = false;
+        if (threadIdx.x < n_visible)
+        {
+            const tgb_object_frame& f = p_frames[threadIdx.x];
+            touched = !(f.x1 < tx0 || f.x0 > tx1 || f.y1 < ty0 || f.y0 > ty1);
+        }
+        if (!__syncthreads_or(touched ? 1 : 0))
+        {
+            if (SHARDED && threadIdx.x == 0) sh.p_tile_flags[(tgb_row_to_virtual(blockIdx.y * TGB_TILE_H, n_ranks, tile_rows) / TGB_BAND_ROWS) * sh.tiles_x + blockIdx.x] = 0u;
+            return;
+        }
+    }
 
     const v3 dir_ws = tgb_pixel_direction(&cam, w, h, in_screen ? px : min(wx0, w - 1u), in_screen ? py : min(wy0, h - 1u));
     u64 best = TG_VIS_CLEAR;
@@ -599,7 +616,7 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
      * inside a phase, not the number of lanes that start it, is what idles the lanes (profiles/r02d_k1pool_*); kept as the measured record */
     const int k1_kernel = tgbd_env_int("TGB_K1_KERNEL", 1);
     if (k1_kernel == 2 && !tgbd_k1_pool_render(d, p_cam)) return TG_FALSE;
-    const u32 fallback_only = k1_kernel == 2 ? 1u : 0u; /* after the pool kernel: only frames it declined (an object too large for its packed iterator) */
+    const u32 fallback_only = (k1_kernel == 2 ? 1u : 0u) | (tgbd_env_int("TGB_K1_EARLY_EXIT", 1) ? 0u : 2u); /* bit 0, after the pool kernel: only frames it declined (an object too large for its packed iterator) */
     const dim3 grid((d->width + TGB_TILE_W - 1) / TGB_TILE_W, (d->height + TGB_TILE_H - 1) / TGB_TILE_H);
     /* register budget: 5 CTAs per SM = 48 registers + ~30 spilled words; measured 0.711 ms against 0.737 with 4 CTAs (64 registers), 0.715 with 6 (40), 0.843 with 3
      * (80): the kernel is issue-bound and more resident warps buy more than the spills cost (TGB_K1_MIN_CTAS selects the other builds; tuning only) */

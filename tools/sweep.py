@@ -73,6 +73,7 @@ def main():
     ap.add_argument("--frames", type=int, default=12)
     ap.add_argument("--rows", type=int, default=0, help="shade only ROWS rows starting at --row0 (emulates the screen tile of a sharded frame)")
     ap.add_argument("--row0", type=int, default=0)
+    ap.add_argument("--shard", default="", help="r,n: the scene of rank r of n (its 1/n of the objects) on this one GPU: K1 as a rank of a sharded frame sees it")
     ap.add_argument("--configs", default="", help="JSON list of knob dicts (overrides --what)")
     args = ap.parse_args()
 
@@ -81,7 +82,8 @@ def main():
     import tg_b200
     from tg_b200.raytracer import from_scene
 
-    scene = bench.build_scene(0, 1, args.workload, host_bits=False)
+    shard = tuple(int(v) for v in args.shard.split(",")) if args.shard else (0, 1)
+    scene = bench.build_scene(shard[0], shard[1], args.workload, host_bits=False)
     rt = from_scene(scene, device=0)
     lib = tg_b200.lib()
     dev = torch.device("cuda", 0)
