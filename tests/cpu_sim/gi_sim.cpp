@@ -170,3 +170,25 @@ void tgbsim_gi_fast(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u
 }
 
 }
+
+extern "C" {
+/* steps the fast walk takes per ray (diagnostics for tools/gi_fast_margin.py) */
+void tgbsim_gi_fast_steps(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, u32 n, const f32* p_origins, const f32* p_dirs, u32* p_steps)
+{
+    tgb_gi_frame fr;
+    tgb_gi_frame_init(&fr, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane, p_grid, p_voxels);
+    for (u32 i = 0; i < n; i++)
+    {
+        const v3 origin = tgb_v3(p_origins[3 * i], p_origins[3 * i + 1], p_origins[3 * i + 2]);
+        const v3 d = tgb_v3(p_dirs[3 * i], p_dirs[3 * i + 1], p_dirs[3 * i + 2]);
+        f32 e0, e1;
+        p_steps[i] = 0;
+        if (!tgb_ray_aabb(tgb_sub(origin, fr.center), d, fr.bmin, fr.bmax, &e0, &e1)) continue;
+        tgb_fast_ray r;
+        memset(&r, 0, sizeof r);
+        u32 kind = tgb_fast_start(&fr, origin, d, e0, TGB_FAST_DELTA, &r);
+        while (kind == TGB_FAST_WALK) kind = tgb_fast_walk(&fr, &r, 8, (u32*)0, (u32*)0);
+        p_steps[i] = r.n_steps;
+    }
+}
+}

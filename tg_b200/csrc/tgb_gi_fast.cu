@@ -44,7 +44,7 @@ enum { P_OBX = 0, P_OBY, P_OBZ, P_DX, P_DY, P_DZ, P_IX, P_IY, P_IZ, P_W, P_T, P_
  */
 __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                     const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, u32* __restrict__ p_exact_list,
-                                                                    float4* __restrict__ p_out, u32 service_lanes, u32 steps)
+                                                                    float4* __restrict__ p_out, u32 service_lanes, u32 steps, u32 max_steps, u32 max_steps_uncertain)
 {
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
 
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
             continue;
         }
 
-        if (kind == TGB_FAST_WALK) kind = tgb_fast_walk(&fr, &r, steps, (u32*)0, (u32*)0);
+        if (kind == TGB_FAST_WALK) kind = tgb_fast_walk(&fr, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain);
     }
     /* [2] cells (empty boxes and voxels) entered by the fast walk in this frame; the exact kernel adds its look-ups there and counts its DDA steps in [3]; [14] rays handed over */
     n_cells = __reduce_add_sync(0xFFFFFFFFu, n_cells);
@@ -215,13 +215,14 @@ extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane)
 {
     const u32 ctas_per_sm = (u32)max(1, min(16, tgbd_env_int("TGB_GI_FAST_CTAS_PER_SM", 8)));
     const u32 service_lanes = (u32)max(1, min(32, tgbd_env_int("TGB_GI_FAST_SERVICE_LANES", 8)));
-    const u32 steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_STEPS", 4));
+    const u32 steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_STEPS", 8));
+    const u32 max_steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_MAX_STEPS", (i32)TGB_FAST_MAX_STEPS)), max_steps_uncertain = (u32)max(1, tgbd_env_int("TGB_GI_FAST_MAX_STEPS_UNCERTAIN", (i32)TGB_FAST_MAX_STEPS_UNCERTAIN));
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
     k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count + 12, 2, 0u); /* handed over / fetched by the exact kernel */
     TGB_LAUNCH_CHECK(d);
     k_gi_trace_fast<<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
-                                                                                 service_lanes, steps);
+                                                                                 service_lanes, steps, max_steps, max_steps_uncertain);
     TGB_LAUNCH_CHECK(d);
     return tgbd_gi_pool_trace_list(d, far_plane, d->d_gi_exact, 12u);
 }
