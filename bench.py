@@ -123,9 +123,9 @@ C2FAR_FAR = 4000.0
 def build_scene(rank, n_ranks, workload="c2", host_bits=True):
     """Rank's shard. c2 / c4 / c2far: the 32 x 32 lattice of configs[1] (1,024 objects), dealt out over the ranks -- the world is the
     same at every N (strong scaling). c5: 12,288 objects out of a 384 x 32N lattice per rank, masks generated on the device (weak
-    scaling: the resident world grows with N). Ownership is interleaved over the lattice (cell (i, j) belongs to rank (i + j) % N):
-    every rank holds 1/N of what the camera sees instead of one rank holding all of it. The global lattice index decides seed,
-    angle and position."""
+    scaling: the resident world grows with N). The lattice cells are dealt out in order of their distance from the camera, boustrophedon
+    (scenes.deal_by_distance): every rank holds the same number of objects and an equal share of the near (large on screen) and far ones.
+    The global lattice index decides seed, angle and position."""
     from tg_b200 import scenes
     if workload == "c5":
         return scenes.config5_shard(rank, n_ranks, WIDTH, HEIGHT)
@@ -556,7 +556,7 @@ def gpu_arm(ctx, args, workload, steps, warmup, headline):
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": SCALING[workload], "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
             "config": {"workload": WORKLOADS[workload]
-                                   + (f"; the objects are dealt out over {world} ranks (interleaved ownership), GI split by screen tile, merge = "
+                                   + (f"; the objects are dealt out over {world} ranks (in order of distance from the camera, boustrophedon), GI split by screen tile, merge = "
                                       + ("one kernel over peer memory (min + winner's material per tile, NVLink)" if args.merge == "peer" else "ncclAllReduce(u64,min) + material reduce-scatter")
                                       if world > 1 else ""),
                        "rays_per_frame": rays_per_frame, "primary_rays": WIDTH * HEIGHT, "gi_rays": n_hit, "rank_primary_rays": world * WIDTH * HEIGHT,

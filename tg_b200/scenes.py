@@ -146,21 +146,39 @@ def config1(k=3, width=1280, height=720, dims=(16, 16, 16), with_materials=True)
     return SceneSpec(name=f"config1_k{k}", width=width, height=height, camera=cam, objects=[obj])
 
 
+def deal_by_distance(grid_x, grid_z, n_ranks, pitch_units=192.0, eye_xz=(0.0, 0.0)):
+    """Which rank holds lattice cell idx = j * grid_x + i: the cells in order of their distance from the camera's ground position,
+    dealt out boustrophedon (0 1 .. n-1 n-1 .. 1 0 ...). Every rank gets the same number of objects and an equal share of the near
+    (large on screen) and of the far ones -- what an engine that balances its GPUs by screen coverage would do. With the plain
+    interleave (i + j) % n the few nearest objects, which cover a quarter of the frame each, made one rank's K1 twice as long as the
+    mean (profiles/r03g_*)."""
+    idx = np.arange(grid_x * grid_z)
+    cx = (idx % grid_x - (grid_x - 1) / 2.0) * pitch_units - eye_xz[0]
+    cz = (idx // grid_x - (grid_z - 1) / 2.0) * pitch_units - eye_xz[1]
+    order = np.argsort(cx * cx + cz * cz, kind="stable")
+    pos = np.arange(len(idx)) % n_ranks
+    snake = np.where((np.arange(len(idx)) // n_ranks) % 2 == 0, pos, n_ranks - 1 - pos)
+    owner = np.empty(len(idx), dtype=np.int64)
+    owner[order] = snake
+    return owner
+
+
 def grid_scene(name, grid_x, grid_z, width, height, k=3, pitch_units=192.0, dims=(16, 8, 16), first_object=0, n_objects=None,
                with_bits=True, owner=None):
     """Objects on a grid_x x grid_z XZ lattice centred on the origin, y = 0 (configs 2-5). with_bits=False leaves the masks to
     the device generator (tg_raytracer_create_object_synthetic with the same seed idx + 1 and k): same bits, no host array.
-    owner=(rank, n_ranks) keeps the objects of one rank of an interleaved multi-GPU partition (seed, angle and position still
+    owner=(rank, n_ranks) keeps the objects of one rank of a multi-GPU partition (deal_by_distance; seed, angle and position still
     follow the global lattice index)."""
     total = grid_x * grid_z
     if n_objects is None:
         n_objects = total - first_object
     n = dims[0] * dims[1] * dims[2]
     objs = []
+    owner_of = deal_by_distance(grid_x, grid_z, owner[1], pitch_units) if owner is not None else None
     for idx in range(first_object, first_object + n_objects):
         i, j = idx % grid_x, idx // grid_x
-        if owner is not None and (i + j) % owner[1] != owner[0]:
-            continue  # interleaved ownership: rank r of n holds the lattice cells with (i + j) % n == r, 1/n of every neighbourhood
+        if owner is not None and owner_of[idx] != owner[0]:
+            continue
         cx = (i - (grid_x - 1) / 2.0) * pitch_units
         cz = (j - (grid_z - 1) / 2.0) * pitch_units
         objs.append(ObjectSpec(center=(cx, 0.0, cz), extent=(dims[0] * 8, dims[1] * 8, dims[2] * 8), angle=reference_object_angle(idx),
@@ -177,8 +195,8 @@ def config2(width=3840, height=2160, grid=32, k=3):
 def config5_shard(rank, n_ranks, width=3840, height=2160, k=3):
     """BASELINE configs[4]: rank's share of a 384 x (32 n_ranks) lattice of 16x8x16-cluster objects -- 12,288 objects
     = 25,165,824 clusters = 1.29e10 voxels per rank; 8 ranks = 98,304 objects, 201,326,592 clusters, 1.03e11 voxels (SURVEY.md
-    section 8d). Ownership is interleaved over the lattice ((i + j) % n_ranks), so every rank holds an equal part of whatever the
-    camera sees; a rank's objects are a contiguous range of GLOBAL cluster pointers (rank-major pointer space). The masks are
+    section 8d). The lattice cells are dealt out over the ranks in order of their distance from the camera (deal_by_distance), so every
+    rank holds an equal part of whatever the camera sees; a rank's objects are a contiguous range of GLOBAL cluster pointers (rank-major pointer space). The masks are
     generated on the device (seed = global lattice index + 1), nothing of that size exists on the host."""
     return grid_scene(f"config5_x{n_ranks}", 384, 32 * n_ranks, width, height, k=k, with_bits=False, owner=(rank, n_ranks))
 
