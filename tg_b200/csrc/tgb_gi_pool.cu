@@ -27,7 +27,7 @@
 /* shared-memory columns */
 enum { W_DX = 0, W_DY, W_DZ, W_PX, W_PY, W_PZ, W_TDX, W_TDY, W_TDZ, W_TMX, W_TMY, W_TMZ, W_CELL, W_VOX, W_DATA, W_SLOT };
 
-template <int K, int GRID>
+template <int K, int GRID, bool LIST>
 __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                     const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, const u32* __restrict__ p_list, u32 count_word,
                                                                     float4* __restrict__ p_out, u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot, u32 n_sms, u32 rounds)
@@ -41,18 +41,18 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
 
     /* the whole queue (p_list == NULL: p_q_count[0] rays, fetch counter [1]) or the slots k_gi_trace_fast handed over (tgb_gi_fast.cu:
      * p_q_count[count_word] entries of p_list, fetch counter [count_word + 1]) */
-    const u32 n_rays = p_q_count[count_word];
-    if (p_list == NULL && blockIdx.x == 0 && tid == 0) { atomicAdd(&p_q_count[10], n_rays); atomicAdd(&p_q_count[14], n_rays); } /* rays of the frame, summed over its bands; all of them traced exactly */
+    const u32 n_rays = p_q_count[LIST ? count_word : 0u];
+    if (!LIST && blockIdx.x == 0 && tid == 0) { atomicAdd(&p_q_count[10], n_rays); atomicAdd(&p_q_count[14], n_rays); } /* rays of the frame, summed over its bands; all of them traced exactly */
     /* CTAs beyond what the queue can feed (a band, a screen tile of a sharded frame) leave at once. min_rays_per_slot > 1 would keep
      * even fewer CTAs so that every ray slot sees several rays; measured on a 272-row tile (873 k rays): 0.41 ms with 1, 0.49 with 4, 0.69
      * with 8 -- with few rays the longest dependent chains set the duration and parallelism is all that helps (profiles/r02k) */
-    if (p_list == NULL && blockIdx.x >= n_sms && (u64)blockIdx.x * (TGB_POOL_THREADS * K) * min_rays_per_slot >= n_rays) return;
+    if (!LIST && blockIdx.x >= n_sms && (u64)blockIdx.x * (TGB_POOL_THREADS * K) * min_rays_per_slot >= n_rays) return;
     /* The handed-over rays are few and long (every one walks out of the box): what bounds this pass is how many of them ONE warp holds.
      * A warp therefore takes its fair share of the list per round (all CTAs of the grid are resident) and comes back for more only when
      * those are decided; the whole queue (p_list == NULL) has no quota. */
     /* `rounds` (tuning, whole-queue mode): a warp takes 1 / rounds of its fair share at a time, so that the last grabs of a small batch (a screen tile) are small */
     const u32 n_warps = gridDim.x * (TGB_POOL_THREADS / 32u);
-    const u32 quota = p_list ? (n_rays + n_warps - 1u) / n_warps + 1u : (rounds ? (n_rays + n_warps * rounds - 1u) / (n_warps * rounds) + 1u : 0xFFFFFFFFu);
+    const u32 quota = LIST ? (n_rays + n_warps - 1u) / n_warps + 1u : 0xFFFFFFFFu; /* (`rounds`: the same for the whole queue, measured worse on tile batches, profiles/r03f; compiled out) */
     u32 round_left = quota;
 
     u32 kinds = 0; /* 4 bits per ray slot, all IDLE */
@@ -68,13 +68,13 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
             const u32 kd = (kinds >> (4 * k)) & 15u;
             has_tree |= (kd == TGB_RAY_TREE) ? 1u : 0u;
             has_dda |= (kd == TGB_RAY_DDA) ? 1u : 0u;
-            n_svc += ((kd >= TGB_RAY_HIT) | ((kd == TGB_RAY_IDLE) & !exhausted & (round_left != 0u))) ? 1u : 0u;
+            n_svc += ((kd >= TGB_RAY_HIT) | ((kd == TGB_RAY_IDLE) & !exhausted & (!LIST || round_left != 0u))) ? 1u : 0u;
         }
         const u32 counts = __reduce_add_sync(0xFFFFFFFFu, has_tree | (has_dda << 8) | (n_svc << 16));
         const u32 n_tree = counts & 0xFFu, n_dda = (counts >> 8) & 0xFFu, n_service = counts >> 16;
         if (n_tree + n_dda == 0 && n_service == 0)
         {
-            if (!exhausted && round_left == 0u) { round_left = quota; continue; } /* the round's rays are decided: next round */
+            if (LIST && !exhausted && round_left == 0u) { round_left = quota; continue; } /* the round's rays are decided: next round */
             break; /* queue drained and every ray finished */
         }
 
@@ -115,21 +115,21 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                     kd = tgb_gi_hit_test(&fr, tgb_v3(q0.x, q0.y, q0.z), tgb_v3(SF(W_DX, k), SF(W_DY, k), SF(W_DZ, k)), child_min,
                                          (i32)(vox & 31u), (i32)((vox >> 5) & 31u), (i32)((vox >> 10) & 31u));
                 }
-                if (!exhausted && round_left != 0u)
+                if (!exhausted && (!LIST || round_left != 0u))
                 {
                     u32 idle = __ballot_sync(0xFFFFFFFFu, kd == TGB_RAY_IDLE);
-                    if ((u32)__popc(idle) > round_left) idle &= (1u << __fns(idle, 0u, (int)round_left + 1)) - 1u; /* the first round_left idle lanes */
+                    if (LIST && (u32)__popc(idle) > round_left) idle &= (1u << __fns(idle, 0u, (int)round_left + 1)) - 1u; /* the first round_left idle lanes */
                     if (idle)
                     {
                         const u32 n = (u32)__popc(idle);
                         u32 base = 0;
                         const u32 leader = (u32)(__ffs(idle) - 1);
-                        if (lane == leader) base = atomicAdd(&p_q_count[count_word + 1u], n);
+                        if (lane == leader) base = atomicAdd(&p_q_count[LIST ? count_word + 1u : 1u], n);
                         base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
                         const u32 mine = base + (u32)__popc(idle & ((1u << lane) - 1u));
                         if (kd == TGB_RAY_IDLE && ((idle >> lane) & 1u) && mine < n_rays)
                         {
-                            const u32 queue_slot = p_list ? __ldcs(&p_list[mine]) : mine;
+                            const u32 queue_slot = LIST ? __ldcs(&p_list[mine]) : mine;
                             const float4 q0 = __ldcg(&p_q0[queue_slot]), q1 = __ldcs(&p_q1[queue_slot]); /* q0 is read again when the ray is decided (L2), q1 never */
                             const v3 d = tgb_v3(q1.x, q1.y, q1.z);
                             v3 position, t_delta; u32 flags;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                             kd = TGB_RAY_TREE;
                         }
                         exhausted = base + n >= n_rays;
-                        if (quota != 0xFFFFFFFFu) round_left -= n;
+                        if (LIST) round_left -= n;
                     }
                 }
                 kinds = (kinds & ~(15u << (4 * k))) | (kd << (4 * k));
@@ -217,21 +217,21 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
  * Launch for one band of rays (called by tgbd__shade_launch, tgb_shade.cu, after k_shade queued them). Tuning knobs are read
  * from the environment once (benchmark sweeps only): rays per lane, CTAs per SM, phase budgets, service threshold.
  */
-template <int K, int GRID>
+template <int K, int GRID, bool LIST>
 static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, const u32* p_list, u32 count_word, u32 rounds, u32 ctas_per_sm, u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot)
 {
     const size_t smem = (size_t)TGB_POOL_WORDS * K * TGB_POOL_THREADS * sizeof(u32);
     static bool attr_set = false;
     if (!attr_set)
     {
-        TGB_CUDA(cudaFuncSetAttribute(k_gi_trace_pool<K, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TGB_CUDA(cudaFuncSetAttribute(k_gi_trace_pool<K, GRID, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     /* resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA) and the 2048-thread limit */
     u32 fit = (u32)((227u * 1024u) / (smem + 1024u));
     if (fit > 2048u / TGB_POOL_THREADS) fit = 2048u / TGB_POOL_THREADS;
     if (ctas_per_sm == 0 || ctas_per_sm > fit) ctas_per_sm = fit < 8u ? fit : 8u;
-    k_gi_trace_pool<K, GRID><<<d->n_sms * ctas_per_sm, TGB_POOL_THREADS, smem, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
+    k_gi_trace_pool<K, GRID, LIST><<<d->n_sms * ctas_per_sm, TGB_POOL_THREADS, smem, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
                                                                                      service_slots, dda_bias, tree_reps, dda_steps, min_rays_per_slot, d->n_sms, rounds);
     TGB_LAUNCH_CHECK(d);
     return TG_TRUE;
@@ -253,16 +253,18 @@ extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, cons
      * stage -- the look-ups are concentrated on few cells and hit L1 either way; what misses is the voxel rows. Off; kept as the measured record. */
     const int grid16 = tgbd_env_int("TGB_GI_POOL_GRID16", 0);
     fr.p_grid16 = (const unsigned short*)(d->svo.d_top_grid + TGB_TOP_GRID_CELLS + 1);
-#define TGB_POOL_CASE(KK) case KK: return grid16 ? tgbd__gi_pool_launch<KK, 1>(d, fr, p_list, count_word, rounds, ctas_per_sm, service_env > 0 ? (u32)service_env : (KK == 3 ? 64u : 16u * KK), dda_bias, tree_reps, dda_steps, min_rays_per_slot) \
-                                                : tgbd__gi_pool_launch<KK, 0>(d, fr, p_list, count_word, rounds, ctas_per_sm, service_env > 0 ? (u32)service_env : (KK == 3 ? 64u : 16u * KK), dda_bias, tree_reps, dda_steps, min_rays_per_slot)
+#define TGB_POOL_ARGS(KK) d, fr, p_list, count_word, rounds, ctas_per_sm, service_env > 0 ? (u32)service_env : (KK == 3 ? 64u : 16u * KK), dda_bias, tree_reps, dda_steps, min_rays_per_slot
+#define TGB_POOL_CASE(KK) case KK: return p_list ? tgbd__gi_pool_launch<KK, 0, true>(TGB_POOL_ARGS(KK)) \
+                                                 : (grid16 ? tgbd__gi_pool_launch<KK, 1, false>(TGB_POOL_ARGS(KK)) : tgbd__gi_pool_launch<KK, 0, false>(TGB_POOL_ARGS(KK)))
     switch (rays_per_lane)
     {
     TGB_POOL_CASE(1);
     TGB_POOL_CASE(2);
     TGB_POOL_CASE(3);
     TGB_POOL_CASE(4);
-    default: return tgbd__gi_pool_launch<3, 1>(d, fr, p_list, count_word, rounds, ctas_per_sm, service_env > 0 ? (u32)service_env : 64u, dda_bias, tree_reps, dda_steps, min_rays_per_slot);
+    default: return p_list ? tgbd__gi_pool_launch<1, 0, true>(TGB_POOL_ARGS(1)) : tgbd__gi_pool_launch<3, 0, false>(TGB_POOL_ARGS(3));
     }
+#undef TGB_POOL_ARGS
 #undef TGB_POOL_CASE
 }
 
