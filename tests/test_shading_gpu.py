@@ -74,6 +74,34 @@ def test_full_frame_through_render(gpu, oracle):
         rt.destroy()
 
 
+@pytest.mark.parametrize("make,seed", [(lambda: scenes.small_grid(), 3), (lambda: scenes.config1(k=3, width=320, height=180), 1),
+                                       (lambda: scenes.grid_scene("g5", 5, 5, 480, 270, k=3), 7)])
+def test_certified_fast_walk_gives_the_exact_kernels_frame(gpu, oracle, make, seed):
+    """TGB_GI_KERNEL=3 (tgb_gi_fast.cu: the certified fast walk decides most rays, the exact kernel the ones it hands over; not the default)
+    must produce the frame of the exact kernel bit for bit, and the oracle's within the tolerance."""
+    s = make()
+    vis, svo, want = oracle_frame(oracle, s, gi=True, seed=seed)
+    oracle.svo_destroy(svo)
+    rt = from_scene(s)
+    try:
+        rt.set_gi(True, seed)
+        rt.clear(); rt.render(); rt.synchronize()
+        exact = rt.read_radiance()
+        t_exact = rt.timings()
+        os.environ["TGB_GI_KERNEL"] = "3"
+        try:
+            rt.render_shading(); rt.synchronize()
+            fast = rt.read_radiance()
+            t_fast = rt.timings()
+        finally:
+            os.environ.pop("TGB_GI_KERNEL", None)
+        assert np.array_equal(exact.view(np.uint32), fast.view(np.uint32)), f"{int((exact != fast).any(axis=-1).sum())} pixels differ"
+        close(fast, want, "fast walk")
+        assert t_fast["n_gi_rays"] == t_exact["n_gi_rays"] > 0 and t_fast["n_gi_rays_exact"] < t_fast["n_gi_rays"]
+    finally:
+        rt.destroy()
+
+
 @pytest.mark.parametrize("name", ["config1_k3_320x180", "config1_k1_320x180", "small_grid3_320x180"])
 def test_against_committed_golden_fixtures(gpu, name):
     from tests.golden.make_golden import CASES
