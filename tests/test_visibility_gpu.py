@@ -41,6 +41,21 @@ def test_against_committed_golden_fixtures(gpu, name):
     assert np.array_equal(got, want), describe_mismatch(got, want)
 
 
+@pytest.mark.parametrize("make", [lambda: scenes.config1(k=3), lambda: scenes.config1(k=1, width=640, height=360), lambda: scenes.small_grid(),
+                                  lambda: scenes.small_grid(grid=5, width=333, height=177, dims=(3, 5, 2))])
+def test_masks_staged_in_shared_memory_variant_is_bit_exact(gpu, oracle, make):
+    """TGB_K1_STAGE_MASKS=1 (cp.async copies of the cluster masks into shared memory, one per group of lanes that march the same cluster;
+    north_star (a) as written, not the default): pure data movement, the words must be those of the default kernel and of the oracle."""
+    s = make()
+    want = oracle_visibility(oracle, s)
+    os.environ["TGB_K1_STAGE_MASKS"] = "1"
+    try:
+        got, _ = gpu_visibility(s)
+    finally:
+        os.environ.pop("TGB_K1_STAGE_MASKS", None)
+    assert np.array_equal(got, want), describe_mismatch(got, want)
+
+
 def test_rotated_objects_grid_brute_force(gpu, oracle):
     check(oracle, scenes.small_grid(), oracle.VIS_BRUTE_FORCE)
     check(oracle, scenes.small_grid(grid=5, width=333, height=177, dims=(3, 5, 2)), oracle.VIS_BRUTE_FORCE)  # ragged resolution

@@ -144,14 +144,12 @@ TGB_HD bool tgb_cluster_candidate(const tgb_object_frame& f, const tgb_ray_in_ob
  * Second half, visibility.frag:83-191: the 8^3 Amanatides-Woo march from `enter`. Returns the index 64 z + 8 y + x of the first solid
  * voxel the shader's DDA meets, or -1 when the ray leaves the cluster without meeting one.
  */
-TGB_HD i32 tgb_cluster_find(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 enter,
-                            const u32* p_cluster_pointers, const u32* p_masks)
+/* STAGED: p_slices points at a copy of the mask in shared memory (k_visibility's TGB_K1_STAGE_MASKS variant), read with plain loads */
+template <bool STAGED>
+TGB_HD i32 tgb_cluster_find_in(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 enter, const tgb_slice* p_slices)
 {
     const v3 o = tgb_hoist_cluster_origin(&f, cx, cy, cz);
     const v3 d = r.d;
-    const u32 cluster_pointer = f.first_cluster_pointer + cx + f.nx * (cy + f.ny * cz);
-    const u32 cluster_idx = TGB_LDG(&p_cluster_pointers[cluster_pointer]);
-    const tgb_slice* p_slices = reinterpret_cast<const tgb_slice*>(p_masks + (u64)cluster_idx * TG_CLUSTER_MASK_WORDS);
 
     /* visibility.frag:83-137 */
     v3 hit;
@@ -173,15 +171,16 @@ TGB_HD i32 tgb_cluster_find(const tgb_object_frame& f, const tgb_ray_in_object& 
     /* visibility.frag:141-191; the 64-bit z-slice (words 2z, 2z+1) is fetched once per z */
     i32 z_cached = -1;
     u32 lo = 0, hi = 0;
+    i32 found = -1;
     for (;;)
     {
         if (z != z_cached)
         {
-            const tgb_slice s = TGB_LDG(&p_slices[z]);
+            const tgb_slice s = STAGED ? p_slices[z] : TGB_LDG(&p_slices[z]);
             lo = s.x; hi = s.y; z_cached = z;
         }
         const u32 word = (y & 4) ? hi : lo;
-        if ((word >> (((y & 3) << 3) + x)) & 1u) return 64 * z + 8 * y + x;
+        if ((word >> (((y & 3) << 3) + x)) & 1u) { found = 64 * z + 8 * y + x; break; }
         if (t_max_x < t_max_y)
         {
             if (t_max_x < t_max_z) { t_max_x += r.t_delta_x; x += step_x; if (x < 0 || x >= 8) break; }
@@ -193,7 +192,15 @@ TGB_HD i32 tgb_cluster_find(const tgb_object_frame& f, const tgb_ray_in_object& 
             else                   { t_max_z += r.t_delta_z; z += step_z; if (z < 0 || z >= 8) break; }
         }
     }
-    return -1;
+    return found;
+}
+
+TGB_HD i32 tgb_cluster_find(const tgb_object_frame& f, const tgb_ray_in_object& r, u32 cx, u32 cy, u32 cz, f32 enter,
+                            const u32* p_cluster_pointers, const u32* p_masks)
+{
+    const u32 cluster_pointer = f.first_cluster_pointer + cx + f.nx * (cy + f.ny * cz);
+    const u32 cluster_idx = TGB_LDG(&p_cluster_pointers[cluster_pointer]);
+    return tgb_cluster_find_in<false>(f, r, cx, cy, cz, enter, reinterpret_cast<const tgb_slice*>(p_masks + (u64)cluster_idx * TG_CLUSTER_MASK_WORDS));
 }
 
 /*

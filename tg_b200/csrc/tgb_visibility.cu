@@ -284,10 +284,22 @@ __global__ void __launch_bounds__(1024) k_sort_frames(const tgb_object_frame* __
  * One ray against one object: enumerate, slice by slice along the dominant axis of d (front to
  * back), every cluster whose box inflated by eps the ray can touch, and visit each.
  */
-template <bool REGROUP, bool DEFER>
+/* 16 bytes global -> shared without passing through registers (LDGSTS) */
+__device__ __forceinline__ void tgb_k1_cp_async16(void* p_shared, const void* p_global)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((u32)__cvta_generic_to_shared(p_shared)), "l"(p_global) : "memory");
+}
+
+/*
+ * STAGE (TGB_K1_STAGE_MASKS=1, the measured alternative north_star (a) names; off by default): the 64-byte mask of the cluster about to be
+ * marched is copied into shared memory by cp.async -- once per group of lanes that march the SAME cluster (__match_any_sync on the cluster
+ * index: neighbouring rays mostly do), by the group's first lane -- and the march reads its z-slices from there. Bit-identical by
+ * construction (pure data movement).
+ */
+template <bool REGROUP, bool DEFER, bool STAGE>
 __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 dir_ws, f32 far_plane,
                                                  const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
-                                                 u32 global_pointer_base, u64& best, f32& t_skip)
+                                                 u32 global_pointer_base, u64& best, f32& t_skip, u32* p_warp_masks)
 {
     const f32 e = f.eps;
     /* ws2ms * (dir_ws, 0) before normalisation (tgb_hoist_direction) */
@@ -427,7 +439,27 @@ __device__ __forceinline__ void tgb_trace_object(const tgb_object_frame& f, v3 d
                 if (tgb_cluster_candidate(f, r, cx, cy, cz, t_skip, &enter)) { have = true; break; }
             }
             if (!have) break;
-            const i32 voxel = tgb_cluster_find(f, r, cx, cy, cz, enter, p_cluster_pointers, p_masks);
+            i32 voxel;
+            if (STAGE)
+            {
+                const u32 lane = threadIdx.x & 31u;
+                const u32 cluster_idx = __ldg(&p_cluster_pointers[f.first_cluster_pointer + cx + f.nx * (cy + f.ny * cz)]);
+                const u32 peers = __match_any_sync(__activemask(), cluster_idx); /* the lanes about to march this cluster */
+                const u32 leader = (u32)(__ffs(peers) - 1);
+                u32* p_slot = p_warp_masks + leader * TG_CLUSTER_MASK_WORDS;
+                if (lane == leader)
+                {
+                    const u32* p_src = p_masks + (u64)cluster_idx * TG_CLUSTER_MASK_WORDS;
+                    tgb_k1_cp_async16(p_slot, p_src); tgb_k1_cp_async16(p_slot + 4, p_src + 4);
+                    tgb_k1_cp_async16(p_slot + 8, p_src + 8); tgb_k1_cp_async16(p_slot + 12, p_src + 12);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp(peers);
+                voxel = tgb_cluster_find_in<true>(f, r, cx, cy, cz, enter, reinterpret_cast<const tgb_slice*>(p_slot));
+                __syncwarp(peers); /* the leader's next candidate reuses its slot */
+            }
+            else voxel = tgb_cluster_find(f, r, cx, cy, cz, enter, p_cluster_pointers, p_masks);
             if (voxel >= 0)
             {
                 if (!can_defer) tgb_cluster_word(f, r, cx, cy, cz, voxel, far_plane, global_pointer_base, best, t_skip);
@@ -494,7 +526,7 @@ struct tgb_k1_shard_args
     u32 tiles_x;
 };
 
-template <int MIN_CTAS, bool REGROUP, bool SHARDED, bool DEFER>
+template <int MIN_CTAS, bool REGROUP, bool SHARDED, bool DEFER, bool STAGE = false>
 __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const tgb_object_frame* __restrict__ p_frames, const u32* __restrict__ p_count,
                                                                tg_camera_rays cam, u32 w, u32 h,
                                                                const u32* __restrict__ p_cluster_pointers, const u32* __restrict__ p_masks,
@@ -503,6 +535,7 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
 {
     __shared__ u32 s_list[TGB_K1_THREADS];
     __shared__ u32 s_warp_count[TGB_K1_THREADS / 32];
+    __shared__ __align__(16) u32 s_staged_masks[STAGE ? TGB_K1_THREADS * TG_CLUSTER_MASK_WORDS : 4]; /* STAGE: one 64-byte slot per lane */
 
     const u32 n_visible = p_count[0];
     if (n_visible == 0)
@@ -578,7 +611,8 @@ __global__ void __launch_bounds__(TGB_K1_THREADS, MIN_CTAS) k_visibility(const t
                 if (sorted && __all_sync(TGB_FULL_MASK, behind_best)) { warp_done = true; break; }
                 if (f.x1 < (i32)wx0 || f.x0 > wx1 || f.y1 < (i32)wy0 || f.y0 > wy1) continue; /* warp-uniform */
                 if (behind_best || (i32)px < f.x0 || (i32)px > f.x1 || (i32)py < f.y0 || (i32)py > f.y1) continue;
-                tgb_trace_object<REGROUP, DEFER>(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip);
+                tgb_trace_object<REGROUP, DEFER, STAGE>(f, dir_ws, cam.far_plane, p_cluster_pointers, p_masks, global_pointer_base, best, t_skip,
+                                                        s_staged_masks + (STAGE ? warp * 32u * TG_CLUSTER_MASK_WORDS : 0u));
             }
         }
         if (base + TGB_K1_THREADS < n_visible) __syncthreads(); /* s_list is rewritten by the next window */
@@ -636,6 +670,13 @@ extern "C" b32 tgbd_render_visibility(struct tgb_device* d, const tg_camera_rays
      * Bit-identical, measured SLOWER (c2: 0.80 ms against 0.72; c2far 1.12 against 0.98): the bound, the second origin evaluation and the candidates the
      * looser bound admits cost more than the idle lanes of the immediate form. Off; kept as the measured record. */
     const int defer = tgbd_env_int("TGB_K1_DEFER_WORD", 0);
+    /* TGB_K1_STAGE_MASKS=1: cluster masks staged in shared memory by cp.async, one copy per group of lanes that march the same cluster
+     * (north_star (a) as written). Bit-identical; measured against the default in profiles/r03p_*: the 8-byte slice loads it replaces already hit L1
+     * 96 % of the time, so the copy's latency (waited for before the march can start) is all it adds. Off; kept as the measured record. */
+    if (tgbd_env_int("TGB_K1_STAGE_MASKS", 0) && !sharded && k1_kernel != 2)
+        k_visibility<5, true, false, false, true><<<grid, TGB_K1_THREADS, 0, d->stream>>>(d->d_frames_sorted, d->d_visible_count, *p_cam, d->width, d->height,
+                                                                                           d->d_cluster_pointers, d->d_masks, d->global_pointer_base, d->d_vis, d->n_ranks, d->tile_rows, fallback_only, sh);
+    else
     if (sharded)      { if (defer) TGB_K1_LAUNCH(5, true, true, true); else TGB_K1_LAUNCH(5, true, true, false); }
     else if (regroup)
     {

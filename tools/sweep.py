@@ -56,6 +56,7 @@ FAST_SWEEP = [
 K1_SWEEP = [
     {"TGB_K1_KERNEL": 1},                                   # round-1 kernel: one pixel per lane
     {"TGB_K1_KERNEL": 2},                                   # pool, defaults (K = 2, 4 CTAs / SM)
+    {"TGB_K1_STAGE_MASKS": 1},                              # cluster masks staged in shared memory by cp.async (north_star (a) as written)
     {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 1},
     {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 1, "TGB_K1_POOL_MIN_CTAS": 3},
     {"TGB_K1_KERNEL": 2, "TGB_K1_PIXELS_PER_LANE": 2, "TGB_K1_POOL_MIN_CTAS": 3},
