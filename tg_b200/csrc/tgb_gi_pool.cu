@@ -30,7 +30,7 @@ enum { W_DX = 0, W_DY, W_DZ, W_PX, W_PY, W_PZ, W_TDX, W_TDY, W_TDZ, W_TMX, W_TMY
 template <int K, int GRID, bool LIST>
 __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                     const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, const u32* __restrict__ p_list, u32 count_word,
-                                                                    float4* __restrict__ p_out, u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot, u32 n_sms, u32 rounds)
+                                                                    float4* __restrict__ p_out, u32 service_slots, u32 dda_bias, u32 tree_reps, u32 dda_steps, u32 min_rays_per_slot, u32 n_sms, u32 tail_boost)
 {
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
 
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
      * those are decided; the whole queue (p_list == NULL) has no quota. */
     /* `rounds` (tuning, whole-queue mode): a warp takes 1 / rounds of its fair share at a time, so that the last grabs of a small batch (a screen tile) are small */
     const u32 n_warps = gridDim.x * (TGB_POOL_THREADS / 32u);
-    const u32 quota = LIST ? (n_rays + n_warps - 1u) / n_warps + 1u : 0xFFFFFFFFu; /* (`rounds`: the same for the whole queue, measured worse on tile batches, profiles/r03f; compiled out) */
+    const u32 quota = LIST ? (n_rays + n_warps - 1u) / n_warps + 1u : 0xFFFFFFFFu; /* (the same for the whole queue was measured worse on tile batches, profiles/r03f) */
     u32 round_left = quota;
 
     u32 kinds = 0; /* 4 bits per ray slot, all IDLE */
@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
         }
         const u32 counts = __reduce_add_sync(0xFFFFFFFFu, has_tree | (has_dda << 8) | (n_svc << 16));
         const u32 n_tree = counts & 0xFFu, n_dda = (counts >> 8) & 0xFFu, n_service = counts >> 16;
+        /* the last few rays of a warp are the long ones and nobody waits behind them: longer phases, less scheduling per step */
+        const u32 boost = (n_tree + n_dda <= 6u) ? tail_boost : 1u;
         if (n_tree + n_dda == 0 && n_service == 0)
         {
             if (LIST && !exhausted && round_left == 0u) { round_left = quota; continue; } /* the round's rays are decided: next round */
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
                     x = (i32)(vox & 31u); y = (i32)((vox >> 5) & 31u); z = (i32)((vox >> 10) & 31u);
                     t_max = tgb_v3(SF(W_TMX, k), SF(W_TMY, k), SF(W_TMZ, k));
                 }
-                const u32 kd = tgb_gi_dda_phase(p_block, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
+                const u32 kd = tgb_gi_dda_phase(p_block, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps * boost, &n_steps);
                 S(W_TMX, k) = __float_as_uint(t_max.x); S(W_TMY, k) = __float_as_uint(t_max.y); S(W_TMZ, k) = __float_as_uint(t_max.z);
                 S(W_VOX, k) = ((u32)x & 31u) | (((u32)y & 31u) << 5) | (((u32)z & 31u) << 10) | (flags << 16);
                 kinds = (kinds & ~(15u << (4 * k))) | (kd << (4 * k));
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
             u32 flags = vox >> 16, cell = S(W_CELL, k), data = 0;
             v3 position = tgb_v3(SF(W_PX, k), SF(W_PY, k), SF(W_PZ, k));
             const u32 kd = tgb_gi_tree_phase_t<GRID>(&fr, tgb_v3(SF(W_DX, k), SF(W_DY, k), SF(W_DZ, k)), tgb_v3(SF(W_TDX, k), SF(W_TDY, k), SF(W_TDZ, k)),
-                                             &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
+                                             &position, &cell, &flags, &data, tree_reps * boost, &n_visits, &n_advances);
             S(W_PX, k) = __float_as_uint(position.x); S(W_PY, k) = __float_as_uint(position.y); S(W_PZ, k) = __float_as_uint(position.z);
             S(W_CELL, k) = cell;
             S(W_VOX, k) = (vox & 0xFFFFu) | (flags << 16);
@@ -246,7 +248,7 @@ extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, cons
     const u32 dda_bias = (u32)tgbd_env_int("TGB_GI_POOL_DDA_BIAS", 0);
     const u32 min_rays_per_slot = (u32)max(1, tgbd_env_int("TGB_GI_POOL_MIN_RAYS_PER_SLOT", 1));
     const int service_env = tgbd_env_int("TGB_GI_POOL_SERVICE_SLOTS", 0);
-    const u32 rounds = (u32)max(0, tgbd_env_int("TGB_GI_POOL_ROUNDS", 0));
+    const u32 rounds = (u32)max(1, tgbd_env_int("TGB_GI_POOL_TAIL_BOOST", 1)); /* phase budgets x this once at most 6 lanes of a warp still hold a working ray */
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
     /* TGB_GI_POOL_GRID16=1 reads the 16-bit form of the table (half the footprint in what L1 the pool leaves): measured 1.381 vs 1.383 ms for the
