@@ -76,6 +76,8 @@ def lib():
         L.tgo_intersect_aabb_obb_ignore_contact.restype = T.b32
         L.tgo_shade.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, C.POINTER(T.u64), C.POINTER(T.tg_svo),
                                 T.u32, T.u32, T.u32, T.u32, T.u32, T.u32, C.POINTER(T.f32)]
+        L.tgo_shade_gi_rays.argtypes = [C.POINTER(tgo_scene_view), C.POINTER(T.tg_camera_rays), T.u32, T.u32, C.POINTER(T.u64), C.POINTER(T.tg_svo),
+                                        T.u32, T.u32, T.u32, T.u32, C.POINTER(T.f32)]
         L.tgo_present_bgra8.argtypes = [C.POINTER(T.f32), T.u64, C.POINTER(T.u32)]
         L.tgo_simplex_noise.argtypes = [T.f32, T.f32, T.f32]
         L.tgo_simplex_noise.restype = T.f32
@@ -267,6 +269,16 @@ def shade(view, rays, w, h, vis, svo=None, gi=False, frame_seed=1, debug=0, y0=0
     lib().tgo_shade(C.byref(view.view), C.byref(rays), w, h, T.ptr(vis, T.u64), C.byref(svo) if svo is not None else None,
                     1 if gi else 0, frame_seed, debug, y0, h if y1 is None else y1, ystep, T.ptr(out, T.f32))
     return out
+
+
+def gi_rays(view, rays, w, h, vis, svo, frame_seed=1, y0=0, y1=None, ystep=1):
+    """the secondary rays shade(..., gi=True) traces: (origins [n, 3], directions [n, 3]) of the pixels of those rows that shoot one"""
+    out = np.zeros((h, w, 6), dtype=np.float32)
+    vis = np.ascontiguousarray(vis, dtype=np.uint64)
+    lib().tgo_shade_gi_rays(C.byref(view.view), C.byref(rays), w, h, T.ptr(vis, T.u64), C.byref(svo), frame_seed, y0, h if y1 is None else y1, ystep, T.ptr(out, T.f32))
+    out = out.reshape(-1, 6)
+    out = out[(out[:, 3:] != 0).any(axis=1)]
+    return np.ascontiguousarray(out[:, :3]), np.ascontiguousarray(out[:, 3:])
 
 
 def present(radiance):

@@ -95,6 +95,10 @@ void tgo_procedural_solid_bits(u32 object_idx, v3u dims, u32* p_out);
 void tgo_shade(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, const u64* p_vis, const tg_svo* p_svo_or_null,
                u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 y0, u32 y1, u32 ystep, f32* p_out_rgba);
 
+/* the secondary rays tgo_shade traces for those rows (6 floats per pixel: origin, direction; direction 0 = no ray) -- workload studies */
+void tgo_shade_gi_rays(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, const u64* p_vis, const tg_svo* p_svo,
+                       u32 frame_seed, u32 y0, u32 y1, u32 ystep, f32* p_out_rays);
+
 /* present.frag + B8G8R8A8_UNORM conversion of n_pixels RGBA32F pixels (see tgo_shade.c) */
 void tgo_present_bgra8(const f32* p_rgba, u64 n_pixels, u32* p_out);
 

@@ -100,7 +100,7 @@ static void tgo__hash_color(u32 v, f32* p_rgba)
 }
 
 static void tgo__shade_pixel(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, u64 packed_data, const tg_svo* p_svo,
-                             u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 px, u32 py, f32* p_rgba)
+                             u32 gi_enabled, u32 frame_seed, u32 debug_visualization, u32 px, u32 py, f32* p_rgba, f32* p_gi_ray_or_null)
 {
     /* shading.frag:116-120 */
     const f32 depth_24b           = (f32)(packed_data >> TG_VIS_DEPTH_SHIFT) / TG_VIS_DEPTH_SCALE;
@@ -226,6 +226,11 @@ static void tgo__shade_pixel(const tgo_scene_view* p_scene, const tg_camera_rays
                 if (tgo_v3_dot(c, normal_ws) > 0.0f) { dir = c; break; }
             }
             const v3 origin = tgo_v3_add(hit_position_ws, tgo_v3_mulf(dir, 1.73205080757f));
+            if (p_gi_ray_or_null)
+            {
+                p_gi_ray_or_null[0] = origin.x; p_gi_ray_or_null[1] = origin.y; p_gi_ray_or_null[2] = origin.z;
+                p_gi_ray_or_null[3] = dir.x; p_gi_ray_or_null[4] = dir.y; p_gi_ray_or_null[5] = dir.z;
+            }
             v3 hp, hn; u32 node_idx, voxel_idx;
             const f32 depth2 = tgo_svo_traverse_glsl(p_svo, p_cam->far_plane, origin, dir, &hp, &hn, &node_idx, &voxel_idx);
             visibility = depth2 < 1.0f ? 0.0f : 1.0f;
@@ -252,7 +257,31 @@ void tgo_shade(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w
         for (u32 px = 0; px < w; px++)
         {
             const size_t i = (size_t)py * w + px;
-            tgo__shade_pixel(p_scene, p_cam, w, h, p_vis[i], p_svo_or_null, gi_enabled, frame_seed, debug_visualization, px, (u32)py, &p_out_rgba[i * 4]);
+            tgo__shade_pixel(p_scene, p_cam, w, h, p_vis[i], p_svo_or_null, gi_enabled, frame_seed, debug_visualization, px, (u32)py, &p_out_rgba[i * 4], NULL);
+        }
+    }
+}
+
+/*
+ * The secondary rays tgo_shade traces (tgvk_raytracer.c:1405-1419 recipe), for tools that study the GI kernels' workload on the host:
+ * p_out_rays[6 * pixel] = origin, direction; a pixel that shoots no ray (sky, zero normal) keeps direction (0, 0, 0).
+ */
+void tgo_shade_gi_rays(const tgo_scene_view* p_scene, const tg_camera_rays* p_cam, u32 w, u32 h, const u64* p_vis, const tg_svo* p_svo,
+                       u32 frame_seed, u32 y0, u32 y1, u32 ystep, f32* p_out_rays)
+{
+    if (y1 > h) y1 = h;
+    if (ystep == 0) ystep = 1;
+    const i64 n_rows = y1 > y0 ? ((i64)(y1 - y0) + ystep - 1) / ystep : 0;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (i64 row = 0; row < n_rows; row++)
+    {
+        const i64 py = (i64)y0 + row * ystep;
+        for (u32 px = 0; px < w; px++)
+        {
+            const size_t i = (size_t)py * w + px;
+            f32 rgba[4];
+            for (u32 k = 0; k < 6; k++) p_out_rays[i * 6 + k] = 0.0f;
+            tgo__shade_pixel(p_scene, p_cam, w, h, p_vis[i], p_svo, 1, frame_seed, TG_DEBUG_SHOW_NONE, px, (u32)py, rgba, &p_out_rays[i * 6]);
         }
     }
 }

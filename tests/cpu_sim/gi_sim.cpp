@@ -192,3 +192,76 @@ void tgbsim_gi_fast_steps(const f32* p_bmin, const f32* p_bmax, f32 far_plane, c
     }
 }
 }
+
+extern "C" {
+
+/*
+ * The coarser tiling of the fast walk (tgb_gi_fast.cuh, second half) built on the host with the per-cell passes the kernels
+ * k_fast_tile_* run (tgb_gi_fast.cu): p_cells[32^3] from the flattened tree, p_bricks[64 * n_leaves] from the leaf blocks' voxels.
+ */
+void tgbsim_fast_tiling(const u32* p_grid, const u32* p_voxels, u32 n_leaves, u32* p_cells, unsigned short* p_bricks)
+{
+    const u32 N = TGB_TOP_GRID_DIM;
+    u32* p1 = (u32*)malloc(TGB_TOP_GRID_CELLS * sizeof(u32));
+    u32* p2 = (u32*)malloc(TGB_TOP_GRID_CELLS * sizeof(u32));
+    auto occ = [&](u32 x, u32 y, u32 z) { return (p_grid[(z << 10) | (y << 5) | x] & TGB_TOP_HAS_DATA) != 0; };
+    auto g1 = [&](u32 x, u32 y, u32 z) { return p1[(z << 10) | (y << 5) | x]; };
+    auto g2 = [&](u32 x, u32 y, u32 z) { return p2[(z << 10) | (y << 5) | x]; };
+    for (u32 c = 0; c < TGB_TOP_GRID_CELLS; c++) p1[c] = tgb_tile_pass1(occ, N, c & 31u, (c >> 5) & 31u, c >> 10);
+    for (u32 c = 0; c < TGB_TOP_GRID_CELLS; c++) p2[c] = tgb_tile_pass2(occ, g1, N, c & 31u, (c >> 5) & 31u, c >> 10);
+    for (u32 c = 0; c < TGB_TOP_GRID_CELLS; c++)
+    {
+        const u32 x = c & 31u, y = (c >> 5) & 31u, z = c >> 10;
+        if (occ(x, y, z)) p_cells[c] = TGB_CELLS_LEAF | (p_grid[c] & TGB_TOP_POINTER_MASK);
+        else p_cells[c] = tgb_tile_entry<5>(p2[c], tgb_tile_pass3(occ, g2, N, x, y, z));
+    }
+    free(p1); free(p2);
+    for (u32 leaf = 0; leaf < n_leaves; leaf++)
+    {
+        const u32* block = p_voxels + (uint64_t)leaf * TG_SVO_BLOCK_WORDS;
+        u32 solid[64], b1[64], b2[64];
+        for (u32 b = 0; b < 64u; b++)
+        {
+            const u32 bx = b & 3u, by = (b >> 2) & 3u, bz = b >> 4;
+            u32 any = 0;
+            for (u32 z = 0; z < 8u; z++) for (u32 y = 0; y < 8u; y++) any |= (block[32u * (8u * bz + z) + 8u * by + y] >> (8u * bx)) & 0xFFu;
+            solid[b] = any != 0;
+        }
+        auto bocc = [&](u32 x, u32 y, u32 z) { return solid[(z << 4) | (y << 2) | x] != 0; };
+        auto bg1 = [&](u32 x, u32 y, u32 z) { return b1[(z << 4) | (y << 2) | x]; };
+        auto bg2 = [&](u32 x, u32 y, u32 z) { return b2[(z << 4) | (y << 2) | x]; };
+        for (u32 b = 0; b < 64u; b++) b1[b] = tgb_tile_pass1(bocc, 4u, b & 3u, (b >> 2) & 3u, b >> 4);
+        for (u32 b = 0; b < 64u; b++) b2[b] = tgb_tile_pass2(bocc, bg1, 4u, b & 3u, (b >> 2) & 3u, b >> 4);
+        for (u32 b = 0; b < 64u; b++)
+            p_bricks[leaf * 64u + b] = solid[b] ? (unsigned short)TGB_BRICK_SOLID
+                                                : (unsigned short)tgb_tile_entry<2>(b2[b], tgb_tile_pass3(bocc, bg2, 4u, b & 3u, (b >> 2) & 3u, b >> 4));
+    }
+}
+
+/* tgbsim_gi_fast over the coarser tiling; p_steps (optional): cells entered per ray */
+void tgbsim_gi_fast_tiled(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, const u32* p_cells, const unsigned short* p_bricks,
+                          u32 n, const f32* p_origins, const f32* p_dirs, u32 steps, f32 delta, u8* p_result, u64* p_work, u32* p_steps)
+{
+    tgb_gi_frame fr;
+    tgb_gi_frame_init(&fr, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane, p_grid, p_voxels);
+    tgb_fast_tiling tl; tl.p_cells = p_cells; tl.p_bricks = p_bricks;
+    for (u32 i = 0; i < n; i++)
+    {
+        const v3 origin = tgb_v3(p_origins[3 * i], p_origins[3 * i + 1], p_origins[3 * i + 2]);
+        const v3 d = tgb_v3(p_dirs[3 * i], p_dirs[3 * i + 1], p_dirs[3 * i + 2]);
+        f32 e0, e1;
+        if (p_steps) p_steps[i] = 0;
+        if (!tgb_ray_aabb(tgb_sub(origin, fr.center), d, fr.bmin, fr.bmax, &e0, &e1)) { p_result[i] = 0; continue; }
+        tgb_fast_ray r;
+        memset(&r, 0, sizeof r);
+        u32 n_cells = 0, n_voxels = 0;
+        u32 kind = tgb_fast_start(&fr, origin, d, e0, delta, &r);
+        while (kind == TGB_FAST_WALK) kind = tgb_fast_walk_tiled(&fr, &tl, &r, steps, &n_cells, &n_voxels);
+        if (kind == TGB_FAST_UNOCCLUDED && (r.flags & TGB_FAST_UNCERTAIN)) kind = TGB_FAST_EXACT;
+        p_result[i] = kind == TGB_FAST_OCCLUDED ? 1 : (kind == TGB_FAST_UNOCCLUDED ? 0 : 2);
+        if (p_work) { p_work[0] += n_cells; p_work[1] += n_voxels; p_work[2] += kind == TGB_FAST_EXACT ? 1 : 0; }
+        if (p_steps) p_steps[i] = n_cells + n_voxels;
+    }
+}
+
+}

@@ -74,21 +74,27 @@ def test_full_frame_through_render(gpu, oracle):
         rt.destroy()
 
 
+@pytest.mark.parametrize("kernel", ["3", "4"])
 @pytest.mark.parametrize("make,seed", [(lambda: scenes.small_grid(), 3), (lambda: scenes.config1(k=3, width=320, height=180), 1),
                                        (lambda: scenes.grid_scene("g5", 5, 5, 480, 270, k=3), 7)])
-def test_certified_fast_walk_gives_the_exact_kernels_frame(gpu, oracle, make, seed):
-    """TGB_GI_KERNEL=3 (tgb_gi_fast.cu: the certified fast walk decides most rays, the exact kernel the ones it hands over; not the default)
-    must produce the frame of the exact kernel bit for bit, and the oracle's within the tolerance."""
+def test_certified_fast_walk_gives_the_exact_kernels_frame(gpu, oracle, make, seed, kernel):
+    """TGB_GI_KERNEL=3 / 4 (tgb_gi_fast.cu: the certified fast walk -- over the octree's cells, or over the coarser tiling of the free space --
+    decides most rays, the exact kernel the ones it hands over) must produce the frame of the exact kernel (TGB_GI_KERNEL=2) bit for bit,
+    and the oracle's within the tolerance."""
     s = make()
     vis, svo, want = oracle_frame(oracle, s, gi=True, seed=seed)
     oracle.svo_destroy(svo)
     rt = from_scene(s)
     try:
         rt.set_gi(True, seed)
-        rt.clear(); rt.render(); rt.synchronize()
+        os.environ["TGB_GI_KERNEL"] = "2"
+        try:
+            rt.clear(); rt.render(); rt.synchronize()
+        finally:
+            os.environ.pop("TGB_GI_KERNEL", None)
         exact = rt.read_radiance()
         t_exact = rt.timings()
-        os.environ["TGB_GI_KERNEL"] = "3"
+        os.environ["TGB_GI_KERNEL"] = kernel
         try:
             rt.render_shading(); rt.synchronize()
             fast = rt.read_radiance()
@@ -221,20 +227,28 @@ def test_config3_full_size_stackless_equals_stack_machine_and_oracle_rows(gpu, o
     rt = from_scene(s)
     try:
         rt.set_gi(True, 1)
-        rt.clear(); rt.render(); rt.synchronize()
-        flat = rt.read_radiance()          # default: the exact kernel on every ray (tgb_gi_pool.cu)
-        t_flat = rt.timings()
-        vis = rt.read_visibility()
-        os.environ["TGB_GI_KERNEL"] = "3"  # the certified fast walk + the exact kernel on the rays it hands over (tgb_gi_fast.cu)
+        os.environ["TGB_GI_KERNEL"] = "2"  # the exact kernel on every ray (tgb_gi_pool.cu)
         try:
-            rt.render_shading(); rt.synchronize()
-            fast = rt.read_radiance()
-            t_fast = rt.timings()
+            rt.clear(); rt.render(); rt.synchronize()
         finally:
             os.environ.pop("TGB_GI_KERNEL", None)
-        assert np.array_equal(flat, fast), f"{int((flat != fast).any(axis=-1).sum())} pixels differ between the certified fast walk and the exact kernel"
-        assert 0 < t_fast["n_gi_rays_exact"] < 0.1 * t_fast["n_gi_rays"], (t_fast["n_gi_rays_exact"], t_fast["n_gi_rays"])
-        assert t_flat["n_gi_rays_exact"] == t_flat["n_gi_rays"] == t_fast["n_gi_rays"]
+        flat = rt.read_radiance()
+        t_flat = rt.timings()
+        vis = rt.read_visibility()
+        handed = {}
+        for kernel in ("3", "4"):          # the certified fast walk (octree cells / coarser tiling) + the exact kernel on the rays it hands over (tgb_gi_fast.cu)
+            os.environ["TGB_GI_KERNEL"] = kernel
+            try:
+                rt.render_shading(); rt.synchronize()
+                fast = rt.read_radiance()
+                t_fast = rt.timings()
+            finally:
+                os.environ.pop("TGB_GI_KERNEL", None)
+            assert np.array_equal(flat, fast), f"TGB_GI_KERNEL={kernel}: {int((flat != fast).any(axis=-1).sum())} pixels differ between the certified fast walk and the exact kernel"
+            assert 0 < t_fast["n_gi_rays_exact"] < 0.1 * t_fast["n_gi_rays"], (t_fast["n_gi_rays_exact"], t_fast["n_gi_rays"])
+            assert t_flat["n_gi_rays_exact"] == t_flat["n_gi_rays"] == t_fast["n_gi_rays"]
+            handed[kernel] = t_fast["n_gi_rays_exact"]
+        assert handed["4"] < handed["3"]   # larger cells: fewer edges passed, fewer uncertain rays
         for kind, what in ((1, "stack machine"),):
             rt.set_gi_traversal(kind)
             rt.render_shading(); rt.synchronize()

@@ -30,6 +30,9 @@ struct tgb_svo_device
     u32* d_counts;      /* [0] nodes, [1] leaves, [2] overflow flag */
     u32* d_top_grid;    /* [32^3 + 1] the tree flattened per 32^3 cell (k_svo_flatten): terminal level | has data | leaf data pointer;
                            last word: non-zero = the grid describes the tree completely (leaves exactly at depth 5) */
+    u32* d_fast_cells;  /* [3 * 32^3] the certified fast walk's coarser tiling of the free table cells (tgb_gi_fast.cuh) + two scratch passes; on first use */
+    unsigned short* d_fast_bricks; /* [leaf_capacity * 64] the same per 8^3 brick of every leaf block */
+    b32  fast_tiling_valid; /* both describe the current tree */
     u32  n_nodes, n_leaves, n_pairs;
     b32  valid;
     /* build scratch */
@@ -192,5 +195,10 @@ static inline u32* tgbd_mat_object_indices(const struct tgb_device* d, const u64
             return TG_FALSE;                                                                        \
         }                                                                                           \
     } while (0)
+
+/* TGB_GI_KERNEL when the environment does not say: 2 = the exact kernel on every ray (tgb_gi_pool.cu); 4 = the certified fast walk over the coarser
+ * tiling, the exact kernel on the rays it hands over (tgb_gi_fast.cu); 1 / 3: see tgb_shade.cu */
+#define TGB_GI_KERNEL_DEFAULT 2
+extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st); /* tgb_gi_fast.cu */
 
 #endif

@@ -42,7 +42,8 @@ enum { P_OBX = 0, P_OBY, P_OBZ, P_DX, P_DY, P_DZ, P_IX, P_IY, P_IZ, P_W, P_T, P_
  * voxel: tgb_fast_start) and file the ready rays in shared memory, one column per word. A lane whose ray is decided only copies
  * a ready ray into its registers: a service costs neither memory latency nor a set-up run by a quarter of the warp.
  */
-__global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
+template <bool TILED>
+__global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi_frame fr, const tgb_fast_tiling tiling, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                     const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, u32* __restrict__ p_exact_list,
                                                                     float4* __restrict__ p_out, u32 service_lanes, u32 steps, u32 max_steps, u32 max_steps_uncertain)
 {
@@ -195,7 +196,9 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
             continue;
         }
 
-        if (kind == TGB_FAST_WALK) kind = tgb_fast_walk(&fr, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain);
+        if (kind == TGB_FAST_WALK)
+            kind = TILED ? tgb_fast_walk_tiled(&fr, &tiling, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain)
+                         : tgb_fast_walk(&fr, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain);
     }
     /* [2] cells (empty boxes and voxels) entered by the fast walk in this frame; the exact kernel adds its look-ups there and counts its DDA steps in [3]; [14] rays handed over */
     n_cells = __reduce_add_sync(0xFFFFFFFFu, n_cells);
@@ -207,12 +210,86 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
     }
 }
 
+/* ---- the coarser tiling (tgb_gi_fast.cuh, second half), rebuilt after every SVO build ---------------------------------------------- */
+
+struct tgb_occ_cells { const u32* p; __device__ bool operator()(u32 x, u32 y, u32 z) const { return (p[(z << 10) | (y << 5) | x] & TGB_TOP_HAS_DATA) != 0u; } };
+struct tgb_get_cells { const u32* p; __device__ u32 operator()(u32 x, u32 y, u32 z) const { return p[(z << 10) | (y << 5) | x]; } };
+struct tgb_occ_bricks { const u32* p; __device__ bool operator()(u32 x, u32 y, u32 z) const { return p[(z << 4) | (y << 2) | x] != 0u; } };
+struct tgb_get_bricks { const u32* p; __device__ u32 operator()(u32 x, u32 y, u32 z) const { return p[(z << 4) | (y << 2) | x]; } };
+
+/* one thread per table cell, one launch per pass (a pass reads its neighbours' values of the pass before) */
+__global__ void k_fast_tile_cells(const u32* __restrict__ p_grid, u32* __restrict__ p_pass1, u32* __restrict__ p_pass2, u32* __restrict__ p_cells, u32 pass)
+{
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= TGB_TOP_GRID_CELLS) return;
+    const u32 x = c & 31u, y = (c >> 5) & 31u, z = c >> 10;
+    const tgb_occ_cells occ = { p_grid };
+    if (pass == 1u) p_pass1[c] = tgb_tile_pass1(occ, TGB_TOP_GRID_DIM, x, y, z);
+    else if (pass == 2u) { const tgb_get_cells g1 = { p_pass1 }; p_pass2[c] = tgb_tile_pass2(occ, g1, TGB_TOP_GRID_DIM, x, y, z); }
+    else
+    {
+        const tgb_get_cells g2 = { p_pass2 };
+        p_cells[c] = occ(x, y, z) ? (TGB_CELLS_LEAF | (p_grid[c] & TGB_TOP_POINTER_MASK)) : tgb_tile_entry<5>(p_pass2[c], tgb_tile_pass3(occ, g2, TGB_TOP_GRID_DIM, x, y, z));
+    }
+}
+
+/* 64 threads per leaf block (one per 8^3 brick), four leaf blocks per CTA: which bricks hold a solid voxel, then the three passes in shared memory */
+__global__ void __launch_bounds__(256) k_fast_tile_bricks(const u32* __restrict__ p_voxels, u32 n_leaves, unsigned short* __restrict__ p_bricks)
+{
+    __shared__ u32 s_solid[4][64], s_p1[4][64], s_p2[4][64];
+    const u32 g = threadIdx.x >> 6, b = threadIdx.x & 63u, leaf = blockIdx.x * 4u + g;
+    const u32 bx = b & 3u, by = (b >> 2) & 3u, bz = b >> 4;
+    u32 any = 0;
+    if (leaf < n_leaves)
+    {
+        const u32* p_block = p_voxels + (u64)leaf * TG_SVO_BLOCK_WORDS;
+        for (u32 i = 0; i < 64u; i++) any |= p_block[32u * (8u * bz + (i >> 3)) + 8u * by + (i & 7u)];
+        any = (any >> (8u * bx)) & 0xFFu;
+    }
+    s_solid[g][b] = any;
+    __syncthreads();
+    const tgb_occ_bricks occ = { s_solid[g] };
+    s_p1[g][b] = tgb_tile_pass1(occ, 4u, bx, by, bz);
+    __syncthreads();
+    const tgb_get_bricks g1 = { s_p1[g] };
+    s_p2[g][b] = tgb_tile_pass2(occ, g1, 4u, bx, by, bz);
+    __syncthreads();
+    const tgb_get_bricks g2 = { s_p2[g] };
+    if (leaf < n_leaves)
+        p_bricks[(u64)leaf * 64u + b] = any ? (unsigned short)TGB_BRICK_SOLID : (unsigned short)tgb_tile_entry<2>(s_p2[g][b], tgb_tile_pass3(occ, g2, 4u, bx, by, bz));
+}
+
+/* called behind k_svo_flatten (tgb_svo.cu) on the stream of the build when the tiled walk is selected, else lazily by the first trace */
+extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st)
+{
+    tgb_svo_device* s = &d->svo;
+    if (!s->d_fast_cells)
+    {
+        TGB_CUDA(cudaMalloc(&s->d_fast_cells, (u64)3 * TGB_TOP_GRID_CELLS * sizeof(u32)));
+        TGB_CUDA(cudaMalloc(&s->d_fast_bricks, (u64)s->leaf_capacity * 64u * sizeof(unsigned short)));
+    }
+    u32* p1 = s->d_fast_cells + TGB_TOP_GRID_CELLS, *p2 = s->d_fast_cells + 2 * TGB_TOP_GRID_CELLS;
+    for (u32 pass = 1; pass <= 3u; pass++)
+    {
+        k_fast_tile_cells<<<TGB_TOP_GRID_CELLS / 256, 256, 0, st>>>(s->d_top_grid, p1, p2, s->d_fast_cells, pass);
+        TGB_LAUNCH_CHECK(d);
+    }
+    if (s->n_leaves)
+    {
+        k_fast_tile_bricks<<<(s->n_leaves + 3u) / 4u, 256, 0, st>>>(s->d_voxels, s->n_leaves, s->d_fast_bricks);
+        TGB_LAUNCH_CHECK(d);
+    }
+    s->fast_tiling_valid = TG_TRUE;
+    return TG_TRUE;
+}
+
 /*
  * One band of rays (called by tgbd__shade_launch, tgb_shade.cu, after k_shade queued them): the fast walk over the whole queue, then
  * the exact kernel over the slots it handed over (p_q_count[12] of them, read on the device).
  */
-extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane)
+extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane, b32 tiled)
 {
+    if (tiled && !d->svo.fast_tiling_valid && !tgbd_gi_fast_tiling_build(d, d->stream)) return TG_FALSE;
     const u32 ctas_per_sm = (u32)max(1, min(16, tgbd_env_int("TGB_GI_FAST_CTAS_PER_SM", 8)));
     const u32 service_lanes = (u32)max(1, min(32, tgbd_env_int("TGB_GI_FAST_SERVICE_LANES", 8)));
     const u32 steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_STEPS", 8));
@@ -221,8 +298,12 @@ extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane)
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
     k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count + 12, 2, 0u); /* handed over / fetched by the exact kernel */
     TGB_LAUNCH_CHECK(d);
-    k_gi_trace_fast<<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
-                                                                                 service_lanes, steps, max_steps, max_steps_uncertain);
+    tgb_fast_tiling tiling;
+    tiling.p_cells = d->svo.d_fast_cells; tiling.p_bricks = d->svo.d_fast_bricks;
+    if (tiled) k_gi_trace_fast<true><<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, tiling, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
+                                                                                                  service_lanes, steps, max_steps, max_steps_uncertain);
+    else       k_gi_trace_fast<false><<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, tiling, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
+                                                                                                   service_lanes, steps, max_steps, max_steps_uncertain);
     TGB_LAUNCH_CHECK(d);
     return tgbd_gi_pool_trace_list(d, far_plane, d->d_gi_exact, 12u);
 }

@@ -188,4 +188,173 @@ TGB_HD u32 tgb_fast_walk(const tgb_gi_frame* f, tgb_fast_ray* r, u32 steps, u32*
     return kind;
 }
 
+/* ---- round 2, second half: the same walk over COARSER CELLS ------------------------------------------------------------------------
+ *
+ * The certificate above never uses that a cell is a node of the shader's octree: it needs the cells the ideal ray visits to be boxes
+ * that tile the root without overlap, each either one voxel of a leaf block or free of solid voxels altogether. (Cells of different
+ * sizes may meet anywhere: a line of the tiling that lies inside a coarser cell's face is an edge of the finer cell next to it, whose
+ * own near-near / far-far / near-far check sees it.) Profiles of the walk over octree cells (profiles/r03e_*) and the host build on
+ * the bench scene's rays say where its steps go: three rays of four leave the root, through ~9 empty terminal boxes and ~14 EMPTY
+ * voxels of the leaf blocks around the objects each. So the empty space is re-tiled with larger boxes, once per SVO build:
+ *
+ *   top level   the 32^3 table cells that hold no leaf data are merged into boxes of cells: a cell's free run along x, runs of
+ *               neighbouring rows along z with the same x extent, then along y with the same (x, z) extent (tgb_tile_*: three
+ *               passes, every cell finds its box on its own, all cells of a box find the same one -- a tiling by construction);
+ *   leaf level  a leaf block is 4^3 bricks of 8^3 voxels; bricks without a solid voxel are merged the same way inside their block.
+ *
+ * A step then enters one of: a voxel of a non-empty brick (side 1), a box of empty bricks (sides 8 .. 32), a box of empty table
+ * cells (sides 32 .. 1024). What changes in the certificate is only the count of the shader's advances, which DELTA(n) grows with:
+ * inside a box of table cells the shader advances once per terminal node it crosses, at most once per 32-unit plane the ray
+ * crosses plus one (tgb_fast_advances), so W grows by that many steps when the box is entered.
+ */
+#define TGB_CELLS_LEAF       0x80000000u /* p_cells entry: leaf block with data, bits 0 .. 27 = data pointer; else x0 | y0 << 5 | z0 << 10 | (sx - 1) << 15 | (sy - 1) << 20 | (sz - 1) << 25 in cells */
+#define TGB_BRICK_SOLID      0x8000u     /* p_bricks entry (64 u16 per leaf, brick = bz << 4 | by << 2 | bx): holds a solid voxel; else x0 | y0 << 2 | z0 << 4 | (sx - 1) << 6 | (sy - 1) << 8 | (sz - 1) << 10 in bricks */
+
+/*
+ * The tiling passes over an occupancy grid of side `side` (bit test `occ(x, y, z)`), one call per cell and pass. Runs are grown along
+ * x first, then z, then y (the engine's up axis: the free space above a terrain becomes a few slabs):
+ *   pass 1  -> x0 | x1 << 8                       the maximal free run along x through the cell
+ *   pass 2  -> pass 1 | z0 << 16 | z1 << 24       the maximal run of z neighbours whose pass-1 value is the same
+ *   pass 3  -> y0 | y1 << 8                       the maximal run of y neighbours whose pass-2 value is the same
+ * Cells of one box compute identical values (a neighbour is joined only when its whole run equals this cell's), so the boxes tile.
+ */
+template <class OCC> TGB_HD u32 tgb_tile_pass1(OCC occ, u32 side, u32 x, u32 y, u32 z)
+{
+    u32 x0 = x, x1 = x;
+    while (x0 > 0u && !occ(x0 - 1u, y, z)) x0--;
+    while (x1 + 1u < side && !occ(x1 + 1u, y, z)) x1++;
+    return x0 | (x1 << 8);
+}
+template <class OCC, class P1> TGB_HD u32 tgb_tile_pass2(OCC occ, P1 p1, u32 side, u32 x, u32 y, u32 z)
+{
+    const u32 mine = p1(x, y, z);
+    u32 z0 = z, z1 = z;
+    while (z0 > 0u && !occ(x, y, z0 - 1u) && p1(x, y, z0 - 1u) == mine) z0--;
+    while (z1 + 1u < side && !occ(x, y, z1 + 1u) && p1(x, y, z1 + 1u) == mine) z1++;
+    return mine | (z0 << 16) | (z1 << 24);
+}
+template <class OCC, class P2> TGB_HD u32 tgb_tile_pass3(OCC occ, P2 p2, u32 side, u32 x, u32 y, u32 z)
+{
+    const u32 mine = p2(x, y, z);
+    u32 y0 = y, y1 = y;
+    while (y0 > 0u && !occ(x, y0 - 1u, z) && p2(x, y0 - 1u, z) == mine) y0--;
+    while (y1 + 1u < side && !occ(x, y1 + 1u, z) && p2(x, y1 + 1u, z) == mine) y1++;
+    return y0 | (y1 << 8);
+}
+/* the entry of a free cell from its pass-2 and pass-3 values; BITS = 5 (table cells) or 2 (bricks) */
+template <u32 BITS> TGB_HD u32 tgb_tile_entry(u32 p2, u32 p3)
+{
+    const u32 x0 = p2 & 0xFFu, x1 = (p2 >> 8) & 0xFFu, z0 = (p2 >> 16) & 0xFFu, z1 = p2 >> 24, y0 = p3 & 0xFFu, y1 = p3 >> 8;
+    return x0 | (y0 << BITS) | (z0 << (2u * BITS)) | ((x1 - x0) << (3u * BITS)) | ((y1 - y0) << (4u * BITS)) | ((z1 - z0) << (5u * BITS));
+}
+
+/* upper bound of the shader's advances while the ray crosses a box of table cells: one per terminal node, nodes are at least one cell
+ * wide, so at most one per 32-unit plane crossed (per axis: distance / 32 + 1, and never more than the box has) plus one */
+TGB_HD f32 tgb_fast_advances(f32 dt, f32 sum_abs_d, u32 planes_in_box)
+{
+    const f32 by_distance = floorf(dt * sum_abs_d * 0.03125f) + 3.0f;
+    const f32 by_box = (f32)planes_in_box;
+    return 1.0f + (by_distance < by_box ? by_distance : by_box);
+}
+
+struct tgb_fast_tiling
+{
+    const u32* p_cells;              /* [32^3] */
+    const unsigned short* p_bricks;  /* [n_leaves * 64] */
+};
+
+/*
+ * tgb_fast_walk over the coarser tiling. Same contract; `r->entry` caches the p_cells entry of `r->cell`.
+ * A ray's `posf`, `r` ... are as before; sum |d_k| is recomputed per step from d (three FADDs against a register).
+ */
+TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl, tgb_fast_ray* r, u32 steps, u32* p_n_cells, u32* p_n_voxels, u32 max_steps = TGB_FAST_MAX_STEPS, u32 max_steps_uncertain = TGB_FAST_MAX_STEPS_UNCERTAIN)
+{
+    i32 vx = r->vx, vy = r->vy, vz = r->vz;
+    f32 t_cur = r->t_cur, w_n = r->w;
+    u32 cell = r->cell, entry = r->entry, flags = r->flags;
+    u32 kind = TGB_FAST_WALK;
+    u32 k = 0;
+    const f32 sum_abs_d = (fabsf(r->d.x) + fabsf(r->d.y)) + fabsf(r->d.z);
+    for (;;)
+    {
+        /* ---- the cell of the tiling around (vx, vy, vz) ---- */
+        const u32 c = (((u32)vz & 0x3E0u) << 5) | ((u32)vy & 0x3E0u) | ((u32)vx >> 5);
+        const bool new_cell = c != cell;
+        if (new_cell) { cell = c; entry = TGB_LDG(&tl->p_cells[c]); }
+        const bool leaf = (entry & TGB_CELLS_LEAF) != 0;
+        u32 mx, my, mz, sx, sy, sz;   /* min corner and sides of the cell, box units */
+        bool solid = false;
+        u32 planes = 0;
+        if (leaf)
+        {
+            const u32 lp = entry & 0x0FFFFFFFu;
+            const u32 brick = (((u32)vz & 24u) << 1) | (((u32)vy & 24u) >> 1) | (((u32)vx & 24u) >> 3);
+            const u32 be = (u32)TGB_LDG(&tl->p_bricks[(lp << 6) | brick]);
+            if (be & TGB_BRICK_SOLID)
+            {
+                const u32 row = TGB_LDG(&f->p_voxels[(lp << 10) | (((u32)vz & 31u) << 5) | ((u32)vy & 31u)]);
+                solid = ((row >> ((u32)vx & 31u)) & 1u) != 0;
+                mx = (u32)vx; my = (u32)vy; mz = (u32)vz; sx = sy = sz = 1u;
+            }
+            else
+            {
+                mx = ((u32)vx & ~31u) | ((be & 3u) << 3); my = ((u32)vy & ~31u) | (((be >> 2) & 3u) << 3); mz = ((u32)vz & ~31u) | (((be >> 4) & 3u) << 3);
+                sx = (((be >> 6) & 3u) + 1u) << 3; sy = (((be >> 8) & 3u) + 1u) << 3; sz = (((be >> 10) & 3u) + 1u) << 3;
+            }
+            if (p_n_cells) (*p_n_voxels)++;
+        }
+        else
+        {
+            mx = (entry & 31u) << 5; my = ((entry >> 5) & 31u) << 5; mz = ((entry >> 10) & 31u) << 5;
+            const u32 ex = (entry >> 15) & 31u, ey = (entry >> 20) & 31u, ez = (entry >> 25) & 31u;
+            sx = (ex + 1u) << 5; sy = (ey + 1u) << 5; sz = (ez + 1u) << 5;
+            planes = ex + ey + ez;
+            if (p_n_cells) (*p_n_cells)++;
+        }
+        const f32 sxf = (f32)sx, syf = (f32)sy, szf = (f32)sz;
+        /* crossing times of the far planes (difference form: exact when the ray is close to the plane) and of the near planes */
+        const f32 fx = (fmaf(sxf, r->posf.x, (f32)mx) - r->ob.x) * r->inv.x;
+        const f32 fy = (fmaf(syf, r->posf.y, (f32)my) - r->ob.y) * r->inv.y;
+        const f32 fz = (fmaf(szf, r->posf.z, (f32)mz) - r->ob.z) * r->inv.z;
+        const f32 nx = fmaf(-sxf, r->r.x, fx), ny = fmaf(-syf, r->r.y, fy), nz = fmaf(-szf, r->r.z, fz);
+        const f32 t_exit = fminf(fminf(fx, fy), fz);
+        const f32 t_in = fmaxf(fmaxf(fmaxf(nx, ny), nz), t_cur);
+        const f32 t_next = fmaxf(t_exit, t_cur);
+        /* one more advance of the shader's `position` per leaf block entered, per terminal node crossed inside a box of free cells */
+        if (leaf) { if (new_cell) w_n += r->w_step; }
+        else w_n = fmaf(tgb_fast_advances(t_next - t_cur, sum_abs_d, planes), r->w_step, w_n);
+        const f32 w = fmaf(t_next, r->w_t, w_n);
+        /* edges of the cell within W in time: near-near, far-far, near-far */
+        const f32 t_lo = t_in - w, t_hi = t_exit + w;
+        const bool bx = nx > t_lo, by = ny > t_lo, bz = nz > t_lo;
+        const bool ex_ = fx < t_hi, ey_ = fy < t_hi, ez_ = fz < t_hi;
+        bool uncertain = ((bx & by) | (bx & bz) | (by & bz)) | ((ex_ & ey_) | (ex_ & ez_) | (ey_ & ez_));
+        if (flags & TGB_FAST_FIRST) uncertain = uncertain | bx | by | bz; /* started inside the cell: any plane close behind */
+        uncertain = uncertain | ((t_exit - t_in) < (solid ? w + w : w));
+        if (solid && !uncertain)
+        {
+            if (t_in < TGB_FAST_FAR_FRACTION * f->far_plane) { kind = TGB_FAST_OCCLUDED; break; }
+            flags |= TGB_FAST_UNCERTAIN; kind = TGB_FAST_UNOCCLUDED; break; /* at the far plane: the exact kernel decides */
+        }
+        flags = (flags & ~TGB_FAST_FIRST) | (uncertain ? TGB_FAST_UNCERTAIN : 0u);
+        /* ---- leave through the nearest far plane(s); time and every coordinate monotone (see tgb_fast_walk) ---- */
+        const f32 px = fmaf(t_next, r->d.x, r->ob.x) + (fx == t_exit ? r->posf.x - 0.5f : 0.0f);
+        const f32 py = fmaf(t_next, r->d.y, r->ob.y) + (fy == t_exit ? r->posf.y - 0.5f : 0.0f);
+        const f32 pz = fmaf(t_next, r->d.z, r->ob.z) + (fz == t_exit ? r->posf.z - 0.5f : 0.0f);
+        const i32 qx = (i32)floorf(px), qy = (i32)floorf(py), qz = (i32)floorf(pz);
+        vx = r->d.x > 0.0f ? (qx > vx ? qx : vx) : (qx < vx ? qx : vx);
+        vy = r->d.y > 0.0f ? (qy > vy ? qy : vy) : (qy < vy ? qy : vy);
+        vz = r->d.z > 0.0f ? (qz > vz ? qz : vz) : (qz < vz ? qz : vz);
+        t_cur = t_next;
+        if ((u32)(vx | vy | vz) >= (u32)TG_SVO_SIDE_LENGTH) { kind = TGB_FAST_UNOCCLUDED; break; } /* left the root */
+        if (++k >= steps) break;
+    }
+    r->n_steps += k;
+    if (kind == TGB_FAST_WALK && r->n_steps > ((flags & TGB_FAST_UNCERTAIN) ? max_steps_uncertain : max_steps)) kind = TGB_FAST_EXACT;
+    r->vx = vx; r->vy = vy; r->vz = vz;
+    r->t_cur = t_cur; r->w = w_n;
+    r->cell = cell; r->entry = entry; r->flags = flags;
+    return kind;
+}
+
 #endif

@@ -96,7 +96,7 @@ b32   tgbd_gather_radiance(struct tgb_device* d);
 /* ---- tgb_gi_pool.cu: the queued secondary rays of one band through the flattened SVO, several rays per lane ---- */
 b32   tgbd_gi_pool_trace(struct tgb_device* d, f32 far_plane);
 b32   tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, const u32* p_list, u32 count_word); /* p_list: queue slots handed over by the fast walk, counted in d_gi_count[count_word] */
-b32   tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane); /* tgb_gi_fast.cu: certified fast walk, then the exact kernel on what it handed over */
+b32   tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane, b32 tiled); /* tgb_gi_fast.cu: certified fast walk (over octree cells, or over the coarser tiling), then the exact kernel on what it handed over */
 
 /* ---- tgb_svo.cu ---- */
 b32   tgbd_svo_build(struct tgb_device* d, v3 extent_min, v3 extent_max, u32 n_cluster_pointers, u32 object_capacity);

@@ -987,10 +987,10 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
             /* TGB_GI_KERNEL: 2 (default) = the exact kernel on every ray, several rays per lane (tgb_gi_pool.cu); 1 = the exact kernel, one ray per
              * lane (k_gi_trace_flat); 3 = certified fast walk, the exact kernel only on the rays it hands over (tgb_gi_fast.cu: bit-identical
              * frames, measured slower: 1.69 vs 1.39 ms for the stage, profiles/r03e_*) */
-            const int gi_kernel = tgbd_env_int("TGB_GI_KERNEL", 2);
-            if (flat && gi_kernel == 3)
+            const int gi_kernel = tgbd_env_int("TGB_GI_KERNEL", TGB_GI_KERNEL_DEFAULT);
+            if (flat && (gi_kernel == 3 || gi_kernel == 4))
             {
-                if (!tgbd_gi_fast_trace(d, p_cam->far_plane)) return TG_FALSE;
+                if (!tgbd_gi_fast_trace(d, p_cam->far_plane, gi_kernel == 4)) return TG_FALSE;
             }
             else if (flat && gi_kernel == 2)
             {

@@ -647,6 +647,10 @@ static b32 tgbd__svo_flatten(struct tgb_device* d, cudaStream_t st)
     TGB_CUDA(cudaMemsetAsync(s->d_top_grid + TGB_TOP_GRID_CELLS, 1, sizeof(u32), st)); /* non-zero = complete, cleared by the kernel */
     k_svo_flatten<<<TGB_TOP_GRID_CELLS / 256, 256, 0, st>>>(s->d_nodes, s->d_leaf_data, s->n_nodes, s->n_leaves, s->d_top_grid, (unsigned short*)(s->d_top_grid + TGB_TOP_GRID_CELLS + 1));
     TGB_LAUNCH_CHECK(d);
+    /* the certified fast walk's coarser tiling of the same tree (tgb_gi_fast.cu): here, on the build's stream, when that kernel is selected;
+     * otherwise the first trace that needs it builds it */
+    s->fast_tiling_valid = TG_FALSE;
+    if (tgbd_env_int("TGB_GI_KERNEL", TGB_GI_KERNEL_DEFAULT) == 4 && !tgbd_gi_fast_tiling_build(d, st)) return TG_FALSE;
     return TG_TRUE;
 }
 
