@@ -199,7 +199,7 @@ extern "C" {
  * The coarser tiling of the fast walk (tgb_gi_fast.cuh, second half) built on the host with the per-cell passes the kernels
  * k_fast_tile_* run (tgb_gi_fast.cu): p_cells[32^3] from the flattened tree, p_bricks[64 * n_leaves] from the leaf blocks' voxels.
  */
-void tgbsim_fast_tiling(const u32* p_grid, const u32* p_voxels, u32 n_leaves, u32* p_cells, unsigned short* p_bricks)
+void tgbsim_fast_tiling(const u32* p_grid, const u32* p_voxels, u32 n_leaves, u32* p_cells, u32* p_bricks)
 {
     const u32 N = TGB_TOP_GRID_DIM;
     u32* p1 = (u32*)malloc(TGB_TOP_GRID_CELLS * sizeof(u32));
@@ -233,13 +233,12 @@ void tgbsim_fast_tiling(const u32* p_grid, const u32* p_voxels, u32 n_leaves, u3
         for (u32 b = 0; b < 64u; b++) b1[b] = tgb_tile_pass1(bocc, 4u, b & 3u, (b >> 2) & 3u, b >> 4);
         for (u32 b = 0; b < 64u; b++) b2[b] = tgb_tile_pass2(bocc, bg1, 4u, b & 3u, (b >> 2) & 3u, b >> 4);
         for (u32 b = 0; b < 64u; b++)
-            p_bricks[leaf * 64u + b] = solid[b] ? (unsigned short)TGB_BRICK_SOLID
-                                                : (unsigned short)tgb_tile_entry<2>(b2[b], tgb_tile_pass3(bocc, bg2, 4u, b & 3u, (b >> 2) & 3u, b >> 4));
+            p_bricks[leaf * 64u + b] = solid[b] ? TGB_BRICK_SOLID : tgb_tile_brick_entry(b2[b], tgb_tile_pass3(bocc, bg2, 4u, b & 3u, (b >> 2) & 3u, b >> 4));
     }
 }
 
 /* tgbsim_gi_fast over the coarser tiling; p_steps (optional): cells entered per ray */
-void tgbsim_gi_fast_tiled(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, const u32* p_cells, const unsigned short* p_bricks,
+void tgbsim_gi_fast_tiled(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, const u32* p_cells, const u32* p_bricks,
                           u32 n, const f32* p_origins, const f32* p_dirs, u32 steps, f32 delta, u8* p_result, u64* p_work, u32* p_steps)
 {
     tgb_gi_frame fr;

@@ -137,12 +137,16 @@ def test_the_coarser_cells_tile_the_root(oracle, make):
     bits = ((rows[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)   # [leaf, z, y, x]
     solid = bits.reshape(n_leaves, 4, 8, 4, 8, 4, 8).any(axis=(2, 4, 6))           # [leaf, bz, by, bx]
     br = bricks[: 64 * n_leaves].reshape(n_leaves, 4, 4, 4).astype(np.int64)
-    assert np.array_equal((br & 0x8000) != 0, solid)
+    assert np.array_equal((br >> 31) != 0, solid)
     for leaf_idx in range(n_leaves):
         e = br[leaf_idx]
         for entry in np.unique(e[~solid[leaf_idx]]):
-            x0, y0, z0 = entry & 3, (entry >> 2) & 3, (entry >> 4) & 3
-            x1, y1, z1 = x0 + ((entry >> 6) & 3), y0 + ((entry >> 8) & 3), z0 + ((entry >> 10) & 3)
+            # corner and sides - 1 in voxels of the block: whole bricks
+            vx0, vy0, vz0 = entry & 31, (entry >> 5) & 31, (entry >> 10) & 31
+            vsx, vsy, vsz = ((entry >> 15) & 31) + 1, ((entry >> 20) & 31) + 1, ((entry >> 25) & 31) + 1
+            assert all(v % 8 == 0 for v in (vx0, vy0, vz0, vsx, vsy, vsz))
+            x0, y0, z0 = vx0 // 8, vy0 // 8, vz0 // 8
+            x1, y1, z1 = x0 + vsx // 8 - 1, y0 + vsy // 8 - 1, z0 + vsz // 8 - 1
             sub = (slice(z0, z1 + 1), slice(y0, y1 + 1), slice(x0, x1 + 1))
             assert not solid[leaf_idx][sub].any() and (e[sub] == entry).all()
         assert sum(int((e == entry).sum()) for entry in np.unique(e[~solid[leaf_idx]])) == int((~solid[leaf_idx]).sum())

@@ -31,7 +31,7 @@ struct tgb_svo_device
     u32* d_top_grid;    /* [32^3 + 1] the tree flattened per 32^3 cell (k_svo_flatten): terminal level | has data | leaf data pointer;
                            last word: non-zero = the grid describes the tree completely (leaves exactly at depth 5) */
     u32* d_fast_cells;  /* [3 * 32^3] the certified fast walk's coarser tiling of the free table cells (tgb_gi_fast.cuh) + two scratch passes; on first use */
-    unsigned short* d_fast_bricks; /* [leaf_capacity * 64] the same per 8^3 brick of every leaf block */
+    u32* d_fast_bricks; /* [leaf_capacity * 64] the same per 8^3 brick of every leaf block */
     b32  fast_tiling_valid; /* both describe the current tree */
     u32  n_nodes, n_leaves, n_pairs;
     b32  valid;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
     r.cell = r.entry = r.flags = r.n_steps = 0;
     u32 kind = TGB_FAST_IDLE;
     /* warp-uniform */
-    u32 ready = 0;                       /* pool entries that hold a ready ray */
+    u32 pool_head = 0, pool_n = 0;       /* pool entries [pool_head, pool_n) hold a ready ray (filed by lanes 0 .. n - 1, taken in order) */
     u32 staged_n = 0;                    /* records in flight / arrived in s_rec (lanes 0 .. staged_n - 1) */
     u32 staged_base = 0;
     u32 c_next = 0, c_end = 0;           /* the warp's reserved chunk of the queue */
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
         /* one REDUX counts the lanes that walk and the lanes whose ray is decided */
         const u32 counts = __reduce_add_sync(0xFFFFFFFFu, kind == TGB_FAST_WALK ? 1u : (kind == TGB_FAST_IDLE ? 0u : 0x100u));
         const u32 n_walking = counts & 0xFFu, n_decided = counts >> 8, n_idle = 32u - n_walking - n_decided;
-        const bool more = ready != 0u || staged_n != 0u || !drained || c_next < c_end;
+        const bool more = pool_head < pool_n || staged_n != 0u || !drained || c_next < c_end;
         if (n_walking == 0 && n_decided == 0 && !more) break; /* queue drained, every ray decided and served */
 
         if (n_decided + (more ? n_idle : 0u) >= service_lanes || n_walking == 0)
@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
                 if (round == 1u) break;
 
                 /* ---- the pool is empty: the staged records become ready rays, all lanes together ---- */
-                if (ready == 0u)
+                if (pool_head >= pool_n)
                 {
-                    for (u32 attempt = 0; attempt < 2u && ready == 0u; attempt++)
+                    for (u32 attempt = 0; attempt < 2u && pool_head >= pool_n; attempt++)
                     {
                         if (staged_n != 0u)
                         {
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
                                 p[P_AX * 32] = __float_as_uint(q2.x); p[P_AY * 32] = __float_as_uint(q2.y); p[P_AZ * 32] = __float_as_uint(q2.z);
                             }
                             __syncwarp();
-                            ready = staged_n >= 32u ? 0xFFFFFFFFu : ((1u << staged_n) - 1u);
+                            pool_head = 0; pool_n = staged_n;
                             staged_n = 0;
                         }
                         /* stage the next 32 records of the warp's chunk (a new chunk when this one is used up) */
@@ -169,9 +169,8 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
                 /* ---- idle lanes take a ready ray ---- */
                 {
                     const u32 idle = __ballot_sync(0xFFFFFFFFu, kind == TGB_FAST_IDLE);
-                    const u32 rank = (u32)__popc(idle & ((1u << lane) - 1u));
-                    const u32 e = __fns(ready, 0u, (int)rank + 1);   /* the rank-th ready entry, or none */
-                    if (kind == TGB_FAST_IDLE && e != 0xFFFFFFFFu)
+                    const u32 e = pool_head + (u32)__popc(idle & ((1u << lane) - 1u));   /* the idle lanes take the entries in order */
+                    if (kind == TGB_FAST_IDLE && e < pool_n)
                     {
                         const u32* p = &s_pool[warp][0][e];
                         const u32 vox = p[P_VOX * 32];
@@ -187,9 +186,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
                         s_cur[2][tid] = p[P_AX * 32]; s_cur[3][tid] = p[P_AY * 32]; s_cur[4][tid] = p[P_AZ * 32];
                         kind = (vox & TGB_FAST_POOL_EXACT) ? TGB_FAST_EXACT : TGB_FAST_WALK;
                     }
-                    const u32 n_taken = (u32)__popc(idle) < (u32)__popc(ready) ? (u32)__popc(idle) : (u32)__popc(ready);
-                    const u32 last = n_taken ? __fns(ready, 0u, (int)n_taken) : 0xFFFFFFFFu; /* position of the last entry taken */
-                    if (n_taken) ready &= last >= 31u ? 0u : ~((2u << last) - 1u);
+                    pool_head = pool_head + (u32)__popc(idle) < pool_n ? pool_head + (u32)__popc(idle) : pool_n;
                     __syncwarp();
                 }
             }
@@ -234,7 +231,7 @@ __global__ void k_fast_tile_cells(const u32* __restrict__ p_grid, u32* __restric
 }
 
 /* 64 threads per leaf block (one per 8^3 brick), four leaf blocks per CTA: which bricks hold a solid voxel, then the three passes in shared memory */
-__global__ void __launch_bounds__(256) k_fast_tile_bricks(const u32* __restrict__ p_voxels, u32 n_leaves, unsigned short* __restrict__ p_bricks)
+__global__ void __launch_bounds__(256) k_fast_tile_bricks(const u32* __restrict__ p_voxels, u32 n_leaves, u32* __restrict__ p_bricks)
 {
     __shared__ u32 s_solid[4][64], s_p1[4][64], s_p2[4][64];
     const u32 g = threadIdx.x >> 6, b = threadIdx.x & 63u, leaf = blockIdx.x * 4u + g;
@@ -256,7 +253,7 @@ __global__ void __launch_bounds__(256) k_fast_tile_bricks(const u32* __restrict_
     __syncthreads();
     const tgb_get_bricks g2 = { s_p2[g] };
     if (leaf < n_leaves)
-        p_bricks[(u64)leaf * 64u + b] = any ? (unsigned short)TGB_BRICK_SOLID : (unsigned short)tgb_tile_entry<2>(s_p2[g][b], tgb_tile_pass3(occ, g2, 4u, bx, by, bz));
+        p_bricks[(u64)leaf * 64u + b] = any ? TGB_BRICK_SOLID : tgb_tile_brick_entry(s_p2[g][b], tgb_tile_pass3(occ, g2, 4u, bx, by, bz));
 }
 
 /* called behind k_svo_flatten (tgb_svo.cu) on the stream of the build when the tiled walk is selected, else lazily by the first trace */
@@ -266,7 +263,7 @@ extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st)
     if (!s->d_fast_cells)
     {
         TGB_CUDA(cudaMalloc(&s->d_fast_cells, (u64)3 * TGB_TOP_GRID_CELLS * sizeof(u32)));
-        TGB_CUDA(cudaMalloc(&s->d_fast_bricks, (u64)s->leaf_capacity * 64u * sizeof(unsigned short)));
+        TGB_CUDA(cudaMalloc(&s->d_fast_bricks, (u64)s->leaf_capacity * 64u * sizeof(u32)));
     }
     u32* p1 = s->d_fast_cells + TGB_TOP_GRID_CELLS, *p2 = s->d_fast_cells + 2 * TGB_TOP_GRID_CELLS;
     for (u32 pass = 1; pass <= 3u; pass++)

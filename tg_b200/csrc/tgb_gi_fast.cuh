@@ -207,8 +207,10 @@ TGB_HD u32 tgb_fast_walk(const tgb_gi_frame* f, tgb_fast_ray* r, u32 steps, u32*
  * inside a box of table cells the shader advances once per terminal node it crosses, at most once per 32-unit plane the ray
  * crosses plus one (tgb_fast_advances), so W grows by that many steps when the box is entered.
  */
-#define TGB_CELLS_LEAF       0x80000000u /* p_cells entry: leaf block with data, bits 0 .. 27 = data pointer; else x0 | y0 << 5 | z0 << 10 | (sx - 1) << 15 | (sy - 1) << 20 | (sz - 1) << 25 in cells */
-#define TGB_BRICK_SOLID      0x8000u     /* p_bricks entry (64 u16 per leaf, brick = bz << 4 | by << 2 | bx): holds a solid voxel; else x0 | y0 << 2 | z0 << 4 | (sx - 1) << 6 | (sy - 1) << 8 | (sz - 1) << 10 in bricks */
+#define TGB_CELLS_LEAF       0x80000000u /* p_cells entry: leaf block with data, bits 0 .. 27 = data pointer; else the box of free cells around the cell, in cells:
+                                            x0 | y0 << 5 | z0 << 10 | (sx - 1) << 15 | (sy - 1) << 20 | (sz - 1) << 25 */
+#define TGB_BRICK_SOLID      0x80000000u /* p_bricks entry (64 per leaf block, brick = bz << 4 | by << 2 | bx): the brick holds a solid voxel; else the box of empty
+                                            bricks around it in the same layout, in VOXELS of the block (corner a multiple of 8, sides 8 .. 32) */
 
 /*
  * The tiling passes over an occupancy grid of side `side` (bit test `occ(x, y, z)`), one call per cell and pass. Runs are grown along
@@ -248,6 +250,13 @@ template <u32 BITS> TGB_HD u32 tgb_tile_entry(u32 p2, u32 p3)
     return x0 | (y0 << BITS) | (z0 << (2u * BITS)) | ((x1 - x0) << (3u * BITS)) | ((y1 - y0) << (4u * BITS)) | ((z1 - z0) << (5u * BITS));
 }
 
+/* the same for an empty brick (pass values in bricks) in voxels of its block */
+TGB_HD u32 tgb_tile_brick_entry(u32 p2, u32 p3)
+{
+    const u32 x0 = p2 & 0xFFu, x1 = (p2 >> 8) & 0xFFu, z0 = (p2 >> 16) & 0xFFu, z1 = p2 >> 24, y0 = p3 & 0xFFu, y1 = p3 >> 8;
+    return (x0 << 3) | (y0 << 8) | (z0 << 13) | ((((x1 - x0 + 1u) << 3) - 1u) << 15) | ((((y1 - y0 + 1u) << 3) - 1u) << 20) | ((((z1 - z0 + 1u) << 3) - 1u) << 25);
+}
+
 /* upper bound of the shader's advances while the ray crosses a box of table cells: one per terminal node, nodes are at least one cell
  * wide, so at most one per 32-unit plane crossed (per axis: distance / 32 + 1, and never more than the box has) plus one */
 TGB_HD f32 tgb_fast_advances(f32 dt, f32 sum_abs_d, u32 planes_in_box)
@@ -260,7 +269,7 @@ TGB_HD f32 tgb_fast_advances(f32 dt, f32 sum_abs_d, u32 planes_in_box)
 struct tgb_fast_tiling
 {
     const u32* p_cells;              /* [32^3] */
-    const unsigned short* p_bricks;  /* [n_leaves * 64] */
+    const u32* p_bricks;             /* [n_leaves * 64] */
 };
 
 /*
@@ -277,40 +286,31 @@ TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl,
     const f32 sum_abs_d = (fabsf(r->d.x) + fabsf(r->d.y)) + fabsf(r->d.z);
     for (;;)
     {
-        /* ---- the cell of the tiling around (vx, vy, vz) ---- */
+        /* ---- the cell of the tiling around (vx, vy, vz): one decode for the three kinds. A box is (e, shift, base): corner and sides - 1 in
+         * 5-bit fields of e, in units of 1 << shift, relative to base -- a box of free table cells (shift 5, base 0), a box of empty bricks or
+         * a single voxel (shift 0, base = the block's corner). The brick entry and the voxel row are requested together. ---- */
         const u32 c = (((u32)vz & 0x3E0u) << 5) | ((u32)vy & 0x3E0u) | ((u32)vx >> 5);
         const bool new_cell = c != cell;
         if (new_cell) { cell = c; entry = TGB_LDG(&tl->p_cells[c]); }
         const bool leaf = (entry & TGB_CELLS_LEAF) != 0;
-        u32 mx, my, mz, sx, sy, sz;   /* min corner and sides of the cell, box units */
+        u32 e = entry, shift = 5u, base_mask = 0u;
         bool solid = false;
-        u32 planes = 0;
         if (leaf)
         {
             const u32 lp = entry & 0x0FFFFFFFu;
             const u32 brick = (((u32)vz & 24u) << 1) | (((u32)vy & 24u) >> 1) | (((u32)vx & 24u) >> 3);
-            const u32 be = (u32)TGB_LDG(&tl->p_bricks[(lp << 6) | brick]);
-            if (be & TGB_BRICK_SOLID)
-            {
-                const u32 row = TGB_LDG(&f->p_voxels[(lp << 10) | (((u32)vz & 31u) << 5) | ((u32)vy & 31u)]);
-                solid = ((row >> ((u32)vx & 31u)) & 1u) != 0;
-                mx = (u32)vx; my = (u32)vy; mz = (u32)vz; sx = sy = sz = 1u;
-            }
-            else
-            {
-                mx = ((u32)vx & ~31u) | ((be & 3u) << 3); my = ((u32)vy & ~31u) | (((be >> 2) & 3u) << 3); mz = ((u32)vz & ~31u) | (((be >> 4) & 3u) << 3);
-                sx = (((be >> 6) & 3u) + 1u) << 3; sy = (((be >> 8) & 3u) + 1u) << 3; sz = (((be >> 10) & 3u) + 1u) << 3;
-            }
-            if (p_n_cells) (*p_n_voxels)++;
+            const u32 be = TGB_LDG(&tl->p_bricks[(lp << 6) | brick]);
+            const u32 row = TGB_LDG(&f->p_voxels[(lp << 10) | (((u32)vz & 31u) << 5) | ((u32)vy & 31u)]);
+            const bool voxel = (be & TGB_BRICK_SOLID) != 0;
+            solid = voxel & (((row >> ((u32)vx & 31u)) & 1u) != 0);
+            e = voxel ? (((u32)vx & 31u) | (((u32)vy & 31u) << 5) | (((u32)vz & 31u) << 10)) : be;
+            shift = 0u; base_mask = ~31u;
         }
-        else
-        {
-            mx = (entry & 31u) << 5; my = ((entry >> 5) & 31u) << 5; mz = ((entry >> 10) & 31u) << 5;
-            const u32 ex = (entry >> 15) & 31u, ey = (entry >> 20) & 31u, ez = (entry >> 25) & 31u;
-            sx = (ex + 1u) << 5; sy = (ey + 1u) << 5; sz = (ez + 1u) << 5;
-            planes = ex + ey + ez;
-            if (p_n_cells) (*p_n_cells)++;
-        }
+        if (p_n_cells) { if (leaf) (*p_n_voxels)++; else (*p_n_cells)++; }
+        const u32 mx = ((u32)vx & base_mask) + ((e & 31u) << shift), my = ((u32)vy & base_mask) + (((e >> 5) & 31u) << shift), mz = ((u32)vz & base_mask) + (((e >> 10) & 31u) << shift);
+        const u32 ex = (e >> 15) & 31u, ey = (e >> 20) & 31u, ez = (e >> 25) & 31u;
+        const u32 sx = (ex + 1u) << shift, sy = (ey + 1u) << shift, sz = (ez + 1u) << shift;
+        const u32 planes = ex + ey + ez;   /* of a box of free cells: 32-unit planes inside it */
         const f32 sxf = (f32)sx, syf = (f32)sy, szf = (f32)sz;
         /* crossing times of the far planes (difference form: exact when the ray is close to the plane) and of the near planes */
         const f32 fx = (fmaf(sxf, r->posf.x, (f32)mx) - r->ob.x) * r->inv.x;

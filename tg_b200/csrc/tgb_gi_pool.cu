@@ -239,6 +239,90 @@ static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, co
     return TG_TRUE;
 }
 
+/*
+ * The rays the certified fast walk hands over (tgb_gi_fast.cu) are few -- under one per cent of the queue -- and long: every one
+ * leaves the box, a few hundred voxel steps and a dozen look-ups one after the other. With so little work the pool's phase machinery
+ * (votes, state in shared memory, a ray waiting for the phase its neighbours need) only stretches those dependent chains: 0.20 ms for
+ * 35 k rays (profiles/r04a_*), whatever their number. Here a warp takes LIST_RAYS rays at a time, one per lane, everything in
+ * registers, and every lane simply runs its ray to the end with the same per-ray functions (tgb_gi_walk.cuh): the duration is the
+ * longest ray's chain and the divergence of a handful of lanes costs nothing on an otherwise idle SM.
+ */
+#define TGB_LIST_THREADS 64
+__global__ void __launch_bounds__(TGB_LIST_THREADS) k_gi_trace_list(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
+                                                                    const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, const u32* __restrict__ p_list, u32 count_word,
+                                                                    float4* __restrict__ p_out, u32 rays_per_grab, u32 tree_reps, u32 dda_steps)
+{
+    if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
+    const u32 lane = threadIdx.x & 31u;
+    const u32 n_rays = p_q_count[count_word];
+    u32 n_visits = 0, n_steps = 0, n_advances = 0;
+    for (;;)
+    {
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(&p_q_count[count_word + 1u], rays_per_grab);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_rays) break;
+        const u32 mine = base + lane;
+        if (lane < rays_per_grab && mine < n_rays)
+        {
+            const u32 slot = __ldcs(&p_list[mine]);
+            const float4 q0 = __ldcg(&p_q0[slot]), q1 = __ldcs(&p_q1[slot]);
+            const v3 origin = tgb_v3(q0.x, q0.y, q0.z), d = tgb_v3(q1.x, q1.y, q1.z);
+            v3 position, t_delta, t_max = tgb_v3(0.0f, 0.0f, 0.0f);
+            u32 flags, cell = 0, data = 0, kind = TGB_RAY_TREE;
+            i32 x = 0, y = 0, z = 0;
+            tgb_gi_ray_start(&fr, origin, d, q1.w, &position, &t_delta, &flags);
+            bool occluded = false;
+            for (;;)
+            {
+                if (kind == TGB_RAY_TREE) kind = tgb_gi_tree_phase(&fr, d, t_delta, &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
+                else if (kind == TGB_RAY_DDA)
+                {
+                    if (flags & TGB_RF_SETUP)
+                    {
+                        flags &= ~TGB_RF_SETUP;
+                        v3 child_min; f32 child_size;
+                        tgb_cell_box(&fr, cell, &child_min, &child_size);
+                        tgb_gi_dda_setup(d, position, child_min, child_size, &x, &y, &z, &t_max);
+                    }
+                    kind = tgb_gi_dda_phase(fr.p_voxels + (u64)data * TG_SVO_BLOCK_WORDS, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
+                    if (kind == TGB_RAY_DDA || kind == TGB_RAY_HIT) { x &= 31; y &= 31; z &= 31; } /* what the pool keeps between phases */
+                }
+                else if (kind == TGB_RAY_HIT)
+                {
+                    v3 child_min; f32 child_size;
+                    tgb_cell_box(&fr, cell, &child_min, &child_size);
+                    kind = tgb_gi_hit_test(&fr, origin, d, child_min, x, y, z);
+                    if (kind == TGB_RAY_IDLE) { occluded = true; break; }
+                }
+                else /* MISS */
+                {
+                    if (flags & TGB_RF_BORDER) kind = tgb_gi_border_test(&fr, d, position, &flags);
+                    if (kind == TGB_RAY_MISS) break;
+                }
+            }
+            if (!occluded)
+            {
+                const float4 q2 = __ldcs(&p_q2[slot]);
+                f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
+                atomicAdd(p_pixel + 0, q2.x);
+                atomicAdd(p_pixel + 1, q2.y);
+                atomicAdd(p_pixel + 2, q2.z);
+            }
+        }
+        __syncwarp();
+    }
+    n_visits = __reduce_add_sync(0xFFFFFFFFu, n_visits);
+    n_steps = __reduce_add_sync(0xFFFFFFFFu, n_steps);
+    n_advances = __reduce_add_sync(0xFFFFFFFFu, n_advances);
+    if (lane == 0 && (n_visits | n_steps | n_advances))
+    {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_visits);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 2, (unsigned long long)n_steps);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 3, (unsigned long long)n_advances);
+    }
+}
+
 extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, const u32* p_list, u32 count_word)
 {
     const int rays_per_lane = tgbd_env_int("TGB_GI_RAYS_PER_LANE", p_list ? 1 : 3); /* measured: 1.40 ms for the stage with 3, 1.43 with 2, 1.52 with 4 (L1 shrinks with the pool), 1.51 for k_gi_trace_flat */
@@ -251,6 +335,16 @@ extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, cons
     const u32 rounds = (u32)max(1, tgbd_env_int("TGB_GI_POOL_TAIL_BOOST", 1)); /* phase budgets x this once at most 6 lanes of a warp still hold a working ray */
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
+    if (p_list && tgbd_env_int("TGB_GI_LIST_KERNEL", 1))
+    {
+        /* the handed-over rays: k_gi_trace_list (TGB_GI_LIST_KERNEL=0: the pool kernel in list mode, the measured predecessor) */
+        const u32 rays_per_grab = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_RAYS", 4)));
+        const u32 list_ctas = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_CTAS_PER_SM", 16)));
+        k_gi_trace_list<<<d->n_sms * list_ctas, TGB_LIST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
+                                                                                  rays_per_grab, (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 4)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 64)));
+        TGB_LAUNCH_CHECK(d);
+        return TG_TRUE;
+    }
     /* TGB_GI_POOL_GRID16=1 reads the 16-bit form of the table (half the footprint in what L1 the pool leaves): measured 1.381 vs 1.383 ms for the
      * stage -- the look-ups are concentrated on few cells and hit L1 either way; what misses is the voxel rows. Off; kept as the measured record. */
     const int grid16 = tgbd_env_int("TGB_GI_POOL_GRID16", 0);

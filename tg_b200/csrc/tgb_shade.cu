@@ -14,6 +14,7 @@
  * nevertheless follows the shader's operation order (this TU is built with -fmad=false like the others).
  */
 #include "tgb_device.cuh"
+#include "tgb_gi_fast.cuh"
 
 #define TGB_PI_F               3.14159265358979323846f
 
@@ -110,6 +111,10 @@ struct tgb_shade_args
     float4* __restrict__ p_q2;
     u32* __restrict__ p_q_count; /* [0] rays queued, [1] rays fetched */
     const u64* __restrict__ p_mat; /* RESOLVED mode: this tile's owner-resolved material words, row y0 first */
+    /* FAST: the certified walk over the coarser tiling (tgb_gi_fast.cuh) takes its first steps here, and only rays still undecided are queued */
+    tgb_gi_frame fast_frame;
+    tgb_fast_tiling fast_tiling;
+    u32 fast_steps;
 };
 
 /* returns true when a secondary ray has to be traced; *p_color is then the pixel WITHOUT its ambient term */
@@ -268,7 +273,14 @@ __device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px,
     return false;
 }
 
-template <bool RESOLVED>
+/*
+ * FAST (TGB_GI_KERNEL=4): two secondary rays of three are decided by the FIRST cell the certified walk enters (tgb_gi_fast.cuh: the
+ * ray starts in the free space above the objects and the box of free cells around it reaches the root's border, or it starts next to a
+ * solid voxel) -- those never see the queue: 48 bytes written and read again, a slot reserved, a set-up and a service per ray saved.
+ * The pixel gets `ambient + lo` here exactly as the trace kernels would add it (one float addition per channel, commutative). Rays
+ * the first steps leave undecided, or decide without certainty, are queued as before and start again from their record.
+ */
+template <bool RESOLVED, bool FAST>
 __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
 {
     /* 8x4 pixel blocks per warp like K1: neighbouring pixels share clusters, objects and material bytes */
@@ -281,7 +293,34 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
     float4 color = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     v3 origin = tgb_v3(0.0f, 0.0f, 0.0f), dir = origin, ambient = origin;
     f32 root_enter = 0.0f; /* `enter` of the slab test against the SVO root (svo_functions.inc:27-31), queued for k_gi_trace_flat */
-    const bool trace = in_tile && tgb_shade_pixel<RESOLVED>(a, px, py, vy, &color, &origin, &dir, &ambient, &root_enter);
+    bool trace = in_tile && tgb_shade_pixel<RESOLVED>(a, px, py, vy, &color, &origin, &dir, &ambient, &root_enter);
+    if (FAST)
+    {
+        u32 n_cells = 0;
+        bool decided = false;
+        if (trace)
+        {
+            tgb_fast_ray r;
+            u32 kind = tgb_fast_start(&a.fast_frame, origin, dir, root_enter, TGB_FAST_DELTA, &r);
+            if (kind == TGB_FAST_WALK) kind = tgb_fast_walk_tiled(&a.fast_frame, &a.fast_tiling, &r, a.fast_steps, (u32*)0, (u32*)0);
+            n_cells = r.n_steps;
+            if (kind == TGB_FAST_OCCLUDED) decided = true;
+            else if (kind == TGB_FAST_UNOCCLUDED && !(r.flags & TGB_FAST_UNCERTAIN))
+            {
+                decided = true;
+                color.x = ambient.x + color.x; color.y = ambient.y + color.y; color.z = ambient.z + color.z;
+            }
+            trace = !decided;
+        }
+        /* the frame's counters: [10] rays of the frame, u64 [1] cells entered */
+        const u32 n_decided = (u32)__popc(__ballot_sync(0xFFFFFFFFu, decided));
+        n_cells = __reduce_add_sync(0xFFFFFFFFu, decided ? n_cells : 0u);
+        if (lane == 0 && n_decided)
+        {
+            atomicAdd(&a.p_q_count[10], n_decided);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.p_q_count) + 1, (unsigned long long)n_cells);
+        }
+    }
     if (in_tile) a.p_out[(u64)vy * a.w + px] = color;
 
     /* warp-aggregated append to the ray queue */
@@ -952,6 +991,18 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         for (int i = 0; i < 6; i++) flat = flat && fmodf(c[i], 32.0f) == 0.0f && fabsf(c[i]) <= 4194304.0f; /* corners on the 32-unit cell lattice */
     }
     const int gi_ctas = max(1, min(16, tgbd_env_int("TGB_GI_CTAS_PER_SM", TGB_GI_FLAT_CTAS_PER_SM))); /* persistent CTAs per SM (tuning only) */
+    /* TGB_GI_KERNEL=4: the first TGB_GI_SHADE_STEPS cells of the certified walk are entered by k_shade itself (0: every ray is queued) */
+    a.fast_steps = 0;
+    if (gi && flat && tgbd_env_int("TGB_GI_KERNEL", TGB_GI_KERNEL_DEFAULT) == 4)
+    {
+        a.fast_steps = (u32)max(0, min(64, tgbd_env_int("TGB_GI_SHADE_STEPS", 1)));
+        if (a.fast_steps)
+        {
+            if (!d->svo.fast_tiling_valid && !tgbd_gi_fast_tiling_build(d, d->stream)) return TG_FALSE;
+            tgb_gi_frame_init(&a.fast_frame, d->svo.bmin, d->svo.bmax, p_cam->far_plane, d->svo.d_top_grid, d->svo.d_voxels);
+            a.fast_tiling.p_cells = d->svo.d_fast_cells; a.fast_tiling.p_bricks = d->svo.d_fast_bricks;
+        }
+    }
 
     /*
      * With a frame sink the rows are shaded in bands and every finished band is copied to the caller's memory on the copy
@@ -978,8 +1029,8 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         a.y0 = by0; a.y1 = by1;
         if (gi && b > 0) { k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count, 2, 0u); TGB_LAUNCH_CHECK(d); } /* queued / fetched; the work counters accumulate over the bands */
         const dim3 grid((d->width + 15) / 16, (by1 - by0 + 15) / 16);
-        if (resolved) k_shade<true><<<grid, 256, 0, d->stream>>>(a);
-        else          k_shade<false><<<grid, 256, 0, d->stream>>>(a);
+        if (a.fast_steps) { if (resolved) k_shade<true, true><<<grid, 256, 0, d->stream>>>(a); else k_shade<false, true><<<grid, 256, 0, d->stream>>>(a); }
+        else              { if (resolved) k_shade<true, false><<<grid, 256, 0, d->stream>>>(a); else k_shade<false, false><<<grid, 256, 0, d->stream>>>(a); }
         TGB_LAUNCH_CHECK(d);
         if (gi)
         {
