@@ -254,7 +254,7 @@ void tgbsim_gi_fast_tiled(const f32* p_bmin, const f32* p_bmax, f32 far_plane, c
         tgb_fast_ray r;
         memset(&r, 0, sizeof r);
         u32 n_cells = 0, n_voxels = 0;
-        u32 kind = tgb_fast_start(&fr, origin, d, e0, delta, &r);
+        u32 kind = tgb_fast_start(&fr, origin, d, e0, delta, &r, true);
         while (kind == TGB_FAST_WALK) kind = tgb_fast_walk_tiled(&fr, &tl, &r, steps, &n_cells, &n_voxels);
         if (kind == TGB_FAST_UNOCCLUDED && (r.flags & TGB_FAST_UNCERTAIN)) kind = TGB_FAST_EXACT;
         p_result[i] = kind == TGB_FAST_OCCLUDED ? 1 : (kind == TGB_FAST_UNOCCLUDED ? 0 : 2);

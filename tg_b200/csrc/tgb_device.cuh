@@ -200,5 +200,6 @@ static inline u32* tgbd_mat_object_indices(const struct tgb_device* d, const u64
  * tiling, the exact kernel on the rays it hands over (tgb_gi_fast.cu); 1 / 3: see tgb_shade.cu */
 #define TGB_GI_KERNEL_DEFAULT 2
 extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st); /* tgb_gi_fast.cu */
+extern "C" f32 tgbd_gi_fast_delta(void);
 
 #endif

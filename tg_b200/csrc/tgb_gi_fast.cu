@@ -43,9 +43,9 @@ enum { P_OBX = 0, P_OBY, P_OBZ, P_DX, P_DY, P_DZ, P_IX, P_IY, P_IZ, P_W, P_T, P_
  * a ready ray into its registers: a service costs neither memory latency nor a set-up run by a quarter of the warp.
  */
 template <bool TILED>
-__global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi_frame fr, const tgb_fast_tiling tiling, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
+__global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fast(const tgb_gi_frame fr, const tgb_fast_tiling tiling, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                     const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, u32* __restrict__ p_exact_list,
-                                                                    float4* __restrict__ p_out, u32 service_lanes, u32 steps, u32 max_steps, u32 max_steps_uncertain)
+                                                                    float4* __restrict__ p_out, u32 service_lanes, u32 steps, u32 max_steps, u32 max_steps_uncertain, f32 delta)
 {
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS) k_gi_trace_fast(const tgb_gi
                             {
                                 const float4 q0 = s_rec[0][tid], q1 = s_rec[1][tid], q2 = s_rec[2][tid];
                                 tgb_fast_ray n;
-                                const u32 k0 = tgb_fast_start(&fr, tgb_v3(q0.x, q0.y, q0.z), tgb_v3(q1.x, q1.y, q1.z), q1.w, TGB_FAST_DELTA, &n);
+                                const u32 k0 = tgb_fast_start(&fr, tgb_v3(q0.x, q0.y, q0.z), tgb_v3(q1.x, q1.y, q1.z), q1.w, delta, &n, TILED);
                                 u32* p = &s_pool[warp][0][lane];
                                 p[P_OBX * 32] = __float_as_uint(n.ob.x); p[P_OBY * 32] = __float_as_uint(n.ob.y); p[P_OBZ * 32] = __float_as_uint(n.ob.z);
                                 p[P_DX * 32] = __float_as_uint(q1.x); p[P_DY * 32] = __float_as_uint(q1.y); p[P_DZ * 32] = __float_as_uint(q1.z);
@@ -256,6 +256,13 @@ __global__ void __launch_bounds__(256) k_fast_tile_bricks(const u32* __restrict_
         p_bricks[(u64)leaf * 64u + b] = any ? TGB_BRICK_SOLID : tgb_tile_brick_entry(s_p2[g][b], tgb_tile_pass3(occ, g2, 4u, bx, by, bz));
 }
 
+/* DELTA0 of the certificate. TGB_GI_FAST_DELTA_PERCENT (tests, margin studies) scales it: the product runs at 100, a frame that still equals the exact
+ * kernel's at 25 shows a fourfold margin on that frame's rays */
+extern "C" f32 tgbd_gi_fast_delta(void)
+{
+    return TGB_FAST_DELTA * 0.01f * (f32)max(0, min(1000, tgbd_env_int("TGB_GI_FAST_DELTA_PERCENT", 100)));
+}
+
 /* called behind k_svo_flatten (tgb_svo.cu) on the stream of the build when the tiled walk is selected, else lazily by the first trace */
 extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st)
 {
@@ -295,12 +302,13 @@ extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane, b32 tiled
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
     k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count + 12, 2, 0u); /* handed over / fetched by the exact kernel */
     TGB_LAUNCH_CHECK(d);
+    const f32 delta = tgbd_gi_fast_delta();
     tgb_fast_tiling tiling;
     tiling.p_cells = d->svo.d_fast_cells; tiling.p_bricks = d->svo.d_fast_bricks;
     if (tiled) k_gi_trace_fast<true><<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, tiling, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
-                                                                                                  service_lanes, steps, max_steps, max_steps_uncertain);
+                                                                                                  service_lanes, steps, max_steps, max_steps_uncertain, delta);
     else       k_gi_trace_fast<false><<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, tiling, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
-                                                                                                   service_lanes, steps, max_steps, max_steps_uncertain);
+                                                                                                   service_lanes, steps, max_steps, max_steps_uncertain, delta);
     TGB_LAUNCH_CHECK(d);
     return tgbd_gi_pool_trace_list(d, far_plane, d->d_gi_exact, 12u);
 }

@@ -54,6 +54,7 @@
 #define TGB_FAST_DELTA        2.0e-4f  /* DELTA0: sideways displacement (world units) a decision must survive at the start of the ray */
 #define TGB_FAST_DELTA_STEP   0.15f    /* DELTA1 / DELTA0: growth per box entered (3e-5 for DELTA0 = 2e-4) */
 #define TGB_FAST_SHALLOW      1.0e-3f  /* direction components below this (zero included) go to the exact kernel */
+#define TGB_FAST_SHALLOW_PER_AXIS 1.0e-4f /* the same for the walk with one margin per axis (tgb_fast_walk_tiled) */
 #define TGB_FAST_MAX_STEPS    256u     /* cells a ray may enter here (median 5, 99.9 % below 220); the few that skim along a leaf layer for longer go to the exact kernel: */
 #define TGB_FAST_MAX_STEPS_UNCERTAIN 64u /* one ray of 1,000 cells is a 0.2 ms dependent chain that the whole kernel waits for. A ray already uncertain can only still end occluded; it gets less */
 #define TGB_FAST_FAR_FRACTION 0.99f    /* a solid voxel beyond this fraction of the far plane is not decided here */
@@ -93,14 +94,17 @@ TGB_HD void tgb_fast_derive(tgb_fast_ray* r, f32 w)
  * rays the fast walk does not take (a direction component below TGB_FAST_SHALLOW). `delta` is TGB_FAST_DELTA in the product; the
  * margin sweep (tools/gi_fast_margin.py) lowers it until the first disagreement with the exact walk appears.
  */
-TGB_HD u32 tgb_fast_start(const tgb_gi_frame* f, v3 origin, v3 dir, f32 root_enter, f32 delta, tgb_fast_ray* r)
+/* `per_axis` (tgb_fast_walk_tiled): the ray carries DELTA itself, in world units, and the walk derives a time margin per axis from it;
+ * directions down to TGB_FAST_SHALLOW_PER_AXIS are taken */
+TGB_HD u32 tgb_fast_start(const tgb_gi_frame* f, v3 origin, v3 dir, f32 root_enter, f32 delta, tgb_fast_ray* r, bool per_axis = false)
 {
     const f32 ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
-    if (!(ax >= TGB_FAST_SHALLOW && ay >= TGB_FAST_SHALLOW && az >= TGB_FAST_SHALLOW)) return TGB_FAST_EXACT; /* NaN included */
+    const f32 shallow = per_axis ? TGB_FAST_SHALLOW_PER_AXIS : TGB_FAST_SHALLOW;
+    if (!(ax >= shallow && ay >= shallow && az >= shallow)) return TGB_FAST_EXACT; /* NaN included */
     r->ob = tgb_sub(tgb_sub(origin, f->center), f->bmin);
     r->d = dir;
     r->inv = tgb_v3(TGB_RCP_RN(dir.x), TGB_RCP_RN(dir.y), TGB_RCP_RN(dir.z));
-    tgb_fast_derive(r, delta * ((fabsf(r->inv.x) + fabsf(r->inv.y)) + fabsf(r->inv.z)));
+    tgb_fast_derive(r, per_axis ? delta : delta * ((fabsf(r->inv.x) + fabsf(r->inv.y)) + fabsf(r->inv.z)));
     r->t_cur = root_enter > 0.0f ? root_enter : 0.0f;
     /* the voxel around the starting point; a ray that starts on (or outside) a root face is clamped into the outermost layer */
     const f32 px = fmaf(r->t_cur, dir.x, r->ob.x), py = fmaf(r->t_cur, dir.y, r->ob.y), pz = fmaf(r->t_cur, dir.z, r->ob.z);
@@ -274,7 +278,17 @@ struct tgb_fast_tiling
 
 /*
  * tgb_fast_walk over the coarser tiling. Same contract; `r->entry` caches the p_cells entry of `r->cell`.
- * A ray's `posf`, `r` ... are as before; sum |d_k| is recomputed per step from d (three FADDs against a register).
+ *
+ * ONE MARGIN PER AXIS. A sideways displacement of at most DELTA per coordinate moves the time at which the ray crosses a plane of axis k
+ * by at most w_k = DELTA / |d_k| -- not by W = DELTA * sum 1 / |d_j|, which tgb_fast_walk charges to every plane alike (three to five times
+ * w_k for a typical direction, and hopeless for a shallow one, which is why it does not take them). With n_k / f_k the crossing times
+ * of the cell's near / far planes, a = the entry axis (n_a = max n_k), e = the exit axis (f_e = min f_k), a displaced ray crosses
+ * plane k at n_k + s_k, |s_k| <= w_k, so it enters through the same face iff n_a - n_b > w_a + w_b for the other two axes b, leaves through
+ * the same face iff f_b - f_e > w_b + w_e, and meets the cell at all iff f_e - n_a > w_a + w_e; a ray that starts inside its cell must have
+ * every near plane b more than w_b behind it. The face it leaves through and the point where it does so (displaced by less than the
+ * margins the next cell's own entry check demands) select the next cell, so a walk on which none of these inequalities failed visits
+ * the cells every displaced ray visits. Each w_k also carries the rounding of the times themselves (2.5e-7 t, twice per comparison).
+ * Here `r->w` is DELTA(n) itself, in world units (tgb_fast_start with per_axis).
  */
 TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl, tgb_fast_ray* r, u32 steps, u32* p_n_cells, u32* p_n_voxels, u32 max_steps = TGB_FAST_MAX_STEPS, u32 max_steps_uncertain = TGB_FAST_MAX_STEPS_UNCERTAIN)
 {
@@ -323,13 +337,18 @@ TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl,
         /* one more advance of the shader's `position` per leaf block entered, per terminal node crossed inside a box of free cells */
         if (leaf) { if (new_cell) w_n += r->w_step; }
         else w_n = fmaf(tgb_fast_advances(t_next - t_cur, sum_abs_d, planes), r->w_step, w_n);
-        const f32 w = fmaf(t_next, r->w_t, w_n);
-        /* edges of the cell within W in time: near-near, far-far, near-far */
-        const f32 t_lo = t_in - w, t_hi = t_exit + w;
-        const bool bx = nx > t_lo, by = ny > t_lo, bz = nz > t_lo;
-        const bool ex_ = fx < t_hi, ey_ = fy < t_hi, ez_ = fz < t_hi;
-        bool uncertain = ((bx & by) | (bx & bz) | (by & bz)) | ((ex_ & ey_) | (ex_ & ez_) | (ey_ & ez_));
-        if (flags & TGB_FAST_FIRST) uncertain = uncertain | bx | by | bz; /* started inside the cell: any plane close behind */
+        /* the margins: w_k = DELTA(n) / |d_k| + the rounding of a crossing time */
+        const f32 e_t = t_next * r->w_t;
+        const f32 wx = fmaf(w_n, r->r.x, e_t), wy = fmaf(w_n, r->r.y, e_t), wz = fmaf(w_n, r->r.z, e_t);
+        const f32 n_max = fmaxf(fmaxf(nx, ny), nz);
+        const f32 w_a = nx == n_max ? wx : (ny == n_max ? wy : wz), w_e = fx == t_exit ? wx : (fy == t_exit ? wy : wz);
+        /* entered / left next to an edge: a second plane within the pair's margin of the entry / exit plane (the plane itself always counts) */
+        const bool bx = n_max - nx < wx + w_a, by = n_max - ny < wy + w_a, bz = n_max - nz < wz + w_a;
+        const bool cx = fx - t_exit < wx + w_e, cy = fy - t_exit < wy + w_e, cz = fz - t_exit < wz + w_e;
+        bool uncertain = ((bx & by) | (bx & bz) | (by & bz)) | ((cx & cy) | (cx & cz) | (cy & cz));
+        /* started inside the cell: any near plane within its own margin behind the starting point */
+        if (flags & TGB_FAST_FIRST) uncertain = uncertain | (t_cur - nx < wx) | (t_cur - ny < wy) | (t_cur - nz < wz);
+        const f32 w = w_a + w_e;
         uncertain = uncertain | ((t_exit - t_in) < (solid ? w + w : w));
         if (solid && !uncertain)
         {

@@ -115,6 +115,7 @@ struct tgb_shade_args
     tgb_gi_frame fast_frame;
     tgb_fast_tiling fast_tiling;
     u32 fast_steps;
+    f32 fast_delta;
 };
 
 /* returns true when a secondary ray has to be traced; *p_color is then the pixel WITHOUT its ambient term */
@@ -294,14 +295,14 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
     v3 origin = tgb_v3(0.0f, 0.0f, 0.0f), dir = origin, ambient = origin;
     f32 root_enter = 0.0f; /* `enter` of the slab test against the SVO root (svo_functions.inc:27-31), queued for k_gi_trace_flat */
     bool trace = in_tile && tgb_shade_pixel<RESOLVED>(a, px, py, vy, &color, &origin, &dir, &ambient, &root_enter);
+    u32 n_cells = 0, n_decided = 0;
     if (FAST)
     {
-        u32 n_cells = 0;
         bool decided = false;
         if (trace)
         {
             tgb_fast_ray r;
-            u32 kind = tgb_fast_start(&a.fast_frame, origin, dir, root_enter, TGB_FAST_DELTA, &r);
+            u32 kind = tgb_fast_start(&a.fast_frame, origin, dir, root_enter, a.fast_delta, &r, true);
             if (kind == TGB_FAST_WALK) kind = tgb_fast_walk_tiled(&a.fast_frame, &a.fast_tiling, &r, a.fast_steps, (u32*)0, (u32*)0);
             n_cells = r.n_steps;
             if (kind == TGB_FAST_OCCLUDED) decided = true;
@@ -312,26 +313,34 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
             }
             trace = !decided;
         }
-        /* the frame's counters: [10] rays of the frame, u64 [1] cells entered */
-        const u32 n_decided = (u32)__popc(__ballot_sync(0xFFFFFFFFu, decided));
+        n_decided = (u32)__popc(__ballot_sync(0xFFFFFFFFu, decided));
         n_cells = __reduce_add_sync(0xFFFFFFFFu, decided ? n_cells : 0u);
-        if (lane == 0 && n_decided)
-        {
-            atomicAdd(&a.p_q_count[10], n_decided);
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.p_q_count) + 1, (unsigned long long)n_cells);
-        }
     }
     if (in_tile) a.p_out[(u64)vy * a.w + px] = color;
 
-    /* warp-aggregated append to the ray queue */
+    /* CTA-aggregated append to the ray queue: one atomic per 16x16 tile. (One per warp was 259 k atomics per 4K frame on a single address, a
+     * fifth of this kernel's stall samples once the counters of the FAST path were added to the same line: profiles/r04b_k_shade.) */
+    __shared__ u32 s_count[8], s_cells[8], s_decided[8], s_base;
     const u32 m = __ballot_sync(0xFFFFFFFFu, trace);
-    if (m == 0) return;
-    u32 base = 0;
-    if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(&a.p_q_count[0], (u32)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if (lane == 0) { s_count[warp] = (u32)__popc(m); if (FAST) { s_cells[warp] = n_cells; s_decided[warp] = n_decided; } }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        u32 total = 0, cells = 0, dec = 0;
+        for (u32 i = 0; i < 8u; i++) { total += s_count[i]; if (FAST) { cells += s_cells[i]; dec += s_decided[i]; } }
+        s_base = total ? atomicAdd(&a.p_q_count[0], total) : 0u;
+        if (FAST && dec)
+        {
+            /* the frame's counters: [10] rays of the frame (the trace kernel adds the queued ones), u64 [1] cells entered */
+            atomicAdd(&a.p_q_count[10], dec);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.p_q_count) + 1, (unsigned long long)cells);
+        }
+    }
+    __syncthreads();
     if (trace)
     {
-        const u32 slot = base + (u32)__popc(m & ((1u << lane) - 1u));
+        u32 slot = s_base + (u32)__popc(m & ((1u << lane) - 1u));
+        for (u32 i = 0; i < warp; i++) slot += s_count[i];
         a.p_q0[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(a.w * vy + px)); /* where the ambient term goes */
         a.p_q1[slot] = make_float4(dir.x, dir.y, dir.z, root_enter);
         a.p_q2[slot] = make_float4(ambient.x, ambient.y, ambient.z, 0.0f);
@@ -992,7 +1001,7 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     }
     const int gi_ctas = max(1, min(16, tgbd_env_int("TGB_GI_CTAS_PER_SM", TGB_GI_FLAT_CTAS_PER_SM))); /* persistent CTAs per SM (tuning only) */
     /* TGB_GI_KERNEL=4: the first TGB_GI_SHADE_STEPS cells of the certified walk are entered by k_shade itself (0: every ray is queued) */
-    a.fast_steps = 0;
+    a.fast_steps = 0; a.fast_delta = tgbd_gi_fast_delta();
     if (gi && flat && tgbd_env_int("TGB_GI_KERNEL", TGB_GI_KERNEL_DEFAULT) == 4)
     {
         a.fast_steps = (u32)max(0, min(64, tgbd_env_int("TGB_GI_SHADE_STEPS", 1)));
