@@ -54,7 +54,7 @@
 #define TGB_FAST_DELTA        2.0e-4f  /* DELTA0: sideways displacement (world units) a decision must survive at the start of the ray */
 #define TGB_FAST_DELTA_STEP   0.15f    /* DELTA1 / DELTA0: growth per box entered (3e-5 for DELTA0 = 2e-4) */
 #define TGB_FAST_SHALLOW      1.0e-3f  /* direction components below this (zero included) go to the exact kernel */
-#define TGB_FAST_SHALLOW_PER_AXIS 1.0e-4f /* the same for the walk with one margin per axis (tgb_fast_walk_tiled) */
+#define TGB_FAST_SHALLOW_PER_AXIS 1.0e-6f /* the same for the walk with one margin per axis (tgb_fast_walk_tiled) */
 #define TGB_FAST_MAX_STEPS    256u     /* cells a ray may enter here (median 5, 99.9 % below 220); the few that skim along a leaf layer for longer go to the exact kernel: */
 #define TGB_FAST_MAX_STEPS_UNCERTAIN 64u /* one ray of 1,000 cells is a 0.2 ms dependent chain that the whole kernel waits for. A ray already uncertain can only still end occluded; it gets less */
 #define TGB_FAST_FAR_FRACTION 0.99f    /* a solid voxel beyond this fraction of the far plane is not decided here */
@@ -276,6 +276,37 @@ struct tgb_fast_tiling
     const u32* p_bricks;             /* [n_leaves * 64] */
 };
 
+/* is the voxel (x, y, z) free space -- outside the root, in a box of free cells, in an empty brick, or an empty voxel of a brick with solid ones? */
+TGB_HD bool tgb_fast_voxel_free(const tgb_gi_frame* f, const tgb_fast_tiling* tl, i32 x, i32 y, i32 z)
+{
+    if ((u32)(x | y | z) >= (u32)TG_SVO_SIDE_LENGTH) return true;
+    const u32 entry = TGB_LDG(&tl->p_cells[(((u32)z & 0x3E0u) << 5) | ((u32)y & 0x3E0u) | ((u32)x >> 5)]);
+    if (!(entry & TGB_CELLS_LEAF)) return true;
+    const u32 lp = entry & 0x0FFFFFFFu;
+    const u32 be = TGB_LDG(&tl->p_bricks[(lp << 6) | (((u32)z & 24u) << 1) | (((u32)y & 24u) >> 1) | (((u32)x & 24u) >> 3)]);
+    if (!(be & TGB_BRICK_SOLID)) return true;
+    const u32 row = TGB_LDG(&f->p_voxels[(lp << 10) | (((u32)z & 31u) << 5) | ((u32)y & 31u)]);
+    return ((row >> ((u32)x & 31u)) & 1u) == 0u;
+}
+
+/*
+ * A step that passed an edge within the margins is not lost yet: what a displaced ray can do there is pass the edge on its other
+ * side, through a cell the ideal ray does not visit. While the ideal ray is that close to the edge (an interval of at most 3 (w_x + w_y + w_z)
+ * around the crossing at time t), every displaced ray stays inside the cube p(t) +- h, h_k = DELTA(n) + 3 (w_x + w_y + w_z) |d_k|; if every cell
+ * that meets the cube is free space, nothing can be hit there whichever side is taken, and once past the edge the displaced ray is in
+ * the cell the ideal ray is in. With h_k < 1/2 the cube meets at most the eight voxels around its corners.
+ */
+TGB_HD bool tgb_fast_cube_free(const tgb_gi_frame* f, const tgb_fast_tiling* tl, const tgb_fast_ray* r, f32 t, f32 m, f32 w_sum)
+{
+    const f32 hx = fmaf(3.0f * w_sum, fabsf(r->d.x), m), hy = fmaf(3.0f * w_sum, fabsf(r->d.y), m), hz = fmaf(3.0f * w_sum, fabsf(r->d.z), m);
+    if (!(hx < 0.49f && hy < 0.49f && hz < 0.49f)) return false;
+    const f32 px = fmaf(t, r->d.x, r->ob.x), py = fmaf(t, r->d.y, r->ob.y), pz = fmaf(t, r->d.z, r->ob.z);
+    const i32 x0 = (i32)floorf(px - hx), x1 = (i32)floorf(px + hx), y0 = (i32)floorf(py - hy), y1 = (i32)floorf(py + hy), z0 = (i32)floorf(pz - hz), z1 = (i32)floorf(pz + hz);
+    bool free_ = true;
+    for (u32 i = 0; i < 8u; i++) free_ = free_ && tgb_fast_voxel_free(f, tl, (i & 1u) ? x1 : x0, (i & 2u) ? y1 : y0, (i & 4u) ? z1 : z0);
+    return free_;
+}
+
 /*
  * tgb_fast_walk over the coarser tiling. Same contract; `r->entry` caches the p_cells entry of `r->cell`.
  *
@@ -290,7 +321,7 @@ struct tgb_fast_tiling
  * the cells every displaced ray visits. Each w_k also carries the rounding of the times themselves (2.5e-7 t, twice per comparison).
  * Here `r->w` is DELTA(n) itself, in world units (tgb_fast_start with per_axis).
  */
-TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl, tgb_fast_ray* r, u32 steps, u32* p_n_cells, u32* p_n_voxels, u32 max_steps = TGB_FAST_MAX_STEPS, u32 max_steps_uncertain = TGB_FAST_MAX_STEPS_UNCERTAIN)
+TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl, tgb_fast_ray* r, u32 steps, u32* p_n_cells, u32* p_n_voxels, u32 max_steps = TGB_FAST_MAX_STEPS, u32 max_steps_uncertain = TGB_FAST_MAX_STEPS_UNCERTAIN, bool cube_check = true)
 {
     i32 vx = r->vx, vy = r->vy, vz = r->vz;
     f32 t_cur = r->t_cur, w_n = r->w;
@@ -345,11 +376,18 @@ TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl,
         /* entered / left next to an edge: a second plane within the pair's margin of the entry / exit plane (the plane itself always counts) */
         const bool bx = n_max - nx < wx + w_a, by = n_max - ny < wy + w_a, bz = n_max - nz < wz + w_a;
         const bool cx = fx - t_exit < wx + w_e, cy = fy - t_exit < wy + w_e, cz = fz - t_exit < wz + w_e;
-        bool uncertain = ((bx & by) | (bx & bz) | (by & bz)) | ((cx & cy) | (cx & cz) | (cy & cz));
+        bool near_edge = (bx & by) | (bx & bz) | (by & bz), far_edge = (cx & cy) | (cx & cz) | (cy & cz);
         /* started inside the cell: any near plane within its own margin behind the starting point */
-        if (flags & TGB_FAST_FIRST) uncertain = uncertain | (t_cur - nx < wx) | (t_cur - ny < wy) | (t_cur - nz < wz);
+        if (flags & TGB_FAST_FIRST) near_edge = near_edge | (t_cur - nx < wx) | (t_cur - ny < wy) | (t_cur - nz < wz);
         const f32 w = w_a + w_e;
-        uncertain = uncertain | ((t_exit - t_in) < (solid ? w + w : w));
+        const bool brief = (t_exit - t_in) < (solid ? w + w : w);
+        bool uncertain = near_edge | far_edge | brief;
+        if (cube_check && uncertain && !solid)
+        {
+            /* the edges passed lie in free space on every side? (a cell met only briefly lies between its entry and its exit point) */
+            const f32 w_sum = (wx + wy) + wz;
+            uncertain = ((near_edge | brief) && !tgb_fast_cube_free(f, tl, r, t_in, w_n, w_sum)) || ((far_edge | brief) && !tgb_fast_cube_free(f, tl, r, t_next, w_n, w_sum));
+        }
         if (solid && !uncertain)
         {
             if (t_in < TGB_FAST_FAR_FRACTION * f->far_plane) { kind = TGB_FAST_OCCLUDED; break; }

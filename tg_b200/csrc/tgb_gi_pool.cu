@@ -255,6 +255,13 @@ __global__ void __launch_bounds__(TGB_LIST_THREADS) k_gi_trace_list(const tgb_gi
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
     const u32 lane = threadIdx.x & 31u;
     const u32 n_rays = p_q_count[count_word];
+    /* rays_per_grab == 0: every warp takes its share of the list at once -- one ray while there are fewer rays than warps */
+    if (rays_per_grab == 0u)
+    {
+        const u32 n_warps = gridDim.x * (TGB_LIST_THREADS / 32u);
+        rays_per_grab = (n_rays + n_warps - 1u) / n_warps;
+        rays_per_grab = rays_per_grab < 1u ? 1u : (rays_per_grab > 32u ? 32u : rays_per_grab);
+    }
     u32 n_visits = 0, n_steps = 0, n_advances = 0;
     for (;;)
     {
@@ -338,10 +345,10 @@ extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, cons
     if (p_list && tgbd_env_int("TGB_GI_LIST_KERNEL", 1))
     {
         /* the handed-over rays: k_gi_trace_list (TGB_GI_LIST_KERNEL=0: the pool kernel in list mode, the measured predecessor) */
-        const u32 rays_per_grab = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_RAYS", 4)));
+        const u32 rays_per_grab = (u32)max(0, min(32, tgbd_env_int("TGB_GI_LIST_RAYS", 0)));
         const u32 list_ctas = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_CTAS_PER_SM", 16)));
         k_gi_trace_list<<<d->n_sms * list_ctas, TGB_LIST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
-                                                                                  rays_per_grab, (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 4)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 64)));
+                                                                                  rays_per_grab, (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 64)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 1024)));
         TGB_LAUNCH_CHECK(d);
         return TG_TRUE;
     }
