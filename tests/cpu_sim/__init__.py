@@ -26,7 +26,7 @@ def lib():
         L.tgbsim_gi_trace.restype = C.c_uint32
         L.tgbsim_gi_fast.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_float, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.tgbsim_fast_tiling.argtypes = [u32p, u32p, C.c_uint32, u32p, u32p]
-        L.tgbsim_gi_fast_tiled.argtypes = [f32p, f32p, C.c_float, u32p, u32p, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_float,
+        L.tgbsim_gi_fast_tiled.argtypes = [f32p, f32p, C.c_float, u32p, u32p, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_float, C.c_uint32,
                                            C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), u32p]
         L.tgbsim_svo_traverse.argtypes = [u32p, u32p, u32p, f32p, f32p, C.c_float, C.c_uint32, f32p, f32p, f32p, u32p, u32p, C.POINTER(C.c_uint64)]
         L.tgbsim_visibility.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -77,8 +77,9 @@ def fast_tiling(grid, voxels):
     return cells, bricks
 
 
-def gi_fast_tiled(bmin, bmax, far_plane, grid, voxels, tiling, origins, dirs, steps=8, delta=1.0e-3, want_steps=False):
-    """gi_fast over the coarser tiling -> (result, work[3]: boxes of free cells entered, cells of leaf blocks entered, rays handed over[, steps per ray])"""
+def gi_fast_tiled(bmin, bmax, far_plane, grid, voxels, tiling, origins, dirs, steps=8, delta=1.0e-3, want_steps=False, cube=False):
+    """gi_fast over the coarser tiling -> (result, work[3]: boxes of free cells entered, cells of leaf blocks entered, rays handed over[, steps per ray]);
+    cube: with the cube check of near-edge steps and without step caps, as the second stage (k_gi_trace_list) walks the rays the bulk kernels hand over"""
     origins = np.ascontiguousarray(origins, dtype=np.float32)
     dirs = np.ascontiguousarray(dirs, dtype=np.float32)
     bmin = np.asarray(bmin, dtype=np.float32); bmax = np.asarray(bmax, dtype=np.float32)
@@ -86,7 +87,7 @@ def gi_fast_tiled(bmin, bmax, far_plane, grid, voxels, tiling, origins, dirs, st
     work = np.zeros(3, dtype=np.uint64)
     per_ray = np.zeros(len(origins), dtype=np.uint32)
     lib().tgbsim_gi_fast_tiled(_p(bmin, C.c_float), _p(bmax, C.c_float), far_plane, _p(grid, C.c_uint32), _p(voxels, C.c_uint32), _p(tiling[0], C.c_uint32),
-                               _p(tiling[1], C.c_uint32), len(origins), _p(origins, C.c_float), _p(dirs, C.c_float), steps, delta, _p(result, C.c_uint8),
+                               _p(tiling[1], C.c_uint32), len(origins), _p(origins, C.c_float), _p(dirs, C.c_float), steps, delta, 1 if cube else 0, _p(result, C.c_uint8),
                                _p(work, C.c_uint64), _p(per_ray, C.c_uint32))
     return (result, work, per_ray) if want_steps else (result, work)
 

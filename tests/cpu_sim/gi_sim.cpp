@@ -237,9 +237,10 @@ void tgbsim_fast_tiling(const u32* p_grid, const u32* p_voxels, u32 n_leaves, u3
     }
 }
 
-/* tgbsim_gi_fast over the coarser tiling; p_steps (optional): cells entered per ray */
+/* tgbsim_gi_fast over the coarser tiling; cube = 0: as the bulk kernels walk (k_shade, k_gi_trace_fast), 1: as the second stage walks the rays they hand
+ * over (cube check of near-edge steps, no step caps to speak of: k_gi_trace_list); p_steps (optional): cells entered per ray */
 void tgbsim_gi_fast_tiled(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, const u32* p_cells, const u32* p_bricks,
-                          u32 n, const f32* p_origins, const f32* p_dirs, u32 steps, f32 delta, u8* p_result, u64* p_work, u32* p_steps)
+                          u32 n, const f32* p_origins, const f32* p_dirs, u32 steps, f32 delta, u32 cube, u8* p_result, u64* p_work, u32* p_steps)
 {
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane, p_grid, p_voxels);
@@ -255,7 +256,7 @@ void tgbsim_gi_fast_tiled(const f32* p_bmin, const f32* p_bmax, f32 far_plane, c
         memset(&r, 0, sizeof r);
         u32 n_cells = 0, n_voxels = 0;
         u32 kind = tgb_fast_start(&fr, origin, d, e0, delta, &r, true);
-        while (kind == TGB_FAST_WALK) kind = tgb_fast_walk_tiled(&fr, &tl, &r, steps, &n_cells, &n_voxels);
+        while (kind == TGB_FAST_WALK) kind = cube ? tgb_fast_walk_tiled<true>(&fr, &tl, &r, steps, &n_cells, &n_voxels, 4096u, 4096u) : tgb_fast_walk_tiled<false>(&fr, &tl, &r, steps, &n_cells, &n_voxels);
         if (kind == TGB_FAST_UNOCCLUDED && (r.flags & TGB_FAST_UNCERTAIN)) kind = TGB_FAST_EXACT;
         p_result[i] = kind == TGB_FAST_OCCLUDED ? 1 : (kind == TGB_FAST_UNOCCLUDED ? 0 : 2);
         if (p_work) { p_work[0] += n_cells; p_work[1] += n_voxels; p_work[2] += kind == TGB_FAST_EXACT ? 1 : 0; }

@@ -194,16 +194,16 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fa
         }
 
         if (kind == TGB_FAST_WALK)
-            kind = TILED ? tgb_fast_walk_tiled(&fr, &tiling, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain)
+            kind = TILED ? tgb_fast_walk_tiled<false>(&fr, &tiling, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain)
                          : tgb_fast_walk(&fr, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain);
     }
-    /* [2] cells (empty boxes and voxels) entered by the fast walk in this frame; the exact kernel adds its look-ups there and counts its DDA steps in [3]; [14] rays handed over */
+    /* [2] cells (empty boxes and voxels) entered by the fast walk in this frame; the exact kernel adds its look-ups there and counts its DDA steps in [3]; [15] rays handed over ([14], rays that needed the exact walk, is counted by the second stage) */
     n_cells = __reduce_add_sync(0xFFFFFFFFu, n_cells);
     n_exact = __reduce_add_sync(0xFFFFFFFFu, n_exact);
     if (lane == 0)
     {
         atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_cells);
-        atomicAdd(&p_q_count[14], n_exact);
+        atomicAdd(&p_q_count[15], n_exact);
     }
 }
 

@@ -321,7 +321,11 @@ TGB_HD bool tgb_fast_cube_free(const tgb_gi_frame* f, const tgb_fast_tiling* tl,
  * the cells every displaced ray visits. Each w_k also carries the rounding of the times themselves (2.5e-7 t, twice per comparison).
  * Here `r->w` is DELTA(n) itself, in world units (tgb_fast_start with per_axis).
  */
-TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl, tgb_fast_ray* r, u32 steps, u32* p_n_cells, u32* p_n_voxels, u32 max_steps = TGB_FAST_MAX_STEPS, u32 max_steps_uncertain = TGB_FAST_MAX_STEPS_UNCERTAIN, bool cube_check = true)
+/* CUBE: with the cube check of steps that pass an edge (tgb_fast_cube_free). The bulk kernels run without it -- a rare, long, divergent piece of
+ * code inside the hot loop cost them a fifth of their time (profiles/r04d_*) -- and hand such rays over; the second stage (k_gi_trace_list) walks
+ * them again with it before it resorts to the shader's own arithmetic. */
+template <bool CUBE>
+TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl, tgb_fast_ray* r, u32 steps, u32* p_n_cells, u32* p_n_voxels, u32 max_steps = TGB_FAST_MAX_STEPS, u32 max_steps_uncertain = TGB_FAST_MAX_STEPS_UNCERTAIN)
 {
     i32 vx = r->vx, vy = r->vy, vz = r->vz;
     f32 t_cur = r->t_cur, w_n = r->w;
@@ -382,7 +386,7 @@ TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl,
         const f32 w = w_a + w_e;
         const bool brief = (t_exit - t_in) < (solid ? w + w : w);
         bool uncertain = near_edge | far_edge | brief;
-        if (cube_check && uncertain && !solid)
+        if (CUBE && uncertain && !solid)
         {
             /* the edges passed lie in free space on every side? (a cell met only briefly lies between its entry and its exit point) */
             const f32 w_sum = (wx + wy) + wz;

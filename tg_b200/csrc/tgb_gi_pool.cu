@@ -20,6 +20,7 @@
  */
 #include "tgb_device.cuh"
 #include "tgb_gi_walk.cuh"
+#include "tgb_gi_fast.cuh"
 
 #define TGB_POOL_THREADS 128
 #define TGB_POOL_WORDS   16
@@ -42,7 +43,8 @@ __global__ void __launch_bounds__(TGB_POOL_THREADS) k_gi_trace_pool(const tgb_gi
     /* the whole queue (p_list == NULL: p_q_count[0] rays, fetch counter [1]) or the slots k_gi_trace_fast handed over (tgb_gi_fast.cu:
      * p_q_count[count_word] entries of p_list, fetch counter [count_word + 1]) */
     const u32 n_rays = p_q_count[LIST ? count_word : 0u];
-    if (!LIST && blockIdx.x == 0 && tid == 0) { atomicAdd(&p_q_count[10], n_rays); atomicAdd(&p_q_count[14], n_rays); } /* rays of the frame, summed over its bands; all of them traced exactly */
+    if (!LIST && blockIdx.x == 0 && tid == 0) { atomicAdd(&p_q_count[10], n_rays); atomicAdd(&p_q_count[14], n_rays); }
+    if (LIST && blockIdx.x == 0 && tid == 0) atomicAdd(&p_q_count[14], n_rays); /* rays of the frame, summed over its bands; all of them traced exactly */
     /* CTAs beyond what the queue can feed (a band, a screen tile of a sharded frame) leave at once. min_rays_per_slot > 1 would keep
      * even fewer CTAs so that every ray slot sees several rays; measured on a 272-row tile (873 k rays): 0.41 ms with 1, 0.49 with 4, 0.69
      * with 8 -- with few rays the longest dependent chains set the duration and parallelism is all that helps (profiles/r02k) */
@@ -250,7 +252,7 @@ static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, co
 #define TGB_LIST_THREADS 64
 __global__ void __launch_bounds__(TGB_LIST_THREADS) k_gi_trace_list(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                     const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, const u32* __restrict__ p_list, u32 count_word,
-                                                                    float4* __restrict__ p_out, u32 rays_per_grab, u32 tree_reps, u32 dda_steps)
+                                                                    float4* __restrict__ p_out, u32 rays_per_grab, u32 tree_reps, u32 dda_steps, const tgb_fast_tiling tiling, f32 careful_delta)
 {
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
     const u32 lane = threadIdx.x & 31u;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(TGB_LIST_THREADS) k_gi_trace_list(const tgb_gi
         rays_per_grab = (n_rays + n_warps - 1u) / n_warps;
         rays_per_grab = rays_per_grab < 1u ? 1u : (rays_per_grab > 32u ? 32u : rays_per_grab);
     }
-    u32 n_visits = 0, n_steps = 0, n_advances = 0;
+    u32 n_visits = 0, n_steps = 0, n_advances = 0, n_exact = 0;
     for (;;)
     {
         u32 base = 0;
@@ -275,12 +277,25 @@ __global__ void __launch_bounds__(TGB_LIST_THREADS) k_gi_trace_list(const tgb_gi
             const u32 slot = __ldcs(&p_list[mine]);
             const float4 q0 = __ldcg(&p_q0[slot]), q1 = __ldcs(&p_q1[slot]);
             const v3 origin = tgb_v3(q0.x, q0.y, q0.z), d = tgb_v3(q1.x, q1.y, q1.z);
+            bool occluded = false, decided = false;
+            /* second chance for the certificate (careful_delta > 0: the tiling exists): the walk of tgb_gi_fast.cuh once more, this time
+             * looking around every edge it passes (cube check) and with step caps only a runaway would meet; nine handed-over rays of ten
+             * are decided here */
+            if (careful_delta > 0.0f)
+            {
+                tgb_fast_ray r;
+                u32 k = tgb_fast_start(&fr, origin, d, q1.w, careful_delta, &r, true);
+                if (k == TGB_FAST_WALK) k = tgb_fast_walk_tiled<true>(&fr, &tiling, &r, 0xFFFFFFFFu, (u32*)0, (u32*)0, 4096u, 4096u);
+                n_visits += r.n_steps;
+                if (k == TGB_FAST_OCCLUDED) { decided = true; occluded = true; }
+                else if (k == TGB_FAST_UNOCCLUDED && !(r.flags & TGB_FAST_UNCERTAIN)) decided = true;
+            }
             v3 position, t_delta, t_max = tgb_v3(0.0f, 0.0f, 0.0f);
             u32 flags, cell = 0, data = 0, kind = TGB_RAY_TREE;
             i32 x = 0, y = 0, z = 0;
             tgb_gi_ray_start(&fr, origin, d, q1.w, &position, &t_delta, &flags);
-            bool occluded = false;
-            for (;;)
+            if (!decided) n_exact++;
+            while (!decided)
             {
                 if (kind == TGB_RAY_TREE) kind = tgb_gi_tree_phase(&fr, d, t_delta, &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
                 else if (kind == TGB_RAY_DDA)
@@ -322,6 +337,8 @@ __global__ void __launch_bounds__(TGB_LIST_THREADS) k_gi_trace_list(const tgb_gi
     n_visits = __reduce_add_sync(0xFFFFFFFFu, n_visits);
     n_steps = __reduce_add_sync(0xFFFFFFFFu, n_steps);
     n_advances = __reduce_add_sync(0xFFFFFFFFu, n_advances);
+    n_exact = __reduce_add_sync(0xFFFFFFFFu, n_exact);
+    if (lane == 0 && n_exact) atomicAdd(&p_q_count[14], n_exact); /* rays that needed the shader's own arithmetic */
     if (lane == 0 && (n_visits | n_steps | n_advances))
     {
         atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_visits);
@@ -346,9 +363,13 @@ extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, cons
     {
         /* the handed-over rays: k_gi_trace_list (TGB_GI_LIST_KERNEL=0: the pool kernel in list mode, the measured predecessor) */
         const u32 rays_per_grab = (u32)max(0, min(32, tgbd_env_int("TGB_GI_LIST_RAYS", 0)));
+        const bool careful = d->svo.fast_tiling_valid && tgbd_env_int("TGB_GI_LIST_CAREFUL", 1) != 0;
+        tgb_fast_tiling tiling;
+        tiling.p_cells = d->svo.d_fast_cells; tiling.p_bricks = d->svo.d_fast_bricks;
         const u32 list_ctas = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_CTAS_PER_SM", 16)));
         k_gi_trace_list<<<d->n_sms * list_ctas, TGB_LIST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
-                                                                                  rays_per_grab, (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 64)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 1024)));
+                                                                                  rays_per_grab, (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 64)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 1024)),
+                                                                                  tiling, careful ? tgbd_gi_fast_delta() : 0.0f);
         TGB_LAUNCH_CHECK(d);
         return TG_TRUE;
     }

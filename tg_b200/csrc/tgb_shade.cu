@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
         {
             tgb_fast_ray r;
             u32 kind = tgb_fast_start(&a.fast_frame, origin, dir, root_enter, a.fast_delta, &r, true);
-            if (kind == TGB_FAST_WALK) kind = tgb_fast_walk_tiled(&a.fast_frame, &a.fast_tiling, &r, a.fast_steps, (u32*)0, (u32*)0);
+            if (kind == TGB_FAST_WALK) kind = tgb_fast_walk_tiled<false>(&a.fast_frame, &a.fast_tiling, &r, a.fast_steps, (u32*)0, (u32*)0);
             n_cells = r.n_steps;
             if (kind == TGB_FAST_OCCLUDED) decided = true;
             else if (kind == TGB_FAST_UNOCCLUDED && !(r.flags & TGB_FAST_UNCERTAIN))
