@@ -25,8 +25,8 @@ def lib():
         L.tgbsim_gi_trace.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.tgbsim_gi_trace.restype = C.c_uint32
         L.tgbsim_gi_fast.argtypes = [f32p, f32p, C.c_float, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_float, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
-        L.tgbsim_fast_tiling.argtypes = [u32p, u32p, C.c_uint32, u32p, u32p]
-        L.tgbsim_gi_fast_tiled.argtypes = [f32p, f32p, C.c_float, u32p, u32p, u32p, u32p, C.c_uint32, f32p, f32p, C.c_uint32, C.c_float, C.c_uint32,
+        L.tgbsim_fast_tiling.argtypes = [u32p, u32p, C.c_uint32, u32p, u32p, u32p]
+        L.tgbsim_gi_fast_tiled.argtypes = [f32p, f32p, C.c_float, u32p, u32p, u32p, u32p, u32p, C.c_uint32, C.c_uint32, f32p, f32p, C.c_uint32, C.c_float, C.c_uint32,
                                            C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), u32p]
         L.tgbsim_svo_traverse.argtypes = [u32p, u32p, u32p, f32p, f32p, C.c_float, C.c_uint32, f32p, f32p, f32p, u32p, u32p, C.POINTER(C.c_uint64)]
         L.tgbsim_visibility.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -69,12 +69,13 @@ def gi_fast(bmin, bmax, far_plane, grid, voxels, origins, dirs, steps=8, delta=1
 
 
 def fast_tiling(grid, voxels):
-    """the coarser tiling of the certified fast walk (tgb_gi_fast.cuh): (cells u32[32^3], bricks u32[64 * n_leaves])"""
+    """the coarser tiling of the certified fast walk (tgb_gi_fast.cuh): (cells u32[32^3], bricks u32[64 * n_leaves], columns u32[2 * 1024 * n_leaves])"""
     n_leaves = len(voxels) // 1024
     cells = np.zeros(32 ** 3, dtype=np.uint32)
     bricks = np.zeros(max(1, 64 * n_leaves), dtype=np.uint32)
-    lib().tgbsim_fast_tiling(_p(grid, C.c_uint32), _p(voxels, C.c_uint32), n_leaves, _p(cells, C.c_uint32), _p(bricks, C.c_uint32))
-    return cells, bricks
+    columns = np.zeros(max(1, 2 * 1024 * n_leaves), dtype=np.uint32)
+    lib().tgbsim_fast_tiling(_p(grid, C.c_uint32), _p(voxels, C.c_uint32), n_leaves, _p(cells, C.c_uint32), _p(bricks, C.c_uint32), _p(columns, C.c_uint32))
+    return cells, bricks, columns
 
 
 def gi_fast_tiled(bmin, bmax, far_plane, grid, voxels, tiling, origins, dirs, steps=8, delta=1.0e-3, want_steps=False, cube=False):
@@ -87,7 +88,7 @@ def gi_fast_tiled(bmin, bmax, far_plane, grid, voxels, tiling, origins, dirs, st
     work = np.zeros(3, dtype=np.uint64)
     per_ray = np.zeros(len(origins), dtype=np.uint32)
     lib().tgbsim_gi_fast_tiled(_p(bmin, C.c_float), _p(bmax, C.c_float), far_plane, _p(grid, C.c_uint32), _p(voxels, C.c_uint32), _p(tiling[0], C.c_uint32),
-                               _p(tiling[1], C.c_uint32), len(origins), _p(origins, C.c_float), _p(dirs, C.c_float), steps, delta, 1 if cube else 0, _p(result, C.c_uint8),
+                               _p(tiling[1], C.c_uint32), _p(tiling[2], C.c_uint32), len(voxels) // 1024, len(origins), _p(origins, C.c_float), _p(dirs, C.c_float), steps, delta, 1 if cube else 0, _p(result, C.c_uint8),
                                _p(work, C.c_uint64), _p(per_ray, C.c_uint32))
     return (result, work, per_ray) if want_steps else (result, work)
 

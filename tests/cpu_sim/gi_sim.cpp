@@ -199,8 +199,17 @@ extern "C" {
  * The coarser tiling of the fast walk (tgb_gi_fast.cuh, second half) built on the host with the per-cell passes the kernels
  * k_fast_tile_* run (tgb_gi_fast.cu): p_cells[32^3] from the flattened tree, p_bricks[64 * n_leaves] from the leaf blocks' voxels.
  */
-void tgbsim_fast_tiling(const u32* p_grid, const u32* p_voxels, u32 n_leaves, u32* p_cells, u32* p_bricks)
+void tgbsim_fast_tiling(const u32* p_grid, const u32* p_voxels, u32 n_leaves, u32* p_cells, u32* p_bricks, u32* p_columns /* [2][n_leaves * 1024] */)
 {
+    /* the blocks once more with y / z as the bit index (k_fast_tile_columns) */
+    for (u32 leaf = 0; leaf < n_leaves; leaf++)
+    {
+        const u32* block = p_voxels + (uint64_t)leaf * 1024u;
+        u32* cy = p_columns + (uint64_t)leaf * 1024u, *cz = p_columns + (uint64_t)n_leaves * 1024u + (uint64_t)leaf * 1024u;
+        for (u32 i = 0; i < 1024u; i++) { cy[i] = 0; cz[i] = 0; }
+        for (u32 z = 0; z < 32u; z++) for (u32 y = 0; y < 32u; y++) for (u32 x = 0; x < 32u; x++)
+            if ((block[32u * z + y] >> x) & 1u) { cy[32u * z + x] |= 1u << y; cz[32u * y + x] |= 1u << z; }
+    }
     const u32 N = TGB_TOP_GRID_DIM;
     u32* p1 = (u32*)malloc(TGB_TOP_GRID_CELLS * sizeof(u32));
     u32* p2 = (u32*)malloc(TGB_TOP_GRID_CELLS * sizeof(u32));
@@ -239,12 +248,12 @@ void tgbsim_fast_tiling(const u32* p_grid, const u32* p_voxels, u32 n_leaves, u3
 
 /* tgbsim_gi_fast over the coarser tiling; cube = 0: as the bulk kernels walk (k_shade, k_gi_trace_fast), 1: as the second stage walks the rays they hand
  * over (cube check of near-edge steps, no step caps to speak of: k_gi_trace_list); p_steps (optional): cells entered per ray */
-void tgbsim_gi_fast_tiled(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, const u32* p_cells, const u32* p_bricks,
+void tgbsim_gi_fast_tiled(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u32* p_grid, const u32* p_voxels, const u32* p_cells, const u32* p_bricks, const u32* p_columns, u32 n_leaves,
                           u32 n, const f32* p_origins, const f32* p_dirs, u32 steps, f32 delta, u32 cube, u8* p_result, u64* p_work, u32* p_steps)
 {
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane, p_grid, p_voxels);
-    tgb_fast_tiling tl; tl.p_cells = p_cells; tl.p_bricks = p_bricks;
+    tgb_fast_tiling tl; tl.p_cells = p_cells; tl.p_bricks = p_bricks; tl.p_columns = p_columns; tl.columns_stride = (u64)n_leaves * 1024u;
     for (u32 i = 0; i < n; i++)
     {
         const v3 origin = tgb_v3(p_origins[3 * i], p_origins[3 * i + 1], p_origins[3 * i + 2]);

@@ -112,7 +112,7 @@ def test_the_coarser_cells_tile_the_root(oracle, make):
     s = make()
     svo, grid, voxels = _svo(oracle, s)
     oracle.svo_destroy(svo)
-    cells, bricks = cpu_sim.fast_tiling(grid, voxels)
+    cells, bricks, columns = cpu_sim.fast_tiling(grid, voxels)
     has_data = (grid[:-1] >> 31) != 0
     leaf, box = _boxes_of(cells)
     assert np.array_equal(leaf, has_data) and np.array_equal(cells[leaf] & 0x0FFFFFFF, grid[:-1][leaf] & 0x0FFFFFFF)
@@ -201,5 +201,14 @@ def test_tiled_walk_a_million_rays_and_fewer_steps(oracle, make):
         got, work = cpu_sim.gi_fast_tiled(BMIN, BMAX, far, grid, voxels, tiling, o, d, delta=2.0e-4)
         assert (got == 2).sum() <= (plain == 2).sum()
         assert work[0] + work[1] < 0.7 * (work_plain[0] + work_plain[1])
+        # the second stage: the handed-over rays once more with the cube check of near-edge steps (k_gi_trace_fast<.., CUBE>): still never a
+        # wrong decision, and most of them decided
+        for delta in (2.0e-4, 4.0e-5):
+            first, _ = cpu_sim.gi_fast_tiled(BMIN, BMAX, far, grid, voxels, tiling, o, d, delta=delta)
+            h = np.flatnonzero(first == 2)
+            second, _ = cpu_sim.gi_fast_tiled(BMIN, BMAX, far, grid, voxels, tiling, o[h], d[h], delta=delta, cube=True)
+            bad = np.flatnonzero((second != 2) & ((second == 1) != exact[h]))
+            assert len(bad) == 0, f"delta {delta}: careful pass decided {len(bad)} rays differently, first: o={o[h][bad[:2]].tolist()} d={d[h][bad[:2]].tolist()}"
+            assert (second != 2).mean() > 0.25, (delta, (second != 2).mean())
     finally:
         oracle.svo_destroy(svo)

@@ -142,7 +142,7 @@ extern "C" b32 tgbd_resize(struct tgb_device* d, u32 width, u32 height)
     TGB_CUDA(cudaMalloc(&d->d_gi_q0, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMalloc(&d->d_gi_q1, (u64)width * height * sizeof(float4)));
     TGB_CUDA(cudaMalloc(&d->d_gi_q2, (u64)width * height * sizeof(float4)));
-    TGB_CUDA(cudaMalloc(&d->d_gi_exact, (u64)width * height * sizeof(u32)));
+    TGB_CUDA(cudaMalloc(&d->d_gi_exact, (u64)2 * width * height * sizeof(u32))); /* two lists: handed over by the first pass, by the careful pass */
     TGB_CUDA(cudaMemsetAsync(d->d_vis, 0xFF, padded_px * sizeof(u64), d->stream));
     TGB_CUDA(cudaMemsetAsync(d->d_radiance, 0, padded_px * sizeof(float4), d->stream));
     return TG_TRUE;
@@ -203,7 +203,7 @@ extern "C" void tgbd_destroy(struct tgb_device* d)
     if (d->h_visible_count) cudaFreeHost(d->h_visible_count);
     if (d->h_gi_stats) cudaFreeHost(d->h_gi_stats);
     free(d->h_objects);
-    cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts); cudaFree(d->svo.d_top_grid); cudaFree(d->svo.d_fast_cells); cudaFree(d->svo.d_fast_bricks);
+    cudaFree(d->svo.d_nodes); cudaFree(d->svo.d_leaf_data); cudaFree(d->svo.d_voxels); cudaFree(d->svo.d_counts); cudaFree(d->svo.d_top_grid); cudaFree(d->svo.d_fast_cells); cudaFree(d->svo.d_fast_bricks); cudaFree(d->svo.d_fast_columns);
     cudaFree(d->svo.d_pairs_a); cudaFree(d->svo.d_pairs_b); cudaFree(d->svo.d_scratch); cudaFree(d->svo.d_pair_flags); cudaFree(d->svo.d_object_flags); cudaFree(d->svo.d_pair_leaf_a); cudaFree(d->svo.d_pair_leaf_b);
     cudaFree(d->svo.d_voxels_alt); cudaFree(d->svo.d_leaf_data_alt); cudaFree(d->svo.d_object_moved); cudaFree(d->svo.d_moved_indices); cudaFree(d->svo.d_part); cudaFree(d->svo.d_gather);
     cudaFree(d->d_mat); cudaFree(d->d_mat_tile); cudaFree(d->d_objects_global); cudaFree(d->d_frames_global);

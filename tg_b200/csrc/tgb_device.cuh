@@ -32,6 +32,7 @@ struct tgb_svo_device
                            last word: non-zero = the grid describes the tree completely (leaves exactly at depth 5) */
     u32* d_fast_cells;  /* [3 * 32^3] the certified fast walk's coarser tiling of the free table cells (tgb_gi_fast.cuh) + two scratch passes; on first use */
     u32* d_fast_bricks; /* [leaf_capacity * 64] the same per 8^3 brick of every leaf block */
+    u32* d_fast_columns; /* [2 * voxel_word_capacity] the blocks' voxels with y, then with z, as the bit index */
     b32  fast_tiling_valid; /* both describe the current tree */
     u32  n_nodes, n_leaves, n_pairs;
     b32  valid;
@@ -201,5 +202,7 @@ static inline u32* tgbd_mat_object_indices(const struct tgb_device* d, const u64
 #define TGB_GI_KERNEL_DEFAULT 2
 extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st); /* tgb_gi_fast.cu */
 extern "C" f32 tgbd_gi_fast_delta(void);
+struct tgb_fast_tiling;
+extern "C" void tgbd_gi_fast_tiling_get(struct tgb_device* d, struct tgb_fast_tiling* p_tiling);
 
 #endif

@@ -42,8 +42,11 @@ enum { P_OBX = 0, P_OBY, P_OBZ, P_DX, P_DY, P_DZ, P_IX, P_IY, P_IZ, P_W, P_T, P_
  * voxel: tgb_fast_start) and file the ready rays in shared memory, one column per word. A lane whose ray is decided only copies
  * a ready ray into its registers: a service costs neither memory latency nor a set-up run by a quarter of the warp.
  */
-template <bool TILED>
-__global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fast(const tgb_gi_frame fr, const tgb_fast_tiling tiling, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
+/* CUBE: the careful second pass over the slots the first pass handed over (p_in_list, counted in p_q_count[in_count_word], fetched through
+ * p_q_count[in_count_word + 1]): the same walk with the cube check of near-edge steps (tgb_fast_cube_free) and generous step caps; what it
+ * hands over in turn (p_exact_list, counted in p_q_count[out_count_word]) goes to the shader's own arithmetic (k_gi_trace_list). */
+template <bool TILED, bool CUBE>
+__global__ void __launch_bounds__(TGB_FAST_THREADS, (TILED && !CUBE) ? 8 : 1) k_gi_trace_fast(const tgb_gi_frame fr, const tgb_fast_tiling tiling, const u32* __restrict__ p_in_list, u32 in_count_word, u32 out_count_word, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                     const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, u32* __restrict__ p_exact_list,
                                                                     float4* __restrict__ p_out, u32 service_lanes, u32 steps, u32 max_steps, u32 max_steps_uncertain, f32 delta)
 {
@@ -52,9 +55,11 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fa
     __shared__ float4 s_rec[3][TGB_FAST_THREADS];                 /* staged records, one per lane */
     __shared__ u32 s_pool[TGB_FAST_WARPS][P_WORDS][32];           /* ready rays of the warp */
     __shared__ u32 s_cur[5][TGB_FAST_THREADS];                    /* of the ray a lane walks: queue slot, pixel, ambient */
+    __shared__ u32 s_slot[CUBE ? TGB_FAST_THREADS : 1];           /* CUBE: queue slots of the staged records */
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 n_rays = p_q_count[0];
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
+    const u32 n_rays = p_q_count[CUBE ? in_count_word : 0u];
+    if (!CUBE && blockIdx.x == 0 && tid == 0) atomicAdd(&p_q_count[10], n_rays); /* rays of the frame, summed over its bands */
+    if (CUBE && (u64)blockIdx.x * TGB_FAST_THREADS >= (u64)n_rays + TGB_FAST_THREADS) return; /* more CTAs than the list can feed */
 
     tgb_fast_ray r;
     r.ob = r.d = r.inv = r.r = r.posf = tgb_v3(0.0f, 0.0f, 0.0f);
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fa
                 {
                     u32 base = 0;
                     const u32 leader = (u32)(__ffs(handed) - 1);
-                    if (lane == leader) base = atomicAdd(&p_q_count[12], (u32)__popc(handed));
+                    if (lane == leader) base = atomicAdd(&p_q_count[out_count_word], (u32)__popc(handed));
                     base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
                     if (kind == TGB_FAST_EXACT)
                     {
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fa
                                 p[P_W * 32] = __float_as_uint(n.w); p[P_T * 32] = __float_as_uint(n.t_cur);
                                 p[P_VOX * 32] = k0 == TGB_FAST_EXACT ? TGB_FAST_POOL_EXACT
                                                                       : ((u32)n.vx | ((u32)n.vy << 10) | ((u32)n.vz << 20) | ((n.flags & TGB_FAST_FIRST) ? TGB_FAST_POOL_FIRST : 0u));
-                                p[P_SLOT * 32] = staged_base + lane; p[P_PIXEL * 32] = __float_as_uint(q0.w);
+                                p[P_SLOT * 32] = CUBE ? s_slot[tid] : staged_base + lane; p[P_PIXEL * 32] = __float_as_uint(q0.w);
                                 p[P_AX * 32] = __float_as_uint(q2.x); p[P_AY * 32] = __float_as_uint(q2.y); p[P_AZ * 32] = __float_as_uint(q2.z);
                             }
                             __syncwarp();
@@ -145,11 +150,12 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fa
                         if (c_next >= c_end && !drained)
                         {
                             u32 nb = 0;
-                            if (lane == 0) nb = atomicAdd(&p_q_count[1], TGB_FAST_CHUNK);
+                            if (lane == 0) nb = atomicAdd(&p_q_count[CUBE ? in_count_word + 1u : 1u], CUBE ? 32u : TGB_FAST_CHUNK);
                             nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
+                            const u32 chunk = CUBE ? 32u : TGB_FAST_CHUNK; /* the few rays of a list are spread over the warps */
                             c_next = nb < n_rays ? nb : n_rays;
-                            c_end = nb + TGB_FAST_CHUNK < n_rays ? nb + TGB_FAST_CHUNK : n_rays;
-                            drained = nb + TGB_FAST_CHUNK >= n_rays;
+                            c_end = nb + chunk < n_rays ? nb + chunk : n_rays;
+                            drained = nb + chunk >= n_rays;
                         }
                         if (c_next < c_end)
                         {
@@ -158,9 +164,11 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fa
                             c_next += staged_n;
                             if (lane < staged_n)
                             {
-                                tgb_cp_async16(&s_rec[0][tid], &p_q0[staged_base + lane]);
-                                tgb_cp_async16(&s_rec[1][tid], &p_q1[staged_base + lane]);
-                                tgb_cp_async16(&s_rec[2][tid], &p_q2[staged_base + lane]);
+                                const u32 slot = CUBE ? p_in_list[staged_base + lane] : staged_base + lane;
+                                if (CUBE) s_slot[tid] = slot;
+                                tgb_cp_async16(&s_rec[0][tid], &p_q0[slot]);
+                                tgb_cp_async16(&s_rec[1][tid], &p_q1[slot]);
+                                tgb_cp_async16(&s_rec[2][tid], &p_q2[slot]);
                             }
                             tgb_cp_async_commit();
                         }
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fa
         }
 
         if (kind == TGB_FAST_WALK)
-            kind = TILED ? tgb_fast_walk_tiled<false>(&fr, &tiling, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain)
+            kind = TILED ? tgb_fast_walk_tiled<CUBE>(&fr, &tiling, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain)
                          : tgb_fast_walk(&fr, &r, steps, (u32*)0, (u32*)0, max_steps, max_steps_uncertain);
     }
     /* [2] cells (empty boxes and voxels) entered by the fast walk in this frame; the exact kernel adds its look-ups there and counts its DDA steps in [3]; [15] rays handed over ([14], rays that needed the exact walk, is counted by the second stage) */
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(TGB_FAST_THREADS, TILED ? 8 : 1) k_gi_trace_fa
     if (lane == 0)
     {
         atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_cells);
-        atomicAdd(&p_q_count[15], n_exact);
+        if (!CUBE) atomicAdd(&p_q_count[15], n_exact);
     }
 }
 
@@ -256,11 +264,37 @@ __global__ void __launch_bounds__(256) k_fast_tile_bricks(const u32* __restrict_
         p_bricks[(u64)leaf * 64u + b] = any ? TGB_BRICK_SOLID : tgb_tile_brick_entry(s_p2[g][b], tgb_tile_pass3(occ, g2, 4u, bx, by, bz));
 }
 
+/* the leaf blocks' voxels once more with y, and with z, as the bit index (tgb_fast_tiling::p_columns): one CTA per block, one warp per z slice (y copy) and
+ * per y line of slices (z copy), a 32 x 32 bit transpose by 32 ballots each */
+__global__ void __launch_bounds__(1024) k_fast_tile_columns(const u32* __restrict__ p_voxels, u32* __restrict__ p_columns_y, u32* __restrict__ p_columns_z)
+{
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const u32* p_block = p_voxels + (u64)blockIdx.x * TG_SVO_BLOCK_WORDS;
+    const u32 row_y = p_block[32u * w + lane];    /* slice z = w, row y = lane */
+    const u32 row_z = p_block[32u * lane + w];    /* slice z = lane, row y = w */
+    u32 out_y = 0, out_z = 0;
+#pragma unroll
+    for (u32 x = 0; x < 32u; x++)
+    {
+        const u32 by = __ballot_sync(0xFFFFFFFFu, (row_y >> x) & 1u);   /* bit y = voxel (x, y, w) */
+        const u32 bz = __ballot_sync(0xFFFFFFFFu, (row_z >> x) & 1u);   /* bit z = voxel (x, w, z) */
+        if (lane == x) { out_y = by; out_z = bz; }
+    }
+    p_columns_y[(u64)blockIdx.x * TG_SVO_BLOCK_WORDS + 32u * w + lane] = out_y;   /* word 32 z + x */
+    p_columns_z[(u64)blockIdx.x * TG_SVO_BLOCK_WORDS + 32u * w + lane] = out_z;   /* word 32 y + x */
+}
+
 /* DELTA0 of the certificate. TGB_GI_FAST_DELTA_PERCENT (tests, margin studies) scales it: the product runs at 100, a frame that still equals the exact
  * kernel's at 25 shows a fourfold margin on that frame's rays */
 extern "C" f32 tgbd_gi_fast_delta(void)
 {
     return TGB_FAST_DELTA * 0.01f * (f32)max(0, min(1000, tgbd_env_int("TGB_GI_FAST_DELTA_PERCENT", 100)));
+}
+
+extern "C" void tgbd_gi_fast_tiling_get(struct tgb_device* d, tgb_fast_tiling* p_tiling)
+{
+    p_tiling->p_cells = d->svo.d_fast_cells; p_tiling->p_bricks = d->svo.d_fast_bricks;
+    p_tiling->p_columns = d->svo.d_fast_columns; p_tiling->columns_stride = d->svo.voxel_word_capacity;
 }
 
 /* called behind k_svo_flatten (tgb_svo.cu) on the stream of the build when the tiled walk is selected, else lazily by the first trace */
@@ -271,6 +305,7 @@ extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st)
     {
         TGB_CUDA(cudaMalloc(&s->d_fast_cells, (u64)3 * TGB_TOP_GRID_CELLS * sizeof(u32)));
         TGB_CUDA(cudaMalloc(&s->d_fast_bricks, (u64)s->leaf_capacity * 64u * sizeof(u32)));
+        TGB_CUDA(cudaMalloc(&s->d_fast_columns, (u64)2 * s->voxel_word_capacity * sizeof(u32)));
     }
     u32* p1 = s->d_fast_cells + TGB_TOP_GRID_CELLS, *p2 = s->d_fast_cells + 2 * TGB_TOP_GRID_CELLS;
     for (u32 pass = 1; pass <= 3u; pass++)
@@ -282,6 +317,8 @@ extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st)
     {
         k_fast_tile_bricks<<<(s->n_leaves + 3u) / 4u, 256, 0, st>>>(s->d_voxels, s->n_leaves, s->d_fast_bricks);
         TGB_LAUNCH_CHECK(d);
+        k_fast_tile_columns<<<s->n_leaves, 1024, 0, st>>>(s->d_voxels, s->d_fast_columns, s->d_fast_columns + s->voxel_word_capacity);
+        TGB_LAUNCH_CHECK(d);
     }
     s->fast_tiling_valid = TG_TRUE;
     return TG_TRUE;
@@ -291,6 +328,11 @@ extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st)
  * One band of rays (called by tgbd__shade_launch, tgb_shade.cu, after k_shade queued them): the fast walk over the whole queue, then
  * the exact kernel over the slots it handed over (p_q_count[12] of them, read on the device).
  */
+__global__ void k_gi_reset_lists(u32* __restrict__ p_q_count)
+{
+    if (threadIdx.x < 2u) { p_q_count[12u + threadIdx.x] = 0u; p_q_count[16u + threadIdx.x] = 0u; } /* handed over / fetched: first pass, careful pass */
+}
+
 extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane, b32 tiled)
 {
     if (tiled && !d->svo.fast_tiling_valid && !tgbd_gi_fast_tiling_build(d, d->stream)) return TG_FALSE;
@@ -300,15 +342,24 @@ extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane, b32 tiled
     const u32 max_steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_MAX_STEPS", (i32)TGB_FAST_MAX_STEPS)), max_steps_uncertain = (u32)max(1, tgbd_env_int("TGB_GI_FAST_MAX_STEPS_UNCERTAIN", (i32)TGB_FAST_MAX_STEPS_UNCERTAIN));
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);
-    k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count + 12, 2, 0u); /* handed over / fetched by the exact kernel */
+    k_gi_reset_lists<<<1, 32, 0, d->stream>>>(d->d_gi_count);
     TGB_LAUNCH_CHECK(d);
     const f32 delta = tgbd_gi_fast_delta();
     tgb_fast_tiling tiling;
-    tiling.p_cells = d->svo.d_fast_cells; tiling.p_bricks = d->svo.d_fast_bricks;
-    if (tiled) k_gi_trace_fast<true><<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, tiling, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
-                                                                                                  service_lanes, steps, max_steps, max_steps_uncertain, delta);
-    else       k_gi_trace_fast<false><<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(fr, tiling, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, d->d_gi_exact, d->d_radiance,
-                                                                                                   service_lanes, steps, max_steps, max_steps_uncertain, delta);
+    tgbd_gi_fast_tiling_get(d, &tiling);
+    u32* p_list_a = d->d_gi_exact, *p_list_b = d->d_gi_exact + (u64)d->width * d->height;
+#define TGB_FAST_ARGS(IN, IN_WORD, OUT, OUT_WORD, SVC, STEPS, CAP, CAP_U) fr, tiling, IN, IN_WORD, OUT_WORD, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, OUT, d->d_radiance, SVC, STEPS, CAP, CAP_U, delta
+    if (tiled) k_gi_trace_fast<true, false><<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(TGB_FAST_ARGS((const u32*)NULL, 0u, p_list_a, 12u, service_lanes, steps, max_steps, max_steps_uncertain));
+    else       k_gi_trace_fast<false, false><<<d->n_sms * ctas_per_sm, TGB_FAST_THREADS, 0, d->stream>>>(TGB_FAST_ARGS((const u32*)NULL, 0u, p_list_a, 12u, service_lanes, steps, max_steps, max_steps_uncertain));
     TGB_LAUNCH_CHECK(d);
-    return tgbd_gi_pool_trace_list(d, far_plane, d->d_gi_exact, 12u);
+    if (tiled && tgbd_env_int("TGB_GI_FAST_CAREFUL", 1))
+    {
+        /* the careful pass over what was handed over; its own hand-overs go to the shader's arithmetic */
+        const u32 careful_ctas = (u32)max(1, min(16, tgbd_env_int("TGB_GI_FAST_CAREFUL_CTAS_PER_SM", 4)));
+        k_gi_trace_fast<true, true><<<d->n_sms * careful_ctas, TGB_FAST_THREADS, 0, d->stream>>>(TGB_FAST_ARGS(p_list_a, 12u, p_list_b, 16u, (u32)max(1, min(32, tgbd_env_int("TGB_GI_FAST_CAREFUL_SERVICE_LANES", 1))), steps, 4096u, 4096u));
+        TGB_LAUNCH_CHECK(d);
+        return tgbd_gi_pool_trace_list(d, far_plane, p_list_b, 16u);
+    }
+#undef TGB_FAST_ARGS
+    return tgbd_gi_pool_trace_list(d, far_plane, p_list_a, 12u);
 }

@@ -204,7 +204,11 @@ TGB_HD u32 tgb_fast_walk(const tgb_gi_frame* f, tgb_fast_ray* r, u32 steps, u32*
  *   top level   the 32^3 table cells that hold no leaf data are merged into boxes of cells: a cell's free run along x, runs of
  *               neighbouring rows along z with the same x extent, then along y with the same (x, z) extent (tgb_tile_*: three
  *               passes, every cell finds its box on its own, all cells of a box find the same one -- a tiling by construction);
- *   leaf level  a leaf block is 4^3 bricks of 8^3 voxels; bricks without a solid voxel are merged the same way inside their block.
+ *   leaf level  a leaf block is 4^3 bricks of 8^3 voxels; bricks without a solid voxel are merged the same way inside their block;
+ *   runs        inside a brick that holds solid voxels the free voxels are taken in runs along the ray's DOMINANT axis (a run = the free
+ *               voxels of one voxel line between two solid ones, at most the brick's 8): one bit scan of the line's word, which the
+ *               voxel test reads anyway -- from the block's rows when x dominates, from copies of the block with y or z as the bit index
+ *               otherwise (tgb_fast_tiling::p_columns). Three tilings, then, and a ray stays with one.
  *
  * A step then enters one of: a voxel of a non-empty brick (side 1), a box of empty bricks (sides 8 .. 32), a box of empty table
  * cells (sides 32 .. 1024). What changes in the certificate is only the count of the shader's advances, which DELTA(n) grows with:
@@ -274,7 +278,24 @@ struct tgb_fast_tiling
 {
     const u32* p_cells;              /* [32^3] */
     const u32* p_bricks;             /* [n_leaves * 64] */
+    const u32* p_columns;            /* [2][n_leaves * 1024] the blocks' voxels once more with y, then with z as the bit index (word 32 z + x / 32 y + x) */
+    u64 columns_stride;              /* words between the two copies */
 };
+
+#ifdef __CUDA_ARCH__
+#define tgb_clz(v) __clz((int)(v))
+#define tgb_ffs(v) __ffs((int)(v))
+#else
+#define tgb_clz(v) __builtin_clz((unsigned)(v))
+#define tgb_ffs(v) __builtin_ffs((int)(v))
+#endif
+
+/* the axis whose voxel lines the walk takes its runs from: 0 = x, 1 = y, 2 = z */
+TGB_HD u32 tgb_fast_dominant_axis(v3 d)
+{
+    const f32 ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    return (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
+}
 
 /* is the voxel (x, y, z) free space -- outside the root, in a box of free cells, in an empty brick, or an empty voxel of a brick with solid ones? */
 TGB_HD bool tgb_fast_voxel_free(const tgb_gi_frame* f, const tgb_fast_tiling* tl, i32 x, i32 y, i32 z)
@@ -333,6 +354,7 @@ TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl,
     u32 kind = TGB_FAST_WALK;
     u32 k = 0;
     const f32 sum_abs_d = (fabsf(r->d.x) + fabsf(r->d.y)) + fabsf(r->d.z);
+    const u32 axis = tgb_fast_dominant_axis(r->d);
     for (;;)
     {
         /* ---- the cell of the tiling around (vx, vy, vz): one decode for the three kinds. A box is (e, shift, base): corner and sides - 1 in
@@ -349,10 +371,23 @@ TGB_HD u32 tgb_fast_walk_tiled(const tgb_gi_frame* f, const tgb_fast_tiling* tl,
             const u32 lp = entry & 0x0FFFFFFFu;
             const u32 brick = (((u32)vz & 24u) << 1) | (((u32)vy & 24u) >> 1) | (((u32)vx & 24u) >> 3);
             const u32 be = TGB_LDG(&tl->p_bricks[(lp << 6) | brick]);
-            const u32 row = TGB_LDG(&f->p_voxels[(lp << 10) | (((u32)vz & 31u) << 5) | ((u32)vy & 31u)]);
+            /* the voxel line through (vx, vy, vz) along the dominant axis: word and bit index */
+            const u32 lx = (u32)vx & 31u, ly = (u32)vy & 31u, lz = (u32)vz & 31u;
+            const u32 line = axis == 0u ? ((lz << 5) | ly) : (axis == 1u ? ((lz << 5) | lx) : ((ly << 5) | lx));
+            const u32 pos = axis == 0u ? lx : (axis == 1u ? ly : lz);
+            const u32* p_lines = axis == 0u ? f->p_voxels : tl->p_columns + (axis == 1u ? 0u : tl->columns_stride);
+            const u32 row = TGB_LDG(&p_lines[(lp << 10) | line]);
             const bool voxel = (be & TGB_BRICK_SOLID) != 0;
-            solid = voxel & (((row >> ((u32)vx & 31u)) & 1u) != 0);
-            e = voxel ? (((u32)vx & 31u) | (((u32)vy & 31u) << 5) | (((u32)vz & 31u) << 10)) : be;
+            solid = voxel & (((row >> pos) & 1u) != 0);
+            /* the run of free voxels around pos inside the brick's 8 (a solid voxel is its own cell) */
+            const u32 seg = (row >> (pos & 24u)) & 0xFFu, q = pos & 7u;
+            const u32 below = seg & ((1u << q) - 1u), above = seg >> (q + 1u);
+            const u32 lo = solid ? q : (below ? 32u - (u32)tgb_clz(below) : 0u);
+            const u32 hi = solid ? q : (above ? q + (u32)tgb_ffs(above) - 1u : 7u);
+            const u32 first = (pos & 24u) | lo, extra = hi - lo;
+            const u32 run = axis == 0u ? (first | (ly << 5) | (lz << 10) | (extra << 15))
+                          : (axis == 1u ? (lx | (first << 5) | (lz << 10) | (extra << 20)) : (lx | (ly << 5) | (first << 10) | (extra << 25)));
+            e = voxel ? run : be;
             shift = 0u; base_mask = ~31u;
         }
         if (p_n_cells) { if (leaf) (*p_n_voxels)++; else (*p_n_cells)++; }

@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(TGB_LIST_THREADS) k_gi_trace_list(const tgb_gi
             if (careful_delta > 0.0f)
             {
                 tgb_fast_ray r;
+                r.n_steps = 0;
                 u32 k = tgb_fast_start(&fr, origin, d, q1.w, careful_delta, &r, true);
                 if (k == TGB_FAST_WALK) k = tgb_fast_walk_tiled<true>(&fr, &tiling, &r, 0xFFFFFFFFu, (u32*)0, (u32*)0, 4096u, 4096u);
                 n_visits += r.n_steps;
@@ -363,9 +364,9 @@ extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, cons
     {
         /* the handed-over rays: k_gi_trace_list (TGB_GI_LIST_KERNEL=0: the pool kernel in list mode, the measured predecessor) */
         const u32 rays_per_grab = (u32)max(0, min(32, tgbd_env_int("TGB_GI_LIST_RAYS", 0)));
-        const bool careful = d->svo.fast_tiling_valid && tgbd_env_int("TGB_GI_LIST_CAREFUL", 1) != 0;
+        const bool careful = d->svo.fast_tiling_valid && tgbd_env_int("TGB_GI_LIST_CAREFUL", 0) != 0; /* measured: the careful walk belongs in a kernel of its own (tgb_gi_fast.cu), 1.6 lanes per instruction here */
         tgb_fast_tiling tiling;
-        tiling.p_cells = d->svo.d_fast_cells; tiling.p_bricks = d->svo.d_fast_bricks;
+        tgbd_gi_fast_tiling_get(d, &tiling);
         const u32 list_ctas = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_CTAS_PER_SM", 16)));
         k_gi_trace_list<<<d->n_sms * list_ctas, TGB_LIST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
                                                                                   rays_per_grab, (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 64)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 1024)),

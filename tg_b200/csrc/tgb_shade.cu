@@ -1009,7 +1009,7 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         {
             if (!d->svo.fast_tiling_valid && !tgbd_gi_fast_tiling_build(d, d->stream)) return TG_FALSE;
             tgb_gi_frame_init(&a.fast_frame, d->svo.bmin, d->svo.bmax, p_cam->far_plane, d->svo.d_top_grid, d->svo.d_voxels);
-            a.fast_tiling.p_cells = d->svo.d_fast_cells; a.fast_tiling.p_bricks = d->svo.d_fast_bricks;
+            tgbd_gi_fast_tiling_get(d, &a.fast_tiling);
         }
     }
 
