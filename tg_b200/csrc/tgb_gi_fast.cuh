@@ -324,7 +324,7 @@ TGB_HD bool tgb_fast_cube_free(const tgb_gi_frame* f, const tgb_fast_tiling* tl,
     const f32 px = fmaf(t, r->d.x, r->ob.x), py = fmaf(t, r->d.y, r->ob.y), pz = fmaf(t, r->d.z, r->ob.z);
     const i32 x0 = (i32)floorf(px - hx), x1 = (i32)floorf(px + hx), y0 = (i32)floorf(py - hy), y1 = (i32)floorf(py + hy), z0 = (i32)floorf(pz - hz), z1 = (i32)floorf(pz + hz);
     bool free_ = true;
-    for (u32 i = 0; i < 8u; i++) free_ = free_ && tgb_fast_voxel_free(f, tl, (i & 1u) ? x1 : x0, (i & 2u) ? y1 : y0, (i & 4u) ? z1 : z0);
+    for (u32 i = 0; i < 8u; i++) free_ = free_ & tgb_fast_voxel_free(f, tl, (i & 1u) ? x1 : x0, (i & 2u) ? y1 : y0, (i & 4u) ? z1 : z0); /* no short cut: eight independent look-ups */
     return free_;
 }
 

@@ -242,106 +242,85 @@ static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, co
 }
 
 /*
- * The rays the certified fast walk hands over (tgb_gi_fast.cu) are few -- under one per cent of the queue -- and long: every one
- * leaves the box, a few hundred voxel steps and a dozen look-ups one after the other. With so little work the pool's phase machinery
- * (votes, state in shared memory, a ray waiting for the phase its neighbours need) only stretches those dependent chains: 0.20 ms for
- * 35 k rays (profiles/r04a_*), whatever their number. Here a warp takes LIST_RAYS rays at a time, one per lane, everything in
- * registers, and every lane simply runs its ray to the end with the same per-ray functions (tgb_gi_walk.cuh): the duration is the
- * longest ray's chain and the divergence of a handful of lanes costs nothing on an otherwise idle SM.
+ * The rays the certified fast walk hands over (tgb_gi_fast.cu) are few -- under a thousandth of the queue -- and long: every one
+ * leaves the box, a hundred voxel steps and a dozen look-ups on average, four times that at worst, one after the other. With so little
+ * work the pool's phase machinery (votes, state in shared memory, a ray waiting for the phase its neighbours need) only stretches those
+ * dependent chains, and so does every cache miss on the way: what this pass takes is the LONGEST ray's chain (0.16 - 0.20 ms whether
+ * 1 k or 35 k rays were handed over, profiles/r04a - r04f). So here ONE WARP runs ONE ray: all lanes execute the same per-ray
+ * functions (tgb_gi_walk.cuh) on the same ray -- no divergence, the issue cost of one lane -- and when the ray enters a leaf block the 32
+ * lanes copy the block's 4 KB to shared memory together (32 coalesced loads in flight at once instead of one dependent, mostly
+ * missing load per voxel row), so that the leaf DDA steps at shared-memory latency.
  */
-#define TGB_LIST_THREADS 64
-__global__ void __launch_bounds__(TGB_LIST_THREADS) k_gi_trace_list(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
-                                                                    const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, const u32* __restrict__ p_list, u32 count_word,
-                                                                    float4* __restrict__ p_out, u32 rays_per_grab, u32 tree_reps, u32 dda_steps, const tgb_fast_tiling tiling, f32 careful_delta)
+#define TGB_LIST_THREADS 32
+__global__ void __launch_bounds__(TGB_LIST_THREADS, 32) k_gi_trace_list(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
+                                                                        const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, const u32* __restrict__ p_list, u32 count_word,
+                                                                        float4* __restrict__ p_out, u32 tree_reps, u32 dda_steps)
 {
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
-    const u32 lane = threadIdx.x & 31u;
+    __shared__ u32 s_block[TG_SVO_BLOCK_WORDS];
+    const u32 lane = threadIdx.x;
     const u32 n_rays = p_q_count[count_word];
-    /* rays_per_grab == 0: every warp takes its share of the list at once -- one ray while there are fewer rays than warps */
-    if (rays_per_grab == 0u)
-    {
-        const u32 n_warps = gridDim.x * (TGB_LIST_THREADS / 32u);
-        rays_per_grab = (n_rays + n_warps - 1u) / n_warps;
-        rays_per_grab = rays_per_grab < 1u ? 1u : (rays_per_grab > 32u ? 32u : rays_per_grab);
-    }
-    u32 n_visits = 0, n_steps = 0, n_advances = 0, n_exact = 0;
+    u32 n_visits = 0, n_steps = 0, n_advances = 0, n_traced = 0;
     for (;;)
     {
-        u32 base = 0;
-        if (lane == 0) base = atomicAdd(&p_q_count[count_word + 1u], rays_per_grab);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n_rays) break;
-        const u32 mine = base + lane;
-        if (lane < rays_per_grab && mine < n_rays)
+        u32 mine = 0;
+        if (lane == 0) mine = atomicAdd(&p_q_count[count_word + 1u], 1u);
+        mine = __shfl_sync(0xFFFFFFFFu, mine, 0);
+        if (mine >= n_rays) break;
+        const u32 slot = __ldcs(&p_list[mine]) & 0x7FFFFFFFu;
+        const float4 q0 = __ldcg(&p_q0[slot]), q1 = __ldcs(&p_q1[slot]);
+        const v3 origin = tgb_v3(q0.x, q0.y, q0.z), d = tgb_v3(q1.x, q1.y, q1.z);
+        v3 position, t_delta, t_max = tgb_v3(0.0f, 0.0f, 0.0f);
+        u32 flags, cell = 0, data = 0, kind = TGB_RAY_TREE;
+        i32 x = 0, y = 0, z = 0;
+        tgb_gi_ray_start(&fr, origin, d, q1.w, &position, &t_delta, &flags);
+        bool occluded = false;
+        n_traced++;
+        for (;;) /* warp-uniform: every lane holds the same state */
         {
-            const u32 slot = __ldcs(&p_list[mine]);
-            const float4 q0 = __ldcg(&p_q0[slot]), q1 = __ldcs(&p_q1[slot]);
-            const v3 origin = tgb_v3(q0.x, q0.y, q0.z), d = tgb_v3(q1.x, q1.y, q1.z);
-            bool occluded = false, decided = false;
-            /* second chance for the certificate (careful_delta > 0: the tiling exists): the walk of tgb_gi_fast.cuh once more, this time
-             * looking around every edge it passes (cube check) and with step caps only a runaway would meet; nine handed-over rays of ten
-             * are decided here */
-            if (careful_delta > 0.0f)
+            if (kind == TGB_RAY_TREE) kind = tgb_gi_tree_phase(&fr, d, t_delta, &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
+            else if (kind == TGB_RAY_DDA)
             {
-                tgb_fast_ray r;
-                r.n_steps = 0;
-                u32 k = tgb_fast_start(&fr, origin, d, q1.w, careful_delta, &r, true);
-                if (k == TGB_FAST_WALK) k = tgb_fast_walk_tiled<true>(&fr, &tiling, &r, 0xFFFFFFFFu, (u32*)0, (u32*)0, 4096u, 4096u);
-                n_visits += r.n_steps;
-                if (k == TGB_FAST_OCCLUDED) { decided = true; occluded = true; }
-                else if (k == TGB_FAST_UNOCCLUDED && !(r.flags & TGB_FAST_UNCERTAIN)) decided = true;
-            }
-            v3 position, t_delta, t_max = tgb_v3(0.0f, 0.0f, 0.0f);
-            u32 flags, cell = 0, data = 0, kind = TGB_RAY_TREE;
-            i32 x = 0, y = 0, z = 0;
-            tgb_gi_ray_start(&fr, origin, d, q1.w, &position, &t_delta, &flags);
-            if (!decided) n_exact++;
-            while (!decided)
-            {
-                if (kind == TGB_RAY_TREE) kind = tgb_gi_tree_phase(&fr, d, t_delta, &position, &cell, &flags, &data, tree_reps, &n_visits, &n_advances);
-                else if (kind == TGB_RAY_DDA)
+                if (flags & TGB_RF_SETUP)
                 {
-                    if (flags & TGB_RF_SETUP)
-                    {
-                        flags &= ~TGB_RF_SETUP;
-                        v3 child_min; f32 child_size;
-                        tgb_cell_box(&fr, cell, &child_min, &child_size);
-                        tgb_gi_dda_setup(d, position, child_min, child_size, &x, &y, &z, &t_max);
-                    }
-                    kind = tgb_gi_dda_phase(fr.p_voxels + (u64)data * TG_SVO_BLOCK_WORDS, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
-                    if (kind == TGB_RAY_DDA || kind == TGB_RAY_HIT) { x &= 31; y &= 31; z &= 31; } /* what the pool keeps between phases */
-                }
-                else if (kind == TGB_RAY_HIT)
-                {
+                    flags &= ~TGB_RF_SETUP;
                     v3 child_min; f32 child_size;
                     tgb_cell_box(&fr, cell, &child_min, &child_size);
-                    kind = tgb_gi_hit_test(&fr, origin, d, child_min, x, y, z);
-                    if (kind == TGB_RAY_IDLE) { occluded = true; break; }
+                    tgb_gi_dda_setup(d, position, child_min, child_size, &x, &y, &z, &t_max);
+                    const u32* __restrict__ p_block = fr.p_voxels + (u64)data * TG_SVO_BLOCK_WORDS;
+                    __syncwarp();
+#pragma unroll
+                    for (u32 i = 0; i < 32u; i++) s_block[32u * i + lane] = __ldg(&p_block[32u * i + lane]);
+                    __syncwarp();
                 }
-                else /* MISS */
-                {
-                    if (flags & TGB_RF_BORDER) kind = tgb_gi_border_test(&fr, d, position, &flags);
-                    if (kind == TGB_RAY_MISS) break;
-                }
+                kind = tgb_gi_dda_phase_t<true>(s_block, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
+                if (kind == TGB_RAY_DDA || kind == TGB_RAY_HIT) { x &= 31; y &= 31; z &= 31; } /* what the pool keeps between phases */
             }
-            if (!occluded)
+            else if (kind == TGB_RAY_HIT)
             {
-                const float4 q2 = __ldcs(&p_q2[slot]);
-                f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
-                atomicAdd(p_pixel + 0, q2.x);
-                atomicAdd(p_pixel + 1, q2.y);
-                atomicAdd(p_pixel + 2, q2.z);
+                v3 child_min; f32 child_size;
+                tgb_cell_box(&fr, cell, &child_min, &child_size);
+                kind = tgb_gi_hit_test(&fr, origin, d, child_min, x, y, z);
+                if (kind == TGB_RAY_IDLE) { occluded = true; break; }
+            }
+            else /* MISS */
+            {
+                if (flags & TGB_RF_BORDER) kind = tgb_gi_border_test(&fr, d, position, &flags);
+                if (kind == TGB_RAY_MISS) break;
             }
         }
-        __syncwarp();
+        if (!occluded && lane == 0)
+        {
+            const float4 q2 = __ldcs(&p_q2[slot]);
+            f32* p_pixel = reinterpret_cast<f32*>(&p_out[__float_as_uint(q0.w)]);
+            atomicAdd(p_pixel + 0, q2.x);
+            atomicAdd(p_pixel + 1, q2.y);
+            atomicAdd(p_pixel + 2, q2.z);
+        }
     }
-    n_visits = __reduce_add_sync(0xFFFFFFFFu, n_visits);
-    n_steps = __reduce_add_sync(0xFFFFFFFFu, n_steps);
-    n_advances = __reduce_add_sync(0xFFFFFFFFu, n_advances);
-    n_exact = __reduce_add_sync(0xFFFFFFFFu, n_exact);
-    if (lane == 0 && n_exact) atomicAdd(&p_q_count[14], n_exact); /* rays that needed the shader's own arithmetic */
-    if (lane == 0 && (n_visits | n_steps | n_advances))
+    if (lane == 0 && n_traced)
     {
+        atomicAdd(&p_q_count[14], n_traced); /* rays that needed the shader's own arithmetic */
         atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 1, (unsigned long long)n_visits);
         atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 2, (unsigned long long)n_steps);
         atomicAdd(reinterpret_cast<unsigned long long*>(p_q_count) + 3, (unsigned long long)n_advances);
@@ -363,14 +342,9 @@ extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, cons
     if (p_list && tgbd_env_int("TGB_GI_LIST_KERNEL", 1))
     {
         /* the handed-over rays: k_gi_trace_list (TGB_GI_LIST_KERNEL=0: the pool kernel in list mode, the measured predecessor) */
-        const u32 rays_per_grab = (u32)max(0, min(32, tgbd_env_int("TGB_GI_LIST_RAYS", 0)));
-        const bool careful = d->svo.fast_tiling_valid && tgbd_env_int("TGB_GI_LIST_CAREFUL", 0) != 0; /* measured: the careful walk belongs in a kernel of its own (tgb_gi_fast.cu), 1.6 lanes per instruction here */
-        tgb_fast_tiling tiling;
-        tgbd_gi_fast_tiling_get(d, &tiling);
-        const u32 list_ctas = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_CTAS_PER_SM", 16)));
+        const u32 list_ctas = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_CTAS_PER_SM", 32)));
         k_gi_trace_list<<<d->n_sms * list_ctas, TGB_LIST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
-                                                                                  rays_per_grab, (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 64)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 1024)),
-                                                                                  tiling, careful ? tgbd_gi_fast_delta() : 0.0f);
+                                                                                  (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 64)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 1024)));
         TGB_LAUNCH_CHECK(d);
         return TG_TRUE;
     }

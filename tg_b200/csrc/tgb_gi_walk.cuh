@@ -309,13 +309,15 @@ TGB_HD void tgb_gi_dda_setup(v3 d, v3 position, v3 child_min, f32 child_size, i3
  * Returns DDA (budget used up), HIT (solid voxel at x, y, z: the shader's slab test decides, tgb_gi_hit_test) or TREE
  * (left the block; the ADVANCE flag is still set from the look-up, so the next tree phase moves past the leaf).
  */
-TGB_HD u32 tgb_gi_dda_phase(const u32* p_block, v3 t_delta, u32 step_codes, v3* p_t_max, i32* p_x, i32* p_y, i32* p_z, u32 steps, u32* p_n_steps)
+/* STAGED: the block was copied to shared memory (k_gi_trace_list): plain loads */
+template <bool STAGED>
+TGB_HD u32 tgb_gi_dda_phase_t(const u32* p_block, v3 t_delta, u32 step_codes, v3* p_t_max, i32* p_x, i32* p_y, i32* p_z, u32 steps, u32* p_n_steps)
 {
     const i32 step_x = tgb_step_decode(step_codes & 3u), step_y = tgb_step_decode((step_codes >> 2) & 3u), step_z = tgb_step_decode((step_codes >> 4) & 3u);
     f32 t_max_x = p_t_max->x, t_max_y = p_t_max->y, t_max_z = p_t_max->z;
     i32 x = *p_x, y = *p_y, z = *p_z;
     u32 kind = TGB_RAY_DDA;
-    u32 bits = TGB_LDG(&p_block[32 * z + y]);
+    u32 bits = STAGED ? p_block[32 * z + y] : TGB_LDG(&p_block[32 * z + y]);
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
@@ -334,11 +336,16 @@ TGB_HD u32 tgb_gi_dda_phase(const u32* p_block, v3 t_delta, u32 step_codes, v3* 
         y += go_y ? step_y : 0;
         z += go_z ? step_z : 0;
         if ((u32)(x | y | z) > 31u) { kind = TGB_RAY_TREE; break; } /* left the block: a coordinate is -1 or 32 */
-        if (!go_x) bits = TGB_LDG(&p_block[32 * z + y]);
+        if (!go_x) bits = STAGED ? p_block[32 * z + y] : TGB_LDG(&p_block[32 * z + y]);
     }
     p_t_max->x = t_max_x; p_t_max->y = t_max_y; p_t_max->z = t_max_z;
     *p_x = x; *p_y = y; *p_z = z;
     return kind;
+}
+
+TGB_HD u32 tgb_gi_dda_phase(const u32* p_block, v3 t_delta, u32 step_codes, v3* p_t_max, i32* p_x, i32* p_y, i32* p_z, u32 steps, u32* p_n_steps)
+{
+    return tgb_gi_dda_phase_t<false>(p_block, t_delta, step_codes, p_t_max, p_x, p_y, p_z, steps, p_n_steps);
 }
 
 /*
