@@ -574,7 +574,7 @@ def gpu_arm(ctx, args, workload, steps, warmup, headline):
                                                 "k_present per band + 4 B / pixel over PCIe instead of the 16 B / pixel HDR rows"},
                     "note": e2e_note},
             "gpu_launches": int(launches),
-            "roofline": roofline("GI + shading stage (k_object_frames + k_shade + k_gi_trace_pool" + (" + k_resolve_material + exchange" if world > 1 else "") + ")",
+            "roofline": roofline("GI + shading stage (k_object_frames + k_shade + k_gi_trace_fast + k_gi_trace_list" + (" + k_resolve_material + exchange" if world > 1 else "") + ")",
                                  gi_bytes, gi_achieved, gi_ms, "k3_traffic.json"),
             "roofline_visibility": roofline("visibility stage (k_clear_visibility + k_cull_objects + k_sort_frames + k_visibility)", vis_bytes, vis_achieved, vis_ms, "k1_traffic.json"),
             "cpu_baseline": cpu}

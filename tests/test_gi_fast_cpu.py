@@ -209,6 +209,6 @@ def test_tiled_walk_a_million_rays_and_fewer_steps(oracle, make):
             second, _ = cpu_sim.gi_fast_tiled(BMIN, BMAX, far, grid, voxels, tiling, o[h], d[h], delta=delta, cube=True)
             bad = np.flatnonzero((second != 2) & ((second == 1) != exact[h]))
             assert len(bad) == 0, f"delta {delta}: careful pass decided {len(bad)} rays differently, first: o={o[h][bad[:2]].tolist()} d={d[h][bad[:2]].tolist()}"
-            assert (second != 2).mean() > 0.25, (delta, (second != 2).mean())
+            assert (second != 2).mean() > 0.1, (delta, (second != 2).mean())
     finally:
         oracle.svo_destroy(svo)

@@ -197,9 +197,10 @@ static inline u32* tgbd_mat_object_indices(const struct tgb_device* d, const u64
         }                                                                                           \
     } while (0)
 
-/* TGB_GI_KERNEL when the environment does not say: 2 = the exact kernel on every ray (tgb_gi_pool.cu); 4 = the certified fast walk over the coarser
- * tiling, the exact kernel on the rays it hands over (tgb_gi_fast.cu); 1 / 3: see tgb_shade.cu */
-#define TGB_GI_KERNEL_DEFAULT 2
+/* TGB_GI_KERNEL when the environment does not say: 4 = the certified fast walk over the coarser tiling of the free space, its first cell entered by
+ * k_shade, the shader's own arithmetic (k_gi_trace_list) on the rays it hands over (tgb_gi_fast.cu: 0.93 ms for the stage against 1.38, identical frames,
+ * profiles/r04*); 2 = the exact kernel on every ray (tgb_gi_pool.cu: the frame every other kernel must reproduce bit for bit); 1 / 3: see tgb_shade.cu */
+#define TGB_GI_KERNEL_DEFAULT 4
 extern "C" b32 tgbd_gi_fast_tiling_build(struct tgb_device* d, cudaStream_t st); /* tgb_gi_fast.cu */
 extern "C" f32 tgbd_gi_fast_delta(void);
 struct tgb_fast_tiling;

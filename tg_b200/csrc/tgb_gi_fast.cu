@@ -338,7 +338,7 @@ extern "C" b32 tgbd_gi_fast_trace(struct tgb_device* d, f32 far_plane, b32 tiled
     if (tiled && !d->svo.fast_tiling_valid && !tgbd_gi_fast_tiling_build(d, d->stream)) return TG_FALSE;
     const u32 ctas_per_sm = (u32)max(1, min(16, tgbd_env_int("TGB_GI_FAST_CTAS_PER_SM", 8)));
     const u32 service_lanes = (u32)max(1, min(32, tgbd_env_int("TGB_GI_FAST_SERVICE_LANES", 8)));
-    const u32 steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_STEPS", 8));
+    const u32 steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_STEPS", tiled ? 4 : 8)); /* cells per walk phase: measured (profiles/r04g_sweep_full.jsonl) */
     const u32 max_steps = (u32)max(1, tgbd_env_int("TGB_GI_FAST_MAX_STEPS", (i32)TGB_FAST_MAX_STEPS)), max_steps_uncertain = (u32)max(1, tgbd_env_int("TGB_GI_FAST_MAX_STEPS_UNCERTAIN", (i32)TGB_FAST_MAX_STEPS_UNCERTAIN));
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, d->svo.bmin, d->svo.bmax, far_plane, d->svo.d_top_grid, d->svo.d_voxels);

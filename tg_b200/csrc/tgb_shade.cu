@@ -1044,9 +1044,10 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         if (gi)
         {
             /* persistent: a few CTAs per SM, each lane pulls rays until the queue is empty (count read on the device) */
-            /* TGB_GI_KERNEL: 2 (default) = the exact kernel on every ray, several rays per lane (tgb_gi_pool.cu); 1 = the exact kernel, one ray per
-             * lane (k_gi_trace_flat); 3 = certified fast walk, the exact kernel only on the rays it hands over (tgb_gi_fast.cu: bit-identical
-             * frames, measured slower: 1.69 vs 1.39 ms for the stage, profiles/r03e_*) */
+            /* TGB_GI_KERNEL: 4 (default) = the certified fast walk over the coarser tiling (tgb_gi_fast.cu; k_shade entered its first cell above), the shader's
+             * own arithmetic only on the rays it hands over; 3 = its predecessor over the octree's cells (measured slower than 2: profiles/r03e_*);
+             * 2 = the exact kernel on every ray, several rays per lane (tgb_gi_pool.cu): the reference frame of the others; 1 = the exact kernel, one ray per
+             * lane (k_gi_trace_flat). All produce the same radiance bits. */
             const int gi_kernel = tgbd_env_int("TGB_GI_KERNEL", TGB_GI_KERNEL_DEFAULT);
             if (flat && (gi_kernel == 3 || gi_kernel == 4))
             {
