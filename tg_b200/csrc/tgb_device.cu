@@ -410,6 +410,7 @@ extern "C" void tgbd_get_timings(struct tgb_device* d, tgb200_timings* p_out)
     if (d->ev_vis) { cudaMemcpy(d->h_visible_count, d->d_visible_count, 2 * sizeof(u32), cudaMemcpyDeviceToHost); d->n_visible_objects = d->h_visible_count[0]; }
     if (d->gi_stats_valid) cudaMemcpy(d->h_gi_stats, d->d_gi_count, 32 * sizeof(u32), cudaMemcpyDeviceToHost);
     p_out->n_visible_objects = d->n_visible_objects;
+    if (d->gi_stats_valid && d->h_gi_stats[20]) tgb_set_error("k_gi_trace_list: a bulk copy of a leaf block never completed (mbarrier wait gave up); the frame's GI term is incomplete");
     p_out->n_gi_rays = d->h_gi_stats[10];
     p_out->n_gi_rays_exact = d->h_gi_stats[14];
     p_out->n_gi_node_visits = ((const u64*)d->h_gi_stats)[1];

@@ -241,6 +241,34 @@ static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, co
     return TG_TRUE;
 }
 
+/* ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of one leaf block into shared memory, completion on an mbarrier ---------------------------- */
+__device__ __forceinline__ void tgb_mbar_init(u64* p_bar, u32 n_arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((u32)__cvta_generic_to_shared(p_bar)), "r"(n_arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+/* one thread: expect `bytes`, then start the copy (16-byte aligned on both sides, a multiple of 16 bytes) */
+__device__ __forceinline__ void tgb_bulk_copy_g2s(void* p_shared, const void* p_global, u32 bytes, u64* p_bar)
+{
+    const u32 bar = (u32)__cvta_generic_to_shared(p_bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the block's previous contents were read through the generic proxy */
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((u32)__cvta_generic_to_shared(p_shared)), "l"(p_global), "r"(bytes), "r"(bar) : "memory");
+}
+/* every consumer: wait for the phase with this parity; bounded (a copy that never lands reports false instead of hanging the GPU) */
+__device__ __forceinline__ bool tgb_mbar_wait(u64* p_bar, u32 parity)
+{
+    const u32 bar = (u32)__cvta_generic_to_shared(p_bar);
+    for (u32 spin = 0; spin < (1u << 22); spin++)
+    {
+        u32 done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
 /*
  * The rays the certified fast walk hands over (tgb_gi_fast.cu) are few -- under a thousandth of the queue -- and long: every one
  * leaves the box, a hundred voxel steps and a dozen look-ups on average, four times that at worst, one after the other. With so little
@@ -248,19 +276,29 @@ static b32 tgbd__gi_pool_launch(struct tgb_device* d, const tgb_gi_frame& fr, co
  * dependent chains, and so does every cache miss on the way: what this pass takes is the LONGEST ray's chain (0.16 - 0.20 ms whether
  * 1 k or 35 k rays were handed over, profiles/r04a - r04f). So here ONE WARP runs ONE ray: all lanes execute the same per-ray
  * functions (tgb_gi_walk.cuh) on the same ray -- no divergence, the issue cost of one lane -- and when the ray enters a leaf block the 32
- * lanes copy the block's 4 KB to shared memory together (32 coalesced loads in flight at once instead of one dependent, mostly
- * missing load per voxel row), so that the leaf DDA steps at shared-memory latency.
+ * lanes have the block's 4 KB in shared memory before the leaf DDA takes its first step, which then runs at shared-memory latency
+ * instead of one dependent, mostly missing load per voxel row. The block is one contiguous, aligned 4 KB: ONE TMA bulk copy
+ * (cp.async.bulk, completion counted on an mbarrier) issued by one lane moves it (TMA = true, default); the predecessor -- 32 coalesced loads and
+ * stores per lane -- stays selectable (TGB_GI_LIST_TMA=0).
  */
 #define TGB_LIST_THREADS 32
+template <bool TMA>
 __global__ void __launch_bounds__(TGB_LIST_THREADS, 32) k_gi_trace_list(const tgb_gi_frame fr, const float4* __restrict__ p_q0, const float4* __restrict__ p_q1,
                                                                         const float4* __restrict__ p_q2, u32* __restrict__ p_q_count, const u32* __restrict__ p_list, u32 count_word,
                                                                         float4* __restrict__ p_out, u32 tree_reps, u32 dda_steps)
 {
     if (fr.p_grid[TGB_TOP_GRID_CELLS] == 0) return; /* not tabulated: k_gi_trace runs */
-    __shared__ u32 s_block[TG_SVO_BLOCK_WORDS];
+    __shared__ __align__(128) u32 s_block[TG_SVO_BLOCK_WORDS];
+    __shared__ __align__(8) u64 s_bar;
     const u32 lane = threadIdx.x;
     const u32 n_rays = p_q_count[count_word];
     u32 n_visits = 0, n_steps = 0, n_advances = 0, n_traced = 0;
+    u32 parity = 0;
+    if (TMA)
+    {
+        if (lane == 0) tgb_mbar_init(&s_bar, 1u);
+        __syncwarp();
+    }
     for (;;)
     {
         u32 mine = 0;
@@ -288,10 +326,19 @@ __global__ void __launch_bounds__(TGB_LIST_THREADS, 32) k_gi_trace_list(const tg
                     tgb_cell_box(&fr, cell, &child_min, &child_size);
                     tgb_gi_dda_setup(d, position, child_min, child_size, &x, &y, &z, &t_max);
                     const u32* __restrict__ p_block = fr.p_voxels + (u64)data * TG_SVO_BLOCK_WORDS;
-                    __syncwarp();
+                    __syncwarp(); /* every lane is done with the previous block */
+                    if (TMA)
+                    {
+                        if (lane == 0) tgb_bulk_copy_g2s(s_block, p_block, TG_SVO_BLOCK_WORDS * (u32)sizeof(u32), &s_bar);
+                        if (!tgb_mbar_wait(&s_bar, parity)) { if (lane == 0) atomicExch(&p_q_count[20], 1u); return; } /* [20]: the copy never landed (reported by the host) */
+                        parity ^= 1u;
+                    }
+                    else
+                    {
 #pragma unroll
-                    for (u32 i = 0; i < 32u; i++) s_block[32u * i + lane] = __ldg(&p_block[32u * i + lane]);
-                    __syncwarp();
+                        for (u32 i = 0; i < 32u; i++) s_block[32u * i + lane] = __ldg(&p_block[32u * i + lane]);
+                        __syncwarp();
+                    }
                 }
                 kind = tgb_gi_dda_phase_t<true>(s_block, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
                 if (kind == TGB_RAY_DDA || kind == TGB_RAY_HIT) { x &= 31; y &= 31; z &= 31; } /* what the pool keeps between phases */
@@ -343,8 +390,11 @@ extern "C" b32 tgbd_gi_pool_trace_list(struct tgb_device* d, f32 far_plane, cons
     {
         /* the handed-over rays: k_gi_trace_list (TGB_GI_LIST_KERNEL=0: the pool kernel in list mode, the measured predecessor) */
         const u32 list_ctas = (u32)max(1, min(32, tgbd_env_int("TGB_GI_LIST_CTAS_PER_SM", 32)));
-        k_gi_trace_list<<<d->n_sms * list_ctas, TGB_LIST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance,
-                                                                                  (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 64)), (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 1024)));
+        const u32 tree_reps = (u32)max(1, tgbd_env_int("TGB_GI_LIST_TREE_REPS", 64)), dda_steps = (u32)max(1, tgbd_env_int("TGB_GI_LIST_DDA_STEPS", 1024));
+        if (tgbd_env_int("TGB_GI_LIST_TMA", 1))
+            k_gi_trace_list<true><<<d->n_sms * list_ctas, TGB_LIST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance, tree_reps, dda_steps);
+        else
+            k_gi_trace_list<false><<<d->n_sms * list_ctas, TGB_LIST_THREADS, 0, d->stream>>>(fr, d->d_gi_q0, d->d_gi_q1, d->d_gi_q2, d->d_gi_count, p_list, count_word, d->d_radiance, tree_reps, dda_steps);
         TGB_LAUNCH_CHECK(d);
         return TG_TRUE;
     }

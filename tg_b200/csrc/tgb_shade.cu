@@ -281,8 +281,8 @@ __device__ __forceinline__ bool tgb_shade_pixel(const tgb_shade_args& a, u32 px,
  * The pixel gets `ambient + lo` here exactly as the trace kernels would add it (one float addition per channel, commutative). Rays
  * the first steps leave undecided, or decide without certainty, are queued as before and start again from their record.
  */
-template <bool RESOLVED, bool FAST>
-__global__ void __launch_bounds__(256) k_shade(const tgb_shade_args a)
+template <bool RESOLVED, bool FAST, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) k_shade(const tgb_shade_args a)
 {
     /* 8x4 pixel blocks per warp like K1: neighbouring pixels share clusters, objects and material bytes */
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1001,6 +1001,7 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     }
     const int gi_ctas = max(1, min(16, tgbd_env_int("TGB_GI_CTAS_PER_SM", TGB_GI_FLAT_CTAS_PER_SM))); /* persistent CTAs per SM (tuning only) */
     /* TGB_GI_KERNEL=4: the first TGB_GI_SHADE_STEPS cells of the certified walk are entered by k_shade itself (0: every ray is queued) */
+    const int shade_min_ctas = tgbd_env_int("TGB_SHADE_MIN_CTAS", 4);
     a.fast_steps = 0; a.fast_delta = tgbd_gi_fast_delta();
     if (gi && flat && tgbd_env_int("TGB_GI_KERNEL", TGB_GI_KERNEL_DEFAULT) == 4)
     {
@@ -1038,8 +1039,10 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
         a.y0 = by0; a.y1 = by1;
         if (gi && b > 0) { k_set_words<<<1, 32, 0, d->stream>>>(d->d_gi_count, 2, 0u); TGB_LAUNCH_CHECK(d); } /* queued / fetched; the work counters accumulate over the bands */
         const dim3 grid((d->width + 15) / 16, (by1 - by0 + 15) / 16);
-        if (a.fast_steps) { if (resolved) k_shade<true, true><<<grid, 256, 0, d->stream>>>(a); else k_shade<false, true><<<grid, 256, 0, d->stream>>>(a); }
-        else              { if (resolved) k_shade<true, false><<<grid, 256, 0, d->stream>>>(a); else k_shade<false, false><<<grid, 256, 0, d->stream>>>(a); }
+        /* FAST: 4 CTAs per SM (64 registers) or 5 (48 registers, a few spilled words): TGB_SHADE_MIN_CTAS, measured */
+        if (a.fast_steps && shade_min_ctas >= 5) { if (resolved) k_shade<true, true, 5><<<grid, 256, 0, d->stream>>>(a); else k_shade<false, true, 5><<<grid, 256, 0, d->stream>>>(a); }
+        else if (a.fast_steps)                    { if (resolved) k_shade<true, true, 4><<<grid, 256, 0, d->stream>>>(a); else k_shade<false, true, 4><<<grid, 256, 0, d->stream>>>(a); }
+        else                                      { if (resolved) k_shade<true, false, 1><<<grid, 256, 0, d->stream>>>(a); else k_shade<false, false, 1><<<grid, 256, 0, d->stream>>>(a); }
         TGB_LAUNCH_CHECK(d);
         if (gi)
         {
