@@ -74,7 +74,8 @@ def test_full_frame_through_render(gpu, oracle):
         rt.destroy()
 
 
-@pytest.mark.parametrize("kernel", ["3", "4"])
+@pytest.mark.parametrize("kernel", ["3", "4", "4:TGB_GI_SHADE_STEPS=0", "4:TGB_GI_LIST_TMA=0", "4:TGB_GI_LIST_KERNEL=0", "4:TGB_GI_FAST_CAREFUL=1", "4:TGB_SHADE_MIN_CTAS=4",
+                                    "4:TGB_GI_FAST_DELTA_PERCENT=25"])
 @pytest.mark.parametrize("make,seed", [(lambda: scenes.small_grid(), 3), (lambda: scenes.config1(k=3, width=320, height=180), 1),
                                        (lambda: scenes.grid_scene("g5", 5, 5, 480, 270, k=3), 7)])
 def test_certified_fast_walk_gives_the_exact_kernels_frame(gpu, oracle, make, seed, kernel):
@@ -94,13 +95,16 @@ def test_certified_fast_walk_gives_the_exact_kernels_frame(gpu, oracle, make, se
             os.environ.pop("TGB_GI_KERNEL", None)
         exact = rt.read_radiance()
         t_exact = rt.timings()
-        os.environ["TGB_GI_KERNEL"] = kernel
+        knobs = {"TGB_GI_KERNEL": kernel.split(":")[0]}
+        knobs.update(kv.split("=") for kv in kernel.split(":")[1:])   # the measured variants of kernel 4: every one must give the same frame
+        os.environ.update(knobs)
         try:
             rt.render_shading(); rt.synchronize()
             fast = rt.read_radiance()
             t_fast = rt.timings()
         finally:
-            os.environ.pop("TGB_GI_KERNEL", None)
+            for k in knobs:
+                os.environ.pop(k, None)
         assert np.array_equal(exact.view(np.uint32), fast.view(np.uint32)), f"{int((exact != fast).any(axis=-1).sum())} pixels differ"
         close(fast, want, "fast walk")
         assert t_fast["n_gi_rays"] == t_exact["n_gi_rays"] > 0 and t_fast["n_gi_rays_exact"] < t_fast["n_gi_rays"]

@@ -1001,7 +1001,7 @@ static b32 tgbd__shade_launch(struct tgb_device* d, const tg_camera_rays* p_cam,
     }
     const int gi_ctas = max(1, min(16, tgbd_env_int("TGB_GI_CTAS_PER_SM", TGB_GI_FLAT_CTAS_PER_SM))); /* persistent CTAs per SM (tuning only) */
     /* TGB_GI_KERNEL=4: the first TGB_GI_SHADE_STEPS cells of the certified walk are entered by k_shade itself (0: every ray is queued) */
-    const int shade_min_ctas = tgbd_env_int("TGB_SHADE_MIN_CTAS", 4);
+    const int shade_min_ctas = tgbd_env_int("TGB_SHADE_MIN_CTAS", 5); /* measured: 0.904 ms for the stage with 5, 0.923 with 4 (profiles/r04k_sweep_full.jsonl) */
     a.fast_steps = 0; a.fast_delta = tgbd_gi_fast_delta();
     if (gi && flat && tgbd_env_int("TGB_GI_KERNEL", TGB_GI_KERNEL_DEFAULT) == 4)
     {

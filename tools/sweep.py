@@ -37,21 +37,22 @@ GI_SWEEP = [
 ]
 FAST_SWEEP = [
     {"TGB_GI_KERNEL": 2},                                   # the exact kernel on every ray (the frame every other line must equal)
-    {"TGB_GI_KERNEL": 3},                                   # certified fast walk + exact kernel on the hand-overs, defaults
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 4},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 6},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 12},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_SERVICE_LANES": 16},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 4},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 6},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_CTAS_PER_SM": 10},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_STEPS": 1},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_STEPS": 2},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_STEPS": 8},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_FAST_STEPS": 16},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_RAYS_PER_LANE": 1, "TGB_GI_POOL_CTAS_PER_SM": 16},   # the exact kernel's shape for the few handed-over rays
-    {"TGB_GI_KERNEL": 3, "TGB_GI_RAYS_PER_LANE": 1, "TGB_GI_POOL_CTAS_PER_SM": 8},
-    {"TGB_GI_KERNEL": 3, "TGB_GI_RAYS_PER_LANE": 2, "TGB_GI_POOL_CTAS_PER_SM": 12},
+    {},                                                     # default: certified walk over the coarser tiling + exact list kernel (TGB_GI_KERNEL=4)
+    {"TGB_GI_KERNEL": 3},                                   # the certified walk's first form, over the octree's cells
+    {"TGB_GI_SHADE_STEPS": 0},                              # every ray queued (k_shade does not enter the first cell)
+    {"TGB_GI_SHADE_STEPS": 2},
+    {"TGB_SHADE_MIN_CTAS": 4},
+    {"TGB_GI_LIST_KERNEL": 0},                              # handed-over rays through the pool kernel's list mode
+    {"TGB_GI_LIST_TMA": 0},                                 # leaf blocks staged by 32 loads per lane instead of one bulk copy
+    {"TGB_GI_FAST_CAREFUL": 1},                             # careful second pass (cube check) in front of the exact list kernel
+    {"TGB_GI_FAST_STEPS": 2},
+    {"TGB_GI_FAST_STEPS": 8},
+    {"TGB_GI_FAST_SERVICE_LANES": 4},
+    {"TGB_GI_FAST_SERVICE_LANES": 16},
+    {"TGB_GI_FAST_CTAS_PER_SM": 6},
+    {"TGB_GI_FAST_MAX_STEPS": 64, "TGB_GI_FAST_MAX_STEPS_UNCERTAIN": 16},
+    {"TGB_GI_FAST_DELTA_PERCENT": 25},                      # a quarter of the certificate's margin: the frame must still be the exact kernel's
+    {"TGB_GI_FAST_DELTA_PERCENT": 10},
 ]
 K1_SWEEP = [
     {"TGB_K1_KERNEL": 1},                                   # round-1 kernel: one pixel per lane
