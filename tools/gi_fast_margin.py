@@ -3,7 +3,8 @@
 Runs the host builds of the fast walk and of the exact state machine (tests/cpu_sim; the latter is held against the oracle's
 transcription of svo_functions.inc by tests/test_gi_walk_cpu.py) on the same rays and reports, per DELTA: the share of rays handed to
 the exact kernel and the number of rays the fast walk DECIDED differently from the exact one. The product uses DELTA0 = 2e-4 (growing by 3e-5 per box entered); the sweep
-goes down until disagreements appear, which shows how far below that the real sideways displacement of the shader's walk stays.
+goes down until disagreements appear, which shows how far below that the real sideways displacement of the shader's walk stays
+(below ~3e-5 DELTA0 no longer covers the half ulp(1024) by which the walk's own origin is rounded: disagreements there are expected).
 
     python tools/gi_fast_margin.py [n_rays] [scene]      scene: g6 (6x6 objects, default) | small | c1
 """
@@ -57,12 +58,17 @@ def main():
     exact, capped, work = cpu_sim.gi_trace(bmin, bmax, far, grid, voxels, o, d)
     t1 = time.time()
     print(f"{which}: {n} rays, exact walk {t1 - t0:.1f} s: occluded {exact.mean():.3f}, per ray {work[0] / n:.1f} look-ups {work[1] / n:.1f} DDA steps; capped {capped}")
-    for delta in (1e-3, 2e-4, 1e-4, 3e-5, 1e-5, 3e-6, 1e-6, 0.0):
-        res, w = cpu_sim.gi_fast(bmin, bmax, far, grid, voxels, o, d, delta=delta)
-        decided = res != 2
-        bad = np.flatnonzero(decided & ((res == 1) != exact))
-        print(f"  delta {delta:8.1e}: handed over {1.0 - decided.mean():7.4f}  decided differently {len(bad):6d}  per ray {w[0] / n:.1f} boxes {w[1] / n:.1f} voxels"
-              + (f"   first: o={o[bad[0]].tolist()} d={d[bad[0]].tolist()}" if len(bad) else ""))
+    tiling = cpu_sim.fast_tiling(grid, voxels)
+    for name, walk in (("octree cells (TGB_GI_KERNEL=3)", lambda delta: cpu_sim.gi_fast(bmin, bmax, far, grid, voxels, o, d, delta=delta)),
+                       ("coarser tiling (TGB_GI_KERNEL=4, default)", lambda delta: cpu_sim.gi_fast_tiled(bmin, bmax, far, grid, voxels, tiling, o, d, delta=delta)),
+                       ("coarser tiling, careful (cube check)", lambda delta: cpu_sim.gi_fast_tiled(bmin, bmax, far, grid, voxels, tiling, o, d, delta=delta, cube=True))):
+        print(f" {name}")
+        for delta in (1e-3, 2e-4, 1e-4, 5e-5, 2e-5, 1e-5, 3e-6, 1e-6, 0.0):
+            res, w = walk(delta)
+            decided = res != 2
+            bad = np.flatnonzero(decided & ((res == 1) != exact))
+            print(f"  delta {delta:8.1e}: handed over {1.0 - decided.mean():7.4f}  decided differently {len(bad):6d}  per ray {w[0] / n:.2f} boxes {w[1] / n:.2f} cells of leaf blocks"
+                  + (f"   first: o={o[bad[0]].tolist()} d={d[bad[0]].tolist()}" if len(bad) else ""))
 
 
 if __name__ == "__main__":
