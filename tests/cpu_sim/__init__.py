@@ -45,14 +45,14 @@ def flatten(nodes, leaf_data):
     return grid
 
 
-def gi_trace(bmin, bmax, far_plane, grid, voxels, origins, dirs, tree_reps=4, dda_steps=16, grid16=False):
+def gi_trace(bmin, bmax, far_plane, grid, voxels, origins, dirs, tree_reps=4, dda_steps=16, grid16=False, uniform_dda=False):
     origins = np.ascontiguousarray(origins, dtype=np.float32)
     dirs = np.ascontiguousarray(dirs, dtype=np.float32)
     bmin = np.asarray(bmin, dtype=np.float32); bmax = np.asarray(bmax, dtype=np.float32)
     occluded = np.zeros(len(origins), dtype=np.uint8)
     work = np.zeros(3, dtype=np.uint64)
     capped = lib().tgbsim_gi_trace(_p(bmin, C.c_float), _p(bmax, C.c_float), far_plane, _p(grid, C.c_uint32), _p(voxels, C.c_uint32), len(origins),
-                                   _p(origins, C.c_float), _p(dirs, C.c_float), tree_reps, dda_steps, 1 if grid16 else 0, _p(occluded, C.c_uint8), _p(work, C.c_uint64))
+                                   _p(origins, C.c_float), _p(dirs, C.c_float), tree_reps, dda_steps, (1 if grid16 else 0) | (2 if uniform_dda else 0), _p(occluded, C.c_uint8), _p(work, C.c_uint64))
     return occluded.astype(bool), int(capped), work
 
 

@@ -60,6 +60,8 @@ u32 tgbsim_gi_trace(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u
     tgb_gi_frame fr;
     tgb_gi_frame_init(&fr, tgb_v3(p_bmin[0], p_bmin[1], p_bmin[2]), tgb_v3(p_bmax[0], p_bmax[1], p_bmax[2]), far_plane, p_grid, p_voxels);
     /* grid16: the kernel's 16-bit form of the table (tgb_top16_pack), read back through tgb_top16_unpack */
+    const bool uniform_dda = (grid16 & 2u) != 0; /* the list kernel's branch form of the leaf DDA (tgb_gi_dda_phase_uniform) */
+    grid16 &= 1u;
     unsigned short* p_grid16 = NULL;
     if (grid16)
     {
@@ -93,7 +95,8 @@ u32 tgbsim_gi_trace(const f32* p_bmin, const f32* p_bmax, f32 far_plane, const u
                     tgb_cell_box(&fr, cell, &child_min, &child_size);
                     tgb_gi_dda_setup(d, position, child_min, child_size, &x, &y, &z, &t_max);
                 }
-                kind = tgb_gi_dda_phase(p_voxels + (uint64_t)data * TG_SVO_BLOCK_WORDS, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
+                kind = uniform_dda ? tgb_gi_dda_phase_uniform(p_voxels + (uint64_t)data * TG_SVO_BLOCK_WORDS, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps)
+                                   : tgb_gi_dda_phase(p_voxels + (uint64_t)data * TG_SVO_BLOCK_WORDS, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
                 /* what the kernel stores between phases: 5 bits per coordinate */
                 if (kind == TGB_RAY_DDA || kind == TGB_RAY_HIT) { x &= 31; y &= 31; z &= 31; }
             }

@@ -48,6 +48,8 @@ def test_state_machine_decides_like_the_shader(oracle, make, spread, budgets):
         assert capped == 0
         got16, _, work16 = cpu_sim.gi_trace(bmin, bmax, far, grid, vox.view(np.uint32).ravel(), o, d, *budgets, grid16=True)
         assert np.array_equal(got16, got) and np.array_equal(work16, work), "the 16-bit form of the flattened tree must describe the same walk"
+        got_u, _, work_u = cpu_sim.gi_trace(bmin, bmax, far, grid, vox.view(np.uint32).ravel(), o, d, *budgets, uniform_dda=True)
+        assert np.array_equal(got_u, got) and np.array_equal(work_u, work), "the branch form of the leaf DDA (k_gi_trace_list) must take the same steps"
         L = oracle.lib()
         want = np.zeros(len(o), dtype=bool)
         hp, hn, ni, vi = T.v3(), T.v3(), T.u32(), T.u32()

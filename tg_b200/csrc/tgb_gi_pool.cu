@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(TGB_LIST_THREADS, 32) k_gi_trace_list(const tg
                         __syncwarp();
                     }
                 }
-                kind = tgb_gi_dda_phase_t<true>(s_block, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
+                kind = tgb_gi_dda_phase_uniform(s_block, t_delta, flags >> TGB_RF_STEP_SHIFT, &t_max, &x, &y, &z, dda_steps, &n_steps);
                 if (kind == TGB_RAY_DDA || kind == TGB_RAY_HIT) { x &= 31; y &= 31; z &= 31; } /* what the pool keeps between phases */
             }
             else if (kind == TGB_RAY_HIT)

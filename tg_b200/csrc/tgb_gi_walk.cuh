@@ -343,6 +343,44 @@ TGB_HD u32 tgb_gi_dda_phase_t(const u32* p_block, v3 t_delta, u32 step_codes, v3
     return kind;
 }
 
+/*
+ * The same DDA for a warp whose lanes all hold the SAME ray (k_gi_trace_list): branches are uniform there, so the step is written with
+ * them -- one comparison chain, one addition, one coordinate, one bound -- a third of the instructions of the select form on the
+ * dependent chain this kernel's duration consists of. Same comparisons, same additions: same t_max bits, same voxel sequence
+ * (tests/test_gi_walk_cpu.py drives both forms side by side). The block is in shared memory.
+ */
+TGB_HD u32 tgb_gi_dda_phase_uniform(const u32* p_block, v3 t_delta, u32 step_codes, v3* p_t_max, i32* p_x, i32* p_y, i32* p_z, u32 steps, u32* p_n_steps)
+{
+    const i32 step_x = tgb_step_decode(step_codes & 3u), step_y = tgb_step_decode((step_codes >> 2) & 3u), step_z = tgb_step_decode((step_codes >> 4) & 3u);
+    f32 t_max_x = p_t_max->x, t_max_y = p_t_max->y, t_max_z = p_t_max->z;
+    i32 x = *p_x, y = *p_y, z = *p_z;
+    u32 kind = TGB_RAY_DDA;
+    u32 bits = p_block[32 * z + y];
+    u32 k = 0;
+    for (; k < steps; k++)
+    {
+        if ((bits >> x) & 1u) { kind = TGB_RAY_HIT; k++; break; }
+        if (t_max_x < t_max_y)
+        {
+            if (t_max_x < t_max_z) { t_max_x += t_delta.x; x += step_x; if ((u32)x > 31u) { kind = TGB_RAY_TREE; k++; break; } continue; }
+        }
+        else if (t_max_y < t_max_z)
+        {
+            t_max_y += t_delta.y; y += step_y;
+            if ((u32)y > 31u) { kind = TGB_RAY_TREE; k++; break; }
+            bits = p_block[32 * z + y];
+            continue;
+        }
+        t_max_z += t_delta.z; z += step_z;
+        if ((u32)z > 31u) { kind = TGB_RAY_TREE; k++; break; }
+        bits = p_block[32 * z + y];
+    }
+    *p_n_steps += k;
+    p_t_max->x = t_max_x; p_t_max->y = t_max_y; p_t_max->z = t_max_z;
+    *p_x = x; *p_y = y; *p_z = z;
+    return kind;
+}
+
 TGB_HD u32 tgb_gi_dda_phase(const u32* p_block, v3 t_delta, u32 step_codes, v3* p_t_max, i32* p_x, i32* p_y, i32* p_z, u32 steps, u32* p_n_steps)
 {
     return tgb_gi_dda_phase_t<false>(p_block, t_delta, step_codes, p_t_max, p_x, p_y, p_z, steps, p_n_steps);
