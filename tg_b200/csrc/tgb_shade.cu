@@ -299,7 +299,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS) k_shade(const tgb_shade_args a)
     if (FAST)
     {
         bool decided = false;
-        if (trace)
+        /* a tree k_svo_flatten could not tabulate (an uploaded tree with leaves off depth 5) has no tiling either: every ray is queued and
+         * the stack machine k_gi_trace traces the queue */
+        if (trace && a.fast_frame.p_grid[TGB_TOP_GRID_CELLS] != 0u)
         {
             tgb_fast_ray r;
             u32 kind = tgb_fast_start(&a.fast_frame, origin, dir, root_enter, a.fast_delta, &r, true);
