@@ -32,7 +32,8 @@ struct tgb_svo_device
                            last word: non-zero = the grid describes the tree completely (leaves exactly at depth 5) */
     u32* d_fast_cells;  /* [3 * 32^3] the certified fast walk's coarser tiling of the free table cells (tgb_gi_fast.cuh) + two scratch passes; on first use */
     u32* d_fast_bricks; /* [leaf_capacity * 64] the same per 8^3 brick of every leaf block */
-    u32* d_fast_columns; /* [2 * voxel_word_capacity] the blocks' voxels with y, then with z, as the bit index */
+    u32* d_fast_columns; /* [2 * fast_columns_capacity_leaves * 1024] the blocks' voxels with y, then with z, as the bit index; grown on demand */
+    u32  fast_columns_capacity_leaves;
     b32  fast_tiling_valid; /* both describe the current tree */
     u32  n_nodes, n_leaves, n_pairs;
     b32  valid;
