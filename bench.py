@@ -548,6 +548,10 @@ def gpu_arm(ctx, args, workload, steps, warmup, headline):
                     "on a copy stream while the next frame renders (radiance double-buffered on the device, two host buffers alternate, frame i is awaited "
                     "after frame i+1 was submitted; every rank receives its own tile). All copies and the per-frame L2 flush are inside the timed region. "
                     "The scene arrays stay resident in HBM like the reference's SSBOs, the camera block is the per-frame input")
+        if world == 1:
+            gbs = WIDTH * HEIGHT * 16 / (t_e2e / steps) / 1e9
+            e2e_note += (f". PCIe-bound: the 133 MB HDR frame reaches host memory at {gbs:.0f} GB/s (the link's practical ceiling is ~55), which is what separates this "
+                         "figure from the device-timed frame; with the reference's own end of frame (presented_bgra8, 33 MB) the loop follows the device time")
         if world > 1:
             e2e_note += (f". Host-ingest bound at N = {world}: the {world} ranks together deliver the 133 MB HDR frame ({133 // world} MB each) into ONE host's memory "
                          "every frame; the gap between e2e and the device-timed frame is that PCIe / host-memory ingest (it shrinks 4x with the 4 B / pixel "
